@@ -1,0 +1,215 @@
+/*
+ * qgpu.h -- C ABI of libqgpu.so: B200-native physical operators for holicc/qurious.
+ *
+ * This is the drop-in boundary.  Every entry point is what a one-file Rust
+ * `impl PhysicalPlan for Gpu*` shim would bind through `extern "C"`.
+ * Data crosses as Arrow C Data Interface structs (arrow-rs: arrow::ffi::{FFI_ArrowSchema,
+ * FFI_ArrowArray}, feature "ffi"); expressions cross as a postfix byte stream because the
+ * reference's PhysicalExpr structs are opaque (`Arc<dyn PhysicalExpr>`, private fields,
+ * qurious/src/physical/expr/mod.rs:33-35) and must be re-serialised from the LogicalExpr tree
+ * by a sibling of DefaultQueryPlanner::create_physical_expr (qurious/src/planner/mod.rs:102-152).
+ *
+ * No torch / C++ types appear here.  All functions return 0 on success, else a qgpu_status;
+ * the message is available through qgpu_last_error().  The library never aborts the process
+ * and has NO CPU fallback: without a CUDA device qgpu_init fails with QGPU_ERR_CUDA.
+ *
+ * Threading: a qgpu_ctx may be used from one thread at a time (internal mutex); independent
+ * contexts may run concurrently.  Calls are synchronous: they return when the output is ready.
+ */
+#ifndef QGPU_H
+#define QGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- Arrow C Data Interface (https://arrow.apache.org/docs/format/CDataInterface.html) ---- */
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+#define ARROW_FLAG_DICTIONARY_ORDERED 1
+#define ARROW_FLAG_NULLABLE 2
+#define ARROW_FLAG_MAP_KEYS_SORTED 4
+struct ArrowSchema {
+  const char* format;
+  const char* name;
+  const char* metadata;
+  int64_t flags;
+  int64_t n_children;
+  struct ArrowSchema** children;
+  struct ArrowSchema* dictionary;
+  void (*release)(struct ArrowSchema*);
+  void* private_data;
+};
+struct ArrowArray {
+  int64_t length;
+  int64_t null_count;
+  int64_t offset;
+  int64_t n_buffers;
+  int64_t n_children;
+  const void** buffers;
+  struct ArrowArray** children;
+  struct ArrowArray* dictionary;
+  void (*release)(struct ArrowArray*);
+  void* private_data;
+};
+#endif
+#ifndef ARROW_C_STREAM_INTERFACE
+#define ARROW_C_STREAM_INTERFACE
+struct ArrowArrayStream {
+  int (*get_schema)(struct ArrowArrayStream*, struct ArrowSchema* out);
+  int (*get_next)(struct ArrowArrayStream*, struct ArrowArray* out);
+  const char* (*get_last_error)(struct ArrowArrayStream*);
+  void (*release)(struct ArrowArrayStream*);
+  void* private_data;
+};
+#endif
+
+/* ---- status codes: mapping to qurious::error::Error (qurious/src/error.rs:41-53) ---------- */
+typedef enum qgpu_status {
+  QGPU_OK = 0,
+  QGPU_ERR_INTERNAL = 1, /* Error::InternalError / unsupported type / unimplemented!() paths */
+  QGPU_ERR_ARROW = 2,    /* Error::ArrowError: type mismatch, divide by zero, cast failure */
+  QGPU_ERR_CUDA = 3,
+  QGPU_ERR_NCCL = 4,
+  QGPU_ERR_OOM = 5
+} qgpu_status;
+
+/* ---- logical type ids used in the expression IR and in qgpu_agg_desc ---------------------- */
+typedef enum qgpu_type_id {
+  QGPU_T_NULL = 0, QGPU_T_BOOL = 1, QGPU_T_INT8 = 2, QGPU_T_INT16 = 3, QGPU_T_INT32 = 4,
+  QGPU_T_INT64 = 5, QGPU_T_UINT8 = 6, QGPU_T_UINT16 = 7, QGPU_T_UINT32 = 8, QGPU_T_UINT64 = 9,
+  QGPU_T_FLOAT32 = 10, QGPU_T_FLOAT64 = 11, QGPU_T_UTF8 = 12, QGPU_T_DATE32 = 13,
+  QGPU_T_DATE64 = 14, QGPU_T_DECIMAL128 = 15
+} qgpu_type_id;
+
+typedef struct qgpu_type {
+  uint8_t id;        /* qgpu_type_id */
+  uint8_t precision; /* Decimal128 only */
+  int8_t scale;      /* Decimal128 only */
+} qgpu_type;
+
+/* ---- expression IR: postfix byte stream, little-endian ------------------------------------
+ *  QGPU_IR_COLUMN      u32 index                    physical/expr/column.rs:24-33
+ *  QGPU_IR_LITERAL     type(3B) u8 is_null value    physical/expr/literal.rs:19-23 (ScalarValue)
+ *                      value: bool/ints/dates = 8B, floats = f64 8B, decimal128 = 16B,
+ *                             utf8 = u32 len + bytes; absent when is_null or type NULL
+ *  QGPU_IR_BINARY      u8 op (Operator order of datatypes/operator.rs:4-20: Eq NotEq Gt GtEq Lt
+ *                      LtEq And Or Add Sub Mul Div Mod)   physical/expr/binary.rs:30-71
+ *  QGPU_IR_CAST        type(3B)                     physical/expr/cast.rs:32-38 (safe:false)
+ *  QGPU_IR_CASE        u32 n_when; stack: when1 then1 .. whenN thenN else   case.rs:30-47
+ *  QGPU_IR_IS_NULL / QGPU_IR_IS_NOT_NULL / QGPU_IR_NEGATIVE   is_null.rs / is_not_null.rs / negative.rs
+ */
+typedef enum qgpu_ir_op {
+  QGPU_IR_COLUMN = 1, QGPU_IR_LITERAL = 2, QGPU_IR_BINARY = 3, QGPU_IR_CAST = 4, QGPU_IR_CASE = 5,
+  QGPU_IR_IS_NULL = 6, QGPU_IR_IS_NOT_NULL = 7, QGPU_IR_NEGATIVE = 8
+} qgpu_ir_op;
+
+/* aggregate operator: AggregateOperator of logical/expr/aggregate.rs:56-62 */
+typedef enum qgpu_agg_op { QGPU_AGG_SUM = 0, QGPU_AGG_MIN = 1, QGPU_AGG_MAX = 2, QGPU_AGG_AVG = 3, QGPU_AGG_COUNT = 4 } qgpu_agg_op;
+
+/* join type: JoinType of common/join_type.rs:4-11 */
+typedef enum qgpu_join_type { QGPU_JOIN_LEFT = 0, QGPU_JOIN_RIGHT = 1, QGPU_JOIN_INNER = 2, QGPU_JOIN_FULL = 3, QGPU_JOIN_LEFT_SEMI = 4, QGPU_JOIN_LEFT_ANTI = 5 } qgpu_join_type;
+
+typedef struct qgpu_ctx qgpu_ctx;
+typedef struct qgpu_table qgpu_table; /* HBM-resident table: the GpuMemoryTable of SURVEY 8b */
+typedef struct qgpu_expr qgpu_expr;   /* parsed PhysicalExpr */
+typedef struct qgpu_plan qgpu_plan;   /* a PhysicalPlan node (owns references to its children) */
+
+/* One aggregate: {Sum,Min,Max,Avg,Count}AggregateExpr (physical/expr/aggregate/{sum,min,max,avg,count}.rs).
+ * `return_type` is the planner-inferred type (logical/expr/aggregate.rs:65-90);
+ * `expr_type` is AvgAggregateExpr::expr_data_type (avg.rs:16-20), ignored otherwise. */
+typedef struct qgpu_agg_desc {
+  int32_t op; /* qgpu_agg_op */
+  const qgpu_expr* expr;
+  qgpu_type return_type;
+  qgpu_type expr_type;
+} qgpu_agg_desc;
+
+/* JoinFilter (physical/plan/join/nest_loop_join.rs:29-40): expr over an intermediate batch whose
+ * column i is column `column_index[i]` of side `column_side[i]` (0 = Left/build, 1 = Right/probe). */
+typedef struct qgpu_join_filter {
+  const qgpu_expr* expr;
+  const struct ArrowSchema* schema;
+  const int32_t* column_index;
+  const int32_t* column_side;
+  int32_t n_columns;
+} qgpu_join_filter;
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* devices: CUDA ordinals this context drives (n = 1 in round 1: one process per GPU). */
+int qgpu_init(const int* devices, int n, qgpu_ctx** out);
+void qgpu_shutdown(qgpu_ctx* ctx);
+/* Last error of this context (or of a failed qgpu_init when ctx == NULL).  Never NULL. */
+const char* qgpu_last_error(const qgpu_ctx* ctx);
+/* Compatibility switches for reference quirks: name in {"avg_precision",
+ * "empty_decimal_sum"}; value 1 reproduces the reference's failure, 0 (default) the intended value. */
+int qgpu_set_compat(qgpu_ctx* ctx, const char* name, int value);
+/* number of kernel launches issued by this context since creation (bench.py: gpu_launches) */
+int64_t qgpu_kernel_launches(const qgpu_ctx* ctx);
+
+/* ---- tables: replaces MemoryTable (datasource/memory.rs:20-45) ---------------------------- */
+int qgpu_table_create(qgpu_ctx* ctx, const struct ArrowSchema* schema, qgpu_table** out);
+/* MemoryTable::insert (memory.rs:104-111): appends one RecordBatch (struct array).  Host buffers are
+ * staged through pinned memory and copied with cudaMemcpyAsync on a side stream.  Takes ownership:
+ * calls batch->release.  Only the columns later referenced need to be uploaded: pass
+ * upload_columns = NULL for all, else n indices. */
+int qgpu_table_append(qgpu_table* t, struct ArrowArray* batch, const int32_t* upload_columns, int32_t n);
+/* Same, but every buffer pointer inside `batch` is a DEVICE pointer on this context's GPU
+ * (Arrow C Device Data Interface, device_type ARROW_DEVICE_CUDA); buffers are copied D2D. */
+int qgpu_table_append_device(qgpu_table* t, struct ArrowArray* batch);
+int64_t qgpu_table_num_rows(const qgpu_table* t);
+int64_t qgpu_table_num_batches(const qgpu_table* t);
+/* bytes of column `col` resident in HBM in the layout the kernels read (after narrowing) */
+int64_t qgpu_table_column_bytes(const qgpu_table* t, int32_t col);
+int qgpu_table_schema(const qgpu_table* t, struct ArrowSchema* out);
+/* download as one RecordBatch (struct array) */
+int qgpu_table_export(qgpu_table* t, struct ArrowArray* out_array, struct ArrowSchema* out_schema);
+void qgpu_table_free(qgpu_table* t);
+
+/* ---- expressions --------------------------------------------------------------------------- */
+int qgpu_expr_parse(qgpu_ctx* ctx, const uint8_t* ir, size_t len, qgpu_expr** out);
+void qgpu_expr_free(qgpu_expr* e);
+
+/* ---- plan nodes: constructor argument lists mirror the reference's ------------------------ */
+/* Scan::new(schema, datasource, projections, filter) (physical/plan/scan.rs:22-35) over a
+ * GpuMemoryTable; execute == MemoryTable::scan(projection, filters) (memory.rs:69-98).
+ * projection: column indices or NULL (n_projection ignored). filter may be NULL. */
+int qgpu_plan_scan(qgpu_ctx* ctx, qgpu_table* datasource, const int32_t* projection, int32_t n_projection,
+                   const qgpu_expr* filter, qgpu_plan** out);
+/* Filter::new(input, predicate) (physical/plan/filter.rs:18-20) */
+int qgpu_plan_filter(qgpu_ctx* ctx, qgpu_plan* input, const qgpu_expr* predicate, qgpu_plan** out);
+/* Projection::new(schema, input, exprs) (physical/plan/projection.rs:17-19) */
+int qgpu_plan_projection(qgpu_ctx* ctx, const struct ArrowSchema* schema, qgpu_plan* input,
+                         const qgpu_expr* const* exprs, int32_t n_exprs, qgpu_plan** out);
+/* HashAggregate::new(schema, input, group_exprs, aggregate_exprs) (aggregate/hash.rs:118-130);
+ * n_group == 0  =>  NoGroupingAggregate::new(schema, input, aggr_expr) (aggregate/no_grouping.rs:16-22) */
+int qgpu_plan_aggregate(qgpu_ctx* ctx, const struct ArrowSchema* schema, qgpu_plan* input,
+                        const qgpu_expr* const* group_exprs, int32_t n_group,
+                        const qgpu_agg_desc* aggs, int32_t n_aggs, qgpu_plan** out);
+/* HashJoinExec::try_new(left, right, join_type, on, filter) (join/hash_join.rs:122-146).
+ * Build side is always `left` (hash_join.rs:355-359).  n_on == 0 is an InternalError. */
+int qgpu_plan_hash_join(qgpu_ctx* ctx, qgpu_plan* left, qgpu_plan* right, int32_t join_type,
+                        const qgpu_expr* const* left_on, const qgpu_expr* const* right_on, int32_t n_on,
+                        const qgpu_join_filter* filter, qgpu_plan** out);
+/* PhysicalPlan::schema (physical/plan/mod.rs:26) */
+int qgpu_plan_schema(const qgpu_plan* p, struct ArrowSchema* out);
+/* PhysicalPlan::execute (physical/plan/mod.rs:27): runs the whole subtree on the GPU (intermediate
+ * results stay in HBM) and returns the materialised Vec<RecordBatch> as a stream of host batches. */
+int qgpu_plan_execute(qgpu_plan* p, struct ArrowArrayStream* out);
+/* Same, but the result stays in HBM as a new table (used to chain operators and by bench.py's
+ * device-resident leg).  *out_batches receives the number of RecordBatches the reference would
+ * have returned (0 for HashAggregate over zero input batches). */
+int qgpu_plan_execute_device(qgpu_plan* p, qgpu_table** out, int64_t* out_batches);
+/* device time (ms, CUDA events on the context stream) and kernel launches of the last execute */
+int qgpu_plan_last_stats(const qgpu_plan* p, double* device_ms, int64_t* launches);
+/* name of the execution strategy chosen for this node by the last execute ("fused_scan_agg", ...) */
+const char* qgpu_plan_strategy(const qgpu_plan* p);
+void qgpu_plan_free(qgpu_plan* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QGPU_H */

@@ -1,0 +1,246 @@
+"""ctypes binding of libqgpu.so (include/qgpu.h).
+
+This is the Python stand-in for the Rust `extern "C"` shim described in INTEGRATION.md: it only
+marshals Arrow C Data Interface structs and the expression IR across the C ABI.  There is no compute
+and no fallback here: if the shared library is missing or no CUDA device is present the operators
+raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional, Sequence
+
+import pyarrow as pa
+from pyarrow.cffi import ffi as _ffi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqgpu.so")
+
+# every symbol include/qgpu.h declares (tests/test_abi.py checks the header against this list)
+SYMBOLS = [
+    "qgpu_init", "qgpu_shutdown", "qgpu_last_error", "qgpu_set_compat", "qgpu_kernel_launches",
+    "qgpu_table_create", "qgpu_table_append", "qgpu_table_append_device", "qgpu_table_num_rows",
+    "qgpu_table_num_batches", "qgpu_table_column_bytes", "qgpu_table_schema", "qgpu_table_export",
+    "qgpu_table_free", "qgpu_expr_parse", "qgpu_expr_free", "qgpu_plan_scan", "qgpu_plan_filter",
+    "qgpu_plan_projection", "qgpu_plan_aggregate", "qgpu_plan_hash_join", "qgpu_plan_schema",
+    "qgpu_plan_execute", "qgpu_plan_execute_device", "qgpu_plan_last_stats", "qgpu_plan_strategy",
+    "qgpu_plan_free",
+]
+
+STATUS_KIND = {1: "InternalError", 2: "ArrowError", 3: "CudaError", 4: "NcclError", 5: "OutOfMemory"}
+
+
+class QuriousError(RuntimeError):
+    """Mirror of qurious::error::Error (qurious/src/error.rs:41-53)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(msg)
+        self.code = code
+        self.kind = STATUS_KIND.get(code, "InternalError")
+
+
+class qgpu_type(ctypes.Structure):
+    _fields_ = [("id", ctypes.c_uint8), ("precision", ctypes.c_uint8), ("scale", ctypes.c_int8)]
+
+
+class qgpu_agg_desc(ctypes.Structure):
+    _fields_ = [("op", ctypes.c_int32), ("expr", ctypes.c_void_p), ("return_type", qgpu_type),
+                ("expr_type", qgpu_type)]
+
+
+class qgpu_join_filter(ctypes.Structure):
+    _fields_ = [("expr", ctypes.c_void_p), ("schema", ctypes.c_void_p),
+                ("column_index", ctypes.POINTER(ctypes.c_int32)),
+                ("column_side", ctypes.POINTER(ctypes.c_int32)), ("n_columns", ctypes.c_int32)]
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen libqgpu.so and declare prototypes.  Raises if the CUDA extension was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise QuriousError(3, f"libqgpu.so not found at {LIB_PATH}: build it with "
+                              f"`python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+    P = ctypes.POINTER
+    lib.qgpu_init.argtypes = [P(ctypes.c_int), ctypes.c_int, P(vp)]
+    lib.qgpu_init.restype = ctypes.c_int
+    lib.qgpu_shutdown.argtypes = [vp]
+    lib.qgpu_shutdown.restype = None
+    lib.qgpu_last_error.argtypes = [vp]
+    lib.qgpu_last_error.restype = ctypes.c_char_p
+    lib.qgpu_set_compat.argtypes = [vp, ctypes.c_char_p, ctypes.c_int]
+    lib.qgpu_kernel_launches.argtypes = [vp]
+    lib.qgpu_kernel_launches.restype = i64
+    lib.qgpu_table_create.argtypes = [vp, vp, P(vp)]
+    lib.qgpu_table_append.argtypes = [vp, vp, P(i32), i32]
+    lib.qgpu_table_append_device.argtypes = [vp, vp]
+    lib.qgpu_table_num_rows.argtypes = [vp]
+    lib.qgpu_table_num_rows.restype = i64
+    lib.qgpu_table_num_batches.argtypes = [vp]
+    lib.qgpu_table_num_batches.restype = i64
+    lib.qgpu_table_column_bytes.argtypes = [vp, i32]
+    lib.qgpu_table_column_bytes.restype = i64
+    lib.qgpu_table_schema.argtypes = [vp, vp]
+    lib.qgpu_table_export.argtypes = [vp, vp, vp]
+    lib.qgpu_table_free.argtypes = [vp]
+    lib.qgpu_table_free.restype = None
+    lib.qgpu_expr_parse.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, P(vp)]
+    lib.qgpu_expr_free.argtypes = [vp]
+    lib.qgpu_expr_free.restype = None
+    lib.qgpu_plan_scan.argtypes = [vp, vp, P(i32), i32, vp, P(vp)]
+    lib.qgpu_plan_filter.argtypes = [vp, vp, vp, P(vp)]
+    lib.qgpu_plan_projection.argtypes = [vp, vp, vp, P(vp), i32, P(vp)]
+    lib.qgpu_plan_aggregate.argtypes = [vp, vp, vp, P(vp), i32, P(qgpu_agg_desc), i32, P(vp)]
+    lib.qgpu_plan_hash_join.argtypes = [vp, vp, vp, i32, P(vp), P(vp), i32, P(qgpu_join_filter), P(vp)]
+    lib.qgpu_plan_schema.argtypes = [vp, vp]
+    lib.qgpu_plan_execute.argtypes = [vp, vp]
+    lib.qgpu_plan_execute_device.argtypes = [vp, P(vp), P(i64)]
+    lib.qgpu_plan_last_stats.argtypes = [vp, P(ctypes.c_double), P(i64)]
+    lib.qgpu_plan_strategy.argtypes = [vp]
+    lib.qgpu_plan_strategy.restype = ctypes.c_char_p
+    lib.qgpu_plan_free.argtypes = [vp]
+    lib.qgpu_plan_free.restype = None
+    _lib = lib
+    return lib
+
+
+def _addr(cdata) -> int:
+    return int(_ffi.cast("uintptr_t", cdata))
+
+
+class Context:
+    """One qgpu_ctx == one GPU (one process per GPU)."""
+
+    def __init__(self, device: Optional[int] = None):
+        self.lib = load_library()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        self.device = device
+        h = ctypes.c_void_p()
+        dev = (ctypes.c_int * 1)(device)
+        rc = self.lib.qgpu_init(dev, 1, ctypes.byref(h))
+        if rc != 0:
+            raise QuriousError(rc, self.lib.qgpu_last_error(None).decode())
+        self.handle = h
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise QuriousError(rc, self.lib.qgpu_last_error(self.handle).decode())
+
+    def set_compat(self, name: str, value: bool):
+        self.check(self.lib.qgpu_set_compat(self.handle, name.encode(), 1 if value else 0))
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.qgpu_kernel_launches(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.qgpu_shutdown(self.handle)
+            self.handle = None
+
+    # ---- marshalling helpers ------------------------------------------------------------------
+    def export_schema(self, schema: pa.Schema):
+        c = _ffi.new("struct ArrowSchema*")
+        schema._export_to_c(_addr(c))
+        return c
+
+    def parse_expr(self, expr) -> ctypes.c_void_p:
+        ir = expr.to_ir()
+        h = ctypes.c_void_p()
+        self.check(self.lib.qgpu_expr_parse(self.handle, ir, len(ir), ctypes.byref(h)))
+        return h
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx
+
+
+class DeviceTable:
+    """Owning wrapper of a qgpu_table handle (an HBM-resident MemoryTable)."""
+
+    def __init__(self, ctx: Context, handle: ctypes.c_void_p, schema: pa.Schema):
+        self.ctx = ctx
+        self.handle = handle
+        self.schema = schema
+
+    @staticmethod
+    def create(ctx: Context, schema: pa.Schema) -> "DeviceTable":
+        h = ctypes.c_void_p()
+        cs = ctx.export_schema(schema)
+        try:
+            ctx.check(ctx.lib.qgpu_table_create(ctx.handle, _addr(cs), ctypes.byref(h)))
+        finally:
+            if cs.release != _ffi.NULL:
+                cs.release(cs)
+        return DeviceTable(ctx, h, schema)
+
+    def append(self, batch: pa.RecordBatch, upload_columns: Optional[Sequence[int]] = None):
+        ca = _ffi.new("struct ArrowArray*")
+        batch._export_to_c(_addr(ca))
+        if upload_columns is None:
+            rc = self.ctx.lib.qgpu_table_append(self.handle, _addr(ca), None, 0)
+        else:
+            arr = (ctypes.c_int32 * len(upload_columns))(*upload_columns)
+            rc = self.ctx.lib.qgpu_table_append(self.handle, _addr(ca), arr, len(upload_columns))
+        self.ctx.check(rc)
+
+    def append_device_struct(self, array_addr: int):
+        """`array_addr`: address of a struct ArrowArray whose buffers are device pointers."""
+        self.ctx.check(self.ctx.lib.qgpu_table_append_device(self.handle, array_addr))
+
+    @property
+    def num_rows(self) -> int:
+        return int(self.ctx.lib.qgpu_table_num_rows(self.handle))
+
+    @property
+    def num_batches(self) -> int:
+        return int(self.ctx.lib.qgpu_table_num_batches(self.handle))
+
+    def column_bytes(self, col: int) -> int:
+        r = int(self.ctx.lib.qgpu_table_column_bytes(self.handle, col))
+        if r < 0:
+            raise QuriousError(1, self.ctx.lib.qgpu_last_error(self.ctx.handle).decode())
+        return r
+
+    def to_batch(self) -> pa.RecordBatch:
+        ca = _ffi.new("struct ArrowArray*")
+        cs = _ffi.new("struct ArrowSchema*")
+        self.ctx.check(self.ctx.lib.qgpu_table_export(self.handle, _addr(ca), _addr(cs)))
+        return pa.RecordBatch._import_from_c(_addr(ca), _addr(cs))
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.qgpu_table_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            if self.ctx.handle:
+                self.free()
+        except Exception:
+            pass
+
+
+def read_stream(ctx: Context, stream_cdata) -> List[pa.RecordBatch]:
+    reader = pa.RecordBatchReader._import_from_c(_addr(stream_cdata))
+    return [b for b in reader]
+
+
+def new_stream():
+    return _ffi.new("struct ArrowArrayStream*")
+
+
+addr = _addr

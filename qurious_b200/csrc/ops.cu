@@ -1,0 +1,1096 @@
+// Generic hash aggregate and hash join on the GPU (interpreter driven, any supported key/argument
+// expression, NULL-aware).  The fused fast paths (fused.cu) cover the hot plan shapes; everything
+// else lands here and produces the same results.
+//
+//   HashAggregate / GroupAccumulator   qurious/src/physical/plan/aggregate/hash.rs:45-107,138-170
+//   NoGroupingAggregate                qurious/src/physical/plan/aggregate/no_grouping.rs:30-62
+//   accumulators                       qurious/src/physical/expr/aggregate/{sum,avg,count,min,max,mod}.rs
+//   HashJoinExec / JoinHashMap         qurious/src/physical/plan/join/hash_join.rs:40-385
+//   join helpers                       qurious/src/physical/plan/join/mod.rs:26-207
+//
+// Grouping is by key EQUALITY through an HBM-resident open-addressing table (linear probing, slot =
+// hash32|representative row, claimed with atomicCAS); the reference groups by 64-bit SipHash only
+// (SURVEY 8a quirk Q1 -- intended semantics are key equality).
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "ops.h"
+
+namespace qgpu {
+
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                  \
+  do {                                                               \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
+    (ctx)->launches++;                                               \
+    CUDA_CHECK(cudaGetLastError());                                  \
+  } while (0)
+
+static inline int grid_for(Ctx* ctx, int64_t n, int per_block) {
+  int64_t g = (n + per_block - 1) / per_block;
+  int64_t cap = (int64_t)ctx->sm_count * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+#define MAX_KEYS 8
+#define NO_GROUP 0xffffffffu
+
+struct KeyClasses {
+  uint8_t c[MAX_KEYS];
+};
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+
+__device__ __forceinline__ uint64_t hash_val(uint64_t h, const Val& v, int vclass) {
+  if (!v.valid) return mix64(h ^ 0x9e3779b97f4a7c15ULL);
+  if (vclass == VC_STR) {
+    const unsigned char* p = (const unsigned char*)v.lo;
+    uint64_t x = 0xcbf29ce484222325ULL ^ v.hi;
+    for (int64_t i = 0; i < (int64_t)v.hi; ++i) x = (x ^ p[i]) * 0x100000001b3ULL;
+    return mix64(h ^ mix64(x));
+  }
+  uint64_t x = mix64(h ^ v.lo);
+  if (vclass == VC_DEC) x = mix64(x ^ v.hi ^ 0x632be59bd9b4e019ULL);
+  return x + 0x2545f4914f6cdd1dULL;
+}
+
+__device__ __forceinline__ bool vals_equal(const Val& a, const Val& b, int vclass) {
+  if (!a.valid || !b.valid) return a.valid == b.valid;
+  if (vclass == VC_STR) {
+    if (a.hi != b.hi) return false;
+    const unsigned char* p = (const unsigned char*)a.lo;
+    const unsigned char* q = (const unsigned char*)b.lo;
+    for (int64_t i = 0; i < (int64_t)a.hi; ++i)
+      if (p[i] != q[i]) return false;
+    return true;
+  }
+  if (vclass == VC_DEC) return a.lo == b.lo && a.hi == b.hi;
+  return a.lo == b.lo;
+}
+
+__device__ __forceinline__ void load_programs(Program* dst, const Program* src, int n) {
+  const int words = (int)(sizeof(Program) / 4) * n;
+  for (int i = threadIdx.x; i < words; i += blockDim.x) ((uint32_t*)dst)[i] = ((const uint32_t*)src)[i];
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// key table: insert every row, remember its slot
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_key_insert(const Program* __restrict__ progs, int n_keys, KeyClasses kc,
+                                                    unsigned long long* __restrict__ slots, uint32_t* __restrict__ slot_gid,
+                                                    long long* __restrict__ gid_rep, uint32_t* __restrict__ row_slot, int64_t n,
+                                                    uint64_t cap_mask, int skip_null, unsigned long long max_groups,
+                                                    unsigned long long* __restrict__ n_groups, int* __restrict__ abort_flag,
+                                                    int* __restrict__ err) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Program* P = (Program*)smem_raw;
+  load_programs(P, progs, n_keys);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride) {
+    if (*(volatile int*)abort_flag) return;
+    Val k[MAX_KEYS];
+    uint64_t h = 0x243f6a8885a308d3ULL;
+    bool anynull = false;
+    for (int i = 0; i < n_keys; ++i) {
+      k[i] = eval_row(P[i], row, err);
+      anynull |= !k[i].valid;
+      h = hash_val(h, k[i], kc.c[i]);
+    }
+    if (skip_null && anynull) {
+      row_slot[row] = NO_GROUP;
+      continue;
+    }
+    const uint32_t h32 = (uint32_t)(h >> 32);
+    uint64_t slot = h & cap_mask;
+    const unsigned long long mine = ((unsigned long long)h32 << 32) | (unsigned long long)(row + 1);
+    while (true) {
+      unsigned long long cur = *(volatile unsigned long long*)&slots[slot];
+      if (cur == 0) {
+        unsigned long long old = atomicCAS(&slots[slot], 0ull, mine);
+        if (old == 0) {
+          unsigned long long g = atomicAdd(n_groups, 1ull);
+          if (g >= max_groups) {
+            *abort_flag = 1;
+          } else {
+            slot_gid[slot] = (uint32_t)g;
+            gid_rep[g] = row;
+          }
+          row_slot[row] = (uint32_t)slot;
+          break;
+        }
+        cur = old;
+      }
+      if ((uint32_t)(cur >> 32) == h32) {
+        const int64_t rep = (int64_t)(cur & 0xffffffffull) - 1;
+        bool eq = true;
+        if (rep != row) {
+          for (int i = 0; i < n_keys && eq; ++i) {
+            Val o = eval_row(P[i], rep, err);
+            eq = vals_equal(k[i], o, kc.c[i]);
+          }
+        }
+        if (eq) {
+          row_slot[row] = (uint32_t)slot;
+          break;
+        }
+      }
+      slot = (slot + 1) & cap_mask;
+    }
+  }
+}
+
+__global__ void k_slot_to_gid(uint32_t* __restrict__ row_slot, const uint32_t* __restrict__ slot_gid, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint32_t s = row_slot[i];
+    if (s != NO_GROUP) row_slot[i] = slot_gid[s];
+  }
+}
+
+static DBufP upload_programs(Ctx* ctx, std::vector<Program>& ps) {
+  DBufP b = ctx->alloc(std::max<size_t>(ps.size() * sizeof(Program), 16));
+  if (!ps.empty()) {
+    CUDA_CHECK(cudaMemcpyAsync(b->ptr, ps.data(), ps.size() * sizeof(Program), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
+  return b;
+}
+
+template <typename K>
+static void set_dyn_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+void check_hash_key_type(const DType& t) {
+  // create_hashes (utils/array.rs:190-210): Int64, UInt8, Int32, Utf8, Date32/64, (Time*), Decimal128/256 only
+  switch (t.id) {
+    case QGPU_T_INT64: case QGPU_T_UINT8: case QGPU_T_INT32: case QGPU_T_UTF8: case QGPU_T_DATE32: case QGPU_T_DATE64:
+    case QGPU_T_DECIMAL128:
+      return;
+    default: throw_internal("Unsupported data type in hasher: " + t.str());
+  }
+}
+
+KeyTable build_key_table(Ctx* ctx, const View& v, std::vector<std::shared_ptr<Compiled>>& keys, bool skip_null_keys,
+                         DBufP* key_programs_out) {
+  const int64_t n = v.num_rows;
+  if ((int)keys.size() > MAX_KEYS) throw_internal("more than 8 key expressions are not supported");
+  if (n >= 0xfffffff0LL) throw_internal("more than 2^32-16 rows per operator input are not supported");
+  KeyClasses kc;
+  memset(&kc, 0, sizeof(kc));
+  std::vector<Program> ps;
+  for (size_t i = 0; i < keys.size(); ++i) {
+    if (keys[i]->deferred_err && n > 0) throw_eval_error(keys[i]->deferred_err);
+    kc.c[i] = (uint8_t)class_of(keys[i]->result_type);
+    ps.push_back(bind_program(ctx, *keys[i], v));
+  }
+  DBufP dprogs = upload_programs(ctx, ps);
+  if (key_programs_out) *key_programs_out = dprogs;
+  KeyTable t;
+  t.row_gid = ctx->alloc(std::max<size_t>((size_t)n * 4, 4));
+  if (n == 0) return t;
+  int64_t need = 2;
+  while (need < 2 * n) need <<= 1;
+  int64_t cap = std::min<int64_t>(need, 1 << 16);
+  if (cap < 1024) cap = 1024;
+  const size_t smem = keys.size() * sizeof(Program);
+  set_dyn_smem(k_key_insert, smem);
+  while (true) {
+    const int64_t max_groups = std::min<int64_t>(cap / 2, n);
+    t.slots = ctx->alloc_zero((size_t)cap * 8);
+    t.slot_gid = ctx->alloc((size_t)cap * 4);
+    t.gid_rep = ctx->alloc((size_t)std::max<int64_t>(max_groups, 1) * 8);
+    DBufP flags = ctx->alloc_zero(16);  // [0] n_groups (u64), [8] abort (int), [12] err (int)
+    LAUNCH(ctx, k_key_insert, grid_for(ctx, n, 256), 256, smem, (const Program*)dprogs->ptr, (int)keys.size(), kc,
+           (unsigned long long*)t.slots->ptr, (uint32_t*)t.slot_gid->ptr, (long long*)t.gid_rep->ptr,
+           (uint32_t*)t.row_gid->ptr, n, (uint64_t)(cap - 1), skip_null_keys ? 1 : 0, (unsigned long long)max_groups,
+           (unsigned long long*)flags->ptr, (int*)((char*)flags->ptr + 8), (int*)((char*)flags->ptr + 12));
+    struct { unsigned long long ng; int abort_; int err; } h;
+    ctx->d2h_sync(&h, flags->ptr, 16);
+    if (h.err) throw_eval_error(h.err);
+    if (!h.abort_) {
+      t.capacity = cap;
+      t.n_groups = (int64_t)h.ng;
+      break;
+    }
+    if (cap >= need) throw_internal("hash table overflow (internal error)");
+    cap = std::min<int64_t>(cap * 16, need);
+  }
+  LAUNCH(ctx, k_slot_to_gid, grid_for(ctx, n, 256), 256, 0, (uint32_t*)t.row_gid->ptr, (const uint32_t*)t.slot_gid->ptr, n);
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// aggregate
+// ------------------------------------------------------------------------------------------------
+enum AccKind : int {
+  AK_COUNT = 0, AK_SUM_I64, AK_SUM_DEC, AK_SUM_F64, AK_MIN_I64, AK_MAX_I64, AK_MIN_U64, AK_MAX_U64, AK_MIN_F64, AK_MAX_F64,
+  AK_MIN_DEC, AK_MAX_DEC
+};
+
+struct AggDev {
+  int kind;
+  int pad;
+  unsigned long long* lo;
+  unsigned long long* hi;
+  unsigned long long* cnt;
+};
+#define MAX_AGGS 16
+struct AggDevs {
+  AggDev a[MAX_AGGS];
+};
+
+__global__ void __launch_bounds__(256) k_agg_accumulate(const Program* __restrict__ progs, AggDevs ad, int n_aggs,
+                                                        const uint32_t* __restrict__ row_gid,
+                                                        long long* __restrict__ first_row, int64_t n, int phase,
+                                                        int* __restrict__ err) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Program* P = (Program*)smem_raw;
+  load_programs(P, progs, n_aggs);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride) {
+    const uint32_t g = row_gid ? row_gid[row] : 0u;
+    if (phase == 0) atomicMin(&first_row[g], (long long)row);
+    for (int a = 0; a < n_aggs; ++a) {
+      const AggDev d = ad.a[a];
+      if (phase == 1 && d.kind != AK_MIN_DEC && d.kind != AK_MAX_DEC) continue;
+      const Val v = eval_row(P[a], row, err);
+      if (!v.valid) continue;
+      if (phase == 0) atomicAdd(&d.cnt[g], 1ull);
+      switch (d.kind) {
+        case AK_SUM_I64: atomicAdd(&d.lo[g], (unsigned long long)v.lo); break;
+        case AK_SUM_DEC: {
+          unsigned long long old = atomicAdd(&d.lo[g], (unsigned long long)v.lo);
+          unsigned long long carry = (old + v.lo < old) ? 1ull : 0ull;
+          unsigned long long addhi = v.hi + carry;
+          if (addhi) atomicAdd(&d.hi[g], addhi);
+          break;
+        }
+        case AK_SUM_F64: atomicAdd((double*)&d.lo[g], val_f64(v)); break;
+        case AK_MIN_I64: atomicMin((long long*)&d.lo[g], (long long)v.lo); break;
+        case AK_MAX_I64: atomicMax((long long*)&d.lo[g], (long long)v.lo); break;
+        case AK_MIN_U64: atomicMin(&d.lo[g], (unsigned long long)v.lo); break;
+        case AK_MAX_U64: atomicMax(&d.lo[g], (unsigned long long)v.lo); break;
+        case AK_MIN_F64: atomicMin((long long*)&d.lo[g], (long long)f64_total_key(val_f64(v))); break;
+        case AK_MAX_F64: atomicMax((long long*)&d.lo[g], (long long)f64_total_key(val_f64(v))); break;
+        case AK_MIN_DEC:
+          if (phase == 0) atomicMin((long long*)&d.hi[g], (long long)v.hi);
+          else if (v.hi == *(volatile unsigned long long*)&d.hi[g]) atomicMin(&d.lo[g], (unsigned long long)v.lo);
+          break;
+        case AK_MAX_DEC:
+          if (phase == 0) atomicMax((long long*)&d.hi[g], (long long)v.hi);
+          else if (v.hi == *(volatile unsigned long long*)&d.hi[g]) atomicMax(&d.lo[g], (unsigned long long)v.lo);
+          break;
+        default: break;
+      }
+    }
+  }
+}
+
+__global__ void k_fill_u64(unsigned long long* p, int64_t n, unsigned long long v) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+struct FinSpec {
+  int op;          // qgpu_agg_op
+  int kind;        // AccKind
+  int out_phys;    // Phys of the output column
+  int sum_scale;   // AVG decimal
+  int target_scale;
+  int target_prec;
+  int compat_avg;  // validate the pre-division value (reference quirk Q5)
+  int no_input;    // ungrouped aggregate over zero input batches
+  const unsigned long long* lo;
+  const unsigned long long* hi;
+  const unsigned long long* cnt;
+  void* out;
+  uint32_t* out_valid;
+};
+
+__device__ __forceinline__ double key_to_f64(long long k) {
+  union { long long i; double d; } c;
+  c.i = k ^ (long long)(((unsigned long long)(k >> 63)) >> 1);
+  return c.d;
+}
+
+// one warp per 32 groups so that the validity word is produced by one ballot
+__global__ void __launch_bounds__(256) k_agg_finalize(FinSpec f, int64_t n_groups, int* __restrict__ err,
+                                                      unsigned long long* __restrict__ null_count) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_words = (n_groups + 31) >> 5;
+  for (int64_t w = warp_id; w < n_words; w += warps) {
+    const int64_t g = (w << 5) + lane;
+    bool valid = false;
+    unsigned long long lo = 0, hi = 0;
+    if (g < n_groups) {
+      const unsigned long long cnt = f.cnt[g];
+      switch (f.op) {
+        case QGPU_AGG_COUNT:
+          lo = cnt;
+          valid = true;
+          break;
+        case QGPU_AGG_SUM:
+          valid = cnt > 0;
+          lo = f.lo[g];
+          hi = f.hi ? f.hi[g] : 0;
+          break;
+        case QGPU_AGG_MIN:
+        case QGPU_AGG_MAX:
+          // an all-NULL input leaves the type's MAX/MIN sentinel, not NULL
+          valid = !f.no_input;
+          lo = f.lo[g];
+          hi = f.hi ? f.hi[g] : 0;
+          if (f.kind == AK_MIN_F64 || f.kind == AK_MAX_F64) {
+            union { unsigned long long u; double d; } c;
+            c.d = key_to_f64((long long)lo);
+            lo = c.u;
+          }
+          break;
+        case QGPU_AGG_AVG:
+          if (cnt > 0) {
+            if (f.kind == AK_SUM_F64) {
+              union { unsigned long long u; double d; } c;
+              c.u = f.lo[g];
+              c.d = c.d / (double)cnt;
+              lo = c.u;
+              valid = true;
+            } else {
+              // avg.rs:89-116: value = sum * 10^(target_scale - sum_scale) (checked); result = value / count
+              i128 sum = (i128)(((u128)f.hi[g] << 64) | (u128)f.lo[g]);
+              i128 mul = pow10_i128(f.target_scale - f.sum_scale);
+              i128 value = sum * mul;
+              bool ovf = sum != 0 && value / mul != sum;
+              if (!ovf && f.compat_avg && !dec_fits_precision(value, f.target_prec)) ovf = true;
+              if (ovf) {
+                // the reference yields a NULL of type Decimal128(38,10) which then fails the schema check
+                if (f.compat_avg) raise_err(err, EE_DEC_PRECISION);
+                else if (sum != 0 && value / mul != sum) raise_err(err, EE_OVERFLOW);
+              } else {
+                i128 q = value / (i128)cnt;
+                lo = (unsigned long long)(u128)q;
+                hi = (unsigned long long)((u128)q >> 64);
+                valid = true;
+              }
+            }
+          }
+          break;
+      }
+    }
+    const uint32_t vw = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) {
+      f.out_valid[w] = vw;
+      int live = (int)min((int64_t)32, n_groups - (w << 5));
+      if (live - __popc(vw)) atomicAdd(null_count, (unsigned long long)(live - __popc(vw)));
+    }
+    if (g < n_groups) {
+      if (!valid) lo = hi = 0;
+      switch (f.out_phys) {
+        case PH_I8: case PH_U8: ((uint8_t*)f.out)[g] = (uint8_t)lo; break;
+        case PH_I16: case PH_U16: ((uint16_t*)f.out)[g] = (uint16_t)lo; break;
+        case PH_I32: case PH_U32: ((uint32_t*)f.out)[g] = (uint32_t)lo; break;
+        case PH_I64: case PH_U64: case PH_F64: ((unsigned long long*)f.out)[g] = lo; break;
+        case PH_F32: {
+          union { unsigned long long u; double d; } c;
+          c.u = lo;
+          ((float*)f.out)[g] = (float)c.d;
+          break;
+        }
+        case PH_I128: ((ulonglong2*)f.out)[g] = make_ulonglong2(lo, hi); break;
+        default: break;
+      }
+    }
+  }
+}
+
+static Phys out_phys_of(const DType& t) {
+  switch (t.id) {
+    case QGPU_T_INT8: return PH_I8;
+    case QGPU_T_INT16: return PH_I16;
+    case QGPU_T_INT32: case QGPU_T_DATE32: return PH_I32;
+    case QGPU_T_INT64: case QGPU_T_DATE64: return PH_I64;
+    case QGPU_T_UINT8: return PH_U8;
+    case QGPU_T_UINT16: return PH_U16;
+    case QGPU_T_UINT32: return PH_U32;
+    case QGPU_T_UINT64: return PH_U64;
+    case QGPU_T_FLOAT32: return PH_F32;
+    case QGPU_T_FLOAT64: return PH_F64;
+    case QGPU_T_DECIMAL128: return PH_I128;
+    default: return PH_NULL;
+  }
+}
+
+static bool same_native(const DType& a, const DType& b) {
+  if (a.is_decimal() && b.is_decimal()) return true;
+  return a.id == b.id;
+}
+
+void validate_agg_types(const std::vector<AggSpec>& aggs) {
+  for (const AggSpec& a : aggs) {
+    const DType& at = a.arg->result_type;
+    const DType& rt = a.return_type;
+    switch (a.op) {
+      case QGPU_AGG_SUM:  // sum.rs:36-51: UInt64 / Int64 / Float64 / Decimal128 only
+        if (!(rt.id == QGPU_T_UINT64 || rt.id == QGPU_T_INT64 || rt.id == QGPU_T_FLOAT64 || rt.is_decimal()))
+          throw_internal("Sum not supported for " + a.arg->display + ": " + rt.str());
+        if (!same_native(at, rt)) throw_internal("SUM input type " + at.str() + " does not match accumulator type " + rt.str());
+        break;
+      case QGPU_AGG_COUNT:
+        if (rt.id != QGPU_T_INT64) throw_internal("COUNT return type must be Int64");
+        break;
+      case QGPU_AGG_AVG:  // avg.rs:36-60
+        if (a.expr_type.is_decimal() && rt.is_decimal()) {
+          if (!at.is_decimal()) throw_internal("AVG decimal accumulator fed a non-decimal array");
+          if (rt.scale < a.expr_type.scale) throw_internal("Arithmetic Overflow in DecimalAvgAccumulator");
+        } else if (rt.id == QGPU_T_FLOAT64) {
+          if (at.id != QGPU_T_FLOAT64) throw_internal("AVG(Float64) accumulator fed a non-Float64 array");  // avg.rs:70
+        } else {
+          throw_internal("Unsupported data type [" + rt.str() + "] for AVG aggregate");
+        }
+        break;
+      case QGPU_AGG_MIN:
+      case QGPU_AGG_MAX:
+        if (!(rt.is_int() || rt.is_float() || rt.is_decimal() || rt.is_date()))
+          throw_internal("PrimitiveAccumulator not supported for datatype: " + rt.str());
+        if (!same_native(at, rt)) throw_internal("MIN/MAX input type " + at.str() + " does not match accumulator type " + rt.str());
+        if (rt.is_date())  // scalar.rs:228 ScalarValue::try_from_array has no Date variants -> unimplemented!()
+          throw_internal("data type " + rt.str() + " not supported");
+        break;
+      default: throw_internal("unknown aggregate operator");
+    }
+  }
+}
+
+View run_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<Compiled>>& keys, std::vector<AggSpec>& aggs,
+                   const Schema& out_schema) {
+  const int64_t n = input.num_rows;
+  const bool grouped = !keys.empty();
+  if ((int)aggs.size() > MAX_AGGS) throw_internal("more than 16 aggregate expressions are not supported");
+  if (out_schema.fields.size() != keys.size() + aggs.size()) throw_arrow("aggregate output schema has the wrong number of fields");
+  View out;
+  out.schema = out_schema;
+  if (grouped && input.num_batches == 0) {  // hash.rs:146-148
+    out.num_batches = 0;
+    out.num_rows = 0;
+    for (size_t i = 0; i < out_schema.fields.size(); ++i) {
+      auto c = std::make_shared<DCol>();
+      c->type = out_schema.fields[i].type;
+      c->phys = PH_NULL;
+      out.cols.push_back({c, nullptr});
+    }
+    return out;
+  }
+  validate_agg_types(aggs);
+  for (auto& k : keys) check_hash_key_type(k->result_type);
+
+  KeyTable kt;
+  int64_t n_groups = 1;
+  if (grouped) {
+    kt = build_key_table(ctx, input, keys, false, nullptr);
+    n_groups = kt.n_groups;
+  }
+  // ---- accumulators ---------------------------------------------------------------------------
+  AggDevs ad;
+  memset(&ad, 0, sizeof(ad));
+  std::vector<DBufP> keep;
+  std::vector<Program> ps;
+  const int64_t ng_alloc = std::max<int64_t>(n_groups, 1);
+  auto fill = [&](DBufP& b, unsigned long long v) {
+    if (v == 0) {
+      CUDA_CHECK(cudaMemsetAsync(b->ptr, 0, (size_t)ng_alloc * 8, ctx->stream));
+    } else {
+      LAUNCH(ctx, k_fill_u64, grid_for(ctx, ng_alloc, 256), 256, 0, (unsigned long long*)b->ptr, ng_alloc, v);
+    }
+  };
+  bool need_phase1 = false;
+  for (size_t i = 0; i < aggs.size(); ++i) {
+    AggSpec& a = aggs[i];
+    if (a.arg->deferred_err && n > 0) throw_eval_error(a.arg->deferred_err);
+    ps.push_back(bind_program(ctx, *a.arg, input));
+    const DType& at = a.arg->result_type;
+    const VClass vc = class_of(at);
+    AggDev& d = ad.a[i];
+    DBufP lo = ctx->alloc((size_t)ng_alloc * 8), hi = ctx->alloc((size_t)ng_alloc * 8), cnt = ctx->alloc((size_t)ng_alloc * 8);
+    keep.push_back(lo);
+    keep.push_back(hi);
+    keep.push_back(cnt);
+    unsigned long long init_lo = 0, init_hi = 0;
+    switch (a.op) {
+      case QGPU_AGG_COUNT: d.kind = AK_COUNT; break;
+      case QGPU_AGG_SUM:
+      case QGPU_AGG_AVG: d.kind = vc == VC_DEC ? AK_SUM_DEC : (vc == VC_FLT ? AK_SUM_F64 : AK_SUM_I64); break;
+      case QGPU_AGG_MIN:
+      case QGPU_AGG_MAX: {
+        const bool mn = a.op == QGPU_AGG_MIN;
+        if (vc == VC_DEC) {
+          d.kind = mn ? AK_MIN_DEC : AK_MAX_DEC;
+          init_hi = mn ? (unsigned long long)INT64_MAX : (unsigned long long)INT64_MIN;
+          init_lo = mn ? ~0ull : 0ull;
+          need_phase1 = true;
+        } else if (vc == VC_FLT) {
+          d.kind = mn ? AK_MIN_F64 : AK_MAX_F64;
+          double lim = at.id == QGPU_T_FLOAT32 ? 3.4028234663852886e38 : 1.7976931348623157e308;
+          init_lo = (unsigned long long)f64_total_key(mn ? lim : -lim);
+        } else if (vc == VC_UINT) {
+          d.kind = mn ? AK_MIN_U64 : AK_MAX_U64;
+          int bits = arrow_width(at) * 8;
+          init_lo = mn ? (bits >= 64 ? ~0ull : ((1ull << bits) - 1ull)) : 0ull;
+        } else {
+          d.kind = mn ? AK_MIN_I64 : AK_MAX_I64;
+          int bits = arrow_width(at) * 8;
+          long long mx = bits >= 64 ? INT64_MAX : (((long long)1 << (bits - 1)) - 1);
+          init_lo = (unsigned long long)(mn ? mx : (-mx - 1));
+        }
+        break;
+      }
+    }
+    fill(lo, init_lo);
+    fill(hi, init_hi);
+    fill(cnt, 0);
+    d.lo = (unsigned long long*)lo->ptr;
+    d.hi = (unsigned long long*)hi->ptr;
+    d.cnt = (unsigned long long*)cnt->ptr;
+  }
+  DBufP first_row = ctx->alloc((size_t)ng_alloc * 8);
+  fill(first_row, (unsigned long long)INT64_MAX);
+  DBufP err = ctx->alloc_zero(16);
+  if (n > 0) {
+    DBufP dprogs = upload_programs(ctx, ps);
+    const size_t smem = ps.size() * sizeof(Program);
+    set_dyn_smem(k_agg_accumulate, smem);
+    for (int phase = 0; phase < (need_phase1 ? 2 : 1); ++phase)
+      LAUNCH(ctx, k_agg_accumulate, grid_for(ctx, n, 256), 256, smem, (const Program*)dprogs->ptr, ad, (int)aggs.size(),
+             grouped ? (const uint32_t*)kt.row_gid->ptr : nullptr, (long long*)first_row->ptr, n, phase, (int*)err->ptr);
+    int e = ctx->read_scalar((const int*)err->ptr);
+    if (e) throw_eval_error(e);
+  }
+  if (!grouped) n_groups = 1;
+  // ---- group order: first occurrence (the reference's order is unspecified) --
+  IdxP order;        // output position -> gid
+  IdxP first_idx;    // output position -> first input row of the group
+  if (grouped) {
+    std::vector<long long> fr((size_t)n_groups);
+    if (n_groups > 0) ctx->d2h_sync(fr.data(), first_row->ptr, (size_t)n_groups * 8);
+    std::vector<long long> ord((size_t)n_groups);
+    std::iota(ord.begin(), ord.end(), 0LL);
+    if (n_groups <= (1 << 22)) std::sort(ord.begin(), ord.end(), [&](long long a, long long b) { return fr[a] < fr[b]; });
+    std::vector<long long> fidx((size_t)n_groups);
+    for (int64_t i = 0; i < n_groups; ++i) fidx[i] = fr[ord[i]];
+    order = std::make_shared<IdxVec>();
+    order->length = n_groups;
+    order->buf = ctx->alloc(std::max<size_t>((size_t)n_groups * 8, 8));
+    first_idx = std::make_shared<IdxVec>();
+    first_idx->length = n_groups;
+    first_idx->buf = ctx->alloc(std::max<size_t>((size_t)n_groups * 8, 8));
+    if (n_groups > 0) {
+      ctx->h2d(order->buf->ptr, ord.data(), (size_t)n_groups * 8);
+      ctx->h2d(first_idx->buf->ptr, fidx.data(), (size_t)n_groups * 8);
+      ctx->sync();
+    }
+  }
+  out.num_rows = n_groups;
+  out.num_batches = 1;
+  // ---- key columns: values of the group's first row (hash.rs:62-68) ---------------------------------
+  if (grouped) {
+    View firsts = apply_selection_view(ctx, input, first_idx);
+    for (size_t i = 0; i < keys.size(); ++i) {
+      Compiled& k = *keys[i];
+      if (k.result_type != out_schema.fields[i].type)
+        throw_arrow("column types must match schema types, expected " + out_schema.fields[i].type.str() + " but found " +
+                    k.result_type.str() + " at column index " + std::to_string(i));
+      if (k.is_column_ref) out.cols.push_back(firsts.cols[k.column_ref]);
+      else out.cols.push_back({eval_to_column(ctx, k, firsts), nullptr});
+    }
+  }
+  // ---- aggregate columns ----------------------------------------------------------------------------
+  for (size_t i = 0; i < aggs.size(); ++i) {
+    AggSpec& a = aggs[i];
+    const Field& of = out_schema.fields[keys.size() + i];
+    // the accumulator's result type must equal the schema's (RecordBatch::try_new check)
+    DType produced = a.return_type;
+    if (a.op == QGPU_AGG_COUNT) produced = mk_type(QGPU_T_INT64);
+    if (produced != of.type)
+      throw_arrow("column types must match schema types, expected " + of.type.str() + " but found " + produced.str() +
+                  " at column index " + std::to_string(keys.size() + i));
+    auto col = std::make_shared<DCol>();
+    col->type = produced;
+    col->phys = out_phys_of(produced);
+    col->length = n_groups;
+    const int64_t n_words = (n_groups + 31) >> 5;
+    col->data = ctx->alloc(std::max<size_t>((size_t)n_groups * std::max(phys_width(col->phys), 1), 16));
+    col->validity = ctx->alloc(std::max<size_t>((size_t)n_words * 4, 4));
+    FinSpec f;
+    memset(&f, 0, sizeof(f));
+    f.op = a.op;
+    f.kind = ad.a[i].kind;
+    f.out_phys = col->phys;
+    f.sum_scale = a.expr_type.scale;
+    f.target_scale = a.return_type.scale;
+    f.target_prec = a.return_type.precision;
+    f.compat_avg = ctx->compat_avg_precision ? 1 : 0;
+    f.no_input = (!grouped && input.num_batches == 0) ? 1 : 0;
+    f.lo = ad.a[i].lo;
+    f.hi = ad.a[i].hi;
+    f.cnt = ad.a[i].cnt;
+    f.out = col->data->ptr;
+    f.out_valid = (uint32_t*)col->validity->ptr;
+    DBufP flags = ctx->alloc_zero(16);
+    if (n_groups > 0) {
+      LAUNCH(ctx, k_agg_finalize, grid_for(ctx, n_groups, 256), 256, 0, f, n_groups, (int*)flags->ptr,
+             (unsigned long long*)((char*)flags->ptr + 8));
+      struct { int err; int pad; unsigned long long nulls; } h;
+      ctx->d2h_sync(&h, flags->ptr, 16);
+      if (h.err) throw_eval_error(h.err);
+      col->null_count = (int64_t)h.nulls;
+    }
+    if (col->null_count == 0) col->validity.reset();
+    if (col->null_count > 0 && a.op == QGPU_AGG_SUM && produced.is_decimal() && ctx->compat_empty_decimal_sum)
+      throw_arrow("column types must match schema types, expected " + produced.str() + " but found Decimal128(38, 10)");
+    if (col->null_count > 0 && (a.op == QGPU_AGG_MIN || a.op == QGPU_AGG_MAX) && ctx->compat_empty_decimal_sum)
+      throw_arrow("column types must match schema types, expected " + produced.str() + " but found Null");
+    out.cols.push_back({col, grouped ? order : nullptr});
+  }
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// hash join
+// ------------------------------------------------------------------------------------------------
+Schema build_join_schema(const Schema& left, const Schema& right, int join_type) {
+  // join/mod.rs:26-123
+  static const std::string KEY = "qurious.field_qualifiers";
+  const std::string SEP = "\x1f";
+  Schema out;
+  if (join_type == QGPU_JOIN_LEFT_SEMI || join_type == QGPU_JOIN_LEFT_ANTI) {
+    out.fields = left.fields;
+    out.metadata = left.metadata;
+    return out;
+  }
+  bool ln = false, rn = false;
+  switch (join_type) {
+    case QGPU_JOIN_LEFT: rn = true; break;
+    case QGPU_JOIN_RIGHT: ln = true; break;
+    case QGPU_JOIN_FULL: ln = rn = true; break;
+    default: break;
+  }
+  for (Field f : left.fields) {
+    if (ln) f.nullable = true;
+    out.fields.push_back(f);
+  }
+  for (Field f : right.fields) {
+    if (rn) f.nullable = true;
+    out.fields.push_back(f);
+  }
+  auto parts = [&](const Schema& s) {
+    std::string q;
+    std::vector<std::string> p;
+    size_t nf = s.fields.size();
+    if (!metadata_get(s.metadata, KEY, &q)) {
+      p.assign(nf, "");
+      return p;
+    }
+    size_t pos = 0;
+    while (true) {
+      size_t e = q.find(SEP, pos);
+      if (e == std::string::npos) {
+        p.push_back(q.substr(pos));
+        break;
+      }
+      p.push_back(q.substr(pos, e - pos));
+      pos = e + 1;
+    }
+    if (p.size() != nf) p.assign(nf, "");
+    return p;
+  };
+  std::vector<std::string> lp = parts(left), rp = parts(right);
+  std::string combined;
+  bool first = true;
+  for (auto* v : {&lp, &rp})
+    for (auto& s : *v) {
+      if (!first) combined += SEP;
+      combined += s;
+      first = false;
+    }
+  out.metadata = merge_metadata(left.metadata, KEY, combined);
+  return out;
+}
+
+// rows of each key group, ascending (hash_join.rs:53-64 inserts in reverse so chains ascend)
+__global__ void k_group_count(const uint32_t* __restrict__ row_gid, int64_t n, long long* __restrict__ counts) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint32_t g = row_gid[i];
+    if (g != NO_GROUP) atomicAdd((unsigned long long*)&counts[g], 1ull);
+  }
+}
+__global__ void k_group_fill(const uint32_t* __restrict__ row_gid, int64_t n, const long long* __restrict__ starts,
+                             unsigned long long* __restrict__ cursor, long long* __restrict__ rows) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint32_t g = row_gid[i];
+    if (g != NO_GROUP) rows[starts[g] + (long long)atomicAdd(&cursor[g], 1ull)] = i;
+  }
+}
+__device__ void sift_down(long long* a, int64_t start, int64_t end) {
+  int64_t root = start;
+  while (2 * root + 1 <= end) {
+    int64_t child = 2 * root + 1, sw = root;
+    if (a[sw] < a[child]) sw = child;
+    if (child + 1 <= end && a[sw] < a[child + 1]) sw = child + 1;
+    if (sw == root) return;
+    long long t = a[root];
+    a[root] = a[sw];
+    a[sw] = t;
+    root = sw;
+  }
+}
+__global__ void k_group_sort(const long long* __restrict__ starts, const long long* __restrict__ counts, int64_t n_groups,
+                             long long* __restrict__ rows) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += stride) {
+    const int64_t c = counts[g];
+    if (c < 2) continue;
+    long long* a = rows + starts[g];
+    if (c <= 24) {
+      for (int64_t i = 1; i < c; ++i) {
+        long long x = a[i];
+        int64_t j = i - 1;
+        while (j >= 0 && a[j] > x) {
+          a[j + 1] = a[j];
+          --j;
+        }
+        a[j + 1] = x;
+      }
+    } else {  // heapsort: O(c log c), in place
+      for (int64_t s = (c - 2) / 2; s >= 0; --s) sift_down(a, s, c - 1);
+      for (int64_t e = c - 1; e > 0; --e) {
+        long long t = a[e];
+        a[e] = a[0];
+        a[0] = t;
+        sift_down(a, 0, e - 1);
+      }
+    }
+  }
+}
+
+// probe: find the build key group of every probe row
+__global__ void __launch_bounds__(256) k_probe_lookup(const Program* __restrict__ build_progs,
+                                                      const Program* __restrict__ probe_progs, int n_keys, KeyClasses kc,
+                                                      const unsigned long long* __restrict__ slots,
+                                                      const uint32_t* __restrict__ slot_gid, uint64_t cap_mask,
+                                                      const long long* __restrict__ group_counts, int64_t n,
+                                                      uint32_t* __restrict__ probe_gid, long long* __restrict__ match_counts,
+                                                      int* __restrict__ err) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Program* PB = (Program*)smem_raw;
+  Program* PP = PB + n_keys;
+  {
+    const int words = (int)(sizeof(Program) / 4) * n_keys;
+    for (int i = threadIdx.x; i < words; i += blockDim.x) {
+      ((uint32_t*)PB)[i] = ((const uint32_t*)build_progs)[i];
+      ((uint32_t*)PP)[i] = ((const uint32_t*)probe_progs)[i];
+    }
+    __syncthreads();
+  }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride) {
+    Val k[MAX_KEYS];
+    uint64_t h = 0x243f6a8885a308d3ULL;
+    bool anynull = false;
+    for (int i = 0; i < n_keys; ++i) {
+      k[i] = eval_row(PP[i], row, err);
+      anynull |= !k[i].valid;
+      h = hash_val(h, k[i], kc.c[i]);
+    }
+    uint32_t g = NO_GROUP;
+    if (!anynull && slots) {
+      const uint32_t h32 = (uint32_t)(h >> 32);
+      uint64_t slot = h & cap_mask;
+      while (true) {
+        const unsigned long long cur = slots[slot];
+        if (cur == 0) break;
+        if ((uint32_t)(cur >> 32) == h32) {
+          const int64_t rep = (int64_t)(cur & 0xffffffffull) - 1;
+          bool eq = true;
+          for (int i = 0; i < n_keys && eq; ++i) {
+            Val o = eval_row(PB[i], rep, err);
+            eq = vals_equal(k[i], o, kc.c[i]);
+          }
+          if (eq) {
+            g = slot_gid[slot];
+            break;
+          }
+        }
+        slot = (slot + 1) & cap_mask;
+      }
+    }
+    probe_gid[row] = g;
+    match_counts[row] = g == NO_GROUP ? 0 : group_counts[g];
+  }
+}
+
+__global__ void k_probe_fill(const uint32_t* __restrict__ probe_gid, const long long* __restrict__ pair_off,
+                             const long long* __restrict__ group_starts, const long long* __restrict__ group_counts,
+                             const long long* __restrict__ group_rows, int64_t n, long long* __restrict__ out_build,
+                             long long* __restrict__ out_probe) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride) {
+    const uint32_t g = probe_gid[row];
+    if (g == NO_GROUP) continue;
+    const long long c = group_counts[g], s = group_starts[g], o = pair_off[row];
+    for (long long j = 0; j < c; ++j) {
+      out_build[o + j] = group_rows[s + j];
+      out_probe[o + j] = row;
+    }
+  }
+}
+
+__global__ void k_mark_visited(const long long* __restrict__ build_idx, int64_t n, uint32_t* __restrict__ visited) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    long long b = build_idx[i];
+    if (b >= 0) atomicOr(&visited[b >> 5], 1u << (b & 31));
+  }
+}
+__global__ void k_count_per_probe(const long long* __restrict__ probe_idx, int64_t n, long long* __restrict__ counts) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    atomicAdd((unsigned long long*)&counts[probe_idx[i]], 1ull);
+}
+__global__ void k_out_counts(const long long* __restrict__ counts, int64_t n, long long* __restrict__ out_counts) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out_counts[i] = counts[i] > 0 ? counts[i] : 1;
+}
+// adjust_right_indices (join/mod.rs:176-207): unmatched probe rows appear once, in order, with a NULL build row
+__global__ void k_right_fill(const long long* __restrict__ counts, const long long* __restrict__ pair_off,
+                             const long long* __restrict__ out_off, const long long* __restrict__ build_idx, int64_t n_probe,
+                             long long* __restrict__ out_build, long long* __restrict__ out_probe) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n_probe; row += stride) {
+    const long long c = counts[row], o = out_off[row];
+    if (c == 0) {
+      out_build[o] = -1;
+      out_probe[o] = row;
+    } else {
+      const long long p = pair_off[row];
+      for (long long j = 0; j < c; ++j) {
+        out_build[o + j] = build_idx[p + j];
+        out_probe[o + j] = row;
+      }
+    }
+  }
+}
+__global__ void k_bits_to_counts(const uint32_t* __restrict__ bits, int64_t n, int invert, uint32_t* __restrict__ keep,
+                                 long long* __restrict__ counts) {
+  const int64_t n_words = (n + 31) >> 5;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+    uint32_t v = bits[w];
+    if (invert) v = ~v;
+    if (w == n_words - 1 && (n & 31)) v &= (1u << (n & 31)) - 1u;
+    keep[w] = v;
+    counts[w] = __popc(v);
+  }
+}
+__global__ void k_select_bits(const uint32_t* __restrict__ keep, const long long* __restrict__ offs, long long* __restrict__ sel,
+                              int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride) {
+    const uint32_t wv = keep[row >> 5];
+    const int b = (int)(row & 31);
+    if ((wv >> b) & 1u) sel[offs[row >> 5] + __popc(wv & ((1u << b) - 1u))] = row;
+  }
+}
+__global__ void k_fill_i64(long long* p, int64_t n, long long v) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+__global__ void k_gather_i64(const long long* __restrict__ src, const long long* __restrict__ idx, long long* __restrict__ dst,
+                             int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[idx[i]];
+}
+
+static IdxP make_idx(Ctx* ctx, int64_t n, bool may_null) {
+  auto r = std::make_shared<IdxVec>();
+  r->length = n;
+  r->may_have_null = may_null;
+  r->buf = ctx->alloc(std::max<size_t>((size_t)n * 8, 8));
+  return r;
+}
+
+static IdxP concat_idx(Ctx* ctx, const IdxP& a, const IdxP& b) {
+  IdxP r = make_idx(ctx, a->length + b->length, a->may_have_null || b->may_have_null);
+  if (a->length) CUDA_CHECK(cudaMemcpyAsync(r->buf->ptr, a->buf->ptr, (size_t)a->length * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (b->length)
+    CUDA_CHECK(cudaMemcpyAsync((char*)r->buf->ptr + a->length * 8, b->buf->ptr, (size_t)b->length * 8, cudaMemcpyDeviceToDevice,
+                               ctx->stream));
+  return r;
+}
+
+View run_hash_join(Ctx* ctx, const View& build, const View& probe, int join_type,
+                   std::vector<std::shared_ptr<Compiled>>& left_on, std::vector<std::shared_ptr<Compiled>>& right_on,
+                   JoinFilterSpec* filter, const Schema& out_schema) {
+  const int64_t nb = build.num_rows, np = probe.num_rows;
+  const int nk = (int)left_on.size();
+  if (nk == 0) throw_internal("On constraints in HashJoinExec should be non-empty");
+  if (np >= 0xfffffff0LL) throw_internal("probe side larger than u32 row indices (hash_join.rs:70-71 uses u32 too)");
+  for (int i = 0; i < nk; ++i) {
+    check_hash_key_type(left_on[i]->result_type);
+    check_hash_key_type(right_on[i]->result_type);
+    if (left_on[i]->result_type != right_on[i]->result_type)
+      throw_arrow("Invalid comparison operation: " + left_on[i]->result_type.str() + " == " + right_on[i]->result_type.str());
+  }
+  // ---- build -------------------------------------------------------------------------------------
+  DBufP build_progs;
+  KeyTable kt = build_key_table(ctx, build, left_on, true, &build_progs);
+  const int64_t ng = kt.n_groups;
+  DBufP g_counts = ctx->alloc_zero((size_t)std::max<int64_t>(ng, 1) * 8);
+  DBufP g_starts = ctx->alloc_zero((size_t)std::max<int64_t>(ng, 1) * 8);
+  DBufP g_rows = ctx->alloc((size_t)std::max<int64_t>(nb, 1) * 8);
+  if (nb > 0 && ng > 0) {
+    LAUNCH(ctx, k_group_count, grid_for(ctx, nb, 256), 256, 0, (const uint32_t*)kt.row_gid->ptr, nb, (long long*)g_counts->ptr);
+    exclusive_scan_i64(ctx, (const int64_t*)g_counts->ptr, (int64_t*)g_starts->ptr, ng);
+    DBufP cursor = ctx->alloc_zero((size_t)ng * 8);
+    LAUNCH(ctx, k_group_fill, grid_for(ctx, nb, 256), 256, 0, (const uint32_t*)kt.row_gid->ptr, nb,
+           (const long long*)g_starts->ptr, (unsigned long long*)cursor->ptr, (long long*)g_rows->ptr);
+    LAUNCH(ctx, k_group_sort, grid_for(ctx, ng, 128), 128, 0, (const long long*)g_starts->ptr, (const long long*)g_counts->ptr,
+           ng, (long long*)g_rows->ptr);
+  }
+  // ---- probe -------------------------------------------------------------------------------------
+  IdxP b_idx = make_idx(ctx, 0, false), p_idx = make_idx(ctx, 0, false);
+  if (np > 0) {
+    KeyClasses kc;
+    memset(&kc, 0, sizeof(kc));
+    std::vector<Program> pp;
+    for (int i = 0; i < nk; ++i) {
+      if (right_on[i]->deferred_err) throw_eval_error(right_on[i]->deferred_err);
+      kc.c[i] = (uint8_t)class_of(right_on[i]->result_type);
+      pp.push_back(bind_program(ctx, *right_on[i], probe));
+    }
+    DBufP probe_progs = upload_programs(ctx, pp);
+    DBufP probe_gid = ctx->alloc((size_t)np * 4);
+    DBufP m_counts = ctx->alloc((size_t)np * 8);
+    DBufP pair_off = ctx->alloc((size_t)np * 8);
+    DBufP err = ctx->alloc_zero(4);
+    const size_t smem = 2 * (size_t)nk * sizeof(Program);
+    set_dyn_smem(k_probe_lookup, smem);
+    LAUNCH(ctx, k_probe_lookup, grid_for(ctx, np, 256), 256, smem, (const Program*)build_progs->ptr,
+           (const Program*)probe_progs->ptr, nk, kc, kt.slots ? (const unsigned long long*)kt.slots->ptr : nullptr,
+           kt.slot_gid ? (const uint32_t*)kt.slot_gid->ptr : nullptr, (uint64_t)(kt.capacity - 1),
+           (const long long*)g_counts->ptr, np, (uint32_t*)probe_gid->ptr, (long long*)m_counts->ptr, (int*)err->ptr);
+    int64_t total = exclusive_scan_i64(ctx, (const int64_t*)m_counts->ptr, (int64_t*)pair_off->ptr, np);
+    int e = ctx->read_scalar((const int*)err->ptr);
+    if (e) throw_eval_error(e);
+    b_idx = make_idx(ctx, total, false);
+    p_idx = make_idx(ctx, total, false);
+    if (total > 0)
+      LAUNCH(ctx, k_probe_fill, grid_for(ctx, np, 256), 256, 0, (const uint32_t*)probe_gid->ptr, (const long long*)pair_off->ptr,
+             (const long long*)g_starts->ptr, (const long long*)g_counts->ptr, (const long long*)g_rows->ptr, np,
+             (long long*)b_idx->buf->ptr, (long long*)p_idx->buf->ptr);
+    // ---- JoinFilter (join/mod.rs:125-154) ------------------------------------------------------------
+    if (filter && total > 0) {
+      View inter;
+      inter.schema = filter->schema;
+      inter.num_rows = total;
+      std::vector<std::pair<IdxP, IdxP>> cb, cp;
+      for (size_t i = 0; i < filter->column_index.size(); ++i) {
+        const bool left = filter->column_side[i] == 0;
+        const View& src = left ? build : probe;
+        int ci = filter->column_index[i];
+        if (ci < 0 || ci >= (int)src.cols.size()) throw_internal("join filter column index out of range");
+        inter.cols.push_back(apply_selection(ctx, src.cols[ci], left ? b_idx : p_idx, left ? &cb : &cp));
+      }
+      IdxP sel = eval_filter(ctx, *filter->expr, inter);
+      IdxP nb_idx = make_idx(ctx, sel->length, false), np_idx = make_idx(ctx, sel->length, false);
+      if (sel->length > 0) {
+        LAUNCH(ctx, k_gather_i64, grid_for(ctx, sel->length, 256), 256, 0, (const long long*)b_idx->buf->ptr,
+               (const long long*)sel->buf->ptr, (long long*)nb_idx->buf->ptr, sel->length);
+        LAUNCH(ctx, k_gather_i64, grid_for(ctx, sel->length, 256), 256, 0, (const long long*)p_idx->buf->ptr,
+               (const long long*)sel->buf->ptr, (long long*)np_idx->buf->ptr, sel->length);
+      }
+      b_idx = nb_idx;
+      p_idx = np_idx;
+    }
+  }
+  // ---- visited bitmap on the build side (hash_join.rs:253-255) ---------------------------------------
+  const int64_t nb_words = (nb + 31) >> 5;
+  DBufP visited = ctx->alloc_zero(std::max<size_t>((size_t)nb_words * 4, 4));
+  if (b_idx->length > 0)
+    LAUNCH(ctx, k_mark_visited, grid_for(ctx, b_idx->length, 256), 256, 0, (const long long*)b_idx->buf->ptr, b_idx->length,
+           (uint32_t*)visited->ptr);
+  // ---- adjust_indices_by_join_type (join/mod.rs:156-207) ---------------------------------------------
+  if ((join_type == QGPU_JOIN_RIGHT || join_type == QGPU_JOIN_FULL) && np > 0) {
+    DBufP counts = ctx->alloc_zero((size_t)np * 8);
+    DBufP pair_off = ctx->alloc((size_t)np * 8);
+    DBufP out_counts = ctx->alloc((size_t)np * 8);
+    DBufP out_off = ctx->alloc((size_t)np * 8);
+    if (p_idx->length > 0)
+      LAUNCH(ctx, k_count_per_probe, grid_for(ctx, p_idx->length, 256), 256, 0, (const long long*)p_idx->buf->ptr, p_idx->length,
+             (long long*)counts->ptr);
+    exclusive_scan_i64(ctx, (const int64_t*)counts->ptr, (int64_t*)pair_off->ptr, np);
+    LAUNCH(ctx, k_out_counts, grid_for(ctx, np, 256), 256, 0, (const long long*)counts->ptr, np, (long long*)out_counts->ptr);
+    int64_t total = exclusive_scan_i64(ctx, (const int64_t*)out_counts->ptr, (int64_t*)out_off->ptr, np);
+    IdxP ob = make_idx(ctx, total, true), op = make_idx(ctx, total, false);
+    LAUNCH(ctx, k_right_fill, grid_for(ctx, np, 256), 256, 0, (const long long*)counts->ptr, (const long long*)pair_off->ptr,
+           (const long long*)out_off->ptr, (const long long*)b_idx->buf->ptr, np, (long long*)ob->buf->ptr,
+           (long long*)op->buf->ptr);
+    b_idx = ob;
+    p_idx = op;
+  }
+  bool emit_probe_phase = !(join_type == QGPU_JOIN_LEFT_SEMI || join_type == QGPU_JOIN_LEFT_ANTI);
+  if (!emit_probe_phase) {
+    b_idx = make_idx(ctx, 0, false);
+    p_idx = make_idx(ctx, 0, false);
+  }
+  // ---- final build-side batch (hash_join.rs:277-342,374-381) -----------------------------------------
+  bool final_batch = false;
+  int invert = 1;
+  if (join_type == QGPU_JOIN_LEFT || join_type == QGPU_JOIN_FULL || join_type == QGPU_JOIN_LEFT_ANTI) final_batch = true;
+  if (join_type == QGPU_JOIN_LEFT_SEMI) {
+    final_batch = true;
+    invert = 0;
+  }
+  if (final_batch && nb > 0) {
+    DBufP keep = ctx->alloc((size_t)nb_words * 4);
+    DBufP counts = ctx->alloc((size_t)nb_words * 8);
+    DBufP offs = ctx->alloc((size_t)nb_words * 8);
+    LAUNCH(ctx, k_bits_to_counts, grid_for(ctx, nb_words, 256), 256, 0, (const uint32_t*)visited->ptr, nb, invert,
+           (uint32_t*)keep->ptr, (long long*)counts->ptr);
+    int64_t total = exclusive_scan_i64(ctx, (const int64_t*)counts->ptr, (int64_t*)offs->ptr, nb_words);
+    if (total > 0) {
+      IdxP fb = make_idx(ctx, total, false), fp = make_idx(ctx, total, true);
+      LAUNCH(ctx, k_select_bits, grid_for(ctx, nb, 256), 256, 0, (const uint32_t*)keep->ptr, (const long long*)offs->ptr,
+             (long long*)fb->buf->ptr, nb);
+      LAUNCH(ctx, k_fill_i64, grid_for(ctx, total, 256), 256, 0, (long long*)fp->buf->ptr, total, (long long)-1);
+      b_idx = concat_idx(ctx, b_idx, fb);
+      p_idx = concat_idx(ctx, p_idx, fp);
+    }
+  }
+  // ---- output view: late materialisation -- only index vectors were produced ---------------------------
+  View out;
+  out.schema = out_schema;
+  out.num_rows = b_idx->length;
+  out.num_batches = (out.num_rows > 0 || final_batch) ? 1 : 0;  // hash_join.rs:369-371 drops empty probe outputs
+  std::vector<std::pair<IdxP, IdxP>> cb, cp;
+  for (const LazyCol& c : build.cols) out.cols.push_back(apply_selection(ctx, c, b_idx, &cb));
+  if (!(join_type == QGPU_JOIN_LEFT_SEMI || join_type == QGPU_JOIN_LEFT_ANTI))
+    for (const LazyCol& c : probe.cols) out.cols.push_back(apply_selection(ctx, c, p_idx, &cp));
+  if (out.cols.size() != out_schema.fields.size()) throw_internal("join output schema mismatch");
+  return out;
+}
+
+}  // namespace qgpu

@@ -1,0 +1,50 @@
+// Operator implementations (generic, interpreter driven).  Fused fast paths live in fused.cu.
+#pragma once
+#include "expr.h"
+#include "kernels.h"
+
+namespace qgpu {
+
+struct AggSpec {
+  int op = 0;  // qgpu_agg_op
+  std::shared_ptr<Compiled> arg;
+  DType return_type;
+  DType expr_type;
+};
+
+// HashAggregate / NoGroupingAggregate (keys.empty()).  SURVEY 8a a7,a8,a10-a13.
+View run_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<Compiled>>& keys, std::vector<AggSpec>& aggs,
+                   const Schema& out_schema);
+
+struct JoinFilterSpec {
+  std::shared_ptr<Compiled> expr;  // compiled against `schema`
+  Schema schema;
+  std::vector<int> column_index;
+  std::vector<int> column_side;  // 0 = Left/build, 1 = Right/probe
+};
+
+// HashJoinExec::execute.  SURVEY 8a a14, a15.
+View run_hash_join(Ctx* ctx, const View& build, const View& probe, int join_type,
+                   std::vector<std::shared_ptr<Compiled>>& left_on, std::vector<std::shared_ptr<Compiled>>& right_on,
+                   JoinFilterSpec* filter, const Schema& out_schema);
+
+Schema build_join_schema(const Schema& left, const Schema& right, int join_type);
+
+// validation helpers shared with the fused paths
+void validate_agg_types(const std::vector<AggSpec>& aggs);
+void check_hash_key_type(const DType& t);
+
+// ---- shared device hash-table machinery (ops.cu) ----------------------------------------------
+struct KeyTable {
+  DBufP slots;     // u64 per slot: (hash32 << 32) | (rep_row + 1); 0 = empty
+  DBufP slot_gid;  // u32 per slot
+  DBufP gid_rep;   // i64 per group: representative row (CAS winner)
+  DBufP row_gid;   // u32 per input row: group id, 0xffffffff = no group (NULL key, joins only)
+  int64_t capacity = 0;
+  int64_t n_groups = 0;
+};
+// Group the rows of `v` by key equality.  skip_null_keys: rows with any NULL key get no group (joins).
+KeyTable build_key_table(Ctx* ctx, const View& v, std::vector<std::shared_ptr<Compiled>>& keys, bool skip_null_keys,
+                         DBufP* key_programs_out);
+
+}  // namespace qgpu

@@ -1,0 +1,652 @@
+// Plan execution + table consolidation + the extern "C" surface declared in include/qgpu.h.
+#include <cstring>
+
+#include "plan.h"
+
+using namespace qgpu;
+
+namespace qgpu {
+
+// ------------------------------------------------------------------------------------------------
+// table consolidation: appended batches -> one contiguous column each
+// ------------------------------------------------------------------------------------------------
+__global__ void k_widen_chunk(const int64_t* __restrict__ src, ulonglong2* __restrict__ dst, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int64_t x = src[i];
+    dst[i] = make_ulonglong2((uint64_t)x, x < 0 ? ~0ull : 0ull);
+  }
+}
+
+void TableImpl::consolidate() {
+  if (consolidated) return;
+  const size_t nf = schema.fields.size();
+  cols.assign(nf, nullptr);
+  for (size_t f = 0; f < nf; ++f) {
+    std::vector<DColP> parts;
+    bool missing = false;
+    for (auto& ch : chunks) {
+      if (!ch.cols[f]) missing = true;
+      else parts.push_back(ch.cols[f]);
+    }
+    if (parts.empty()) continue;
+    if (missing) throw_internal("column '" + schema.fields[f].name + "' was uploaded for some batches only");
+    if (parts.size() == 1) {
+      cols[f] = parts[0];
+      continue;
+    }
+    auto out = std::make_shared<DCol>();
+    out->type = schema.fields[f].type;
+    out->length = num_rows;
+    Phys phys = parts[0]->phys;
+    bool any_valid_buf = false, all_null_phys = true;
+    for (auto& p : parts) {
+      if (p->phys == PH_I128) phys = PH_I128;  // one wide chunk forces the wide layout
+      if (p->validity) any_valid_buf = true;
+      if (p->phys != PH_NULL) all_null_phys = false;
+      out->null_count += p->null_count;
+      out->str_bytes += p->str_bytes;
+    }
+    if (all_null_phys) {
+      out->phys = PH_NULL;
+      out->null_count = num_rows;
+      cols[f] = out;
+      continue;
+    }
+    if (phys == PH_NULL) phys = parts.back()->phys;
+    for (auto& p : parts)
+      if (p->phys != PH_NULL && p->phys != phys && !(p->phys == PH_D64 && phys == PH_I128) && !(p->phys == PH_I128 && phys == PH_D64))
+        throw_internal("inconsistent chunk layouts");
+    for (auto& p : parts)
+      if (p->phys == PH_I128) phys = PH_I128;
+    out->phys = phys;
+    const int w = phys_width(phys);
+    const int64_t n_words = (num_rows + 31) >> 5;
+    if (phys == PH_BIT) out->data = ctx->alloc_zero((size_t)n_words * 4 + 4);
+    else if (phys == PH_STR) {
+      if (out->str_bytes > 2147483647LL) throw_arrow("Utf8 column exceeds 2 GiB of string data; LargeUtf8 is not supported");
+      out->data = ctx->alloc(std::max<size_t>((size_t)out->str_bytes, 4));
+      out->offsets = ctx->alloc_zero((size_t)(num_rows + 1) * 4);
+    } else {
+      out->data = ctx->alloc(std::max<size_t>((size_t)num_rows * w, 16));
+    }
+    if (any_valid_buf || out->null_count > 0) out->validity = ctx->alloc_zero((size_t)n_words * 4 + 4);
+    int64_t row = 0, byte = 0;
+    bool stats_ok = true;
+    i128 mn = 0, mx = 0;
+    bool first_stats = true;
+    for (auto& p : parts) {
+      const int64_t n = p->length;
+      if (n == 0) continue;
+      if (out->validity) {
+        if (p->phys == PH_NULL) fill_bits(ctx, (uint32_t*)out->validity->ptr, row, n, false);
+        else if (p->validity) copy_bits(ctx, (uint32_t*)out->validity->ptr, row, (const uint32_t*)p->validity->ptr, 0, n);
+        else fill_bits(ctx, (uint32_t*)out->validity->ptr, row, n, true);
+      }
+      if (p->phys == PH_NULL) {
+        if (phys == PH_STR) {
+          // offsets of NULL rows all equal the running byte offset
+          std::vector<int32_t> o((size_t)n + 1, (int32_t)byte);
+          ctx->h2d((int32_t*)out->offsets->ptr + row, o.data(), o.size() * 4);
+          ctx->sync();
+        } else if (phys != PH_BIT) {
+          CUDA_CHECK(cudaMemsetAsync((char*)out->data->ptr + row * w, 0, (size_t)n * w, ctx->stream));
+        }
+      } else if (phys == PH_BIT) {
+        copy_bits(ctx, (uint32_t*)out->data->ptr, row, (const uint32_t*)p->data->ptr, 0, n);
+      } else if (phys == PH_STR) {
+        rebase_offsets(ctx, (int32_t*)out->offsets->ptr + row, (const int32_t*)p->offsets->ptr, n + 1, byte);
+        if (p->str_bytes > 0)
+          CUDA_CHECK(cudaMemcpyAsync((char*)out->data->ptr + byte, p->data->ptr, (size_t)p->str_bytes, cudaMemcpyDeviceToDevice,
+                                     ctx->stream));
+        byte += p->str_bytes;
+      } else if (p->phys == PH_D64 && phys == PH_I128) {
+        int g = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+        k_widen_chunk<<<g, 256, 0, ctx->stream>>>((const int64_t*)p->data->ptr, (ulonglong2*)out->data->ptr + row, n);
+        ctx->launches++;
+        CUDA_CHECK(cudaGetLastError());
+      } else {
+        CUDA_CHECK(cudaMemcpyAsync((char*)out->data->ptr + row * w, p->data->ptr, (size_t)n * w, cudaMemcpyDeviceToDevice,
+                                   ctx->stream));
+      }
+      if (p->has_stats) {
+        if (first_stats) {
+          mn = p->vmin;
+          mx = p->vmax;
+          first_stats = false;
+        } else {
+          mn = std::min(mn, p->vmin);
+          mx = std::max(mx, p->vmax);
+        }
+      } else if (p->null_count != p->length) {
+        stats_ok = false;
+      }
+      row += n;
+    }
+    if (stats_ok && !first_stats) {
+      out->has_stats = true;
+      out->vmin = mn;
+      out->vmax = mx;
+    }
+    if (out->null_count == 0) out->validity.reset();
+    cols[f] = out;
+  }
+  ctx->sync();
+  chunks.clear();
+  consolidated = true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// execution
+// ------------------------------------------------------------------------------------------------
+static View scan_view(PlanNode& n) {
+  TableImpl& t = *n.table;
+  t.consolidate();
+  View v;
+  v.num_rows = t.num_rows;
+  v.num_batches = t.num_batches;
+  if (n.has_projection) {
+    for (int ci : n.projection) {
+      if (ci < 0 || ci >= (int)t.schema.fields.size()) throw_arrow("Schema error: projection index out of bounds");
+      v.schema.fields.push_back(t.schema.fields[ci]);
+      v.cols.push_back({t.cols[ci], nullptr});
+    }
+    v.schema.metadata = t.schema.metadata;
+  } else {
+    v.schema = t.schema;
+    for (auto& c : t.cols) v.cols.push_back({c, nullptr});
+  }
+  return v;
+}
+
+View PlanNode::execute() {
+  switch (kind) {
+    case PK_SCAN: {
+      View v = scan_view(*this);
+      strategy = "scan";
+      if (predicate) {
+        auto c = compile_expr(*predicate, v.schema);
+        IdxP sel = eval_filter(ctx, *c, v);
+        v = apply_selection_view(ctx, v, sel);
+        strategy = "scan+filter(selection-vector)";
+      }
+      return v;
+    }
+    case PK_FILTER: {
+      View in = children[0]->execute();
+      auto c = compile_expr(*predicate, in.schema);
+      IdxP sel = eval_filter(ctx, *c, in);
+      strategy = "filter(selection-vector)";
+      return apply_selection_view(ctx, in, sel);
+    }
+    case PK_PROJECTION: {
+      View in = children[0]->execute();
+      View out;
+      out.schema = schema;
+      out.num_rows = in.num_rows;
+      out.num_batches = in.num_batches;
+      if (exprs.size() != schema.fields.size()) throw_arrow("number of columns must match number of fields in schema");
+      for (size_t i = 0; i < exprs.size(); ++i) {
+        auto c = compile_expr(*exprs[i], in.schema);
+        if (in.num_batches > 0 && c->result_type != schema.fields[i].type)
+          throw_arrow("column types must match schema types, expected " + schema.fields[i].type.str() + " but found " +
+                      c->result_type.str() + " at column index " + std::to_string(i));
+        if (c->is_column_ref) out.cols.push_back(in.cols[c->column_ref]);
+        else out.cols.push_back({eval_to_column(ctx, *c, in), nullptr});
+      }
+      strategy = "projection";
+      return out;
+    }
+    case PK_AGGREGATE: {
+      View fused;
+      if (try_fused_scan_aggregate(*this, &fused)) return fused;
+      View in = children[0]->execute();
+      std::vector<std::shared_ptr<Compiled>> keys;
+      for (auto& e : group_exprs) keys.push_back(compile_expr(*e, in.schema));
+      std::vector<AggSpec> specs;
+      for (auto& a : aggs) {
+        AggSpec s;
+        s.op = a.op;
+        s.arg = compile_expr(*a.expr, in.schema);
+        s.return_type = a.return_type;
+        s.expr_type = a.expr_type;
+        specs.push_back(s);
+      }
+      strategy = group_exprs.empty() ? "generic-no-grouping-aggregate" : "generic-hash-aggregate";
+      return run_aggregate(ctx, in, keys, specs, schema);
+    }
+    case PK_HASH_JOIN: {
+      View l = children[0]->execute();
+      View r = children[1]->execute();
+      std::vector<std::shared_ptr<Compiled>> lo, ro;
+      for (auto& e : left_on) lo.push_back(compile_expr(*e, l.schema));
+      for (auto& e : right_on) ro.push_back(compile_expr(*e, r.schema));
+      JoinFilterSpec fs;
+      if (has_join_filter) {
+        fs.schema = join_filter_schema;
+        fs.column_index = join_filter_index;
+        fs.column_side = join_filter_side;
+        fs.expr = compile_expr(*join_filter_expr, join_filter_schema);
+      }
+      strategy = "generic-hash-join(late-materialisation)";
+      return run_hash_join(ctx, l, r, join_type, lo, ro, has_join_filter ? &fs : nullptr, schema);
+    }
+  }
+  throw_internal("unknown plan node");
+}
+
+static std::vector<DColP> materialize_view(Ctx* ctx, const View& v) {
+  std::vector<DColP> cols;
+  for (size_t i = 0; i < v.cols.size(); ++i) {
+    if (!v.cols[i].base)
+      throw_internal("column '" + v.schema.fields[i].name + "' must be returned but was not uploaded to the GPU table");
+    cols.push_back(materialize_arrow(ctx, v.cols[i], v.num_rows));
+  }
+  return cols;
+}
+
+}  // namespace qgpu
+
+// ================================================================================================
+// extern "C"
+// ================================================================================================
+static thread_local std::string g_last_error = "";
+
+template <typename F>
+static int guard(Ctx* ctx, F&& f) {
+  try {
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) throw QError(QGPU_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
+    f();
+    return QGPU_OK;
+  } catch (QError& e) {
+    ctx->last_error = e.what();
+    cudaGetLastError();
+    return e.code;
+  } catch (std::bad_alloc&) {
+    ctx->last_error = "out of host memory";
+    return QGPU_ERR_OOM;
+  } catch (std::exception& e) {
+    ctx->last_error = std::string("InternalError: ") + e.what();
+    return QGPU_ERR_INTERNAL;
+  }
+}
+
+extern "C" {
+
+int qgpu_init(const int* devices, int n, qgpu_ctx** out) {
+  if (!out) return QGPU_ERR_INTERNAL;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_last_error = std::string("CUDA error: no CUDA device available (") + cudaGetErrorString(e) +
+                   "); libqgpu has no CPU fallback";
+    cudaGetLastError();
+    return QGPU_ERR_CUDA;
+  }
+  int dev = (devices && n > 0) ? devices[0] : 0;
+  if (n > 1) {
+    g_last_error = "InternalError: one qgpu_ctx drives one GPU (one process per GPU); create one context per device";
+    return QGPU_ERR_INTERNAL;
+  }
+  if (dev < 0 || dev >= count) {
+    g_last_error = "InternalError: invalid CUDA device ordinal " + std::to_string(dev);
+    return QGPU_ERR_INTERNAL;
+  }
+  qgpu_ctx* h = new qgpu_ctx();
+  Ctx* c = &h->c;
+  c->device = dev;
+  try {
+    CUDA_CHECK(cudaSetDevice(dev));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaDeviceGetDefaultMemPool(&c->pool, dev));
+    uint64_t thr = UINT64_MAX;
+    CUDA_CHECK(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    c->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < Ctx::kStageSlots; ++i) {
+      CUDA_CHECK(cudaHostAlloc(&c->stage[i], c->stage_bytes, cudaHostAllocDefault));
+      CUDA_CHECK(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
+    }
+    CUDA_CHECK(cudaHostAlloc(&c->pinned_scratch, c->pinned_scratch_bytes, cudaHostAllocDefault));
+  } catch (QError& err) {
+    g_last_error = err.what();
+    delete h;
+    return err.code;
+  }
+  *out = h;
+  return QGPU_OK;
+}
+
+void qgpu_shutdown(qgpu_ctx* ctx) {
+  if (!ctx) return;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->copy_stream);
+  for (int i = 0; i < Ctx::kStageSlots; ++i) {
+    if (c->stage[i]) cudaFreeHost(c->stage[i]);
+    if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
+  }
+  if (c->pinned_scratch) cudaFreeHost(c->pinned_scratch);
+  cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->copy_stream);
+  delete ctx;
+}
+
+const char* qgpu_last_error(const qgpu_ctx* ctx) { return ctx ? ctx->c.last_error.c_str() : g_last_error.c_str(); }
+
+int qgpu_set_compat(qgpu_ctx* ctx, const char* name, int value) {
+  if (!ctx || !name) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] {
+    std::string s(name);
+    if (s == "avg_precision") ctx->c.compat_avg_precision = value != 0;
+    else if (s == "empty_decimal_sum") ctx->c.compat_empty_decimal_sum = value != 0;
+    else throw_internal("unknown compat switch '" + s + "'");
+  });
+}
+
+int64_t qgpu_kernel_launches(const qgpu_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+
+// ---- tables ------------------------------------------------------------------------------------
+int qgpu_table_create(qgpu_ctx* ctx, const struct ArrowSchema* schema, qgpu_table** out) {
+  if (!ctx || !out) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] {
+    auto t = std::make_shared<TableImpl>();
+    t->ctx = &ctx->c;
+    t->schema = import_schema(schema);
+    t->cols.assign(t->schema.fields.size(), nullptr);
+    *out = new qgpu_table{t};
+  });
+}
+
+static int table_append(qgpu_table* t, struct ArrowArray* batch, const int32_t* cols, int32_t n, bool dev) {
+  if (!t || !batch) return QGPU_ERR_INTERNAL;
+  TableImpl& ti = *t->t;
+  int rc = guard(ti.ctx, [&] {
+    if (ti.consolidated && ti.num_batches > 0) {
+      // re-open: keep the consolidated columns as the first chunk
+      TableChunk first;
+      first.cols = ti.cols;
+      first.rows = ti.num_rows;
+      ti.chunks.push_back(first);
+    }
+    TableChunk ch = import_batch(ti.ctx, ti.schema, batch, cols, n, dev);
+    ti.chunks.push_back(ch);
+    ti.num_rows += ch.rows;
+    ti.num_batches += 1;
+    ti.consolidated = false;
+  });
+  if (batch->release) batch->release(batch);  // takes ownership, also on failure
+  return rc;
+}
+
+int qgpu_table_append(qgpu_table* t, struct ArrowArray* batch, const int32_t* upload_columns, int32_t n) {
+  return table_append(t, batch, upload_columns, n, false);
+}
+int qgpu_table_append_device(qgpu_table* t, struct ArrowArray* batch) { return table_append(t, batch, nullptr, 0, true); }
+
+int64_t qgpu_table_num_rows(const qgpu_table* t) { return t ? t->t->num_rows : -1; }
+int64_t qgpu_table_num_batches(const qgpu_table* t) { return t ? t->t->num_batches : -1; }
+
+int64_t qgpu_table_column_bytes(const qgpu_table* t, int32_t col) {
+  if (!t) return -1;
+  TableImpl& ti = *t->t;
+  int64_t r = -1;
+  guard(ti.ctx, [&] {
+    ti.consolidate();
+    if (col < 0 || col >= (int32_t)ti.cols.size()) throw_internal("column index out of range");
+    if (!ti.cols[col]) {
+      r = 0;
+      return;
+    }
+    const DCol& c = *ti.cols[col];
+    int64_t b = 0;
+    if (c.phys == PH_STR) b = (c.length + 1) * 4 + c.str_bytes;
+    else if (c.phys == PH_BIT) b = (c.length + 7) / 8;
+    else b = c.length * phys_width(c.phys);
+    if (c.validity) b += (c.length + 7) / 8;
+    r = b;
+  });
+  return r;
+}
+
+int qgpu_table_schema(const qgpu_table* t, struct ArrowSchema* out) {
+  if (!t || !out) return QGPU_ERR_INTERNAL;
+  return guard(t->t->ctx, [&] { export_schema(t->t->schema, out); });
+}
+
+int qgpu_table_export(qgpu_table* t, struct ArrowArray* out_array, struct ArrowSchema* out_schema) {
+  if (!t || !out_array || !out_schema) return QGPU_ERR_INTERNAL;
+  TableImpl& ti = *t->t;
+  return guard(ti.ctx, [&] {
+    ti.consolidate();
+    View v;
+    v.schema = ti.schema;
+    v.num_rows = ti.num_rows;
+    for (auto& c : ti.cols) v.cols.push_back({c, nullptr});
+    std::vector<DColP> cols = materialize_view(ti.ctx, v);
+    export_batch(ti.ctx, ti.schema, cols, ti.num_rows, out_array);
+    export_schema(ti.schema, out_schema);
+  });
+}
+
+void qgpu_table_free(qgpu_table* t) {
+  if (!t) return;
+  {
+    std::lock_guard<std::recursive_mutex> lk(t->t->ctx->mu);
+    cudaSetDevice(t->t->ctx->device);
+    t->t.reset();
+  }
+  delete t;
+}
+
+// ---- expressions ---------------------------------------------------------------------------------
+int qgpu_expr_parse(qgpu_ctx* ctx, const uint8_t* ir, size_t len, qgpu_expr** out) {
+  if (!ctx || !ir || !out) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] {
+    auto root = parse_ir(ir, len);
+    auto* e = new qgpu_expr();
+    e->ctx = &ctx->c;
+    e->root = std::shared_ptr<ExprNode>(root.release());
+    *out = e;
+  });
+}
+void qgpu_expr_free(qgpu_expr* e) { delete e; }
+
+// ---- plan nodes ------------------------------------------------------------------------------------
+static std::shared_ptr<PlanNode> new_node(qgpu_ctx* ctx, int kind) {
+  auto n = std::make_shared<PlanNode>();
+  n->ctx = &ctx->c;
+  n->kind = kind;
+  return n;
+}
+
+int qgpu_plan_scan(qgpu_ctx* ctx, qgpu_table* datasource, const int32_t* projection, int32_t n_projection,
+                   const qgpu_expr* filter, qgpu_plan** out) {
+  if (!ctx || !datasource || !out) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] {
+    auto n = new_node(ctx, PK_SCAN);
+    n->table = datasource->t;
+    if (projection) {
+      n->has_projection = true;
+      n->projection.assign(projection, projection + n_projection);
+      for (int ci : n->projection) {
+        if (ci < 0 || ci >= (int)n->table->schema.fields.size()) throw_arrow("Schema error: projection index out of bounds");
+        n->schema.fields.push_back(n->table->schema.fields[ci]);
+      }
+      n->schema.metadata = n->table->schema.metadata;
+    } else {
+      n->schema = n->table->schema;
+    }
+    if (filter) n->predicate = filter->root;
+    *out = new qgpu_plan{n};
+  });
+}
+
+int qgpu_plan_filter(qgpu_ctx* ctx, qgpu_plan* input, const qgpu_expr* predicate, qgpu_plan** out) {
+  if (!ctx || !input || !predicate || !out) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] {
+    auto n = new_node(ctx, PK_FILTER);
+    n->children.push_back(input->node);
+    n->schema = input->node->schema;  // filter.rs:24-26
+    n->predicate = predicate->root;
+    *out = new qgpu_plan{n};
+  });
+}
+
+int qgpu_plan_projection(qgpu_ctx* ctx, const struct ArrowSchema* schema, qgpu_plan* input, const qgpu_expr* const* exprs,
+                         int32_t n_exprs, qgpu_plan** out) {
+  if (!ctx || !schema || !input || !out || (n_exprs > 0 && !exprs)) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] {
+    auto n = new_node(ctx, PK_PROJECTION);
+    n->children.push_back(input->node);
+    n->schema = import_schema(schema);
+    for (int i = 0; i < n_exprs; ++i) n->exprs.push_back(exprs[i]->root);
+    *out = new qgpu_plan{n};
+  });
+}
+
+int qgpu_plan_aggregate(qgpu_ctx* ctx, const struct ArrowSchema* schema, qgpu_plan* input, const qgpu_expr* const* group_exprs,
+                        int32_t n_group, const qgpu_agg_desc* aggs, int32_t n_aggs, qgpu_plan** out) {
+  if (!ctx || !schema || !input || !out || (n_group > 0 && !group_exprs) || (n_aggs > 0 && !aggs)) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] {
+    auto n = new_node(ctx, PK_AGGREGATE);
+    n->children.push_back(input->node);
+    n->schema = import_schema(schema);
+    for (int i = 0; i < n_group; ++i) n->group_exprs.push_back(group_exprs[i]->root);
+    for (int i = 0; i < n_aggs; ++i) {
+      AggDesc d;
+      d.op = aggs[i].op;
+      if (d.op < 0 || d.op > QGPU_AGG_COUNT) throw_internal("unknown aggregate operator");
+      if (!aggs[i].expr) throw_internal("aggregate expression missing");
+      d.expr = aggs[i].expr->root;
+      d.return_type = mk_type(aggs[i].return_type.id, aggs[i].return_type.precision, aggs[i].return_type.scale);
+      d.expr_type = mk_type(aggs[i].expr_type.id, aggs[i].expr_type.precision, aggs[i].expr_type.scale);
+      n->aggs.push_back(d);
+    }
+    *out = new qgpu_plan{n};
+  });
+}
+
+int qgpu_plan_hash_join(qgpu_ctx* ctx, qgpu_plan* left, qgpu_plan* right, int32_t join_type, const qgpu_expr* const* left_on,
+                        const qgpu_expr* const* right_on, int32_t n_on, const qgpu_join_filter* filter, qgpu_plan** out) {
+  if (!ctx || !left || !right || !out) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] {
+    if (n_on <= 0 || !left_on || !right_on) throw_internal("On constraints in HashJoinExec should be non-empty");
+    if (join_type < 0 || join_type > QGPU_JOIN_LEFT_ANTI) throw_internal("unknown join type");
+    auto n = new_node(ctx, PK_HASH_JOIN);
+    n->children.push_back(left->node);
+    n->children.push_back(right->node);
+    n->join_type = join_type;
+    n->schema = build_join_schema(left->node->schema, right->node->schema, join_type);
+    for (int i = 0; i < n_on; ++i) {
+      n->left_on.push_back(left_on[i]->root);
+      n->right_on.push_back(right_on[i]->root);
+    }
+    if (filter) {
+      n->has_join_filter = true;
+      n->join_filter_expr = filter->expr->root;
+      n->join_filter_schema = import_schema(filter->schema);
+      n->join_filter_index.assign(filter->column_index, filter->column_index + filter->n_columns);
+      n->join_filter_side.assign(filter->column_side, filter->column_side + filter->n_columns);
+      if ((int)n->join_filter_schema.fields.size() != filter->n_columns) throw_internal("join filter schema/column_indices mismatch");
+    }
+    *out = new qgpu_plan{n};
+  });
+}
+
+int qgpu_plan_schema(const qgpu_plan* p, struct ArrowSchema* out) {
+  if (!p || !out) return QGPU_ERR_INTERNAL;
+  return guard(p->node->ctx, [&] { export_schema(p->node->schema, out); });
+}
+
+namespace {
+struct Timer {
+  Ctx* ctx;
+  cudaEvent_t a, b;
+  int64_t l0;
+  explicit Timer(Ctx* c) : ctx(c) {
+    CUDA_CHECK(cudaEventCreate(&a));
+    CUDA_CHECK(cudaEventCreate(&b));
+    l0 = c->launches;
+    CUDA_CHECK(cudaEventRecord(a, c->stream));
+  }
+  void stop(PlanNode& n) {
+    CUDA_CHECK(cudaEventRecord(b, ctx->stream));
+    CUDA_CHECK(cudaEventSynchronize(b));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+    n.last_ms = ms;
+    n.last_launches = ctx->launches - l0;
+  }
+  ~Timer() {
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+  }
+};
+}  // namespace
+
+int qgpu_plan_execute(qgpu_plan* p, struct ArrowArrayStream* out) {
+  if (!p || !out) return QGPU_ERR_INTERNAL;
+  PlanNode& n = *p->node;
+  return guard(n.ctx, [&] {
+    Timer tm(n.ctx);
+    View v = n.execute();
+    tm.stop(n);
+    std::vector<ArrowArray> batches;
+    if (v.num_batches > 0) {
+      std::vector<DColP> cols = materialize_view(n.ctx, v);
+      batches.resize(1);
+      export_batch(n.ctx, v.schema, cols, v.num_rows, &batches[0]);
+    }
+    make_stream(n.schema, std::move(batches), out);
+  });
+}
+
+int qgpu_plan_execute_device(qgpu_plan* p, qgpu_table** out, int64_t* out_batches) {
+  if (!p || !out) return QGPU_ERR_INTERNAL;
+  PlanNode& n = *p->node;
+  return guard(n.ctx, [&] {
+    Timer tm(n.ctx);
+    View v = n.execute();
+    auto t = std::make_shared<TableImpl>();
+    t->ctx = n.ctx;
+    t->schema = n.schema;
+    t->num_rows = v.num_rows;
+    t->num_batches = v.num_batches;
+    for (size_t i = 0; i < v.cols.size(); ++i) {
+      if (!v.cols[i].base) t->cols.push_back(nullptr);
+      else t->cols.push_back(materialize(n.ctx, v.cols[i], v.num_rows));
+    }
+    tm.stop(n);
+    if (out_batches) *out_batches = v.num_batches;
+    *out = new qgpu_table{t};
+  });
+}
+
+int qgpu_plan_last_stats(const qgpu_plan* p, double* device_ms, int64_t* launches) {
+  if (!p) return QGPU_ERR_INTERNAL;
+  if (device_ms) *device_ms = p->node->last_ms;
+  if (launches) *launches = p->node->last_launches;
+  return QGPU_OK;
+}
+
+const char* qgpu_plan_strategy(const qgpu_plan* p) { return p ? p->node->strategy.c_str() : ""; }
+
+void qgpu_plan_free(qgpu_plan* p) {
+  if (!p) return;
+  {
+    Ctx* c = p->node->ctx;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    p->node.reset();
+  }
+  delete p;
+}
+
+}  // extern "C"

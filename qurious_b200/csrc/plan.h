@@ -1,0 +1,54 @@
+// Physical plan nodes: the C++ host-side mirror of qurious/src/physical/plan/* for the hot path.
+#pragma once
+#include "ops.h"
+
+namespace qgpu {
+
+enum PlanKind { PK_SCAN = 1, PK_FILTER, PK_PROJECTION, PK_AGGREGATE, PK_HASH_JOIN };
+
+struct AggDesc {
+  int op = 0;
+  std::shared_ptr<ExprNode> expr;
+  DType return_type;
+  DType expr_type;
+};
+
+struct PlanNode {
+  Ctx* ctx = nullptr;
+  int kind = 0;
+  Schema schema;  // PhysicalPlan::schema()
+  std::vector<std::shared_ptr<PlanNode>> children;
+  // Scan
+  std::shared_ptr<TableImpl> table;
+  bool has_projection = false;
+  std::vector<int> projection;
+  std::shared_ptr<ExprNode> predicate;  // Scan filter / Filter predicate (may be null for Scan)
+  // Projection
+  std::vector<std::shared_ptr<ExprNode>> exprs;
+  // Aggregate
+  std::vector<std::shared_ptr<ExprNode>> group_exprs;
+  std::vector<AggDesc> aggs;
+  // HashJoin
+  int join_type = QGPU_JOIN_INNER;
+  std::vector<std::shared_ptr<ExprNode>> left_on, right_on;
+  bool has_join_filter = false;
+  std::shared_ptr<ExprNode> join_filter_expr;
+  Schema join_filter_schema;
+  std::vector<int> join_filter_index, join_filter_side;
+  // stats of the last execute
+  double last_ms = 0;
+  int64_t last_launches = 0;
+  std::string strategy = "not-executed";
+
+  View execute();
+};
+
+// fused.cu: returns true and fills `out` when the aggregate over this input can run as one fused
+// scan+filter+aggregate pipeline kernel.
+bool try_fused_scan_aggregate(PlanNode& agg, View* out);
+
+}  // namespace qgpu
+
+struct qgpu_plan {
+  std::shared_ptr<qgpu::PlanNode> node;
+};

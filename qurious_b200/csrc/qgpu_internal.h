@@ -1,0 +1,245 @@
+// Internal data model of libqgpu.so (not part of the ABI; the ABI is include/qgpu.h).
+//
+// HBM layout (DESIGN.md "Data layout"):
+//   * a table is a set of immutable, contiguous, 256B-aligned device columns (Arrow layout:
+//     values / i32 offsets + bytes / bit-packed validity); Decimal128(p<=18) columns whose values
+//     are proven to fit are stored NARROWED to int64 (8 B/value) -- the kernels read that layout;
+//   * operators exchange `View`s: lazy columns = (base column, optional int64 row-index vector,
+//     -1 = NULL).  Filters and joins only produce index vectors; payload columns are gathered
+//     once, when something finally needs them (late materialisation).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/qgpu.h"
+
+namespace qgpu {
+
+typedef __int128 i128;
+typedef unsigned __int128 u128;
+
+// ----------------------------------------------------------------------------------------------
+// errors
+// ----------------------------------------------------------------------------------------------
+struct QError : public std::runtime_error {
+  int code;
+  QError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+[[noreturn]] inline void throw_internal(const std::string& m) { throw QError(QGPU_ERR_INTERNAL, "InternalError: " + m); }
+[[noreturn]] inline void throw_arrow(const std::string& m) { throw QError(QGPU_ERR_ARROW, "ArrowError: " + m); }
+
+#define CUDA_CHECK(expr)                                                                          \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      int _c = (_e == cudaErrorMemoryAllocation) ? QGPU_ERR_OOM : QGPU_ERR_CUDA;                  \
+      throw ::qgpu::QError(_c, std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " +    \
+                                   __FILE__ + ":" + std::to_string(__LINE__));                    \
+    }                                                                                             \
+  } while (0)
+
+// ----------------------------------------------------------------------------------------------
+// logical types
+// ----------------------------------------------------------------------------------------------
+struct DType {
+  uint8_t id = QGPU_T_NULL;
+  uint8_t precision = 0;
+  int8_t scale = 0;
+  bool operator==(const DType& o) const { return id == o.id && precision == o.precision && scale == o.scale; }
+  bool operator!=(const DType& o) const { return !(*this == o); }
+  bool is_decimal() const { return id == QGPU_T_DECIMAL128; }
+  bool is_signed_int() const { return id >= QGPU_T_INT8 && id <= QGPU_T_INT64; }
+  bool is_unsigned_int() const { return id >= QGPU_T_UINT8 && id <= QGPU_T_UINT64; }
+  bool is_int() const { return is_signed_int() || is_unsigned_int(); }
+  bool is_float() const { return id == QGPU_T_FLOAT32 || id == QGPU_T_FLOAT64; }
+  bool is_date() const { return id == QGPU_T_DATE32 || id == QGPU_T_DATE64; }
+  std::string str() const;
+};
+inline DType mk_type(int id, int p = 0, int s = 0) {
+  DType t;
+  t.id = (uint8_t)id;
+  t.precision = (uint8_t)p;
+  t.scale = (int8_t)s;
+  return t;
+}
+// byte width of one value in the canonical (Arrow) layout; 0 for bool (bit-packed) / utf8 / null
+int arrow_width(const DType& t);
+
+struct Field {
+  std::string name;
+  DType type;
+  bool nullable = true;
+  std::string metadata;  // raw Arrow-encoded metadata blob (may be empty)
+};
+struct Schema {
+  std::vector<Field> fields;
+  std::string metadata;  // raw Arrow-encoded metadata blob
+};
+
+// ----------------------------------------------------------------------------------------------
+// device memory
+// ----------------------------------------------------------------------------------------------
+struct Ctx;
+struct DBuf {
+  Ctx* ctx = nullptr;
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  DBuf(Ctx* c, size_t n);
+  ~DBuf();
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+};
+typedef std::shared_ptr<DBuf> DBufP;
+
+// physical storage class of a device column
+enum Phys : uint8_t {
+  PH_NULL = 0,  // no buffers (all NULL)
+  PH_BIT,       // bit-packed booleans
+  PH_I8, PH_I16, PH_I32, PH_I64,
+  PH_U8, PH_U16, PH_U32, PH_U64,
+  PH_F32, PH_F64,
+  PH_I128,      // Decimal128 in Arrow layout (16 B)
+  PH_D64,       // Decimal128 narrowed to int64 (8 B) -- value fits, proven at ingest
+  PH_STR        // utf8: i32 offsets + bytes
+};
+inline int phys_width(Phys p) {
+  switch (p) {
+    case PH_I8: case PH_U8: return 1;
+    case PH_I16: case PH_U16: return 2;
+    case PH_I32: case PH_U32: case PH_F32: return 4;
+    case PH_I64: case PH_U64: case PH_F64: case PH_D64: return 8;
+    case PH_I128: return 16;
+    default: return 0;
+  }
+}
+
+struct DCol {
+  DType type;
+  Phys phys = PH_NULL;
+  int64_t length = 0;
+  int64_t null_count = 0;
+  DBufP data;      // values (or utf8 bytes)
+  DBufP offsets;   // utf8: (length+1) int32
+  DBufP validity;  // bitmap (uint32 words), null when null_count == 0
+  int64_t str_bytes = 0;
+  // lazily computed value range of the non-null values (ints / dates / decimals)
+  bool has_stats = false;
+  i128 vmin = 0, vmax = 0;
+  int64_t bytes_resident() const {
+    int64_t b = 0;
+    if (data) b += (int64_t)data->bytes;
+    if (offsets) b += (int64_t)offsets->bytes;
+    if (validity) b += (int64_t)validity->bytes;
+    return b;
+  }
+};
+typedef std::shared_ptr<DCol> DColP;
+
+// int64 row-index vector; -1 = NULL row (outer joins)
+struct IdxVec {
+  DBufP buf;
+  int64_t length = 0;
+  bool may_have_null = false;
+  const int64_t* ptr() const { return buf ? (const int64_t*)buf->ptr : nullptr; }
+};
+typedef std::shared_ptr<IdxVec> IdxP;
+
+struct LazyCol {
+  DColP base;  // may be null for a column that was never uploaded (selective upload)
+  IdxP idx;    // null = identity
+};
+
+struct View {
+  Schema schema;
+  std::vector<LazyCol> cols;
+  int64_t num_rows = 0;
+  int64_t num_batches = 1;  // how many RecordBatches the reference would have returned
+};
+
+// ----------------------------------------------------------------------------------------------
+// context
+// ----------------------------------------------------------------------------------------------
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;       // compute stream
+  cudaStream_t copy_stream = nullptr;  // H2D staging side stream
+  cudaMemPool_t pool = nullptr;
+  std::recursive_mutex mu;
+  std::string last_error;
+  int64_t launches = 0;
+  int sm_count = 148;
+  bool compat_avg_precision = false;
+  bool compat_empty_decimal_sum = false;
+  // pinned staging ring for pageable host buffers
+  static const int kStageSlots = 2;
+  size_t stage_bytes = (size_t)32 << 20;
+  void* stage[kStageSlots] = {nullptr, nullptr};
+  cudaEvent_t stage_ev[kStageSlots] = {nullptr, nullptr};
+  int stage_next = 0;
+  // small pinned scratch for D2H of scalars / flags
+  void* pinned_scratch = nullptr;
+  size_t pinned_scratch_bytes = 1 << 16;
+
+  DBufP alloc(size_t bytes);
+  DBufP alloc_zero(size_t bytes);
+  void h2d(void* dst, const void* src, size_t bytes);        // pageable or pinned host -> device
+  void d2h_sync(void* dst, const void* src, size_t bytes);   // device -> host, waits
+  void sync();
+  template <typename T>
+  T read_scalar(const T* dptr) {
+    T v;
+    d2h_sync(&v, dptr, sizeof(T));
+    return v;
+  }
+};
+
+// ----------------------------------------------------------------------------------------------
+// table (HBM-resident MemoryTable)
+// ----------------------------------------------------------------------------------------------
+struct TableChunk {
+  std::vector<DColP> cols;  // null entries for columns that were not uploaded
+  int64_t rows = 0;
+};
+}  // namespace qgpu
+
+namespace qgpu {
+struct TableImpl {
+  Ctx* ctx = nullptr;
+  Schema schema;
+  std::vector<TableChunk> chunks;  // appended batches, consolidated lazily
+  std::vector<DColP> cols;         // consolidated columns (one per schema field; null = not uploaded)
+  bool consolidated = true;
+  int64_t num_rows = 0;
+  int64_t num_batches = 0;
+  void consolidate();
+};
+}  // namespace qgpu
+
+struct qgpu_ctx {
+  qgpu::Ctx c;
+};
+struct qgpu_table {
+  std::shared_ptr<qgpu::TableImpl> t;
+};
+
+namespace qgpu {
+
+// ---- arrow_io.cu -------------------------------------------------------------------------------
+Schema import_schema(const ArrowSchema* s);
+void export_schema(const Schema& s, ArrowSchema* out);
+TableChunk import_batch(Ctx* ctx, const Schema& schema, ArrowArray* batch, const int32_t* upload_columns,
+                        int32_t n_upload, bool device_resident);
+// materialised columns -> host ArrowArray (struct); blocks until the copy is done
+void export_batch(Ctx* ctx, const Schema& schema, const std::vector<DColP>& cols, int64_t num_rows,
+                  ArrowArray* out);
+void make_stream(const Schema& schema, std::vector<ArrowArray>&& batches, ArrowArrayStream* out);
+std::string merge_metadata(const std::string& base, const std::string& key, const std::string& value);
+bool metadata_get(const std::string& blob, const std::string& key, std::string* value);
+
+}  // namespace qgpu
