@@ -483,8 +483,13 @@ Program bind_program(Ctx* ctx, Compiled& c, const View& v) {
     const LazyCol& lc = v.cols[ci];
     ColRef& r = P.cols[s];
     memset(&r, 0, sizeof(ColRef));
-    if (!lc.base)
+    if (!lc.base) {
+      if (v.num_rows == 0) {  // a table with zero batches has no buffers at all
+        r.phys = PH_NULL;
+        continue;
+      }
       throw_internal("column '" + v.schema.fields[ci].name + "' is referenced but was not uploaded to the GPU table");
+    }
     const DCol& d = *lc.base;
     r.phys = d.phys;
     r.data = d.data ? d.data->ptr : nullptr;

@@ -233,11 +233,6 @@ KeyTable build_key_table(Ctx* ctx, const View& v, std::vector<std::shared_ptr<Co
 // ------------------------------------------------------------------------------------------------
 // aggregate
 // ------------------------------------------------------------------------------------------------
-enum AccKind : int {
-  AK_COUNT = 0, AK_SUM_I64, AK_SUM_DEC, AK_SUM_F64, AK_MIN_I64, AK_MAX_I64, AK_MIN_U64, AK_MAX_U64, AK_MIN_F64, AK_MAX_F64,
-  AK_MIN_DEC, AK_MAX_DEC
-};
-
 struct AggDev {
   int kind;
   int pad;
@@ -245,7 +240,7 @@ struct AggDev {
   unsigned long long* hi;
   unsigned long long* cnt;
 };
-#define MAX_AGGS 16
+#define MAX_AGGS 24
 struct AggDevs {
   AggDev a[MAX_AGGS];
 };
@@ -477,7 +472,7 @@ View run_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<Comp
                    const Schema& out_schema) {
   const int64_t n = input.num_rows;
   const bool grouped = !keys.empty();
-  if ((int)aggs.size() > MAX_AGGS) throw_internal("more than 16 aggregate expressions are not supported");
+  if ((int)aggs.size() > MAX_AGGS) throw_internal("more than 24 aggregate expressions are not supported");
   if (out_schema.fields.size() != keys.size() + aggs.size()) throw_arrow("aggregate output schema has the wrong number of fields");
   View out;
   out.schema = out_schema;
@@ -576,13 +571,30 @@ View run_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<Comp
     int e = ctx->read_scalar((const int*)err->ptr);
     if (e) throw_eval_error(e);
   }
-  if (!grouped) n_groups = 1;
+  GroupAccs accs;
+  accs.n_groups = grouped ? n_groups : 1;
+  for (size_t i = 0; i < aggs.size(); ++i) {
+    accs.kind.push_back(ad.a[i].kind);
+    accs.lo.push_back(keep[3 * i]);
+    accs.hi.push_back(keep[3 * i + 1]);
+    accs.cnt.push_back(keep[3 * i + 2]);
+  }
+  accs.first_row = first_row;
+  return finish_aggregate(ctx, input, keys, aggs, out_schema, accs);
+}
+
+View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<Compiled>>& keys, std::vector<AggSpec>& aggs,
+                      const Schema& out_schema, GroupAccs& accs) {
+  const bool grouped = !keys.empty();
+  const int64_t n_groups = accs.n_groups;
+  View out;
+  out.schema = out_schema;
   // ---- group order: first occurrence (the reference's order is unspecified) --
   IdxP order;        // output position -> gid
   IdxP first_idx;    // output position -> first input row of the group
   if (grouped) {
     std::vector<long long> fr((size_t)n_groups);
-    if (n_groups > 0) ctx->d2h_sync(fr.data(), first_row->ptr, (size_t)n_groups * 8);
+    if (n_groups > 0) ctx->d2h_sync(fr.data(), accs.first_row->ptr, (size_t)n_groups * 8);
     std::vector<long long> ord((size_t)n_groups);
     std::iota(ord.begin(), ord.end(), 0LL);
     if (n_groups <= (1 << 22)) std::sort(ord.begin(), ord.end(), [&](long long a, long long b) { return fr[a] < fr[b]; });
@@ -634,16 +646,16 @@ View run_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<Comp
     FinSpec f;
     memset(&f, 0, sizeof(f));
     f.op = a.op;
-    f.kind = ad.a[i].kind;
+    f.kind = accs.kind[i];
     f.out_phys = col->phys;
     f.sum_scale = a.expr_type.scale;
     f.target_scale = a.return_type.scale;
     f.target_prec = a.return_type.precision;
     f.compat_avg = ctx->compat_avg_precision ? 1 : 0;
     f.no_input = (!grouped && input.num_batches == 0) ? 1 : 0;
-    f.lo = ad.a[i].lo;
-    f.hi = ad.a[i].hi;
-    f.cnt = ad.a[i].cnt;
+    f.lo = (const unsigned long long*)accs.lo[i]->ptr;
+    f.hi = (const unsigned long long*)accs.hi[i]->ptr;
+    f.cnt = (const unsigned long long*)accs.cnt[i]->ptr;
     f.out = col->data->ptr;
     f.out_valid = (uint32_t*)col->validity->ptr;
     DBufP flags = ctx->alloc_zero(16);

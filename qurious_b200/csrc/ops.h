@@ -12,6 +12,22 @@ struct AggSpec {
   DType expr_type;
 };
 
+enum AccKind : int {
+  AK_COUNT = 0, AK_SUM_I64, AK_SUM_DEC, AK_SUM_F64, AK_MIN_I64, AK_MAX_I64, AK_MIN_U64, AK_MAX_U64, AK_MIN_F64, AK_MAX_F64,
+  AK_MIN_DEC, AK_MAX_DEC
+};
+
+// Per-group accumulator state handed from an accumulation strategy (generic atomics in ops.cu or
+// the fused pipeline in fused.cu) to the common finalisation (AVG division, NULL-ness, output order).
+struct GroupAccs {
+  int64_t n_groups = 0;
+  std::vector<int> kind;            // AccKind per aggregate
+  std::vector<DBufP> lo, hi, cnt;   // per aggregate: u64[n_groups] each (cnt = number of non-NULL inputs)
+  DBufP first_row;                  // i64[n_groups]: first input row of the group
+};
+View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<Compiled>>& keys, std::vector<AggSpec>& aggs,
+                      const Schema& out_schema, GroupAccs& accs);
+
 // HashAggregate / NoGroupingAggregate (keys.empty()).  SURVEY 8a a7,a8,a10-a13.
 View run_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<Compiled>>& keys, std::vector<AggSpec>& aggs,
                    const Schema& out_schema);

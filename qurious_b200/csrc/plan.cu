@@ -145,6 +145,17 @@ static View scan_view(PlanNode& n) {
   View v;
   v.num_rows = t.num_rows;
   v.num_batches = t.num_batches;
+  if (t.num_batches == 0) {
+    // CREATE TABLE without INSERT: no buffers exist; give every column an empty all-NULL placeholder so
+    // that outer joins can still emit NULL-padded rows for this side
+    for (size_t i = 0; i < t.cols.size(); ++i)
+      if (!t.cols[i]) {
+        auto c = std::make_shared<DCol>();
+        c->type = t.schema.fields[i].type;
+        c->phys = PH_NULL;
+        t.cols[i] = c;
+      }
+  }
   if (n.has_projection) {
     for (int ci : n.projection) {
       if (ci < 0 || ci >= (int)t.schema.fields.size()) throw_arrow("Schema error: projection index out of bounds");
