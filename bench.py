@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""bench.py -- TPC-H Q1 (default) / Q6 / Q3 rows/sec through the B200-native physical operators.
+
+Contract (one JSON line on rank 0):
+  value      input rows of the driving table (lineitem) / device time of one step, table resident in HBM
+             (a step = one execution of the query's physical plan: Scan(pushed-down filter) ->
+             [HashJoin ->] Aggregate -> Projection), whole job over all ranks, max over ranks.
+  e2e        the same metric through the reference-facing operator API with HOST Arrow buffers:
+             MemoryTable(host RecordBatches) -> H2D staging -> plan.execute() -> host RecordBatches.
+  roofline   dominant kernel: algorithmic bytes of the layout the kernel reads / its CUDA-event duration
+             (events recorded on the library's own stream by qgpu_profile_enable) vs MEASURED_PEAKS.json.
+  cpu_baseline  oracle/qref_cpu.cpp (single-threaded C++ port of qurious's CPU steps) on a bounded sample.
+
+`--impl reference` times that CPU port alone (the reference is Rust; no cargo/rustc in this image, so the
+real binary cannot be built -- DESIGN.md "Oracle"); rank 0 only.
+
+Workload at N GPUs: lineitem of TPC-H SF(sf*N) row-range sharded over the ranks (weak scaling, sf=10 per
+GPU by default); partial aggregates are all-gathered over NCCL and merged identically on every rank.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--query", default="q1", choices=["q1", "q6", "q3"])
+    ap.add_argument("--sf", type=float, default=10.0, help="TPC-H scale factor PER GPU")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample-rows", type=int, default=20_000_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--extra-queries", default="", help="comma list of further queries reported under 'queries'")
+    return ap.parse_args()
+
+
+QUERY_COLUMNS = {
+    "q1": {"lineitem": ["l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus",
+                        "l_shipdate"]},
+    "q6": {"lineitem": ["l_quantity", "l_extendedprice", "l_discount", "l_shipdate"]},
+    "q3": {"customer": ["c_custkey", "c_mktsegment"],
+           "orders": ["o_orderkey", "o_custkey", "o_orderdate", "o_shippriority"],
+           "lineitem": ["l_orderkey", "l_extendedprice", "l_discount", "l_shipdate"]},
+}
+WORKLOAD = {"q1": "TPC-H Q1 group-by aggregate", "q6": "TPC-H Q6 filter + SUM",
+            "q3": "TPC-H Q3 customer-orders-lineitem hash join + aggregate"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks (NVML) sampled DURING the timed regions
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, cuda_index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._active = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(cuda_index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        except Exception as e:  # NVML missing: report that instead of inventing numbers
+            self.err = repr(e)
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            if self._active.is_set():
+                try:
+                    self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    try:
+                        mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    except Exception:
+                        mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    for bit, name in self.REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.005)
+
+    def region(self, on: bool):
+        (self._active.set if on else self._active.clear)()
+
+    def result(self):
+        self._stop.set()
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": getattr(self, "err", "nvml unavailable")}
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def pin_batches(batches):
+    """cudaHostRegister every Arrow buffer of the host batches so that H2D is a direct pinned DMA."""
+    import torch
+    rt = torch.cuda.cudart()
+    regs = []
+    seen = set()
+    for b in batches:
+        for col in b.columns:
+            for buf in col.buffers():
+                if buf is None or buf.size == 0 or buf.address in seen:
+                    continue
+                seen.add(buf.address)
+                if int(rt.cudaHostRegister(buf.address, buf.size, 0)) == 0:
+                    regs.append(buf.address)
+    return regs
+
+
+def unpin(regs):
+    import torch
+    rt = torch.cuda.cudart()
+    for a in regs:
+        rt.cudaHostUnregister(a)
+
+
+def batches_nbytes(batches):
+    n = 0
+    for b in batches:
+        for col in b.columns:
+            for buf in col.buffers():
+                if buf is not None:
+                    n += buf.size
+    return n
+
+
+def build_plan(query, tables):
+    from qurious_b200 import tpch
+    db = tpch.Database(0.0, tables.get("customer"), tables.get("orders"), tables.get("lineitem"))
+    return getattr(tpch, query + "_plan")(db)
+
+
+def shard_range(total_rows, rank, world):
+    return (total_rows * rank) // world, (total_rows * (rank + 1)) // world
+
+
+def gen_raw(query, sf_total, device, rank, world):
+    """RawTables for `query`; lineitem is this rank's row range, the (small) dimension tables are whole."""
+    from qurious_b200 import tpch
+    cols = QUERY_COLUMNS[query]
+    out = {}
+    n_l = tpch.n_lineitems(sf_total)
+    rr = shard_range(n_l, rank, world) if world > 1 else None
+    out["lineitem"] = tpch.gen_lineitem(sf_total, device=device, columns=cols["lineitem"], row_range=rr)
+    if "orders" in cols:
+        out["orders"] = tpch.gen_orders(sf_total, device=device, columns=cols["orders"])
+    if "customer" in cols:
+        out["customer"] = tpch.gen_customer(sf_total, device=device, columns=cols["customer"])
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the CPU port on host cores
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_port
+    from qurious_b200 import tpch
+    if args.query not in ("q1", "q6"):
+        print(json.dumps({"impl": "reference", "unavailable": f"no CPU port of {args.query} yet"}))
+        return
+    sample_rows = 2_000_000
+    sf = sample_rows / 6_001_215
+    raw = tpch.gen_lineitem(sf, columns=QUERY_COLUMNS[args.query]["lineitem"])
+    batches = tpch.to_arrow(raw, 1024 * 1024)
+    fn = getattr(cpu_port, args.query)
+    for _ in range(max(args.warmup, 1)):
+        fn(batches)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn(batches)
+    dt = time.perf_counter() - t0
+    rows_s = raw.rows * args.steps / dt
+    sample = (f"first {raw.rows} rows of the same synthetic lineitem generator (SF{sf:.3f}), referenced columns only, "
+              f"1024-row batches, single thread (the reference has no threads)")
+    line = {"impl": "reference", "metric": f"TPC-H {args.query.upper()} rows/sec", "value": rows_s, "unit": "rows/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i128", "data": "synthetic",
+            "config": {"workload": f"{WORKLOAD[args.query]} at SF{args.sf:g} per GPU (bounded sample per step)"},
+            "cpu_baseline": {"value": rows_s, "unit": "rows/s", "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": rows_s, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(query, dev_tables):
+    """Bytes of every referenced column in the layout the kernels read (after ingest narrowing), once."""
+    total = 0
+    per_table = {}
+    for name, mt in dev_tables.items():
+        dev = mt._dev
+        b = sum(dev.column_bytes(i) for i in range(len(dev.schema)))
+        per_table[name] = b
+        total += b
+    return total, per_table
+
+
+def run_query_device(ctx, plan, steps, warmup, sampler, torch, stream, merge=None):
+    """K timed steps, table resident in HBM; returns (ms_total, per-kernel profile, launches per step)."""
+    for _ in range(warmup):
+        t = plan.execute_device(ctx)
+        if merge:
+            merge(t)
+        t.free()
+    ctx.profile(True)
+    ctx.profile_report()
+    l0 = ctx.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    sampler.region(True)
+    e0.record(stream)
+    for _ in range(steps):
+        t = plan.execute_device(ctx)
+        if merge:
+            merge(t)
+        t.free()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    sampler.region(False)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof = ctx.profile_report()
+    ctx.profile(False)
+    launches = (ctx.kernel_launches() - l0) / max(steps, 1)
+    return ms, prof, launches
+
+
+_dist = None
+
+
+def barrier():
+    if _dist is not None:
+        _dist.barrier()
+
+
+def run_b200(args):
+    global _dist
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        _dist = dist
+    from qurious_b200 import _lib, tpch
+    ctx = _lib.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", local_rank))
+    sampler = ClockSampler(local_rank)
+    peak, peak_src = measured_peak_gbs()
+    sf_total = args.sf * world
+    q = args.query
+
+    # ---- device-resident leg -----------------------------------------------------------------
+    raw = gen_raw(q, sf_total, "cuda", rank, world)
+    rows_local = raw["lineitem"].rows
+    dev_tables = {k: tpch.to_device_table(ctx, v) for k, v in raw.items()}
+    plan = build_plan(q, dev_tables)
+    merge = None
+    if world > 1:
+        from qurious_b200 import distributed as qd
+        merge = qd.make_partial_merger(ctx, plan, _dist)
+    ms, prof, launches = run_query_device(ctx, plan, args.steps, args.warmup, sampler, torch, stream, merge)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    rows_t = torch.tensor([rows_local], dtype=torch.int64, device="cuda")
+    if world > 1:
+        _dist.all_reduce(t_ms, op=_dist.ReduceOp.MAX)
+        _dist.all_reduce(rows_t, op=_dist.ReduceOp.SUM)
+    ms_max, rows_total = float(t_ms.item()), int(rows_t.item())
+    value = rows_total * args.steps / (ms_max / 1e3)
+    strategy = plan.last_strategy()
+    alg_bytes, per_table = algorithmic_bytes(q, dev_tables)
+    # dominant kernel by total device time
+    prof_sorted = sorted(prof, key=lambda r: -r[2])
+    top = prof_sorted[0] if prof_sorted else ("none", 0, 0.0, 0.0)
+    top_ms = top[2] / max(top[1], 1)
+    top_share = top[2] / max(sum(r[2] for r in prof), 1e-9)
+    top_bytes = per_table.get("lineitem", alg_bytes)   # the dominant kernel streams the driving table
+    achieved = top_bytes / (top_ms / 1e3) / 1e9 if top_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": top_bytes, "bytes_per_row": top_bytes / max(rows_local, 1),
+                "kernel_ms_avg": top_ms, "kernel_share_of_step": top_share, "launches_of_kernel_per_step": top[1] / args.steps,
+                "step_frac_of_roofline": (alg_bytes / (ms / args.steps / 1e3) / 1e9) / peak}
+    del raw
+
+    # ---- end-to-end leg: host Arrow buffers -> operators -> host RecordBatches ---------------------
+    e2e = None
+    cpu = None
+    host_batches = None
+    if not args.no_e2e:
+        raw_h = gen_raw(q, sf_total, "cuda", rank, world)
+        host = {}
+        for k, v in raw_h.items():
+            for d in (v.cols, v.codes):
+                for c in list(d):
+                    d[c] = d[c].cpu()
+            host[k] = tpch.to_arrow(v, None)
+        del raw_h
+        torch.cuda.empty_cache()
+        regs = []
+        for k in host:
+            regs += pin_batches(host[k])
+        host_batches = host
+        h2d = sum(batches_nbytes(b) for b in host.values())
+        from qurious_b200.physical.plan import MemoryTable
+
+        def one_e2e():
+            tabs = {k: MemoryTable.try_new(b[0].schema, b) for k, b in host.items()}
+            p = build_plan(q, tabs)
+            out = p.execute(ctx)
+            if merge is not None:
+                pass  # multi-GPU e2e: shard-local result; merge is part of the device leg
+            d2h = batches_nbytes(out)
+            for t in tabs.values():
+                if t._dev is not None:
+                    t._dev.free()
+            return d2h
+        for _ in range(min(args.warmup, 2)):
+            d2h = one_e2e()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        torch.cuda.synchronize()
+        sampler.region(True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(args.e2e_steps):
+            d2h = one_e2e()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        sampler.region(False)
+        barrier()
+        ems = max(e0.elapsed_time(e1), wall * 1e3)   # host-side staging is part of the step
+        t_e = torch.tensor([ems], dtype=torch.float64, device="cuda")
+        if world > 1:
+            _dist.all_reduce(t_e, op=_dist.ReduceOp.MAX)
+        e2e = {"value": rows_total * args.e2e_steps / (float(t_e.item()) / 1e3), "unit": "rows/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+               "ms_per_step": float(t_e.item()) / args.e2e_steps,
+               "path": "MemoryTable(host RecordBatches, pinned) -> qgpu_table_append (cudaMemcpyAsync) -> "
+                       "plan.execute() -> host RecordBatches"}
+        unpin(regs)
+
+    # ---- CPU baseline (rank 0, N=1): the C++ port on a bounded sample of the same workload -----------
+    if not args.no_cpu and rank == 0 and world == 1 and q in ("q1", "q6") and host_batches is not None:
+        from oracle import cpu_port
+        n = min(args.cpu_sample_rows, host_batches["lineitem"][0].num_rows)
+        sample = [host_batches["lineitem"][0].slice(0, n)]
+        t0 = time.perf_counter()
+        getattr(cpu_port, q)(sample)
+        dt = time.perf_counter() - t0
+        cpu = {"value": n / dt, "unit": "rows/s", "cores": 1, "kind": "port",
+               "sample": f"first {n} rows of this run's lineitem (referenced columns only), 1024-row batches, "
+                         f"{dt:.1f} s on 1 of {os.cpu_count()} host cores (the reference is single-threaded)"}
+
+    clocks = sampler.result()
+    if rank == 0:
+        line = {"metric": f"TPC-H {q.upper()} rows/sec", "value": value, "unit": "rows/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "i64/i128 (exact decimal)", "data": "synthetic",
+                "config": {"workload": f"{WORKLOAD[q]} at SF{args.sf:g} per GPU ({rows_total} lineitem rows total, "
+                                       f"row-range sharded over {world} GPU(s))",
+                           "l2": "inputs larger than L2 (resident columns >> 126 MB), no flush needed",
+                           "strategy": strategy, "rows_per_gpu": rows_local},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(round(launches * args.steps)),
+                "gpu_launches_per_step": launches, "clocks": clocks,
+                "kernels": [{"name": r[0], "launches": r[1], "total_ms": round(r[2], 4)} for r in prof_sorted[:8]]}
+        print(json.dumps(line))
+    if world > 1:
+        _dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

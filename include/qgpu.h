@@ -149,6 +149,15 @@ const char* qgpu_last_error(const qgpu_ctx* ctx);
 int qgpu_set_compat(qgpu_ctx* ctx, const char* name, int value);
 /* number of kernel launches issued by this context since creation (bench.py: gpu_launches) */
 int64_t qgpu_kernel_launches(const qgpu_ctx* ctx);
+/* The context's compute stream (a cudaStream_t) so that callers can record their own CUDA events
+ * around calls (bench.py times steps with events on THIS stream). */
+void* qgpu_ctx_stream(const qgpu_ctx* ctx);
+/* Per-kernel device timing: while enabled every kernel launch is bracketed by CUDA events on the
+ * compute stream.  qgpu_profile_report synchronises, writes "kernel\tlaunches\ttotal_ms\tmax_ms\n"
+ * lines for the launches since the last report into buf (NUL terminated, truncated to cap) and
+ * returns the number of bytes the full report needs. */
+int qgpu_profile_enable(qgpu_ctx* ctx, int on);
+int64_t qgpu_profile_report(qgpu_ctx* ctx, char* buf, int64_t cap);
 
 /* ---- tables: replaces MemoryTable (datasource/memory.rs:20-45) ---------------------------- */
 int qgpu_table_create(qgpu_ctx* ctx, const struct ArrowSchema* schema, qgpu_table** out);

@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libqgpu.so")
 # every symbol include/qgpu.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
     "qgpu_init", "qgpu_shutdown", "qgpu_last_error", "qgpu_set_compat", "qgpu_kernel_launches",
+    "qgpu_ctx_stream", "qgpu_profile_enable", "qgpu_profile_report",
     "qgpu_table_create", "qgpu_table_append", "qgpu_table_append_device", "qgpu_table_num_rows",
     "qgpu_table_num_batches", "qgpu_table_column_bytes", "qgpu_table_schema", "qgpu_table_export",
     "qgpu_table_free", "qgpu_expr_parse", "qgpu_expr_free", "qgpu_plan_scan", "qgpu_plan_filter",
@@ -78,6 +79,11 @@ def load_library() -> ctypes.CDLL:
     lib.qgpu_set_compat.argtypes = [vp, ctypes.c_char_p, ctypes.c_int]
     lib.qgpu_kernel_launches.argtypes = [vp]
     lib.qgpu_kernel_launches.restype = i64
+    lib.qgpu_ctx_stream.argtypes = [vp]
+    lib.qgpu_ctx_stream.restype = vp
+    lib.qgpu_profile_enable.argtypes = [vp, ctypes.c_int]
+    lib.qgpu_profile_report.argtypes = [vp, ctypes.c_char_p, i64]
+    lib.qgpu_profile_report.restype = i64
     lib.qgpu_table_create.argtypes = [vp, vp, P(vp)]
     lib.qgpu_table_append.argtypes = [vp, vp, P(i32), i32]
     lib.qgpu_table_append_device.argtypes = [vp, vp]
@@ -139,6 +145,26 @@ class Context:
 
     def kernel_launches(self) -> int:
         return int(self.lib.qgpu_kernel_launches(self.handle))
+
+    def stream_handle(self) -> int:
+        """cudaStream_t of the context's compute stream (for caller-side CUDA events)."""
+        return int(self.lib.qgpu_ctx_stream(self.handle) or 0)
+
+    def profile(self, on: bool):
+        self.check(self.lib.qgpu_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_report(self):
+        """[(kernel, launches, total_ms, max_ms)] since the last report; device time from CUDA events."""
+        cap = 1 << 16
+        buf = ctypes.create_string_buffer(cap)
+        need = int(self.lib.qgpu_profile_report(self.handle, buf, cap))
+        if need < 0:
+            raise QuriousError(1, self.lib.qgpu_last_error(self.handle).decode())
+        out = []
+        for line in buf.value.decode().splitlines():
+            name, n, ms, mx = line.split("\t")
+            out.append((name, int(n), float(ms), float(mx)))
+        return out
 
     def close(self):
         if getattr(self, "handle", None):

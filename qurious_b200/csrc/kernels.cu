@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "kernels.h"
+#include "launch.h"
 
 namespace qgpu {
 
@@ -76,19 +77,43 @@ void Ctx::d2h_sync(void* dst, const void* src, size_t bytes) {
   }
 }
 
-#define LAUNCH(ctx, kernel, grid, block, smem, ...)                 \
-  do {                                                              \
-    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
-    (ctx)->launches++;                                              \
-    CUDA_CHECK(cudaGetLastError());                                 \
-  } while (0)
-
-static inline int grid_for(Ctx* ctx, int64_t n, int per_block) {
-  int64_t g = (n + per_block - 1) / per_block;
-  int64_t cap = (int64_t)ctx->sm_count * 16;
-  if (g > cap) g = cap;
-  if (g < 1) g = 1;
-  return (int)g;
+// ---- per-kernel profiling (bench.py roofline leg) ---------------------------------------------------
+int Ctx::prof_begin(const char* name) {
+  if (prof_used == (int)prof_events.size()) {
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return -1;
+    prof_events.push_back({a, b});
+  }
+  int slot = prof_used++;
+  prof_names.push_back(name);
+  cudaEventRecord(prof_events[slot].first, stream);
+  return slot;
+}
+void Ctx::prof_end(int slot) { cudaEventRecord(prof_events[slot].second, stream); }
+std::string Ctx::prof_report() {
+  cudaStreamSynchronize(stream);
+  struct Agg { int64_t n = 0; double ms = 0, mx = 0; };
+  std::vector<std::pair<std::string, Agg>> aggs;
+  for (int i = 0; i < prof_used; ++i) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, prof_events[i].first, prof_events[i].second) != cudaSuccess) continue;
+    size_t j = 0;
+    for (; j < aggs.size(); ++j)
+      if (aggs[j].first == prof_names[i]) break;
+    if (j == aggs.size()) aggs.push_back({prof_names[i], Agg()});
+    aggs[j].second.n++;
+    aggs[j].second.ms += ms;
+    aggs[j].second.mx = std::max(aggs[j].second.mx, (double)ms);
+  }
+  std::string out;
+  for (auto& a : aggs) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s\t%lld\t%.6f\t%.6f\n", a.first.c_str(), (long long)a.second.n, a.second.ms, a.second.mx);
+    out += buf;
+  }
+  prof_used = 0;
+  prof_names.clear();
+  return out;
 }
 
 // ================================================================================================

@@ -15,24 +15,10 @@
 #include <cstring>
 #include <numeric>
 
+#include "launch.h"
 #include "ops.h"
 
 namespace qgpu {
-
-#define LAUNCH(ctx, kernel, grid, block, smem, ...)                  \
-  do {                                                               \
-    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
-    (ctx)->launches++;                                               \
-    CUDA_CHECK(cudaGetLastError());                                  \
-  } while (0)
-
-static inline int grid_for(Ctx* ctx, int64_t n, int per_block) {
-  int64_t g = (n + per_block - 1) / per_block;
-  int64_t cap = (int64_t)ctx->sm_count * 16;
-  if (g > cap) g = cap;
-  if (g < 1) g = 1;
-  return (int)g;
-}
 
 #define MAX_KEYS 8
 #define NO_GROUP 0xffffffffu

@@ -1,6 +1,7 @@
 // Plan execution + table consolidation + the extern "C" surface declared in include/qgpu.h.
 #include <cstring>
 
+#include "launch.h"
 #include "plan.h"
 
 using namespace qgpu;
@@ -101,10 +102,8 @@ void TableImpl::consolidate() {
                                      ctx->stream));
         byte += p->str_bytes;
       } else if (p->phys == PH_D64 && phys == PH_I128) {
-        int g = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
-        k_widen_chunk<<<g, 256, 0, ctx->stream>>>((const int64_t*)p->data->ptr, (ulonglong2*)out->data->ptr + row, n);
-        ctx->launches++;
-        CUDA_CHECK(cudaGetLastError());
+        LAUNCH(ctx, k_widen_chunk, grid_for(ctx, n, 256), 256, 0, (const int64_t*)p->data->ptr,
+               (ulonglong2*)out->data->ptr + row, n);
       } else {
         CUDA_CHECK(cudaMemcpyAsync((char*)out->data->ptr + row * w, p->data->ptr, (size_t)n * w, cudaMemcpyDeviceToDevice,
                                    ctx->stream));
@@ -339,6 +338,10 @@ void qgpu_shutdown(qgpu_ctx* ctx) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->copy_stream);
+  for (auto& e : c->prof_events) {
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
   for (int i = 0; i < Ctx::kStageSlots; ++i) {
     if (c->stage[i]) cudaFreeHost(c->stage[i]);
     if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
@@ -362,6 +365,31 @@ int qgpu_set_compat(qgpu_ctx* ctx, const char* name, int value) {
 }
 
 int64_t qgpu_kernel_launches(const qgpu_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+
+void* qgpu_ctx_stream(const qgpu_ctx* ctx) { return ctx ? (void*)ctx->c.stream : nullptr; }
+
+int qgpu_profile_enable(qgpu_ctx* ctx, int on) {
+  if (!ctx) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] {
+    ctx->c.profiling = on != 0;
+    if (!on) ctx->c.prof_report();
+  });
+}
+
+int64_t qgpu_profile_report(qgpu_ctx* ctx, char* buf, int64_t cap) {
+  if (!ctx) return -1;
+  int64_t need = -1;
+  guard(&ctx->c, [&] {
+    std::string r = ctx->c.prof_report();
+    need = (int64_t)r.size() + 1;
+    if (buf && cap > 0) {
+      size_t n = std::min<size_t>(r.size(), (size_t)cap - 1);
+      memcpy(buf, r.data(), n);
+      buf[n] = 0;
+    }
+  });
+  return need;
+}
 
 // ---- tables ------------------------------------------------------------------------------------
 int qgpu_table_create(qgpu_ctx* ctx, const struct ArrowSchema* schema, qgpu_table** out) {
@@ -647,7 +675,22 @@ int qgpu_plan_last_stats(const qgpu_plan* p, double* device_ms, int64_t* launche
   return QGPU_OK;
 }
 
-const char* qgpu_plan_strategy(const qgpu_plan* p) { return p ? p->node->strategy.c_str() : ""; }
+static std::string describe_strategy(const PlanNode& n) {
+  std::string s = n.strategy;
+  if (!n.children.empty() && n.strategy.find("fused") == std::string::npos) {
+    s += " <- ";
+    if (n.children.size() > 1) s += "[";
+    for (size_t i = 0; i < n.children.size(); ++i) s += (i ? ", " : "") + describe_strategy(*n.children[i]);
+    if (n.children.size() > 1) s += "]";
+  }
+  return s;
+}
+
+const char* qgpu_plan_strategy(const qgpu_plan* p) {
+  if (!p) return "";
+  p->node->strategy_desc = describe_strategy(*p->node);
+  return p->node->strategy_desc.c_str();
+}
 
 void qgpu_plan_free(qgpu_plan* p) {
   if (!p) return;

@@ -39,6 +39,7 @@ struct PlanNode {
   double last_ms = 0;
   int64_t last_launches = 0;
   std::string strategy = "not-executed";
+  std::string strategy_desc;
 
   View execute();
 };

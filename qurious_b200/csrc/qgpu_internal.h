@@ -186,6 +186,16 @@ struct Ctx {
   void* pinned_scratch = nullptr;
   size_t pinned_scratch_bytes = 1 << 16;
 
+  // per-kernel CUDA-event profiling (off by default; qgpu_profile_enable)
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  std::vector<const char*> prof_names;
+  int prof_used = 0;
+  std::string prof_text;
+  int prof_begin(const char* name);
+  void prof_end(int slot);
+  std::string prof_report();  // "name\tlaunches\ttotal_ms\tmax_ms\n" per kernel; resets the log
+
   DBufP alloc(size_t bytes);
   DBufP alloc_zero(size_t bytes);
   void h2d(void* dst, const void* src, size_t bytes);        // pageable or pinned host -> device

@@ -291,6 +291,81 @@ def to_arrow(t: RawTable, batch_rows: Optional[int] = None) -> List[pa.RecordBat
     return [full.slice(o, min(batch_rows, t.rows - o)) for o in range(0, t.rows, batch_rows)]
 
 
+# ------------------------------------------------------------------------------------------------
+# RawTable -> HBM-resident table (no host round trip): Arrow-layout device buffers handed to the
+# library through qgpu_table_append_device (Arrow C Device Data Interface convention).
+# ------------------------------------------------------------------------------------------------
+def _device_string_buffers(codes: torch.Tensor, vocab: List[str]):
+    dev = codes.device
+    enc = [v.encode() for v in vocab]
+    maxlen = max(max(len(e) for e in enc), 1)
+    lens = torch.tensor([len(e) for e in enc], dtype=torch.int64, device=dev)
+    table = torch.zeros((len(enc), maxlen), dtype=torch.uint8, device=dev)
+    for i, e in enumerate(enc):
+        if e:
+            table[i, :len(e)] = torch.tensor(list(e), dtype=torch.uint8, device=dev)
+    row_len = lens[codes]
+    offsets = torch.zeros(codes.numel() + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(row_len, 0, out=offsets[1:])
+    total = int(offsets[-1].item())
+    if total >= (1 << 31):
+        raise ValueError("Utf8 column exceeds 2 GiB")
+    if bool((row_len == 1).all().item()):
+        data = table[codes, 0].contiguous()
+    else:
+        row_of = torch.repeat_interleave(torch.arange(codes.numel(), device=dev), row_len)
+        pos = torch.arange(total, device=dev) - offsets[row_of]
+        data = table[codes[row_of], pos].contiguous()
+    return offsets.to(torch.int32), data
+
+
+def to_device_table(ctx, t: RawTable, keep_arrow_layout: bool = False):
+    """Build an HBM-resident `MemoryTable` from a RawTable generated on `cuda` (bench.py device leg).
+    Decimals are handed over in Arrow layout (16 B little-endian two's complement); the library narrows
+    them itself exactly as it does for host batches."""
+    from pyarrow.cffi import ffi
+    from . import _lib
+    n = t.rows
+    keep = []
+    children = []
+    for f in t.schema:
+        bufs: List[int] = [0]
+        if f.name in t.cols:
+            x = t.cols[f.name]
+            if pa.types.is_decimal(f.type):
+                x = torch.stack([x, x >> 63], dim=1).contiguous()
+            elif f.type == pa.date32():
+                x = x.to(torch.int32).contiguous()
+            else:
+                x = x.contiguous()
+            keep.append(x)
+            bufs.append(x.data_ptr())
+        else:
+            off, data = _device_string_buffers(t.codes[f.name], t.vocab[f.name])
+            keep += [off, data]
+            bufs += [off.data_ptr(), data.data_ptr() if data.numel() else 0]
+        cb = ffi.new("const void*[]", [ffi.cast("void*", b) for b in bufs])
+        ca = ffi.new("struct ArrowArray*")
+        ca.length, ca.null_count, ca.offset = n, 0, 0
+        ca.n_buffers, ca.n_children = len(bufs), 0
+        ca.buffers = cb
+        ca.release = ffi.NULL
+        keep += [cb, ca]
+        children.append(ca)
+    top = ffi.new("struct ArrowArray*")
+    kids = ffi.new("struct ArrowArray*[]", children)
+    topbufs = ffi.new("const void*[]", [ffi.NULL])
+    top.length, top.null_count, top.offset = n, 0, 0
+    top.n_buffers, top.n_children = 1, len(children)
+    top.buffers, top.children, top.release = topbufs, kids, ffi.NULL
+    torch.cuda.synchronize()                     # generator kernels ran on torch's stream
+    dev = _lib.DeviceTable.create(ctx, t.schema)
+    dev.append_device_struct(_lib.addr(top))
+    dev.column_bytes(0)                          # consolidates + synchronises the library's D2D copies
+    del keep, kids, topbufs
+    return MemoryTable.from_device_table(dev)
+
+
 @dataclass
 class Database:
     sf: float
