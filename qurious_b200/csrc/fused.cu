@@ -1,10 +1,1171 @@
-// Fused scan -> predicate -> (group-by) aggregate pipeline kernels (filled in below).
+// Fused Scan -> pushed-down predicate -> (group-by) aggregate pipeline: ONE kernel over the resident
+// columns of a table, no selection vector, no materialised temporaries.  This is the hot path of
+// TPC-H Q6 / Q1 and of every HashAggregate/NoGroupingAggregate whose input is a
+// (filtered) MemoryTable scan:
+//   MemoryTable::scan + filter        qurious/src/datasource/memory.rs:69-98
+//   Filter::execute                   qurious/src/physical/plan/filter.rs:28-44
+//   BinaryExpr / CastExpr / Literal   qurious/src/physical/expr/{binary,cast,literal}.rs
+//   NoGroupingAggregate::execute      qurious/src/physical/plan/aggregate/no_grouping.rs:30-62
+//   HashAggregate / GroupAccumulator  qurious/src/physical/plan/aggregate/hash.rs:45-107,138-170
+//   Sum/Avg/Count/Min/Max             qurious/src/physical/expr/aggregate/*.rs
+//
+// Design (DESIGN.md "Fused scan-aggregate kernel"):
+//   * column tiles (1024 rows of every referenced column, in the narrowed resident layout) are staged
+//     into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx), 2-4 stages
+//     deep, one persistent CTA per SM; operands of the predicate / key / aggregate expressions are then
+//     addressed dynamically in shared memory, so one kernel serves every plan of the supported shape;
+//   * predicate  = conjunction of integer range tests (constants folded once on the host);
+//   * aggregates = SUM / MIN / MAX / COUNT / AVG over products of affine terms (a + b*column), exact in
+//     int64 per row -- proven from the column statistics, otherwise the generic i128 path runs -- with
+//     128-bit group totals;
+//   * grouping   = (a) DENSE: small key domain (dictionary codes / small integer ranges): every thread
+//     owns a private accumulator table in shared memory (no atomics, no inter-lane traffic per row),
+//     reduced once per CTA into the 128-bit global table; (b) HASH: HBM-resident open-addressing table
+//     on the packed key, claimed with atomicCAS, accumulators updated with 64-bit atomics (+ carry).
+// Anything outside this shape (NULLs, OR/!=, wide decimals, computed keys, ...) returns false and the
+// generic interpreter path (ops.cu) runs instead: same results, lower speed.
+#include <algorithm>
+#include <cstring>
+
+#include "launch.h"
 #include "plan.h"
 
 namespace qgpu {
-bool try_fused_scan_aggregate(PlanNode& agg, View* out) {
-  (void)agg;
-  (void)out;
-  return false;
+
+constexpr int F_T = 1024;   // rows per tile
+constexpr int F_NT = 256;   // threads per CTA
+constexpr int F_R = F_T / F_NT;
+constexpr int F_MAXC = 10, F_MAXP = 8, F_MAXK = 4, F_MAXA = 8, F_MAXF = 3;
+constexpr int F_SMEM_MAX = 232448 - 1024;  // 227 KB opt-in limit minus static slack
+enum { FK_SUM = 0, FK_MIN = 1, FK_MAX = 2, FK_SUMF = 3 };
+enum { FM_DENSE = 0, FM_HASH = 1 };
+#define F_EMPTY 0xffffffffffffffffULL
+
+struct FCol {
+  const unsigned char* ptr;
+  uint32_t width;     // 1, 2, 4, 8
+  uint32_t kind;      // 0 signed, 1 unsigned
+  uint32_t smem_off;  // offset of this column's tile inside a stage
+  uint32_t pad;
+};
+struct FPred {
+  int32_t col;
+  int32_t pad;
+  int64_t lo;
+  uint64_t span;  // pass iff (uint64)(x - lo) <= span
+};
+struct FKey {
+  int32_t col;
+  int32_t pad;
+  int64_t base;
+  uint64_t mult;  // code += (uint64)(x - base) * mult
+};
+struct FFactor {
+  int32_t col;
+  int32_t pad;
+  int64_t a, b;  // a + b * x
+};
+struct FAcc {
+  int32_t kind;
+  int32_t chain;  // 1: value = previous accumulator's value * factors
+  int32_t n_factors;
+  int32_t pad;
+  int64_t coef;
+  FFactor f[F_MAXF];
+};
+struct FParams {
+  int64_t n_rows, n_tiles;
+  int32_t n_cols, n_pred, n_keys, n_accs;
+  int32_t mode, stages, dense_groups, carry;
+  uint32_t stage_bytes, priv_off;
+  uint64_t cap_mask;  // HASH: capacity - 1 (slot `capacity` is reserved for the key whose code == F_EMPTY)
+  // DENSE: lo/hi[g * (n_accs + 2) + k];  HASH: lo/hi[k * (capacity + 1) + slot]
+  unsigned long long* g_lo;
+  unsigned long long* g_hi;
+  unsigned long long* t_keys;
+  unsigned long long* n_groups;
+  int* abort_flag;
+  FCol cols[F_MAXC];
+  FPred pred[F_MAXP];
+  FKey keys[F_MAXK];
+  FAcc accs[F_MAXA];
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D TMA bulk copy (SASS: UBLKCP / SYNCS)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t a = smem_u32(bar);
+  while (!ok) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ uint64_t fmix64(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+
+__device__ __forceinline__ int64_t ldc(const unsigned char* stage, const FCol& c, int r) {
+  const unsigned char* b = stage + c.smem_off;
+  switch (c.width) {
+    case 8: return *(const int64_t*)(b + (size_t)r * 8);
+    case 4: {
+      const int32_t v = *(const int32_t*)(b + (size_t)r * 4);
+      return c.kind ? (int64_t)(uint32_t)v : (int64_t)v;
+    }
+    case 2: {
+      const int16_t v = *(const int16_t*)(b + (size_t)r * 2);
+      return c.kind ? (int64_t)(uint16_t)v : (int64_t)v;
+    }
+    default: {
+      const int8_t v = *(const int8_t*)(b + r);
+      return c.kind ? (int64_t)(uint8_t)v : (int64_t)v;
+    }
+  }
+}
+
+__device__ __forceinline__ long long acc_init(const FParams& p, int k) {
+  if (k < p.n_accs) {
+    const int kind = p.accs[k].kind;
+    return kind == FK_MIN ? INT64_MAX : (kind == FK_MAX ? INT64_MIN : 0);
+  }
+  return k == p.n_accs ? 0 : INT64_MAX;  // row count, first row
+}
+
+__device__ __forceinline__ void add128_global(unsigned long long* lo, unsigned long long* hi, unsigned long long vlo,
+                                              unsigned long long vhi) {
+  const unsigned long long old = atomicAdd(lo, vlo);
+  const unsigned long long carry = (old + vlo < old) ? 1ull : 0ull;
+  if (vhi + carry) atomicAdd(hi, vhi + carry);
+}
+
+// value of accumulator k for row r of the staged tile
+__device__ __forceinline__ int64_t acc_value(const FParams& p, const FAcc& A, const unsigned char* stage, int r, int64_t prev) {
+  int64_t v = A.chain ? prev : A.coef;
+#pragma unroll
+  for (int f = 0; f < F_MAXF; ++f) {
+    if (f < A.n_factors) {
+      const int64_t x = ldc(stage, p.cols[A.f[f].col], r);
+      v *= (A.f[f].a + A.f[f].b * x);
+    }
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(F_NT, 1) k_fused_scan_agg(const __grid_constant__ FParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full = (uint64_t*)smem;
+  unsigned char* tiles = smem + 128;
+  long long* priv = (long long*)(smem + p.priv_off);
+  const int tid = threadIdx.x;
+  const int NA2 = p.n_accs + 2;
+
+  if (p.mode == FM_DENSE) {
+    const int total = p.dense_groups * NA2 * F_NT;
+    for (int i = tid; i < total; i += F_NT) priv[i] = acc_init(p, (i / F_NT) % NA2);
+  }
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int64_t first_tile = blockIdx.x;
+  const int64_t my_tiles = first_tile < p.n_tiles ? (p.n_tiles - first_tile + gridDim.x - 1) / gridDim.x : 0;
+
+  auto issue = [&](int64_t i) {
+    const int s = (int)(i % p.stages);
+    const int64_t t = first_tile + i * gridDim.x;
+    const int64_t row0 = t * F_T;
+    const int64_t rows = min((int64_t)F_T, p.n_rows - row0);
+    unsigned char* dst = tiles + (size_t)s * p.stage_bytes;
+    uint32_t total = 0;
+    for (int c = 0; c < p.n_cols; ++c) total += ((uint32_t)(rows * p.cols[c].width) + 15u) & ~15u;
+    mbar_expect_tx(&full[s], total);
+    for (int c = 0; c < p.n_cols; ++c) {
+      const uint32_t bytes = ((uint32_t)(rows * p.cols[c].width) + 15u) & ~15u;
+      bulk_g2s(dst + p.cols[c].smem_off, p.cols[c].ptr + (size_t)row0 * p.cols[c].width, bytes, &full[s]);
+    }
+  };
+  if (tid == 0)
+    for (int64_t i = 0; i < my_tiles && i < p.stages; ++i) issue(i);
+
+  for (int64_t i = 0; i < my_tiles; ++i) {
+    const int s = (int)(i % p.stages);
+    mbar_wait(&full[s], (uint32_t)((i / p.stages) & 1));
+    {
+      const unsigned char* stage = tiles + (size_t)s * p.stage_bytes;
+      const int64_t row0 = (first_tile + i * gridDim.x) * F_T;
+      const int rows = (int)min((int64_t)F_T, p.n_rows - row0);
+#pragma unroll 1
+      for (int j = 0; j < F_R; ++j) {
+        const int r = j * F_NT + tid;
+        bool pass = r < rows;
+#pragma unroll
+        for (int k = 0; k < F_MAXP; ++k) {
+          if (k < p.n_pred) {
+            const int64_t x = ldc(stage, p.cols[p.pred[k].col], r);
+            pass = pass && (((uint64_t)x - (uint64_t)p.pred[k].lo) <= p.pred[k].span);
+          }
+        }
+        if (!__any_sync(0xffffffffu, pass)) continue;
+        if (pass) {
+          uint64_t code = 0;
+#pragma unroll
+          for (int k = 0; k < F_MAXK; ++k) {
+            if (k < p.n_keys) {
+              const int64_t x = ldc(stage, p.cols[p.keys[k].col], r);
+              code += ((uint64_t)x - (uint64_t)p.keys[k].base) * p.keys[k].mult;
+            }
+          }
+          const long long row = row0 + r;
+          if (p.mode == FM_DENSE) {
+            long long* a = priv + (size_t)code * NA2 * F_NT + tid;
+            int64_t prev = 0;
+#pragma unroll
+            for (int k = 0; k < F_MAXA; ++k) {
+              if (k < p.n_accs) {
+                const FAcc& A = p.accs[k];
+                long long* slot = a + k * F_NT;
+                if (A.kind == FK_SUMF) {
+                  const double x = __longlong_as_double(ldc(stage, p.cols[A.f[0].col], r));
+                  *slot = __double_as_longlong(__longlong_as_double(*slot) + x);
+                } else {
+                  const int64_t v = acc_value(p, A, stage, r, prev);
+                  prev = v;
+                  const long long cur = *slot;
+                  *slot = A.kind == FK_SUM ? cur + v : (A.kind == FK_MIN ? min(cur, (long long)v) : max(cur, (long long)v));
+                }
+              }
+            }
+            a[p.n_accs * F_NT] += 1;
+            long long* fr = a + (p.n_accs + 1) * F_NT;
+            if (row < *fr) *fr = row;
+          } else {
+            // ---- HBM-resident open-addressing table on the packed key ----
+            uint64_t slot;
+            if (code == F_EMPTY) {
+              slot = p.cap_mask + 1;
+            } else {
+              slot = fmix64(code) & p.cap_mask;
+              int probes = 0;
+              while (true) {
+                unsigned long long cur = *(volatile unsigned long long*)&p.t_keys[slot];
+                if (cur == code) break;
+                if (((++probes) & 63) == 0 && *(volatile int*)p.abort_flag) {  // table (nearly) full: host retries larger
+                  slot = F_EMPTY;
+                  break;
+                }
+                if (cur == F_EMPTY) {
+                  cur = atomicCAS(&p.t_keys[slot], F_EMPTY, (unsigned long long)code);
+                  if (cur == F_EMPTY) {
+                    const unsigned long long ng = atomicAdd(p.n_groups, 1ull);
+                    if (2 * (ng + 1) > p.cap_mask + 1) *p.abort_flag = 1;
+                    break;
+                  }
+                  if (cur == code) break;
+                }
+                slot = (slot + 1) & p.cap_mask;
+              }
+            }
+            if (slot == F_EMPTY) continue;
+            const size_t stride = (size_t)p.cap_mask + 2;
+            int64_t prev = 0;
+#pragma unroll
+            for (int k = 0; k < F_MAXA; ++k) {
+              if (k < p.n_accs) {
+                const FAcc& A = p.accs[k];
+                unsigned long long* lo = p.g_lo + k * stride + slot;
+                if (A.kind == FK_SUMF) {
+                  atomicAdd((double*)lo, __longlong_as_double(ldc(stage, p.cols[A.f[0].col], r)));
+                } else {
+                  const int64_t v = acc_value(p, A, stage, r, prev);
+                  prev = v;
+                  if (A.kind == FK_SUM) {
+                    if (p.carry) add128_global(lo, p.g_hi + k * stride + slot, (unsigned long long)v, v < 0 ? ~0ull : 0ull);
+                    else atomicAdd(lo, (unsigned long long)v);
+                  } else if (A.kind == FK_MIN) {
+                    atomicMin((long long*)lo, (long long)v);
+                  } else {
+                    atomicMax((long long*)lo, (long long)v);
+                  }
+                }
+              }
+            }
+            atomicAdd(p.g_lo + (size_t)p.n_accs * stride + slot, 1ull);
+            atomicMin((long long*)(p.g_lo + (size_t)(p.n_accs + 1) * stride + slot), row);
+          }
+        }
+      }
+    }
+    // every thread is done with stage s before it is refilled; the same barrier broadcasts the abort flag
+    const int aborted = __syncthreads_or(p.mode == FM_HASH && tid == 0 && *(volatile int*)p.abort_flag != 0);
+    if (aborted) {
+      // drain the copies already in flight (the CTA's shared memory must outlive them), then leave
+      if (tid == 0)
+        for (int64_t j = i + 1; j < my_tiles && j < i + p.stages; ++j)
+          mbar_wait(&full[(int)(j % p.stages)], (uint32_t)((j / p.stages) & 1));
+      return;
+    }
+    if (tid == 0 && i + p.stages < my_tiles) issue(i + p.stages);
+  }
+
+  // ---- DENSE: reduce the per-thread private tables once per CTA into the 128-bit global table ----
+  if (p.mode == FM_DENSE) {
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5;
+    const int n_lines = p.dense_groups * NA2;
+    for (int line = warp; line < n_lines; line += F_NT / 32) {
+      const int k = line % NA2;
+      const int g = line / NA2;
+      const long long* src = priv + (size_t)line * F_NT;
+      int kind = FK_SUM;
+      if (k < p.n_accs) kind = p.accs[k].kind;
+      else if (k == p.n_accs + 1) kind = FK_MIN;
+      // skip groups this CTA never saw
+      long long cnt = 0;
+      {
+        const long long* csrc = priv + ((size_t)g * NA2 + p.n_accs) * F_NT;
+        for (int j = lane; j < F_NT; j += 32) cnt += csrc[j];
+#pragma unroll
+        for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+      }
+      if (cnt == 0) continue;
+      unsigned long long* glo = p.g_lo + line;
+      unsigned long long* ghi = p.g_hi + line;
+      if (kind == FK_SUM) {
+        i128 s = 0;
+        for (int j = lane; j < F_NT; j += 32) s += (i128)src[j];
+        unsigned long long lo = (unsigned long long)(u128)s, hi = (unsigned long long)((u128)s >> 64);
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+          const unsigned long long olo = __shfl_xor_sync(0xffffffffu, lo, d), ohi = __shfl_xor_sync(0xffffffffu, hi, d);
+          const u128 t = (((u128)hi << 64) | lo) + (((u128)ohi << 64) | olo);
+          lo = (unsigned long long)t;
+          hi = (unsigned long long)(t >> 64);
+        }
+        if (lane == 0) add128_global(glo, ghi, lo, hi);
+      } else if (kind == FK_SUMF) {
+        double s = 0;
+        for (int j = lane; j < F_NT; j += 32) s += __longlong_as_double(src[j]);
+#pragma unroll
+        for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (lane == 0) atomicAdd((double*)glo, s);
+      } else {
+        long long m = kind == FK_MIN ? INT64_MAX : INT64_MIN;
+        for (int j = lane; j < F_NT; j += 32) m = kind == FK_MIN ? min(m, src[j]) : max(m, src[j]);
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+          const long long o = __shfl_xor_sync(0xffffffffu, m, d);
+          m = kind == FK_MIN ? min(m, o) : max(m, o);
+        }
+        if (lane == 0) {
+          if (kind == FK_MIN) atomicMin((long long*)glo, m);
+          else atomicMax((long long*)glo, m);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// global table init + export to the GroupAccs layout consumed by finish_aggregate (ops.cu)
+// ------------------------------------------------------------------------------------------------
+struct FInit {
+  long long v[F_MAXA + 2];
+};
+__global__ void k_fused_init(unsigned long long* lo, unsigned long long* hi, int64_t n_slots, int na2, int dense, FInit init) {
+  const int64_t total = n_slots * na2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int k = dense ? (int)(i % na2) : (int)(i / n_slots);
+    lo[i] = (unsigned long long)init.v[k];
+    if (hi) hi[i] = 0;
+  }
+}
+
+__global__ void k_fused_occupied(const unsigned long long* __restrict__ lo, int64_t n_slots, int64_t cnt_base, int64_t cnt_stride,
+                                 int64_t* __restrict__ flags) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_slots; g += stride)
+    flags[g] = lo[cnt_base + g * cnt_stride] != 0 ? 1 : 0;
+}
+
+struct FExport {
+  int n_aggs;
+  int acc_of[24];   // accumulator index per aggregate (-1: COUNT only)
+  int kind_of[24];  // FK_* of that accumulator
+  int wide[24];     // 1: the accumulator has a real hi word (DENSE sums / carry mode)
+  unsigned long long* out_lo[24];
+  unsigned long long* out_hi[24];
+};
+__global__ void k_fused_export(const unsigned long long* __restrict__ lo, const unsigned long long* __restrict__ hi, int64_t n_slots,
+                               int64_t k_stride, int64_t g_stride, int n_accs, const int64_t* __restrict__ flags,
+                               const int64_t* __restrict__ offs, FExport ex, unsigned long long* __restrict__ out_cnt,
+                               long long* __restrict__ out_first) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_slots; g += stride) {
+    if (!flags[g]) continue;
+    const int64_t o = offs[g];
+    out_cnt[o] = lo[(int64_t)n_accs * k_stride + g * g_stride];
+    out_first[o] = (long long)lo[(int64_t)(n_accs + 1) * k_stride + g * g_stride];
+    for (int a = 0; a < ex.n_aggs; ++a) {
+      const int k = ex.acc_of[a];
+      if (k < 0) continue;
+      const unsigned long long l = lo[(int64_t)k * k_stride + g * g_stride];
+      unsigned long long h = 0;
+      if (ex.wide[a]) h = hi[(int64_t)k * k_stride + g * g_stride];
+      else if (ex.kind_of[a] != FK_SUMF) h = ((long long)l < 0) ? ~0ull : 0ull;
+      ex.out_lo[a][o] = l;
+      ex.out_hi[a][o] = h;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dictionary encoding of low-cardinality Utf8 columns (<= 255 distinct values)
+// ------------------------------------------------------------------------------------------------
+#define DICT_CAP 1024
+__device__ __forceinline__ uint64_t str_hash(const char* s, int len) {
+  uint64_t x = 0xcbf29ce484222325ULL ^ (uint64_t)len;
+  for (int i = 0; i < len; ++i) x = (x ^ (unsigned char)s[i]) * 0x100000001b3ULL;
+  return fmix64(x);
+}
+// slots[s] = (tag32 << 32) | (rep_row + 1); row_slot[row] = s
+__global__ void __launch_bounds__(256) k_dict_insert(const int32_t* __restrict__ offs, const char* __restrict__ data, int64_t n,
+                                                     unsigned long long* __restrict__ slots, uint16_t* __restrict__ row_slot,
+                                                     unsigned int* __restrict__ n_dict, int* __restrict__ abort_flag) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride) {
+    if (*(volatile int*)abort_flag) return;
+    const int32_t o0 = offs[row], len = offs[row + 1] - o0;
+    const uint64_t h = str_hash(data + o0, len);
+    const uint32_t tag = (uint32_t)(h >> 32);
+    uint32_t s = (uint32_t)h & (DICT_CAP - 1);
+    const unsigned long long mine = ((unsigned long long)tag << 32) | (unsigned long long)(row + 1);
+    while (true) {
+      unsigned long long cur = *(volatile unsigned long long*)&slots[s];
+      if (cur == 0) {
+        cur = atomicCAS(&slots[s], 0ull, mine);
+        if (cur == 0) {
+          if (atomicAdd(n_dict, 1u) >= 255u) *abort_flag = 1;
+          break;
+        }
+      }
+      if ((uint32_t)(cur >> 32) == tag) {
+        const int64_t rep = (int64_t)(cur & 0xffffffffull) - 1;
+        const int32_t r0 = offs[rep], rl = offs[rep + 1] - r0;
+        bool eq = rl == len;
+        for (int i = 0; eq && i < len; ++i) eq = data[r0 + i] == data[o0 + i];
+        if (eq) break;
+      }
+      s = (s + 1) & (DICT_CAP - 1);
+    }
+    row_slot[row] = (uint16_t)s;
+  }
+}
+__global__ void k_dict_codes(const uint16_t* __restrict__ row_slot, const uint8_t* __restrict__ slot_code, int64_t n,
+                             uint8_t* __restrict__ codes) {
+  __shared__ uint8_t lut[DICT_CAP];
+  for (int i = threadIdx.x; i < DICT_CAP; i += blockDim.x) lut[i] = slot_code[i];
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) codes[i] = lut[row_slot[i]];
+}
+
+// Build (once per resident column) the dictionary encoding; returns false when the column has more
+// than 255 distinct values, NULLs, or rows beyond the u32 representative-row range.
+static bool ensure_dict(Ctx* ctx, DCol& col) {
+  if (col.dict_state != 0) return col.dict_state > 0;
+  col.dict_state = -1;
+  if (col.phys != PH_STR || col.null_count != 0 || col.length == 0 || col.length >= 0xfffffff0LL) return false;
+  const int64_t n = col.length;
+  DBufP slots = ctx->alloc_zero(DICT_CAP * 8);
+  DBufP row_slot = ctx->alloc((size_t)n * 2);
+  DBufP flags = ctx->alloc_zero(8);
+  LAUNCH(ctx, k_dict_insert, grid_for(ctx, n, 256 * 4), 256, 0, (const int32_t*)col.offsets->ptr, (const char*)col.data->ptr, n,
+         (unsigned long long*)slots->ptr, (uint16_t*)row_slot->ptr, (unsigned int*)flags->ptr, (int*)((char*)flags->ptr + 4));
+  struct { unsigned int n; int abort_; } h;
+  ctx->d2h_sync(&h, flags->ptr, 8);
+  if (h.abort_ || h.n > 255) return false;
+  std::vector<unsigned long long> hs(DICT_CAP);
+  ctx->d2h_sync(hs.data(), slots->ptr, DICT_CAP * 8);
+  // codes in ascending representative-row order (deterministic); fetch the strings of the representatives
+  std::vector<std::pair<long long, int>> reps;
+  for (int s = 0; s < DICT_CAP; ++s)
+    if (hs[s]) reps.push_back({(long long)(hs[s] & 0xffffffffull) - 1, s});
+  std::sort(reps.begin(), reps.end());
+  std::vector<uint8_t> slot_code(DICT_CAP, 0);
+  std::vector<long long> rep_rows;
+  for (size_t i = 0; i < reps.size(); ++i) {
+    slot_code[reps[i].second] = (uint8_t)i;
+    rep_rows.push_back(reps[i].first);
+  }
+  DBufP idx = ctx->alloc(rep_rows.size() * 8);
+  ctx->h2d(idx->ptr, rep_rows.data(), rep_rows.size() * 8);
+  ctx->sync();
+  DColP taken = take_column(ctx, col, (const int64_t*)idx->ptr, (int64_t)rep_rows.size());
+  std::vector<int32_t> toffs(rep_rows.size() + 1);
+  ctx->d2h_sync(toffs.data(), taken->offsets->ptr, toffs.size() * 4);
+  std::vector<char> tdata((size_t)std::max<int64_t>(taken->str_bytes, 1));
+  if (taken->str_bytes > 0) ctx->d2h_sync(tdata.data(), taken->data->ptr, (size_t)taken->str_bytes);
+  col.dict_values.clear();
+  for (size_t i = 0; i < rep_rows.size(); ++i) col.dict_values.emplace_back(tdata.data() + toffs[i], (size_t)(toffs[i + 1] - toffs[i]));
+  DBufP sc = ctx->alloc(DICT_CAP);
+  ctx->h2d(sc->ptr, slot_code.data(), DICT_CAP);
+  ctx->sync();
+  col.dict_codes = ctx->alloc((size_t)n);
+  LAUNCH(ctx, k_dict_codes, grid_for(ctx, n, 256 * 8), 256, 0, (const uint16_t*)row_slot->ptr, (const uint8_t*)sc->ptr, n,
+         (uint8_t*)col.dict_codes->ptr);
+  col.dict_state = 1;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side plan analysis
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Unsupported {};  // thrown to leave the fused path (the generic path then runs)
+
+const i128 LIM62 = (i128)1 << 62;
+
+struct Slot {
+  DCol* col;
+  bool dict;
+  i128 vmin, vmax;
+};
+
+struct Poly {                      // coef * prod(a_i + b_i * x_i)
+  i128 coef = 1;
+  std::vector<FFactor> fs;
+  i128 lo = 1, hi = 1;             // value range
+  DType type;
+};
+
+struct Analyzer {
+  Ctx* ctx;
+  const View& v;
+  std::vector<Slot> slots;
+  std::vector<int> slot_view_col;
+
+  int slot_for(int view_col, bool want_dict) {
+    if (view_col < 0 || view_col >= (int)v.cols.size()) throw Unsupported();
+    const LazyCol& lc = v.cols[view_col];
+    if (!lc.base || lc.idx) throw Unsupported();
+    DCol& c = *lc.base;
+    if (c.null_count != 0 || c.length != v.num_rows) throw Unsupported();
+    for (size_t i = 0; i < slots.size(); ++i)
+      if (slots[i].col == &c && slots[i].dict == want_dict) return (int)i;
+    Slot s;
+    s.col = &c;
+    s.dict = want_dict;
+    if (want_dict) {
+      if (!ensure_dict(ctx, c)) throw Unsupported();
+      s.vmin = 0;
+      s.vmax = (i128)c.dict_values.size() - 1;
+    } else {
+      switch (c.phys) {
+        case PH_I8: case PH_I16: case PH_I32: case PH_I64: case PH_D64: case PH_U8: case PH_U16: case PH_U32: break;
+        default: throw Unsupported();
+      }
+      ensure_stats(ctx, c);
+      if (!c.has_stats) throw Unsupported();
+      s.vmin = c.vmin;
+      s.vmax = c.vmax;
+    }
+    if ((int)slots.size() >= F_MAXC) throw Unsupported();
+    slots.push_back(s);
+    slot_view_col.push_back(view_col);
+    return (int)slots.size() - 1;
+  }
+  int f64_slot_for(int view_col) {
+    if (view_col < 0 || view_col >= (int)v.cols.size()) throw Unsupported();
+    const LazyCol& lc = v.cols[view_col];
+    if (!lc.base || lc.idx) throw Unsupported();
+    DCol& c = *lc.base;
+    if (c.null_count != 0 || c.phys != PH_F64 || c.length != v.num_rows) throw Unsupported();
+    for (size_t i = 0; i < slots.size(); ++i)
+      if (slots[i].col == &c) return (int)i;
+    if ((int)slots.size() >= F_MAXC) throw Unsupported();
+    slots.push_back({&c, false, 0, 0});
+    slot_view_col.push_back(view_col);
+    return (int)slots.size() - 1;
+  }
+
+  static bool const_i128(const Compiled& c, i128* out) {
+    if (!c.is_const || !c.const_val.valid) return false;
+    switch (class_of(c.result_type)) {
+      case VC_INT: *out = (i128)(int64_t)c.const_val.lo; return true;
+      case VC_UINT: case VC_BOOL: *out = (i128)(uint64_t)c.const_val.lo; return true;
+      case VC_DEC: *out = val_i128(c.const_val); return true;
+      default: return false;
+    }
+  }
+
+  static void check_range(i128 lo, i128 hi) {
+    if (lo <= -LIM62 || hi >= LIM62) throw Unsupported();
+  }
+  static void mul_range(i128 alo, i128 ahi, i128 blo, i128 bhi, i128* lo, i128* hi) {
+    check_range(alo, ahi);
+    check_range(blo, bhi);
+    const i128 c[4] = {alo * blo, alo * bhi, ahi * blo, ahi * bhi};
+    *lo = std::min(std::min(c[0], c[1]), std::min(c[2], c[3]));
+    *hi = std::max(std::max(c[0], c[1]), std::max(c[2], c[3]));
+    check_range(*lo, *hi);
+  }
+  // the declared integer width must not wrap (narrow ints wrap in the reference; we only take the proven-safe case)
+  static void check_width(const DType& t, i128 lo, i128 hi) {
+    if (t.is_signed_int() || t.is_date()) {
+      const int bits = arrow_width(t) * 8;
+      const i128 lim = (i128)1 << (bits - 1);
+      if (lo < -lim || hi >= lim) throw Unsupported();
+    } else if (t.is_unsigned_int()) {
+      const int bits = arrow_width(t) * 8;
+      if (lo < 0 || hi >= ((i128)1 << bits)) throw Unsupported();
+    }
+  }
+
+  Poly analyze(const ExprNode& n) {
+    auto c = compile_expr(n, v.schema);
+    if (c->deferred_err) throw Unsupported();
+    Poly p;
+    p.type = c->result_type;
+    const VClass vc = class_of(c->result_type);
+    if (vc != VC_INT && vc != VC_UINT && vc != VC_DEC) throw Unsupported();
+    i128 cv;
+    if (c->is_const) {
+      if (!const_i128(*c, &cv)) throw Unsupported();
+      check_range(cv, cv);
+      p.coef = cv;
+      p.lo = p.hi = cv;
+      return p;
+    }
+    switch (n.kind) {
+      case QGPU_IR_COLUMN: {
+        const int s = slot_for(n.col_index, false);
+        FFactor f;
+        memset(&f, 0, sizeof(f));
+        f.col = s;
+        f.a = 0;
+        f.b = 1;
+        p.fs.push_back(f);
+        p.lo = slots[s].vmin;
+        p.hi = slots[s].vmax;
+        check_range(p.lo, p.hi);
+        return p;
+      }
+      case QGPU_IR_NEGATIVE: {
+        Poly q = analyze(*n.children[0]);
+        q.coef = -q.coef;
+        const i128 lo = -q.hi, hi = -q.lo;
+        q.lo = lo;
+        q.hi = hi;
+        q.type = p.type;
+        check_width(p.type, q.lo, q.hi);
+        return q;
+      }
+      case QGPU_IR_BINARY: {
+        Poly l = analyze(*n.children[0]);
+        Poly r = analyze(*n.children[1]);
+        if (n.op == 10) {
+          p.coef = l.coef * r.coef;
+          check_range(p.coef, p.coef);
+          p.fs = l.fs;
+          p.fs.insert(p.fs.end(), r.fs.begin(), r.fs.end());
+          mul_range(l.lo, l.hi, r.lo, r.hi, &p.lo, &p.hi);
+          check_width(p.type, p.lo, p.hi);
+          return p;
+        }
+        if (n.op != 8 && n.op != 9) throw Unsupported();
+        // affine (+/-): each side is a constant or coef * (a + b x) with a single factor
+        i128 ml = 1, mr = 1;
+        if (vc == VC_DEC) {
+          ml = pow10_i128(p.type.scale - l.type.scale);
+          mr = pow10_i128(p.type.scale - r.type.scale);
+        }
+        auto affine = [&](const Poly& q, i128 m, i128* a, i128* b, int* col) {
+          if (q.fs.size() > 1) throw Unsupported();
+          if (q.fs.empty()) {
+            *a = q.coef * m;
+            *b = 0;
+            *col = -1;
+          } else {
+            *a = q.coef * m * q.fs[0].a;
+            *b = q.coef * m * q.fs[0].b;
+            *col = q.fs[0].col;
+          }
+          check_range(*a, *a);
+          check_range(*b, *b);
+        };
+        i128 al, bl, ar, br;
+        int cl, cr;
+        affine(l, ml, &al, &bl, &cl);
+        affine(r, mr, &ar, &br, &cr);
+        if (cl >= 0 && cr >= 0 && cl != cr) throw Unsupported();
+        const int sgn = n.op == 8 ? 1 : -1;
+        const i128 a = al + sgn * ar, b = bl + sgn * br;
+        const int col = cl >= 0 ? cl : cr;
+        check_range(a, a);
+        check_range(b, b);
+        i128 lo = l.lo * ml, hi = l.hi * ml, rlo = r.lo * mr, rhi = r.hi * mr;
+        check_range(lo, hi);
+        check_range(rlo, rhi);
+        p.lo = sgn > 0 ? lo + rlo : lo - rhi;
+        p.hi = sgn > 0 ? hi + rhi : hi - rlo;
+        check_range(p.lo, p.hi);
+        check_width(p.type, p.lo, p.hi);
+        if (col < 0 || b == 0) {
+          p.coef = a;
+          p.lo = p.hi = a;
+          return p;
+        }
+        FFactor f;
+        memset(&f, 0, sizeof(f));
+        f.col = col;
+        f.a = (int64_t)a;
+        f.b = (int64_t)b;
+        p.coef = 1;
+        p.fs.push_back(f);
+        return p;
+      }
+      default: throw Unsupported();
+    }
+  }
+};
+
+void flatten_and(const ExprNode& n, std::vector<const ExprNode*>& out) {
+  if (n.kind == QGPU_IR_BINARY && n.op == 6) {
+    flatten_and(*n.children[0], out);
+    flatten_and(*n.children[1], out);
+  } else {
+    out.push_back(&n);
+  }
+}
+
+struct Range {
+  i128 lo, hi;
+};
+
+}  // namespace
+
+bool try_fused_scan_aggregate(PlanNode& agg, View* out) {
+  Ctx* ctx = agg.ctx;
+  // ---- shape: Aggregate <- (Filter <-)* Scan --------------------------------------------------------
+  std::vector<const ExprNode*> predicates;
+  PlanNode* n = agg.children[0].get();
+  while (n->kind == PK_FILTER) {
+    predicates.push_back(n->predicate.get());
+    n = n->children[0].get();
+  }
+  if (n->kind != PK_SCAN) return false;
+  if (n->predicate) predicates.push_back(n->predicate.get());
+  if ((int)agg.aggs.size() > 24 || agg.aggs.empty() || (int)agg.group_exprs.size() > F_MAXK) return false;
+  View v = scan_view(*n);
+  if (v.num_batches == 0 || v.num_rows == 0 || v.num_rows >= ((int64_t)1 << 40)) return false;
+  if (agg.schema.fields.size() != agg.group_exprs.size() + agg.aggs.size()) return false;
+
+  FParams P;
+  memset(&P, 0, sizeof(P));
+  std::vector<std::shared_ptr<Compiled>> keys;
+  std::vector<AggSpec> specs;
+  std::vector<int> acc_of(agg.aggs.size(), -1);
+  std::vector<i128> acc_maxabs;
+  bool dense_ok = true;
+  i128 dense_groups = 1;
+  int total_bits = 0;
+  Analyzer A{ctx, v, {}, {}};
+  try {
+    // same validation (and the same errors) as the generic path
+    for (auto& e : agg.group_exprs) keys.push_back(compile_expr(*e, v.schema));
+    for (auto& a : agg.aggs) {
+      AggSpec s;
+      s.op = a.op;
+      s.arg = compile_expr(*a.expr, v.schema);
+      s.return_type = a.return_type;
+      s.expr_type = a.expr_type;
+      specs.push_back(s);
+    }
+    validate_agg_types(specs);
+    for (auto& k : keys) check_hash_key_type(k->result_type);
+
+    // ---- predicate: conjunction of range tests ------------------------------------------------------
+    std::vector<const ExprNode*> terms;
+    for (auto* pe : predicates) flatten_and(*pe, terms);
+    std::vector<std::pair<int, Range>> ranges;
+    for (const ExprNode* t : terms) {
+      auto ct = compile_expr(*t, v.schema);  // type-checks the comparison exactly like the generic path
+      if (ct->result_type.id != QGPU_T_BOOL) return false;
+      if (t->kind != QGPU_IR_BINARY || t->op > 5) return false;
+      const ExprNode* cn = t->children[0].get();
+      const ExprNode* kn = t->children[1].get();
+      int op = t->op;
+      if (cn->kind != QGPU_IR_COLUMN) {
+        std::swap(cn, kn);
+        static const int flip[6] = {0, 1, 4, 5, 2, 3};  // c op x  ==  x flip(op) c
+        op = flip[op];
+      }
+      if (cn->kind != QGPU_IR_COLUMN) return false;
+      auto kc = compile_expr(*kn, v.schema);
+      if (!kc->is_const || !kc->const_val.valid || kc->deferred_err) return false;
+      const DType ct_type = v.schema.fields[cn->col_index].type;
+      Range r{-(LIM62 * 2), LIM62 * 2 - 1};  // int64 domain
+      int slot;
+      if (ct_type.id == QGPU_T_UTF8) {
+        if (op != 0) return false;
+        slot = A.slot_for(cn->col_index, true);
+        const std::string lit(kc->blob.data() + kc->const_val.lo, (size_t)kc->const_val.hi);
+        const auto& dv = A.slots[slot].col->dict_values;
+        auto it = std::find(dv.begin(), dv.end(), lit);
+        if (it == dv.end()) r = Range{1, 0};
+        else r = Range{(i128)(it - dv.begin()), (i128)(it - dv.begin())};
+      } else {
+        i128 c;
+        if (!Analyzer::const_i128(*kc, &c)) return false;
+        slot = A.slot_for(cn->col_index, false);
+        switch (op) {
+          case 0: r = Range{c, c}; break;
+          case 2: r.lo = c + 1; break;
+          case 3: r.lo = c; break;
+          case 4: r.hi = c - 1; break;
+          case 5: r.hi = c; break;
+          default: return false;  // != is not a range
+        }
+      }
+      bool merged = false;
+      for (auto& pr : ranges)
+        if (pr.first == slot) {
+          pr.second.lo = std::max(pr.second.lo, r.lo);
+          pr.second.hi = std::min(pr.second.hi, r.hi);
+          merged = true;
+        }
+      if (!merged) ranges.push_back({slot, r});
+    }
+    if ((int)ranges.size() > F_MAXP) return false;
+    for (auto& pr : ranges) {
+      FPred& fp = P.pred[P.n_pred++];
+      fp.col = pr.first;
+      i128 lo = std::max(pr.second.lo, -(LIM62 * 2)), hi = std::min(pr.second.hi, LIM62 * 2 - 1);
+      if (lo > hi) {  // empty: no row passes
+        fp.lo = 1;
+        fp.span = 0;
+        fp.col = pr.first;
+        // (x - 1) <= 0 only for x == 1; make it impossible by pairing with a second contradictory test
+        if (P.n_pred >= F_MAXP) return false;
+        FPred& fq = P.pred[P.n_pred++];
+        fq.col = pr.first;
+        fq.lo = 2;
+        fq.span = 0;
+      } else {
+        fp.lo = (int64_t)lo;
+        fp.span = (uint64_t)(hi - lo);
+      }
+    }
+
+    // ---- group keys: bare columns, packed into one code ----------------------------------------------
+    for (size_t i = 0; i < keys.size(); ++i) {
+      if (!keys[i]->is_column_ref) return false;
+      const DType kt = keys[i]->result_type;
+      const int slot = A.slot_for(keys[i]->column_ref, kt.id == QGPU_T_UTF8);
+      const i128 range = A.slots[slot].vmax - A.slots[slot].vmin + 1;
+      FKey& fk = P.keys[P.n_keys++];
+      fk.col = slot;
+      fk.base = (int64_t)A.slots[slot].vmin;
+      int bits = 0;
+      while (((i128)1 << bits) < range) ++bits;
+      // DENSE: mixed-radix index; HASH: bit-packed code (filled below once the mode is known)
+      fk.mult = (uint64_t)dense_groups;  // provisional (dense)
+      fk.pad = bits;
+      if (dense_ok) {
+        dense_groups *= range;
+        if (dense_groups > 4096) dense_ok = false;
+      }
+      total_bits += bits;
+    }
+    if (total_bits > 64) return false;
+
+    // ---- accumulators ---------------------------------------------------------------------------------
+    std::vector<std::string> acc_sig;
+    for (size_t i = 0; i < specs.size(); ++i) {
+      AggSpec& s = specs[i];
+      if (s.arg->deferred_err) return false;
+      if (s.op == QGPU_AGG_COUNT) {
+        // COUNT(x): x must be provably non-NULL for every row
+        if (s.arg->is_const) {
+          if (!s.arg->const_val.valid) return false;
+        } else if (s.arg->is_column_ref) {
+          const LazyCol& lc = v.cols[s.arg->column_ref];
+          if (!lc.base || lc.idx || lc.base->null_count != 0) return false;
+        } else {
+          A.analyze(*agg.aggs[i].expr);  // arithmetic over non-NULL columns is never NULL
+        }
+        continue;
+      }
+      FAcc fa;
+      memset(&fa, 0, sizeof(fa));
+      i128 maxabs = 0;
+      const VClass vc = class_of(s.arg->result_type);
+      if (vc == VC_FLT) {
+        if (!(s.op == QGPU_AGG_SUM || s.op == QGPU_AGG_AVG) || !s.arg->is_column_ref || s.arg->result_type.id != QGPU_T_FLOAT64)
+          return false;
+        fa.kind = FK_SUMF;
+        fa.n_factors = 1;
+        fa.f[0].col = A.f64_slot_for(s.arg->column_ref);
+        fa.f[0].a = 0;
+        fa.f[0].b = 1;
+        fa.coef = 1;
+      } else {
+        Poly p = A.analyze(*agg.aggs[i].expr);
+        if (p.fs.size() > F_MAXF) return false;
+        fa.kind = (s.op == QGPU_AGG_MIN) ? FK_MIN : (s.op == QGPU_AGG_MAX ? FK_MAX : FK_SUM);
+        fa.coef = (int64_t)p.coef;
+        fa.n_factors = (int)p.fs.size();
+        for (size_t f = 0; f < p.fs.size(); ++f) fa.f[f] = p.fs[f];
+        // every prefix product must stay inside int64
+        i128 lo = p.coef, hi = p.coef;
+        for (size_t f = 0; f < p.fs.size(); ++f) {
+          const Slot& sl = A.slots[p.fs[f].col];
+          i128 flo = (i128)p.fs[f].a + (i128)p.fs[f].b * sl.vmin, fhi = (i128)p.fs[f].a + (i128)p.fs[f].b * sl.vmax;
+          if (flo > fhi) std::swap(flo, fhi);
+          Analyzer::mul_range(lo, hi, flo, fhi, &lo, &hi);
+        }
+        maxabs = std::max(lo < 0 ? -lo : lo, hi < 0 ? -hi : hi);
+      }
+      std::string sig((const char*)&fa, sizeof(fa));
+      int found = -1;
+      for (size_t j = 0; j < acc_sig.size(); ++j)
+        if (acc_sig[j] == sig) found = (int)j;
+      if (found < 0) {
+        if (P.n_accs >= F_MAXA) return false;
+        found = P.n_accs;
+        P.accs[P.n_accs++] = fa;
+        acc_sig.push_back(sig);
+        acc_maxabs.push_back(maxabs);
+      }
+      acc_of[i] = found;
+    }
+  } catch (Unsupported&) {
+    return false;
+  }
+  // chain detection: accumulator k = accumulator k-1 times extra factors (prefix test on the full factor lists)
+  {
+    std::vector<FAcc> full(P.accs, P.accs + P.n_accs);
+    for (int k = 1; k < P.n_accs; ++k) {
+      const FAcc& prv = full[k - 1];
+      FAcc& cur = P.accs[k];
+      if (full[k].kind == FK_SUMF || prv.kind == FK_SUMF) continue;
+      if (prv.n_factors == 0 || prv.n_factors > full[k].n_factors || prv.coef != full[k].coef) continue;
+      bool prefix = true;
+      for (int f = 0; f < prv.n_factors && prefix; ++f)
+        prefix = prv.f[f].col == full[k].f[f].col && prv.f[f].a == full[k].f[f].a && prv.f[f].b == full[k].f[f].b;
+      if (!prefix) continue;
+      cur.chain = 1;
+      cur.n_factors = full[k].n_factors - prv.n_factors;
+      for (int f = 0; f < cur.n_factors; ++f) cur.f[f] = full[k].f[prv.n_factors + f];
+    }
+  }
+
+  // ---- columns + shared-memory layout -------------------------------------------------------------------
+  const int64_t n_rows = v.num_rows;
+  P.n_rows = n_rows;
+  P.n_tiles = (n_rows + F_T - 1) / F_T;
+  P.n_cols = (int)A.slots.size();
+  uint32_t stage_bytes = 0;
+  for (int c = 0; c < P.n_cols; ++c) {
+    const Slot& s = A.slots[c];
+    FCol& fc = P.cols[c];
+    if (s.dict) {
+      fc.ptr = (const unsigned char*)s.col->dict_codes->ptr;
+      fc.width = 1;
+      fc.kind = 1;
+    } else {
+      fc.ptr = (const unsigned char*)s.col->data->ptr;
+      fc.width = (uint32_t)phys_width(s.col->phys);
+      fc.kind = (s.col->phys == PH_U8 || s.col->phys == PH_U16 || s.col->phys == PH_U32) ? 1 : 0;
+    }
+    if (((uintptr_t)fc.ptr & 15) != 0) return false;
+    fc.smem_off = stage_bytes;
+    stage_bytes += (uint32_t)(((size_t)F_T * fc.width + 127) & ~(size_t)127);
+  }
+  if (P.n_cols == 0) return false;  // nothing to stream (COUNT(*) without predicate): generic path
+  P.stage_bytes = stage_bytes;
+  const int NA2 = P.n_accs + 2;
+  const int grid_max = ctx->sm_count;
+  const int64_t tiles_per_cta = (P.n_tiles + grid_max - 1) / grid_max;
+  // DENSE needs: small domain, private tables + >= 2 stages in shared memory, int64-safe per-thread partial sums
+  size_t priv_bytes = 0;
+  if (dense_ok) {
+    priv_bytes = (size_t)dense_groups * NA2 * F_NT * 8;
+    if (priv_bytes + 128 + 2 * (size_t)stage_bytes > (size_t)F_SMEM_MAX) dense_ok = false;
+    for (i128 m : acc_maxabs)
+      if (m * (i128)(tiles_per_cta * F_R + 1) >= LIM62) dense_ok = false;
+  }
+  P.mode = dense_ok ? FM_DENSE : FM_HASH;
+  if (P.mode == FM_HASH) {
+    priv_bytes = 0;
+    // bit-packed code
+    int shift = 0;
+    for (int k = 0; k < P.n_keys; ++k) {
+      const int bits = P.keys[k].pad;
+      P.keys[k].mult = shift >= 64 ? 0 : (1ull << shift);
+      shift += bits;
+    }
+    for (i128 m : acc_maxabs)
+      if (m * (i128)n_rows >= LIM62) P.carry = 1;
+  }
+  for (int k = 0; k < P.n_keys; ++k) P.keys[k].pad = 0;
+  int stages = (int)(((size_t)F_SMEM_MAX - 128 - priv_bytes) / stage_bytes);
+  stages = std::min(stages, 4);
+  if (stages < 2) return false;
+  P.stages = stages;
+  P.priv_off = 128 + (uint32_t)stages * stage_bytes;
+  P.dense_groups = (int)dense_groups;
+  const size_t smem_bytes = (size_t)P.priv_off + priv_bytes;
+  const int grid = (int)std::min<int64_t>(P.n_tiles, grid_max);
+
+  // ---- global accumulator table ---------------------------------------------------------------------------
+  FInit init;
+  for (int k = 0; k < NA2; ++k) {
+    if (k < P.n_accs) init.v[k] = P.accs[k].kind == FK_MIN ? INT64_MAX : (P.accs[k].kind == FK_MAX ? INT64_MIN : 0);
+    else init.v[k] = k == P.n_accs ? 0 : INT64_MAX;
+  }
+  CUDA_CHECK(cudaFuncSetAttribute(k_fused_scan_agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  DBufP g_lo, g_hi, t_keys, flags;
+  int64_t n_slots = 0, k_stride = 0, g_stride = 0;
+  int64_t cap = 0;
+  if (P.mode == FM_DENSE) {
+    n_slots = P.dense_groups;
+    k_stride = 1;
+    g_stride = NA2;
+    g_lo = ctx->alloc((size_t)n_slots * NA2 * 8);
+    g_hi = ctx->alloc((size_t)n_slots * NA2 * 8);
+    flags = ctx->alloc_zero(16);
+    LAUNCH(ctx, k_fused_init, grid_for(ctx, n_slots * NA2, 256), 256, 0, (unsigned long long*)g_lo->ptr,
+           (unsigned long long*)g_hi->ptr, n_slots, NA2, 1, init);
+    P.g_lo = (unsigned long long*)g_lo->ptr;
+    P.g_hi = (unsigned long long*)g_hi->ptr;
+    P.abort_flag = (int*)((char*)flags->ptr + 8);
+    P.n_groups = (unsigned long long*)flags->ptr;
+    LAUNCH(ctx, k_fused_scan_agg, grid, F_NT, smem_bytes, P);
+  } else {
+    // capacity: bounded by the key domain and by the row count; grown x8 on overflow
+    i128 domain = total_bits >= 63 ? ((i128)1 << 63) : ((i128)1 << total_bits);
+    int64_t max_groups = (int64_t)std::min<i128>(domain, (i128)n_rows);
+    int64_t need = 2;
+    while (need < 2 * max_groups) need <<= 1;
+    cap = std::min<int64_t>(need, (int64_t)1 << 22);
+    while (true) {
+      n_slots = cap + 1;
+      k_stride = n_slots;
+      g_stride = 1;
+      t_keys = ctx->alloc((size_t)cap * 8);
+      CUDA_CHECK(cudaMemsetAsync(t_keys->ptr, 0xff, (size_t)cap * 8, ctx->stream));
+      g_lo = ctx->alloc((size_t)n_slots * NA2 * 8);
+      g_hi = P.carry ? ctx->alloc((size_t)n_slots * NA2 * 8) : nullptr;
+      flags = ctx->alloc_zero(16);
+      LAUNCH(ctx, k_fused_init, grid_for(ctx, n_slots * NA2, 256), 256, 0, (unsigned long long*)g_lo->ptr,
+             g_hi ? (unsigned long long*)g_hi->ptr : nullptr, n_slots, NA2, 0, init);
+      P.g_lo = (unsigned long long*)g_lo->ptr;
+      P.g_hi = g_hi ? (unsigned long long*)g_hi->ptr : nullptr;
+      P.t_keys = (unsigned long long*)t_keys->ptr;
+      P.cap_mask = (uint64_t)(cap - 1);
+      P.n_groups = (unsigned long long*)flags->ptr;
+      P.abort_flag = (int*)((char*)flags->ptr + 8);
+      LAUNCH(ctx, k_fused_scan_agg, grid, F_NT, smem_bytes, P);
+      const int aborted = ctx->read_scalar((const int*)((char*)flags->ptr + 8));
+      if (!aborted) break;
+      if (cap >= need) throw_internal("fused aggregate: hash table overflow (internal error)");
+      cap = std::min<int64_t>(cap * 8, need);
+    }
+  }
+
+  // ---- export: occupied slots -> dense group ids, accumulators -> GroupAccs ---------------------------------
+  DBufP occ = ctx->alloc((size_t)n_slots * 8), offs = ctx->alloc((size_t)n_slots * 8);
+  LAUNCH(ctx, k_fused_occupied, grid_for(ctx, n_slots, 256), 256, 0, (const unsigned long long*)g_lo->ptr, n_slots,
+         (int64_t)P.n_accs * k_stride, g_stride, (int64_t*)occ->ptr);
+  int64_t n_groups = exclusive_scan_i64(ctx, (const int64_t*)occ->ptr, (int64_t*)offs->ptr, n_slots);
+  const bool grouped = !keys.empty();
+  GroupAccs accs;
+  accs.n_groups = grouped ? n_groups : 1;
+  const int64_t ng_alloc = std::max<int64_t>(accs.n_groups, 1);
+  DBufP cnt = ctx->alloc_zero((size_t)ng_alloc * 8);
+  DBufP first = ctx->alloc_zero((size_t)ng_alloc * 8);
+  DBufP zero = ctx->alloc_zero((size_t)ng_alloc * 8);
+  FExport ex;
+  memset(&ex, 0, sizeof(ex));
+  ex.n_aggs = (int)specs.size();
+  for (size_t i = 0; i < specs.size(); ++i) {
+    AggSpec& s = specs[i];
+    const int k = acc_of[i];
+    ex.acc_of[i] = k;
+    int ak = AK_COUNT;
+    if (k >= 0) {
+      const int fk = P.accs[k].kind;
+      ex.kind_of[i] = fk;
+      ex.wide[i] = (fk == FK_SUM && (P.mode == FM_DENSE || P.carry)) ? 1 : 0;
+      const VClass vc = class_of(s.arg->result_type);
+      if (fk == FK_SUMF) ak = AK_SUM_F64;
+      else if (fk == FK_SUM) ak = vc == VC_DEC ? AK_SUM_DEC : AK_SUM_I64;
+      else if (vc == VC_DEC) ak = fk == FK_MIN ? AK_MIN_DEC : AK_MAX_DEC;
+      else if (vc == VC_UINT) ak = fk == FK_MIN ? AK_MIN_U64 : AK_MAX_U64;
+      else ak = fk == FK_MIN ? AK_MIN_I64 : AK_MAX_I64;
+      DBufP lo = ctx->alloc_zero((size_t)ng_alloc * 8), hi = ctx->alloc_zero((size_t)ng_alloc * 8);
+      ex.out_lo[i] = (unsigned long long*)lo->ptr;
+      ex.out_hi[i] = (unsigned long long*)hi->ptr;
+      accs.lo.push_back(lo);
+      accs.hi.push_back(hi);
+    } else {
+      accs.lo.push_back(zero);
+      accs.hi.push_back(zero);
+    }
+    accs.kind.push_back(ak);
+    accs.cnt.push_back(cnt);
+  }
+  accs.first_row = first;
+  if (n_groups > 0)
+    LAUNCH(ctx, k_fused_export, grid_for(ctx, n_slots, 256), 256, 0, (const unsigned long long*)g_lo->ptr,
+           g_hi ? (const unsigned long long*)g_hi->ptr : nullptr, n_slots, k_stride, g_stride, P.n_accs, (const int64_t*)occ->ptr,
+           (const int64_t*)offs->ptr, ex, (unsigned long long*)cnt->ptr, (long long*)first->ptr);
+  if (!grouped && n_groups == 0) {
+    // no row passed the filter: MIN/MAX keep their sentinels (reference quirk Q4), SUM/AVG are NULL (cnt == 0)
+    for (size_t i = 0; i < specs.size(); ++i) {
+      const int k = acc_of[i];
+      if (k < 0 || P.accs[k].kind == FK_SUM || P.accs[k].kind == FK_SUMF) continue;
+      const long long sent = P.accs[k].kind == FK_MIN ? INT64_MAX : INT64_MIN;
+      unsigned long long h[2] = {(unsigned long long)sent, sent < 0 ? ~0ull : 0ull};
+      ctx->h2d(accs.lo[i]->ptr, &h[0], 8);
+      ctx->h2d(accs.hi[i]->ptr, &h[1], 8);
+      ctx->sync();
+    }
+  }
+  agg.strategy = std::string("fused_scan_agg[") + (P.mode == FM_DENSE ? "dense-private" : "hbm-hash") + ", " +
+                 std::to_string(P.n_cols) + " cols, " + std::to_string(P.n_pred) + " range preds, " + std::to_string(P.n_accs) +
+                 " accs, " + std::to_string(P.stages) + " TMA stages]";
+  *out = finish_aggregate(ctx, v, keys, specs, agg.schema, accs);
+  return true;
+}
+
 }  // namespace qgpu

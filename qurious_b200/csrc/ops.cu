@@ -99,7 +99,11 @@ __global__ void __launch_bounds__(256) k_key_insert(const Program* __restrict__ 
     const uint32_t h32 = (uint32_t)(h >> 32);
     uint64_t slot = h & cap_mask;
     const unsigned long long mine = ((unsigned long long)h32 << 32) | (unsigned long long)(row + 1);
+    int probes = 0;
     while (true) {
+      // the table can fill up completely between the overflow being flagged and every thread noticing it:
+      // never probe forever, the host retries with a larger table
+      if (((++probes) & 63) == 0 && *(volatile int*)abort_flag) return;
       unsigned long long cur = *(volatile unsigned long long*)&slots[slot];
       if (cur == 0) {
         unsigned long long old = atomicCAS(&slots[slot], 0ull, mine);

@@ -138,7 +138,7 @@ void TableImpl::consolidate() {
 // ------------------------------------------------------------------------------------------------
 // execution
 // ------------------------------------------------------------------------------------------------
-static View scan_view(PlanNode& n) {
+View scan_view(PlanNode& n) {
   TableImpl& t = *n.table;
   t.consolidate();
   View v;

@@ -44,6 +44,9 @@ struct PlanNode {
   View execute();
 };
 
+// the (unfiltered) view of a Scan node's table: consolidates appended batches, applies the projection
+View scan_view(PlanNode& scan);
+
 // fused.cu: returns true and fills `out` when the aggregate over this input can run as one fused
 // scan+filter+aggregate pipeline kernel.
 bool try_fused_scan_aggregate(PlanNode& agg, View* out);

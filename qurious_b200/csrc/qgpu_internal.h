@@ -131,6 +131,11 @@ struct DCol {
   // lazily computed value range of the non-null values (ints / dates / decimals)
   bool has_stats = false;
   i128 vmin = 0, vmax = 0;
+  // lazily built dictionary encoding of a low-cardinality Utf8 column (fused.cu: ensure_dict):
+  // dict_codes[row] = index into dict_values; dict_state: 0 = not tried, 1 = encoded, -1 = too many values
+  int dict_state = 0;
+  DBufP dict_codes;  // uint8 per row
+  std::vector<std::string> dict_values;
   int64_t bytes_resident() const {
     int64_t b = 0;
     if (data) b += (int64_t)data->bytes;
