@@ -25,6 +25,8 @@
 // Anything outside this shape (NULLs, OR/!=, wide decimals, computed keys, ...) returns false and the
 // generic interpreter path (ops.cu) runs instead: same results, lower speed.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "launch.h"
@@ -48,28 +50,30 @@ struct FCol {
   uint32_t smem_off;  // offset of this column's tile inside a stage
   uint32_t pad;
 };
+// every operand reference carries the staged tile's offset and its width/sign (resolved on the host)
 struct FPred {
   int32_t col;
-  int32_t pad;
+  uint32_t off, wk, pad;
   int64_t lo;
   uint64_t span;  // pass iff (uint64)(x - lo) <= span
 };
 struct FKey {
   int32_t col;
-  int32_t pad;
+  uint32_t off, wk, pad;
   int64_t base;
   uint64_t mult;  // code += (uint64)(x - base) * mult
 };
 struct FFactor {
   int32_t col;
-  int32_t pad;
-  int64_t a, b;  // a + b * x
+  uint32_t off, wk;
+  int32_t plain;  // a == 0 && b == 1
+  int64_t a, b;   // a + b * x
 };
 struct FAcc {
   int32_t kind;
   int32_t chain;  // 1: value = previous accumulator's value * factors
   int32_t n_factors;
-  int32_t pad;
+  int32_t unit;   // !chain && coef == 1 && f[0].plain: value starts as the bare column
   int64_t coef;
   FFactor f[F_MAXF];
 };
@@ -127,22 +131,38 @@ __device__ __forceinline__ uint64_t fmix64(uint64_t x) {
   return x;
 }
 
-__device__ __forceinline__ int64_t ldc(const unsigned char* stage, const FCol& c, int r) {
-  const unsigned char* b = stage + c.smem_off;
-  switch (c.width) {
-    case 8: return *(const int64_t*)(b + (size_t)r * 8);
-    case 4: {
-      const int32_t v = *(const int32_t*)(b + (size_t)r * 4);
-      return c.kind ? (int64_t)(uint32_t)v : (int64_t)v;
-    }
-    case 2: {
-      const int16_t v = *(const int16_t*)(b + (size_t)r * 2);
-      return c.kind ? (int64_t)(uint16_t)v : (int64_t)v;
-    }
-    default: {
-      const int8_t v = *(const int8_t*)(b + r);
-      return c.kind ? (int64_t)(uint8_t)v : (int64_t)v;
-    }
+// Vectorised operand fetch: the F_R rows this thread owns in the staged tile (row j*F_NT + tid), one
+// width/sign dispatch for all of them (the dispatch is warp-uniform).
+__device__ __forceinline__ void load_rows(const unsigned char* col, uint32_t wk, int tid, int64_t (&x)[F_R]) {
+  switch (wk) {
+    case 8:
+#pragma unroll
+      for (int j = 0; j < F_R; ++j) x[j] = ((const int64_t*)col)[j * F_NT + tid];
+      break;
+    case 4:
+#pragma unroll
+      for (int j = 0; j < F_R; ++j) x[j] = (int64_t)((const int32_t*)col)[j * F_NT + tid];
+      break;
+    case 4 | 256:
+#pragma unroll
+      for (int j = 0; j < F_R; ++j) x[j] = (int64_t)((const uint32_t*)col)[j * F_NT + tid];
+      break;
+    case 2:
+#pragma unroll
+      for (int j = 0; j < F_R; ++j) x[j] = (int64_t)((const int16_t*)col)[j * F_NT + tid];
+      break;
+    case 2 | 256:
+#pragma unroll
+      for (int j = 0; j < F_R; ++j) x[j] = (int64_t)((const uint16_t*)col)[j * F_NT + tid];
+      break;
+    case 1:
+#pragma unroll
+      for (int j = 0; j < F_R; ++j) x[j] = (int64_t)((const int8_t*)col)[j * F_NT + tid];
+      break;
+    default:
+#pragma unroll
+      for (int j = 0; j < F_R; ++j) x[j] = (int64_t)((const uint8_t*)col)[j * F_NT + tid];
+      break;
   }
 }
 
@@ -161,20 +181,223 @@ __device__ __forceinline__ void add128_global(unsigned long long* lo, unsigned l
   if (vhi + carry) atomicAdd(hi, vhi + carry);
 }
 
-// value of accumulator k for row r of the staged tile
-__device__ __forceinline__ int64_t acc_value(const FParams& p, const FAcc& A, const unsigned char* stage, int r, int64_t prev) {
-  int64_t v = A.chain ? prev : A.coef;
-#pragma unroll
-  for (int f = 0; f < F_MAXF; ++f) {
-    if (f < A.n_factors) {
-      const int64_t x = ldc(stage, p.cols[A.f[f].col], r);
-      v *= (A.f[f].a + A.f[f].b * x);
-    }
-  }
-  return v;
+template <int KIND>
+__device__ __forceinline__ long long comb(long long a, long long b) {
+  if (KIND == FK_SUM) return a + b;
+  if (KIND == FK_MIN) return min(a, b);
+  if (KIND == FK_MAX) return max(a, b);
+  return __double_as_longlong(__longlong_as_double(a) + __longlong_as_double(b));
 }
 
-__global__ void __launch_bounds__(F_NT, 1) k_fused_scan_agg(const __grid_constant__ FParams p) {
+// merge bits: 0:(0<-1) 1:(0<-2) 2:(0<-3) 3:(1<-2) 4:(1<-3) 5:(2<-3); rep bits: row j is the representative
+// of its group among this thread's rows.  After the merge the representatives own DISTINCT private slots,
+// so all loads are issued before the stores.
+template <int KIND>
+__device__ __forceinline__ void dense_update(long long* const (&a)[F_R], uint32_t koff, int64_t (&v)[F_R], uint32_t merge,
+                                             uint32_t rep) {
+  if (merge & 1) v[0] = comb<KIND>(v[0], v[1]);
+  if (merge & 2) v[0] = comb<KIND>(v[0], v[2]);
+  if (merge & 4) v[0] = comb<KIND>(v[0], v[3]);
+  if (merge & 8) v[1] = comb<KIND>(v[1], v[2]);
+  if (merge & 16) v[1] = comb<KIND>(v[1], v[3]);
+  if (merge & 32) v[2] = comb<KIND>(v[2], v[3]);
+  long long cur[F_R];
+#pragma unroll
+  for (int j = 0; j < F_R; ++j) cur[j] = ((rep >> j) & 1) ? a[j][koff] : 0;
+#pragma unroll
+  for (int j = 0; j < F_R; ++j)
+    if ((rep >> j) & 1) a[j][koff] = comb<KIND>(cur[j], v[j]);
+}
+
+static_assert(F_R == 4, "the in-thread duplicate-group merge below is written for 4 rows per thread");
+
+// ------------------------------------------------------------------------------------------------
+// tile body #1: the generic (interpreted) one -- every structural property is a runtime parameter
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+struct GenericBody {
+  static __device__ __forceinline__ void tile(const FParams& p, const unsigned char* stage, const int64_t row0, const int rows,
+                                              const int tid, long long* priv, const int NA2) {
+    // ---- predicate: range tests, operand-major over the thread's F_R rows -----------------------------
+    uint32_t pass = 0;
+#pragma unroll
+    for (int j = 0; j < F_R; ++j)
+      if (j * F_NT + tid < rows) pass |= 1u << j;
+#pragma unroll 1
+    for (int k = 0; k < p.n_pred; ++k) {
+      int64_t x[F_R];
+      load_rows(stage + p.pred[k].off, p.pred[k].wk, tid, x);
+      const uint64_t lo = (uint64_t)p.pred[k].lo, span = p.pred[k].span;
+#pragma unroll
+      for (int j = 0; j < F_R; ++j)
+        if (((uint64_t)x[j] - lo) > span) pass &= ~(1u << j);
+    }
+    if (__any_sync(0xffffffffu, pass != 0)) {
+      // ---- packed group key ---------------------------------------------------------------------------
+      uint64_t code[F_R] = {0, 0, 0, 0};
+#pragma unroll 1
+      for (int k = 0; k < p.n_keys; ++k) {
+        int64_t x[F_R];
+        load_rows(stage + p.keys[k].off, p.keys[k].wk, tid, x);
+        const uint64_t base = (uint64_t)p.keys[k].base, mult = p.keys[k].mult;
+#pragma unroll
+        for (int j = 0; j < F_R; ++j) code[j] += ((uint64_t)x[j] - base) * mult;
+      }
+      const bool p0 = pass & 1, p1 = pass & 2, p2 = pass & 4, p3 = pass & 8;
+      int64_t prev[F_R] = {0, 0, 0, 0};
+
+      if (MODE == FM_DENSE) {
+        // Rows of this thread that fall into the same group are merged in registers first, so that the
+        // read-modify-writes of the representatives touch DISTINCT private slots: all loads can then be
+        // issued before the stores (no serialisation on may-alias shared-memory accesses).
+        const bool m01 = p0 && p1 && code[0] == code[1];
+        const bool m02 = p0 && p2 && code[0] == code[2];
+        const bool m03 = p0 && p3 && code[0] == code[3];
+        const bool r1 = p1 && !m01;
+        const bool m12 = r1 && p2 && code[1] == code[2];
+        const bool m13 = r1 && p3 && code[1] == code[3];
+        const bool r2 = p2 && !m02 && !m12;
+        const bool m23 = r2 && p3 && code[2] == code[3];
+        const bool r3 = p3 && !m03 && !m13 && !m23;
+        const uint32_t merge = (uint32_t)m01 | ((uint32_t)m02 << 1) | ((uint32_t)m03 << 2) | ((uint32_t)m12 << 3) |
+                               ((uint32_t)m13 << 4) | ((uint32_t)m23 << 5);
+        const uint32_t rep = (uint32_t)p0 | ((uint32_t)r1 << 1) | ((uint32_t)r2 << 2) | ((uint32_t)r3 << 3);
+        long long* a[F_R];
+#pragma unroll
+        for (int j = 0; j < F_R; ++j)
+          a[j] = priv + (((rep >> j) & 1) ? (uint32_t)code[j] * (uint32_t)(NA2 * F_NT) : 0u) + (uint32_t)tid;
+#pragma unroll 1
+        for (uint32_t k = 0; k < (uint32_t)p.n_accs; ++k) {
+          const FAcc& A = p.accs[k];
+          const int kind = A.kind;
+          int64_t v[F_R];
+          if (kind == FK_SUMF || A.unit) {
+            load_rows(stage + A.f[0].off, A.f[0].wk, tid, v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < F_R; ++j) v[j] = A.chain ? prev[j] : A.coef;
+          }
+          if (kind != FK_SUMF) {
+#pragma unroll 1
+            for (int f = A.unit ? 1 : 0; f < A.n_factors; ++f) {
+              int64_t x[F_R];
+              load_rows(stage + A.f[f].off, A.f[f].wk, tid, x);
+              if (A.f[f].plain) {
+#pragma unroll
+                for (int j = 0; j < F_R; ++j) v[j] *= x[j];
+              } else {
+                const int64_t fa = A.f[f].a, fb = A.f[f].b;
+#pragma unroll
+                for (int j = 0; j < F_R; ++j) v[j] *= (fa + fb * x[j]);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < F_R; ++j) prev[j] = v[j];
+          }
+          const uint32_t koff = k * F_NT;
+          if (kind == FK_SUM) dense_update<FK_SUM>(a, koff, v, merge, rep);
+          else if (kind == FK_MIN) dense_update<FK_MIN>(a, koff, v, merge, rep);
+          else if (kind == FK_MAX) dense_update<FK_MAX>(a, koff, v, merge, rep);
+          else dense_update<FK_SUMF>(a, koff, v, merge, rep);
+        }
+        // row count and first row of each representative's class
+        int64_t cnt[F_R] = {1, 1, 1, 1};
+        dense_update<FK_SUM>(a, (uint32_t)p.n_accs * F_NT, cnt, merge, rep);
+        int64_t fr[F_R];
+#pragma unroll
+        for (int j = 0; j < F_R; ++j) fr[j] = row0 + j * F_NT + tid;
+        dense_update<FK_MIN>(a, (uint32_t)(p.n_accs + 1) * F_NT, fr, 0u, rep);  // the representative is the smallest row
+      } else {
+        // ---- HBM-resident open-addressing table on the packed key -------------------------------------------
+        uint64_t slot[F_R];
+#pragma unroll
+        for (int j = 0; j < F_R; ++j) {
+          slot[j] = F_EMPTY;
+          if (!((pass >> j) & 1)) continue;
+          const uint64_t c = code[j];
+          if (c == F_EMPTY) {
+            slot[j] = p.cap_mask + 1;
+            continue;
+          }
+          uint64_t sl = fmix64(c) & p.cap_mask;
+          int probes = 0;
+          while (true) {
+            unsigned long long cur = *(volatile unsigned long long*)&p.t_keys[sl];
+            if (cur == c) break;
+            if (((++probes) & 63) == 0 && *(volatile int*)p.abort_flag) {  // table (nearly) full: host retries larger
+              sl = F_EMPTY;
+              break;
+            }
+            if (cur == F_EMPTY) {
+              cur = atomicCAS(&p.t_keys[sl], F_EMPTY, (unsigned long long)c);
+              if (cur == F_EMPTY) {
+                const unsigned long long ng = atomicAdd(p.n_groups, 1ull);
+                if (2 * (ng + 1) > p.cap_mask + 1) *p.abort_flag = 1;
+                break;
+              }
+              if (cur == c) break;
+            }
+            sl = (sl + 1) & p.cap_mask;
+          }
+          slot[j] = sl;
+        }
+        const size_t stride = (size_t)p.cap_mask + 2;
+#pragma unroll 1
+        for (int k = 0; k < p.n_accs; ++k) {
+          const FAcc& A = p.accs[k];
+          const int kind = A.kind;
+          int64_t v[F_R];
+          if (kind == FK_SUMF || A.unit) {
+            load_rows(stage + A.f[0].off, A.f[0].wk, tid, v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < F_R; ++j) v[j] = A.chain ? prev[j] : A.coef;
+          }
+          if (kind != FK_SUMF) {
+#pragma unroll 1
+            for (int f = A.unit ? 1 : 0; f < A.n_factors; ++f) {
+              int64_t x[F_R];
+              load_rows(stage + A.f[f].off, A.f[f].wk, tid, x);
+              const int64_t fa = A.f[f].a, fb = A.f[f].b;
+#pragma unroll
+              for (int j = 0; j < F_R; ++j) v[j] *= (fa + fb * x[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < F_R; ++j) prev[j] = v[j];
+          }
+          unsigned long long* lo = p.g_lo + k * stride;
+#pragma unroll
+          for (int j = 0; j < F_R; ++j) {
+            if (slot[j] == F_EMPTY) continue;
+            if (kind == FK_SUM) {
+              if (p.carry) add128_global(lo + slot[j], p.g_hi + k * stride + slot[j], (unsigned long long)v[j], v[j] < 0 ? ~0ull : 0ull);
+              else atomicAdd(lo + slot[j], (unsigned long long)v[j]);
+            } else if (kind == FK_MIN) {
+              atomicMin((long long*)(lo + slot[j]), (long long)v[j]);
+            } else if (kind == FK_MAX) {
+              atomicMax((long long*)(lo + slot[j]), (long long)v[j]);
+            } else {
+              atomicAdd((double*)(lo + slot[j]), __longlong_as_double(v[j]));
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < F_R; ++j) {
+          if (slot[j] == F_EMPTY) continue;
+          atomicAdd(p.g_lo + (size_t)p.n_accs * stride + slot[j], 1ull);
+          atomicMin((long long*)(p.g_lo + (size_t)(p.n_accs + 1) * stride + slot[j]), (long long)(row0 + j * F_NT + tid));
+        }
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// kernel skeleton: TMA/mbarrier tile pipeline + per-CTA reduction of the private tables; `Body::tile`
+// consumes one staged tile
+// ------------------------------------------------------------------------------------------------
+template <int MODE, class Body>
+__device__ __forceinline__ void fused_main(const FParams& p) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = (uint64_t*)smem;
   unsigned char* tiles = smem + 128;
@@ -182,7 +405,7 @@ __global__ void __launch_bounds__(F_NT, 1) k_fused_scan_agg(const __grid_constan
   const int tid = threadIdx.x;
   const int NA2 = p.n_accs + 2;
 
-  if (p.mode == FM_DENSE) {
+  if (MODE == FM_DENSE) {
     const int total = p.dense_groups * NA2 * F_NT;
     for (int i = tid; i < total; i += F_NT) priv[i] = acc_init(p, (i / F_NT) % NA2);
   }
@@ -203,8 +426,10 @@ __global__ void __launch_bounds__(F_NT, 1) k_fused_scan_agg(const __grid_constan
     const int64_t rows = min((int64_t)F_T, p.n_rows - row0);
     unsigned char* dst = tiles + (size_t)s * p.stage_bytes;
     uint32_t total = 0;
+#pragma unroll 1
     for (int c = 0; c < p.n_cols; ++c) total += ((uint32_t)(rows * p.cols[c].width) + 15u) & ~15u;
     mbar_expect_tx(&full[s], total);
+#pragma unroll 1
     for (int c = 0; c < p.n_cols; ++c) {
       const uint32_t bytes = ((uint32_t)(rows * p.cols[c].width) + 15u) & ~15u;
       bulk_g2s(dst + p.cols[c].smem_off, p.cols[c].ptr + (size_t)row0 * p.cols[c].width, bytes, &full[s]);
@@ -213,116 +438,17 @@ __global__ void __launch_bounds__(F_NT, 1) k_fused_scan_agg(const __grid_constan
   if (tid == 0)
     for (int64_t i = 0; i < my_tiles && i < p.stages; ++i) issue(i);
 
+#pragma unroll 1
   for (int64_t i = 0; i < my_tiles; ++i) {
     const int s = (int)(i % p.stages);
     mbar_wait(&full[s], (uint32_t)((i / p.stages) & 1));
-    {
-      const unsigned char* stage = tiles + (size_t)s * p.stage_bytes;
-      const int64_t row0 = (first_tile + i * gridDim.x) * F_T;
-      const int rows = (int)min((int64_t)F_T, p.n_rows - row0);
-#pragma unroll 1
-      for (int j = 0; j < F_R; ++j) {
-        const int r = j * F_NT + tid;
-        bool pass = r < rows;
-#pragma unroll
-        for (int k = 0; k < F_MAXP; ++k) {
-          if (k < p.n_pred) {
-            const int64_t x = ldc(stage, p.cols[p.pred[k].col], r);
-            pass = pass && (((uint64_t)x - (uint64_t)p.pred[k].lo) <= p.pred[k].span);
-          }
-        }
-        if (!__any_sync(0xffffffffu, pass)) continue;
-        if (pass) {
-          uint64_t code = 0;
-#pragma unroll
-          for (int k = 0; k < F_MAXK; ++k) {
-            if (k < p.n_keys) {
-              const int64_t x = ldc(stage, p.cols[p.keys[k].col], r);
-              code += ((uint64_t)x - (uint64_t)p.keys[k].base) * p.keys[k].mult;
-            }
-          }
-          const long long row = row0 + r;
-          if (p.mode == FM_DENSE) {
-            long long* a = priv + (size_t)code * NA2 * F_NT + tid;
-            int64_t prev = 0;
-#pragma unroll
-            for (int k = 0; k < F_MAXA; ++k) {
-              if (k < p.n_accs) {
-                const FAcc& A = p.accs[k];
-                long long* slot = a + k * F_NT;
-                if (A.kind == FK_SUMF) {
-                  const double x = __longlong_as_double(ldc(stage, p.cols[A.f[0].col], r));
-                  *slot = __double_as_longlong(__longlong_as_double(*slot) + x);
-                } else {
-                  const int64_t v = acc_value(p, A, stage, r, prev);
-                  prev = v;
-                  const long long cur = *slot;
-                  *slot = A.kind == FK_SUM ? cur + v : (A.kind == FK_MIN ? min(cur, (long long)v) : max(cur, (long long)v));
-                }
-              }
-            }
-            a[p.n_accs * F_NT] += 1;
-            long long* fr = a + (p.n_accs + 1) * F_NT;
-            if (row < *fr) *fr = row;
-          } else {
-            // ---- HBM-resident open-addressing table on the packed key ----
-            uint64_t slot;
-            if (code == F_EMPTY) {
-              slot = p.cap_mask + 1;
-            } else {
-              slot = fmix64(code) & p.cap_mask;
-              int probes = 0;
-              while (true) {
-                unsigned long long cur = *(volatile unsigned long long*)&p.t_keys[slot];
-                if (cur == code) break;
-                if (((++probes) & 63) == 0 && *(volatile int*)p.abort_flag) {  // table (nearly) full: host retries larger
-                  slot = F_EMPTY;
-                  break;
-                }
-                if (cur == F_EMPTY) {
-                  cur = atomicCAS(&p.t_keys[slot], F_EMPTY, (unsigned long long)code);
-                  if (cur == F_EMPTY) {
-                    const unsigned long long ng = atomicAdd(p.n_groups, 1ull);
-                    if (2 * (ng + 1) > p.cap_mask + 1) *p.abort_flag = 1;
-                    break;
-                  }
-                  if (cur == code) break;
-                }
-                slot = (slot + 1) & p.cap_mask;
-              }
-            }
-            if (slot == F_EMPTY) continue;
-            const size_t stride = (size_t)p.cap_mask + 2;
-            int64_t prev = 0;
-#pragma unroll
-            for (int k = 0; k < F_MAXA; ++k) {
-              if (k < p.n_accs) {
-                const FAcc& A = p.accs[k];
-                unsigned long long* lo = p.g_lo + k * stride + slot;
-                if (A.kind == FK_SUMF) {
-                  atomicAdd((double*)lo, __longlong_as_double(ldc(stage, p.cols[A.f[0].col], r)));
-                } else {
-                  const int64_t v = acc_value(p, A, stage, r, prev);
-                  prev = v;
-                  if (A.kind == FK_SUM) {
-                    if (p.carry) add128_global(lo, p.g_hi + k * stride + slot, (unsigned long long)v, v < 0 ? ~0ull : 0ull);
-                    else atomicAdd(lo, (unsigned long long)v);
-                  } else if (A.kind == FK_MIN) {
-                    atomicMin((long long*)lo, (long long)v);
-                  } else {
-                    atomicMax((long long*)lo, (long long)v);
-                  }
-                }
-              }
-            }
-            atomicAdd(p.g_lo + (size_t)p.n_accs * stride + slot, 1ull);
-            atomicMin((long long*)(p.g_lo + (size_t)(p.n_accs + 1) * stride + slot), row);
-          }
-        }
-      }
-    }
+    const unsigned char* stage = tiles + (size_t)s * p.stage_bytes;
+    const int64_t row0 = (first_tile + i * gridDim.x) * F_T;
+    const int rows = (int)min((int64_t)F_T, p.n_rows - row0);
+
+    Body::tile(p, stage, row0, rows, tid, priv, NA2);
     // every thread is done with stage s before it is refilled; the same barrier broadcasts the abort flag
-    const int aborted = __syncthreads_or(p.mode == FM_HASH && tid == 0 && *(volatile int*)p.abort_flag != 0);
+    const int aborted = __syncthreads_or(MODE == FM_HASH && tid == 0 && *(volatile int*)p.abort_flag != 0);
     if (aborted) {
       // drain the copies already in flight (the CTA's shared memory must outlive them), then leave
       if (tid == 0)
@@ -334,7 +460,7 @@ __global__ void __launch_bounds__(F_NT, 1) k_fused_scan_agg(const __grid_constan
   }
 
   // ---- DENSE: reduce the per-thread private tables once per CTA into the 128-bit global table ----
-  if (p.mode == FM_DENSE) {
+  if (MODE == FM_DENSE) {
     __syncthreads();
     const int lane = tid & 31, warp = tid >> 5;
     const int n_lines = p.dense_groups * NA2;
@@ -389,6 +515,238 @@ __global__ void __launch_bounds__(F_NT, 1) k_fused_scan_agg(const __grid_constan
       }
     }
   }
+}
+
+
+template <int MODE>
+__global__ void __launch_bounds__(F_NT, 1) k_fused_scan_agg(const __grid_constant__ FParams p) {
+  fused_main<MODE, GenericBody<MODE>>(p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tile body #2: compile-time specialised on the plan's SHAPE SIGNATURE (operand widths, accumulator
+// kinds / chaining / factor counts); constants (bounds, coefficients, tile offsets) stay runtime
+// parameters.  The host computes the signature of every fused plan and launches the matching
+// instantiation when one is registered (the shapes of TPC-H Q1 and Q6 are); everything else runs the
+// generic body above.  Registering a shape = one line in SPEC_SHAPES below.
+//
+// signature: s[0] = n_pred(4) | 8 x pred width code(3) | n_keys(3) | 4 x key width code(3) | n_accs(4)
+//            s[1..3]: 3 accumulators each, 18 bits: kind(2) chain(1) unit(1) n_factors(2) 3 x {width code(3) plain(1)}
+// width codes: 0 i8, 1 u8, 2 i16, 3 u16, 4 i32, 5 u32, 6 i64
+// ------------------------------------------------------------------------------------------------
+struct FSig {
+  uint64_t s[4];
+};
+__host__ __device__ constexpr uint32_t wk_to_code(uint32_t wk) {
+  return wk == 1 ? 0u : wk == (1u | 256u) ? 1u : wk == 2 ? 2u : wk == (2u | 256u) ? 3u : wk == 4 ? 4u : wk == (4u | 256u) ? 5u : 6u;
+}
+enum : uint32_t { WC_I8 = 0, WC_U8 = 1, WC_I16 = 2, WC_U16 = 3, WC_I32 = 4, WC_U32 = 5, WC_I64 = 6 };
+__host__ __device__ constexpr uint64_t sig_factor(uint32_t wc, bool plain) { return (uint64_t)wc | ((uint64_t)(plain ? 1 : 0) << 3); }
+__host__ __device__ constexpr uint64_t sig_acc(int kind, bool chain, bool unit, int nf, uint64_t f0 = 0, uint64_t f1 = 0, uint64_t f2 = 0) {
+  return (uint64_t)kind | ((uint64_t)(chain ? 1 : 0) << 2) | ((uint64_t)(unit ? 1 : 0) << 3) | ((uint64_t)nf << 4) | (f0 << 6) | (f1 << 10) |
+         (f2 << 14);
+}
+__host__ __device__ constexpr uint64_t sig_head(int n_pred, uint64_t preds, int n_keys, uint64_t keys, int n_accs) {
+  return (uint64_t)n_pred | (preds << 4) | ((uint64_t)n_keys << 28) | (keys << 31) | ((uint64_t)n_accs << 43);
+}
+__host__ __device__ constexpr uint64_t sig_list(uint32_t a = 0, uint32_t b = 0, uint32_t c = 0, uint32_t d = 0, uint32_t e = 0,
+                                                uint32_t f = 0, uint32_t g = 0, uint32_t h = 0) {
+  return (uint64_t)a | ((uint64_t)b << 3) | ((uint64_t)c << 6) | ((uint64_t)d << 9) | ((uint64_t)e << 12) | ((uint64_t)f << 15) |
+         ((uint64_t)g << 18) | ((uint64_t)h << 21);
+}
+__host__ __device__ constexpr uint64_t sig_accs3(uint64_t a0 = 0, uint64_t a1 = 0, uint64_t a2 = 0) { return a0 | (a1 << 18) | (a2 << 36); }
+
+template <uint64_t S0, uint64_t S1, uint64_t S2, uint64_t S3>
+struct SigView {
+  static constexpr int n_pred = (int)(S0 & 15);
+  static constexpr int n_keys = (int)((S0 >> 28) & 7);
+  static constexpr int n_accs = (int)((S0 >> 43) & 15);
+  static constexpr uint32_t pred_wc(int k) { return (uint32_t)((S0 >> (4 + 3 * k)) & 7); }
+  static constexpr uint32_t key_wc(int k) { return (uint32_t)((S0 >> (31 + 3 * k)) & 7); }
+  static constexpr uint64_t acc(int k) { return ((k < 3 ? S1 : (k < 6 ? S2 : S3)) >> (18 * (k % 3))) & 0x3ffff; }
+  static constexpr int kind(int k) { return (int)(acc(k) & 3); }
+  static constexpr bool chain(int k) { return (acc(k) >> 2) & 1; }
+  static constexpr bool unit(int k) { return (acc(k) >> 3) & 1; }
+  static constexpr int n_factors(int k) { return (int)((acc(k) >> 4) & 3); }
+  static constexpr uint32_t f_wc(int k, int f) { return (uint32_t)((acc(k) >> (6 + 4 * f)) & 7); }
+  static constexpr bool f_plain(int k, int f) { return (acc(k) >> (6 + 4 * f + 3)) & 1; }
+};
+
+template <uint32_t WC>
+__device__ __forceinline__ void load_rows_t(const unsigned char* col, int tid, int64_t (&x)[F_R]) {
+#pragma unroll
+  for (int j = 0; j < F_R; ++j) {
+    if (WC == WC_I64) x[j] = ((const int64_t*)col)[j * F_NT + tid];
+    else if (WC == WC_I32) x[j] = (int64_t)((const int32_t*)col)[j * F_NT + tid];
+    else if (WC == WC_U32) x[j] = (int64_t)((const uint32_t*)col)[j * F_NT + tid];
+    else if (WC == WC_I16) x[j] = (int64_t)((const int16_t*)col)[j * F_NT + tid];
+    else if (WC == WC_U16) x[j] = (int64_t)((const uint16_t*)col)[j * F_NT + tid];
+    else if (WC == WC_I8) x[j] = (int64_t)((const int8_t*)col)[j * F_NT + tid];
+    else x[j] = (int64_t)((const uint8_t*)col)[j * F_NT + tid];
+  }
+}
+
+template <uint64_t S0, uint64_t S1, uint64_t S2, uint64_t S3>
+struct SpecBody {
+  typedef SigView<S0, S1, S2, S3> G;
+  // value of accumulator K for the thread's rows (compile-time recursion keeps every index static)
+  template <int K, int F>
+  static __device__ __forceinline__ void factors(const FParams& p, const unsigned char* stage, int tid, int64_t (&v)[F_R]) {
+    if constexpr (F < G::n_factors(K)) {
+      int64_t x[F_R];
+      load_rows_t<G::f_wc(K, F)>(stage + p.accs[K].f[F].off, tid, x);
+      if constexpr (G::f_plain(K, F)) {
+#pragma unroll
+        for (int j = 0; j < F_R; ++j) v[j] *= x[j];
+      } else {
+        const int64_t fa = p.accs[K].f[F].a, fb = p.accs[K].f[F].b;
+#pragma unroll
+        for (int j = 0; j < F_R; ++j) v[j] *= (fa + fb * x[j]);
+      }
+      factors<K, F + 1>(p, stage, tid, v);
+    }
+  }
+  template <int K>
+  static __device__ __forceinline__ void values(const FParams& p, const unsigned char* stage, int tid, int64_t (&val)[F_MAXA][F_R]) {
+    if constexpr (K < G::n_accs) {
+      if constexpr (G::kind(K) == FK_SUMF || G::unit(K)) {
+        load_rows_t<G::f_wc(K, 0)>(stage + p.accs[K].f[0].off, tid, val[K]);
+        if constexpr (G::kind(K) != FK_SUMF) factors<K, 1>(p, stage, tid, val[K]);
+      } else {
+        if constexpr (G::chain(K)) {
+#pragma unroll
+          for (int j = 0; j < F_R; ++j) val[K][j] = val[K - 1][j];
+        } else {
+          const int64_t c = p.accs[K].coef;
+#pragma unroll
+          for (int j = 0; j < F_R; ++j) val[K][j] = c;
+        }
+        factors<K, 0>(p, stage, tid, val[K]);
+      }
+      values<K + 1>(p, stage, tid, val);
+    }
+  }
+  template <int K>
+  static __device__ __forceinline__ void preds(const FParams& p, const unsigned char* stage, int tid, uint32_t& pass) {
+    if constexpr (K < G::n_pred) {
+      int64_t x[F_R];
+      load_rows_t<G::pred_wc(K)>(stage + p.pred[K].off, tid, x);
+      const uint64_t lo = (uint64_t)p.pred[K].lo, span = p.pred[K].span;
+#pragma unroll
+      for (int j = 0; j < F_R; ++j)
+        if (((uint64_t)x[j] - lo) > span) pass &= ~(1u << j);
+      preds<K + 1>(p, stage, tid, pass);
+    }
+  }
+  template <int K>
+  static __device__ __forceinline__ void keys(const FParams& p, const unsigned char* stage, int tid, uint32_t (&code)[F_R]) {
+    if constexpr (K < G::n_keys) {
+      int64_t x[F_R];
+      load_rows_t<G::key_wc(K)>(stage + p.keys[K].off, tid, x);
+      const uint32_t base = (uint32_t)p.keys[K].base, mult = (uint32_t)p.keys[K].mult;
+#pragma unroll
+      for (int j = 0; j < F_R; ++j) code[j] += ((uint32_t)x[j] - base) * mult;  // dense index < 4096: 32-bit is exact
+      keys<K + 1>(p, stage, tid, code);
+    }
+  }
+  template <int K>
+  static __device__ __forceinline__ void rmw_load(const long long* a, long long (&cur)[F_MAXA]) {
+    if constexpr (K < G::n_accs) {
+      cur[K] = a[K * F_NT];
+      rmw_load<K + 1>(a, cur);
+    }
+  }
+  template <int K>
+  static __device__ __forceinline__ void rmw_store(long long* a, const long long (&cur)[F_MAXA], const int64_t (&val)[F_MAXA][F_R], int j) {
+    if constexpr (K < G::n_accs) {
+      a[K * F_NT] = comb<G::kind(K)>(cur[K], val[K][j]);
+      rmw_store<K + 1>(a, cur, val, j);
+    }
+  }
+
+  static __device__ __forceinline__ void tile(const FParams& p, const unsigned char* stage, const int64_t row0, const int rows,
+                                              const int tid, long long* priv, const int /*NA2*/) {
+    constexpr int NA2c = G::n_accs + 2;
+    uint32_t pass = 0;
+#pragma unroll
+    for (int j = 0; j < F_R; ++j)
+      if (j * F_NT + tid < rows) pass |= 1u << j;
+    preds<0>(p, stage, tid, pass);
+    if (!__any_sync(0xffffffffu, pass != 0)) return;
+    uint32_t code[F_R] = {0, 0, 0, 0};
+    keys<0>(p, stage, tid, code);
+    int64_t val[F_MAXA][F_R];
+    values<0>(p, stage, tid, val);
+    // Row-sequential read-modify-write of the thread's private slots: the K loads of one row are issued
+    // together (distinct slots), rows follow in program order (two rows may share a group).
+#pragma unroll
+    for (int j = 0; j < F_R; ++j) {
+      if ((pass >> j) & 1) {
+        long long* a = priv + code[j] * (uint32_t)(NA2c * F_NT) + (uint32_t)tid;
+        long long cur[F_MAXA];
+        rmw_load<0>(a, cur);
+        const long long cc = a[G::n_accs * F_NT];
+        const long long ff = a[(G::n_accs + 1) * F_NT];
+        rmw_store<0>(a, cur, val, j);
+        a[G::n_accs * F_NT] = cc + 1;
+        a[(G::n_accs + 1) * F_NT] = min(ff, (long long)(row0 + j * F_NT + tid));
+      }
+    }
+  }
+};
+
+template <uint64_t S0, uint64_t S1, uint64_t S2, uint64_t S3>
+__global__ void __launch_bounds__(F_NT, 1) k_fused_scan_agg_spec(const __grid_constant__ FParams p) {
+  fused_main<FM_DENSE, SpecBody<S0, S1, S2, S3>>(p);
+}
+
+// ---- registered shapes --------------------------------------------------------------------------------
+// TPC-H Q1: 1 Date32 range; keys = 2 dictionary-coded Utf8 columns; SUM(qty), SUM(price),
+// SUM(price*(100-disc)) chained on price, SUM(..*(100+tax)) chained, SUM(disc)  [AVGs share the sums]
+#define SIG_Q1                                                                                                                     \
+  sig_head(1, sig_list(WC_I32), 2, sig_list(WC_U8, WC_U8), 5),                                                                       \
+      sig_accs3(sig_acc(FK_SUM, false, true, 1, sig_factor(WC_I64, true)), sig_acc(FK_SUM, false, true, 1, sig_factor(WC_I64, true)), \
+                sig_acc(FK_SUM, true, false, 1, sig_factor(WC_I64, false))),                                                         \
+      sig_accs3(sig_acc(FK_SUM, true, false, 1, sig_factor(WC_I64, false)), sig_acc(FK_SUM, false, true, 1, sig_factor(WC_I64, true))), 0
+// TPC-H Q6: ranges on Date32, Decimal(15,2), Decimal(15,2); no keys; SUM(price * disc)
+#define SIG_Q6                                                       \
+  sig_head(3, sig_list(WC_I32, WC_I64, WC_I64), 0, 0, 1),            \
+      sig_accs3(sig_acc(FK_SUM, false, true, 2, sig_factor(WC_I64, true), sig_factor(WC_I64, true))), 0, 0
+
+static FSig make_sig(const FParams& P) {
+  FSig g;
+  uint64_t preds = 0, keys = 0;
+  for (int k = 0; k < P.n_pred; ++k) preds |= (uint64_t)wk_to_code(P.pred[k].wk) << (3 * k);
+  for (int k = 0; k < P.n_keys; ++k) keys |= (uint64_t)wk_to_code(P.keys[k].wk) << (3 * k);
+  g.s[0] = sig_head(P.n_pred, preds, P.n_keys, keys, P.n_accs);
+  g.s[1] = g.s[2] = g.s[3] = 0;
+  for (int k = 0; k < P.n_accs; ++k) {
+    const FAcc& a = P.accs[k];
+    uint64_t f[3] = {0, 0, 0};
+    for (int i = 0; i < a.n_factors; ++i) f[i] = sig_factor(wk_to_code(a.f[i].wk), a.f[i].plain != 0);
+    g.s[1 + k / 3] |= sig_acc(a.kind, a.chain != 0, a.unit != 0, a.n_factors, f[0], f[1], f[2]) << (18 * (k % 3));
+  }
+  return g;
+}
+
+typedef void (*FusedKernel)(const FParams);
+template <uint64_t S0, uint64_t S1, uint64_t S2, uint64_t S3>
+static bool sig_matches(const FSig& g, FusedKernel* out) {
+  if (g.s[0] != S0 || g.s[1] != S1 || g.s[2] != S2 || g.s[3] != S3) return false;
+  *out = k_fused_scan_agg_spec<S0, S1, S2, S3>;
+  return true;
+}
+// returns the specialised DENSE kernel registered for this shape, or nullptr
+static FusedKernel find_specialised(const FParams& P) {
+  if (P.mode != FM_DENSE) return nullptr;
+  const FSig g = make_sig(P);
+  FusedKernel k = nullptr;
+  if (sig_matches<SIG_Q1>(g, &k)) return k;
+  if (sig_matches<SIG_Q6>(g, &k)) return k;
+  if (getenv("QGPU_FUSED_DEBUG"))
+    fprintf(stderr, "[qgpu] fused shape without a specialised kernel: %016llx %016llx %016llx %016llx\n", (unsigned long long)g.s[0],
+            (unsigned long long)g.s[1], (unsigned long long)g.s[2], (unsigned long long)g.s[3]);
+  return nullptr;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1011,6 +1369,21 @@ bool try_fused_scan_aggregate(PlanNode& agg, View* out) {
     stage_bytes += (uint32_t)(((size_t)F_T * fc.width + 127) & ~(size_t)127);
   }
   if (P.n_cols == 0) return false;  // nothing to stream (COUNT(*) without predicate): generic path
+  auto resolve = [&](int col, uint32_t* off, uint32_t* wk) {
+    *off = P.cols[col].smem_off;
+    *wk = P.cols[col].width | (P.cols[col].kind ? 256u : 0u);
+    if (P.cols[col].width == 8) *wk = 8;
+  };
+  for (int k = 0; k < P.n_pred; ++k) resolve(P.pred[k].col, &P.pred[k].off, &P.pred[k].wk);
+  for (int k = 0; k < P.n_keys; ++k) resolve(P.keys[k].col, &P.keys[k].off, &P.keys[k].wk);
+  for (int k = 0; k < P.n_accs; ++k) {
+    FAcc& a = P.accs[k];
+    for (int f = 0; f < a.n_factors; ++f) {
+      resolve(a.f[f].col, &a.f[f].off, &a.f[f].wk);
+      a.f[f].plain = (a.f[f].a == 0 && a.f[f].b == 1) ? 1 : 0;
+    }
+    a.unit = (a.kind != FK_SUMF && !a.chain && a.coef == 1 && a.n_factors > 0 && a.f[0].plain) ? 1 : 0;
+  }
   P.stage_bytes = stage_bytes;
   const int NA2 = P.n_accs + 2;
   const int grid_max = ctx->sm_count;
@@ -1052,8 +1425,10 @@ bool try_fused_scan_aggregate(PlanNode& agg, View* out) {
     if (k < P.n_accs) init.v[k] = P.accs[k].kind == FK_MIN ? INT64_MAX : (P.accs[k].kind == FK_MAX ? INT64_MIN : 0);
     else init.v[k] = k == P.n_accs ? 0 : INT64_MAX;
   }
-  CUDA_CHECK(cudaFuncSetAttribute(k_fused_scan_agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  CUDA_CHECK(cudaFuncSetAttribute(k_fused_scan_agg<FM_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  CUDA_CHECK(cudaFuncSetAttribute(k_fused_scan_agg<FM_HASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   DBufP g_lo, g_hi, t_keys, flags;
+  bool specialised = false;
   int64_t n_slots = 0, k_stride = 0, g_stride = 0;
   int64_t cap = 0;
   if (P.mode == FM_DENSE) {
@@ -1069,7 +1444,16 @@ bool try_fused_scan_aggregate(PlanNode& agg, View* out) {
     P.g_hi = (unsigned long long*)g_hi->ptr;
     P.abort_flag = (int*)((char*)flags->ptr + 8);
     P.n_groups = (unsigned long long*)flags->ptr;
-    LAUNCH(ctx, k_fused_scan_agg, grid, F_NT, smem_bytes, P);
+    FusedKernel spec = getenv("QGPU_FUSED_GENERIC") ? nullptr : find_specialised(P);
+    if (spec) {
+      specialised = true;
+      CUDA_CHECK(cudaFuncSetAttribute(spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      ::qgpu::KernelScope ks(ctx, "k_fused_scan_agg_spec");
+      spec<<<grid, F_NT, smem_bytes, ctx->stream>>>(P);
+      CUDA_CHECK(cudaGetLastError());
+    } else {
+      LAUNCH(ctx, k_fused_scan_agg<FM_DENSE>, grid, F_NT, smem_bytes, P);
+    }
   } else {
     // capacity: bounded by the key domain and by the row count; grown x8 on overflow
     i128 domain = total_bits >= 63 ? ((i128)1 << 63) : ((i128)1 << total_bits);
@@ -1094,7 +1478,7 @@ bool try_fused_scan_aggregate(PlanNode& agg, View* out) {
       P.cap_mask = (uint64_t)(cap - 1);
       P.n_groups = (unsigned long long*)flags->ptr;
       P.abort_flag = (int*)((char*)flags->ptr + 8);
-      LAUNCH(ctx, k_fused_scan_agg, grid, F_NT, smem_bytes, P);
+      LAUNCH(ctx, k_fused_scan_agg<FM_HASH>, grid, F_NT, smem_bytes, P);
       const int aborted = ctx->read_scalar((const int*)((char*)flags->ptr + 8));
       if (!aborted) break;
       if (cap >= need) throw_internal("fused aggregate: hash table overflow (internal error)");
@@ -1161,7 +1545,8 @@ bool try_fused_scan_aggregate(PlanNode& agg, View* out) {
       ctx->sync();
     }
   }
-  agg.strategy = std::string("fused_scan_agg[") + (P.mode == FM_DENSE ? "dense-private" : "hbm-hash") + ", " +
+  agg.strategy = std::string("fused_scan_agg[") + (P.mode == FM_DENSE ? "dense-private" : "hbm-hash") +
+                 (specialised ? "/shape-specialised, " : ", ") +
                  std::to_string(P.n_cols) + " cols, " + std::to_string(P.n_pred) + " range preds, " + std::to_string(P.n_accs) +
                  " accs, " + std::to_string(P.stages) + " TMA stages]";
   *out = finish_aggregate(ctx, v, keys, specs, agg.schema, accs);
