@@ -803,6 +803,54 @@ __global__ void k_fused_export(const unsigned long long* __restrict__ lo, const 
   }
 }
 
+// Small tables (DENSE mode: <= 4096 slots): occupied flags, prefix sum, compaction and export in ONE CTA; the
+// group count stays on the device (finish_aggregate fetches it together with its own flags).
+__global__ void __launch_bounds__(1024) k_fused_export_small(const unsigned long long* __restrict__ lo,
+                                                             const unsigned long long* __restrict__ hi, int n_slots, int64_t k_stride,
+                                                             int64_t g_stride, int n_accs, int force_all, FExport ex,
+                                                             unsigned long long* __restrict__ out_cnt, long long* __restrict__ out_first,
+                                                             long long* __restrict__ n_groups_out) {
+  __shared__ int pre[1024];
+  const int tid = threadIdx.x;
+  const int per = (n_slots + 1023) / 1024;
+  const int base = tid * per;
+  int c = 0;
+  unsigned mask = 0;
+  for (int i = 0; i < per; ++i) {
+    const int g = base + i;
+    const bool occ = g < n_slots && (force_all || lo[(int64_t)n_accs * k_stride + g * g_stride] != 0);
+    c += occ;
+    mask |= (unsigned)occ << i;
+  }
+  pre[tid] = c;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    const int v = tid >= d ? pre[tid - d] : 0;
+    __syncthreads();
+    pre[tid] += v;
+    __syncthreads();
+  }
+  int o = pre[tid] - c;
+  if (tid == 1023) *n_groups_out = pre[1023];
+  for (int i = 0; i < per; ++i) {
+    if (!((mask >> i) & 1)) continue;
+    const int64_t g = base + i;
+    out_cnt[o] = lo[(int64_t)n_accs * k_stride + g * g_stride];
+    out_first[o] = (long long)lo[(int64_t)(n_accs + 1) * k_stride + g * g_stride];
+    for (int a = 0; a < ex.n_aggs; ++a) {
+      const int k = ex.acc_of[a];
+      if (k < 0) continue;
+      const unsigned long long l = lo[(int64_t)k * k_stride + g * g_stride];
+      unsigned long long h = 0;
+      if (ex.wide[a]) h = hi[(int64_t)k * k_stride + g * g_stride];
+      else if (ex.kind_of[a] != FK_SUMF) h = ((long long)l < 0) ? ~0ull : 0ull;
+      ex.out_lo[a][o] = l;
+      ex.out_hi[a][o] = h;
+    }
+    ++o;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // dictionary encoding of low-cardinality Utf8 columns (<= 255 distinct values)
 // ------------------------------------------------------------------------------------------------
@@ -1130,27 +1178,38 @@ struct Range {
 
 }  // namespace
 
-bool try_fused_scan_aggregate(PlanNode& agg, View* out) {
-  Ctx* ctx = agg.ctx;
-  // ---- shape: Aggregate <- (Filter <-)* Scan --------------------------------------------------------
-  std::vector<const ExprNode*> predicates;
-  PlanNode* n = agg.children[0].get();
-  while (n->kind == PK_FILTER) {
-    predicates.push_back(n->predicate.get());
-    n = n->children[0].get();
-  }
-  if (n->kind != PK_SCAN) return false;
-  if (n->predicate) predicates.push_back(n->predicate.get());
-  if ((int)agg.aggs.size() > 24 || agg.aggs.empty() || (int)agg.group_exprs.size() > F_MAXK) return false;
-  View v = scan_view(*n);
-  if (v.num_batches == 0 || v.num_rows == 0 || v.num_rows >= ((int64_t)1 << 40)) return false;
-  if (agg.schema.fields.size() != agg.group_exprs.size() + agg.aggs.size()) return false;
-
+namespace {
+// Everything the analysis of one Aggregate <- (Filter)* <- Scan subtree produces; cached on the plan node and
+// re-used by later executes while the table's resident columns are unchanged.
+struct FusedPlan {
   FParams P;
-  memset(&P, 0, sizeof(P));
   std::vector<std::shared_ptr<Compiled>> keys;
   std::vector<AggSpec> specs;
-  std::vector<int> acc_of(agg.aggs.size(), -1);
+  std::vector<int> acc_of;
+  int total_bits = 0;
+  size_t smem_bytes = 0;
+  int grid = 0;
+  FusedKernel spec = nullptr;
+  // validity of the cache
+  std::vector<const DCol*> col_ids;
+  int64_t n_rows = 0, n_batches = 0;
+  bool usable = false;
+};
+}  // namespace
+
+static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& predicates, const View& v, FusedPlan& fp) {
+  Ctx* ctx = agg.ctx;
+  if ((int)agg.aggs.size() > 24 || agg.aggs.empty() || (int)agg.group_exprs.size() > F_MAXK) return false;
+  if (agg.schema.fields.size() != agg.group_exprs.size() + agg.aggs.size()) return false;
+
+  FParams& P = fp.P;
+  memset(&P, 0, sizeof(P));
+  std::vector<std::shared_ptr<Compiled>>& keys = fp.keys;
+  std::vector<AggSpec>& specs = fp.specs;
+  std::vector<int>& acc_of = fp.acc_of;
+  keys.clear();
+  specs.clear();
+  acc_of.assign(agg.aggs.size(), -1);
   std::vector<i128> acc_maxabs;
   bool dense_ok = true;
   i128 dense_groups = 1;
@@ -1416,9 +1475,25 @@ bool try_fused_scan_aggregate(PlanNode& agg, View* out) {
   P.stages = stages;
   P.priv_off = 128 + (uint32_t)stages * stage_bytes;
   P.dense_groups = (int)dense_groups;
-  const size_t smem_bytes = (size_t)P.priv_off + priv_bytes;
-  const int grid = (int)std::min<int64_t>(P.n_tiles, grid_max);
+  fp.smem_bytes = (size_t)P.priv_off + priv_bytes;
+  fp.grid = (int)std::min<int64_t>(P.n_tiles, grid_max);
+  fp.total_bits = total_bits;
+  fp.spec = getenv("QGPU_FUSED_GENERIC") ? nullptr : find_specialised(P);
+  return true;
+}
 
+
+static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
+  Ctx* ctx = agg.ctx;
+  FParams P = fp.P;
+  std::vector<std::shared_ptr<Compiled>>& keys = fp.keys;
+  std::vector<AggSpec>& specs = fp.specs;
+  std::vector<int>& acc_of = fp.acc_of;
+  const int total_bits = fp.total_bits;
+  const size_t smem_bytes = fp.smem_bytes;
+  const int grid = fp.grid;
+  const int64_t n_rows = P.n_rows;
+  const int NA2 = P.n_accs + 2;
   // ---- global accumulator table ---------------------------------------------------------------------------
   FInit init;
   for (int k = 0; k < NA2; ++k) {
@@ -1444,7 +1519,7 @@ bool try_fused_scan_aggregate(PlanNode& agg, View* out) {
     P.g_hi = (unsigned long long*)g_hi->ptr;
     P.abort_flag = (int*)((char*)flags->ptr + 8);
     P.n_groups = (unsigned long long*)flags->ptr;
-    FusedKernel spec = getenv("QGPU_FUSED_GENERIC") ? nullptr : find_specialised(P);
+    FusedKernel spec = fp.spec;
     if (spec) {
       specialised = true;
       CUDA_CHECK(cudaFuncSetAttribute(spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
@@ -1487,13 +1562,23 @@ bool try_fused_scan_aggregate(PlanNode& agg, View* out) {
   }
 
   // ---- export: occupied slots -> dense group ids, accumulators -> GroupAccs ---------------------------------
-  DBufP occ = ctx->alloc((size_t)n_slots * 8), offs = ctx->alloc((size_t)n_slots * 8);
-  LAUNCH(ctx, k_fused_occupied, grid_for(ctx, n_slots, 256), 256, 0, (const unsigned long long*)g_lo->ptr, n_slots,
-         (int64_t)P.n_accs * k_stride, g_stride, (int64_t*)occ->ptr);
-  int64_t n_groups = exclusive_scan_i64(ctx, (const int64_t*)occ->ptr, (int64_t*)offs->ptr, n_slots);
   const bool grouped = !keys.empty();
+  const bool small = P.mode == FM_DENSE;  // <= 4096 slots: one-CTA export, no host round trip for the group count
+  int64_t n_groups = 0;
+  DBufP occ, offs, n_groups_dev;
+  if (small) {
+    n_groups = grouped ? n_slots : 1;
+    n_groups_dev = ctx->alloc_zero(8);
+  } else {
+    occ = ctx->alloc((size_t)n_slots * 8);
+    offs = ctx->alloc((size_t)n_slots * 8);
+    LAUNCH(ctx, k_fused_occupied, grid_for(ctx, n_slots, 256), 256, 0, (const unsigned long long*)g_lo->ptr, n_slots,
+           (int64_t)P.n_accs * k_stride, g_stride, (int64_t*)occ->ptr);
+    n_groups = exclusive_scan_i64(ctx, (const int64_t*)occ->ptr, (int64_t*)offs->ptr, n_slots);
+  }
   GroupAccs accs;
   accs.n_groups = grouped ? n_groups : 1;
+  if (small && grouped) accs.n_groups_dev = n_groups_dev;
   const int64_t ng_alloc = std::max<int64_t>(accs.n_groups, 1);
   DBufP cnt = ctx->alloc_zero((size_t)ng_alloc * 8);
   DBufP first = ctx->alloc_zero((size_t)ng_alloc * 8);
@@ -1529,27 +1614,65 @@ bool try_fused_scan_aggregate(PlanNode& agg, View* out) {
     accs.cnt.push_back(cnt);
   }
   accs.first_row = first;
-  if (n_groups > 0)
-    LAUNCH(ctx, k_fused_export, grid_for(ctx, n_slots, 256), 256, 0, (const unsigned long long*)g_lo->ptr,
-           g_hi ? (const unsigned long long*)g_hi->ptr : nullptr, n_slots, k_stride, g_stride, P.n_accs, (const int64_t*)occ->ptr,
-           (const int64_t*)offs->ptr, ex, (unsigned long long*)cnt->ptr, (long long*)first->ptr);
-  if (!grouped && n_groups == 0) {
-    // no row passed the filter: MIN/MAX keep their sentinels (reference quirk Q4), SUM/AVG are NULL (cnt == 0)
-    for (size_t i = 0; i < specs.size(); ++i) {
-      const int k = acc_of[i];
-      if (k < 0 || P.accs[k].kind == FK_SUM || P.accs[k].kind == FK_SUMF) continue;
-      const long long sent = P.accs[k].kind == FK_MIN ? INT64_MAX : INT64_MIN;
-      unsigned long long h[2] = {(unsigned long long)sent, sent < 0 ? ~0ull : 0ull};
-      ctx->h2d(accs.lo[i]->ptr, &h[0], 8);
-      ctx->h2d(accs.hi[i]->ptr, &h[1], 8);
-      ctx->sync();
+  if (small) {
+    // ungrouped: slot 0 is exported even when no row passed -- MIN/MAX then keep their sentinels (reference
+    // quirk Q4), SUM/AVG are NULL because the row count is 0
+    LAUNCH(ctx, k_fused_export_small, 1, 1024, 0, (const unsigned long long*)g_lo->ptr,
+           g_hi ? (const unsigned long long*)g_hi->ptr : nullptr, (int)n_slots, k_stride, g_stride, P.n_accs, grouped ? 0 : 1, ex,
+           (unsigned long long*)cnt->ptr, (long long*)first->ptr, (long long*)n_groups_dev->ptr);
+  } else {
+    if (n_groups > 0)
+      LAUNCH(ctx, k_fused_export, grid_for(ctx, n_slots, 256), 256, 0, (const unsigned long long*)g_lo->ptr,
+             g_hi ? (const unsigned long long*)g_hi->ptr : nullptr, n_slots, k_stride, g_stride, P.n_accs, (const int64_t*)occ->ptr,
+             (const int64_t*)offs->ptr, ex, (unsigned long long*)cnt->ptr, (long long*)first->ptr);
+    if (!grouped && n_groups == 0) {
+      // no row passed the filter: MIN/MAX keep their sentinels (reference quirk Q4), SUM/AVG are NULL (cnt == 0)
+      for (size_t i = 0; i < specs.size(); ++i) {
+        const int k = acc_of[i];
+        if (k < 0 || P.accs[k].kind == FK_SUM || P.accs[k].kind == FK_SUMF) continue;
+        const long long sent = P.accs[k].kind == FK_MIN ? INT64_MAX : INT64_MIN;
+        unsigned long long h[2] = {(unsigned long long)sent, sent < 0 ? ~0ull : 0ull};
+        ctx->h2d(accs.lo[i]->ptr, &h[0], 8);
+        ctx->h2d(accs.hi[i]->ptr, &h[1], 8);
+        ctx->sync();
+      }
     }
   }
   agg.strategy = std::string("fused_scan_agg[") + (P.mode == FM_DENSE ? "dense-private" : "hbm-hash") +
                  (specialised ? "/shape-specialised, " : ", ") +
                  std::to_string(P.n_cols) + " cols, " + std::to_string(P.n_pred) + " range preds, " + std::to_string(P.n_accs) +
                  " accs, " + std::to_string(P.stages) + " TMA stages]";
-  *out = finish_aggregate(ctx, v, keys, specs, agg.schema, accs);
+  return finish_aggregate(ctx, v, keys, specs, agg.schema, accs);
+}
+
+bool try_fused_scan_aggregate(PlanNode& agg, View* out) {
+  // ---- shape: Aggregate <- (Filter <-)* Scan --------------------------------------------------------
+  std::vector<const ExprNode*> predicates;
+  PlanNode* n = agg.children[0].get();
+  while (n->kind == PK_FILTER) {
+    predicates.push_back(n->predicate.get());
+    n = n->children[0].get();
+  }
+  if (n->kind != PK_SCAN) return false;
+  if (n->predicate) predicates.push_back(n->predicate.get());
+  View v = scan_view(*n);
+  if (v.num_batches == 0 || v.num_rows == 0 || v.num_rows >= ((int64_t)1 << 40)) return false;
+  std::shared_ptr<FusedPlan> fp = std::static_pointer_cast<FusedPlan>(agg.fused_cache);
+  bool fresh = false;
+  if (fp) {
+    fresh = fp->n_rows == v.num_rows && fp->n_batches == v.num_batches && fp->col_ids.size() == v.cols.size();
+    for (size_t i = 0; fresh && i < v.cols.size(); ++i) fresh = fp->col_ids[i] == v.cols[i].base.get() && !v.cols[i].idx;
+  }
+  if (!fresh) {
+    fp = std::make_shared<FusedPlan>();
+    fp->usable = analyze_fused(agg, predicates, v, *fp);
+    fp->n_rows = v.num_rows;
+    fp->n_batches = v.num_batches;
+    for (auto& c : v.cols) fp->col_ids.push_back(c.base.get());
+    agg.fused_cache = fp;
+  }
+  if (!fp->usable) return false;
+  *out = run_fused(agg, v, *fp);
   return true;
 }
 

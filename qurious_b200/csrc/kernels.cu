@@ -500,7 +500,7 @@ __global__ void k_str_copy(const char* __restrict__ src, const int32_t* __restri
   }
 }
 
-DColP take_column(Ctx* ctx, const DCol& base, const int64_t* idx, int64_t n) {
+DColP take_column(Ctx* ctx, const DCol& base, const int64_t* idx, int64_t n, bool idx_may_have_null) {
   auto col = std::make_shared<DCol>();
   col->type = base.type;
   col->phys = base.phys;
@@ -512,8 +512,8 @@ DColP take_column(Ctx* ctx, const DCol& base, const int64_t* idx, int64_t n) {
   }
   const int g = grid_for(ctx, n, 256);
   const int64_t n_words = (n + 31) >> 5;
-  // validity: a NULL index or a NULL source slot => NULL
-  {
+  // validity: a NULL index or a NULL source slot => NULL (skipped when neither can occur)
+  if (base.null_count != 0 || idx_may_have_null) {
     col->validity = ctx->alloc(std::max<size_t>((size_t)n_words * 4, 4));
     DBufP zc = ctx->alloc_zero(8);
     if (n > 0)
@@ -583,7 +583,7 @@ __global__ void k_widen_d64(const int64_t* __restrict__ src, ulonglong2* __restr
 DColP materialize(Ctx* ctx, const LazyCol& col, int64_t n) {
   if (!col.base) throw_internal("column was not uploaded to the GPU table");
   if (!col.idx) return col.base;
-  return take_column(ctx, *col.base, col.idx->ptr(), n);
+  return take_column(ctx, *col.base, col.idx->ptr(), n, col.idx->may_have_null);
 }
 
 DColP materialize_arrow(Ctx* ctx, const LazyCol& col, int64_t n) {

@@ -19,7 +19,7 @@ IdxP eval_filter(Ctx* ctx, Compiled& c, const View& v);
 // ---- gathers ------------------------------------------------------------------------------------
 IdxP compose_idx(Ctx* ctx, const IdxP& inner, const IdxP& outer);  // r[i] = outer[i]<0 ? -1 : inner[outer[i]]
 LazyCol apply_selection(Ctx* ctx, const LazyCol& col, const IdxP& sel, std::vector<std::pair<IdxP, IdxP>>* cache);
-DColP take_column(Ctx* ctx, const DCol& base, const int64_t* idx, int64_t n);
+DColP take_column(Ctx* ctx, const DCol& base, const int64_t* idx, int64_t n, bool idx_may_have_null = true);
 // Column in canonical Arrow layout (narrowed decimals widened, gathers applied).
 DColP materialize_arrow(Ctx* ctx, const LazyCol& col, int64_t n);
 // Column with gathers applied but physical narrowing kept (internal consumers).

@@ -309,18 +309,32 @@ __device__ __forceinline__ double key_to_f64(long long k) {
   return c.d;
 }
 
-// one warp per 32 groups so that the validity word is produced by one ballot
-__global__ void __launch_bounds__(256) k_agg_finalize(FinSpec f, int64_t n_groups, int* __restrict__ err,
-                                                      unsigned long long* __restrict__ null_count) {
+struct FinAll {
+  int n_aggs;
+  int pad;
+  const long long* order;  // output position -> group id (nullptr = identity)
+  FinSpec f[MAX_AGGS];
+};
+
+// blockIdx.y = aggregate; one warp per 32 output rows so that the validity word is produced by one ballot.
+// flags: [0] = max EvalErr, [1 + a] = NULL count of aggregate a
+__global__ void __launch_bounds__(256) k_agg_finalize(const __grid_constant__ FinAll all, int64_t n_groups_host,
+                                                      const long long* __restrict__ n_groups_dev,
+                                                      unsigned long long* __restrict__ flags) {
+  const int64_t n_groups = n_groups_dev ? (int64_t)*n_groups_dev : n_groups_host;
+  const FinSpec& f = all.f[blockIdx.y];
+  int* err = (int*)flags;
+  unsigned long long* null_count = flags + 1 + blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t n_words = (n_groups + 31) >> 5;
   for (int64_t w = warp_id; w < n_words; w += warps) {
-    const int64_t g = (w << 5) + lane;
+    const int64_t pos = (w << 5) + lane;
     bool valid = false;
     unsigned long long lo = 0, hi = 0;
-    if (g < n_groups) {
+    if (pos < n_groups) {
+      const int64_t g = all.order ? all.order[pos] : pos;
       const unsigned long long cnt = f.cnt[g];
       switch (f.op) {
         case QGPU_AGG_COUNT:
@@ -380,23 +394,42 @@ __global__ void __launch_bounds__(256) k_agg_finalize(FinSpec f, int64_t n_group
       int live = (int)min((int64_t)32, n_groups - (w << 5));
       if (live - __popc(vw)) atomicAdd(null_count, (unsigned long long)(live - __popc(vw)));
     }
-    if (g < n_groups) {
+    if (pos < n_groups) {
       if (!valid) lo = hi = 0;
       switch (f.out_phys) {
-        case PH_I8: case PH_U8: ((uint8_t*)f.out)[g] = (uint8_t)lo; break;
-        case PH_I16: case PH_U16: ((uint16_t*)f.out)[g] = (uint16_t)lo; break;
-        case PH_I32: case PH_U32: ((uint32_t*)f.out)[g] = (uint32_t)lo; break;
-        case PH_I64: case PH_U64: case PH_F64: ((unsigned long long*)f.out)[g] = lo; break;
+        case PH_I8: case PH_U8: ((uint8_t*)f.out)[pos] = (uint8_t)lo; break;
+        case PH_I16: case PH_U16: ((uint16_t*)f.out)[pos] = (uint16_t)lo; break;
+        case PH_I32: case PH_U32: ((uint32_t*)f.out)[pos] = (uint32_t)lo; break;
+        case PH_I64: case PH_U64: case PH_F64: ((unsigned long long*)f.out)[pos] = lo; break;
         case PH_F32: {
           union { unsigned long long u; double d; } c;
           c.u = lo;
-          ((float*)f.out)[g] = (float)c.d;
+          ((float*)f.out)[pos] = (float)c.d;
           break;
         }
-        case PH_I128: ((ulonglong2*)f.out)[g] = make_ulonglong2(lo, hi); break;
+        case PH_I128: ((ulonglong2*)f.out)[pos] = make_ulonglong2(lo, hi); break;
         default: break;
       }
     }
+  }
+}
+
+// Output order = first occurrence (the reference's order is unspecified).  Small group
+// counts are ranked on the device by one CTA (first rows are distinct): order[rank] = g, first_idx[rank] = row.
+#define RANK_MAX 4096
+__global__ void __launch_bounds__(1024) k_rank_order(const long long* __restrict__ first_row, int n_host,
+                                                     const long long* __restrict__ n_dev, long long* __restrict__ order,
+                                                     long long* __restrict__ first_idx) {
+  __shared__ long long fr[RANK_MAX];
+  const int n = n_dev ? (int)*n_dev : n_host;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) fr[i] = first_row[i];
+  __syncthreads();
+  for (int g = threadIdx.x; g < n; g += blockDim.x) {
+    const long long mine = fr[g];
+    int rank = 0;
+    for (int h = 0; h < n; ++h) rank += fr[h] < mine;
+    order[rank] = g;
+    first_idx[rank] = mine;
   }
 }
 
@@ -576,47 +609,45 @@ View run_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<Comp
 View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<Compiled>>& keys, std::vector<AggSpec>& aggs,
                       const Schema& out_schema, GroupAccs& accs) {
   const bool grouped = !keys.empty();
-  const int64_t n_groups = accs.n_groups;
+  // with a device-side count, `n_max` only sizes the buffers; the real count arrives with the flags below
+  const int64_t n_max = accs.n_groups;
+  const long long* n_dev = accs.n_groups_dev ? (const long long*)accs.n_groups_dev->ptr : nullptr;
+  if (n_dev && n_max > RANK_MAX) throw_internal("deferred group count needs n_groups <= RANK_MAX");
   View out;
   out.schema = out_schema;
   // ---- group order: first occurrence (the reference's order is unspecified) --
   IdxP order;        // output position -> gid
   IdxP first_idx;    // output position -> first input row of the group
   if (grouped) {
-    std::vector<long long> fr((size_t)n_groups);
-    if (n_groups > 0) ctx->d2h_sync(fr.data(), accs.first_row->ptr, (size_t)n_groups * 8);
-    std::vector<long long> ord((size_t)n_groups);
-    std::iota(ord.begin(), ord.end(), 0LL);
-    if (n_groups <= (1 << 22)) std::sort(ord.begin(), ord.end(), [&](long long a, long long b) { return fr[a] < fr[b]; });
-    std::vector<long long> fidx((size_t)n_groups);
-    for (int64_t i = 0; i < n_groups; ++i) fidx[i] = fr[ord[i]];
     order = std::make_shared<IdxVec>();
-    order->length = n_groups;
-    order->buf = ctx->alloc(std::max<size_t>((size_t)n_groups * 8, 8));
+    order->length = n_max;
+    order->buf = ctx->alloc(std::max<size_t>((size_t)n_max * 8, 8));
     first_idx = std::make_shared<IdxVec>();
-    first_idx->length = n_groups;
-    first_idx->buf = ctx->alloc(std::max<size_t>((size_t)n_groups * 8, 8));
-    if (n_groups > 0) {
-      ctx->h2d(order->buf->ptr, ord.data(), (size_t)n_groups * 8);
-      ctx->h2d(first_idx->buf->ptr, fidx.data(), (size_t)n_groups * 8);
+    first_idx->length = n_max;
+    first_idx->buf = ctx->alloc(std::max<size_t>((size_t)n_max * 8, 8));
+    if (n_max > 0 && n_max <= RANK_MAX) {
+      LAUNCH(ctx, k_rank_order, 1, 1024, 0, (const long long*)accs.first_row->ptr, (int)n_max, n_dev, (long long*)order->buf->ptr,
+             (long long*)first_idx->buf->ptr);
+    } else if (n_max > 0) {
+      std::vector<long long> fr((size_t)n_max);
+      ctx->d2h_sync(fr.data(), accs.first_row->ptr, (size_t)n_max * 8);
+      std::vector<long long> ord((size_t)n_max);
+      std::iota(ord.begin(), ord.end(), 0LL);
+      if (n_max <= (1 << 22)) std::sort(ord.begin(), ord.end(), [&](long long a, long long b) { return fr[a] < fr[b]; });
+      std::vector<long long> fidx((size_t)n_max);
+      for (int64_t i = 0; i < n_max; ++i) fidx[i] = fr[ord[i]];
+      ctx->h2d(order->buf->ptr, ord.data(), (size_t)n_max * 8);
+      ctx->h2d(first_idx->buf->ptr, fidx.data(), (size_t)n_max * 8);
       ctx->sync();
     }
   }
-  out.num_rows = n_groups;
-  out.num_batches = 1;
-  // ---- key columns: values of the group's first row (hash.rs:62-68) ---------------------------------
-  if (grouped) {
-    View firsts = apply_selection_view(ctx, input, first_idx);
-    for (size_t i = 0; i < keys.size(); ++i) {
-      Compiled& k = *keys[i];
-      if (k.result_type != out_schema.fields[i].type)
-        throw_arrow("column types must match schema types, expected " + out_schema.fields[i].type.str() + " but found " +
-                    k.result_type.str() + " at column index " + std::to_string(i));
-      if (k.is_column_ref) out.cols.push_back(firsts.cols[k.column_ref]);
-      else out.cols.push_back({eval_to_column(ctx, k, firsts), nullptr});
-    }
-  }
-  // ---- aggregate columns ----------------------------------------------------------------------------
+  // ---- aggregate columns: ONE launch finalises every aggregate directly in output order ----------------
+  FinAll all;
+  memset(&all, 0, sizeof(all));
+  all.n_aggs = (int)aggs.size();
+  all.order = grouped ? (const long long*)order->buf->ptr : nullptr;
+  std::vector<DColP> cols;
+  const int64_t max_words = (n_max + 31) >> 5;
   for (size_t i = 0; i < aggs.size(); ++i) {
     AggSpec& a = aggs[i];
     const Field& of = out_schema.fields[keys.size() + i];
@@ -629,12 +660,9 @@ View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<C
     auto col = std::make_shared<DCol>();
     col->type = produced;
     col->phys = out_phys_of(produced);
-    col->length = n_groups;
-    const int64_t n_words = (n_groups + 31) >> 5;
-    col->data = ctx->alloc(std::max<size_t>((size_t)n_groups * std::max(phys_width(col->phys), 1), 16));
-    col->validity = ctx->alloc(std::max<size_t>((size_t)n_words * 4, 4));
-    FinSpec f;
-    memset(&f, 0, sizeof(f));
+    col->data = ctx->alloc(std::max<size_t>((size_t)n_max * std::max(phys_width(col->phys), 1), 16));
+    col->validity = ctx->alloc(std::max<size_t>((size_t)max_words * 4, 4));
+    FinSpec& f = all.f[i];
     f.op = a.op;
     f.kind = accs.kind[i];
     f.out_phys = col->phys;
@@ -648,21 +676,50 @@ View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<C
     f.cnt = (const unsigned long long*)accs.cnt[i]->ptr;
     f.out = col->data->ptr;
     f.out_valid = (uint32_t*)col->validity->ptr;
-    DBufP flags = ctx->alloc_zero(16);
-    if (n_groups > 0) {
-      LAUNCH(ctx, k_agg_finalize, grid_for(ctx, n_groups, 256), 256, 0, f, n_groups, (int*)flags->ptr,
-             (unsigned long long*)((char*)flags->ptr + 8));
-      struct { int err; int pad; unsigned long long nulls; } h;
-      ctx->d2h_sync(&h, flags->ptr, 16);
-      if (h.err) throw_eval_error(h.err);
-      col->null_count = (int64_t)h.nulls;
+    cols.push_back(col);
+  }
+  int64_t n_groups = n_max;
+  if (n_max > 0 && !aggs.empty()) {
+    // flags: [0] EvalErr, [1..n_aggs] NULL counts, [MAX_AGGS + 1] group count (copied from the device-side counter)
+    DBufP flags = ctx->alloc_zero(8 * (MAX_AGGS + 2));
+    dim3 grid((unsigned)grid_for(ctx, n_max, 256), (unsigned)aggs.size());
+    LAUNCH(ctx, k_agg_finalize, grid, 256, 0, all, n_max, n_dev, (unsigned long long*)flags->ptr);
+    if (n_dev)
+      CUDA_CHECK(cudaMemcpyAsync((char*)flags->ptr + 8 * (MAX_AGGS + 1), n_dev, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    unsigned long long h[MAX_AGGS + 2];
+    ctx->d2h_sync(h, flags->ptr, 8 * (MAX_AGGS + 2));
+    if ((int)h[0]) throw_eval_error((int)h[0]);
+    for (size_t i = 0; i < aggs.size(); ++i) cols[i]->null_count = (int64_t)h[1 + i];
+    if (n_dev) n_groups = (int64_t)h[MAX_AGGS + 1];
+  } else if (n_dev) {
+    n_groups = (int64_t)ctx->read_scalar(n_dev);
+  }
+  out.num_rows = n_groups;
+  out.num_batches = 1;
+  // ---- key columns: values of the group's first row (hash.rs:62-68) ---------------------------------
+  if (grouped) {
+    order->length = n_groups;
+    first_idx->length = n_groups;
+    View firsts = apply_selection_view(ctx, input, first_idx);
+    for (size_t i = 0; i < keys.size(); ++i) {
+      Compiled& k = *keys[i];
+      if (k.result_type != out_schema.fields[i].type)
+        throw_arrow("column types must match schema types, expected " + out_schema.fields[i].type.str() + " but found " +
+                    k.result_type.str() + " at column index " + std::to_string(i));
+      if (k.is_column_ref) out.cols.push_back(firsts.cols[k.column_ref]);
+      else out.cols.push_back({eval_to_column(ctx, k, firsts), nullptr});
     }
+  }
+  for (size_t i = 0; i < aggs.size(); ++i) {
+    AggSpec& a = aggs[i];
+    DColP& col = cols[i];
+    col->length = n_groups;
     if (col->null_count == 0) col->validity.reset();
-    if (col->null_count > 0 && a.op == QGPU_AGG_SUM && produced.is_decimal() && ctx->compat_empty_decimal_sum)
-      throw_arrow("column types must match schema types, expected " + produced.str() + " but found Decimal128(38, 10)");
+    if (col->null_count > 0 && a.op == QGPU_AGG_SUM && col->type.is_decimal() && ctx->compat_empty_decimal_sum)
+      throw_arrow("column types must match schema types, expected " + col->type.str() + " but found Decimal128(38, 10)");
     if (col->null_count > 0 && (a.op == QGPU_AGG_MIN || a.op == QGPU_AGG_MAX) && ctx->compat_empty_decimal_sum)
-      throw_arrow("column types must match schema types, expected " + produced.str() + " but found Null");
-    out.cols.push_back({col, grouped ? order : nullptr});
+      throw_arrow("column types must match schema types, expected " + col->type.str() + " but found Null");
+    out.cols.push_back({col, nullptr});
   }
   return out;
 }

@@ -24,6 +24,9 @@ struct GroupAccs {
   std::vector<int> kind;            // AccKind per aggregate
   std::vector<DBufP> lo, hi, cnt;   // per aggregate: u64[n_groups] each (cnt = number of non-NULL inputs)
   DBufP first_row;                  // i64[n_groups]: first input row of the group
+  // optional: the actual group count is still on the device (int64); n_groups is then an upper bound and
+  // finish_aggregate reads the count together with its own flags in ONE device->host copy
+  DBufP n_groups_dev;
 };
 View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<Compiled>>& keys, std::vector<AggSpec>& aggs,
                       const Schema& out_schema, GroupAccs& accs);

@@ -445,7 +445,8 @@ int64_t qgpu_table_column_bytes(const qgpu_table* t, int32_t col) {
     }
     const DCol& c = *ti.cols[col];
     int64_t b = 0;
-    if (c.phys == PH_STR) b = (c.length + 1) * 4 + c.str_bytes;
+    if (c.phys == PH_STR && c.dict_state == 1) b = c.length;  // dictionary codes are what the kernels stream
+    else if (c.phys == PH_STR) b = (c.length + 1) * 4 + c.str_bytes;
     else if (c.phys == PH_BIT) b = (c.length + 7) / 8;
     else b = c.length * phys_width(c.phys);
     if (c.validity) b += (c.length + 7) / 8;

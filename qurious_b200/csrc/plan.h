@@ -40,6 +40,7 @@ struct PlanNode {
   int64_t last_launches = 0;
   std::string strategy = "not-executed";
   std::string strategy_desc;
+  std::shared_ptr<void> fused_cache;  // fused.cu: analysis of this Aggregate <- (Filter)* <- Scan subtree
 
   View execute();
 };

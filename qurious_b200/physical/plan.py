@@ -101,29 +101,49 @@ class PhysicalPlan:
             elif kind == "expr":
                 ctx.lib.qgpu_expr_free(h)
 
-    def execute(self, ctx: Optional[_lib.Context] = None) -> List[pa.RecordBatch]:
+    def _native_cached(self, ctx: Optional[_lib.Context] = None):
+        """The native plan (qgpu_plan handles) is built once per (plan object, context) and re-used by later
+        execute() calls: like the reference's operators, a plan is immutable and re-executable
+        (physical/plan/mod.rs:25-29 takes &self)."""
+        ctx = ctx or _lib.default_context()
+        cached = self.__dict__.get("_native_handles")
+        if cached is not None and cached[0] is ctx and ctx.handle:
+            return cached
+        if cached is not None:
+            self.release()
         ctx, h, keep = self._native(ctx)
+        self.__dict__["_native_handles"] = (ctx, h, keep)
+        return ctx, h, keep
+
+    def release(self):
+        """Free the cached native plan handles."""
+        cached = self.__dict__.pop("_native_handles", None)
+        if cached is not None and cached[0].handle:
+            self._free(cached[0], cached[2])
+
+    def __del__(self):
         try:
-            stream = _lib.new_stream()
-            ctx.check(ctx.lib.qgpu_plan_execute(h, _lib.addr(stream)))
-            self._record_stats(ctx, h)
-            return _lib.read_stream(ctx, stream)
-        finally:
-            self._free(ctx, keep)
+            self.release()
+        except Exception:
+            pass
+
+    def execute(self, ctx: Optional[_lib.Context] = None) -> List[pa.RecordBatch]:
+        ctx, h, keep = self._native_cached(ctx)
+        stream = _lib.new_stream()
+        ctx.check(ctx.lib.qgpu_plan_execute(h, _lib.addr(stream)))
+        self._record_stats(ctx, h)
+        return _lib.read_stream(ctx, stream)
 
     def execute_device(self, ctx: Optional[_lib.Context] = None) -> "_lib.DeviceTable":
         """Like execute() but the result stays in HBM."""
-        ctx, h, keep = self._native(ctx)
-        try:
-            out = ctypes.c_void_p()
-            nb = ctypes.c_int64()
-            ctx.check(ctx.lib.qgpu_plan_execute_device(h, ctypes.byref(out), ctypes.byref(nb)))
-            self._record_stats(ctx, h)
-            t = _lib.DeviceTable(ctx, out, self.schema)
-            t.reference_num_batches = nb.value
-            return t
-        finally:
-            self._free(ctx, keep)
+        ctx, h, keep = self._native_cached(ctx)
+        out = ctypes.c_void_p()
+        nb = ctypes.c_int64()
+        ctx.check(ctx.lib.qgpu_plan_execute_device(h, ctypes.byref(out), ctypes.byref(nb)))
+        self._record_stats(ctx, h)
+        t = _lib.DeviceTable(ctx, out, self.schema)
+        t.reference_num_batches = nb.value
+        return t
 
     def _record_stats(self, ctx, h):
         ms = ctypes.c_double()
