@@ -239,13 +239,10 @@ def algorithmic_bytes(query, dev_tables):
     return total, per_table
 
 
-def run_query_device(ctx, plan, steps, warmup, sampler, torch, stream, merge=None):
+def run_query_device(ctx, step, steps, warmup, sampler, torch, stream):
     """K timed steps, table resident in HBM; returns (ms_total, per-kernel profile, launches per step)."""
     for _ in range(warmup):
-        t = plan.execute_device(ctx)
-        if merge:
-            merge(t)
-        t.free()
+        step()
     ctx.profile(True)
     ctx.profile_report()
     l0 = ctx.kernel_launches()
@@ -255,10 +252,7 @@ def run_query_device(ctx, plan, steps, warmup, sampler, torch, stream, merge=Non
     sampler.region(True)
     e0.record(stream)
     for _ in range(steps):
-        t = plan.execute_device(ctx)
-        if merge:
-            merge(t)
-        t.free()
+        step()
     e1.record(stream)
     torch.cuda.synchronize()
     sampler.region(False)
@@ -304,11 +298,19 @@ def run_b200(args):
     rows_local = raw["lineitem"].rows
     dev_tables = {k: tpch.to_device_table(ctx, v) for k, v in raw.items()}
     plan = build_plan(q, dev_tables)
-    merge = None
+    sharded = None
     if world > 1:
+        # row-range shards: shard-local partial aggregate -> NCCL all-gather of the state blocks -> exact merge
         from qurious_b200 import distributed as qd
-        merge = qd.make_partial_merger(ctx, plan, _dist)
-    ms, prof, launches = run_query_device(ctx, plan, args.steps, args.warmup, sampler, torch, stream, merge)
+        lo, _hi = shard_range(tpch.n_lineitems(sf_total), rank, world)
+        sharded = qd.ShardedAggregate(ctx, plan, lo, world)
+
+        def step():
+            sharded.execute()
+    else:
+        def step():
+            plan.execute_device(ctx).free()
+    ms, prof, launches = run_query_device(ctx, step, args.steps, args.warmup, sampler, torch, stream)
     t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     rows_t = torch.tensor([rows_local], dtype=torch.int64, device="cuda")
     if world > 1:
@@ -356,9 +358,10 @@ def run_b200(args):
         def one_e2e():
             tabs = {k: MemoryTable.try_new(b[0].schema, b) for k, b in host.items()}
             p = build_plan(q, tabs)
-            out = p.execute(ctx)
-            if merge is not None:
-                pass  # multi-GPU e2e: shard-local result; merge is part of the device leg
+            if world > 1:
+                out = qd.ShardedAggregate(ctx, p, lo, world).execute()
+            else:
+                out = p.execute(ctx)
             d2h = batches_nbytes(out)
             for t in tabs.values():
                 if t._dev is not None:

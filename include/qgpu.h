@@ -218,6 +218,24 @@ int qgpu_plan_last_stats(const qgpu_plan* p, double* device_ms, int64_t* launche
 const char* qgpu_plan_strategy(const qgpu_plan* p);
 void qgpu_plan_free(qgpu_plan* p);
 
+/* ---- sharded (multi-GPU) aggregates: SURVEY 8e -----------------------------------------------------------
+ * The reference has no exchange operator (single process); this is the B200 build's distribution strategy for
+ * aggregates over row-range shards.  `p` must be (Projection|Filter)* <- HashAggregate/NoGroupingAggregate <- ...
+ * and every process runs the same plan over its own shard:
+ *   1. qgpu_plan_state_bytes(p, max_groups, &n)          size of one state block
+ *   2. qgpu_plan_partial_state(p, row_offset, max_groups, buf, n)
+ *        runs the aggregate on this shard up to (not including) finalisation and writes the per-group state
+ *        (packed key values, first row + row_offset, 128-bit accumulator words, counts) into the DEVICE buffer
+ *        `buf` (stream-ordered on qgpu_ctx_stream);
+ *   3. the caller all-gathers the blocks of all shards (ncclAllGather) into one device buffer;
+ *   4. qgpu_plan_execute_merged(p, gathered, n_states, max_groups, out)
+ *        merges the states exactly (integer/decimal results are bit-identical to one GPU over the whole table)
+ *        and finishes the plan.  More than max_groups groups on a shard -> QGPU_ERR_INTERNAL (use repartition). */
+int qgpu_plan_state_bytes(qgpu_plan* p, int32_t max_groups, int64_t* bytes);
+int qgpu_plan_partial_state(qgpu_plan* p, int64_t row_offset, int32_t max_groups, void* device_buf, int64_t cap_bytes);
+int qgpu_plan_execute_merged(qgpu_plan* p, const void* gathered_device_buf, int32_t n_states, int32_t max_groups,
+                             struct ArrowArrayStream* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,7 +26,7 @@ SYMBOLS = [
     "qgpu_table_free", "qgpu_expr_parse", "qgpu_expr_free", "qgpu_plan_scan", "qgpu_plan_filter",
     "qgpu_plan_projection", "qgpu_plan_aggregate", "qgpu_plan_hash_join", "qgpu_plan_schema",
     "qgpu_plan_execute", "qgpu_plan_execute_device", "qgpu_plan_last_stats", "qgpu_plan_strategy",
-    "qgpu_plan_free",
+    "qgpu_plan_free", "qgpu_plan_state_bytes", "qgpu_plan_partial_state", "qgpu_plan_execute_merged",
 ]
 
 STATUS_KIND = {1: "InternalError", 2: "ArrowError", 3: "CudaError", 4: "NcclError", 5: "OutOfMemory"}
@@ -113,6 +113,9 @@ def load_library() -> ctypes.CDLL:
     lib.qgpu_plan_strategy.restype = ctypes.c_char_p
     lib.qgpu_plan_free.argtypes = [vp]
     lib.qgpu_plan_free.restype = None
+    lib.qgpu_plan_state_bytes.argtypes = [vp, i32, P(i64)]
+    lib.qgpu_plan_partial_state.argtypes = [vp, i64, i32, vp, i64]
+    lib.qgpu_plan_execute_merged.argtypes = [vp, vp, i32, i32, vp]
     _lib = lib
     return lib
 

@@ -1642,6 +1642,14 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
                  (specialised ? "/shape-specialised, " : ", ") +
                  std::to_string(P.n_cols) + " cols, " + std::to_string(P.n_pred) + " range preds, " + std::to_string(P.n_accs) +
                  " accs, " + std::to_string(P.stages) + " TMA stages]";
+  if (agg.defer) {
+    agg.defer->set = true;
+    agg.defer->input = v;
+    agg.defer->keys = keys;
+    agg.defer->specs = specs;
+    agg.defer->accs = accs;
+    return View();
+  }
   return finish_aggregate(ctx, v, keys, specs, agg.schema, accs);
 }
 

@@ -492,7 +492,7 @@ void validate_agg_types(const std::vector<AggSpec>& aggs) {
 }
 
 View run_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<Compiled>>& keys, std::vector<AggSpec>& aggs,
-                   const Schema& out_schema) {
+                   const Schema& out_schema, AggPending* defer) {
   const int64_t n = input.num_rows;
   const bool grouped = !keys.empty();
   if ((int)aggs.size() > MAX_AGGS) throw_internal("more than 24 aggregate expressions are not supported");
@@ -603,11 +603,19 @@ View run_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<Comp
     accs.cnt.push_back(keep[3 * i + 2]);
   }
   accs.first_row = first_row;
+  if (defer) {
+    defer->set = true;
+    defer->input = input;
+    defer->keys = keys;
+    defer->specs = aggs;
+    defer->accs = accs;
+    return View();
+  }
   return finish_aggregate(ctx, input, keys, aggs, out_schema, accs);
 }
 
 View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<Compiled>>& keys, std::vector<AggSpec>& aggs,
-                      const Schema& out_schema, GroupAccs& accs) {
+                      const Schema& out_schema, GroupAccs& accs, std::vector<DColP>* key_cols, const unsigned long long* key_nulls) {
   const bool grouped = !keys.empty();
   // with a device-side count, `n_max` only sizes the buffers; the real count arrives with the flags below
   const int64_t n_max = accs.n_groups;
@@ -681,16 +689,21 @@ View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<C
   int64_t n_groups = n_max;
   if (n_max > 0 && !aggs.empty()) {
     // flags: [0] EvalErr, [1..n_aggs] NULL counts, [MAX_AGGS + 1] group count (copied from the device-side counter)
-    DBufP flags = ctx->alloc_zero(8 * (MAX_AGGS + 2));
+    DBufP flags = ctx->alloc_zero(8 * (MAX_AGGS + 2 + MAX_KEYS));
     dim3 grid((unsigned)grid_for(ctx, n_max, 256), (unsigned)aggs.size());
     LAUNCH(ctx, k_agg_finalize, grid, 256, 0, all, n_max, n_dev, (unsigned long long*)flags->ptr);
     if (n_dev)
       CUDA_CHECK(cudaMemcpyAsync((char*)flags->ptr + 8 * (MAX_AGGS + 1), n_dev, 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    unsigned long long h[MAX_AGGS + 2];
-    ctx->d2h_sync(h, flags->ptr, 8 * (MAX_AGGS + 2));
+    if (key_nulls && !keys.empty())
+      CUDA_CHECK(cudaMemcpyAsync((char*)flags->ptr + 8 * (MAX_AGGS + 2), key_nulls, 8 * keys.size(), cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+    unsigned long long h[MAX_AGGS + 2 + MAX_KEYS];
+    ctx->d2h_sync(h, flags->ptr, 8 * (MAX_AGGS + 2 + MAX_KEYS));
     if ((int)h[0]) throw_eval_error((int)h[0]);
     for (size_t i = 0; i < aggs.size(); ++i) cols[i]->null_count = (int64_t)h[1 + i];
     if (n_dev) n_groups = (int64_t)h[MAX_AGGS + 1];
+    if (key_cols && key_nulls)
+      for (size_t i = 0; i < keys.size(); ++i) (*key_cols)[i]->null_count = (int64_t)h[MAX_AGGS + 2 + i];
   } else if (n_dev) {
     n_groups = (int64_t)ctx->read_scalar(n_dev);
   }
@@ -700,14 +713,22 @@ View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<C
   if (grouped) {
     order->length = n_groups;
     first_idx->length = n_groups;
-    View firsts = apply_selection_view(ctx, input, first_idx);
+    View firsts;
+    if (!key_cols) firsts = apply_selection_view(ctx, input, first_idx);
     for (size_t i = 0; i < keys.size(); ++i) {
       Compiled& k = *keys[i];
       if (k.result_type != out_schema.fields[i].type)
         throw_arrow("column types must match schema types, expected " + out_schema.fields[i].type.str() + " but found " +
                     k.result_type.str() + " at column index " + std::to_string(i));
-      if (k.is_column_ref) out.cols.push_back(firsts.cols[k.column_ref]);
-      else out.cols.push_back({eval_to_column(ctx, k, firsts), nullptr});
+      if (key_cols) {
+        DColP kc = (*key_cols)[i];
+        if (!kc->validity || kc->null_count == 0) kc->validity.reset();
+        out.cols.push_back({kc, order});
+      } else if (k.is_column_ref) {
+        out.cols.push_back(firsts.cols[k.column_ref]);
+      } else {
+        out.cols.push_back({eval_to_column(ctx, k, firsts), nullptr});
+      }
     }
   }
   for (size_t i = 0; i < aggs.size(); ++i) {

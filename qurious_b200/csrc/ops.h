@@ -28,12 +28,25 @@ struct GroupAccs {
   // finish_aggregate reads the count together with its own flags in ONE device->host copy
   DBufP n_groups_dev;
 };
+// key_cols (optional): the group key VALUES as gid-indexed device columns (sharded execution: the first row of a
+// merged group may live on another shard, so keys travel with the state instead of being gathered from `input`);
+// key_nulls: device u64[n_keys] NULL counts of those columns, fetched together with the other flags.
 View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<Compiled>>& keys, std::vector<AggSpec>& aggs,
-                      const Schema& out_schema, GroupAccs& accs);
+                      const Schema& out_schema, GroupAccs& accs, std::vector<DColP>* key_cols = nullptr,
+                      const unsigned long long* key_nulls = nullptr);
+
+// An aggregate stopped right before finalisation: per-group accumulator state + what finish_aggregate needs.
+struct AggPending {
+  bool set = false;
+  View input;
+  std::vector<std::shared_ptr<Compiled>> keys;
+  std::vector<AggSpec> specs;
+  GroupAccs accs;
+};
 
 // HashAggregate / NoGroupingAggregate (keys.empty()).  SURVEY 8a a7,a8,a10-a13.
 View run_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<Compiled>>& keys, std::vector<AggSpec>& aggs,
-                   const Schema& out_schema);
+                   const Schema& out_schema, AggPending* defer = nullptr);
 
 struct JoinFilterSpec {
   std::shared_ptr<Compiled> expr;  // compiled against `schema`

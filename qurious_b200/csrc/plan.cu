@@ -208,6 +208,11 @@ View PlanNode::execute() {
       return out;
     }
     case PK_AGGREGATE: {
+      if (merged_override) {  // sharded execution: the merged states were finalised by shard_execute_merged
+        View v = *merged_override;
+        merged_override.reset();
+        return v;
+      }
       View fused;
       if (try_fused_scan_aggregate(*this, &fused)) return fused;
       View in = children[0]->execute();
@@ -223,7 +228,7 @@ View PlanNode::execute() {
         specs.push_back(s);
       }
       strategy = group_exprs.empty() ? "generic-no-grouping-aggregate" : "generic-hash-aggregate";
-      return run_aggregate(ctx, in, keys, specs, schema);
+      return run_aggregate(ctx, in, keys, specs, schema, defer);
     }
     case PK_HASH_JOIN: {
       View l = children[0]->execute();
@@ -638,6 +643,36 @@ int qgpu_plan_execute(qgpu_plan* p, struct ArrowArrayStream* out) {
     Timer tm(n.ctx);
     View v = n.execute();
     tm.stop(n);
+    std::vector<ArrowArray> batches;
+    if (v.num_batches > 0) {
+      std::vector<DColP> cols = materialize_view(n.ctx, v);
+      batches.resize(1);
+      export_batch(n.ctx, v.schema, cols, v.num_rows, &batches[0]);
+    }
+    make_stream(n.schema, std::move(batches), out);
+  });
+}
+
+int qgpu_plan_state_bytes(qgpu_plan* p, int32_t max_groups, int64_t* bytes) {
+  if (!p || !bytes) return QGPU_ERR_INTERNAL;
+  return guard(p->node->ctx, [&] { *bytes = shard_state_bytes(*p->node, max_groups); });
+}
+
+int qgpu_plan_partial_state(qgpu_plan* p, int64_t row_offset, int32_t max_groups, void* device_buf, int64_t cap_bytes) {
+  if (!p || !device_buf) return QGPU_ERR_INTERNAL;
+  PlanNode& n = *p->node;
+  return guard(n.ctx, [&] {
+    Timer tm(n.ctx);
+    shard_partial_state(n, row_offset, max_groups, device_buf, cap_bytes);
+    tm.stop(n);
+  });
+}
+
+int qgpu_plan_execute_merged(qgpu_plan* p, const void* gathered, int32_t n_states, int32_t max_groups, struct ArrowArrayStream* out) {
+  if (!p || !gathered || !out) return QGPU_ERR_INTERNAL;
+  PlanNode& n = *p->node;
+  return guard(n.ctx, [&] {
+    View v = shard_execute_merged(n, gathered, n_states, max_groups);
     std::vector<ArrowArray> batches;
     if (v.num_batches > 0) {
       std::vector<DColP> cols = materialize_view(n.ctx, v);

@@ -40,13 +40,23 @@ struct PlanNode {
   int64_t last_launches = 0;
   std::string strategy = "not-executed";
   std::string strategy_desc;
-  std::shared_ptr<void> fused_cache;  // fused.cu: analysis of this Aggregate <- (Filter)* <- Scan subtree
+  std::shared_ptr<void> fused_cache;
+  // sharded execution (shard.cu): stop before finalisation / resume from merged states
+  AggPending* defer = nullptr;
+  std::shared_ptr<View> merged_override;
+  std::shared_ptr<AggPending> shard_pending;  // kept between qgpu_plan_partial_state and qgpu_plan_execute_merged  // fused.cu: analysis of this Aggregate <- (Filter)* <- Scan subtree
 
   View execute();
 };
 
 // the (unfiltered) view of a Scan node's table: consolidates appended batches, applies the projection
 View scan_view(PlanNode& scan);
+
+// shard.cu
+PlanNode* find_aggregate_node(PlanNode& root);
+void shard_partial_state(PlanNode& root, int64_t row_offset, int32_t max_groups, void* out_buf, int64_t cap_bytes);
+int64_t shard_state_bytes(PlanNode& root, int32_t max_groups);
+View shard_execute_merged(PlanNode& root, const void* gathered, int32_t n_states, int32_t max_groups);
 
 // fused.cu: returns true and fills `out` when the aggregate over this input can run as one fused
 // scan+filter+aggregate pipeline kernel.

@@ -1,0 +1,447 @@
+// Sharded (multi-GPU) aggregates: exact merge of per-shard partial aggregate states.
+//
+// The reference is single-process (no exchange operator exists in qurious); this is the one distribution
+// strategy the B200 build adds for low/medium-cardinality aggregates over row-range shards:
+//   1. every process runs the SAME plan over its shard up to -- but not including -- the finalisation of
+//      HashAggregate / NoGroupingAggregate (aggregate/hash.rs:89-107, no_grouping.rs:48-61), i.e. it stops at
+//      the per-group accumulator state (SUM words, counts, MIN/MAX, first row);
+//   2. the state is packed into a fixed-size, self-describing block of 64-bit words in HBM
+//      (k_pack_records): header + one record per group = packed KEY VALUES (so records from different shards
+//      can be matched by value; no dictionary or statistics need to agree across shards), first row +
+//      shard row offset, and (lo, hi, count) per aggregate;
+//   3. the caller all-gathers the blocks (ncclAllGather -- qurious_b200/distributed.py uses torch.distributed);
+//   4. every process merges the gathered records (k_merge_records, one CTA, deterministic order: 128-bit
+//      integer adds, MIN/MAX, count sums) and runs the ordinary finalisation (finish_aggregate) on the merged
+//      state.  Integer/decimal results are bit-identical to a single-GPU run over the whole table; Float64
+//      sums differ only in reduction order (tolerance 1e-12, north_star).
+#include <algorithm>
+#include <cstring>
+
+#include "launch.h"
+#include "plan.h"
+
+namespace qgpu {
+
+#define SH_MAGIC 0x5147505553544154ULL  // "QGPUSTAT"
+#define SH_HDR 8                        // header words
+#define SH_MAX_MERGE 4096               // records one merge CTA handles
+#define SH_MAX_KEYS 8
+#define SH_MAX_AGGS 24
+
+// header: [0] magic [1] n_groups [2] n_keys [3] n_aggs [4] overflow (too many groups / key too long) [5] max_groups
+// record: n_keys x {tag, w1, w2} | first_row | n_aggs x {lo, hi, cnt}
+//   tag: 0 = NULL key, 1 = fixed-width value (w1 = lo, w2 = hi, sign-extended), 2 + len = Utf8 of len <= 16 bytes
+static inline int rec_words(int n_keys, int n_aggs) { return 3 * n_keys + 1 + 3 * n_aggs; }
+
+struct PackArgs {
+  int n_keys, n_aggs, max_groups, pad;
+  long long row_offset;
+  long long n_host;
+  const long long* n_dev;
+  const long long* first_row;
+  ColRef key[SH_MAX_KEYS];
+  const unsigned long long* lo[SH_MAX_AGGS];
+  const unsigned long long* hi[SH_MAX_AGGS];
+  const unsigned long long* cnt[SH_MAX_AGGS];
+};
+
+__global__ void __launch_bounds__(256) k_pack_records(const __grid_constant__ PackArgs a, unsigned long long* __restrict__ out) {
+  const long long n = a.n_dev ? *a.n_dev : a.n_host;
+  const int rw = 3 * a.n_keys + 1 + 3 * a.n_aggs;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    out[0] = SH_MAGIC;
+    out[1] = (unsigned long long)min(n, (long long)a.max_groups);
+    out[2] = (unsigned long long)a.n_keys;
+    out[3] = (unsigned long long)a.n_aggs;
+    if (n > a.max_groups) out[4] = 1;
+    out[5] = (unsigned long long)a.max_groups;
+  }
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n && g < a.max_groups; g += stride) {
+    unsigned long long* r = out + SH_HDR + g * rw;
+    const long long row = a.first_row[g];
+    for (int k = 0; k < a.n_keys; ++k) {
+      const Val v = load_col(a.key[k], row);
+      unsigned long long tag = 0, w1 = 0, w2 = 0;
+      if (v.valid) {
+        if (a.key[k].phys == PH_STR) {
+          const int len = (int)v.hi;
+          if (len > 16) {
+            out[4] = 1;
+          } else {
+            const unsigned char* s = (const unsigned char*)v.lo;
+            for (int i = 0; i < len; ++i) {
+              if (i < 8) w1 |= (unsigned long long)s[i] << (8 * i);
+              else w2 |= (unsigned long long)s[i] << (8 * (i - 8));
+            }
+            tag = 2 + (unsigned long long)len;
+          }
+        } else {
+          tag = 1;
+          w1 = v.lo;
+          w2 = v.hi;
+          if (a.key[k].phys != PH_I128 && a.key[k].phys != PH_D64) w2 = 0;
+        }
+      }
+      r[3 * k] = tag;
+      r[3 * k + 1] = w1;
+      r[3 * k + 2] = w2;
+    }
+    r[3 * a.n_keys] = (unsigned long long)(row + a.row_offset);
+    for (int i = 0; i < a.n_aggs; ++i) {
+      unsigned long long* q = r + 3 * a.n_keys + 1 + 3 * i;
+      q[0] = a.lo[i][g];
+      q[1] = a.hi[i][g];
+      q[2] = a.cnt[i][g];
+    }
+  }
+}
+
+struct KeyOut {
+  void* data;
+  int32_t* offsets;   // Utf8
+  uint32_t* validity;
+  int phys;
+  int pad;
+};
+struct MergeArgs {
+  int n_states, n_keys, n_aggs, max_groups;
+  long long block_words;
+  int kind[SH_MAX_AGGS];  // AccKind
+  unsigned long long* lo[SH_MAX_AGGS];
+  unsigned long long* hi[SH_MAX_AGGS];
+  unsigned long long* cnt[SH_MAX_AGGS];
+  KeyOut key[SH_MAX_KEYS];
+  long long* first_row;
+  long long* n_groups_out;
+  unsigned long long* key_nulls;  // [n_keys]
+  int* err;                       // 1: bad block, 2: overflow flagged by a shard, 3: too many records
+};
+
+__device__ __forceinline__ bool i128_less(unsigned long long alo, unsigned long long ahi, unsigned long long blo, unsigned long long bhi) {
+  return ((long long)ahi < (long long)bhi) || (ahi == bhi && alo < blo);
+}
+
+// One CTA merges every record of every shard.  Deterministic: a group's records are folded in (shard, slot) order.
+__global__ void __launch_bounds__(1024) k_merge_records(const __grid_constant__ MergeArgs a, const unsigned long long* __restrict__ in) {
+  __shared__ unsigned int pos[SH_MAX_MERGE];     // word offset of record i inside `in`
+  __shared__ unsigned short leader[SH_MAX_MERGE];
+  __shared__ unsigned short gid[SH_MAX_MERGE];
+  __shared__ int base[64];
+  __shared__ int total_s, bad_s, ng_s;
+  const int tid = threadIdx.x;
+  const int rw = 3 * a.n_keys + 1 + 3 * a.n_aggs;
+  if (tid == 0) {
+    int t = 0, bad = 0;
+    for (int s = 0; s < a.n_states; ++s) {
+      const unsigned long long* h = in + (long long)s * a.block_words;
+      base[s] = t;
+      if (h[0] != SH_MAGIC || (int)h[2] != a.n_keys || (int)h[3] != a.n_aggs) bad = 1;
+      else if (h[4]) bad = 2;
+      else t += (int)h[1];
+    }
+    if (!bad && t > SH_MAX_MERGE) bad = 3;
+    total_s = bad ? 0 : t;
+    bad_s = bad;
+    if (bad) *a.err = bad;
+  }
+  __syncthreads();
+  const int M = total_s;
+  for (int s = 0; s < a.n_states; ++s) {
+    const unsigned long long* h = in + (long long)s * a.block_words;
+    const int n = bad_s ? 0 : (int)h[1];
+    for (int g = tid; g < n; g += blockDim.x) pos[base[s] + g] = (unsigned int)((long long)s * a.block_words + SH_HDR + (long long)g * rw);
+  }
+  __syncthreads();
+  // leader of record i = first record with the same key words
+  for (int i = tid; i < M; i += blockDim.x) {
+    const unsigned long long* ri = in + pos[i];
+    int l = i;
+    for (int j = 0; j < i; ++j) {
+      const unsigned long long* rj = in + pos[j];
+      bool eq = true;
+      for (int w = 0; w < 3 * a.n_keys && eq; ++w) eq = ri[w] == rj[w];
+      if (eq) {
+        l = j;
+        break;
+      }
+    }
+    leader[i] = (unsigned short)l;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int ng = 0;
+    for (int i = 0; i < M; ++i)
+      if (leader[i] == i) gid[i] = (unsigned short)ng++;
+    ng_s = ng;
+    *a.n_groups_out = ng;
+  }
+  __syncthreads();
+  const int NG = ng_s;
+  // one thread per merged group folds that group's records in order
+  for (int i = tid; i < M; i += blockDim.x) {
+    if (leader[i] != i) continue;
+    const int t = gid[i];
+    long long first = INT64_MAX;
+    for (int ag = 0; ag < a.n_aggs; ++ag) {
+      const int kind = a.kind[ag];
+      unsigned long long lo = 0, hi = 0, cnt = 0;
+      bool have = false;
+      for (int j = i; j < M; ++j) {
+        if (leader[j] != i) continue;
+        const unsigned long long* q = in + pos[j] + 3 * a.n_keys + 1 + 3 * ag;
+        const unsigned long long l2 = q[0], h2 = q[1];
+        cnt += q[2];
+        if (!have) {
+          lo = l2;
+          hi = h2;
+          have = true;
+          continue;
+        }
+        switch (kind) {
+          case AK_COUNT: break;
+          case AK_SUM_I64: lo += l2; break;
+          case AK_SUM_DEC: {
+            const u128 s = (((u128)hi << 64) | lo) + (((u128)h2 << 64) | l2);
+            lo = (unsigned long long)s;
+            hi = (unsigned long long)(s >> 64);
+            break;
+          }
+          case AK_SUM_F64: lo = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)lo) + __longlong_as_double((long long)l2)); break;
+          case AK_MIN_I64: case AK_MIN_F64: if ((long long)l2 < (long long)lo) lo = l2; break;   // f64 travels as its total-order key
+          case AK_MAX_I64: case AK_MAX_F64: if ((long long)l2 > (long long)lo) lo = l2; break;
+          case AK_MIN_U64: if (l2 < lo) lo = l2; break;
+          case AK_MAX_U64: if (l2 > lo) lo = l2; break;
+          case AK_MIN_DEC: if (i128_less(l2, h2, lo, hi)) { lo = l2; hi = h2; } break;
+          case AK_MAX_DEC: if (i128_less(lo, hi, l2, h2)) { lo = l2; hi = h2; } break;
+          default: break;
+        }
+      }
+      a.lo[ag][t] = lo;
+      a.hi[ag][t] = hi;
+      a.cnt[ag][t] = cnt;
+    }
+    for (int j = i; j < M; ++j)
+      if (leader[j] == i) first = min(first, (long long)in[pos[j] + 3 * a.n_keys]);
+    a.first_row[t] = first;
+    // fixed-width key values
+    const unsigned long long* r = in + pos[i];
+    for (int k = 0; k < a.n_keys; ++k) {
+      const unsigned long long tag = r[3 * k], w1 = r[3 * k + 1], w2 = r[3 * k + 2];
+      const KeyOut& ko = a.key[k];
+      switch (ko.phys) {
+        case PH_I8: case PH_U8: ((uint8_t*)ko.data)[t] = (uint8_t)w1; break;
+        case PH_I16: case PH_U16: ((uint16_t*)ko.data)[t] = (uint16_t)w1; break;
+        case PH_I32: case PH_U32: ((uint32_t*)ko.data)[t] = (uint32_t)w1; break;
+        case PH_I64: case PH_U64: ((unsigned long long*)ko.data)[t] = w1; break;
+        case PH_I128: ((ulonglong2*)ko.data)[t] = make_ulonglong2(w1, w2); break;
+        default: break;  // PH_STR below
+      }
+      if (tag == 0) atomicAdd(&a.key_nulls[k], 1ull);
+    }
+  }
+  __syncthreads();
+  // validity words + Utf8 offsets/bytes (group count is small: serial per key column)
+  for (int k = tid; k < a.n_keys; k += blockDim.x) {
+    const KeyOut& ko = a.key[k];
+    for (int w = 0; w < (NG + 31) / 32; ++w) ko.validity[w] = 0;
+    int off = 0;
+    for (int i = 0; i < M; ++i) {
+      if (leader[i] != i) continue;
+      const int t = gid[i];
+      const unsigned long long* r = in + pos[i];
+      const unsigned long long tag = r[3 * k];
+      if (tag) ko.validity[t >> 5] |= 1u << (t & 31);
+      if (ko.phys == PH_STR) {
+        ko.offsets[t] = off;
+        const int len = tag >= 2 ? (int)(tag - 2) : 0;
+        for (int b = 0; b < len; ++b) {
+          const unsigned long long w = b < 8 ? r[3 * k + 1] : r[3 * k + 2];
+          ((char*)ko.data)[off + b] = (char)((w >> (8 * (b & 7))) & 0xff);
+        }
+        off += len;
+      }
+    }
+    if (ko.phys == PH_STR) ko.offsets[NG] = off;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+PlanNode* find_aggregate_node(PlanNode& root) {
+  PlanNode* n = &root;
+  while (n->kind == PK_PROJECTION || n->kind == PK_FILTER) n = n->children[0].get();
+  if (n->kind != PK_AGGREGATE) throw_internal("sharded execution needs a plan of the form (Projection|Filter)* <- Aggregate <- ...");
+  return n;
+}
+
+int64_t shard_state_bytes(PlanNode& root, int32_t max_groups) {
+  PlanNode* agg = find_aggregate_node(root);
+  if (max_groups < 1 || max_groups > SH_MAX_MERGE) throw_internal("max_groups must be in [1, 4096]");
+  return 8 * (int64_t)(SH_HDR + (int64_t)max_groups * rec_words((int)agg->group_exprs.size(), (int)agg->aggs.size()));
+}
+
+static Phys key_phys(const DType& t) {
+  switch (t.id) {
+    case QGPU_T_INT8: return PH_I8;
+    case QGPU_T_INT16: return PH_I16;
+    case QGPU_T_INT32: case QGPU_T_DATE32: return PH_I32;
+    case QGPU_T_INT64: case QGPU_T_DATE64: return PH_I64;
+    case QGPU_T_UINT8: return PH_U8;
+    case QGPU_T_UINT16: return PH_U16;
+    case QGPU_T_UINT32: return PH_U32;
+    case QGPU_T_UINT64: return PH_U64;
+    case QGPU_T_DECIMAL128: return PH_I128;
+    case QGPU_T_UTF8: return PH_STR;
+    default: throw_internal("unsupported group key type for sharded execution: " + t.str());
+  }
+}
+
+void shard_partial_state(PlanNode& root, int64_t row_offset, int32_t max_groups, void* out_buf, int64_t cap_bytes) {
+  PlanNode* agg = find_aggregate_node(root);
+  Ctx* ctx = agg->ctx;
+  const int nk = (int)agg->group_exprs.size(), na = (int)agg->aggs.size();
+  if (nk > SH_MAX_KEYS || na > SH_MAX_AGGS) throw_internal("too many keys / aggregates for sharded execution");
+  const int64_t need = shard_state_bytes(root, max_groups);
+  if (cap_bytes < need) throw_internal("state buffer too small: need " + std::to_string(need) + " bytes");
+  auto pend = std::make_shared<AggPending>();
+  agg->merged_override.reset();
+  agg->defer = pend.get();
+  try {
+    agg->execute();
+  } catch (...) {
+    agg->defer = nullptr;
+    throw;
+  }
+  agg->defer = nullptr;
+  agg->shard_pending = pend;
+  CUDA_CHECK(cudaMemsetAsync(out_buf, 0, (size_t)need, ctx->stream));
+  PackArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_keys = nk;
+  a.n_aggs = na;
+  a.max_groups = max_groups;
+  a.row_offset = row_offset;
+  if (!pend->set) {  // grouped aggregate over zero input batches (hash.rs:146-148): no groups
+    a.n_host = 0;
+    DBufP z = ctx->alloc_zero(8);
+    a.first_row = (const long long*)z->ptr;
+    LAUNCH(ctx, k_pack_records, 1, 256, 0, a, (unsigned long long*)out_buf);
+    return;
+  }
+  GroupAccs& accs = pend->accs;
+  a.n_host = accs.n_groups;
+  a.n_dev = accs.n_groups_dev ? (const long long*)accs.n_groups_dev->ptr : nullptr;
+  a.first_row = (const long long*)accs.first_row->ptr;
+  for (int k = 0; k < nk; ++k) {
+    Compiled& kc = *pend->keys[k];
+    if (!kc.is_column_ref) throw_internal("sharded execution supports plain column group keys only");
+    const LazyCol& lc = pend->input.cols[kc.column_ref];
+    if (!lc.base) throw_internal("group key column was not uploaded");
+    key_phys(kc.result_type);
+    ColRef& r = a.key[k];
+    const DCol& d = *lc.base;
+    r.phys = d.phys;
+    r.data = d.data ? d.data->ptr : nullptr;
+    r.offsets = d.offsets ? (const int32_t*)d.offsets->ptr : nullptr;
+    r.validity = d.validity ? (const uint32_t*)d.validity->ptr : nullptr;
+    r.idx = lc.idx ? lc.idx->ptr() : nullptr;
+  }
+  for (int i = 0; i < na; ++i) {
+    a.lo[i] = (const unsigned long long*)accs.lo[i]->ptr;
+    a.hi[i] = (const unsigned long long*)accs.hi[i]->ptr;
+    a.cnt[i] = (const unsigned long long*)accs.cnt[i]->ptr;
+  }
+  const int64_t n_bound = std::min<int64_t>(std::max<int64_t>(accs.n_groups, 1), max_groups);
+  LAUNCH(ctx, k_pack_records, grid_for(ctx, n_bound, 256), 256, 0, a, (unsigned long long*)out_buf);
+}
+
+View shard_execute_merged(PlanNode& root, const void* gathered, int32_t n_states, int32_t max_groups) {
+  PlanNode* agg = find_aggregate_node(root);
+  Ctx* ctx = agg->ctx;
+  std::shared_ptr<AggPending> pend = agg->shard_pending;
+  const int nk = (int)agg->group_exprs.size(), na = (int)agg->aggs.size();
+  if (n_states < 1 || n_states > 64) throw_internal("n_states must be in [1, 64]");
+  // plan-side descriptions (keys / specs) come from the local partial run; a shard whose input had zero batches
+  // compiles them against its own (empty) scan schema
+  std::vector<std::shared_ptr<Compiled>> keys;
+  std::vector<AggSpec> specs;
+  std::vector<int> kinds;
+  View local_input;
+  if (pend && pend->set) {
+    keys = pend->keys;
+    specs = pend->specs;
+    kinds = pend->accs.kind;
+    local_input = pend->input;
+  } else {
+    throw_internal("qgpu_plan_execute_merged: call qgpu_plan_partial_state on this plan first (and the local shard must have at "
+                   "least one batch)");
+  }
+  const int64_t m_max = std::min<int64_t>((int64_t)n_states * max_groups, SH_MAX_MERGE);
+  const bool grouped = nk > 0;
+  MergeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_states = n_states;
+  a.n_keys = nk;
+  a.n_aggs = na;
+  a.max_groups = max_groups;
+  a.block_words = SH_HDR + (long long)max_groups * rec_words(nk, na);
+  GroupAccs accs;
+  accs.n_groups = grouped ? m_max : 1;
+  accs.kind = kinds;
+  for (int i = 0; i < na; ++i) {
+    DBufP lo = ctx->alloc_zero((size_t)m_max * 8), hi = ctx->alloc_zero((size_t)m_max * 8), cnt = ctx->alloc_zero((size_t)m_max * 8);
+    accs.lo.push_back(lo);
+    accs.hi.push_back(hi);
+    accs.cnt.push_back(cnt);
+    a.kind[i] = kinds[i];
+    a.lo[i] = (unsigned long long*)lo->ptr;
+    a.hi[i] = (unsigned long long*)hi->ptr;
+    a.cnt[i] = (unsigned long long*)cnt->ptr;
+  }
+  accs.first_row = ctx->alloc_zero((size_t)m_max * 8);
+  a.first_row = (long long*)accs.first_row->ptr;
+  DBufP misc = ctx->alloc_zero(8 * (2 + SH_MAX_KEYS));  // [0] n_groups [1] err [2..] key NULL counts
+  a.n_groups_out = (long long*)misc->ptr;
+  a.err = (int*)((char*)misc->ptr + 8);
+  a.key_nulls = (unsigned long long*)((char*)misc->ptr + 16);
+  if (grouped) accs.n_groups_dev = misc;  // first word is the merged group count
+  std::vector<DColP> key_cols;
+  for (int k = 0; k < nk; ++k) {
+    auto c = std::make_shared<DCol>();
+    c->type = keys[k]->result_type;
+    c->phys = key_phys(c->type);
+    c->length = m_max;
+    c->validity = ctx->alloc_zero((size_t)((m_max + 31) / 32) * 4 + 4);
+    if (c->phys == PH_STR) {
+      c->data = ctx->alloc_zero((size_t)m_max * 16 + 16);
+      c->offsets = ctx->alloc_zero((size_t)(m_max + 1) * 4);
+      c->str_bytes = m_max * 16;
+    } else {
+      c->data = ctx->alloc_zero((size_t)m_max * std::max(phys_width(c->phys), 1) + 16);
+    }
+    c->null_count = 1;  // replaced by the real count inside finish_aggregate
+    a.key[k].data = c->data->ptr;
+    a.key[k].offsets = c->offsets ? (int32_t*)c->offsets->ptr : nullptr;
+    a.key[k].validity = (uint32_t*)c->validity->ptr;
+    a.key[k].phys = c->phys;
+    key_cols.push_back(c);
+  }
+  LAUNCH(ctx, k_merge_records, 1, 1024, 0, a, (const unsigned long long*)gathered);
+  if (!grouped) {
+    // n_groups_out is 1 when any shard contributed its single record; nothing else to do
+  }
+  View merged = finish_aggregate(ctx, local_input, keys, specs, agg->schema, accs, grouped ? &key_cols : nullptr, a.key_nulls);
+  const int err = ctx->read_scalar((const int*)a.err);
+  if (err == 2)
+    throw_internal("sharded aggregate: a shard produced more than max_groups groups (or a key longer than 16 bytes); use hash "
+                   "repartition for high-cardinality keys");
+  if (err) throw_internal("sharded aggregate: malformed state block (" + std::to_string(err) + ")");
+  for (auto& c : key_cols) c->length = merged.num_rows;
+  agg->merged_override = std::make_shared<View>(merged);
+  agg->strategy = "sharded-merge(" + std::to_string(n_states) + " states) <- " + agg->strategy;
+  return root.execute();
+}
+
+}  // namespace qgpu
