@@ -363,7 +363,17 @@ void* host_alloc(ArrayPriv* p, size_t bytes) {
 }
 }  // namespace
 
-static void export_column(Ctx* ctx, const DCol& c, int64_t n, ArrowArray* out) {
+namespace {
+struct PendingCopy {
+  void* dst;
+  const void* src;
+  size_t bytes;
+};
+}  // namespace
+
+// device->host copies are only RECORDED here; export_batch issues them (small results go through the pinned
+// scratch so that every copy is truly asynchronous and the whole batch costs one synchronisation)
+static void export_column(Ctx* ctx, const DCol& c, int64_t n, ArrowArray* out, std::vector<PendingCopy>& copies) {
   ArrayPriv* p = new ArrayPriv();
   memset(out, 0, sizeof(ArrowArray));
   out->private_data = p;
@@ -382,28 +392,28 @@ static void export_column(Ctx* ctx, const DCol& c, int64_t n, ArrowArray* out) {
     vb = host_alloc(p, vbytes);  // all-zero bitmap: every slot NULL
   } else if (c.validity && c.null_count > 0) {
     vb = host_alloc(p, vbytes + 4);
-    CUDA_CHECK(cudaMemcpyAsync(vb, c.validity->ptr, ((vbytes + 3) / 4) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    copies.push_back({vb, c.validity->ptr, ((vbytes + 3) / 4) * 4});
   }
   p->buffers.push_back(vb);
   const int w = arrow_width(c.type);
   if (c.type.id == QGPU_T_BOOL) {
     void* d = host_alloc(p, vbytes + 4);
     if (c.phys != PH_NULL && n > 0)
-      CUDA_CHECK(cudaMemcpyAsync(d, c.data->ptr, ((vbytes + 3) / 4) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      copies.push_back({d, c.data->ptr, ((vbytes + 3) / 4) * 4});
     p->buffers.push_back(d);
   } else if (c.type.id == QGPU_T_UTF8) {
     void* o = host_alloc(p, (size_t)(n + 1) * 4);
     void* d = host_alloc(p, (size_t)std::max<int64_t>(c.str_bytes, 1));
     if (c.phys != PH_NULL) {
-      CUDA_CHECK(cudaMemcpyAsync(o, c.offsets->ptr, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-      if (c.str_bytes > 0) CUDA_CHECK(cudaMemcpyAsync(d, c.data->ptr, (size_t)c.str_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      copies.push_back({o, c.offsets->ptr, (size_t)(n + 1) * 4});
+      if (c.str_bytes > 0) copies.push_back({d, c.data->ptr, (size_t)c.str_bytes});
     }
     p->buffers.push_back(o);
     p->buffers.push_back(d);
   } else {
     if (c.phys == PH_D64) throw_internal("export: narrowed decimal must be widened first");
     void* d = host_alloc(p, (size_t)n * w);
-    if (c.phys != PH_NULL && n > 0) CUDA_CHECK(cudaMemcpyAsync(d, c.data->ptr, (size_t)n * w, cudaMemcpyDeviceToHost, ctx->stream));
+    if (c.phys != PH_NULL && n > 0) copies.push_back({d, c.data->ptr, (size_t)n * w});
     p->buffers.push_back(d);
   }
   out->n_buffers = (int64_t)p->buffers.size();
@@ -429,8 +439,26 @@ void export_batch(Ctx* ctx, const Schema& schema, const std::vector<DColP>& cols
   out->n_children = (int64_t)cols.size();
   out->children = p->child_ptrs.data();
   try {
-    for (size_t i = 0; i < cols.size(); ++i) export_column(ctx, *cols[i], num_rows, &p->children[i]);
-    ctx->sync();
+    std::vector<PendingCopy> copies;
+    for (size_t i = 0; i < cols.size(); ++i) export_column(ctx, *cols[i], num_rows, &p->children[i], copies);
+    size_t total = 0;
+    for (auto& c : copies) total += ((c.bytes + 15) / 16) * 16;
+    if (total <= ctx->pinned_scratch_bytes) {
+      size_t off = 0;
+      for (auto& c : copies) {
+        CUDA_CHECK(cudaMemcpyAsync((char*)ctx->pinned_scratch + off, c.src, c.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        off += ((c.bytes + 15) / 16) * 16;
+      }
+      ctx->sync();
+      off = 0;
+      for (auto& c : copies) {
+        memcpy(c.dst, (char*)ctx->pinned_scratch + off, c.bytes);
+        off += ((c.bytes + 15) / 16) * 16;
+      }
+    } else {
+      for (auto& c : copies) CUDA_CHECK(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->sync();
+    }
   } catch (...) {
     release_array(out);
     throw;

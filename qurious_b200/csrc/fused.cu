@@ -40,7 +40,7 @@ constexpr int F_R = F_T / F_NT;
 constexpr int F_MAXC = 10, F_MAXP = 8, F_MAXK = 4, F_MAXA = 8, F_MAXF = 3;
 constexpr int F_SMEM_MAX = 232448 - 1024;  // 227 KB opt-in limit minus static slack
 enum { FK_SUM = 0, FK_MIN = 1, FK_MAX = 2, FK_SUMF = 3 };
-enum { FM_DENSE = 0, FM_HASH = 1 };
+enum { FM_DENSE = 0, FM_HASH = 1, FM_PROBE = 2 };
 #define F_EMPTY 0xffffffffffffffffULL
 
 struct FCol {
@@ -89,6 +89,14 @@ struct FParams {
   unsigned long long* t_keys;
   unsigned long long* n_groups;
   int* abort_flag;
+  // FM_PROBE: join table on the BUILD side (unique keys): slot = (tag32 << 32) | (build row + 1), 0 = empty;
+  // equality is verified against the immutable build key column; the accumulator slot of a probe row is its
+  // matching build row (accumulator stride = acc_stride)
+  const unsigned long long* jt_slots;
+  uint64_t jt_mask;
+  const void* bkey;
+  int32_t bkey_width, pad_probe;
+  int64_t acc_stride;
   FCol cols[F_MAXC];
   FPred pred[F_MAXP];
   FKey keys[F_MAXK];
@@ -116,9 +124,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   }
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+// streamed-once column tiles are tagged evict-first in L2 so that they do not push out the HBM-resident hash /
+// join tables that the same kernel probes at random
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                : "memory");
 }
 
@@ -315,6 +331,7 @@ struct GenericBody {
           slot[j] = F_EMPTY;
           if (!((pass >> j) & 1)) continue;
           const uint64_t c = code[j];
+          if (MODE == FM_PROBE) continue;  // resolved below (the first probes of all rows are issued together)
           if (c == F_EMPTY) {
             slot[j] = p.cap_mask + 1;
             continue;
@@ -341,7 +358,41 @@ struct GenericBody {
           }
           slot[j] = sl;
         }
-        const size_t stride = (size_t)p.cap_mask + 2;
+        if (MODE == FM_PROBE) {
+          // hash-join probe (hash_join.rs:70-107,177-216): the packed code IS the probe key value.  Most probe rows
+          // miss (Q3: ~1% match), so the cost is the latency of the first slot load: issue all F_R of them first.
+          uint64_t hh[F_R], sl[F_R];
+          unsigned long long cur[F_R];
+#pragma unroll
+          for (int j = 0; j < F_R; ++j) {
+            hh[j] = fmix64(code[j]);
+            sl[j] = hh[j] & p.jt_mask;
+            cur[j] = ((pass >> j) & 1) ? __ldg(&p.jt_slots[sl[j]]) : 0ull;
+          }
+#pragma unroll
+          for (int j = 0; j < F_R; ++j) {
+            const uint32_t tag = (uint32_t)(hh[j] >> 32);
+            unsigned long long c = cur[j];
+            uint64_t s2 = sl[j];
+            while (c != 0) {
+              if ((uint32_t)(c >> 32) == tag) {
+                const uint64_t row = (c & 0xffffffffull) - 1;
+                const int64_t bk = p.bkey_width == 8 ? __ldg((const long long*)p.bkey + row) : (int64_t)__ldg((const int*)p.bkey + row);
+                if (bk == (int64_t)code[j]) {
+                  slot[j] = row;
+                  break;
+                }
+              }
+              s2 = (s2 + 1) & p.jt_mask;
+              c = __ldg(&p.jt_slots[s2]);
+            }
+          }
+        }
+        const size_t stride = (size_t)p.acc_stride;
+        bool any_slot = false;
+#pragma unroll
+        for (int j = 0; j < F_R; ++j) any_slot |= slot[j] != F_EMPTY;
+        if (MODE == FM_PROBE && !__any_sync(0xffffffffu, any_slot)) return;  // nothing in this warp matched a build row
 #pragma unroll 1
         for (int k = 0; k < p.n_accs; ++k) {
           const FAcc& A = p.accs[k];
@@ -419,6 +470,7 @@ __device__ __forceinline__ void fused_main(const FParams& p) {
   const int64_t first_tile = blockIdx.x;
   const int64_t my_tiles = first_tile < p.n_tiles ? (p.n_tiles - first_tile + gridDim.x - 1) / gridDim.x : 0;
 
+  const uint64_t l2_policy = l2_evict_first_policy();
   auto issue = [&](int64_t i) {
     const int s = (int)(i % p.stages);
     const int64_t t = first_tile + i * gridDim.x;
@@ -432,7 +484,7 @@ __device__ __forceinline__ void fused_main(const FParams& p) {
 #pragma unroll 1
     for (int c = 0; c < p.n_cols; ++c) {
       const uint32_t bytes = ((uint32_t)(rows * p.cols[c].width) + 15u) & ~15u;
-      bulk_g2s(dst + p.cols[c].smem_off, p.cols[c].ptr + (size_t)row0 * p.cols[c].width, bytes, &full[s]);
+      bulk_g2s(dst + p.cols[c].smem_off, p.cols[c].ptr + (size_t)row0 * p.cols[c].width, bytes, &full[s], l2_policy);
     }
   };
   if (tid == 0)
@@ -518,8 +570,10 @@ __device__ __forceinline__ void fused_main(const FParams& p) {
 }
 
 
+// DENSE keeps one CTA per SM (its private tables fill shared memory); the table-probing modes run two CTAs per
+// SM (16 warps) to hide the latency of their random HBM/L2 accesses
 template <int MODE>
-__global__ void __launch_bounds__(F_NT, 1) k_fused_scan_agg(const __grid_constant__ FParams p) {
+__global__ void __launch_bounds__(F_NT, MODE == FM_DENSE ? 1 : 2) k_fused_scan_agg(const __grid_constant__ FParams p) {
   fused_main<MODE, GenericBody<MODE>>(p);
 }
 
@@ -1197,8 +1251,19 @@ struct FusedPlan {
 };
 }  // namespace
 
-static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& predicates, const View& v, FusedPlan& fp) {
+namespace {
+// probe-side analysis for the fused join-probe + aggregate pipeline: no group keys in the kernel (the group of a
+// probe row is its matching build row); aggregate arguments are given re-based onto the probe scan's schema
+struct ProbeOpts {
+  int probe_key_col = -1;
+  std::vector<std::unique_ptr<ExprNode>> agg_exprs;
+};
+}  // namespace
+
+static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& predicates, const View& v, FusedPlan& fp,
+                          const ProbeOpts* probe = nullptr) {
   Ctx* ctx = agg.ctx;
+  auto agg_expr = [&](size_t i) -> const ExprNode& { return probe ? *probe->agg_exprs[i] : *agg.aggs[i].expr; };
   if ((int)agg.aggs.size() > 24 || agg.aggs.empty() || (int)agg.group_exprs.size() > F_MAXK) return false;
   if (agg.schema.fields.size() != agg.group_exprs.size() + agg.aggs.size()) return false;
 
@@ -1217,11 +1282,13 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
   Analyzer A{ctx, v, {}, {}};
   try {
     // same validation (and the same errors) as the generic path
-    for (auto& e : agg.group_exprs) keys.push_back(compile_expr(*e, v.schema));
-    for (auto& a : agg.aggs) {
+    if (!probe)
+      for (auto& e : agg.group_exprs) keys.push_back(compile_expr(*e, v.schema));
+    for (size_t i = 0; i < agg.aggs.size(); ++i) {
+      const AggDesc& a = agg.aggs[i];
       AggSpec s;
       s.op = a.op;
-      s.arg = compile_expr(*a.expr, v.schema);
+      s.arg = compile_expr(agg_expr(i), v.schema);
       s.return_type = a.return_type;
       s.expr_type = a.expr_type;
       specs.push_back(s);
@@ -1323,6 +1390,14 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
       total_bits += bits;
     }
     if (total_bits > 64) return false;
+    if (probe) {  // the one kernel-side "key" is the probe join key: code = its value
+      const int slot = A.slot_for(probe->probe_key_col, false);
+      FKey& fk = P.keys[P.n_keys++];
+      fk.col = slot;
+      fk.base = 0;
+      fk.mult = 1;
+      dense_ok = false;
+    }
 
     // ---- accumulators ---------------------------------------------------------------------------------
     std::vector<std::string> acc_sig;
@@ -1337,7 +1412,7 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
           const LazyCol& lc = v.cols[s.arg->column_ref];
           if (!lc.base || lc.idx || lc.base->null_count != 0) return false;
         } else {
-          A.analyze(*agg.aggs[i].expr);  // arithmetic over non-NULL columns is never NULL
+          A.analyze(agg_expr(i));  // arithmetic over non-NULL columns is never NULL
         }
         continue;
       }
@@ -1355,7 +1430,7 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
         fa.f[0].b = 1;
         fa.coef = 1;
       } else {
-        Poly p = A.analyze(*agg.aggs[i].expr);
+        Poly p = A.analyze(agg_expr(i));
         if (p.fs.size() > F_MAXF) return false;
         fa.kind = (s.op == QGPU_AGG_MIN) ? FK_MIN : (s.op == QGPU_AGG_MAX ? FK_MAX : FK_SUM);
         fa.coef = (int64_t)p.coef;
@@ -1455,7 +1530,12 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
     for (i128 m : acc_maxabs)
       if (m * (i128)(tiles_per_cta * F_R + 1) >= LIM62) dense_ok = false;
   }
-  P.mode = dense_ok ? FM_DENSE : FM_HASH;
+  P.mode = probe ? FM_PROBE : (dense_ok ? FM_DENSE : FM_HASH);
+  if (P.mode == FM_PROBE) {
+    priv_bytes = 0;
+    for (i128 m : acc_maxabs)
+      if (m * (i128)n_rows >= LIM62) P.carry = 1;
+  }
   if (P.mode == FM_HASH) {
     priv_bytes = 0;
     // bit-packed code
@@ -1469,14 +1549,22 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
       if (m * (i128)n_rows >= LIM62) P.carry = 1;
   }
   for (int k = 0; k < P.n_keys; ++k) P.keys[k].pad = 0;
+  int ctas_per_sm = 1;
   int stages = (int)(((size_t)F_SMEM_MAX - 128 - priv_bytes) / stage_bytes);
   stages = std::min(stages, 4);
+  if (P.mode != FM_DENSE) {
+    const int s2 = (int)std::min<size_t>(((size_t)F_SMEM_MAX / 2 - 1024 - 128) / stage_bytes, 4);
+    if (s2 >= 2) {
+      stages = s2;
+      ctas_per_sm = 2;
+    }
+  }
   if (stages < 2) return false;
   P.stages = stages;
   P.priv_off = 128 + (uint32_t)stages * stage_bytes;
   P.dense_groups = (int)dense_groups;
   fp.smem_bytes = (size_t)P.priv_off + priv_bytes;
-  fp.grid = (int)std::min<int64_t>(P.n_tiles, grid_max);
+  fp.grid = (int)std::min<int64_t>(P.n_tiles, (int64_t)grid_max * ctas_per_sm);
   fp.total_bits = total_bits;
   fp.spec = getenv("QGPU_FUSED_GENERIC") ? nullptr : find_specialised(P);
   return true;
@@ -1551,6 +1639,7 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
       P.g_hi = g_hi ? (unsigned long long*)g_hi->ptr : nullptr;
       P.t_keys = (unsigned long long*)t_keys->ptr;
       P.cap_mask = (uint64_t)(cap - 1);
+      P.acc_stride = cap + 1;
       P.n_groups = (unsigned long long*)flags->ptr;
       P.abort_flag = (int*)((char*)flags->ptr + 8);
       LAUNCH(ctx, k_fused_scan_agg<FM_HASH>, grid, F_NT, smem_bytes, P);
@@ -1651,6 +1740,253 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
     return View();
   }
   return finish_aggregate(ctx, v, keys, specs, agg.schema, accs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused hash-join probe + aggregate (TPC-H Q3's J2 + HashAggregate):
+//   HashAggregate <- HashJoinExec(Inner, one integer key, no JoinFilter) <- [build: any sub-plan, probe: (Filter)* <- Scan]
+//   HashJoinExec::{build_hash_table, probe_hash_table}   qurious/src/physical/plan/join/hash_join.rs:148-216,354-385
+//   HashAggregate                                        qurious/src/physical/plan/aggregate/hash.rs:138-170
+// The build side runs through the ordinary operators (it is small); its join key is inserted into an
+// HBM-resident open-addressing table (slot = hash tag | build row, equality verified on the key column).
+// When the build keys are UNIQUE and every group key is the join key or a build-side column, the group of a
+// probe row is fully determined by its matching build row: the probe scan then streams through the same
+// TMA-staged pipeline as the scan-aggregate kernel and accumulates straight into per-build-row accumulators
+// (FM_PROBE) -- no join output, no second hash table.  Anything else returns false (generic operators run).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_join_build_unique(const void* __restrict__ bkey, int width, const uint32_t* __restrict__ validity,
+                                                           int64_t n, unsigned long long* __restrict__ slots, uint64_t mask,
+                                                           int* __restrict__ dup_flag) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride) {
+    if (validity && !((validity[row >> 5] >> (row & 31)) & 1u)) continue;  // NULL keys never match (hash_join.rs:177-216)
+    const int64_t key = width == 8 ? ((const long long*)bkey)[row] : (int64_t)((const int*)bkey)[row];
+    const uint64_t h = fmix64((uint64_t)key);
+    const uint32_t tag = (uint32_t)(h >> 32);
+    const unsigned long long mine = ((unsigned long long)tag << 32) | (unsigned long long)(row + 1);
+    uint64_t sl = h & mask;
+    while (true) {
+      unsigned long long cur = *(volatile unsigned long long*)&slots[sl];
+      if (cur == 0) {
+        cur = atomicCAS(&slots[sl], 0ull, mine);
+        if (cur == 0) break;
+      }
+      if ((uint32_t)(cur >> 32) == tag) {
+        const int64_t other = (int64_t)(cur & 0xffffffffull) - 1;
+        const int64_t ok = width == 8 ? ((const long long*)bkey)[other] : (int64_t)((const int*)bkey)[other];
+        if (ok == key) {  // duplicate build key: the fused path requires uniqueness
+          *dup_flag = 1;
+          break;
+        }
+      }
+      sl = (sl + 1) & mask;
+    }
+  }
+}
+
+__global__ void k_occupied_rows(const int64_t* __restrict__ flags, const int64_t* __restrict__ offs, int64_t n, int64_t* __restrict__ rows) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    if (flags[i]) rows[offs[i]] = i;
+}
+
+namespace {
+std::unique_ptr<ExprNode> clone_shift(const ExprNode& n, int shift, bool* ok) {
+  auto c = std::make_unique<ExprNode>();
+  c->kind = n.kind;
+  c->col_index = n.col_index;
+  c->lit_type = n.lit_type;
+  c->lit_null = n.lit_null;
+  c->lit_lo = n.lit_lo;
+  c->lit_hi = n.lit_hi;
+  c->lit_str = n.lit_str;
+  c->op = n.op;
+  c->cast_type = n.cast_type;
+  c->n_when = n.n_when;
+  if (n.kind == QGPU_IR_COLUMN) {
+    if (n.col_index < shift) *ok = false;  // references the build side
+    c->col_index = n.col_index - shift;
+  }
+  for (auto& ch : n.children) c->children.push_back(clone_shift(*ch, shift, ok));
+  return c;
+}
+bool int_like_key(const DCol& c) { return c.phys == PH_I64 || c.phys == PH_I32 || c.phys == PH_D64; }
+}  // namespace
+
+bool try_fused_join_aggregate(PlanNode& agg, View* out) {
+  Ctx* ctx = agg.ctx;
+  if (agg.defer || agg.group_exprs.empty() || agg.aggs.empty() || (int)agg.aggs.size() > 24) return false;
+  PlanNode* join = agg.children[0].get();
+  if (join->kind != PK_HASH_JOIN || join->join_type != QGPU_JOIN_INNER || join->left_on.size() != 1 || join->has_join_filter) return false;
+  const ExprNode& lk = *join->left_on[0];
+  const ExprNode& rk = *join->right_on[0];
+  if (lk.kind != QGPU_IR_COLUMN || rk.kind != QGPU_IR_COLUMN) return false;
+  // probe side: (Filter)* <- Scan
+  std::vector<const ExprNode*> predicates;
+  PlanNode* n = join->children[1].get();
+  while (n->kind == PK_FILTER) {
+    predicates.push_back(n->predicate.get());
+    n = n->children[0].get();
+  }
+  if (n->kind != PK_SCAN) return false;
+  if (n->predicate) predicates.push_back(n->predicate.get());
+  View pv = scan_view(*n);
+  if (pv.num_batches == 0 || pv.num_rows == 0 || pv.num_rows >= ((int64_t)1 << 40)) return false;
+  const int n_left = (int)join->children[0]->schema.fields.size();
+  const int n_right = (int)pv.cols.size();
+  if (rk.col_index < 0 || rk.col_index >= n_right || lk.col_index < 0 || lk.col_index >= n_left) return false;
+  // group keys: the join key (either side) or a build-side column
+  std::vector<int> key_build_col;  // build column that carries each group key's value
+  for (auto& g : agg.group_exprs) {
+    if (g->kind != QGPU_IR_COLUMN) return false;
+    if (g->col_index < n_left) key_build_col.push_back(g->col_index);
+    else if (g->col_index - n_left == rk.col_index) key_build_col.push_back(lk.col_index);
+    else return false;
+  }
+  ProbeOpts po;
+  po.probe_key_col = rk.col_index;
+  bool ok = true;
+  for (auto& a : agg.aggs) po.agg_exprs.push_back(clone_shift(*a.expr, n_left, &ok));
+  if (!ok) return false;
+
+  // ---- probe-side analysis (cached like the scan-aggregate one) -------------------------------------------
+  std::shared_ptr<FusedPlan> fp = std::static_pointer_cast<FusedPlan>(agg.fused_cache);
+  bool fresh = false;
+  if (fp) {
+    fresh = fp->n_rows == pv.num_rows && fp->n_batches == pv.num_batches && fp->col_ids.size() == pv.cols.size();
+    for (size_t i = 0; fresh && i < pv.cols.size(); ++i) fresh = fp->col_ids[i] == pv.cols[i].base.get() && !pv.cols[i].idx;
+  }
+  if (!fresh) {
+    fp = std::make_shared<FusedPlan>();
+    try {
+      fp->usable = analyze_fused(agg, predicates, pv, *fp, &po);
+    } catch (QError&) {
+      fp->usable = false;  // let the generic operators raise the error in their own order
+    }
+    fp->n_rows = pv.num_rows;
+    fp->n_batches = pv.num_batches;
+    for (auto& c : pv.cols) fp->col_ids.push_back(c.base.get());
+    agg.fused_cache = fp;
+  }
+  if (!fp->usable) return false;
+
+  // ---- build side: ordinary operators, then the join table ------------------------------------------------
+  View bv = join->children[0]->execute();
+  const int64_t nb = bv.num_rows;
+  if (nb >= 0xfffffff0LL) return false;
+  DColP bkey = nb > 0 ? materialize(ctx, bv.cols[lk.col_index], nb) : nullptr;
+  if (nb > 0 && !int_like_key(*bkey)) return false;
+  // the probe key must compare like the build key: same logical type (the generic join raises otherwise)
+  if (join->children[0]->schema.fields[lk.col_index].type != pv.schema.fields[rk.col_index].type) return false;
+  int64_t cap = 1024;
+  while (cap < 2 * nb) cap <<= 1;
+  DBufP slots = ctx->alloc_zero((size_t)cap * 8);
+  DBufP dup = ctx->alloc_zero(8);
+  if (nb > 0) {
+    LAUNCH(ctx, k_join_build_unique, grid_for(ctx, nb, 256), 256, 0, bkey->data->ptr, phys_width(bkey->phys),
+           bkey->validity ? (const uint32_t*)bkey->validity->ptr : nullptr, nb, (unsigned long long*)slots->ptr, (uint64_t)(cap - 1),
+           (int*)dup->ptr);
+    if (ctx->read_scalar((const int*)dup->ptr)) return false;  // duplicate build keys: generic join
+  }
+
+  // ---- probe + aggregate ---------------------------------------------------------------------------------------
+  FParams P = fp->P;
+  const int NA2 = P.n_accs + 2;
+  const int64_t n_slots = std::max<int64_t>(nb, 1);
+  FInit init;
+  for (int k = 0; k < NA2; ++k) {
+    if (k < P.n_accs) init.v[k] = P.accs[k].kind == FK_MIN ? INT64_MAX : (P.accs[k].kind == FK_MAX ? INT64_MIN : 0);
+    else init.v[k] = k == P.n_accs ? 0 : INT64_MAX;
+  }
+  DBufP g_lo = ctx->alloc((size_t)n_slots * NA2 * 8);
+  DBufP g_hi = P.carry ? ctx->alloc((size_t)n_slots * NA2 * 8) : nullptr;
+  DBufP flags = ctx->alloc_zero(16);
+  LAUNCH(ctx, k_fused_init, grid_for(ctx, n_slots * NA2, 256), 256, 0, (unsigned long long*)g_lo->ptr,
+         g_hi ? (unsigned long long*)g_hi->ptr : nullptr, n_slots, NA2, 0, init);
+  P.g_lo = (unsigned long long*)g_lo->ptr;
+  P.g_hi = g_hi ? (unsigned long long*)g_hi->ptr : nullptr;
+  P.n_groups = (unsigned long long*)flags->ptr;
+  P.abort_flag = (int*)((char*)flags->ptr + 8);
+  P.jt_slots = (const unsigned long long*)slots->ptr;
+  P.jt_mask = (uint64_t)(cap - 1);
+  P.bkey = nb > 0 ? bkey->data->ptr : slots->ptr;
+  P.bkey_width = nb > 0 ? phys_width(bkey->phys) : 8;
+  P.acc_stride = n_slots;
+  CUDA_CHECK(cudaFuncSetAttribute(k_fused_scan_agg<FM_PROBE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem_bytes));
+  LAUNCH(ctx, k_fused_scan_agg<FM_PROBE>, fp->grid, F_NT, fp->smem_bytes, P);
+
+  // ---- groups = build rows that were matched at least once -----------------------------------------------------
+  DBufP occ = ctx->alloc((size_t)n_slots * 8), offs = ctx->alloc((size_t)n_slots * 8);
+  LAUNCH(ctx, k_fused_occupied, grid_for(ctx, n_slots, 256), 256, 0, (const unsigned long long*)g_lo->ptr, n_slots,
+         (int64_t)P.n_accs * n_slots, (int64_t)1, (int64_t*)occ->ptr);
+  const int64_t n_groups = exclusive_scan_i64(ctx, (const int64_t*)occ->ptr, (int64_t*)offs->ptr, n_slots);
+  std::vector<AggSpec>& specs = fp->specs;
+  std::vector<int>& acc_of = fp->acc_of;
+  GroupAccs accs;
+  accs.n_groups = n_groups;
+  const int64_t ng_alloc = std::max<int64_t>(n_groups, 1);
+  DBufP cnt = ctx->alloc_zero((size_t)ng_alloc * 8), first = ctx->alloc_zero((size_t)ng_alloc * 8), zero = ctx->alloc_zero((size_t)ng_alloc * 8);
+  FExport ex;
+  memset(&ex, 0, sizeof(ex));
+  ex.n_aggs = (int)specs.size();
+  for (size_t i = 0; i < specs.size(); ++i) {
+    const int k = acc_of[i];
+    ex.acc_of[i] = k;
+    int ak = AK_COUNT;
+    if (k >= 0) {
+      const int fk = P.accs[k].kind;
+      ex.kind_of[i] = fk;
+      ex.wide[i] = (fk == FK_SUM && P.carry) ? 1 : 0;
+      const VClass vc = class_of(specs[i].arg->result_type);
+      if (fk == FK_SUMF) ak = AK_SUM_F64;
+      else if (fk == FK_SUM) ak = vc == VC_DEC ? AK_SUM_DEC : AK_SUM_I64;
+      else if (vc == VC_DEC) ak = fk == FK_MIN ? AK_MIN_DEC : AK_MAX_DEC;
+      else if (vc == VC_UINT) ak = fk == FK_MIN ? AK_MIN_U64 : AK_MAX_U64;
+      else ak = fk == FK_MIN ? AK_MIN_I64 : AK_MAX_I64;
+      DBufP lo = ctx->alloc_zero((size_t)ng_alloc * 8), hi = ctx->alloc_zero((size_t)ng_alloc * 8);
+      ex.out_lo[i] = (unsigned long long*)lo->ptr;
+      ex.out_hi[i] = (unsigned long long*)hi->ptr;
+      accs.lo.push_back(lo);
+      accs.hi.push_back(hi);
+    } else {
+      accs.lo.push_back(zero);
+      accs.hi.push_back(zero);
+    }
+    accs.kind.push_back(ak);
+    accs.cnt.push_back(cnt);
+  }
+  accs.first_row = first;
+  auto rows = std::make_shared<IdxVec>();
+  rows->length = n_groups;
+  rows->buf = ctx->alloc((size_t)ng_alloc * 8);
+  if (n_groups > 0) {
+    LAUNCH(ctx, k_fused_export, grid_for(ctx, n_slots, 256), 256, 0, (const unsigned long long*)g_lo->ptr,
+           g_hi ? (const unsigned long long*)g_hi->ptr : nullptr, n_slots, n_slots, (int64_t)1, P.n_accs, (const int64_t*)occ->ptr,
+           (const int64_t*)offs->ptr, ex, (unsigned long long*)cnt->ptr, (long long*)first->ptr);
+    LAUNCH(ctx, k_occupied_rows, grid_for(ctx, n_slots, 256), 256, 0, (const int64_t*)occ->ptr, (const int64_t*)offs->ptr, n_slots,
+           (int64_t*)rows->buf->ptr);
+  }
+  // key values travel with the group (gid-indexed): the build columns at the matched build rows
+  std::vector<std::shared_ptr<Compiled>> keys;
+  Schema js = join->schema;
+  for (auto& g : agg.group_exprs) keys.push_back(compile_expr(*g, js));
+  std::vector<DColP> key_cols;
+  std::vector<std::pair<IdxP, IdxP>> cache;
+  for (size_t i = 0; i < keys.size(); ++i) {
+    check_hash_key_type(keys[i]->result_type);
+    LazyCol lc = apply_selection(ctx, bv.cols[key_build_col[i]], rows, &cache);
+    DColP kc = materialize(ctx, lc, n_groups);
+    if (kc->phys == PH_D64) kc = materialize_arrow(ctx, {kc, nullptr}, n_groups);
+    key_cols.push_back(kc);
+  }
+  agg.strategy = "fused_join_probe_agg[unique-build " + std::to_string(nb) + " rows, " + std::to_string(P.n_cols) + " probe cols, " +
+                 std::to_string(P.n_pred) + " range preds, " + std::to_string(P.n_accs) + " accs, " + std::to_string(P.stages) +
+                 " TMA stages]";
+  join->strategy = "fused-into-aggregate";
+  View dummy;
+  dummy.schema = js;
+  *out = finish_aggregate(ctx, dummy, keys, specs, agg.schema, accs, &key_cols, nullptr);
+  return true;
 }
 
 bool try_fused_scan_aggregate(PlanNode& agg, View* out) {

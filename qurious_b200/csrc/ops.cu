@@ -689,16 +689,17 @@ View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<C
   int64_t n_groups = n_max;
   if (n_max > 0 && !aggs.empty()) {
     // flags: [0] EvalErr, [1..n_aggs] NULL counts, [MAX_AGGS + 1] group count (copied from the device-side counter)
-    DBufP flags = ctx->alloc_zero(8 * (MAX_AGGS + 2 + MAX_KEYS));
+    DBufP flags = ctx->alloc_zero(8 * (MAX_AGGS + 3 + MAX_KEYS));
     dim3 grid((unsigned)grid_for(ctx, n_max, 256), (unsigned)aggs.size());
     LAUNCH(ctx, k_agg_finalize, grid, 256, 0, all, n_max, n_dev, (unsigned long long*)flags->ptr);
     if (n_dev)
       CUDA_CHECK(cudaMemcpyAsync((char*)flags->ptr + 8 * (MAX_AGGS + 1), n_dev, 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    if (key_nulls && !keys.empty())
-      CUDA_CHECK(cudaMemcpyAsync((char*)flags->ptr + 8 * (MAX_AGGS + 2), key_nulls, 8 * keys.size(), cudaMemcpyDeviceToDevice,
-                                 ctx->stream));
-    unsigned long long h[MAX_AGGS + 2 + MAX_KEYS];
-    ctx->d2h_sync(h, flags->ptr, 8 * (MAX_AGGS + 2 + MAX_KEYS));
+    if (key_nulls)
+      CUDA_CHECK(cudaMemcpyAsync((char*)flags->ptr + 8 * (MAX_AGGS + 2), key_nulls, 8 * (keys.size() + 1), cudaMemcpyDeviceToDevice,
+                                 ctx->stream));  // + one caller-defined word (shard.cu: merge error code)
+    unsigned long long h[MAX_AGGS + 3 + MAX_KEYS];
+    ctx->d2h_sync(h, flags->ptr, 8 * (MAX_AGGS + 3 + MAX_KEYS));
+    if (key_nulls) accs.side_word = h[MAX_AGGS + 2 + keys.size()];
     if ((int)h[0]) throw_eval_error((int)h[0]);
     for (size_t i = 0; i < aggs.size(); ++i) cols[i]->null_count = (int64_t)h[1 + i];
     if (n_dev) n_groups = (int64_t)h[MAX_AGGS + 1];

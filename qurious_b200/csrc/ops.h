@@ -27,6 +27,7 @@ struct GroupAccs {
   // optional: the actual group count is still on the device (int64); n_groups is then an upper bound and
   // finish_aggregate reads the count together with its own flags in ONE device->host copy
   DBufP n_groups_dev;
+  unsigned long long side_word = 0;  // out: the word following the key NULL counts (see finish_aggregate)
 };
 // key_cols (optional): the group key VALUES as gid-indexed device columns (sharded execution: the first row of a
 // merged group may live on another shard, so keys travel with the state instead of being gathered from `input`);

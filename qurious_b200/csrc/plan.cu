@@ -215,6 +215,7 @@ View PlanNode::execute() {
       }
       View fused;
       if (try_fused_scan_aggregate(*this, &fused)) return fused;
+      if (try_fused_join_aggregate(*this, &fused)) return fused;
       View in = children[0]->execute();
       std::vector<std::shared_ptr<Compiled>> keys;
       for (auto& e : group_exprs) keys.push_back(compile_expr(*e, in.schema));

@@ -61,6 +61,8 @@ View shard_execute_merged(PlanNode& root, const void* gathered, int32_t n_states
 // fused.cu: returns true and fills `out` when the aggregate over this input can run as one fused
 // scan+filter+aggregate pipeline kernel.
 bool try_fused_scan_aggregate(PlanNode& agg, View* out);
+// fused.cu: Aggregate <- HashJoin(Inner, unique build keys) <- [build plan, probe scan]: probe + aggregate in one kernel
+bool try_fused_join_aggregate(PlanNode& agg, View* out);
 
 }  // namespace qgpu
 

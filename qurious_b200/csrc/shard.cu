@@ -402,10 +402,12 @@ View shard_execute_merged(PlanNode& root, const void* gathered, int32_t n_states
   }
   accs.first_row = ctx->alloc_zero((size_t)m_max * 8);
   a.first_row = (long long*)accs.first_row->ptr;
-  DBufP misc = ctx->alloc_zero(8 * (2 + SH_MAX_KEYS));  // [0] n_groups [1] err [2..] key NULL counts
+  // [0] n_groups, [1 .. 1+nk) key NULL counts, [1+nk] error code: the last nk+1 words travel to the host together
+  // with finish_aggregate's own flags (one synchronisation for the whole merge)
+  DBufP misc = ctx->alloc_zero(8 * (3 + SH_MAX_KEYS));
   a.n_groups_out = (long long*)misc->ptr;
-  a.err = (int*)((char*)misc->ptr + 8);
-  a.key_nulls = (unsigned long long*)((char*)misc->ptr + 16);
+  a.key_nulls = (unsigned long long*)((char*)misc->ptr + 8);
+  a.err = (int*)((char*)misc->ptr + 8 + 8 * nk);
   if (grouped) accs.n_groups_dev = misc;  // first word is the merged group count
   std::vector<DColP> key_cols;
   for (int k = 0; k < nk; ++k) {
@@ -433,7 +435,7 @@ View shard_execute_merged(PlanNode& root, const void* gathered, int32_t n_states
     // n_groups_out is 1 when any shard contributed its single record; nothing else to do
   }
   View merged = finish_aggregate(ctx, local_input, keys, specs, agg->schema, accs, grouped ? &key_cols : nullptr, a.key_nulls);
-  const int err = ctx->read_scalar((const int*)a.err);
+  const int err = (int)accs.side_word;
   if (err == 2)
     throw_internal("sharded aggregate: a shard produced more than max_groups groups (or a key longer than 16 bytes); use hash "
                    "repartition for high-cardinality keys");

@@ -177,3 +177,38 @@ def test_shapes_the_fused_kernel_must_refuse(gpu_ctx):
                          [bx(C(t, "k"), "Add", lit(1))], [CountAggregateExpr(lit(1))])
     s = run_both(plan, gpu_ctx)
     assert "generic" in s, s
+
+
+@pytest.mark.parametrize("batch_rows", [1024, None])
+def test_q3_uses_the_fused_join_probe_aggregate(gpu_ctx, batch_rows):
+    db = tpch.generate(0.02, batch_rows=batch_rows)
+    plan = tpch.q3_plan(db)
+    got, ref = plan.execute(gpu_ctx), qref.execute(plan)
+    assert "fused_join_probe_agg[unique-build" in plan.last_strategy(), plan.last_strategy()
+    assert got[0].schema.types == ref[0].schema.types
+    # same rows AND the same (first-occurrence) order as the generic operators / the oracle
+    check_rows("q3", rows_of(got), rows_of(ref), ordered=True)
+
+
+def test_join_aggregate_falls_back_on_duplicate_build_keys(gpu_ctx):
+    from qurious_b200.datatypes import JoinType
+    from qurious_b200.physical.plan import HashJoinExec
+    rng = np.random.default_rng(4)
+    nb, n_probe = 500, 20000
+    bs = pa.schema([("bk", pa.int64()), ("tag", pa.int64())])
+    ps = pa.schema([("pk", pa.int64()), ("v", pa.int64())])
+    for dup in (False, True):
+        bk = np.arange(nb) * 3 if not dup else rng.integers(0, 200, nb) * 3
+        build = MemoryTable.try_new(bs, [pa.record_batch([pa.array(bk), pa.array(rng.integers(0, 9, nb))], schema=bs)])
+        probe = MemoryTable.try_new(ps, [pa.record_batch([pa.array(rng.integers(0, 3 * nb, n_probe)),
+                                                          pa.array(rng.integers(-1000, 1000, n_probe))], schema=ps)])
+        j = HashJoinExec.try_new(Scan(bs, build, None, None), Scan(ps, probe, None, bx(Column("v", 1), "GtEq", lit(-500))),
+                                 JoinType.Inner, [(Column("bk", 0), Column("pk", 0))], None)
+        out = pa.schema([("pk", pa.int64()), ("tag", pa.int64()), ("s", pa.int64()), ("c", pa.int64()), ("mn", pa.int64())])
+        keys = [Column("pk", 2), Column("tag", 1)] if not dup else [Column("pk", 2)]
+        if dup:
+            out = pa.schema([("pk", pa.int64()), ("s", pa.int64()), ("c", pa.int64()), ("mn", pa.int64())])
+        plan = HashAggregate(out, j, keys, [SumAggregateExpr(Column("v", 3), pa.int64()), CountAggregateExpr(lit(1)),
+                                            MinAggregateExpr(Column("v", 3), pa.int64())])
+        s = run_both(plan, gpu_ctx, ordered=True)
+        assert ("fused_join_probe_agg" in s) == (not dup), s
