@@ -40,7 +40,7 @@ constexpr int F_R = F_T / F_NT;
 constexpr int F_MAXC = 10, F_MAXP = 8, F_MAXK = 4, F_MAXA = 8, F_MAXF = 3;
 constexpr int F_SMEM_MAX = 232448 - 1024;  // 227 KB opt-in limit minus static slack
 enum { FK_SUM = 0, FK_MIN = 1, FK_MAX = 2, FK_SUMF = 3 };
-enum { FM_DENSE = 0, FM_HASH = 1, FM_PROBE = 2 };
+enum { FM_DENSE = 0, FM_HASH = 1, FM_PROBE = 2, FM_EMIT = 3 };
 #define F_EMPTY 0xffffffffffffffffULL
 
 struct FCol {
@@ -331,7 +331,7 @@ struct GenericBody {
           slot[j] = F_EMPTY;
           if (!((pass >> j) & 1)) continue;
           const uint64_t c = code[j];
-          if (MODE == FM_PROBE) continue;  // resolved below (the first probes of all rows are issued together)
+          if (MODE == FM_PROBE || MODE == FM_EMIT) continue;  // resolved below (the first probes of all rows are issued together)
           if (c == F_EMPTY) {
             slot[j] = p.cap_mask + 1;
             continue;
@@ -358,7 +358,7 @@ struct GenericBody {
           }
           slot[j] = sl;
         }
-        if (MODE == FM_PROBE) {
+        if (MODE == FM_PROBE || MODE == FM_EMIT) {
           // hash-join probe (hash_join.rs:70-107,177-216): the packed code IS the probe key value.  Most probe rows
           // miss (Q3: ~1% match), so the cost is the latency of the first slot load: issue all F_R of them first.
           uint64_t hh[F_R], sl[F_R];
@@ -387,6 +387,31 @@ struct GenericBody {
               c = __ldg(&p.jt_slots[s2]);
             }
           }
+        }
+        if (MODE == FM_EMIT) {
+          // order-free join output: (build row, probe row) pairs appended with one atomic per warp and row slot
+          const unsigned lane = threadIdx.x & 31;
+          unsigned m[F_R];
+          unsigned total = 0;
+#pragma unroll
+          for (int j = 0; j < F_R; ++j) {
+            m[j] = __ballot_sync(0xffffffffu, slot[j] != F_EMPTY);
+            total += __popc(m[j]);
+          }
+          if (total == 0) return;
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(p.n_groups, (unsigned long long)total);  // ONE atomic per warp and tile pass
+          base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+          for (int j = 0; j < F_R; ++j) {
+            if (slot[j] != F_EMPTY) {
+              const unsigned long long pos = base + __popc(m[j] & ((1u << lane) - 1u));
+              p.g_lo[pos] = slot[j];
+              p.g_hi[pos] = (unsigned long long)(row0 + j * F_NT + tid);
+            }
+            base += __popc(m[j]);
+          }
+          return;
         }
         const size_t stride = (size_t)p.acc_stride;
         bool any_slot = false;
@@ -1255,6 +1280,7 @@ namespace {
 // probe-side analysis for the fused join-probe + aggregate pipeline: no group keys in the kernel (the group of a
 // probe row is its matching build row); aggregate arguments are given re-based onto the probe scan's schema
 struct ProbeOpts {
+  bool emit = false;  // join output pairs instead of aggregation: no aggregate list
   int probe_key_col = -1;
   std::vector<std::unique_ptr<ExprNode>> agg_exprs;
 };
@@ -1264,8 +1290,11 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
                           const ProbeOpts* probe = nullptr) {
   Ctx* ctx = agg.ctx;
   auto agg_expr = [&](size_t i) -> const ExprNode& { return probe ? *probe->agg_exprs[i] : *agg.aggs[i].expr; };
-  if ((int)agg.aggs.size() > 24 || agg.aggs.empty() || (int)agg.group_exprs.size() > F_MAXK) return false;
-  if (agg.schema.fields.size() != agg.group_exprs.size() + agg.aggs.size()) return false;
+  const bool emit = probe && probe->emit;
+  if (!emit) {
+    if ((int)agg.aggs.size() > 24 || agg.aggs.empty() || (int)agg.group_exprs.size() > F_MAXK) return false;
+    if (agg.schema.fields.size() != agg.group_exprs.size() + agg.aggs.size()) return false;
+  }
 
   FParams& P = fp.P;
   memset(&P, 0, sizeof(P));
@@ -1530,7 +1559,7 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
     for (i128 m : acc_maxabs)
       if (m * (i128)(tiles_per_cta * F_R + 1) >= LIM62) dense_ok = false;
   }
-  P.mode = probe ? FM_PROBE : (dense_ok ? FM_DENSE : FM_HASH);
+  P.mode = probe ? (emit ? FM_EMIT : FM_PROBE) : (dense_ok ? FM_DENSE : FM_HASH);
   if (P.mode == FM_PROBE) {
     priv_bytes = 0;
     for (i128 m : acc_maxabs)
@@ -1813,6 +1842,106 @@ std::unique_ptr<ExprNode> clone_shift(const ExprNode& n, int shift, bool* ok) {
 bool int_like_key(const DCol& c) { return c.phys == PH_I64 || c.phys == PH_I32 || c.phys == PH_D64; }
 }  // namespace
 
+// Order-free Inner join used INSIDE a fused pipeline whose consumer does not depend on row order (the build
+// side of try_fused_join_aggregate): HashJoin(Inner, one integer key, no JoinFilter, unique build keys) with a
+// (Filter)* <- Scan probe side.  The probe scan streams through the TMA pipeline (FM_EMIT) and appends
+// (build row, probe row) pairs with warp-aggregated atomics; the result is a View of index vectors (late
+// materialisation), like the generic join's -- only the row ORDER differs, which is why this path is never used
+// for a join whose output is returned to the caller (hash_join.rs:474-512 pins that order).
+static bool fused_unordered_join(PlanNode& join, View* out) {
+  Ctx* ctx = join.ctx;
+  if (join.kind != PK_HASH_JOIN || join.join_type != QGPU_JOIN_INNER || join.left_on.size() != 1 || join.has_join_filter) return false;
+  const ExprNode& lk = *join.left_on[0];
+  const ExprNode& rk = *join.right_on[0];
+  if (lk.kind != QGPU_IR_COLUMN || rk.kind != QGPU_IR_COLUMN) return false;
+  std::vector<const ExprNode*> predicates;
+  PlanNode* n = join.children[1].get();
+  while (n->kind == PK_FILTER) {
+    predicates.push_back(n->predicate.get());
+    n = n->children[0].get();
+  }
+  if (n->kind != PK_SCAN) return false;
+  if (n->predicate) predicates.push_back(n->predicate.get());
+  View pv = scan_view(*n);
+  if (pv.num_batches == 0 || pv.num_rows == 0 || pv.num_rows >= ((int64_t)1 << 40)) return false;
+  const int n_left = (int)join.children[0]->schema.fields.size();
+  if (rk.col_index < 0 || rk.col_index >= (int)pv.cols.size() || lk.col_index < 0 || lk.col_index >= n_left) return false;
+  if (join.children[0]->schema.fields[lk.col_index].type != pv.schema.fields[rk.col_index].type) return false;
+  ProbeOpts po;
+  po.emit = true;
+  po.probe_key_col = rk.col_index;
+  std::shared_ptr<FusedPlan> fp = std::static_pointer_cast<FusedPlan>(join.fused_cache);
+  bool fresh = false;
+  if (fp) {
+    fresh = fp->n_rows == pv.num_rows && fp->n_batches == pv.num_batches && fp->col_ids.size() == pv.cols.size();
+    for (size_t i = 0; fresh && i < pv.cols.size(); ++i) fresh = fp->col_ids[i] == pv.cols[i].base.get() && !pv.cols[i].idx;
+  }
+  if (!fresh) {
+    fp = std::make_shared<FusedPlan>();
+    PlanNode shell;  // analyze_fused only needs the context in emit mode
+    shell.ctx = ctx;
+    try {
+      fp->usable = analyze_fused(shell, predicates, pv, *fp, &po);
+    } catch (QError&) {
+      fp->usable = false;
+    }
+    fp->n_rows = pv.num_rows;
+    fp->n_batches = pv.num_batches;
+    for (auto& c : pv.cols) fp->col_ids.push_back(c.base.get());
+    join.fused_cache = fp;
+  }
+  if (!fp->usable) return false;
+  // build side (recursively order-free when it is itself such a join)
+  View bv;
+  if (!fused_unordered_join(*join.children[0], &bv)) bv = join.children[0]->execute();
+  const int64_t nb = bv.num_rows;
+  if (nb >= 0xfffffff0LL) return false;
+  DColP bkey = nb > 0 ? materialize(ctx, bv.cols[lk.col_index], nb) : nullptr;
+  if (nb > 0 && !int_like_key(*bkey)) return false;
+  int64_t cap = 1024;
+  while (cap < 2 * nb) cap <<= 1;
+  DBufP slots = ctx->alloc_zero((size_t)cap * 8);
+  DBufP dup = ctx->alloc_zero(8);
+  if (nb > 0) {
+    LAUNCH(ctx, k_join_build_unique, grid_for(ctx, nb, 256), 256, 0, bkey->data->ptr, phys_width(bkey->phys),
+           bkey->validity ? (const uint32_t*)bkey->validity->ptr : nullptr, nb, (unsigned long long*)slots->ptr, (uint64_t)(cap - 1),
+           (int*)dup->ptr);
+    if (ctx->read_scalar((const int*)dup->ptr)) return false;
+  }
+  ctx->trace("  emit-join: build side + table");
+  FParams P = fp->P;
+  auto b_idx = std::make_shared<IdxVec>();
+  auto p_idx = std::make_shared<IdxVec>();
+  b_idx->buf = ctx->alloc((size_t)pv.num_rows * 8);
+  p_idx->buf = ctx->alloc((size_t)pv.num_rows * 8);
+  DBufP flags = ctx->alloc_zero(16);
+  P.g_lo = (unsigned long long*)b_idx->buf->ptr;
+  P.g_hi = (unsigned long long*)p_idx->buf->ptr;
+  P.n_groups = (unsigned long long*)flags->ptr;
+  P.abort_flag = (int*)((char*)flags->ptr + 8);
+  P.jt_slots = (const unsigned long long*)slots->ptr;
+  P.jt_mask = (uint64_t)(cap - 1);
+  P.bkey = nb > 0 ? bkey->data->ptr : slots->ptr;
+  P.bkey_width = nb > 0 ? phys_width(bkey->phys) : 8;
+  CUDA_CHECK(cudaFuncSetAttribute(k_fused_scan_agg<FM_EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem_bytes));
+  LAUNCH(ctx, k_fused_scan_agg<FM_EMIT>, fp->grid, F_NT, fp->smem_bytes, P);
+  const int64_t n_out = (int64_t)ctx->read_scalar((const unsigned long long*)flags->ptr);
+  ctx->trace("  emit-join: probe kernel");
+  b_idx->length = p_idx->length = n_out;
+  View v;
+  v.schema = join.schema;
+  v.num_rows = n_out;
+  v.num_batches = n_out > 0 ? 1 : 0;
+  std::vector<std::pair<IdxP, IdxP>> cb, cp;
+  for (const LazyCol& c : bv.cols) v.cols.push_back(apply_selection(ctx, c, b_idx, &cb));
+  for (const LazyCol& c : pv.cols) v.cols.push_back(apply_selection(ctx, c, p_idx, &cp));
+  ctx->trace("  emit-join: output view");
+  if (v.cols.size() != join.schema.fields.size()) return false;
+  join.strategy = "fused_join_probe_emit[unordered, unique-build " + std::to_string(nb) + " rows -> " + std::to_string(n_out) + " pairs]";
+  *out = v;
+  return true;
+}
+
 bool try_fused_join_aggregate(PlanNode& agg, View* out) {
   Ctx* ctx = agg.ctx;
   if (agg.defer || agg.group_exprs.empty() || agg.aggs.empty() || (int)agg.aggs.size() > 24) return false;
@@ -1871,7 +2000,9 @@ bool try_fused_join_aggregate(PlanNode& agg, View* out) {
   if (!fp->usable) return false;
 
   // ---- build side: ordinary operators, then the join table ------------------------------------------------
-  View bv = join->children[0]->execute();
+  ctx->trace(nullptr);
+  View bv;
+  if (!fused_unordered_join(*join->children[0], &bv)) bv = join->children[0]->execute();
   const int64_t nb = bv.num_rows;
   if (nb >= 0xfffffff0LL) return false;
   DColP bkey = nb > 0 ? materialize(ctx, bv.cols[lk.col_index], nb) : nullptr;
@@ -1889,6 +2020,7 @@ bool try_fused_join_aggregate(PlanNode& agg, View* out) {
     if (ctx->read_scalar((const int*)dup->ptr)) return false;  // duplicate build keys: generic join
   }
 
+  ctx->trace("join-agg: build side + join table");
   // ---- probe + aggregate ---------------------------------------------------------------------------------------
   FParams P = fp->P;
   const int NA2 = P.n_accs + 2;
@@ -1915,6 +2047,7 @@ bool try_fused_join_aggregate(PlanNode& agg, View* out) {
   CUDA_CHECK(cudaFuncSetAttribute(k_fused_scan_agg<FM_PROBE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem_bytes));
   LAUNCH(ctx, k_fused_scan_agg<FM_PROBE>, fp->grid, F_NT, fp->smem_bytes, P);
 
+  ctx->trace("join-agg: probe+aggregate kernel");
   // ---- groups = build rows that were matched at least once -----------------------------------------------------
   DBufP occ = ctx->alloc((size_t)n_slots * 8), offs = ctx->alloc((size_t)n_slots * 8);
   LAUNCH(ctx, k_fused_occupied, grid_for(ctx, n_slots, 256), 256, 0, (const unsigned long long*)g_lo->ptr, n_slots,
@@ -1966,6 +2099,7 @@ bool try_fused_join_aggregate(PlanNode& agg, View* out) {
     LAUNCH(ctx, k_occupied_rows, grid_for(ctx, n_slots, 256), 256, 0, (const int64_t*)occ->ptr, (const int64_t*)offs->ptr, n_slots,
            (int64_t*)rows->buf->ptr);
   }
+  ctx->trace("join-agg: export");
   // key values travel with the group (gid-indexed): the build columns at the matched build rows
   std::vector<std::shared_ptr<Compiled>> keys;
   Schema js = join->schema;
@@ -1981,11 +2115,13 @@ bool try_fused_join_aggregate(PlanNode& agg, View* out) {
   }
   agg.strategy = "fused_join_probe_agg[unique-build " + std::to_string(nb) + " rows, " + std::to_string(P.n_cols) + " probe cols, " +
                  std::to_string(P.n_pred) + " range preds, " + std::to_string(P.n_accs) + " accs, " + std::to_string(P.stages) +
-                 " TMA stages]";
-  join->strategy = "fused-into-aggregate";
+                 " TMA stages] <- build[" + join->children[0]->strategy + "]";
+  join->strategy = "fused-into-aggregate <- [" + join->children[0]->strategy + ", probe scan]";
+  ctx->trace("join-agg: key columns");
   View dummy;
   dummy.schema = js;
   *out = finish_aggregate(ctx, dummy, keys, specs, agg.schema, accs, &key_cols, nullptr);
+  ctx->trace("join-agg: finish_aggregate");
   return true;
 }
 

@@ -1,7 +1,10 @@
 // Context plumbing + the generic kernels: interpreter-driven evaluation, predicate -> selection
 // vector (ballot/popc stream compaction), gathers ("take"), prefix scan, ingest helpers.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 
 #include "kernels.h"
 #include "launch.h"
@@ -26,6 +29,17 @@ DBufP Ctx::alloc_zero(size_t bytes) {
   return b;
 }
 void Ctx::sync() { CUDA_CHECK(cudaStreamSynchronize(stream)); }
+
+void Ctx::trace(const char* what) {
+  if (trace_on < 0) trace_on = getenv("QGPU_TRACE") ? 1 : 0;
+  if (!trace_on) return;
+  cudaStreamSynchronize(stream);
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  if (what) fprintf(stderr, "[qgpu trace] %-40s %8.3f ms\n", what, now - trace_t0);
+  trace_t0 = now;
+}
 
 void Ctx::h2d(void* dst, const void* src, size_t bytes) {
   if (bytes == 0) return;

@@ -15,6 +15,8 @@
 #include <cstring>
 #include <numeric>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "launch.h"
 #include "ops.h"
 
@@ -637,16 +639,19 @@ View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<C
       LAUNCH(ctx, k_rank_order, 1, 1024, 0, (const long long*)accs.first_row->ptr, (int)n_max, n_dev, (long long*)order->buf->ptr,
              (long long*)first_idx->buf->ptr);
     } else if (n_max > 0) {
-      std::vector<long long> fr((size_t)n_max);
-      ctx->d2h_sync(fr.data(), accs.first_row->ptr, (size_t)n_max * 8);
-      std::vector<long long> ord((size_t)n_max);
-      std::iota(ord.begin(), ord.end(), 0LL);
-      if (n_max <= (1 << 22)) std::sort(ord.begin(), ord.end(), [&](long long a, long long b) { return fr[a] < fr[b]; });
-      std::vector<long long> fidx((size_t)n_max);
-      for (int64_t i = 0; i < n_max; ++i) fidx[i] = fr[ord[i]];
-      ctx->h2d(order->buf->ptr, ord.data(), (size_t)n_max * 8);
-      ctx->h2d(first_idx->buf->ptr, fidx.data(), (size_t)n_max * 8);
-      ctx->sync();
+      // larger results: device radix sort of (first row, group id) pairs.  Output ordering is not part of the
+      // reference's contract (HashMap iteration order, hash.rs:98) -- it is ours -- so the library sort (CUB) is
+      // used here rather than a hand-written one; it is not on the measured hot path of Q1/Q6.
+      IdxP gids = iota_idx(ctx, n_max);
+      size_t tmp_bytes = 0;
+      CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const long long*)accs.first_row->ptr, (long long*)first_idx->buf->ptr,
+                                                 (const long long*)gids->buf->ptr, (long long*)order->buf->ptr, (int)n_max, 0, 64,
+                                                 ctx->stream));
+      DBufP tmp = ctx->alloc(std::max<size_t>(tmp_bytes, 16));
+      CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp->ptr, tmp_bytes, (const long long*)accs.first_row->ptr, (long long*)first_idx->buf->ptr,
+                                                 (const long long*)gids->buf->ptr, (long long*)order->buf->ptr, (int)n_max, 0, 64,
+                                                 ctx->stream));
+      ctx->launches += 1;
     }
   }
   // ---- aggregate columns: ONE launch finalises every aggregate directly in output order ----------------

@@ -201,6 +201,11 @@ struct Ctx {
   void prof_end(int slot);
   std::string prof_report();  // "name\tlaunches\ttotal_ms\tmax_ms\n" per kernel; resets the log
 
+  // QGPU_TRACE=1: synchronising wall-clock marks printed to stderr (debug aid, never on in benchmarks)
+  void trace(const char* what);
+  double trace_t0 = 0;
+  int trace_on = -1;
+
   DBufP alloc(size_t bytes);
   DBufP alloc_zero(size_t bytes);
   void h2d(void* dst, const void* src, size_t bytes);        // pageable or pinned host -> device
