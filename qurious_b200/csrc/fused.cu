@@ -113,6 +113,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
   const uint32_t a = smem_u32(bar);
@@ -474,19 +477,28 @@ struct GenericBody {
 // ------------------------------------------------------------------------------------------------
 template <int MODE, class Body>
 __device__ __forceinline__ void fused_main(const FParams& p) {
+  // Warp-specialised TMA pipeline: warps 0..7 (F_NT threads) consume tiles, warp 8 is the producer (one elected
+  // lane issues the bulk copies).  full[s]: producer -> consumers (complete_tx bytes); empty[s]: consumers ->
+  // producer (one arrive per consumer warp).  No CTA-wide barrier per tile: a fast warp runs up to `stages`
+  // tiles ahead of a slow one.
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = (uint64_t*)smem;
+  uint64_t* empty = full + 8;
   unsigned char* tiles = smem + 128;
   long long* priv = (long long*)(smem + p.priv_off);
   const int tid = threadIdx.x;
   const int NA2 = p.n_accs + 2;
+  const bool producer = tid >= F_NT;
 
-  if (MODE == FM_DENSE) {
+  if (MODE == FM_DENSE && !producer) {
     const int total = p.dense_groups * NA2 * F_NT;
     for (int i = tid; i < total; i += F_NT) priv[i] = acc_init(p, (i / F_NT) % NA2);
   }
   if (tid == 0) {
-    for (int s = 0; s < p.stages; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], F_NT / 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -495,45 +507,41 @@ __device__ __forceinline__ void fused_main(const FParams& p) {
   const int64_t first_tile = blockIdx.x;
   const int64_t my_tiles = first_tile < p.n_tiles ? (p.n_tiles - first_tile + gridDim.x - 1) / gridDim.x : 0;
 
-  const uint64_t l2_policy = l2_evict_first_policy();
-  auto issue = [&](int64_t i) {
-    const int s = (int)(i % p.stages);
-    const int64_t t = first_tile + i * gridDim.x;
-    const int64_t row0 = t * F_T;
-    const int64_t rows = min((int64_t)F_T, p.n_rows - row0);
-    unsigned char* dst = tiles + (size_t)s * p.stage_bytes;
-    uint32_t total = 0;
+  if (producer) {
+    if (tid == F_NT) {
+      const uint64_t l2_policy = l2_evict_first_policy();
 #pragma unroll 1
-    for (int c = 0; c < p.n_cols; ++c) total += ((uint32_t)(rows * p.cols[c].width) + 15u) & ~15u;
-    mbar_expect_tx(&full[s], total);
+      for (int64_t i = 0; i < my_tiles; ++i) {
+        const int s = (int)(i % p.stages);
+        const int64_t use = i / p.stages;
+        if (use > 0) mbar_wait(&empty[s], (uint32_t)((use - 1) & 1));  // every consumer warp released the previous use
+        const int64_t row0 = (first_tile + i * gridDim.x) * F_T;
+        const int64_t rows = min((int64_t)F_T, p.n_rows - row0);
+        unsigned char* dst = tiles + (size_t)s * p.stage_bytes;
+        uint32_t total = 0;
 #pragma unroll 1
-    for (int c = 0; c < p.n_cols; ++c) {
-      const uint32_t bytes = ((uint32_t)(rows * p.cols[c].width) + 15u) & ~15u;
-      bulk_g2s(dst + p.cols[c].smem_off, p.cols[c].ptr + (size_t)row0 * p.cols[c].width, bytes, &full[s], l2_policy);
+        for (int c = 0; c < p.n_cols; ++c) total += ((uint32_t)(rows * p.cols[c].width) + 15u) & ~15u;
+        mbar_expect_tx(&full[s], total);
+#pragma unroll 1
+        for (int c = 0; c < p.n_cols; ++c) {
+          const uint32_t bytes = ((uint32_t)(rows * p.cols[c].width) + 15u) & ~15u;
+          bulk_g2s(dst + p.cols[c].smem_off, p.cols[c].ptr + (size_t)row0 * p.cols[c].width, bytes, &full[s], l2_policy);
+        }
+      }
     }
-  };
-  if (tid == 0)
-    for (int64_t i = 0; i < my_tiles && i < p.stages; ++i) issue(i);
-
+  } else {
 #pragma unroll 1
-  for (int64_t i = 0; i < my_tiles; ++i) {
-    const int s = (int)(i % p.stages);
-    mbar_wait(&full[s], (uint32_t)((i / p.stages) & 1));
-    const unsigned char* stage = tiles + (size_t)s * p.stage_bytes;
-    const int64_t row0 = (first_tile + i * gridDim.x) * F_T;
-    const int rows = (int)min((int64_t)F_T, p.n_rows - row0);
-
-    Body::tile(p, stage, row0, rows, tid, priv, NA2);
-    // every thread is done with stage s before it is refilled; the same barrier broadcasts the abort flag
-    const int aborted = __syncthreads_or(MODE == FM_HASH && tid == 0 && *(volatile int*)p.abort_flag != 0);
-    if (aborted) {
-      // drain the copies already in flight (the CTA's shared memory must outlive them), then leave
-      if (tid == 0)
-        for (int64_t j = i + 1; j < my_tiles && j < i + p.stages; ++j)
-          mbar_wait(&full[(int)(j % p.stages)], (uint32_t)((j / p.stages) & 1));
-      return;
+    for (int64_t i = 0; i < my_tiles; ++i) {
+      const int s = (int)(i % p.stages);
+      mbar_wait(&full[s], (uint32_t)((i / p.stages) & 1));
+      const unsigned char* stage = tiles + (size_t)s * p.stage_bytes;
+      const int64_t row0 = (first_tile + i * gridDim.x) * F_T;
+      const int rows = (int)min((int64_t)F_T, p.n_rows - row0);
+      // HASH: once the table overflowed the host retries with a larger one; the rest of this pass only drains
+      if (!(MODE == FM_HASH && *(volatile int*)p.abort_flag != 0)) Body::tile(p, stage, row0, rows, tid, priv, NA2);
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s
     }
-    if (tid == 0 && i + p.stages < my_tiles) issue(i + p.stages);
   }
 
   // ---- DENSE: reduce the per-thread private tables once per CTA into the 128-bit global table ----
@@ -541,7 +549,7 @@ __device__ __forceinline__ void fused_main(const FParams& p) {
     __syncthreads();
     const int lane = tid & 31, warp = tid >> 5;
     const int n_lines = p.dense_groups * NA2;
-    for (int line = warp; line < n_lines; line += F_NT / 32) {
+    for (int line = producer ? n_lines : warp; line < n_lines; line += F_NT / 32) {
       const int k = line % NA2;
       const int g = line / NA2;
       const long long* src = priv + (size_t)line * F_NT;
@@ -598,7 +606,7 @@ __device__ __forceinline__ void fused_main(const FParams& p) {
 // DENSE keeps one CTA per SM (its private tables fill shared memory); the table-probing modes run two CTAs per
 // SM (16 warps) to hide the latency of their random HBM/L2 accesses
 template <int MODE>
-__global__ void __launch_bounds__(F_NT, MODE == FM_DENSE ? 1 : 2) k_fused_scan_agg(const __grid_constant__ FParams p) {
+__global__ void __launch_bounds__(F_NT + 32, MODE == FM_DENSE ? 1 : 2) k_fused_scan_agg(const __grid_constant__ FParams p) {
   fused_main<MODE, GenericBody<MODE>>(p);
 }
 
@@ -775,7 +783,7 @@ struct SpecBody {
 };
 
 template <uint64_t S0, uint64_t S1, uint64_t S2, uint64_t S3>
-__global__ void __launch_bounds__(F_NT, 1) k_fused_scan_agg_spec(const __grid_constant__ FParams p) {
+__global__ void __launch_bounds__(F_NT + 32, 1) k_fused_scan_agg_spec(const __grid_constant__ FParams p) {
   fused_main<FM_DENSE, SpecBody<S0, S1, S2, S3>>(p);
 }
 
@@ -1641,10 +1649,10 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
       specialised = true;
       CUDA_CHECK(cudaFuncSetAttribute(spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
       ::qgpu::KernelScope ks(ctx, "k_fused_scan_agg_spec");
-      spec<<<grid, F_NT, smem_bytes, ctx->stream>>>(P);
+      spec<<<grid, F_NT + 32, smem_bytes, ctx->stream>>>(P);
       CUDA_CHECK(cudaGetLastError());
     } else {
-      LAUNCH(ctx, k_fused_scan_agg<FM_DENSE>, grid, F_NT, smem_bytes, P);
+      LAUNCH(ctx, k_fused_scan_agg<FM_DENSE>, grid, F_NT + 32, smem_bytes, P);
     }
   } else {
     // capacity: bounded by the key domain and by the row count; grown x8 on overflow
@@ -1671,7 +1679,7 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
       P.acc_stride = cap + 1;
       P.n_groups = (unsigned long long*)flags->ptr;
       P.abort_flag = (int*)((char*)flags->ptr + 8);
-      LAUNCH(ctx, k_fused_scan_agg<FM_HASH>, grid, F_NT, smem_bytes, P);
+      LAUNCH(ctx, k_fused_scan_agg<FM_HASH>, grid, F_NT + 32, smem_bytes, P);
       const int aborted = ctx->read_scalar((const int*)((char*)flags->ptr + 8));
       if (!aborted) break;
       if (cap >= need) throw_internal("fused aggregate: hash table overflow (internal error)");
@@ -1924,7 +1932,7 @@ static bool fused_unordered_join(PlanNode& join, View* out) {
   P.bkey = nb > 0 ? bkey->data->ptr : slots->ptr;
   P.bkey_width = nb > 0 ? phys_width(bkey->phys) : 8;
   CUDA_CHECK(cudaFuncSetAttribute(k_fused_scan_agg<FM_EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem_bytes));
-  LAUNCH(ctx, k_fused_scan_agg<FM_EMIT>, fp->grid, F_NT, fp->smem_bytes, P);
+  LAUNCH(ctx, k_fused_scan_agg<FM_EMIT>, fp->grid, F_NT + 32, fp->smem_bytes, P);
   const int64_t n_out = (int64_t)ctx->read_scalar((const unsigned long long*)flags->ptr);
   ctx->trace("  emit-join: probe kernel");
   b_idx->length = p_idx->length = n_out;
@@ -2045,7 +2053,7 @@ bool try_fused_join_aggregate(PlanNode& agg, View* out) {
   P.bkey_width = nb > 0 ? phys_width(bkey->phys) : 8;
   P.acc_stride = n_slots;
   CUDA_CHECK(cudaFuncSetAttribute(k_fused_scan_agg<FM_PROBE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem_bytes));
-  LAUNCH(ctx, k_fused_scan_agg<FM_PROBE>, fp->grid, F_NT, fp->smem_bytes, P);
+  LAUNCH(ctx, k_fused_scan_agg<FM_PROBE>, fp->grid, F_NT + 32, fp->smem_bytes, P);
 
   ctx->trace("join-agg: probe+aggregate kernel");
   // ---- groups = build rows that were matched at least once -----------------------------------------------------
