@@ -37,7 +37,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--query", default="q1", choices=["q1", "q6", "q3"])
+    ap.add_argument("--query", default="q1", choices=["q1", "q6", "q3", "groupby"])
+    ap.add_argument("--rows", type=int, default=1_000_000_000, help="groupby workload: total rows (all GPUs)")
+    ap.add_argument("--groups", type=int, default=100_000_000, help="groupby workload: distinct keys")
     ap.add_argument("--sf", type=float, default=10.0, help="TPC-H scale factor PER GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample-rows", type=int, default=20_000_000)
@@ -56,7 +58,9 @@ QUERY_COLUMNS = {
            "lineitem": ["l_orderkey", "l_extendedprice", "l_discount", "l_shipdate"]},
 }
 WORKLOAD = {"q1": "TPC-H Q1 group-by aggregate", "q6": "TPC-H Q6 filter + SUM",
-            "q3": "TPC-H Q3 customer-orders-lineitem hash join + aggregate"}
+            "q3": "TPC-H Q3 customer-orders-lineitem hash join + aggregate",
+            "groupby": "synthetic int64-key group-by SUM/COUNT/MIN/MAX(v) AVG(f)"}
+GROUPBY_SCHEMA = [("k", "int64"), ("v", "int64"), ("f", "float64")]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -164,8 +168,38 @@ def batches_nbytes(batches):
     return n
 
 
+def gen_groupby(rows, groups, device, row_range=None):
+    """BASELINE.json configs[3]: k = bijectively scrambled uniform key over `groups` values, v in [-1e6, 1e6],
+    f in [0, 1); counter-based like the TPC-H generator, so any row range can be generated independently."""
+    import pyarrow as pa
+    import torch
+    from qurious_b200 import tpch
+    lo, hi = row_range if row_range is not None else (0, rows)
+    i = torch.arange(lo, hi, dtype=torch.int64, device=device)
+    k = tpch._mix(tpch.rnd(50, i) % groups)
+    v = tpch.uniform(51, i, -1_000_000, 1_000_000)
+    f = (tpch.rnd(52, i) >> 9).to(torch.float64) / float(1 << 53)
+    schema = pa.schema([("k", pa.int64()), ("v", pa.int64()), ("f", pa.float64())])
+    return tpch.RawTable("t", schema, hi - lo, {"k": k, "v": v, "f": f}, {}, {})
+
+
+def groupby_plan(table):
+    import pyarrow as pa
+    from qurious_b200.physical.expr import (AvgAggregateExpr, Column, CountAggregateExpr, MaxAggregateExpr, MinAggregateExpr,
+                                            SumAggregateExpr)
+    from qurious_b200.physical.plan import HashAggregate, Scan
+    K, V, F = Column("k", 0), Column("v", 1), Column("f", 2)
+    out = pa.schema([("k", pa.int64()), ("sum_v", pa.int64()), ("count_v", pa.int64()), ("min_v", pa.int64()),
+                     ("max_v", pa.int64()), ("avg_f", pa.float64())])
+    return HashAggregate(out, Scan(table.schema, table, None, None), [K],
+                         [SumAggregateExpr(V, pa.int64()), CountAggregateExpr(V), MinAggregateExpr(V, pa.int64()),
+                          MaxAggregateExpr(V, pa.int64()), AvgAggregateExpr(F, pa.float64(), pa.float64())])
+
+
 def build_plan(query, tables):
     from qurious_b200 import tpch
+    if query == "groupby":
+        return groupby_plan(tables["t"])
     db = tpch.Database(0.0, tables.get("customer"), tables.get("orders"), tables.get("lineitem"))
     return getattr(tpch, query + "_plan")(db)
 
@@ -177,6 +211,9 @@ def shard_range(total_rows, rank, world):
 def gen_raw(query, sf_total, device, rank, world):
     """RawTables for `query`; lineitem is this rank's row range, the (small) dimension tables are whole."""
     from qurious_b200 import tpch
+    if query == "groupby":
+        rows, groups = sf_total     # (total rows, groups) for this workload
+        return {"t": gen_groupby(rows, groups, device, shard_range(rows, rank, world) if world > 1 else None)}
     cols = QUERY_COLUMNS[query]
     out = {}
     n_l = tpch.n_lineitems(sf_total)
@@ -290,18 +327,21 @@ def run_b200(args):
     stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", local_rank))
     sampler = ClockSampler(local_rank)
     peak, peak_src = measured_peak_gbs()
-    sf_total = args.sf * world
+    sf_total = args.sf * world if args.query != "groupby" else (args.rows, args.groups)
+    driving = "t" if args.query == "groupby" else "lineitem"
     q = args.query
 
     # ---- device-resident leg -----------------------------------------------------------------
     raw = gen_raw(q, sf_total, "cuda", rank, world)
-    rows_local = raw["lineitem"].rows
+    rows_local = raw[driving].rows
     dev_tables = {k: tpch.to_device_table(ctx, v) for k, v in raw.items()}
     plan = build_plan(q, dev_tables)
     sharded = None
     if world > 1:
         # row-range shards: shard-local partial aggregate -> NCCL all-gather of the state blocks -> exact merge
         from qurious_b200 import distributed as qd
+        if q == "groupby":
+            raise SystemExit("groupby at N > 1 needs the hash-repartition path (python bench.py --query groupby-repartition)")
         lo, _hi = shard_range(tpch.n_lineitems(sf_total), rank, world)
         sharded = qd.ShardedAggregate(ctx, plan, lo, world)
 
@@ -325,7 +365,9 @@ def run_b200(args):
     top = prof_sorted[0] if prof_sorted else ("none", 0, 0.0, 0.0)
     top_ms = top[2] / max(top[1], 1)
     top_share = top[2] / max(sum(r[2] for r in prof), 1e-9)
-    top_bytes = per_table.get("lineitem", alg_bytes)   # the dominant kernel streams the driving table
+    top_bytes = per_table.get(driving, alg_bytes)   # the dominant kernel streams the driving table
+    if q == "groupby":
+        top_bytes += 64 * rows_local            # + one random 32 B sector read + write per row on the group table
     achieved = top_bytes / (top_ms / 1e3) / 1e9 if top_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -338,7 +380,7 @@ def run_b200(args):
     e2e = None
     cpu = None
     host_batches = None
-    if not args.no_e2e:
+    if not args.no_e2e and q != "groupby":
         raw_h = gen_raw(q, sf_total, "cuda", rank, world)
         host = {}
         for k, v in raw_h.items():
@@ -410,8 +452,9 @@ def run_b200(args):
         line = {"metric": f"TPC-H {q.upper()} rows/sec", "value": value, "unit": "rows/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "i64/i128 (exact decimal)", "data": "synthetic",
-                "config": {"workload": f"{WORKLOAD[q]} at SF{args.sf:g} per GPU ({rows_total} lineitem rows total, "
-                                       f"row-range sharded over {world} GPU(s))",
+                "config": {"workload": (f"{WORKLOAD[q]} at SF{args.sf:g} per GPU ({rows_total} lineitem rows total, "
+                                        f"row-range sharded over {world} GPU(s))") if q != "groupby" else
+                           f"{WORKLOAD[q]}: {rows_total} rows, {args.groups} groups, {world} GPU(s)",
                            "l2": "inputs larger than L2 (resident columns >> 126 MB), no flush needed",
                            "strategy": strategy, "rows_per_gpu": rows_local},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(round(launches * args.steps)),

@@ -86,7 +86,6 @@ struct FParams {
   // DENSE: lo/hi[g * (n_accs + 2) + k];  HASH: lo/hi[k * (capacity + 1) + slot]
   unsigned long long* g_lo;
   unsigned long long* g_hi;
-  unsigned long long* t_keys;
   unsigned long long* n_groups;
   int* abort_flag;
   // FM_PROBE: join table on the BUILD side (unique keys): slot = (tag32 << 32) | (build row + 1), 0 = empty;
@@ -96,7 +95,11 @@ struct FParams {
   uint64_t jt_mask;
   const void* bkey;
   int32_t bkey_width, pad_probe;
-  int64_t acc_stride;
+  // accumulator word of (accumulator k, slot g) = g_lo[acc_base + k * acc_kstride + g * acc_gstride]
+  //   HASH : array of records {key, acc[0..n_accs), count, first row, pad} (acc_base 1, kstride 1, gstride = record words):
+  //          one 64 B record per group => one cache line per row instead of one per accumulator
+  //   PROBE: structure of arrays over build rows (acc_base 0, kstride = build rows, gstride 1)
+  int64_t acc_base, acc_kstride, acc_gstride;
   FCol cols[F_MAXC];
   FPred pred[F_MAXP];
   FKey keys[F_MAXK];
@@ -342,14 +345,15 @@ struct GenericBody {
           uint64_t sl = fmix64(c) & p.cap_mask;
           int probes = 0;
           while (true) {
-            unsigned long long cur = *(volatile unsigned long long*)&p.t_keys[sl];
+            unsigned long long* keyp = p.g_lo + sl * (uint64_t)p.acc_gstride;
+            unsigned long long cur = *(volatile unsigned long long*)keyp;
             if (cur == c) break;
             if (((++probes) & 63) == 0 && *(volatile int*)p.abort_flag) {  // table (nearly) full: host retries larger
               sl = F_EMPTY;
               break;
             }
             if (cur == F_EMPTY) {
-              cur = atomicCAS(&p.t_keys[sl], F_EMPTY, (unsigned long long)c);
+              cur = atomicCAS(keyp, F_EMPTY, (unsigned long long)c);
               if (cur == F_EMPTY) {
                 const unsigned long long ng = atomicAdd(p.n_groups, 1ull);
                 if (2 * (ng + 1) > p.cap_mask + 1) *p.abort_flag = 1;
@@ -416,7 +420,9 @@ struct GenericBody {
           }
           return;
         }
-        const size_t stride = (size_t)p.acc_stride;
+        const size_t kstride = (size_t)p.acc_kstride, gstride = (size_t)p.acc_gstride;
+        unsigned long long* const acc0 = p.g_lo + p.acc_base;
+        unsigned long long* const acc0_hi = p.g_hi + p.acc_base;
         bool any_slot = false;
 #pragma unroll
         for (int j = 0; j < F_R; ++j) any_slot |= slot[j] != F_EMPTY;
@@ -444,27 +450,27 @@ struct GenericBody {
 #pragma unroll
             for (int j = 0; j < F_R; ++j) prev[j] = v[j];
           }
-          unsigned long long* lo = p.g_lo + k * stride;
 #pragma unroll
           for (int j = 0; j < F_R; ++j) {
             if (slot[j] == F_EMPTY) continue;
+            unsigned long long* lo = acc0 + k * kstride + slot[j] * gstride;
             if (kind == FK_SUM) {
-              if (p.carry) add128_global(lo + slot[j], p.g_hi + k * stride + slot[j], (unsigned long long)v[j], v[j] < 0 ? ~0ull : 0ull);
-              else atomicAdd(lo + slot[j], (unsigned long long)v[j]);
+              if (p.carry) add128_global(lo, acc0_hi + k * kstride + slot[j] * gstride, (unsigned long long)v[j], v[j] < 0 ? ~0ull : 0ull);
+              else atomicAdd(lo, (unsigned long long)v[j]);
             } else if (kind == FK_MIN) {
-              atomicMin((long long*)(lo + slot[j]), (long long)v[j]);
+              atomicMin((long long*)lo, (long long)v[j]);
             } else if (kind == FK_MAX) {
-              atomicMax((long long*)(lo + slot[j]), (long long)v[j]);
+              atomicMax((long long*)lo, (long long)v[j]);
             } else {
-              atomicAdd((double*)(lo + slot[j]), __longlong_as_double(v[j]));
+              atomicAdd((double*)lo, __longlong_as_double(v[j]));
             }
           }
         }
 #pragma unroll
         for (int j = 0; j < F_R; ++j) {
           if (slot[j] == F_EMPTY) continue;
-          atomicAdd(p.g_lo + (size_t)p.n_accs * stride + slot[j], 1ull);
-          atomicMin((long long*)(p.g_lo + (size_t)(p.n_accs + 1) * stride + slot[j]), (long long)(row0 + j * F_NT + tid));
+          atomicAdd(acc0 + (size_t)p.n_accs * kstride + slot[j] * gstride, 1ull);
+          atomicMin((long long*)(acc0 + (size_t)(p.n_accs + 1) * kstride + slot[j] * gstride), (long long)(row0 + j * F_NT + tid));
         }
       }
     }
@@ -842,12 +848,19 @@ static FusedKernel find_specialised(const FParams& P) {
 struct FInit {
   long long v[F_MAXA + 2];
 };
-__global__ void k_fused_init(unsigned long long* lo, unsigned long long* hi, int64_t n_slots, int na2, int dense, FInit init) {
-  const int64_t total = n_slots * na2;
+// layout 0: [k][slot] (PROBE), 1: [slot][k] (DENSE), 2: records of `rec` words {key = EMPTY, acc[0..na2), pad} (HASH)
+__global__ void k_fused_init(unsigned long long* lo, unsigned long long* hi, int64_t n_slots, int na2, int layout, int rec, FInit init) {
+  const int64_t total = layout == 2 ? n_slots * rec : n_slots * na2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int k = dense ? (int)(i % na2) : (int)(i / n_slots);
-    lo[i] = (unsigned long long)init.v[k];
+    unsigned long long v;
+    if (layout == 2) {
+      const int w = (int)(i % rec);
+      v = w == 0 ? F_EMPTY : (w <= na2 ? (unsigned long long)init.v[w - 1] : 0ull);
+    } else {
+      v = (unsigned long long)init.v[layout == 1 ? (int)(i % na2) : (int)(i / n_slots)];
+    }
+    lo[i] = v;
     if (hi) hi[i] = 0;
   }
 }
@@ -1277,6 +1290,7 @@ struct FusedPlan {
   size_t smem_bytes = 0;
   int grid = 0;
   FusedKernel spec = nullptr;
+  int64_t learned_cap = 0;  // HASH: capacity that held every group last time (skips the growth retries)
   // validity of the cache
   std::vector<const DCol*> col_ids;
   int64_t n_rows = 0, n_batches = 0;
@@ -1610,6 +1624,7 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
 
 static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
   Ctx* ctx = agg.ctx;
+  ctx->trace(nullptr);
   FParams P = fp.P;
   std::vector<std::shared_ptr<Compiled>>& keys = fp.keys;
   std::vector<AggSpec>& specs = fp.specs;
@@ -1627,7 +1642,8 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
   }
   CUDA_CHECK(cudaFuncSetAttribute(k_fused_scan_agg<FM_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   CUDA_CHECK(cudaFuncSetAttribute(k_fused_scan_agg<FM_HASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  DBufP g_lo, g_hi, t_keys, flags;
+  DBufP g_lo, g_hi, flags;
+  int64_t rec = 0;        // HASH: words per group record (0: accumulators start at word 0)
   bool specialised = false;
   int64_t n_slots = 0, k_stride = 0, g_stride = 0;
   int64_t cap = 0;
@@ -1639,7 +1655,7 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
     g_hi = ctx->alloc((size_t)n_slots * NA2 * 8);
     flags = ctx->alloc_zero(16);
     LAUNCH(ctx, k_fused_init, grid_for(ctx, n_slots * NA2, 256), 256, 0, (unsigned long long*)g_lo->ptr,
-           (unsigned long long*)g_hi->ptr, n_slots, NA2, 1, init);
+           (unsigned long long*)g_hi->ptr, n_slots, NA2, 1, 0, init);
     P.g_lo = (unsigned long long*)g_lo->ptr;
     P.g_hi = (unsigned long long*)g_hi->ptr;
     P.abort_flag = (int*)((char*)flags->ptr + 8);
@@ -1660,33 +1676,37 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
     int64_t max_groups = (int64_t)std::min<i128>(domain, (i128)n_rows);
     int64_t need = 2;
     while (need < 2 * max_groups) need <<= 1;
-    cap = std::min<int64_t>(need, (int64_t)1 << 22);
+    cap = std::min<int64_t>(need, std::max<int64_t>((int64_t)1 << 22, fp.learned_cap));
     while (true) {
       n_slots = cap + 1;
-      k_stride = n_slots;
-      g_stride = 1;
-      t_keys = ctx->alloc((size_t)cap * 8);
-      CUDA_CHECK(cudaMemsetAsync(t_keys->ptr, 0xff, (size_t)cap * 8, ctx->stream));
-      g_lo = ctx->alloc((size_t)n_slots * NA2 * 8);
-      g_hi = P.carry ? ctx->alloc((size_t)n_slots * NA2 * 8) : nullptr;
+      rec = ((NA2 + 1 + 7) / 8) * 8;  // record words: key + accumulators + count + first row, padded to 64 B
+      k_stride = 1;
+      g_stride = rec;
+      g_lo = ctx->alloc((size_t)n_slots * rec * 8);
+      g_hi = P.carry ? ctx->alloc((size_t)n_slots * rec * 8) : nullptr;
       flags = ctx->alloc_zero(16);
-      LAUNCH(ctx, k_fused_init, grid_for(ctx, n_slots * NA2, 256), 256, 0, (unsigned long long*)g_lo->ptr,
-             g_hi ? (unsigned long long*)g_hi->ptr : nullptr, n_slots, NA2, 0, init);
+      LAUNCH(ctx, k_fused_init, grid_for(ctx, n_slots * rec, 256), 256, 0, (unsigned long long*)g_lo->ptr,
+             g_hi ? (unsigned long long*)g_hi->ptr : nullptr, n_slots, NA2, 2, (int)rec, init);
       P.g_lo = (unsigned long long*)g_lo->ptr;
       P.g_hi = g_hi ? (unsigned long long*)g_hi->ptr : nullptr;
-      P.t_keys = (unsigned long long*)t_keys->ptr;
       P.cap_mask = (uint64_t)(cap - 1);
-      P.acc_stride = cap + 1;
+      P.acc_base = 1;
+      P.acc_kstride = 1;
+      P.acc_gstride = rec;
       P.n_groups = (unsigned long long*)flags->ptr;
       P.abort_flag = (int*)((char*)flags->ptr + 8);
       LAUNCH(ctx, k_fused_scan_agg<FM_HASH>, grid, F_NT + 32, smem_bytes, P);
       const int aborted = ctx->read_scalar((const int*)((char*)flags->ptr + 8));
-      if (!aborted) break;
+      if (!aborted) {
+        fp.learned_cap = cap;
+        break;
+      }
       if (cap >= need) throw_internal("fused aggregate: hash table overflow (internal error)");
       cap = std::min<int64_t>(cap * 8, need);
     }
   }
 
+  ctx->trace("scan-agg: init + kernel(s)");
   // ---- export: occupied slots -> dense group ids, accumulators -> GroupAccs ---------------------------------
   const bool grouped = !keys.empty();
   const bool small = P.mode == FM_DENSE;  // <= 4096 slots: one-CTA export, no host round trip for the group count
@@ -1698,7 +1718,7 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
   } else {
     occ = ctx->alloc((size_t)n_slots * 8);
     offs = ctx->alloc((size_t)n_slots * 8);
-    LAUNCH(ctx, k_fused_occupied, grid_for(ctx, n_slots, 256), 256, 0, (const unsigned long long*)g_lo->ptr, n_slots,
+    LAUNCH(ctx, k_fused_occupied, grid_for(ctx, n_slots, 256), 256, 0, (const unsigned long long*)g_lo->ptr + (rec ? 1 : 0), n_slots,
            (int64_t)P.n_accs * k_stride, g_stride, (int64_t*)occ->ptr);
     n_groups = exclusive_scan_i64(ctx, (const int64_t*)occ->ptr, (int64_t*)offs->ptr, n_slots);
   }
@@ -1748,9 +1768,9 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
            (unsigned long long*)cnt->ptr, (long long*)first->ptr, (long long*)n_groups_dev->ptr);
   } else {
     if (n_groups > 0)
-      LAUNCH(ctx, k_fused_export, grid_for(ctx, n_slots, 256), 256, 0, (const unsigned long long*)g_lo->ptr,
-             g_hi ? (const unsigned long long*)g_hi->ptr : nullptr, n_slots, k_stride, g_stride, P.n_accs, (const int64_t*)occ->ptr,
-             (const int64_t*)offs->ptr, ex, (unsigned long long*)cnt->ptr, (long long*)first->ptr);
+      LAUNCH(ctx, k_fused_export, grid_for(ctx, n_slots, 256), 256, 0, (const unsigned long long*)g_lo->ptr + (rec ? 1 : 0),
+             g_hi ? (const unsigned long long*)g_hi->ptr + (rec ? 1 : 0) : nullptr, n_slots, k_stride, g_stride, P.n_accs,
+             (const int64_t*)occ->ptr, (const int64_t*)offs->ptr, ex, (unsigned long long*)cnt->ptr, (long long*)first->ptr);
     if (!grouped && n_groups == 0) {
       // no row passed the filter: MIN/MAX keep their sentinels (reference quirk Q4), SUM/AVG are NULL (cnt == 0)
       for (size_t i = 0; i < specs.size(); ++i) {
@@ -1768,6 +1788,7 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
                  (specialised ? "/shape-specialised, " : ", ") +
                  std::to_string(P.n_cols) + " cols, " + std::to_string(P.n_pred) + " range preds, " + std::to_string(P.n_accs) +
                  " accs, " + std::to_string(P.stages) + " TMA stages]";
+  ctx->trace("scan-agg: export");
   if (agg.defer) {
     agg.defer->set = true;
     agg.defer->input = v;
@@ -1776,7 +1797,9 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
     agg.defer->accs = accs;
     return View();
   }
-  return finish_aggregate(ctx, v, keys, specs, agg.schema, accs);
+  View fin = finish_aggregate(ctx, v, keys, specs, agg.schema, accs);
+  ctx->trace("scan-agg: finish_aggregate");
+  return fin;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2042,7 +2065,7 @@ bool try_fused_join_aggregate(PlanNode& agg, View* out) {
   DBufP g_hi = P.carry ? ctx->alloc((size_t)n_slots * NA2 * 8) : nullptr;
   DBufP flags = ctx->alloc_zero(16);
   LAUNCH(ctx, k_fused_init, grid_for(ctx, n_slots * NA2, 256), 256, 0, (unsigned long long*)g_lo->ptr,
-         g_hi ? (unsigned long long*)g_hi->ptr : nullptr, n_slots, NA2, 0, init);
+         g_hi ? (unsigned long long*)g_hi->ptr : nullptr, n_slots, NA2, 0, 0, init);
   P.g_lo = (unsigned long long*)g_lo->ptr;
   P.g_hi = g_hi ? (unsigned long long*)g_hi->ptr : nullptr;
   P.n_groups = (unsigned long long*)flags->ptr;
@@ -2051,7 +2074,9 @@ bool try_fused_join_aggregate(PlanNode& agg, View* out) {
   P.jt_mask = (uint64_t)(cap - 1);
   P.bkey = nb > 0 ? bkey->data->ptr : slots->ptr;
   P.bkey_width = nb > 0 ? phys_width(bkey->phys) : 8;
-  P.acc_stride = n_slots;
+  P.acc_base = 0;
+  P.acc_kstride = n_slots;
+  P.acc_gstride = 1;
   CUDA_CHECK(cudaFuncSetAttribute(k_fused_scan_agg<FM_PROBE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem_bytes));
   LAUNCH(ctx, k_fused_scan_agg<FM_PROBE>, fp->grid, F_NT + 32, fp->smem_bytes, P);
 

@@ -654,6 +654,7 @@ View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<C
       ctx->launches += 1;
     }
   }
+  ctx->trace("  finish: group order");
   // ---- aggregate columns: ONE launch finalises every aggregate directly in output order ----------------
   FinAll all;
   memset(&all, 0, sizeof(all));
@@ -713,6 +714,7 @@ View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<C
   } else if (n_dev) {
     n_groups = (int64_t)ctx->read_scalar(n_dev);
   }
+  ctx->trace("  finish: finalize kernel + flags");
   out.num_rows = n_groups;
   out.num_batches = 1;
   // ---- key columns: values of the group's first row (hash.rs:62-68) ---------------------------------

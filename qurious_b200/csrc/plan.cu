@@ -484,9 +484,12 @@ int qgpu_table_export(qgpu_table* t, struct ArrowArray* out_array, struct ArrowS
 void qgpu_table_free(qgpu_table* t) {
   if (!t) return;
   {
-    std::lock_guard<std::recursive_mutex> lk(t->t->ctx->mu);
-    cudaSetDevice(t->t->ctx->device);
+    qgpu::Ctx* c = t->t->ctx;
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    c->trace("(before table_free)");
     t->t.reset();
+    c->trace("table_free");
   }
   delete t;
 }
@@ -688,8 +691,10 @@ int qgpu_plan_execute_device(qgpu_plan* p, qgpu_table** out, int64_t* out_batche
   if (!p || !out) return QGPU_ERR_INTERNAL;
   PlanNode& n = *p->node;
   return guard(n.ctx, [&] {
+    n.ctx->trace("(between calls)");
     Timer tm(n.ctx);
     View v = n.execute();
+    n.ctx->trace("execute_device: plan");
     auto t = std::make_shared<TableImpl>();
     t->ctx = n.ctx;
     t->schema = n.schema;
@@ -699,6 +704,7 @@ int qgpu_plan_execute_device(qgpu_plan* p, qgpu_table** out, int64_t* out_batche
       if (!v.cols[i].base) t->cols.push_back(nullptr);
       else t->cols.push_back(materialize(n.ctx, v.cols[i], v.num_rows));
     }
+    n.ctx->trace("execute_device: materialize result");
     tm.stop(n);
     if (out_batches) *out_batches = v.num_batches;
     *out = new qgpu_table{t};
