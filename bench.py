@@ -340,13 +340,31 @@ def run_b200(args):
     if world > 1:
         # row-range shards: shard-local partial aggregate -> NCCL all-gather of the state blocks -> exact merge
         from qurious_b200 import distributed as qd
+        lo = 0 if q == "groupby" else shard_range(tpch.n_lineitems(sf_total), rank, world)[0]
         if q == "groupby":
-            raise SystemExit("groupby at N > 1 needs the hash-repartition path (python bench.py --query groupby-repartition)")
-        lo, _hi = shard_range(tpch.n_lineitems(sf_total), rank, world)
-        sharded = qd.ShardedAggregate(ctx, plan, lo, world)
+            # config 4: hash repartition of (k, v, f) on fmix64(k) % world with NCCL all-to-all over NVLink, then a
+            # purely local aggregate (groups are rank-disjoint afterwards); the result is the concatenation
+            from qurious_b200.physical.plan import MemoryTable
 
-        def step():
-            sharded.execute()
+            def step():
+                recv = qd.hash_repartition(ctx, dev_tables["t"]._dev, 0, world)
+                p = groupby_plan(MemoryTable.from_device_table(recv))
+                p.execute_device(ctx).free()
+                step.strategy = "hash_repartition[all_to_all x%d] -> %s" % (world, p.last_strategy())
+                p.release()
+                recv.free()
+        elif q == "q3":
+            # lineitem row-range shards, build sides replicated (broadcast join); groups straddling a shard boundary
+            # are merged by all-gathering the per-rank result rows and re-aggregating them
+            gm = qd.GatherMergeAggregate(ctx, plan, world)
+
+            def step():
+                gm.execute_device().free()
+        else:
+            sharded = qd.ShardedAggregate(ctx, plan, lo, world)
+
+            def step():
+                sharded.execute()
     else:
         def step():
             plan.execute_device(ctx).free()
@@ -358,7 +376,7 @@ def run_b200(args):
         _dist.all_reduce(rows_t, op=_dist.ReduceOp.SUM)
     ms_max, rows_total = float(t_ms.item()), int(rows_t.item())
     value = rows_total * args.steps / (ms_max / 1e3)
-    strategy = plan.last_strategy()
+    strategy = getattr(step, "strategy", None) or plan.last_strategy()
     alg_bytes, per_table = algorithmic_bytes(q, dev_tables)
     # dominant kernel by total device time
     prof_sorted = sorted(prof, key=lambda r: -r[2])
@@ -400,7 +418,9 @@ def run_b200(args):
         def one_e2e():
             tabs = {k: MemoryTable.try_new(b[0].schema, b) for k, b in host.items()}
             p = build_plan(q, tabs)
-            if world > 1:
+            if world > 1 and q == "q3":
+                out = qd.GatherMergeAggregate(ctx, p, world).execute()
+            elif world > 1:
                 out = qd.ShardedAggregate(ctx, p, lo, world).execute()
             else:
                 out = p.execute(ctx)

@@ -231,6 +231,15 @@ void qgpu_plan_free(qgpu_plan* p);
  *   4. qgpu_plan_execute_merged(p, gathered, n_states, max_groups, out)
  *        merges the states exactly (integer/decimal results are bit-identical to one GPU over the whole table)
  *        and finishes the plan.  More than max_groups groups on a shard -> QGPU_ERR_INTERNAL (use repartition). */
+/* Hash repartition (high-cardinality group-by / join inputs): `out` = the same rows grouped by
+ * partition id = mix64(key) % n_parts (order inside a partition unspecified); offsets[n_parts + 1] = row offsets of
+ * the partitions.  The key must be a NULL-free integer / date / Decimal(p<=18) column; every resident column must
+ * be NULL-free and fixed-width.  The per-partition slices are contiguous: the caller sends slice p of every column
+ * to rank p (ncclSend/ncclRecv == torch.distributed.all_to_all_single) using qgpu_table_column_device_buffer. */
+int qgpu_table_hash_partition(qgpu_table* t, int32_t key_col, int32_t n_parts, qgpu_table** out, int64_t* offsets);
+/* device pointer, byte size and value width of a resident fixed-width column's value buffer (valid while `t` lives) */
+int qgpu_table_column_device_buffer(qgpu_table* t, int32_t col, void** ptr, int64_t* bytes, int32_t* value_width);
+
 int qgpu_plan_state_bytes(qgpu_plan* p, int32_t max_groups, int64_t* bytes);
 int qgpu_plan_partial_state(qgpu_plan* p, int64_t row_offset, int32_t max_groups, void* device_buf, int64_t cap_bytes);
 int qgpu_plan_execute_merged(qgpu_plan* p, const void* gathered_device_buf, int32_t n_states, int32_t max_groups,

@@ -27,6 +27,7 @@ SYMBOLS = [
     "qgpu_plan_projection", "qgpu_plan_aggregate", "qgpu_plan_hash_join", "qgpu_plan_schema",
     "qgpu_plan_execute", "qgpu_plan_execute_device", "qgpu_plan_last_stats", "qgpu_plan_strategy",
     "qgpu_plan_free", "qgpu_plan_state_bytes", "qgpu_plan_partial_state", "qgpu_plan_execute_merged",
+    "qgpu_table_hash_partition", "qgpu_table_column_device_buffer",
 ]
 
 STATUS_KIND = {1: "InternalError", 2: "ArrowError", 3: "CudaError", 4: "NcclError", 5: "OutOfMemory"}
@@ -113,6 +114,8 @@ def load_library() -> ctypes.CDLL:
     lib.qgpu_plan_strategy.restype = ctypes.c_char_p
     lib.qgpu_plan_free.argtypes = [vp]
     lib.qgpu_plan_free.restype = None
+    lib.qgpu_table_hash_partition.argtypes = [vp, i32, i32, P(vp), P(i64)]
+    lib.qgpu_table_column_device_buffer.argtypes = [vp, i32, P(vp), P(i64), P(i32)]
     lib.qgpu_plan_state_bytes.argtypes = [vp, i32, P(i64)]
     lib.qgpu_plan_partial_state.argtypes = [vp, i64, i32, vp, i64]
     lib.qgpu_plan_execute_merged.argtypes = [vp, vp, i32, i32, vp]
@@ -243,6 +246,20 @@ class DeviceTable:
         if r < 0:
             raise QuriousError(1, self.ctx.lib.qgpu_last_error(self.ctx.handle).decode())
         return r
+
+    def hash_partition(self, key_col: int, n_parts: int):
+        """-> (DeviceTable with rows grouped by partition, [n_parts + 1] row offsets)."""
+        out = ctypes.c_void_p()
+        offs = (ctypes.c_int64 * (n_parts + 1))()
+        self.ctx.check(self.ctx.lib.qgpu_table_hash_partition(self.handle, key_col, n_parts, ctypes.byref(out), offs))
+        return DeviceTable(self.ctx, out, self.schema), list(offs)
+
+    def column_device_buffer(self, col: int):
+        """-> (device pointer, bytes, value width) of a fixed-width column's value buffer."""
+        p, n, w = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int32()
+        self.ctx.check(self.ctx.lib.qgpu_table_column_device_buffer(self.handle, col, ctypes.byref(p), ctypes.byref(n),
+                                                                   ctypes.byref(w)))
+        return int(p.value or 0), n.value, w.value
 
     def to_batch(self) -> pa.RecordBatch:
         ca = _ffi.new("struct ArrowArray*")

@@ -481,6 +481,34 @@ int qgpu_table_export(qgpu_table* t, struct ArrowArray* out_array, struct ArrowS
   });
 }
 
+int qgpu_table_hash_partition(qgpu_table* t, int32_t key_col, int32_t n_parts, qgpu_table** out, int64_t* offsets) {
+  if (!t || !out || !offsets) return QGPU_ERR_INTERNAL;
+  TableImpl& ti = *t->t;
+  return guard(ti.ctx, [&] {
+    std::vector<int64_t> offs;
+    auto r = hash_partition_table(ti, key_col, n_parts, offs);
+    for (size_t i = 0; i < offs.size(); ++i) offsets[i] = offs[i];
+    *out = new qgpu_table{r};
+  });
+}
+
+int qgpu_table_column_device_buffer(qgpu_table* t, int32_t col, void** ptr, int64_t* bytes, int32_t* value_width) {
+  if (!t || !ptr || !bytes) return QGPU_ERR_INTERNAL;
+  TableImpl& ti = *t->t;
+  return guard(ti.ctx, [&] {
+    ti.consolidate();
+    if (col < 0 || col >= (int32_t)ti.cols.size() || !ti.cols[col]) throw_internal("column is not resident");
+    const DCol& c = *ti.cols[col];
+    const int w = phys_width(c.phys);
+    if (w == 0) throw_internal("column has no fixed-width value buffer");
+    if (c.phys == PH_D64) throw_internal("column is resident as a narrowed decimal: it has no Arrow-layout value buffer");
+    if (c.null_count != 0) throw_internal("column has NULLs: the value buffer alone does not describe it");
+    *ptr = c.data->ptr;
+    *bytes = c.length * w;
+    if (value_width) *value_width = w;
+  });
+}
+
 void qgpu_table_free(qgpu_table* t) {
   if (!t) return;
   {

@@ -58,6 +58,8 @@ void shard_partial_state(PlanNode& root, int64_t row_offset, int32_t max_groups,
 int64_t shard_state_bytes(PlanNode& root, int32_t max_groups);
 View shard_execute_merged(PlanNode& root, const void* gathered, int32_t n_states, int32_t max_groups);
 
+std::shared_ptr<TableImpl> hash_partition_table(TableImpl& t, int key_col, int n_parts, std::vector<int64_t>& offsets);
+
 // fused.cu: returns true and fills `out` when the aggregate over this input can run as one fused
 // scan+filter+aggregate pipeline kernel.
 bool try_fused_scan_aggregate(PlanNode& agg, View* out);

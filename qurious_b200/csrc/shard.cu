@@ -447,3 +447,142 @@ View shard_execute_merged(PlanNode& root, const void* gathered, int32_t n_states
 }
 
 }  // namespace qgpu
+
+// ================================================================================================
+// Hash partitioning of a resident table ("high-cardinality group-by and join inputs are
+// hash-repartitioned with NCCL all-to-all").  partition id = mix64(key) % n_parts; the output table holds the
+// same rows grouped by partition (order inside a partition unspecified) -- the contiguous per-partition slices
+// are what the caller hands to ncclSend/ncclRecv (torch.distributed.all_to_all_single).
+// ================================================================================================
+namespace qgpu {
+
+#define PART_MAX 1024
+#define PART_THREADS 256
+#define PART_ITEMS 8
+#define PART_TILE (PART_THREADS * PART_ITEMS)
+
+__device__ __forceinline__ uint64_t part_mix(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+__device__ __forceinline__ int64_t part_key(const void* key, int width, int64_t row) {
+  return width == 8 ? ((const long long*)key)[row] : (int64_t)((const int*)key)[row];
+}
+
+__global__ void __launch_bounds__(PART_THREADS) k_part_hist(const void* __restrict__ key, int width, int64_t n, int n_parts,
+                                                            unsigned long long* __restrict__ counts) {
+  __shared__ unsigned int h[PART_MAX];
+  for (int i = threadIdx.x; i < n_parts; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride)
+    atomicAdd(&h[(unsigned)(part_mix((uint64_t)part_key(key, width, row)) % (unsigned)n_parts)], 1u);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_parts; i += blockDim.x)
+    if (h[i]) atomicAdd(&counts[i], (unsigned long long)h[i]);
+}
+
+struct PartCols {
+  int n_cols;
+  int width[16];
+  const unsigned char* src[16];
+  unsigned char* dst[16];
+};
+
+// one tile of PART_TILE rows per iteration: shared-memory histogram -> one global reservation per (CTA, partition)
+// -> scatter of every column
+__global__ void __launch_bounds__(PART_THREADS) k_part_scatter(const void* __restrict__ key, int width, int64_t n, int n_parts,
+                                                               unsigned long long* __restrict__ cursor, const __grid_constant__ PartCols pc) {
+  __shared__ unsigned int h[PART_MAX];
+  __shared__ unsigned long long base[PART_MAX];
+  const int64_t n_tiles = (n + PART_TILE - 1) / PART_TILE;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    for (int i = threadIdx.x; i < n_parts; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    unsigned part[PART_ITEMS], rank[PART_ITEMS];
+#pragma unroll
+    for (int j = 0; j < PART_ITEMS; ++j) {
+      const int64_t row = t * PART_TILE + (int64_t)j * PART_THREADS + threadIdx.x;
+      part[j] = 0xffffffffu;
+      if (row < n) {
+        part[j] = (unsigned)(part_mix((uint64_t)part_key(key, width, row)) % (unsigned)n_parts);
+        rank[j] = atomicAdd(&h[part[j]], 1u);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_parts; i += blockDim.x)
+      if (h[i]) base[i] = atomicAdd(&cursor[i], (unsigned long long)h[i]);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PART_ITEMS; ++j) {
+      if (part[j] == 0xffffffffu) continue;
+      const int64_t row = t * PART_TILE + (int64_t)j * PART_THREADS + threadIdx.x;
+      const unsigned long long d = base[part[j]] + rank[j];
+      for (int c = 0; c < pc.n_cols; ++c) {
+        if (pc.width[c] == 8) ((unsigned long long*)pc.dst[c])[d] = ((const unsigned long long*)pc.src[c])[row];
+        else if (pc.width[c] == 4) ((unsigned int*)pc.dst[c])[d] = ((const unsigned int*)pc.src[c])[row];
+        else if (pc.width[c] == 2) ((unsigned short*)pc.dst[c])[d] = ((const unsigned short*)pc.src[c])[row];
+        else pc.dst[c][d] = pc.src[c][row];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+std::shared_ptr<TableImpl> hash_partition_table(TableImpl& t, int key_col, int n_parts, std::vector<int64_t>& offsets) {
+  Ctx* ctx = t.ctx;
+  t.consolidate();
+  if (n_parts < 1 || n_parts > PART_MAX) throw_internal("n_parts must be in [1, 1024]");
+  if (key_col < 0 || key_col >= (int)t.cols.size() || !t.cols[key_col]) throw_internal("partition key column is not resident");
+  const int64_t n = t.num_rows;
+  const DCol& kc = *t.cols[key_col];
+  if (!(kc.phys == PH_I64 || kc.phys == PH_I32 || kc.phys == PH_D64 || kc.phys == PH_U64 || kc.phys == PH_U32) || kc.null_count != 0)
+    throw_internal("hash partitioning needs a NULL-free 32/64-bit integer, date or narrowed decimal key column");
+  PartCols pc;
+  memset(&pc, 0, sizeof(pc));
+  auto out = std::make_shared<TableImpl>();
+  out->ctx = ctx;
+  out->schema = t.schema;
+  out->num_rows = n;
+  out->num_batches = t.num_batches > 0 ? 1 : 0;
+  out->cols.assign(t.cols.size(), nullptr);
+  for (size_t c = 0; c < t.cols.size(); ++c) {
+    if (!t.cols[c]) continue;
+    const DCol& s = *t.cols[c];
+    const int w = phys_width(s.phys);
+    if (w == 0 || s.null_count != 0) throw_internal("hash partitioning supports NULL-free fixed-width columns only (column '" + t.schema.fields[c].name + "')");
+    if (pc.n_cols >= 16) throw_internal("hash partitioning supports at most 16 resident columns");
+    auto d = std::make_shared<DCol>(s);
+    d->data = ctx->alloc(std::max<size_t>((size_t)n * w, 16));
+    d->validity.reset();
+    d->dict_state = 0;
+    d->dict_codes.reset();
+    pc.width[pc.n_cols] = w;
+    pc.src[pc.n_cols] = (const unsigned char*)s.data->ptr;
+    pc.dst[pc.n_cols] = (unsigned char*)d->data->ptr;
+    pc.n_cols++;
+    out->cols[c] = d;
+  }
+  DBufP counts = ctx->alloc_zero((size_t)n_parts * 8), cursor = ctx->alloc((size_t)n_parts * 8);
+  std::vector<unsigned long long> h((size_t)n_parts, 0);
+  if (n > 0) {
+    LAUNCH(ctx, k_part_hist, grid_for(ctx, n, PART_THREADS * 8), PART_THREADS, 0, kc.data->ptr, phys_width(kc.phys), n, n_parts,
+           (unsigned long long*)counts->ptr);
+    ctx->d2h_sync(h.data(), counts->ptr, (size_t)n_parts * 8);
+  }
+  offsets.assign((size_t)n_parts + 1, 0);
+  for (int p = 0; p < n_parts; ++p) offsets[p + 1] = offsets[p] + (int64_t)h[p];
+  std::vector<unsigned long long> start(offsets.begin(), offsets.end() - 1);
+  ctx->h2d(cursor->ptr, start.data(), (size_t)n_parts * 8);
+  ctx->sync();
+  if (n > 0)
+    LAUNCH(ctx, k_part_scatter, grid_for(ctx, n, PART_TILE), PART_THREADS, 0, kc.data->ptr, phys_width(kc.phys), n, n_parts,
+           (unsigned long long*)cursor->ptr, pc);
+  return out;
+}
+
+}  // namespace qgpu

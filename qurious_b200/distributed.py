@@ -65,3 +65,212 @@ class ShardedAggregate:
         with torch.cuda.stream(self.stream):       # the collective is ordered after the library's stream work
             self.all_gather(self.gathered, self.state)
         return self.merge(self.gathered, self.world)
+
+
+# ------------------------------------------------------------------------------------------------
+# hash repartition (high-cardinality group-by / join inputs) over NCCL all-to-all
+# ------------------------------------------------------------------------------------------------
+def partition_ids_host(keys, n_parts: int):
+    """numpy mirror of csrc/shard.cu part_mix(): partition id = fmix64(key) % n_parts (tests / documentation only)."""
+    import numpy as np
+    x = np.asarray(keys).astype(np.int64).view(np.uint64).copy()
+    with np.errstate(over="ignore"):
+        x ^= x >> np.uint64(33)
+        x *= np.uint64(0xff51afd7ed558ccd)
+        x ^= x >> np.uint64(33)
+        x *= np.uint64(0xc4ceb9fe1a85ec53)
+        x ^= x >> np.uint64(33)
+    return (x % np.uint64(n_parts)).astype(np.int64)
+
+
+class _DevBuf:
+    """Zero-copy view of a library-owned device buffer as a torch byte tensor (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def column_bytes_tensor(table: _lib.DeviceTable, col: int):
+    """-> (uint8 tensor aliasing the column's Arrow-layout value buffer in HBM, value width in bytes)."""
+    ptr, nbytes, width = table.column_device_buffer(col)
+    dev = torch.device("cuda", table.ctx.device)
+    if nbytes == 0:
+        return torch.empty(0, dtype=torch.uint8, device=dev), width
+    return torch.as_tensor(_DevBuf(ptr, nbytes), device=dev), width
+
+
+def table_from_tensors(ctx: _lib.Context, schema: pa.Schema, tensors: List[torch.Tensor], n_rows: int) -> _lib.DeviceTable:
+    """HBM-resident table from one device tensor per (fixed-width, NULL-free) column; the library copies the buffers
+    (qgpu_table_append_device), so the tensors may be reused afterwards."""
+    from pyarrow.cffi import ffi
+    keep, children = [], []
+    for t in tensors:
+        cb = ffi.new("const void*[]", [ffi.NULL, ffi.cast("void*", t.data_ptr() if t.numel() else 0)])
+        ca = ffi.new("struct ArrowArray*")
+        ca.length, ca.null_count, ca.offset, ca.n_buffers, ca.n_children = n_rows, 0, 0, 2, 0
+        ca.buffers, ca.release = cb, ffi.NULL
+        keep += [cb, ca]
+        children.append(ca)
+    top = ffi.new("struct ArrowArray*")
+    kids = ffi.new("struct ArrowArray*[]", children)
+    topbufs = ffi.new("const void*[]", [ffi.NULL])
+    top.length, top.null_count, top.offset, top.n_buffers, top.n_children = n_rows, 0, 0, 1, len(children)
+    top.buffers, top.children, top.release = topbufs, kids, ffi.NULL
+    dev = _lib.DeviceTable.create(ctx, schema)
+    if n_rows > 0:
+        dev.append_device_struct(_lib.addr(top))
+        dev.column_bytes(0)  # consolidate + synchronise the library's D2D copies before the tensors go away
+    return dev
+
+
+def exchange_columns(columns: List[torch.Tensor], widths: List[int], send_rows: List[int], all_to_all: Callable,
+                     device=None):
+    """The exchange step of a hash repartition, device-agnostic (NCCL on the GPU, gloo in the CPU tests).
+    columns[c]: uint8 tensor holding this rank's rows of column c grouped by destination rank; send_rows[p]: rows
+    going to rank p.  -> (received byte tensors, rows received from every rank)."""
+    send = torch.tensor(send_rows, dtype=torch.int64, device=device)
+    recv = torch.empty_like(send)
+    all_to_all(recv, send, None, None)
+    recv_rows = [int(x) for x in recv.tolist()]
+    n_recv = sum(recv_rows)
+    outs = []
+    for col, w in zip(columns, widths):
+        out = torch.empty(n_recv * w, dtype=torch.uint8, device=col.device)
+        all_to_all(out, col, [r * w for r in recv_rows], [r * w for r in send_rows])
+        outs.append(out)
+    return outs, recv_rows
+
+
+def _dist_all_to_all(out, inp, out_splits, in_splits):
+    import torch.distributed as dist
+    dist.all_to_all_single(out, inp, out_splits, in_splits)
+
+
+def hash_repartition(ctx: _lib.Context, table: _lib.DeviceTable, key_col: int, world: int,
+                     all_to_all: Optional[Callable] = None) -> _lib.DeviceTable:
+    """Every rank: partition its rows by fmix64(key) % world on the GPU (csrc/shard.cu: k_part_hist/k_part_scatter),
+    exchange the per-destination slices of every column with NCCL all-to-all (ncclSend/ncclRecv over NVLink), return
+    the received rows as a new HBM-resident table.  Afterwards equal keys live on exactly one rank, so a purely
+    local aggregate is exact and the whole result is the concatenation of the ranks' results."""
+    dev = torch.device("cuda", ctx.device)
+    stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
+    parted, offs = table.hash_partition(key_col, world)
+    cols, widths = [], []
+    for c in range(len(table.schema)):
+        t, w = column_bytes_tensor(parted, c)
+        cols.append(t)
+        widths.append(w)
+    with torch.cuda.stream(stream):                # ordered after the library's partition kernels
+        outs, recv_rows = exchange_columns(cols, widths, [offs[i + 1] - offs[i] for i in range(world)],
+                                           all_to_all or _dist_all_to_all, device=dev)
+    stream.synchronize()
+    res = table_from_tensors(ctx, table.schema, outs, sum(recv_rows))
+    parted.free()
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
+# group-by results that straddle shards (SURVEY 8e "Q3 joins"): all-gather the per-rank result rows, re-aggregate
+# ------------------------------------------------------------------------------------------------
+def merge_spec_of(plan):
+    """(key output columns, [(output column, merge kind)]) of `Projection(plain columns)? <- HashAggregate`.
+    SUM and COUNT partials merge by SUM, MIN by MIN, MAX by MAX (exact for integers/decimals: wrapping adds are
+    associative); AVG has no mergeable output (use ShardedAggregate, which carries (sum, count))."""
+    from .physical.expr import (AvgAggregateExpr, Column, CountAggregateExpr, MaxAggregateExpr, MinAggregateExpr,
+                                SumAggregateExpr)
+    from .physical.plan import HashAggregate, Projection
+    proj = None
+    node = plan
+    if isinstance(node, Projection):
+        proj, node = node, node.input
+    if not isinstance(node, HashAggregate):
+        raise _lib.QuriousError(1, "InternalError: gather-merge needs (Projection <-) HashAggregate")
+    n_keys = len(node.group_exprs)
+    kinds = []
+    for a in node.aggregate_exprs:
+        if isinstance(a, (SumAggregateExpr, CountAggregateExpr)):
+            kinds.append("sum")
+        elif isinstance(a, MinAggregateExpr):
+            kinds.append("min")
+        elif isinstance(a, MaxAggregateExpr):
+            kinds.append("max")
+        else:
+            raise _lib.QuriousError(1, f"InternalError: {type(a).__name__} partials cannot be merged from result rows")
+    src = list(range(n_keys + len(kinds)))
+    if proj is not None:
+        if not all(isinstance(e, Column) for e in proj.exprs):
+            raise _lib.QuriousError(1, "InternalError: gather-merge needs a Projection of plain columns")
+        src = [e.index for e in proj.exprs]
+    keys = [o for o, s in enumerate(src) if s < n_keys]
+    aggs = [(o, kinds[s - n_keys]) for o, s in enumerate(src) if s >= n_keys]
+    return keys, aggs
+
+
+class GatherMergeAggregate:
+    """Row-range shards whose groups can straddle shard boundaries and are too many for fixed-size state blocks
+    (Q3: ~114k x SF groups, lineitem sorted by l_orderkey so at most world-1 groups straddle):
+        every rank:  the whole local plan, result kept in HBM                    plan.execute_device
+        NCCL:        all-gather of the result columns (ragged: counts first)      dist.all_gather
+        every rank:  re-aggregate the gathered rows by the same keys             HashAggregate over the gathered table
+    Output column order = the plan's."""
+
+    def __init__(self, ctx: _lib.Context, plan, world: int, all_gather_ragged: Optional[Callable] = None):
+        self.ctx, self.plan, self.world = ctx, plan, int(world)
+        self.keys, self.aggs = merge_spec_of(plan)
+        self.gather = all_gather_ragged or _dist_all_gather_ragged
+        self.stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", ctx.device))
+        self._merge_plan = None
+        self._merge_table = None
+
+    def _make_merge_plan(self, table):
+        from .physical.expr import Column, MaxAggregateExpr, MinAggregateExpr, SumAggregateExpr
+        from .physical.plan import HashAggregate, MemoryTable, Projection, Scan
+        schema = self.plan.schema
+        mk = {"sum": SumAggregateExpr, "min": MinAggregateExpr, "max": MaxAggregateExpr}
+        fields = [schema.field(o) for o in self.keys] + [schema.field(o) for o, _ in self.aggs]
+        agg = HashAggregate(pa.schema(fields), Scan(schema, MemoryTable.from_device_table(table), None, None),
+                            [Column(schema.field(o).name, o) for o in self.keys],
+                            [mk[k](Column(schema.field(o).name, o), schema.field(o).type) for o, k in self.aggs])
+        order = self.keys + [o for o, _ in self.aggs]          # position in agg output -> plan output column
+        back = [order.index(o) for o in range(len(schema))]
+        return Projection(schema, agg, [Column(schema.field(o).name, back[o]) for o in range(len(schema))])
+
+    def execute_device(self) -> _lib.DeviceTable:
+        local = self.plan.execute_device(self.ctx)
+        cols, widths = [], []
+        for c in range(len(self.plan.schema)):
+            t, w = column_bytes_tensor(local, c)
+            cols.append(t)
+            widths.append(w)
+        with torch.cuda.stream(self.stream):
+            outs, n = self.gather(cols, widths, local.num_rows, self.world)
+        self.stream.synchronize()
+        gathered = table_from_tensors(self.ctx, self.plan.schema, outs, n)
+        local.free()
+        merged = self._make_merge_plan(gathered).execute_device(self.ctx)
+        gathered.free()
+        return merged
+
+    def execute(self) -> List[pa.RecordBatch]:
+        t = self.execute_device()
+        out = [t.to_batch()] if t.num_rows > 0 else []
+        t.free()
+        return out
+
+
+def _dist_all_gather_ragged(cols, widths, n_rows, world):
+    import torch.distributed as dist
+    dev = cols[0].device if cols else None
+    mine = torch.tensor([n_rows], dtype=torch.int64, device=dev)
+    counts = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, mine)
+    rows = [int(x) for x in counts.tolist()]
+    outs, mx = [], max(rows) if rows else 0
+    for t, w in zip(cols, widths):
+        # equal-size collective on buffers padded to the largest shard (result rows are few), then compaction
+        mine_p = torch.zeros(mx * w, dtype=torch.uint8, device=t.device)
+        mine_p[:t.numel()] = t
+        allp = torch.empty(world * mx * w, dtype=torch.uint8, device=t.device)
+        dist.all_gather_into_tensor(allp, mine_p)
+        outs.append(torch.cat([allp[r * mx * w:r * mx * w + rows[r] * w] for r in range(world)]))
+    return outs, sum(rows)

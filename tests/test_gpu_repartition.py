@@ -1,0 +1,128 @@
+"""Hash repartition and gather-merge on ONE GPU: the N ranks are emulated, the NCCL collectives are
+replaced by slicing / concatenating the same device buffers.  The reference is single-process, so the checks are
+(a) partition ids bit-equal to the host mirror of the partition function, (b) the rows are a permutation of the
+input, (c) the distributed result equals the single-table plan (which the other GPU tests pin to the oracle)."""
+import decimal
+
+import numpy as np
+import pyarrow as pa
+import pytest
+import torch
+
+from oracle import qref
+from qurious_b200 import QuriousError, tpch
+from qurious_b200.distributed import (GatherMergeAggregate, column_bytes_tensor, merge_spec_of, partition_ids_host,
+                                      shard_range, table_from_tensors)
+from qurious_b200.physical.expr import (AvgAggregateExpr, Column, CountAggregateExpr, MaxAggregateExpr, MinAggregateExpr,
+                                        SumAggregateExpr)
+from qurious_b200.physical.plan import HashAggregate, MemoryTable, Scan
+from tests.cases import check_rows, rows_of
+
+pytestmark = pytest.mark.gpu
+
+SCHEMA = pa.schema([("k", pa.int64()), ("v", pa.int64()), ("f", pa.float64()), ("d", pa.date32()),
+                    ("w", pa.decimal128(30, 2))])
+
+
+def make_table(n, groups, seed=3):
+    rng = np.random.default_rng(seed)
+    k = rng.integers(0, max(groups, 1), n).astype(np.int64) * 0x9E3779B97F4A7C15 % (2**63)
+    cols = [pa.array(k), pa.array(rng.integers(-10**6, 10**6, n).astype(np.int64)), pa.array(rng.random(n)),
+            pa.array(rng.integers(0, 20000, n).astype(np.int32), pa.date32()),
+            pa.array([decimal.Decimal(int(x)).scaleb(-2) for x in rng.integers(-10**15, 10**15, n)], pa.decimal128(30, 2))]
+    return MemoryTable.try_new(SCHEMA, [pa.record_batch(cols, schema=SCHEMA)])
+
+
+def groupby_plan(table):
+    K, V, F, W = (Column(n, SCHEMA.get_field_index(n)) for n in ("k", "v", "f", "w"))
+    aggs = [SumAggregateExpr(V, pa.int64()), CountAggregateExpr(V), MinAggregateExpr(V, pa.int64()), MaxAggregateExpr(V, pa.int64()),
+            AvgAggregateExpr(F, pa.float64(), pa.float64()), SumAggregateExpr(W, pa.decimal128(38, 2))]
+    out = pa.schema([("k", pa.int64())] + [(f"a{i}", a.return_type) for i, a in enumerate(aggs)])
+    return HashAggregate(out, Scan(SCHEMA, table, None, None), [K], aggs)
+
+
+@pytest.mark.parametrize("n,n_parts", [(0, 2), (1, 1), (5000, 2), (100_000, 3), (100_000, 8), (33_333, 64)])
+def test_hash_partition_rows_and_ids(gpu_ctx, n, n_parts):
+    t = make_table(n, max(n // 10, 1))
+    dev = t.device_table(gpu_ctx)
+    parted, offs = dev.hash_partition(0, n_parts)
+    assert offs[0] == 0 and offs[-1] == n and all(a <= b for a, b in zip(offs, offs[1:]))
+    got = parted.to_batch() if n else None
+    parted.free()
+    if n == 0:
+        return
+    keys = got.column(0).to_numpy()
+    pid = partition_ids_host(keys, n_parts)
+    for p in range(n_parts):
+        assert (pid[offs[p]:offs[p + 1]] == p).all()
+    src = t.data[0]
+    a = sorted(zip(*[src.column(i).to_pylist() for i in range(len(SCHEMA))]))
+    b = sorted(zip(*[got.column(i).to_pylist() for i in range(len(SCHEMA))]))
+    assert a == b            # the same rows, bit for bit (floats included: they are only moved)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_repartitioned_groupby_equals_single(gpu_ctx, world):
+    n = 60_000
+    t = make_table(n, 7000, seed=world)
+    full = pa.Table.from_batches(t.data).combine_chunks()
+    single = rows_of(groupby_plan(t).execute(gpu_ctx))
+    check_rows("single vs oracle", single, rows_of(qref.execute(groupby_plan(t))), ordered=False)
+    # every emulated rank partitions its row range; "all-to-all" = slice p of every rank's buffers goes to rank p
+    parted = []
+    for r in range(world):
+        lo, hi = shard_range(n, r, world)
+        st = MemoryTable.try_new(SCHEMA, full.slice(lo, hi - lo).to_batches())
+        pt, offs = st.device_table(gpu_ctx).hash_partition(0, world)
+        parted.append((pt, offs, [column_bytes_tensor(pt, c) for c in range(len(SCHEMA))]))
+    rows, seen = [], set()
+    for p in range(world):
+        cols, n_recv = [], 0
+        for c in range(len(SCHEMA)):
+            w = parted[0][2][c][1]
+            cols.append(torch.cat([pt_cols[c][0][offs[p] * w:offs[p + 1] * w] for _, offs, pt_cols in parted]))
+        n_recv = sum(offs[p + 1] - offs[p] for _, offs, _ in parted)
+        local = table_from_tensors(gpu_ctx, SCHEMA, cols, n_recv)
+        got = rows_of(groupby_plan(MemoryTable.from_device_table(local)).execute(gpu_ctx)) if n_recv else []
+        keys = {r_[0] for r_ in got}
+        assert not (keys & seen)          # groups are rank-disjoint after the exchange
+        seen |= keys
+        rows += got
+    check_rows(f"repartitioned x{world}", rows, single, ordered=False)
+
+
+def test_narrowed_decimal_has_no_arrow_buffer(gpu_ctx):
+    schema = pa.schema([("k", pa.int64()), ("p", pa.decimal128(15, 2))])
+    t = MemoryTable.try_new(schema, [pa.record_batch([pa.array([1, 2, 3]), pa.array([decimal.Decimal("1.25")] * 3, pa.decimal128(15, 2))],
+                                                     schema=schema)])
+    dev = t.device_table(gpu_ctx)
+    with pytest.raises(QuriousError):
+        dev.column_device_buffer(1)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_q3_gather_merge_equals_single(gpu_ctx, world):
+    sf = 0.02
+    db = tpch.generate(sf, batch_rows=None)
+    single = rows_of(tpch.q3_plan(db).execute(gpu_ctx))
+    check_rows("q3 vs oracle", single, rows_of(qref.execute(tpch.q3_plan(db))), ordered=False)
+    full = pa.Table.from_batches(db.lineitem.data).combine_chunks()
+    n = full.num_rows
+    plans = []
+    for r in range(world):
+        lo, hi = shard_range(n, r, world)
+        li = MemoryTable.try_new(db.lineitem.schema, full.slice(lo, hi - lo).to_batches())
+        plans.append(tpch.q3_plan(tpch.Database(sf, db.customer, db.orders, li)))
+    assert merge_spec_of(plans[0]) == ([0, 2, 3], [(1, "sum")])
+    locals_ = []
+    for p in plans:                               # phase 1: every rank's local result, kept as byte tensors
+        d = p.execute_device(gpu_ctx)
+        locals_.append(([column_bytes_tensor(d, c)[0].clone() for c in range(len(p.schema))], d.num_rows))
+        d.free()
+    assert sum(nr for _, nr in locals_) >= len(single)
+
+    def fake_gather(cols, widths, n_rows, w):
+        return [torch.cat([l[0][c] for l in locals_]) for c in range(len(cols))], sum(l[1] for l in locals_)
+    for p in plans:                               # phase 2: every rank merges the gathered rows identically
+        got = rows_of(GatherMergeAggregate(gpu_ctx, p, world, all_gather_ragged=fake_gather).execute())
+        check_rows(f"q3 gather-merge x{world}", got, single, ordered=False)

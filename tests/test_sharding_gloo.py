@@ -60,3 +60,42 @@ def test_shard_range_partitions(total, world):
     assert edges[0][0] == 0 and edges[-1][1] == total
     assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
     assert max(h - l for l, h in edges) - min(h - l for l, h in edges) <= 1
+
+
+# ------------------------------------------------------------------------------------------------
+# hash repartition / ragged gather protocols over a real process group (gloo, CPU tensors)
+# ------------------------------------------------------------------------------------------------
+def _repart_worker(rank, world, port, out):
+    from qurious_b200.distributed import _dist_all_gather_ragged, _dist_all_to_all, exchange_columns, partition_ids_host
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(100 + rank)
+    n = 1000 + 37 * rank
+    k = rng.integers(0, 300, n).astype(np.int64) * 7919
+    v = rng.integers(-50, 50, n).astype(np.int32)
+    pid = partition_ids_host(k, world)
+    order = np.argsort(pid, kind="stable")
+    send_rows = [int((pid == p).sum()) for p in range(world)]
+    cols = [torch.from_numpy(k[order].copy()).view(torch.uint8), torch.from_numpy(v[order].copy()).view(torch.uint8)]
+    outs, recv_rows = exchange_columns(cols, [8, 4], send_rows, _dist_all_to_all)
+    rk, rv = outs[0].view(torch.int64).numpy(), outs[1].view(torch.int32).numpy()
+    assert len(rk) == len(rv) == sum(recv_rows)
+    assert (partition_ids_host(rk, world) == rank).all()
+    g, n_all = _dist_all_gather_ragged([torch.from_numpy(rk.copy()).view(torch.uint8)], [8], len(rk), world)
+    out[rank] = (sorted(zip(rk.tolist(), rv.tolist())), sorted(zip(k.tolist(), v.tolist())), n_all,
+                 sorted(g[0].view(torch.int64).tolist()))
+    dist.destroy_process_group()
+
+
+def test_hash_repartition_protocol_gloo():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_repart_worker, args=(world, port, out), nprocs=world, join=True)
+    received = sorted(sum((out[r][0] for r in range(world)), []))
+    sent = sorted(sum((out[r][1] for r in range(world)), []))
+    assert received == sent                                     # nothing lost, nothing duplicated
+    keys = [set(k for k, _ in out[r][0]) for r in range(world)]
+    assert not (keys[0] & keys[1])                              # equal keys meet on exactly one rank
+    assert out[0][2] == out[1][2] == len(sent) and out[0][3] == out[1][3] == sorted(k for k, _ in sent)
