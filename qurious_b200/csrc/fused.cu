@@ -616,6 +616,8 @@ __global__ void __launch_bounds__(F_NT + 32, MODE == FM_DENSE ? 1 : 2) k_fused_s
   fused_main<MODE, GenericBody<MODE>>(p);
 }
 
+#include "radix_agg.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // tile body #2: compile-time specialised on the plan's SHAPE SIGNATURE (operand widths, accumulator
 // kinds / chaining / factor counts); constants (bounds, coefficients, tile offsets) stay runtime
@@ -1291,6 +1293,12 @@ struct FusedPlan {
   int grid = 0;
   FusedKernel spec = nullptr;
   int64_t learned_cap = 0;  // HASH: capacity that held every group last time (skips the growth retries)
+  // RADIX (radix_agg.cuh): usable when the plan is a HASH-mode plan with integer-like keys and few operand values
+  bool radix_ok = false;
+  bool radix_failed = false;  // overflowed or declined (few groups) once on this table: stay on FM_HASH
+  RParams R;                  // comps / comp_of / kind_of filled by the analysis
+  int key_bits[F_MAXK] = {0, 0, 0, 0}, key_shift[F_MAXK] = {0, 0, 0, 0}, key_width[F_MAXK] = {0, 0, 0, 0};
+  std::vector<DColP> key_src;  // source column of every key (type / phys of the decoded key column)
   // validity of the cache
   std::vector<const DCol*> col_ids;
   int64_t n_rows = 0, n_batches = 0;
@@ -1325,6 +1333,7 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
   std::vector<int>& acc_of = fp.acc_of;
   keys.clear();
   specs.clear();
+  fp.key_src.clear();
   acc_of.assign(agg.aggs.size(), -1);
   std::vector<i128> acc_maxabs;
   bool dense_ok = true;
@@ -1434,6 +1443,9 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
       // DENSE: mixed-radix index; HASH: bit-packed code (filled below once the mode is known)
       fk.mult = (uint64_t)dense_groups;  // provisional (dense)
       fk.pad = bits;
+      fp.key_bits[i] = bits;
+      fp.key_width[i] = A.slots[slot].dict ? 0 : phys_width(A.slots[slot].col->phys);
+      fp.key_src.push_back(v.cols[keys[i]->column_ref].base);
       if (dense_ok) {
         dense_groups *= range;
         if (dense_groups > 4096) dense_ok = false;
@@ -1516,6 +1528,32 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
   // chain detection: accumulator k = accumulator k-1 times extra factors (prefix test on the full factor lists)
   {
     std::vector<FAcc> full(P.accs, P.accs + P.n_accs);
+    // RADIX tuple components: the distinct operand values (SUM(v), MIN(v), MAX(v) share one)
+    memset(&fp.R, 0, sizeof(fp.R));
+    fp.R.n_comp = 1;
+    fp.radix_ok = !probe && !keys.empty();
+    for (int k = 0; k < P.n_accs && fp.radix_ok; ++k) {
+      RComp c;
+      memset(&c, 0, sizeof(c));
+      c.is_f64 = full[k].kind == FK_SUMF;
+      c.n_factors = full[k].n_factors;
+      c.coef = full[k].coef;
+      for (int f = 0; f < full[k].n_factors; ++f) c.f[f] = full[k].f[f];
+      int found = -1;
+      for (int j = 0; j + 1 < fp.R.n_comp; ++j)
+        if (memcmp(&fp.R.comp[j], &c, sizeof(c)) == 0) found = j + 1;
+      if (found < 0) {
+        if (fp.R.n_comp >= R_MAXCOMP) {
+          fp.radix_ok = false;
+          break;
+        }
+        fp.R.comp[fp.R.n_comp - 1] = c;
+        found = fp.R.n_comp++;
+      }
+      fp.R.comp_of[k] = found;
+      fp.R.kind_of[k] = full[k].kind;
+    }
+    fp.R.n_accs = P.n_accs;
     for (int k = 1; k < P.n_accs; ++k) {
       const FAcc& prv = full[k - 1];
       FAcc& cur = P.accs[k];
@@ -1569,6 +1607,8 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
     }
     a.unit = (a.kind != FK_SUMF && !a.chain && a.coef == 1 && a.n_factors > 0 && a.f[0].plain) ? 1 : 0;
   }
+  for (int c = 0; c + 1 < fp.R.n_comp; ++c)
+    for (int f = 0; f < fp.R.comp[c].n_factors; ++f) resolve(fp.R.comp[c].f[f].col, &fp.R.comp[c].f[f].off, &fp.R.comp[c].f[f].wk);
   P.stage_bytes = stage_bytes;
   const int NA2 = P.n_accs + 2;
   const int grid_max = ctx->sm_count;
@@ -1594,12 +1634,15 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
     for (int k = 0; k < P.n_keys; ++k) {
       const int bits = P.keys[k].pad;
       P.keys[k].mult = shift >= 64 ? 0 : (1ull << shift);
+      fp.key_shift[k] = shift;
+      if (fp.key_width[k] == 0) fp.radix_ok = false;  // dictionary-coded Utf8 key: FM_HASH only
       shift += bits;
     }
     for (i128 m : acc_maxabs)
       if (m * (i128)n_rows >= LIM62) P.carry = 1;
   }
   for (int k = 0; k < P.n_keys; ++k) P.keys[k].pad = 0;
+  if (P.mode != FM_HASH || P.carry) fp.radix_ok = false;
   int ctas_per_sm = 1;
   int stages = (int)(((size_t)F_SMEM_MAX - 128 - priv_bytes) / stage_bytes);
   stages = std::min(stages, 4);
@@ -1621,6 +1664,179 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
   return true;
 }
 
+
+
+// ------------------------------------------------------------------------------------------------
+// RADIX mode driver (kernels: radix_agg.cuh).  Returns false when the radix path declines (few groups: the
+// L2-resident FM_HASH table is the better plan) or overflowed (estimate off / skewed bucket): FM_HASH then runs.
+// ------------------------------------------------------------------------------------------------
+static bool run_radix(PlanNode& agg, const View& v, FusedPlan& fp, View* out) {
+  Ctx* ctx = agg.ctx;
+  const FParams& P = fp.P;
+  const char* mode_env = getenv("QGPU_RADIX");  // "off": never, "force": whenever the shape allows (tests)
+  const bool force = mode_env && strcmp(mode_env, "force") == 0;
+  if (mode_env && strcmp(mode_env, "off") == 0) return false;
+  const int64_t n_rows = P.n_rows;
+  if (!force && n_rows < ((int64_t)1 << 24)) return false;
+  RParams R = fp.R;
+  // ---- pass 0: level-1 histogram + HyperLogLog sketch ---------------------------------------------------------
+  // layout of the small state block: hll[4096] u32 | hist1[256] u32 | tpre[257] u32 (+pad) | off1[257] u64 | cur1[256] u64 |
+  //                                  n_out u64 | overflow int
+  const size_t o_hll = 0, o_hist1 = o_hll + R_HLL_M * 4, o_tpre = o_hist1 + R_P1 * 4, o_off1 = o_tpre + 260 * 4,
+               o_cur1 = o_off1 + 257 * 8, o_nout = o_cur1 + 256 * 8, o_ovf = o_nout + 8, st_bytes = o_ovf + 8;
+  DBufP st = ctx->alloc_zero(st_bytes);
+  char* sp = (char*)st->ptr;
+  R.hll = (unsigned int*)(sp + o_hll);
+  R.hist1 = (unsigned int*)(sp + o_hist1);
+  R.tpre = (unsigned int*)(sp + o_tpre);
+  R.off1 = (unsigned long long*)(sp + o_off1);
+  R.cur1 = (unsigned long long*)(sp + o_cur1);
+  R.n_out = (unsigned long long*)(sp + o_nout);
+  R.overflow = (int*)(sp + o_ovf);
+  const int grid1 = (int)std::min<int64_t>(P.n_tiles, (int64_t)ctx->sm_count * 8);
+  LAUNCH(ctx, k_radix_hist1, grid1, R_NT, 0, P, R.hist1, R.hll);
+  LAUNCH(ctx, k_radix_scan1, 1, R_P1, 0, R.hist1, R.off1, R.cur1, R.tpre);
+  std::vector<unsigned char> hst(o_cur1);
+  ctx->d2h_sync(hst.data(), sp, o_cur1);
+  const double est = hll_estimate((const unsigned int*)(hst.data() + o_hll));
+  const int64_t n_tuples = (int64_t)((const unsigned long long*)(hst.data() + o_off1))[R_P1];
+  const unsigned int n_tiles2 = ((const unsigned int*)(hst.data() + o_tpre))[R_P1];
+  ctx->trace("radix: hist1 + sketch");
+  if (n_tuples == 0) return false;
+  // ---- plan: level-2 fan-out, table capacity, output size --------------------------------------------------------
+  // final pass shared memory: 16 B per table slot (key, row count, first staged row) + per staged row 8 B per operand
+  // value and 4 B (slot, rank); the table should stay below ~45 % load, the staging area needs ~15 % headroom
+  const size_t smem_budget = (size_t)F_SMEM_MAX - 256;
+  const size_t row_bytes = 8 * (size_t)(R.n_comp - 1) + 4;
+  const double groups = std::min(est * 1.05 + 64.0, (double)n_tuples);
+  if (!force && groups < 4.0e6) {
+    // the hash table stays (mostly) L2-resident: FM_HASH, sized from the estimate so that it does not grow
+    int64_t c = 1 << 12;
+    while ((double)c < 2.2 * groups) c <<= 1;
+    fp.learned_cap = std::max(fp.learned_cap, c);
+    fp.radix_failed = true;  // same table, same answer: do not sketch again
+    return false;
+  }
+  int b2 = 0, cap = 0, row_cap = 0;
+  for (b2 = 1; b2 <= R_MAXB2; ++b2) {
+    const double nb = (double)((int64_t)R_P1 << b2);
+    const double g_b = groups / nb, r_b = (double)n_tuples / nb;
+    cap = 64;
+    while (cap < 4096 && g_b > 0.45 * cap) cap *= 2;
+    if (g_b > 0.45 * cap) continue;
+    const size_t table = (size_t)(cap + 1) * 16;
+    if (table + 1024 >= smem_budget) continue;
+    row_cap = (int)std::min<size_t>((smem_budget - table) / row_bytes, (size_t)1 << 18);
+    if ((double)row_cap >= r_b * 1.15 + 6.0 * sqrt(r_b) + 64.0) break;
+  }
+  if (b2 > R_MAXB2) return false;
+  if (const char* tc = getenv("QGPU_RADIX_TEST_CAP")) {  // tests: provoke the overflow -> FM_HASH fallback
+    cap = std::max(64, std::min(4096, atoi(tc)));
+    b2 = 1;
+    row_cap = (int)std::min<size_t>((smem_budget - (size_t)(cap + 1) * 16) / row_bytes, (size_t)1 << 18);
+  }
+  R.b2 = b2;
+  R.cap = cap;
+  R.row_cap = row_cap;
+  const int64_t n_buckets = (int64_t)R_P1 << b2;
+  const int64_t out_cap = std::min<int64_t>(n_tuples, (int64_t)(est * 1.15) + 65536);
+  R.out_cap = out_cap;
+  std::vector<DBufP> keep;
+  for (int c = 0; c < R.n_comp; ++c) {
+    DBufP a = ctx->alloc((size_t)n_tuples * 8 + 64), b = ctx->alloc((size_t)n_tuples * 8 + 64);
+    R.tup_a[c] = (unsigned long long*)a->ptr;
+    R.tup_b[c] = (unsigned long long*)b->ptr;
+    keep.push_back(a);
+    keep.push_back(b);
+  }
+  DBufP hist2 = ctx->alloc_zero((size_t)n_buckets * 4), off2 = ctx->alloc((size_t)(n_buckets + 1) * 8), cur2 = ctx->alloc((size_t)n_buckets * 8);
+  R.hist2 = (unsigned int*)hist2->ptr;
+  R.off2 = (unsigned long long*)off2->ptr;
+  R.cur2 = (unsigned long long*)cur2->ptr;
+  DBufP out_code = ctx->alloc((size_t)out_cap * 8 + 64), out_cnt = ctx->alloc((size_t)out_cap * 8 + 64);
+  std::vector<DBufP> out_acc;
+  R.out_code = (unsigned long long*)out_code->ptr;
+  R.out_cnt = (unsigned long long*)out_cnt->ptr;
+  for (int k = 0; k < P.n_accs; ++k) {
+    out_acc.push_back(ctx->alloc((size_t)out_cap * 8 + 64));
+    R.out_acc[k] = (unsigned long long*)out_acc.back()->ptr;
+  }
+  // ---- passes ----------------------------------------------------------------------------------------------------
+  const size_t sc_smem = (size_t)R.n_comp * R_T * 8 + 512 * 8 + 512 * 4 * 2 + (size_t)R_T * 2;
+  CUDA_CHECK(cudaFuncSetAttribute(k_radix_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
+  CUDA_CHECK(cudaFuncSetAttribute(k_radix_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
+  const int sc_per_sm = (2 * (sc_smem + 1024 + 64) <= (size_t)233472) ? 2 : 1;
+  const int64_t tiles1 = (n_rows + R_T - 1) / R_T;
+  LAUNCH(ctx, k_radix_scatter<1>, (int)std::min<int64_t>(tiles1, (int64_t)ctx->sm_count * sc_per_sm), R_NT, sc_smem, P, R);
+  LAUNCH(ctx, k_radix_hist2, (int)std::min<int64_t>(std::max<int64_t>(n_tiles2, 1), (int64_t)ctx->sm_count * 8), R_NT, 0, R);
+  LAUNCH(ctx, k_radix_scan2, 1, 1024, 0, R.hist2, (int)n_buckets, R.off2, R.cur2);
+  LAUNCH(ctx, k_radix_scatter<2>, (int)std::min<int64_t>(std::max<int64_t>(n_tiles2, 1), (int64_t)ctx->sm_count * sc_per_sm), R_NT, sc_smem,
+         P, R);
+  const size_t ag_smem = (size_t)(cap + 1) * 16 + (size_t)row_cap * row_bytes + 64;
+  CUDA_CHECK(cudaFuncSetAttribute(k_radix_agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ag_smem));
+  LAUNCH(ctx, k_radix_agg, (int)std::min<int64_t>(n_buckets, (int64_t)ctx->sm_count), R_AGG_NT, ag_smem, R);
+  unsigned long long fin[2];
+  ctx->d2h_sync(fin, sp + o_nout, 16);
+  ctx->trace("radix: partition passes + aggregate");
+  const int64_t n_groups = (int64_t)fin[0];
+  if ((int)fin[1] != 0) {
+    fp.radix_failed = true;  // FM_HASH from now on (the results of this attempt are discarded)
+    return false;
+  }
+  keep.clear();
+  // ---- key columns from the packed codes --------------------------------------------------------------------------
+  RKeys rk;
+  memset(&rk, 0, sizeof(rk));
+  rk.n_keys = P.n_keys;
+  std::vector<DColP> key_cols;
+  for (int k = 0; k < P.n_keys; ++k) {
+    auto d = std::make_shared<DCol>();
+    d->type = fp.key_src[k]->type;
+    d->phys = fp.key_src[k]->phys;
+    d->length = n_groups;
+    d->null_count = 0;
+    d->data = ctx->alloc(std::max<size_t>((size_t)n_groups * fp.key_width[k], 16));
+    rk.shift[k] = fp.key_shift[k];
+    rk.bits[k] = fp.key_bits[k];
+    rk.width[k] = fp.key_width[k];
+    rk.base[k] = P.keys[k].base;
+    rk.out[k] = d->data->ptr;
+    key_cols.push_back(d);
+  }
+  if (n_groups > 0) LAUNCH(ctx, k_radix_keys, grid_for(ctx, n_groups, 256), 256, 0, (const unsigned long long*)out_code->ptr, n_groups, rk);
+  for (auto& kc : key_cols)
+    if (kc->phys == PH_D64) kc = materialize_arrow(ctx, {kc, nullptr}, n_groups);
+  // ---- GroupAccs ----------------------------------------------------------------------------------------------------
+  GroupAccs accs;
+  accs.n_groups = n_groups;
+  accs.unordered = true;
+  for (size_t i = 0; i < fp.specs.size(); ++i) {
+    const int k = fp.acc_of[i];
+    int ak = AK_COUNT;
+    if (k >= 0) {
+      const int fk = P.accs[k].kind;
+      const VClass vc = class_of(fp.specs[i].arg->result_type);
+      if (fk == FK_SUMF) ak = AK_SUM_F64;
+      else if (fk == FK_SUM) ak = vc == VC_DEC ? AK_SUM_DEC : AK_SUM_I64;
+      else if (vc == VC_DEC) ak = fk == FK_MIN ? AK_MIN_DEC : AK_MAX_DEC;
+      else if (vc == VC_UINT) ak = fk == FK_MIN ? AK_MIN_U64 : AK_MAX_U64;
+      else ak = fk == FK_MIN ? AK_MIN_I64 : AK_MAX_I64;
+      accs.lo.push_back(out_acc[k]);
+    } else {
+      accs.lo.push_back(out_cnt);
+    }
+    accs.hi.push_back(nullptr);  // no carry in this mode: the high word is the sign extension
+    accs.kind.push_back(ak);
+    accs.cnt.push_back(out_cnt);
+  }
+  agg.strategy = "fused_scan_agg[radix-partitioned: 256 x " + std::to_string(1 << b2) + " buckets, smem table " + std::to_string(cap) +
+                 " slots / " + std::to_string(row_cap) + " rows, " + std::to_string(R.n_comp) + " x 8 B tuples, " + std::to_string(P.n_cols) + " cols, " +
+                 std::to_string(P.n_pred) + " range preds, " + std::to_string(P.n_accs) + " accs, est " +
+                 std::to_string((int64_t)est) + " groups]";
+  *out = finish_aggregate(ctx, v, fp.keys, fp.specs, agg.schema, accs, &key_cols, nullptr);
+  ctx->trace("radix: finish_aggregate");
+  return true;
+}
 
 static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
   Ctx* ctx = agg.ctx;
@@ -1671,6 +1887,10 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
       LAUNCH(ctx, k_fused_scan_agg<FM_DENSE>, grid, F_NT + 32, smem_bytes, P);
     }
   } else {
+    if (fp.radix_ok && !fp.radix_failed && !agg.defer) {
+      View rv;
+      if (run_radix(agg, v, fp, &rv)) return rv;
+    }
     // capacity: bounded by the key domain and by the row count; grown x8 on overflow
     i128 domain = total_bits >= 63 ? ((i128)1 << 63) : ((i128)1 << total_bits);
     int64_t max_groups = (int64_t)std::min<i128>(domain, (i128)n_rows);

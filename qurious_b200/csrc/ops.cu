@@ -311,6 +311,13 @@ __device__ __forceinline__ double key_to_f64(long long k) {
   return c.d;
 }
 
+// high word of an accumulator: stored, or (hi == nullptr) the sign extension of lo (0 for f64 / unsigned kinds)
+__device__ __forceinline__ unsigned long long fin_hi(const FinSpec& f, int64_t g, unsigned long long lo) {
+  if (f.hi) return f.hi[g];
+  if (f.kind == AK_SUM_F64 || f.kind == AK_MIN_F64 || f.kind == AK_MAX_F64 || f.kind == AK_MIN_U64 || f.kind == AK_MAX_U64) return 0;
+  return ((long long)lo < 0) ? ~0ull : 0ull;
+}
+
 struct FinAll {
   int n_aggs;
   int pad;
@@ -346,14 +353,14 @@ __global__ void __launch_bounds__(256) k_agg_finalize(const __grid_constant__ Fi
         case QGPU_AGG_SUM:
           valid = cnt > 0;
           lo = f.lo[g];
-          hi = f.hi ? f.hi[g] : 0;
+          hi = fin_hi(f, g, lo);
           break;
         case QGPU_AGG_MIN:
         case QGPU_AGG_MAX:
           // an all-NULL input leaves the type's MAX/MIN sentinel, not NULL
           valid = !f.no_input;
           lo = f.lo[g];
-          hi = f.hi ? f.hi[g] : 0;
+          hi = fin_hi(f, g, lo);
           if (f.kind == AK_MIN_F64 || f.kind == AK_MAX_F64) {
             union { unsigned long long u; double d; } c;
             c.d = key_to_f64((long long)lo);
@@ -370,7 +377,7 @@ __global__ void __launch_bounds__(256) k_agg_finalize(const __grid_constant__ Fi
               valid = true;
             } else {
               // avg.rs:89-116: value = sum * 10^(target_scale - sum_scale) (checked); result = value / count
-              i128 sum = (i128)(((u128)f.hi[g] << 64) | (u128)f.lo[g]);
+              i128 sum = (i128)(((u128)fin_hi(f, g, f.lo[g]) << 64) | (u128)f.lo[g]);
               i128 mul = pow10_i128(f.target_scale - f.sum_scale);
               i128 value = sum * mul;
               bool ovf = sum != 0 && value / mul != sum;
@@ -628,7 +635,8 @@ View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<C
   // ---- group order: first occurrence (the reference's order is unspecified) --
   IdxP order;        // output position -> gid
   IdxP first_idx;    // output position -> first input row of the group
-  if (grouped) {
+  if (accs.unordered && !key_cols) throw_internal("unordered group output needs explicit key columns");
+  if (grouped && !accs.unordered) {
     order = std::make_shared<IdxVec>();
     order->length = n_max;
     order->buf = ctx->alloc(std::max<size_t>((size_t)n_max * 8, 8));
@@ -659,7 +667,7 @@ View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<C
   FinAll all;
   memset(&all, 0, sizeof(all));
   all.n_aggs = (int)aggs.size();
-  all.order = grouped ? (const long long*)order->buf->ptr : nullptr;
+  all.order = (grouped && order) ? (const long long*)order->buf->ptr : nullptr;
   std::vector<DColP> cols;
   const int64_t max_words = (n_max + 31) >> 5;
   for (size_t i = 0; i < aggs.size(); ++i) {
@@ -686,7 +694,7 @@ View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<C
     f.compat_avg = ctx->compat_avg_precision ? 1 : 0;
     f.no_input = (!grouped && input.num_batches == 0) ? 1 : 0;
     f.lo = (const unsigned long long*)accs.lo[i]->ptr;
-    f.hi = (const unsigned long long*)accs.hi[i]->ptr;
+    f.hi = accs.hi[i] ? (const unsigned long long*)accs.hi[i]->ptr : nullptr;
     f.cnt = (const unsigned long long*)accs.cnt[i]->ptr;
     f.out = col->data->ptr;
     f.out_valid = (uint32_t*)col->validity->ptr;
@@ -719,8 +727,10 @@ View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<C
   out.num_batches = 1;
   // ---- key columns: values of the group's first row (hash.rs:62-68) ---------------------------------
   if (grouped) {
-    order->length = n_groups;
-    first_idx->length = n_groups;
+    if (order) {
+      order->length = n_groups;
+      first_idx->length = n_groups;
+    }
     View firsts;
     if (!key_cols) firsts = apply_selection_view(ctx, input, first_idx);
     for (size_t i = 0; i < keys.size(); ++i) {

@@ -22,11 +22,15 @@ enum AccKind : int {
 struct GroupAccs {
   int64_t n_groups = 0;
   std::vector<int> kind;            // AccKind per aggregate
-  std::vector<DBufP> lo, hi, cnt;   // per aggregate: u64[n_groups] each (cnt = number of non-NULL inputs)
+  std::vector<DBufP> lo, hi, cnt;   // per aggregate: u64[n_groups] each (cnt = number of non-NULL inputs); hi may be
+                                    // null: the high word is then the sign extension of lo (0 for f64 / unsigned kinds)
   DBufP first_row;                  // i64[n_groups]: first input row of the group
   // optional: the actual group count is still on the device (int64); n_groups is then an upper bound and
   // finish_aggregate reads the count together with its own flags in ONE device->host copy
   DBufP n_groups_dev;
+  // unordered: keep the producer's group order (no first-occurrence ranking; needs key_cols).  The reference's
+  // order is unspecified (hash.rs:98); the radix-partitioned aggregate uses this for 10^8-group results.
+  bool unordered = false;
   unsigned long long side_word = 0;  // out: the word following the key NULL counts (see finish_aggregate)
 };
 // key_cols (optional): the group key VALUES as gid-indexed device columns (sharded execution: the first row of a

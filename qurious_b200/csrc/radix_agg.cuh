@@ -1,0 +1,629 @@
+// radix_agg.cuh -- included by fused.cu (inside namespace qgpu, after the FParams helpers).
+//
+// High-cardinality group-by (BASELINE.json configs[3]: 1 B rows / 100 M groups) as a RADIX-PARTITIONED aggregate:
+// the HBM-resident hash table of FM_HASH costs one random 64 B read-modify-write (and ~7 L2 atomics) per row once
+// the table outgrows L2; here the rows are instead streamed twice through a partitioning pass until every bucket
+// holds few enough groups for a SHARED-MEMORY table, so that all random accesses stay on chip:
+//
+//   k_radix_hist1    scan (predicate, packed key) -> 256-bin histogram of the hash's top byte + HyperLogLog sketch
+//                    (the group-count estimate picks level-2 fan-out, table capacity and output sizes)
+//   k_radix_scan1    bucket offsets / cursors / bucket-aligned tile list
+//   k_radix_scatter<1>  scan again, materialise tuples (code, operand values) and scatter them into the 256
+//                    level-1 buckets: tile of 4096 tuples -> shared-memory counting sort (unordered ranks from
+//                    shared atomics) -> one global reservation per (tile, bucket) -> coalesced run write-out
+//   k_radix_hist2    per level-1 bucket: histogram of the next b2 hash bits
+//   k_radix_scan2    offsets of the 256 << b2 final buckets
+//   k_radix_scatter<2>  same scatter, tuples -> final buckets
+//   k_radix_agg      one CTA per final bucket: rows counting-sorted by group in shared memory (key table claimed
+//                    with 64-bit CAS, ranks from native 32-bit shared atomics), one thread reduces each group
+//                    sequentially in registers and writes it straight to the group arrays
+//   k_radix_keys     packed code -> key columns
+//
+// Semantics are those of FM_HASH (hash.rs:45-107,138-170 with grouping by key equality);
+// output order is the bucket order (the reference's order is unspecified, quirk Q2).  Anything that does not fit
+// (estimate wrong, skewed bucket overflowing its table) raises a flag and the caller re-runs FM_HASH.
+
+constexpr int R_NT = 256;                 // threads per CTA of the partition kernels (== F_NT: load_rows mapping)
+constexpr int R_SUB = 4;                  // sub-tiles of F_T rows
+constexpr int R_T = F_T * R_SUB;          // tuples per tile
+constexpr int R_B1 = 8;                   // level-1 digit: top 8 hash bits
+constexpr int R_P1 = 1 << R_B1;
+constexpr int R_MAXB2 = 9;
+constexpr int R_MAXCOMP = 6;              // tuple components (code + operand values) that fit the sort tile
+constexpr int R_HLL_BITS = 12;
+constexpr int R_HLL_M = 1 << R_HLL_BITS;
+constexpr int R_AGG_NT = 1024;            // threads per CTA of the final pass
+constexpr int R_U = 8;                    // final pass: global loads in flight per thread
+static_assert(R_NT == F_NT, "load_rows_g uses the F_NT row mapping");
+
+struct RComp {           // operand value = coef * prod(a_i + b_i * x_i) (int64, proven not to overflow) or raw f64 bits
+  int32_t is_f64, n_factors;
+  int64_t coef;
+  FFactor f[F_MAXF];
+};
+
+struct RParams {
+  int32_t n_comp, b2, cap, n_accs;
+  int32_t row_cap, pad0;     // final pass: rows a bucket may hold (staging area)
+  int32_t comp_of[F_MAXA];   // accumulator -> tuple component (>= 1)
+  int32_t kind_of[F_MAXA];
+  RComp comp[R_MAXCOMP - 1]; // component c >= 1 is comp[c - 1]
+  unsigned long long* tup_a[R_MAXCOMP];
+  unsigned long long* tup_b[R_MAXCOMP];
+  unsigned int* hist1;        // [256]
+  unsigned int* hll;          // [4096]
+  unsigned long long* off1;   // [257]
+  unsigned long long* cur1;   // [256]
+  unsigned int* tpre;         // [257] first tile of every level-1 bucket (tiles of R_T tuples, bucket-aligned)
+  unsigned int* hist2;        // [256 << b2]
+  unsigned long long* off2;   // [(256 << b2) + 1]
+  unsigned long long* cur2;   // [256 << b2]
+  unsigned long long* out_code;
+  unsigned long long* out_acc[F_MAXA];
+  unsigned long long* out_cnt;
+  unsigned long long* n_out;
+  int64_t out_cap;
+  int* overflow;
+};
+
+// guarded variant of load_rows for operands read straight from global memory (no staged tile behind the tail)
+__device__ __forceinline__ void load_rows_g(const unsigned char* col, uint32_t wk, int tid, int rows, int64_t (&x)[F_R]) {
+#pragma unroll
+  for (int j = 0; j < F_R; ++j) {
+    const int r = j * F_NT + tid;
+    int64_t v = 0;
+    if (r < rows) {
+      switch (wk) {
+        case 8: v = ((const int64_t*)col)[r]; break;
+        case 4: v = (int64_t)((const int32_t*)col)[r]; break;
+        case 4 | 256: v = (int64_t)((const uint32_t*)col)[r]; break;
+        case 2: v = (int64_t)((const int16_t*)col)[r]; break;
+        case 2 | 256: v = (int64_t)((const uint16_t*)col)[r]; break;
+        case 1: v = (int64_t)((const int8_t*)col)[r]; break;
+        default: v = (int64_t)((const uint8_t*)col)[r]; break;
+      }
+    }
+    x[j] = v;
+  }
+}
+__device__ __forceinline__ const unsigned char* gcol(const FParams& p, int col, int64_t row0) {
+  return p.cols[col].ptr + (size_t)row0 * p.cols[col].width;
+}
+
+// predicate + packed key of the F_R rows this thread owns in the sub-tile starting at row0
+__device__ __forceinline__ uint32_t r_pass_code(const FParams& p, int64_t row0, int rows, int tid, uint64_t (&code)[F_R]) {
+  uint32_t pass = 0;
+#pragma unroll
+  for (int j = 0; j < F_R; ++j)
+    if (j * F_NT + tid < rows) pass |= 1u << j;
+#pragma unroll 1
+  for (int k = 0; k < p.n_pred; ++k) {
+    int64_t x[F_R];
+    load_rows_g(gcol(p, p.pred[k].col, row0), p.pred[k].wk, tid, rows, x);
+    const uint64_t lo = (uint64_t)p.pred[k].lo, span = p.pred[k].span;
+#pragma unroll
+    for (int j = 0; j < F_R; ++j)
+      if (((uint64_t)x[j] - lo) > span) pass &= ~(1u << j);
+  }
+#pragma unroll
+  for (int j = 0; j < F_R; ++j) code[j] = 0;
+#pragma unroll 1
+  for (int k = 0; k < p.n_keys; ++k) {
+    int64_t x[F_R];
+    load_rows_g(gcol(p, p.keys[k].col, row0), p.keys[k].wk, tid, rows, x);
+    const uint64_t base = (uint64_t)p.keys[k].base, mult = p.keys[k].mult;
+#pragma unroll
+    for (int j = 0; j < F_R; ++j) code[j] += ((uint64_t)x[j] - base) * mult;
+  }
+  return pass;
+}
+
+__global__ void __launch_bounds__(R_NT) k_radix_hist1(const __grid_constant__ FParams p, unsigned int* __restrict__ hist1,
+                                                      unsigned int* __restrict__ hll) {
+  __shared__ unsigned int sh[R_P1];
+  __shared__ unsigned int sl[R_HLL_M];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < R_P1; i += R_NT) sh[i] = 0;
+  for (int i = tid; i < R_HLL_M; i += R_NT) sl[i] = 0;
+  __syncthreads();
+  for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+    const int64_t row0 = t * F_T;
+    const int rows = (int)min((int64_t)F_T, p.n_rows - row0);
+    uint64_t code[F_R];
+    const uint32_t pass = r_pass_code(p, row0, rows, tid, code);
+#pragma unroll
+    for (int j = 0; j < F_R; ++j) {
+      if (!((pass >> j) & 1)) continue;
+      const uint64_t h = fmix64(code[j]);
+      atomicAdd(&sh[h >> (64 - R_B1)], 1u);
+      // HyperLogLog: register = low 12 bits, rank = leading zeros of bits 12..51 (40 bits) + 1
+      const uint64_t w = (h >> R_HLL_BITS) & ((1ull << 40) - 1);
+      const unsigned rho = w ? (unsigned)(__clzll((long long)w) - 24 + 1) : 41u;
+      atomicMax(&sl[h & (R_HLL_M - 1)], rho);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < R_P1; i += R_NT)
+    if (sh[i]) atomicAdd(&hist1[i], sh[i]);
+  for (int i = tid; i < R_HLL_M; i += R_NT)
+    if (sl[i]) atomicMax(&hll[i], sl[i]);
+}
+
+// one CTA of 256 threads: thread b owns level-1 bucket b
+__global__ void __launch_bounds__(R_P1) k_radix_scan1(const unsigned int* __restrict__ hist1, unsigned long long* __restrict__ off1,
+                                                      unsigned long long* __restrict__ cur1, unsigned int* __restrict__ tpre) {
+  __shared__ unsigned long long a[R_P1];
+  __shared__ unsigned int b[R_P1];
+  const int t = threadIdx.x;
+  const unsigned int h = hist1[t];
+  a[t] = h;
+  b[t] = (h + R_T - 1) / R_T;
+  __syncthreads();
+  for (int d = 1; d < R_P1; d <<= 1) {
+    const unsigned long long x = t >= d ? a[t - d] : 0;
+    const unsigned int y = t >= d ? b[t - d] : 0;
+    __syncthreads();
+    a[t] += x;
+    b[t] += y;
+    __syncthreads();
+  }
+  off1[t + 1] = a[t];
+  tpre[t + 1] = b[t];
+  cur1[t] = a[t] - h;
+  if (t == 0) {
+    off1[0] = 0;
+    tpre[0] = 0;
+  }
+}
+
+// tile -> (level-1 bucket, first tuple, tuple count) through the bucket-aligned tile list
+__device__ __forceinline__ void r_tile_of(const RParams& r, unsigned int tile, int* b1, int64_t* base, int* rows) {
+  int lo = 0, hi = R_P1;  // largest b with tpre[b] <= tile
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (r.tpre[mid] <= tile) lo = mid;
+    else hi = mid;
+  }
+  *b1 = lo;
+  const int64_t start = (int64_t)r.off1[lo] + (int64_t)(tile - r.tpre[lo]) * R_T;
+  *base = start;
+  *rows = (int)min((int64_t)R_T, (int64_t)r.off1[lo + 1] - start);
+}
+
+// LEVEL 1: input rows -> tuples in level-1 buckets.  LEVEL 2: level-1 tuples -> final buckets.
+// dynamic shared memory: sorted[n_comp][R_T] u64 | gbase[512] u64 | hist[512] u32 | toff[512] u32 | bin[R_T] u16
+template <int LEVEL>
+__global__ void __launch_bounds__(R_NT, 2) k_radix_scatter(const __grid_constant__ FParams p, const __grid_constant__ RParams r) {
+  extern __shared__ __align__(16) unsigned char rsm[];
+  unsigned long long* sorted = (unsigned long long*)rsm;
+  unsigned long long* gbase = sorted + (size_t)r.n_comp * R_T;
+  unsigned int* hist = (unsigned int*)(gbase + 512);
+  unsigned int* toff = hist + 512;
+  unsigned short* bin = (unsigned short*)(toff + 512);
+  __shared__ unsigned int warp_tot[R_NT / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NB = LEVEL == 1 ? R_P1 : (1 << r.b2);
+  const int shift = LEVEL == 1 ? (64 - R_B1) : (64 - R_B1 - r.b2);
+  const unsigned int n_tiles = LEVEL == 1 ? (unsigned int)((p.n_rows + R_T - 1) / R_T) : r.tpre[R_P1];
+  unsigned long long* const cursor = LEVEL == 1 ? r.cur1 : r.cur2;
+  unsigned long long* const* out = LEVEL == 1 ? r.tup_a : r.tup_b;
+
+  for (unsigned int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    int b1 = 0, rows;
+    int64_t base;
+    if (LEVEL == 1) {
+      base = (int64_t)t * R_T;
+      rows = (int)min((int64_t)R_T, p.n_rows - base);
+    } else {
+      r_tile_of(r, t, &b1, &base, &rows);
+    }
+    for (int i = tid; i < NB; i += R_NT) hist[i] = 0;
+    __syncthreads();
+    // ---- phase 1: digit + unordered rank of every tuple (shared atomics) ------------------------------------
+    uint64_t code[R_SUB][F_R];
+    uint32_t pr[R_SUB][F_R];
+#pragma unroll
+    for (int s = 0; s < R_SUB; ++s) {
+      const int srows = max(0, min(F_T, rows - s * F_T));
+      uint32_t pass;
+      if (LEVEL == 1) {
+        pass = srows > 0 ? r_pass_code(p, base + s * F_T, srows, tid, code[s]) : 0u;
+      } else {
+        pass = 0;
+#pragma unroll
+        for (int j = 0; j < F_R; ++j) {
+          const int i = j * F_NT + tid;
+          code[s][j] = 0;
+          if (i < srows) {
+            code[s][j] = r.tup_a[0][base + s * F_T + i];
+            pass |= 1u << j;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < F_R; ++j) {
+        pr[s][j] = 0xffffffffu;
+        if ((pass >> j) & 1) {
+          const unsigned d = (unsigned)(fmix64(code[s][j]) >> shift) & (unsigned)(NB - 1);
+          pr[s][j] = (d << 16) | atomicAdd(&hist[d], 1u);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- exclusive scan of the histogram (2 bins per thread) + one global reservation per non-empty bin --------
+    {
+      const unsigned h0 = 2 * tid < NB ? hist[2 * tid] : 0u, h1 = 2 * tid + 1 < NB ? hist[2 * tid + 1] : 0u;
+      unsigned incl = h0 + h1;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      if (lane == 31) warp_tot[warp] = incl;
+      __syncthreads();
+      unsigned wbase = 0;
+#pragma unroll
+      for (int w = 0; w < R_NT / 32; ++w)
+        if (w < warp) wbase += warp_tot[w];
+      const unsigned excl = wbase + incl - (h0 + h1);
+      if (2 * tid < NB) {
+        toff[2 * tid] = excl;
+        if (h0) gbase[2 * tid] = atomicAdd(&cursor[(LEVEL == 1 ? 0 : (b1 << r.b2)) + 2 * tid], (unsigned long long)h0);
+      }
+      if (2 * tid + 1 < NB) {
+        toff[2 * tid + 1] = excl + h0;
+        if (h1) gbase[2 * tid + 1] = atomicAdd(&cursor[(LEVEL == 1 ? 0 : (b1 << r.b2)) + 2 * tid + 1], (unsigned long long)h1);
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: tuples into the shared-memory tile, grouped by bin ---------------------------------------------
+#pragma unroll
+    for (int s = 0; s < R_SUB; ++s) {
+      const int srows = max(0, min(F_T, rows - s * F_T));
+      if (srows <= 0) continue;
+      uint32_t pos[F_R];
+#pragma unroll
+      for (int j = 0; j < F_R; ++j) {
+        pos[j] = 0xffffffffu;
+        if (pr[s][j] != 0xffffffffu) {
+          const unsigned d = pr[s][j] >> 16;
+          pos[j] = toff[d] + (pr[s][j] & 0xffffu);
+          sorted[pos[j]] = code[s][j];
+          bin[pos[j]] = (unsigned short)d;
+        }
+      }
+#pragma unroll 1
+      for (int c = 1; c < r.n_comp; ++c) {
+        int64_t v[F_R];
+        if (LEVEL == 1) {
+          const RComp& C = r.comp[c - 1];
+          const int64_t row0 = base + s * F_T;
+          if (C.is_f64) {
+            load_rows_g(gcol(p, C.f[0].col, row0), C.f[0].wk, tid, srows, v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < F_R; ++j) v[j] = C.coef;
+#pragma unroll 1
+            for (int f = 0; f < C.n_factors; ++f) {
+              int64_t x[F_R];
+              load_rows_g(gcol(p, C.f[f].col, row0), C.f[f].wk, tid, srows, x);
+              const int64_t fa = C.f[f].a, fb = C.f[f].b;
+#pragma unroll
+              for (int j = 0; j < F_R; ++j) v[j] *= (fa + fb * x[j]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < F_R; ++j) {
+            const int i = j * F_NT + tid;
+            v[j] = i < srows ? (int64_t)r.tup_a[c][base + s * F_T + i] : 0;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < F_R; ++j)
+          if (pos[j] != 0xffffffffu) sorted[(size_t)c * R_T + pos[j]] = (unsigned long long)v[j];
+      }
+    }
+    __syncthreads();
+    // ---- phase 3: coalesced write-out (consecutive threads = consecutive tuples of one bin) -----------------------
+    const unsigned total = toff[NB - 1] + hist[NB - 1];
+    for (unsigned i = tid; i < total; i += R_NT) {
+      const unsigned d = bin[i];
+      const unsigned long long dest = gbase[d] + (i - toff[d]);
+#pragma unroll 1
+      for (int c = 0; c < r.n_comp; ++c) out[c][dest] = sorted[(size_t)c * R_T + i];
+    }
+    __syncthreads();
+  }
+}
+
+// level-2 histogram: every CTA owns a contiguous range of tiles so that the shared histogram is flushed only when
+// the level-1 bucket changes
+__global__ void __launch_bounds__(R_NT) k_radix_hist2(const __grid_constant__ RParams r) {
+  __shared__ unsigned int sh[1 << R_MAXB2];
+  const int tid = threadIdx.x;
+  const int NB = 1 << r.b2;
+  const unsigned int n_tiles = r.tpre[R_P1];
+  const unsigned int per = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const unsigned int t0 = blockIdx.x * per, t1 = min(n_tiles, t0 + per);
+  for (int i = tid; i < NB; i += R_NT) sh[i] = 0;
+  __syncthreads();
+  int cur_b1 = -1;
+  for (unsigned int t = t0; t < t1; ++t) {
+    int b1, rows;
+    int64_t base;
+    r_tile_of(r, t, &b1, &base, &rows);
+    if (b1 != cur_b1) {
+      if (cur_b1 >= 0) {
+        __syncthreads();
+        for (int i = tid; i < NB; i += R_NT) {
+          if (sh[i]) atomicAdd(&r.hist2[(cur_b1 << r.b2) + i], sh[i]);
+          sh[i] = 0;
+        }
+        __syncthreads();
+      }
+      cur_b1 = b1;
+    }
+    for (int i = tid; i < rows; i += R_NT) {
+      const uint64_t h = fmix64(r.tup_a[0][base + i]);
+      atomicAdd(&sh[(unsigned)(h >> (64 - R_B1 - r.b2)) & (unsigned)(NB - 1)], 1u);
+    }
+  }
+  __syncthreads();
+  if (cur_b1 >= 0)
+    for (int i = tid; i < NB; i += R_NT)
+      if (sh[i]) atomicAdd(&r.hist2[(cur_b1 << r.b2) + i], sh[i]);
+}
+
+// exclusive scan of n counters by ONE CTA of 1024 threads (n <= 131072): off[0..n], cur[i] = off[i]
+__global__ void __launch_bounds__(1024) k_radix_scan2(const unsigned int* __restrict__ hist, int n, unsigned long long* __restrict__ off,
+                                                      unsigned long long* __restrict__ cur) {
+  __shared__ unsigned long long part[1024];
+  const int t = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int i0 = t * per, i1 = min(n, i0 + per);
+  unsigned long long s = 0;
+  for (int i = i0; i < i1; ++i) s += hist[i];
+  part[t] = s;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    const unsigned long long x = t >= d ? part[t - d] : 0;
+    __syncthreads();
+    part[t] += x;
+    __syncthreads();
+  }
+  unsigned long long run = part[t] - s;
+  for (int i = i0; i < i1; ++i) {
+    off[i] = run;
+    cur[i] = run;
+    run += hist[i];
+  }
+  if (t == 1023) off[n] = part[1023];
+}
+
+// Final pass: one CTA per final bucket.  No accumulator atomics: the bucket's rows are counting-sorted by GROUP in
+// shared memory and every group is then reduced sequentially in registers by one thread.
+//   A  stream the packed codes: claim / find the group's slot in an open-addressing key table (64-bit CAS only for
+//      the first row of a group), rank = native 32-bit shared atomicAdd on the slot's row count; remember (slot, rank)
+//   S  block scan of the slot row counts -> first staged row of every slot; occupied slots -> output positions
+//   B  stream the operand values (coalesced) into the staging area at start[slot] + rank
+//   R  thread-per-slot: reduce the slot's contiguous staged rows, write the group straight to the output arrays
+// dynamic shared memory: keys[C1] u64 | stage[n_comp - 1][row_cap] u64 | cnt[C1] u32 | start[C1] u32 | pk[row_cap] u32
+__global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant__ RParams r) {
+  extern __shared__ __align__(16) unsigned char rsm[];
+  const int cap = r.cap, C1 = cap + 1, RC = r.row_cap, NV = r.n_comp - 1;
+  unsigned long long* keys = (unsigned long long*)rsm;
+  unsigned long long* stage = keys + C1;
+  unsigned int* cnt = (unsigned int*)(stage + (size_t)NV * RC);
+  unsigned int* start = cnt + C1;
+  unsigned int* pk = start + C1;
+  __shared__ unsigned long long warp_tot[R_AGG_NT / 32];
+  __shared__ unsigned long long out_base;
+  __shared__ int bucket_overflow;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_buckets = R_P1 << r.b2;
+  const int per = (C1 + R_AGG_NT - 1) / R_AGG_NT;
+  const int s0 = min(C1, tid * per), s1 = min(C1, s0 + per);
+
+  for (int b = blockIdx.x; b < n_buckets; b += gridDim.x) {
+    const int64_t lo = (int64_t)r.off2[b];
+    const int64_t n64 = (int64_t)r.off2[b + 1] - lo;
+    if (n64 == 0) continue;  // uniform for the CTA
+    if (n64 > RC) {          // skewed bucket: more rows than the staging area holds
+      if (tid == 0) *r.overflow = 3;
+      continue;
+    }
+    const int n = (int)n64;
+    // the next bucket of this CTA: pull its tuples towards L2 while this one is processed
+    if (b + (int)gridDim.x < n_buckets && tid < r.n_comp) {
+      const int64_t nlo = (int64_t)r.off2[b + gridDim.x];
+      const int64_t nn = min((int64_t)r.off2[b + gridDim.x + 1] - nlo, (int64_t)RC);
+      const uintptr_t a0 = ((uintptr_t)(r.tup_b[tid] + nlo) + 15) & ~(uintptr_t)15;   // 16 B aligned address and size
+      const uintptr_t a1 = (uintptr_t)(r.tup_b[tid] + nlo + nn) & ~(uintptr_t)15;
+      if (a1 > a0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((uint32_t)(a1 - a0)) : "memory");
+    }
+    for (int i = tid; i < C1; i += R_AGG_NT) {
+      keys[i] = F_EMPTY;
+      cnt[i] = 0;
+    }
+    if (tid == 0) bucket_overflow = 0;
+    __syncthreads();
+    // ---- A: slot + rank of every row (R_U loads in flight per thread: the bucket is read at HBM latency) ------------
+    for (int i0 = 0; i0 < n; i0 += R_U * R_AGG_NT) {
+      unsigned long long c8[R_U];
+#pragma unroll
+      for (int u = 0; u < R_U; ++u) {
+        const int i = i0 + u * R_AGG_NT + tid;
+        c8[u] = i < n ? __ldcs(&r.tup_b[0][lo + i]) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < R_U; ++u) {
+        const int i = i0 + u * R_AGG_NT + tid;
+        if (i >= n) continue;
+        const unsigned long long code = c8[u];
+        int slot = cap;  // the key whose code equals the EMPTY marker owns the extra slot
+        if (code != F_EMPTY) {
+          slot = (int)(fmix64(code) & (uint64_t)(cap - 1));
+          int probes = 0;
+          while (true) {
+            unsigned long long cur = *(volatile unsigned long long*)&keys[slot];
+            if (cur == code) break;
+            if (cur == F_EMPTY) {
+              cur = atomicCAS(&keys[slot], F_EMPTY, code);
+              if (cur == F_EMPTY || cur == code) break;
+            }
+            slot = (slot + 1) & (cap - 1);
+            if (++probes >= cap) {  // table full: this bucket holds more groups than the estimate allowed for
+              slot = -1;
+              break;
+            }
+          }
+        }
+        if (slot < 0) {
+          bucket_overflow = 1;
+          continue;
+        }
+        pk[i] = (unsigned)slot | (atomicAdd(&cnt[slot], 1u) << 13);
+      }
+    }
+    __syncthreads();
+    if (bucket_overflow) {
+      if (tid == 0) *r.overflow = 1;
+      __syncthreads();
+      continue;
+    }
+    // ---- S: (rows, occupied slots) exclusive scan over the slots, `per` consecutive slots per thread ------------------
+    unsigned long long mine = 0;  // rows in the low word, occupied slots in the high word
+    for (int s = s0; s < s1; ++s) mine += (unsigned long long)cnt[s] + (cnt[s] ? (1ull << 32) : 0ull);
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned long long wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < R_AGG_NT / 32; ++w) {
+      if (w < warp) wbase += warp_tot[w];
+      total += warp_tot[w];
+    }
+    const unsigned long long excl = wbase + incl - mine;
+    {
+      unsigned run = (unsigned)excl;
+      for (int s = s0; s < s1; ++s) {
+        start[s] = run;
+        run += cnt[s];
+      }
+    }
+    const unsigned n_occ = (unsigned)(total >> 32);
+    if (tid == 0) out_base = atomicAdd(r.n_out, (unsigned long long)n_occ);
+    __syncthreads();
+    const unsigned long long ob = out_base;
+    if (ob + n_occ > (unsigned long long)r.out_cap) {  // uniform
+      if (tid == 0) *r.overflow = 2;
+      __syncthreads();
+      continue;
+    }
+    // ---- B: operand values into the staging area, grouped by slot --------------------------------------------------------
+#pragma unroll 1
+    for (int c = 0; c < NV; ++c) {
+      const unsigned long long* src = r.tup_b[c + 1] + lo;
+      unsigned long long* dst = stage + (size_t)c * RC;
+      for (int i0 = 0; i0 < n; i0 += R_U * R_AGG_NT) {
+        unsigned long long v8[R_U];
+#pragma unroll
+        for (int u = 0; u < R_U; ++u) {
+          const int i = i0 + u * R_AGG_NT + tid;
+          v8[u] = i < n ? __ldcs(&src[i]) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < R_U; ++u) {
+          const int i = i0 + u * R_AGG_NT + tid;
+          if (i >= n) continue;
+          const unsigned p = pk[i];
+          dst[start[p & 8191u] + (p >> 13)] = v8[u];
+        }
+      }
+    }
+    __syncthreads();
+    // ---- R: one thread per slot reduces its rows in registers and writes the group ---------------------------------------
+    {
+      unsigned long long o = ob + (excl >> 32);
+      for (int s = s0; s < s1; ++s) {
+        const unsigned c = cnt[s];
+        if (c == 0) continue;
+        const unsigned first = start[s];
+        long long a[F_MAXA];
+#pragma unroll
+        for (int k = 0; k < F_MAXA; ++k) a[k] = 0;
+#pragma unroll
+        for (int k = 0; k < F_MAXA; ++k) {
+          if (k >= r.n_accs) break;
+          const int kind = r.kind_of[k];
+          const unsigned long long* src = stage + (size_t)(r.comp_of[k] - 1) * RC + first;
+          long long acc = (long long)src[0];
+          if (kind == FK_SUM) {
+            for (unsigned i = 1; i < c; ++i) acc += (long long)src[i];
+          } else if (kind == FK_MIN) {
+            for (unsigned i = 1; i < c; ++i) acc = min(acc, (long long)src[i]);
+          } else if (kind == FK_MAX) {
+            for (unsigned i = 1; i < c; ++i) acc = max(acc, (long long)src[i]);
+          } else {
+            double d = __longlong_as_double(acc);
+            for (unsigned i = 1; i < c; ++i) d += __longlong_as_double((long long)src[i]);
+            acc = __double_as_longlong(d);
+          }
+          a[k] = acc;
+        }
+        r.out_code[o] = s == cap ? F_EMPTY : keys[s];
+        r.out_cnt[o] = c;
+#pragma unroll
+        for (int k = 0; k < F_MAXA; ++k)
+          if (k < r.n_accs) r.out_acc[k][o] = (unsigned long long)a[k];
+        ++o;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+struct RKeys {
+  int n_keys;
+  int shift[F_MAXK], bits[F_MAXK], width[F_MAXK];
+  long long base[F_MAXK];
+  void* out[F_MAXK];
+};
+// packed code -> key columns (key k = base_k + bits [shift_k, shift_k + bits_k) of the code)
+__global__ void __launch_bounds__(256) k_radix_keys(const unsigned long long* __restrict__ code, int64_t n, const RKeys rk) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) {
+    const unsigned long long c = code[g];
+    for (int k = 0; k < rk.n_keys; ++k) {
+      const unsigned long long field = rk.bits[k] >= 64 ? c : ((c >> rk.shift[k]) & ((1ull << rk.bits[k]) - 1ull));
+      const long long v = (long long)((unsigned long long)rk.base[k] + field);
+      switch (rk.width[k]) {
+        case 8: ((long long*)rk.out[k])[g] = v; break;
+        case 4: ((int*)rk.out[k])[g] = (int)v; break;
+        case 2: ((short*)rk.out[k])[g] = (short)v; break;
+        default: ((signed char*)rk.out[k])[g] = (signed char)v; break;
+      }
+    }
+  }
+}
+
+// HyperLogLog estimate from the 4096 registers (host side)
+static double hll_estimate(const unsigned int* reg) {
+  const double m = (double)R_HLL_M;
+  double sum = 0;
+  int zeros = 0;
+  for (int i = 0; i < R_HLL_M; ++i) {
+    sum += ldexp(1.0, -(int)reg[i]);
+    zeros += reg[i] == 0;
+  }
+  const double alpha = 0.7213 / (1.0 + 1.079 / m);
+  double e = alpha * m * m / sum;
+  if (e <= 2.5 * m && zeros > 0) e = m * log(m / (double)zeros);
+  return e;
+}

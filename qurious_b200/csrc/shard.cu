@@ -523,7 +523,8 @@ __global__ void __launch_bounds__(PART_THREADS) k_part_scatter(const void* __res
       const int64_t row = t * PART_TILE + (int64_t)j * PART_THREADS + threadIdx.x;
       const unsigned long long d = base[part[j]] + rank[j];
       for (int c = 0; c < pc.n_cols; ++c) {
-        if (pc.width[c] == 8) ((unsigned long long*)pc.dst[c])[d] = ((const unsigned long long*)pc.src[c])[row];
+        if (pc.width[c] == 16) ((ulonglong2*)pc.dst[c])[d] = ((const ulonglong2*)pc.src[c])[row];
+        else if (pc.width[c] == 8) ((unsigned long long*)pc.dst[c])[d] = ((const unsigned long long*)pc.src[c])[row];
         else if (pc.width[c] == 4) ((unsigned int*)pc.dst[c])[d] = ((const unsigned int*)pc.src[c])[row];
         else if (pc.width[c] == 2) ((unsigned short*)pc.dst[c])[d] = ((const unsigned short*)pc.src[c])[row];
         else pc.dst[c][d] = pc.src[c][row];

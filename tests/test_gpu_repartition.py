@@ -26,7 +26,8 @@ SCHEMA = pa.schema([("k", pa.int64()), ("v", pa.int64()), ("f", pa.float64()), (
 
 def make_table(n, groups, seed=3):
     rng = np.random.default_rng(seed)
-    k = rng.integers(0, max(groups, 1), n).astype(np.int64) * 0x9E3779B97F4A7C15 % (2**63)
+    with np.errstate(over="ignore"):
+        k = (rng.integers(0, max(groups, 1), n).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)).view(np.int64)
     cols = [pa.array(k), pa.array(rng.integers(-10**6, 10**6, n).astype(np.int64)), pa.array(rng.random(n)),
             pa.array(rng.integers(0, 20000, n).astype(np.int32), pa.date32()),
             pa.array([decimal.Decimal(int(x)).scaleb(-2) for x in rng.integers(-10**15, 10**15, n)], pa.decimal128(30, 2))]
