@@ -1552,6 +1552,8 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
       }
       fp.R.comp_of[k] = found;
       fp.R.kind_of[k] = full[k].kind;
+      fp.R.cmask[found - 1] |= 1 << full[k].kind;
+      fp.R.acc_at[found - 1][full[k].kind] = k;
     }
     fp.R.n_accs = P.n_accs;
     for (int k = 1; k < P.n_accs; ++k) {
@@ -1724,7 +1726,7 @@ static bool run_radix(PlanNode& agg, const View& v, FusedPlan& fp, View* out) {
     cap = 64;
     while (cap < 4096 && g_b > 0.45 * cap) cap *= 2;
     if (g_b > 0.45 * cap) continue;
-    const size_t table = (size_t)(cap + 1) * 16;
+    const size_t table = (size_t)(cap + 1) * 18 + 16;
     if (table + 1024 >= smem_budget) continue;
     row_cap = (int)std::min<size_t>((smem_budget - table) / row_bytes, (size_t)1 << 18);
     if ((double)row_cap >= r_b * 1.15 + 6.0 * sqrt(r_b) + 64.0) break;
@@ -1733,7 +1735,7 @@ static bool run_radix(PlanNode& agg, const View& v, FusedPlan& fp, View* out) {
   if (const char* tc = getenv("QGPU_RADIX_TEST_CAP")) {  // tests: provoke the overflow -> FM_HASH fallback
     cap = std::max(64, std::min(4096, atoi(tc)));
     b2 = 1;
-    row_cap = (int)std::min<size_t>((smem_budget - (size_t)(cap + 1) * 16) / row_bytes, (size_t)1 << 18);
+    row_cap = (int)std::min<size_t>((smem_budget - (size_t)(cap + 1) * 18 - 16) / row_bytes, (size_t)1 << 18);
   }
   R.b2 = b2;
   R.cap = cap;
@@ -1767,12 +1769,12 @@ static bool run_radix(PlanNode& agg, const View& v, FusedPlan& fp, View* out) {
   CUDA_CHECK(cudaFuncSetAttribute(k_radix_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
   const int sc_per_sm = (2 * (sc_smem + 1024 + 64) <= (size_t)233472) ? 2 : 1;
   const int64_t tiles1 = (n_rows + R_T - 1) / R_T;
-  LAUNCH(ctx, k_radix_scatter<1>, (int)std::min<int64_t>(tiles1, (int64_t)ctx->sm_count * sc_per_sm), R_NT, sc_smem, P, R);
+  LAUNCH(ctx, k_radix_scatter<1>, (int)std::min<int64_t>(tiles1, (int64_t)ctx->sm_count * sc_per_sm), R_SNT, sc_smem, P, R);
   LAUNCH(ctx, k_radix_hist2, (int)std::min<int64_t>(std::max<int64_t>(n_tiles2, 1), (int64_t)ctx->sm_count * 8), R_NT, 0, R);
   LAUNCH(ctx, k_radix_scan2, 1, 1024, 0, R.hist2, (int)n_buckets, R.off2, R.cur2);
-  LAUNCH(ctx, k_radix_scatter<2>, (int)std::min<int64_t>(std::max<int64_t>(n_tiles2, 1), (int64_t)ctx->sm_count * sc_per_sm), R_NT, sc_smem,
+  LAUNCH(ctx, k_radix_scatter<2>, (int)std::min<int64_t>(std::max<int64_t>(n_tiles2, 1), (int64_t)ctx->sm_count * sc_per_sm), R_SNT, sc_smem,
          P, R);
-  const size_t ag_smem = (size_t)(cap + 1) * 16 + (size_t)row_cap * row_bytes + 64;
+  const size_t ag_smem = (size_t)(cap + 1) * 18 + (size_t)row_cap * row_bytes + 64;
   CUDA_CHECK(cudaFuncSetAttribute(k_radix_agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ag_smem));
   LAUNCH(ctx, k_radix_agg, (int)std::min<int64_t>(n_buckets, (int64_t)ctx->sm_count), R_AGG_NT, ag_smem, R);
   unsigned long long fin[2];

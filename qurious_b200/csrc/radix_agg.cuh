@@ -25,6 +25,9 @@
 
 constexpr int R_NT = 256;                 // threads per CTA of the partition kernels (== F_NT: load_rows mapping)
 constexpr int R_SUB = 4;                  // sub-tiles of F_T rows
+constexpr int R_SNT = 512;                // threads per CTA of the scatter kernels
+constexpr int R_SPT = R_SUB * F_NT / R_SNT;  // sub-tiles per thread
+static_assert(R_SNT == 512 && R_SPT == 2, "scatter: one histogram bin per thread, two sub-tiles per thread");
 constexpr int R_T = F_T * R_SUB;          // tuples per tile
 constexpr int R_B1 = 8;                   // level-1 digit: top 8 hash bits
 constexpr int R_P1 = 1 << R_B1;
@@ -34,6 +37,7 @@ constexpr int R_HLL_BITS = 12;
 constexpr int R_HLL_M = 1 << R_HLL_BITS;
 constexpr int R_AGG_NT = 1024;            // threads per CTA of the final pass
 constexpr int R_U = 8;                    // final pass: global loads in flight per thread
+static_assert(R_AGG_NT == 1024, "the final pass scans 32 warp totals with one warp");
 static_assert(R_NT == F_NT, "load_rows_g uses the F_NT row mapping");
 
 struct RComp {           // operand value = coef * prod(a_i + b_i * x_i) (int64, proven not to overflow) or raw f64 bits
@@ -47,6 +51,8 @@ struct RParams {
   int32_t row_cap, pad0;     // final pass: rows a bucket may hold (staging area)
   int32_t comp_of[F_MAXA];   // accumulator -> tuple component (>= 1)
   int32_t kind_of[F_MAXA];
+  int32_t cmask[R_MAXCOMP - 1];      // operand value -> kinds reduced over it (bit FK_*)
+  int32_t acc_at[R_MAXCOMP - 1][4];  // (operand value, kind) -> accumulator
   RComp comp[R_MAXCOMP - 1]; // component c >= 1 is comp[c - 1]
   unsigned long long* tup_a[R_MAXCOMP];
   unsigned long long* tup_b[R_MAXCOMP];
@@ -193,67 +199,103 @@ __device__ __forceinline__ void r_tile_of(const RParams& r, unsigned int tile, i
 // LEVEL 1: input rows -> tuples in level-1 buckets.  LEVEL 2: level-1 tuples -> final buckets.
 // dynamic shared memory: sorted[n_comp][R_T] u64 | gbase[512] u64 | hist[512] u32 | toff[512] u32 | bin[R_T] u16
 template <int LEVEL>
-__global__ void __launch_bounds__(R_NT, 2) k_radix_scatter(const __grid_constant__ FParams p, const __grid_constant__ RParams r) {
+__global__ void __launch_bounds__(R_SNT, 2) k_radix_scatter(const __grid_constant__ FParams p, const __grid_constant__ RParams r) {
   extern __shared__ __align__(16) unsigned char rsm[];
   unsigned long long* sorted = (unsigned long long*)rsm;
   unsigned long long* gbase = sorted + (size_t)r.n_comp * R_T;
   unsigned int* hist = (unsigned int*)(gbase + 512);
   unsigned int* toff = hist + 512;
   unsigned short* bin = (unsigned short*)(toff + 512);
-  __shared__ unsigned int warp_tot[R_NT / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ unsigned int warp_tot[R_SNT / 32];
+  // 512 threads: threads 0..255 own sub-tiles 0 and 1 of the 4096-tuple tile, threads 256..511 sub-tiles 2 and 3
+  // (row mapping inside a sub-tile = load_rows_g's: row j * 256 + t256)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t256 = tid & (F_NT - 1), s_first = (tid >> 8) * R_SPT;
   const int NB = LEVEL == 1 ? R_P1 : (1 << r.b2);
   const int shift = LEVEL == 1 ? (64 - R_B1) : (64 - R_B1 - r.b2);
   const unsigned int n_tiles = LEVEL == 1 ? (unsigned int)((p.n_rows + R_T - 1) / R_T) : r.tpre[R_P1];
   unsigned long long* const cursor = LEVEL == 1 ? r.cur1 : r.cur2;
   unsigned long long* const* out = LEVEL == 1 ? r.tup_a : r.tup_b;
 
+  // tiles are taken round-robin (at any time all CTAs append to the same few hundred output runs, which keeps the
+  // partially written sectors together in L2); LEVEL 2 walks the bucket-aligned tile list instead of searching it
+  int b1 = 0;
+  unsigned int b_tile0 = 0, b_tile1 = 0;     // tiles [b_tile0, b_tile1) belong to level-1 bucket b1
+  unsigned long long b_off0 = 0, b_off1 = 0; // its tuples
+  if (LEVEL == 2) {
+    b_tile1 = r.tpre[1];
+    b_off1 = r.off1[1];
+  }
   for (unsigned int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    int b1 = 0, rows;
+    int rows;
     int64_t base;
     if (LEVEL == 1) {
       base = (int64_t)t * R_T;
       rows = (int)min((int64_t)R_T, p.n_rows - base);
+      // pull this CTA's next tile towards L2 (base pointers are 256 B aligned, tiles are 4096 rows)
+      const int64_t nbase = base + (int64_t)gridDim.x * R_T;
+      if (nbase < p.n_rows && tid < p.n_cols) {
+        const int64_t nrows = min((int64_t)R_T, p.n_rows - nbase);
+        const uint32_t bytes = (uint32_t)((nrows * p.cols[tid].width) & ~15ll);
+        if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gcol(p, tid, nbase)), "r"(bytes) : "memory");
+      }
     } else {
-      r_tile_of(r, t, &b1, &base, &rows);
+      while (t >= b_tile1) {  // next non-empty level-1 bucket
+        ++b1;
+        b_tile0 = b_tile1;
+        b_tile1 = r.tpre[b1 + 1];
+        b_off0 = b_off1;
+        b_off1 = r.off1[b1 + 1];
+      }
+      base = (int64_t)b_off0 + (int64_t)(t - b_tile0) * R_T;
+      rows = (int)min((int64_t)R_T, (int64_t)b_off1 - base);
+      if (t + gridDim.x < b_tile1 && tid < r.n_comp) {  // this CTA's next tile, when it lies in the same bucket
+        const int64_t nbase = base + (int64_t)gridDim.x * R_T;
+        const uintptr_t a0 = ((uintptr_t)(r.tup_a[tid] + nbase) + 15) & ~(uintptr_t)15;
+        const uintptr_t a1 = (uintptr_t)(r.tup_a[tid] + min((int64_t)b_off1, nbase + R_T)) & ~(uintptr_t)15;
+        if (a1 > a0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((uint32_t)(a1 - a0)) : "memory");
+      }
     }
-    for (int i = tid; i < NB; i += R_NT) hist[i] = 0;
+    for (int i = tid; i < NB; i += R_SNT) hist[i] = 0;
     __syncthreads();
-    // ---- phase 1: digit + unordered rank of every tuple (shared atomics) ------------------------------------
-    uint64_t code[R_SUB][F_R];
-    uint32_t pr[R_SUB][F_R];
+    // ---- phase 1: digit + unordered rank of every tuple (shared atomics).  All global loads of the tile are issued
+    //      before the first atomic so that they overlap (16 rows per thread in flight) ---------------------------------
+    uint64_t code[R_SPT][F_R];
+    uint32_t pr[R_SPT][F_R];
+    uint32_t passm[R_SPT];
 #pragma unroll
-    for (int s = 0; s < R_SUB; ++s) {
-      const int srows = max(0, min(F_T, rows - s * F_T));
-      uint32_t pass;
+    for (int s = 0; s < R_SPT; ++s) {
+      const int srows = max(0, min(F_T, rows - (s_first + s) * F_T));
       if (LEVEL == 1) {
-        pass = srows > 0 ? r_pass_code(p, base + s * F_T, srows, tid, code[s]) : 0u;
+        passm[s] = r_pass_code(p, base + (s_first + s) * F_T, srows, t256, code[s]);
       } else {
-        pass = 0;
+        passm[s] = 0;
 #pragma unroll
         for (int j = 0; j < F_R; ++j) {
-          const int i = j * F_NT + tid;
+          const int i = j * F_NT + t256;
           code[s][j] = 0;
           if (i < srows) {
-            code[s][j] = r.tup_a[0][base + s * F_T + i];
-            pass |= 1u << j;
+            code[s][j] = r.tup_a[0][base + (s_first + s) * F_T + i];
+            passm[s] |= 1u << j;
           }
         }
       }
+    }
+#pragma unroll
+    for (int s = 0; s < R_SPT; ++s) {
 #pragma unroll
       for (int j = 0; j < F_R; ++j) {
         pr[s][j] = 0xffffffffu;
-        if ((pass >> j) & 1) {
+        if ((passm[s] >> j) & 1) {
           const unsigned d = (unsigned)(fmix64(code[s][j]) >> shift) & (unsigned)(NB - 1);
           pr[s][j] = (d << 16) | atomicAdd(&hist[d], 1u);
         }
       }
     }
     __syncthreads();
-    // ---- exclusive scan of the histogram (2 bins per thread) + one global reservation per non-empty bin --------
+    // ---- exclusive scan of the histogram (one bin per thread) + one global reservation per non-empty bin --------------
     {
-      const unsigned h0 = 2 * tid < NB ? hist[2 * tid] : 0u, h1 = 2 * tid + 1 < NB ? hist[2 * tid + 1] : 0u;
-      unsigned incl = h0 + h1;
+      const unsigned h0 = tid < NB ? hist[tid] : 0u;
+      unsigned incl = h0;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
@@ -263,71 +305,77 @@ __global__ void __launch_bounds__(R_NT, 2) k_radix_scatter(const __grid_constant
       __syncthreads();
       unsigned wbase = 0;
 #pragma unroll
-      for (int w = 0; w < R_NT / 32; ++w)
+      for (int w = 0; w < R_SNT / 32; ++w)
         if (w < warp) wbase += warp_tot[w];
-      const unsigned excl = wbase + incl - (h0 + h1);
-      if (2 * tid < NB) {
-        toff[2 * tid] = excl;
-        if (h0) gbase[2 * tid] = atomicAdd(&cursor[(LEVEL == 1 ? 0 : (b1 << r.b2)) + 2 * tid], (unsigned long long)h0);
-      }
-      if (2 * tid + 1 < NB) {
-        toff[2 * tid + 1] = excl + h0;
-        if (h1) gbase[2 * tid + 1] = atomicAdd(&cursor[(LEVEL == 1 ? 0 : (b1 << r.b2)) + 2 * tid + 1], (unsigned long long)h1);
+      if (tid < NB) {
+        toff[tid] = wbase + incl - h0;
+        if (h0) gbase[tid] = atomicAdd(&cursor[(LEVEL == 1 ? 0 : (b1 << r.b2)) + tid], (unsigned long long)h0);
       }
     }
     __syncthreads();
-    // ---- phase 2: tuples into the shared-memory tile, grouped by bin ---------------------------------------------
+    // ---- phase 2: tuples into the shared-memory tile, grouped by bin; per component all 16 loads first -----------------
+    uint32_t pos[R_SPT][F_R];
 #pragma unroll
-    for (int s = 0; s < R_SUB; ++s) {
-      const int srows = max(0, min(F_T, rows - s * F_T));
-      if (srows <= 0) continue;
-      uint32_t pos[F_R];
+    for (int s = 0; s < R_SPT; ++s) {
 #pragma unroll
       for (int j = 0; j < F_R; ++j) {
-        pos[j] = 0xffffffffu;
+        pos[s][j] = 0xffffffffu;
         if (pr[s][j] != 0xffffffffu) {
           const unsigned d = pr[s][j] >> 16;
-          pos[j] = toff[d] + (pr[s][j] & 0xffffu);
-          sorted[pos[j]] = code[s][j];
-          bin[pos[j]] = (unsigned short)d;
+          pos[s][j] = toff[d] + (pr[s][j] & 0xffffu);
+          sorted[pos[s][j]] = code[s][j];
+          bin[pos[s][j]] = (unsigned short)d;
         }
       }
+    }
 #pragma unroll 1
-      for (int c = 1; c < r.n_comp; ++c) {
-        int64_t v[F_R];
-        if (LEVEL == 1) {
-          const RComp& C = r.comp[c - 1];
-          const int64_t row0 = base + s * F_T;
-          if (C.is_f64) {
-            load_rows_g(gcol(p, C.f[0].col, row0), C.f[0].wk, tid, srows, v);
-          } else {
+    for (int c = 1; c < r.n_comp; ++c) {
+      int64_t v[R_SPT][F_R];
+      if (LEVEL == 1) {
+        const RComp& C = r.comp[c - 1];
+        if (C.is_f64) {
 #pragma unroll
-            for (int j = 0; j < F_R; ++j) v[j] = C.coef;
-#pragma unroll 1
-            for (int f = 0; f < C.n_factors; ++f) {
-              int64_t x[F_R];
-              load_rows_g(gcol(p, C.f[f].col, row0), C.f[f].wk, tid, srows, x);
-              const int64_t fa = C.f[f].a, fb = C.f[f].b;
-#pragma unroll
-              for (int j = 0; j < F_R; ++j) v[j] *= (fa + fb * x[j]);
-            }
-          }
+          for (int s = 0; s < R_SPT; ++s)
+            load_rows_g(gcol(p, C.f[0].col, base + (s_first + s) * F_T), C.f[0].wk, t256, max(0, min(F_T, rows - (s_first + s) * F_T)), v[s]);
         } else {
 #pragma unroll
-          for (int j = 0; j < F_R; ++j) {
-            const int i = j * F_NT + tid;
-            v[j] = i < srows ? (int64_t)r.tup_a[c][base + s * F_T + i] : 0;
+          for (int s = 0; s < R_SPT; ++s)
+#pragma unroll
+            for (int j = 0; j < F_R; ++j) v[s][j] = C.coef;
+#pragma unroll 1
+          for (int f = 0; f < C.n_factors; ++f) {
+            int64_t x[R_SPT][F_R];
+#pragma unroll
+            for (int s = 0; s < R_SPT; ++s)
+              load_rows_g(gcol(p, C.f[f].col, base + (s_first + s) * F_T), C.f[f].wk, t256, max(0, min(F_T, rows - (s_first + s) * F_T)), x[s]);
+            const int64_t fa = C.f[f].a, fb = C.f[f].b;
+#pragma unroll
+            for (int s = 0; s < R_SPT; ++s)
+#pragma unroll
+              for (int j = 0; j < F_R; ++j) v[s][j] *= (fa + fb * x[s][j]);
           }
         }
+      } else {
+#pragma unroll
+        for (int s = 0; s < R_SPT; ++s) {
+          const int srows = max(0, min(F_T, rows - (s_first + s) * F_T));
+#pragma unroll
+          for (int j = 0; j < F_R; ++j) {
+            const int i = j * F_NT + t256;
+            v[s][j] = i < srows ? (int64_t)r.tup_a[c][base + (s_first + s) * F_T + i] : 0;
+          }
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < R_SPT; ++s)
 #pragma unroll
         for (int j = 0; j < F_R; ++j)
-          if (pos[j] != 0xffffffffu) sorted[(size_t)c * R_T + pos[j]] = (unsigned long long)v[j];
-      }
+          if (pos[s][j] != 0xffffffffu) sorted[(size_t)c * R_T + pos[s][j]] = (unsigned long long)v[s][j];
     }
     __syncthreads();
     // ---- phase 3: coalesced write-out (consecutive threads = consecutive tuples of one bin) -----------------------
     const unsigned total = toff[NB - 1] + hist[NB - 1];
-    for (unsigned i = tid; i < total; i += R_NT) {
+    for (unsigned i = tid; i < total; i += R_SNT) {
       const unsigned d = bin[i];
       const unsigned long long dest = gbase[d] + (i - toff[d]);
 #pragma unroll 1
@@ -408,7 +456,8 @@ __global__ void __launch_bounds__(1024) k_radix_scan2(const unsigned int* __rest
 //   S  block scan of the slot row counts -> first staged row of every slot; occupied slots -> output positions
 //   B  stream the operand values (coalesced) into the staging area at start[slot] + rank
 //   R  thread-per-slot: reduce the slot's contiguous staged rows, write the group straight to the output arrays
-// dynamic shared memory: keys[C1] u64 | stage[n_comp - 1][row_cap] u64 | cnt[C1] u32 | start[C1] u32 | pk[row_cap] u32
+// dynamic shared memory: keys[C1] u64 | stage[n_comp - 1][row_cap] u64 | cnt[C1] u32 | start[C1] u32 | pk[row_cap] u32 |
+//                        occ[C1] u16
 __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant__ RParams r) {
   extern __shared__ __align__(16) unsigned char rsm[];
   const int cap = r.cap, C1 = cap + 1, RC = r.row_cap, NV = r.n_comp - 1;
@@ -417,8 +466,9 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
   unsigned int* cnt = (unsigned int*)(stage + (size_t)NV * RC);
   unsigned int* start = cnt + C1;
   unsigned int* pk = start + C1;
+  unsigned short* occ = (unsigned short*)(pk + RC);
   __shared__ unsigned long long warp_tot[R_AGG_NT / 32];
-  __shared__ unsigned long long out_base;
+  __shared__ unsigned long long out_base, bucket_total;
   __shared__ int bucket_overflow;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_buckets = R_P1 << r.b2;
@@ -463,7 +513,9 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
         const unsigned long long code = c8[u];
         int slot = cap;  // the key whose code equals the EMPTY marker owns the extra slot
         if (code != F_EMPTY) {
-          slot = (int)(fmix64(code) & (uint64_t)(cap - 1));
+          const uint64_t h = fmix64(code);
+          slot = (int)(h & (uint64_t)(cap - 1));
+          const int step = (int)((h >> 13) & (uint64_t)(cap - 1)) | 1;  // double hashing: odd step, no clustering tails
           int probes = 0;
           while (true) {
             unsigned long long cur = *(volatile unsigned long long*)&keys[slot];
@@ -472,7 +524,7 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
               cur = atomicCAS(&keys[slot], F_EMPTY, code);
               if (cur == F_EMPTY || cur == code) break;
             }
-            slot = (slot + 1) & (cap - 1);
+            slot = (slot + step) & (cap - 1);
             if (++probes >= cap) {  // table full: this bucket holds more groups than the estimate allowed for
               slot = -1;
               break;
@@ -503,29 +555,39 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
     }
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    unsigned long long wbase = 0, total = 0;
+    if (warp == 0) {  // second level: exclusive scan of the 32 warp totals
+      const unsigned long long wt = warp_tot[lane];
+      unsigned long long wi = wt;
 #pragma unroll
-    for (int w = 0; w < R_AGG_NT / 32; ++w) {
-      if (w < warp) wbase += warp_tot[w];
-      total += warp_tot[w];
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xffffffffu, wi, d);
+        if (lane >= d) wi += o;
+      }
+      warp_tot[lane] = wi - wt;
+      if (lane == 31) {
+        bucket_total = wi;
+        out_base = atomicAdd(r.n_out, wi >> 32);
+      }
     }
-    const unsigned long long excl = wbase + incl - mine;
+    __syncthreads();
+    const unsigned long long excl = warp_tot[warp] + incl - mine;
     {
       unsigned run = (unsigned)excl;
+      unsigned g = (unsigned)(excl >> 32);
       for (int s = s0; s < s1; ++s) {
         start[s] = run;
         run += cnt[s];
+        if (cnt[s]) occ[g++] = (unsigned short)s;   // dense list of the occupied slots
       }
     }
-    const unsigned n_occ = (unsigned)(total >> 32);
-    if (tid == 0) out_base = atomicAdd(r.n_out, (unsigned long long)n_occ);
-    __syncthreads();
+    const unsigned n_occ = (unsigned)(bucket_total >> 32);
     const unsigned long long ob = out_base;
     if (ob + n_occ > (unsigned long long)r.out_cap) {  // uniform
       if (tid == 0) *r.overflow = 2;
       __syncthreads();
       continue;
     }
+    __syncthreads();
     // ---- B: operand values into the staging area, grouped by slot --------------------------------------------------------
 #pragma unroll 1
     for (int c = 0; c < NV; ++c) {
@@ -548,41 +610,49 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
       }
     }
     __syncthreads();
-    // ---- R: one thread per slot reduces its rows in registers and writes the group ---------------------------------------
-    {
-      unsigned long long o = ob + (excl >> 32);
-      for (int s = s0; s < s1; ++s) {
-        const unsigned c = cnt[s];
-        if (c == 0) continue;
-        const unsigned first = start[s];
-        long long a[F_MAXA];
-#pragma unroll
-        for (int k = 0; k < F_MAXA; ++k) a[k] = 0;
-#pragma unroll
-        for (int k = 0; k < F_MAXA; ++k) {
-          if (k >= r.n_accs) break;
-          const int kind = r.kind_of[k];
-          const unsigned long long* src = stage + (size_t)(r.comp_of[k] - 1) * RC + first;
-          long long acc = (long long)src[0];
-          if (kind == FK_SUM) {
-            for (unsigned i = 1; i < c; ++i) acc += (long long)src[i];
-          } else if (kind == FK_MIN) {
-            for (unsigned i = 1; i < c; ++i) acc = min(acc, (long long)src[i]);
-          } else if (kind == FK_MAX) {
-            for (unsigned i = 1; i < c; ++i) acc = max(acc, (long long)src[i]);
-          } else {
-            double d = __longlong_as_double(acc);
-            for (unsigned i = 1; i < c; ++i) d += __longlong_as_double((long long)src[i]);
-            acc = __double_as_longlong(d);
+    // ---- R: one thread per GROUP (dense over the lanes) reduces its contiguous staged rows in registers, operand by
+    //         operand (SUM / MIN / MAX of the same operand share one pass), and writes the group; consecutive threads
+    //         write consecutive output rows
+    for (unsigned g = tid; g < n_occ; g += R_AGG_NT) {
+      const int sl = occ[g];
+      const unsigned c = cnt[sl];
+      const unsigned first = start[sl];
+      const unsigned long long o = ob + g;
+      r.out_code[o] = sl == cap ? F_EMPTY : keys[sl];
+      r.out_cnt[o] = c;
+#pragma unroll 1
+      for (int cc = 0; cc < NV; ++cc) {
+        const unsigned long long* src = stage + (size_t)cc * RC + first;
+        const int m = r.cmask[cc];
+        const long long v0 = (long long)src[0];
+        if (m == 8) {
+          double fs = __longlong_as_double(v0);
+#pragma unroll 4
+          for (unsigned i = 1; i < c; ++i) fs += __longlong_as_double((long long)src[i]);
+          r.out_acc[r.acc_at[cc][3]][o] = (unsigned long long)__double_as_longlong(fs);
+        } else if (m == 1) {
+          long long sm = v0;
+#pragma unroll 4
+          for (unsigned i = 1; i < c; ++i) sm += (long long)src[i];
+          r.out_acc[r.acc_at[cc][0]][o] = (unsigned long long)sm;
+        } else {
+          long long sm = v0, mn = v0, mx = v0;
+#pragma unroll 4
+          for (unsigned i = 1; i < c; ++i) {
+            const long long v = (long long)src[i];
+            sm += v;
+            mn = min(mn, v);
+            mx = max(mx, v);
           }
-          a[k] = acc;
+          if (m & 1) r.out_acc[r.acc_at[cc][0]][o] = (unsigned long long)sm;
+          if (m & 2) r.out_acc[r.acc_at[cc][1]][o] = (unsigned long long)mn;
+          if (m & 4) r.out_acc[r.acc_at[cc][2]][o] = (unsigned long long)mx;
+          if (m & 8) {  // (an f64 operand never carries integer kinds; kept for completeness)
+            double fs = __longlong_as_double(v0);
+            for (unsigned i = 1; i < c; ++i) fs += __longlong_as_double((long long)src[i]);
+            r.out_acc[r.acc_at[cc][3]][o] = (unsigned long long)__double_as_longlong(fs);
+          }
         }
-        r.out_code[o] = s == cap ? F_EMPTY : keys[s];
-        r.out_cnt[o] = c;
-#pragma unroll
-        for (int k = 0; k < F_MAXA; ++k)
-          if (k < r.n_accs) r.out_acc[k][o] = (unsigned long long)a[k];
-        ++o;
       }
     }
     __syncthreads();
