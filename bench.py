@@ -134,6 +134,9 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+PIN_FAILURES = []
+
+
 def pin_batches(batches):
     """cudaHostRegister every Arrow buffer of the host batches so that H2D is a direct pinned DMA."""
     import torch
@@ -146,8 +149,11 @@ def pin_batches(batches):
                 if buf is None or buf.size == 0 or buf.address in seen:
                     continue
                 seen.add(buf.address)
-                if int(rt.cudaHostRegister(buf.address, buf.size, 0)) == 0:
+                rc = int(rt.cudaHostRegister(buf.address, buf.size, 0))
+                if rc == 0:
                     regs.append(buf.address)
+                else:
+                    PIN_FAILURES.append((buf.size, rc))
     return regs
 
 

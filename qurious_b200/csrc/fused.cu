@@ -93,6 +93,11 @@ struct FParams {
   // matching build row (accumulator stride = acc_stride)
   const unsigned long long* jt_slots;
   uint64_t jt_mask;
+  // exact membership bitmap of the build keys over [jt_kmin, jt_kmin + jt_kspan] (null: none): most probe rows
+  // miss, and they are rejected here -- a few MB that stay in L1/L2 -- before the random access to the join table
+  const uint32_t* jt_bitmap;
+  int64_t jt_kmin;
+  uint64_t jt_kspan;
   const void* bkey;
   int32_t bkey_width, pad_probe;
   // accumulator word of (accumulator k, slot g) = g_lo[acc_base + k * acc_kstride + g * acc_gstride]
@@ -370,6 +375,19 @@ struct GenericBody {
           // miss (Q3: ~1% match), so the cost is the latency of the first slot load: issue all F_R of them first.
           uint64_t hh[F_R], sl[F_R];
           unsigned long long cur[F_R];
+          if (p.jt_bitmap) {
+            uint32_t word[F_R];
+            uint64_t kk[F_R];
+#pragma unroll
+            for (int j = 0; j < F_R; ++j) {
+              kk[j] = code[j] - (uint64_t)p.jt_kmin;
+              word[j] = (((pass >> j) & 1) && kk[j] <= p.jt_kspan) ? __ldg(&p.jt_bitmap[kk[j] >> 5]) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < F_R; ++j)
+              if (!((word[j] >> (kk[j] & 31)) & 1u)) pass &= ~(1u << j);
+            if (!__any_sync(0xffffffffu, pass != 0)) return;  // no row of this warp has a build partner
+          }
 #pragma unroll
           for (int j = 0; j < F_R; ++j) {
             hh[j] = fmix64(code[j]);
@@ -2036,9 +2054,25 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
 // TMA-staged pipeline as the scan-aggregate kernel and accumulates straight into per-build-row accumulators
 // (FM_PROBE) -- no join output, no second hash table.  Anything else returns false (generic operators run).
 // ------------------------------------------------------------------------------------------------
+
+// membership bitmap over the build key's value range (from the base column's statistics: the gathered subset lies
+// inside it); skipped when the range is unknown or would need more than 64 MB
+static DBufP join_key_bitmap(Ctx* ctx, const LazyCol& key, int64_t nb, int64_t* kmin, uint64_t* kspan) {
+  *kmin = 0;
+  *kspan = 0;
+  if (nb <= 0 || !key.base || getenv("QGPU_NO_JOIN_BITMAP")) return nullptr;
+  ensure_stats(ctx, *key.base);
+  if (!key.base->has_stats) return nullptr;
+  const i128 range = key.base->vmax - key.base->vmin + 1;
+  if (range <= 0 || range > ((i128)1 << 29) || key.base->vmin < -(LIM62 * 2) || key.base->vmax > LIM62 * 2 - 1) return nullptr;
+  *kmin = (int64_t)key.base->vmin;
+  *kspan = (uint64_t)(range - 1);
+  return ctx->alloc_zero((size_t)((range + 31) / 32) * 4 + 16);
+}
+
 __global__ void __launch_bounds__(256) k_join_build_unique(const void* __restrict__ bkey, int width, const uint32_t* __restrict__ validity,
                                                            int64_t n, unsigned long long* __restrict__ slots, uint64_t mask,
-                                                           int* __restrict__ dup_flag) {
+                                                           int* __restrict__ dup_flag, uint32_t* __restrict__ bitmap, int64_t kmin) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride) {
     if (validity && !((validity[row >> 5] >> (row & 31)) & 1u)) continue;  // NULL keys never match (hash_join.rs:177-216)
@@ -2046,6 +2080,10 @@ __global__ void __launch_bounds__(256) k_join_build_unique(const void* __restric
     const uint64_t h = fmix64((uint64_t)key);
     const uint32_t tag = (uint32_t)(h >> 32);
     const unsigned long long mine = ((unsigned long long)tag << 32) | (unsigned long long)(row + 1);
+    if (bitmap) {
+      const uint64_t k = (uint64_t)key - (uint64_t)kmin;
+      atomicOr(&bitmap[k >> 5], 1u << (k & 31));
+    }
     uint64_t sl = h & mask;
     while (true) {
       unsigned long long cur = *(volatile unsigned long long*)&slots[sl];
@@ -2155,10 +2193,13 @@ static bool fused_unordered_join(PlanNode& join, View* out) {
   while (cap < 2 * nb) cap <<= 1;
   DBufP slots = ctx->alloc_zero((size_t)cap * 8);
   DBufP dup = ctx->alloc_zero(8);
+  int64_t jt_kmin = 0;
+  uint64_t jt_kspan = 0;
+  DBufP bitmap = join_key_bitmap(ctx, bv.cols[lk.col_index], nb, &jt_kmin, &jt_kspan);
   if (nb > 0) {
     LAUNCH(ctx, k_join_build_unique, grid_for(ctx, nb, 256), 256, 0, bkey->data->ptr, phys_width(bkey->phys),
            bkey->validity ? (const uint32_t*)bkey->validity->ptr : nullptr, nb, (unsigned long long*)slots->ptr, (uint64_t)(cap - 1),
-           (int*)dup->ptr);
+           (int*)dup->ptr, bitmap ? (uint32_t*)bitmap->ptr : nullptr, jt_kmin);
     if (ctx->read_scalar((const int*)dup->ptr)) return false;
   }
   ctx->trace("  emit-join: build side + table");
@@ -2174,6 +2215,9 @@ static bool fused_unordered_join(PlanNode& join, View* out) {
   P.abort_flag = (int*)((char*)flags->ptr + 8);
   P.jt_slots = (const unsigned long long*)slots->ptr;
   P.jt_mask = (uint64_t)(cap - 1);
+  P.jt_bitmap = bitmap ? (const uint32_t*)bitmap->ptr : nullptr;
+  P.jt_kmin = jt_kmin;
+  P.jt_kspan = jt_kspan;
   P.bkey = nb > 0 ? bkey->data->ptr : slots->ptr;
   P.bkey_width = nb > 0 ? phys_width(bkey->phys) : 8;
   CUDA_CHECK(cudaFuncSetAttribute(k_fused_scan_agg<FM_EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem_bytes));
@@ -2266,10 +2310,13 @@ bool try_fused_join_aggregate(PlanNode& agg, View* out) {
   while (cap < 2 * nb) cap <<= 1;
   DBufP slots = ctx->alloc_zero((size_t)cap * 8);
   DBufP dup = ctx->alloc_zero(8);
+  int64_t jt_kmin = 0;
+  uint64_t jt_kspan = 0;
+  DBufP bitmap = join_key_bitmap(ctx, bv.cols[lk.col_index], nb, &jt_kmin, &jt_kspan);
   if (nb > 0) {
     LAUNCH(ctx, k_join_build_unique, grid_for(ctx, nb, 256), 256, 0, bkey->data->ptr, phys_width(bkey->phys),
            bkey->validity ? (const uint32_t*)bkey->validity->ptr : nullptr, nb, (unsigned long long*)slots->ptr, (uint64_t)(cap - 1),
-           (int*)dup->ptr);
+           (int*)dup->ptr, bitmap ? (uint32_t*)bitmap->ptr : nullptr, jt_kmin);
     if (ctx->read_scalar((const int*)dup->ptr)) return false;  // duplicate build keys: generic join
   }
 
@@ -2294,6 +2341,9 @@ bool try_fused_join_aggregate(PlanNode& agg, View* out) {
   P.abort_flag = (int*)((char*)flags->ptr + 8);
   P.jt_slots = (const unsigned long long*)slots->ptr;
   P.jt_mask = (uint64_t)(cap - 1);
+  P.jt_bitmap = bitmap ? (const uint32_t*)bitmap->ptr : nullptr;
+  P.jt_kmin = jt_kmin;
+  P.jt_kspan = jt_kspan;
   P.bkey = nb > 0 ? bkey->data->ptr : slots->ptr;
   P.bkey_width = nb > 0 ? phys_width(bkey->phys) : 8;
   P.acc_base = 0;

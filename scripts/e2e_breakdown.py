@@ -27,7 +27,7 @@ torch.cuda.empty_cache()
 regs = []
 for k in host:
     regs += bench.pin_batches(host[k])
-print("h2d bytes", sum(bench.batches_nbytes(b) for b in host.values()))
+print("h2d bytes", sum(bench.batches_nbytes(b) for b in host.values()), "pinned buffers", len(regs), "pin failures", bench.PIN_FAILURES)
 for it in range(3):
     ctx.profile(True)
     ctx.profile_report()
