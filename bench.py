@@ -348,17 +348,14 @@ def run_b200(args):
         from qurious_b200 import distributed as qd
         lo = 0 if q == "groupby" else shard_range(tpch.n_lineitems(sf_total), rank, world)[0]
         if q == "groupby":
-            # config 4: hash repartition of (k, v, f) on fmix64(k) % world with NCCL all-to-all over NVLink, then a
-            # purely local aggregate (groups are rank-disjoint afterwards); the result is the concatenation
-            from qurious_b200.physical.plan import MemoryTable
+            # config 4: one kernel partitions the rows by key hash and stores every tuple into its owner's HBM over
+            # NVLink (peer-to-peer), then a purely local aggregate (groups are rank-disjoint); result = concatenation
+
+            xg = qd.ExchangeGroupBy(ctx, plan, world, rank)
 
             def step():
-                recv = qd.hash_repartition(ctx, dev_tables["t"]._dev, 0, world)
-                p = groupby_plan(MemoryTable.from_device_table(recv))
-                p.execute_device(ctx).free()
-                step.strategy = "hash_repartition[all_to_all x%d] -> %s" % (world, p.last_strategy())
-                p.release()
-                recv.free()
+                xg.execute_device().free()
+                step.strategy = "%s x%d -> %s" % (xg.last_path, world, plan.last_strategy())
         elif q == "q3":
             # lineitem row-range shards, build sides replicated (broadcast join); groups straddling a shard boundary
             # are merged by all-gathering the per-rank result rows and re-aggregating them

@@ -240,6 +240,33 @@ int qgpu_table_hash_partition(qgpu_table* t, int32_t key_col, int32_t n_parts, q
 /* device pointer, byte size and value width of a resident fixed-width column's value buffer (valid while `t` lives) */
 int qgpu_table_column_device_buffer(qgpu_table* t, int32_t col, void** ptr, int64_t* bytes, int32_t* value_width);
 
+/* Multi-GPU exchange of a high-cardinality group-by (SURVEY 8e "hash-repartitioned ... over NVLink"; the reference is
+ * single-process, so there is no reference interface behind these).  Plan: (Projection|Filter)* <- HashAggregate <-
+ * (Filter)* <- Scan with integer-like keys.  One process per GPU, every rank runs the same sequence:
+ *   0. qgpu_plan_exchange_keystats -> (min, max) of every group key on this rank (stats[2k], stats[2k+1]; up to 4 keys);
+ *                                     the caller reduces them over the ranks (once per table: they do not change)
+ *   1. qgpu_plan_exchange_sketch   (global (min, max) per key: keys then pack to the same code on every rank)
+ *                                     -> device buffer (histogram of the key hash's top byte + HyperLogLog registers);
+ *                                     the caller all-gathers the blocks (NCCL) and copies them to the host;
+ *                                     *eligible = 0: the keys do not pack into 64 bits (same answer on every rank)
+ *   2. qgpu_plan_exchange_prepare  (gathered blocks, world, rank) -> *n_handles opaque 80-byte handles of this rank's
+ *                                     receive buffers (handles_out must hold 6 of them); *eligible = 0 when the plan
+ *                                     cannot run this way (the same answer on every rank) -- use qgpu_table_hash_partition
+ *   3. the caller all-gathers the handles (rank-major), then
+ *      qgpu_plan_exchange_scatter  partitions this rank's rows and stores every tuple straight into its owner's
+ *                                     buffers (peer-to-peer over NVLink); returns when this rank's stores are issued
+ *   4. the caller runs a barrier, then
+ *      qgpu_plan_exchange_finish   aggregates the tuples this rank received; *overflow != 0 -> a skewed bucket did not
+ *                                     fit (fall back on every rank); otherwise the next qgpu_plan_execute /
+ *                                     qgpu_plan_execute_device of `p` returns this rank's share of the groups.
+ * The whole result is the concatenation of the ranks' results (groups are rank-disjoint). */
+int qgpu_plan_exchange_keystats(qgpu_plan* p, int64_t* stats, int32_t* n_keys);
+int qgpu_plan_exchange_sketch(qgpu_plan* p, const int64_t* global_stats, void** device_buf, int64_t* bytes, int32_t* eligible);
+int qgpu_plan_exchange_prepare(qgpu_plan* p, const void* gathered_host, int32_t world, int32_t rank, void* handles_out,
+                               int32_t* n_handles, int32_t* eligible);
+int qgpu_plan_exchange_scatter(qgpu_plan* p, const void* all_handles_host);
+int qgpu_plan_exchange_finish(qgpu_plan* p, int32_t* overflow);
+
 int qgpu_plan_state_bytes(qgpu_plan* p, int32_t max_groups, int64_t* bytes);
 int qgpu_plan_partial_state(qgpu_plan* p, int64_t row_offset, int32_t max_groups, void* device_buf, int64_t cap_bytes);
 int qgpu_plan_execute_merged(qgpu_plan* p, const void* gathered_device_buf, int32_t n_states, int32_t max_groups,

@@ -28,6 +28,7 @@ SYMBOLS = [
     "qgpu_plan_execute", "qgpu_plan_execute_device", "qgpu_plan_last_stats", "qgpu_plan_strategy",
     "qgpu_plan_free", "qgpu_plan_state_bytes", "qgpu_plan_partial_state", "qgpu_plan_execute_merged",
     "qgpu_table_hash_partition", "qgpu_table_column_device_buffer",
+    "qgpu_plan_exchange_keystats", "qgpu_plan_exchange_sketch", "qgpu_plan_exchange_prepare", "qgpu_plan_exchange_scatter", "qgpu_plan_exchange_finish",
 ]
 
 STATUS_KIND = {1: "InternalError", 2: "ArrowError", 3: "CudaError", 4: "NcclError", 5: "OutOfMemory"}
@@ -116,6 +117,11 @@ def load_library() -> ctypes.CDLL:
     lib.qgpu_plan_free.restype = None
     lib.qgpu_table_hash_partition.argtypes = [vp, i32, i32, P(vp), P(i64)]
     lib.qgpu_table_column_device_buffer.argtypes = [vp, i32, P(vp), P(i64), P(i32)]
+    lib.qgpu_plan_exchange_keystats.argtypes = [vp, P(i64), P(i32)]
+    lib.qgpu_plan_exchange_sketch.argtypes = [vp, P(i64), P(vp), P(i64), P(i32)]
+    lib.qgpu_plan_exchange_prepare.argtypes = [vp, vp, i32, i32, vp, P(i32), P(i32)]
+    lib.qgpu_plan_exchange_scatter.argtypes = [vp, vp]
+    lib.qgpu_plan_exchange_finish.argtypes = [vp, P(i32)]
     lib.qgpu_plan_state_bytes.argtypes = [vp, i32, P(i64)]
     lib.qgpu_plan_partial_state.argtypes = [vp, i64, i32, vp, i64]
     lib.qgpu_plan_execute_merged.argtypes = [vp, vp, i32, i32, vp]

@@ -25,6 +25,7 @@
 // Anything outside this shape (NULLs, OR/!=, wide decimals, computed keys, ...) returns false and the
 // generic interpreter path (ops.cu) runs instead: same results, lower speed.
 #include <algorithm>
+#include <unistd.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1314,8 +1315,10 @@ struct FusedPlan {
   // RADIX (radix_agg.cuh): usable when the plan is a HASH-mode plan with integer-like keys and few operand values
   bool radix_ok = false;
   bool radix_failed = false;  // overflowed or declined (few groups) once on this table: stay on FM_HASH
+  std::shared_ptr<void> exchange;  // RadixExchange: state of a multi-GPU exchange in flight + its receive buffers
   RParams R;                  // comps / comp_of / kind_of filled by the analysis
   int key_bits[F_MAXK] = {0, 0, 0, 0}, key_shift[F_MAXK] = {0, 0, 0, 0}, key_width[F_MAXK] = {0, 0, 0, 0};
+  int64_t key_min[F_MAXK] = {0, 0, 0, 0}, key_max[F_MAXK] = {0, 0, 0, 0};  // value range of every key column (this table)
   std::vector<DColP> key_src;  // source column of every key (type / phys of the decoded key column)
   // validity of the cache
   std::vector<const DCol*> col_ids;
@@ -1462,6 +1465,8 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
       fk.mult = (uint64_t)dense_groups;  // provisional (dense)
       fk.pad = bits;
       fp.key_bits[i] = bits;
+      fp.key_min[i] = (int64_t)A.slots[slot].vmin;
+      fp.key_max[i] = (int64_t)A.slots[slot].vmax;
       fp.key_width[i] = A.slots[slot].dict ? 0 : phys_width(A.slots[slot].col->phys);
       fp.key_src.push_back(v.cols[keys[i]->column_ref].base);
       if (dense_ok) {
@@ -1687,59 +1692,39 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
 
 
 // ------------------------------------------------------------------------------------------------
-// RADIX mode driver (kernels: radix_agg.cuh).  Returns false when the radix path declines (few groups: the
-// L2-resident FM_HASH table is the better plan) or overflowed (estimate off / skewed bucket): FM_HASH then runs.
+// RADIX mode driver (kernels: radix_agg.cuh).  run_radix returns false when the radix path declines (few groups:
+// the L2-resident FM_HASH table is the better plan) or overflowed (estimate off / skewed bucket): FM_HASH then runs.
+// The same stages, cut at the level-1 scatter, form the multi-GPU exchange (radix_exchange_* below).
 // ------------------------------------------------------------------------------------------------
-static bool run_radix(PlanNode& agg, const View& v, FusedPlan& fp, View* out) {
-  Ctx* ctx = agg.ctx;
-  const FParams& P = fp.P;
-  const char* mode_env = getenv("QGPU_RADIX");  // "off": never, "force": whenever the shape allows (tests)
-  const bool force = mode_env && strcmp(mode_env, "force") == 0;
-  if (mode_env && strcmp(mode_env, "off") == 0) return false;
-  const int64_t n_rows = P.n_rows;
-  if (!force && n_rows < ((int64_t)1 << 24)) return false;
-  RParams R = fp.R;
-  // ---- pass 0: level-1 histogram + HyperLogLog sketch ---------------------------------------------------------
-  // layout of the small state block: hll[4096] u32 | hist1[256] u32 | tpre[257] u32 (+pad) | off1[257] u64 | cur1[256] u64 |
-  //                                  n_out u64 | overflow int
-  const size_t o_hll = 0, o_hist1 = o_hll + R_HLL_M * 4, o_tpre = o_hist1 + R_P1 * 4, o_off1 = o_tpre + 260 * 4,
-               o_cur1 = o_off1 + 257 * 8, o_nout = o_cur1 + 256 * 8, o_ovf = o_nout + 8, st_bytes = o_ovf + 8;
-  DBufP st = ctx->alloc_zero(st_bytes);
+namespace {
+// small device state block: hll[4096] u32 | hist1[256] u32 | tpre[257] u32 (+pad) | off1[257] u64 | cur1[256] u64 | n_out u64 | overflow
+constexpr size_t RO_HLL = 0, RO_HIST1 = RO_HLL + R_HLL_M * 4, RO_TPRE = RO_HIST1 + R_P1 * 4, RO_OFF1 = RO_TPRE + 260 * 4,
+                 RO_CUR1 = RO_OFF1 + 257 * 8, RO_NOUT = RO_CUR1 + 256 * 8, RO_OVF = RO_NOUT + 8, RO_BYTES = RO_OVF + 8;
+constexpr size_t R_SKETCH_BYTES = RO_TPRE;  // hll + hist1: what the ranks exchange
+}  // namespace
+
+static DBufP radix_state_block(Ctx* ctx, RParams& R) {
+  DBufP st = ctx->alloc_zero(RO_BYTES);
   char* sp = (char*)st->ptr;
-  R.hll = (unsigned int*)(sp + o_hll);
-  R.hist1 = (unsigned int*)(sp + o_hist1);
-  R.tpre = (unsigned int*)(sp + o_tpre);
-  R.off1 = (unsigned long long*)(sp + o_off1);
-  R.cur1 = (unsigned long long*)(sp + o_cur1);
-  R.n_out = (unsigned long long*)(sp + o_nout);
-  R.overflow = (int*)(sp + o_ovf);
-  const int grid1 = (int)std::min<int64_t>(P.n_tiles, (int64_t)ctx->sm_count * 8);
-  LAUNCH(ctx, k_radix_hist1, grid1, R_NT, 0, P, R.hist1, R.hll);
-  LAUNCH(ctx, k_radix_scan1, 1, R_P1, 0, R.hist1, R.off1, R.cur1, R.tpre);
-  std::vector<unsigned char> hst(o_cur1);
-  ctx->d2h_sync(hst.data(), sp, o_cur1);
-  const double est = hll_estimate((const unsigned int*)(hst.data() + o_hll));
-  const int64_t n_tuples = (int64_t)((const unsigned long long*)(hst.data() + o_off1))[R_P1];
-  const unsigned int n_tiles2 = ((const unsigned int*)(hst.data() + o_tpre))[R_P1];
-  ctx->trace("radix: hist1 + sketch");
-  if (n_tuples == 0) return false;
-  // ---- plan: level-2 fan-out, table capacity, output size --------------------------------------------------------
-  // final pass shared memory: 16 B per table slot (key, row count, first staged row) + per staged row 8 B per operand
-  // value and 4 B (slot, rank); the table should stay below ~45 % load, the staging area needs ~15 % headroom
+  R.hll = (unsigned int*)(sp + RO_HLL);
+  R.hist1 = (unsigned int*)(sp + RO_HIST1);
+  R.tpre = (unsigned int*)(sp + RO_TPRE);
+  R.off1 = (unsigned long long*)(sp + RO_OFF1);
+  R.cur1 = (unsigned long long*)(sp + RO_CUR1);
+  R.n_out = (unsigned long long*)(sp + RO_NOUT);
+  R.overflow = (int*)(sp + RO_OVF);
+  return st;
+}
+
+// level-2 fan-out, shared-memory table capacity and staging rows of the final pass for `groups` groups in n_tuples rows.
+// final pass shared memory: 18 B per table slot (key, row count, first staged row, occupied list) + per staged row 8 B
+// per operand value and 4 B (slot, rank); the table stays below ~45 % load, the staging area keeps ~15 % headroom
+static bool radix_choose(const RParams& R, double groups, int64_t n_tuples, int l1_buckets, int* b2_out, int* cap_out, int* row_cap_out) {
   const size_t smem_budget = (size_t)F_SMEM_MAX - 256;
   const size_t row_bytes = 8 * (size_t)(R.n_comp - 1) + 4;
-  const double groups = std::min(est * 1.05 + 64.0, (double)n_tuples);
-  if (!force && groups < 4.0e6) {
-    // the hash table stays (mostly) L2-resident: FM_HASH, sized from the estimate so that it does not grow
-    int64_t c = 1 << 12;
-    while ((double)c < 2.2 * groups) c <<= 1;
-    fp.learned_cap = std::max(fp.learned_cap, c);
-    fp.radix_failed = true;  // same table, same answer: do not sketch again
-    return false;
-  }
   int b2 = 0, cap = 0, row_cap = 0;
   for (b2 = 1; b2 <= R_MAXB2; ++b2) {
-    const double nb = (double)((int64_t)R_P1 << b2);
+    const double nb = (double)((int64_t)std::max(l1_buckets, 1) << b2);  // populated final buckets
     const double g_b = groups / nb, r_b = (double)n_tuples / nb;
     cap = 64;
     while (cap < 4096 && g_b > 0.45 * cap) cap *= 2;
@@ -1755,18 +1740,36 @@ static bool run_radix(PlanNode& agg, const View& v, FusedPlan& fp, View* out) {
     b2 = 1;
     row_cap = (int)std::min<size_t>((smem_budget - (size_t)(cap + 1) * 18 - 16) / row_bytes, (size_t)1 << 18);
   }
-  R.b2 = b2;
-  R.cap = cap;
-  R.row_cap = row_cap;
+  *b2_out = b2;
+  *cap_out = cap;
+  *row_cap_out = row_cap;
+  return true;
+}
+
+static size_t radix_scatter_smem(const RParams& R) { return (size_t)R.n_comp * R_T * 8 + 512 * 8 + 512 * 4 * 2 + (size_t)R_T * 2; }
+
+static void radix_launch_scatter1(Ctx* ctx, const FParams& P, const RParams& R) {
+  const size_t sc_smem = radix_scatter_smem(R);
+  CUDA_CHECK(cudaFuncSetAttribute(k_radix_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
+  const int sc_per_sm = (2 * (sc_smem + 1024 + 64) <= (size_t)233472) ? 2 : 1;
+  const int64_t tiles1 = (P.n_rows + R_T - 1) / R_T;
+  LAUNCH(ctx, k_radix_scatter<1>, (int)std::max<int64_t>(1, std::min<int64_t>(tiles1, (int64_t)ctx->sm_count * sc_per_sm)), R_SNT, sc_smem, P, R);
+}
+
+// level-1 tuples (R.tup_a, bucket offsets R.off1 / tile list R.tpre on the device) -> level 2 -> final pass -> View.
+// returns false on overflow (*fail = the kernel's code)
+static bool radix_tail(PlanNode& agg, const View& v, FusedPlan& fp, const FParams& P, const int* key_shift, const int* key_bits, RParams& R,
+                       const DBufP& st, int64_t n_tuples, unsigned int n_tiles2, double est, View* out, int* fail) {
+  Ctx* ctx = agg.ctx;
+  const int b2 = R.b2, cap = R.cap, row_cap = R.row_cap;
+  const size_t row_bytes = 8 * (size_t)(R.n_comp - 1) + 4;
   const int64_t n_buckets = (int64_t)R_P1 << b2;
-  const int64_t out_cap = std::min<int64_t>(n_tuples, (int64_t)(est * 1.15) + 65536);
+  const int64_t out_cap = std::max<int64_t>(1, std::min<int64_t>(n_tuples, (int64_t)(est * 1.15) + 65536));
   R.out_cap = out_cap;
   std::vector<DBufP> keep;
   for (int c = 0; c < R.n_comp; ++c) {
-    DBufP a = ctx->alloc((size_t)n_tuples * 8 + 64), b = ctx->alloc((size_t)n_tuples * 8 + 64);
-    R.tup_a[c] = (unsigned long long*)a->ptr;
+    DBufP b = ctx->alloc((size_t)n_tuples * 8 + 64);
     R.tup_b[c] = (unsigned long long*)b->ptr;
-    keep.push_back(a);
     keep.push_back(b);
   }
   DBufP hist2 = ctx->alloc_zero((size_t)n_buckets * 4), off2 = ctx->alloc((size_t)(n_buckets + 1) * 8), cur2 = ctx->alloc((size_t)n_buckets * 8);
@@ -1781,28 +1784,24 @@ static bool run_radix(PlanNode& agg, const View& v, FusedPlan& fp, View* out) {
     out_acc.push_back(ctx->alloc((size_t)out_cap * 8 + 64));
     R.out_acc[k] = (unsigned long long*)out_acc.back()->ptr;
   }
-  // ---- passes ----------------------------------------------------------------------------------------------------
-  const size_t sc_smem = (size_t)R.n_comp * R_T * 8 + 512 * 8 + 512 * 4 * 2 + (size_t)R_T * 2;
-  CUDA_CHECK(cudaFuncSetAttribute(k_radix_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
+  const size_t sc_smem = radix_scatter_smem(R);
   CUDA_CHECK(cudaFuncSetAttribute(k_radix_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
   const int sc_per_sm = (2 * (sc_smem + 1024 + 64) <= (size_t)233472) ? 2 : 1;
-  const int64_t tiles1 = (n_rows + R_T - 1) / R_T;
-  LAUNCH(ctx, k_radix_scatter<1>, (int)std::min<int64_t>(tiles1, (int64_t)ctx->sm_count * sc_per_sm), R_SNT, sc_smem, P, R);
-  LAUNCH(ctx, k_radix_hist2, (int)std::min<int64_t>(std::max<int64_t>(n_tiles2, 1), (int64_t)ctx->sm_count * 8), R_NT, 0, R);
-  LAUNCH(ctx, k_radix_scan2, 1, 1024, 0, R.hist2, (int)n_buckets, R.off2, R.cur2);
+  RParams R2 = R;
+  R2.world = 1;  // level 2 and the final pass are local
+  LAUNCH(ctx, k_radix_hist2, (int)std::min<int64_t>(std::max<int64_t>(n_tiles2, 1), (int64_t)ctx->sm_count * 8), R_NT, 0, R2);
+  LAUNCH(ctx, k_radix_scan2, 1, 1024, 0, R2.hist2, (int)n_buckets, R2.off2, R2.cur2);
   LAUNCH(ctx, k_radix_scatter<2>, (int)std::min<int64_t>(std::max<int64_t>(n_tiles2, 1), (int64_t)ctx->sm_count * sc_per_sm), R_SNT, sc_smem,
-         P, R);
+         P, R2);
   const size_t ag_smem = (size_t)(cap + 1) * 18 + (size_t)row_cap * row_bytes + 64;
   CUDA_CHECK(cudaFuncSetAttribute(k_radix_agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ag_smem));
-  LAUNCH(ctx, k_radix_agg, (int)std::min<int64_t>(n_buckets, (int64_t)ctx->sm_count), R_AGG_NT, ag_smem, R);
+  LAUNCH(ctx, k_radix_agg, (int)std::min<int64_t>(n_buckets, (int64_t)ctx->sm_count), R_AGG_NT, ag_smem, R2);
   unsigned long long fin[2];
-  ctx->d2h_sync(fin, sp + o_nout, 16);
-  ctx->trace("radix: partition passes + aggregate");
+  ctx->d2h_sync(fin, (char*)st->ptr + RO_NOUT, 16);
+  ctx->trace("radix: level 2 + aggregate");
   const int64_t n_groups = (int64_t)fin[0];
-  if ((int)fin[1] != 0) {
-    fp.radix_failed = true;  // FM_HASH from now on (the results of this attempt are discarded)
-    return false;
-  }
+  *fail = (int)fin[1];
+  if (*fail != 0) return false;
   keep.clear();
   // ---- key columns from the packed codes --------------------------------------------------------------------------
   RKeys rk;
@@ -1816,8 +1815,8 @@ static bool run_radix(PlanNode& agg, const View& v, FusedPlan& fp, View* out) {
     d->length = n_groups;
     d->null_count = 0;
     d->data = ctx->alloc(std::max<size_t>((size_t)n_groups * fp.key_width[k], 16));
-    rk.shift[k] = fp.key_shift[k];
-    rk.bits[k] = fp.key_bits[k];
+    rk.shift[k] = key_shift[k];
+    rk.bits[k] = key_bits[k];
     rk.width[k] = fp.key_width[k];
     rk.base[k] = P.keys[k].base;
     rk.out[k] = d->data->ptr;
@@ -1850,11 +1849,57 @@ static bool run_radix(PlanNode& agg, const View& v, FusedPlan& fp, View* out) {
     accs.cnt.push_back(out_cnt);
   }
   agg.strategy = "fused_scan_agg[radix-partitioned: 256 x " + std::to_string(1 << b2) + " buckets, smem table " + std::to_string(cap) +
-                 " slots / " + std::to_string(row_cap) + " rows, " + std::to_string(R.n_comp) + " x 8 B tuples, " + std::to_string(P.n_cols) + " cols, " +
-                 std::to_string(P.n_pred) + " range preds, " + std::to_string(P.n_accs) + " accs, est " +
-                 std::to_string((int64_t)est) + " groups]";
+                 " slots / " + std::to_string(row_cap) + " rows, " + std::to_string(R.n_comp) + " x 8 B tuples, " +
+                 std::to_string(P.n_cols) + " cols, " + std::to_string(P.n_pred) + " range preds, " + std::to_string(P.n_accs) +
+                 " accs, est " + std::to_string((int64_t)est) + " groups]";
   *out = finish_aggregate(ctx, v, fp.keys, fp.specs, agg.schema, accs, &key_cols, nullptr);
   ctx->trace("radix: finish_aggregate");
+  return true;
+}
+
+static bool run_radix(PlanNode& agg, const View& v, FusedPlan& fp, View* out) {
+  Ctx* ctx = agg.ctx;
+  const FParams& P = fp.P;
+  const char* mode_env = getenv("QGPU_RADIX");  // "off": never, "force": whenever the shape allows (tests)
+  const bool force = mode_env && strcmp(mode_env, "force") == 0;
+  if (mode_env && strcmp(mode_env, "off") == 0) return false;
+  if (!force && P.n_rows < ((int64_t)1 << 24)) return false;
+  RParams R = fp.R;
+  R.world = 1;
+  // ---- pass 0: level-1 histogram + HyperLogLog sketch ---------------------------------------------------------
+  DBufP st = radix_state_block(ctx, R);
+  const int grid1 = (int)std::min<int64_t>(P.n_tiles, (int64_t)ctx->sm_count * 8);
+  LAUNCH(ctx, k_radix_hist1, grid1, R_NT, 0, P, R.hist1, R.hll);
+  LAUNCH(ctx, k_radix_scan1, 1, R_P1, 0, R.hist1, R.off1, R.cur1, R.tpre);
+  std::vector<unsigned char> hst(RO_CUR1);
+  ctx->d2h_sync(hst.data(), st->ptr, RO_CUR1);
+  const double est = hll_estimate((const unsigned int*)(hst.data() + RO_HLL));
+  const int64_t n_tuples = (int64_t)((const unsigned long long*)(hst.data() + RO_OFF1))[R_P1];
+  const unsigned int n_tiles2 = ((const unsigned int*)(hst.data() + RO_TPRE))[R_P1];
+  ctx->trace("radix: hist1 + sketch");
+  if (n_tuples == 0) return false;
+  const double groups = std::min(est * 1.05 + 64.0, (double)n_tuples);
+  if (!force && groups < 4.0e6) {
+    // the hash table stays (mostly) L2-resident: FM_HASH, sized from the estimate so that it does not grow
+    int64_t c = 1 << 12;
+    while ((double)c < 2.2 * groups) c <<= 1;
+    fp.learned_cap = std::max(fp.learned_cap, c);
+    fp.radix_failed = true;  // same table, same answer: do not sketch again
+    return false;
+  }
+  if (!radix_choose(R, groups, n_tuples, R_P1, &R.b2, &R.cap, &R.row_cap)) return false;
+  std::vector<DBufP> keep;
+  for (int c = 0; c < R.n_comp; ++c) {
+    DBufP a = ctx->alloc((size_t)n_tuples * 8 + 64);
+    R.tup_a[c] = (unsigned long long*)a->ptr;
+    keep.push_back(a);
+  }
+  radix_launch_scatter1(ctx, P, R);
+  int fail = 0;
+  if (!radix_tail(agg, v, fp, P, fp.key_shift, fp.key_bits, R, st, n_tuples, n_tiles2, est, out, &fail)) {
+    fp.radix_failed = true;  // FM_HASH from now on (the results of this attempt are discarded)
+    return false;
+  }
   return true;
 }
 
@@ -2430,18 +2475,18 @@ bool try_fused_join_aggregate(PlanNode& agg, View* out) {
   return true;
 }
 
-bool try_fused_scan_aggregate(PlanNode& agg, View* out) {
-  // ---- shape: Aggregate <- (Filter <-)* Scan --------------------------------------------------------
+// analysis (cached on the node) of Aggregate <- (Filter <-)* Scan; null when the subtree has another shape
+static std::shared_ptr<FusedPlan> fused_plan_for(PlanNode& agg, View* vout) {
   std::vector<const ExprNode*> predicates;
   PlanNode* n = agg.children[0].get();
   while (n->kind == PK_FILTER) {
     predicates.push_back(n->predicate.get());
     n = n->children[0].get();
   }
-  if (n->kind != PK_SCAN) return false;
+  if (n->kind != PK_SCAN) return nullptr;
   if (n->predicate) predicates.push_back(n->predicate.get());
   View v = scan_view(*n);
-  if (v.num_batches == 0 || v.num_rows == 0 || v.num_rows >= ((int64_t)1 << 40)) return false;
+  if (v.num_batches == 0 || v.num_rows == 0 || v.num_rows >= ((int64_t)1 << 40)) return nullptr;
   std::shared_ptr<FusedPlan> fp = std::static_pointer_cast<FusedPlan>(agg.fused_cache);
   bool fresh = false;
   if (fp) {
@@ -2456,9 +2501,246 @@ bool try_fused_scan_aggregate(PlanNode& agg, View* out) {
     for (auto& c : v.cols) fp->col_ids.push_back(c.base.get());
     agg.fused_cache = fp;
   }
-  if (!fp->usable) return false;
+  *vout = v;
+  return fp;
+}
+
+bool try_fused_scan_aggregate(PlanNode& agg, View* out) {
+  View v;
+  std::shared_ptr<FusedPlan> fp = fused_plan_for(agg, &v);
+  if (!fp || !fp->usable) return false;
   *out = run_fused(agg, v, *fp);
   return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU exchange of a high-cardinality group-by (BASELINE.json configs[3]): the radix aggregate cut
+// at its level-1 scatter.  Level-1 bucket b (top 8 hash bits) belongs to rank b % world; every rank scatters its
+// tuples STRAIGHT INTO THE OWNER'S tuple arrays with peer-to-peer stores over NVLink (one kernel partitions and
+// exchanges; no send buffers, no NCCL all-to-all), then runs level 2 + the final pass on the buckets it owns.
+//   sketch   local 256-bin histogram + HyperLogLog registers                     (caller: all-gather, 17 KB per rank)
+//   prepare  owner-side bucket offsets, this rank's write cursors inside every owner's arrays, receive buffers
+//            (cudaMalloc, exported as CUDA IPC handles)                           (caller: all-gather of the handles)
+//   scatter  k_radix_scatter<1> with peer destinations                            (caller: barrier)
+//   finish   level 2 + final pass over the received tuples -> the aggregate's result (consumed by the next execute)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct ExHandle {  // what a rank publishes per tuple component
+  uint64_t raw_ptr, pid;
+  cudaIpcMemHandle_t ipc;
+};
+struct RadixExchange {
+  Ctx* ctx = nullptr;
+  FParams P;   // the plan re-based on the GLOBAL key ranges: a key packs to the same code (and hash) on every rank
+  int key_shift[F_MAXK] = {0, 0, 0, 0}, key_bits[F_MAXK] = {0, 0, 0, 0};
+  RParams R;
+  DBufP st;
+  View view;
+  int world = 0, rank = 0;
+  double est_owned = 0;
+  int64_t n_owned = 0;
+  unsigned int n_tiles2 = 0;
+  void* recv[R_MAXCOMP] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t recv_cap = 0;  // bytes per component
+  std::vector<std::pair<std::string, void*>> opened;
+  ~RadixExchange() {
+    for (auto& o : opened) cudaIpcCloseMemHandle(o.second);
+    for (void* p : recv)
+      if (p) cudaFree(p);
+  }
+};
+}  // namespace
+
+static std::shared_ptr<FusedPlan> exchange_plan(PlanNode& root, PlanNode** agg_out, View* v) {
+  PlanNode* agg = find_aggregate_node(root);
+  std::shared_ptr<FusedPlan> fp = fused_plan_for(*agg, v);
+  if (!fp || !fp->usable || !fp->radix_ok)
+    throw_internal("exchange needs a radix-eligible group-by over a table scan (integer-like keys, at most 5 operand values, "
+                   "64-bit sums)");
+  *agg_out = agg;
+  return fp;
+}
+
+void radix_exchange_keystats(PlanNode& root, int64_t* stats, int32_t* n_keys) {
+  PlanNode* agg;
+  View v;
+  std::shared_ptr<FusedPlan> fp = exchange_plan(root, &agg, &v);
+  *n_keys = fp->P.n_keys;
+  for (int k = 0; k < fp->P.n_keys; ++k) {
+    stats[2 * k] = fp->key_min[k];
+    stats[2 * k + 1] = fp->key_max[k];
+  }
+}
+
+int radix_exchange_sketch(PlanNode& root, const int64_t* global_stats, void** dev_buf, int64_t* bytes) {
+  PlanNode* agg;
+  View v;
+  std::shared_ptr<FusedPlan> fp = exchange_plan(root, &agg, &v);
+  Ctx* ctx = agg->ctx;
+  auto ex = std::static_pointer_cast<RadixExchange>(fp->exchange);
+  if (!ex) {
+    ex = std::make_shared<RadixExchange>();
+    ex->ctx = ctx;
+    fp->exchange = ex;
+  }
+  // re-base the packed key on the global value ranges (min over ranks, max over ranks)
+  ex->P = fp->P;
+  int shift = 0;
+  for (int k = 0; k < ex->P.n_keys; ++k) {
+    const i128 lo = global_stats[2 * k], hi = global_stats[2 * k + 1];
+    if (lo > fp->key_min[k] || hi < fp->key_max[k]) throw_internal("exchange: the global key range does not cover this rank's keys");
+    const i128 range = hi - lo + 1;
+    int bits = 0;
+    while (((i128)1 << bits) < range) ++bits;
+    ex->P.keys[k].base = (int64_t)lo;
+    ex->P.keys[k].mult = shift >= 64 ? 0 : (1ull << shift);
+    ex->key_shift[k] = shift;
+    ex->key_bits[k] = bits;
+    shift += bits;
+  }
+  *dev_buf = nullptr;
+  *bytes = (int64_t)R_SKETCH_BYTES;
+  if (shift > 64) return 1;  // the keys do not pack into 64 bits over the global ranges (the same answer on every rank)
+  ex->R = fp->R;
+  ex->view = v;
+  ex->st = radix_state_block(ctx, ex->R);
+  const FParams& P = ex->P;
+  LAUNCH(ctx, k_radix_hist1, (int)std::max<int64_t>(1, std::min<int64_t>(P.n_tiles, (int64_t)ctx->sm_count * 8)), R_NT, 0, P, ex->R.hist1,
+         ex->R.hll);
+  *dev_buf = ex->st->ptr;
+  return 0;
+}
+
+int radix_exchange_prepare(PlanNode& root, const void* gathered_host, int world, int rank, void* handles_out, int32_t* n_handles) {
+  PlanNode* agg;
+  View v;
+  std::shared_ptr<FusedPlan> fp = exchange_plan(root, &agg, &v);
+  Ctx* ctx = agg->ctx;
+  auto ex = std::static_pointer_cast<RadixExchange>(fp->exchange);
+  if (!ex || !ex->st) throw_internal("exchange: prepare without sketch");
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) throw_internal("exchange: world must be in [1, 8]");
+  ex->world = world;
+  ex->rank = rank;
+  RParams& R = ex->R;
+  // ---- merge the sketches: HyperLogLog registers by max, histograms kept per source rank --------------------------------
+  std::vector<unsigned int> hll(R_HLL_M, 0);
+  std::vector<const unsigned int*> hist((size_t)world);
+  for (int s = 0; s < world; ++s) {
+    const unsigned int* blk = (const unsigned int*)((const char*)gathered_host + (size_t)s * R_SKETCH_BYTES);
+    for (int i = 0; i < R_HLL_M; ++i) hll[i] = std::max(hll[i], blk[RO_HLL / 4 + i]);
+    hist[s] = blk + RO_HIST1 / 4;
+  }
+  const double est = hll_estimate(hll.data());
+  // ---- bucket b belongs to rank b % world: owner-side layout and this rank's cursors ------------------------------------
+  std::vector<unsigned long long> off1(R_P1 + 1, 0), cur1(R_P1, 0), owner_fill((size_t)world, 0);
+  std::vector<unsigned int> tpre(R_P1 + 1, 0);
+  std::vector<int64_t> owned((size_t)world, 0);
+  int64_t total = 0;
+  for (int b = 0; b < R_P1; ++b) {
+    const int o = b % world;
+    unsigned long long tot_b = 0, before_me = 0;
+    for (int s = 0; s < world; ++s) {
+      if (s < rank) before_me += hist[s][b];
+      tot_b += hist[s][b];
+    }
+    cur1[b] = owner_fill[o] + before_me;  // where my tuples of bucket b start inside the owner's arrays
+    owner_fill[o] += tot_b;
+    owned[o] += (int64_t)tot_b;
+    total += (int64_t)tot_b;
+    const unsigned long long mine_b = o == rank ? tot_b : 0;  // as an owner: non-owned buckets are empty here
+    off1[b + 1] = off1[b] + mine_b;
+    tpre[b + 1] = tpre[b] + (unsigned int)((mine_b + R_T - 1) / R_T);
+  }
+  // eligibility must be the same decision on every rank: test every owner's share
+  int ok = 1;
+  for (int o = 0; o < world && ok; ++o) {
+    if (owned[o] == 0) continue;
+    const double g_o = std::min(est * ((double)owned[o] / (double)std::max<int64_t>(total, 1)) * 1.05 + 64.0, (double)owned[o]);
+    int b2, cap, rc;
+    if (!radix_choose(R, g_o, owned[o], (R_P1 - o + world - 1) / world, &b2, &cap, &rc)) ok = 0;
+  }
+  *n_handles = R.n_comp;
+  if (!ok) return 1;
+  ex->n_owned = owned[rank];
+  ex->n_tiles2 = tpre[R_P1];
+  ex->est_owned = est * ((double)owned[rank] / (double)std::max<int64_t>(total, 1));
+  const double g_me = std::min(ex->est_owned * 1.05 + 64.0, (double)std::max<int64_t>(owned[rank], 1));
+  if (!radix_choose(R, g_me, std::max<int64_t>(owned[rank], 1), (R_P1 - rank + world - 1) / world, &R.b2, &R.cap, &R.row_cap)) return 1;
+  char* sp = (char*)ex->st->ptr;
+  ctx->h2d(sp + RO_OFF1, off1.data(), (R_P1 + 1) * 8);
+  ctx->h2d(sp + RO_TPRE, tpre.data(), (R_P1 + 1) * 4);
+  ctx->h2d(sp + RO_CUR1, cur1.data(), R_P1 * 8);
+  ctx->sync();
+  // ---- receive buffers: plain cudaMalloc (exportable through CUDA IPC), kept across executions ----------------------------
+  const size_t need = (size_t)owned[rank] * 8 + 256;
+  if (need > ex->recv_cap) {
+    ctx->sync();
+    for (int c = 0; c < R_MAXCOMP; ++c) {
+      if (ex->recv[c]) CUDA_CHECK(cudaFree(ex->recv[c]));
+      ex->recv[c] = nullptr;
+    }
+    ex->recv_cap = need + need / 8 + ((size_t)1 << 20);
+    for (int c = 0; c < R.n_comp; ++c) CUDA_CHECK(cudaMalloc(&ex->recv[c], ex->recv_cap));
+  }
+  ExHandle* hs = (ExHandle*)handles_out;
+  for (int c = 0; c < R.n_comp; ++c) {
+    memset(&hs[c], 0, sizeof(ExHandle));
+    hs[c].raw_ptr = (uint64_t)(uintptr_t)ex->recv[c];
+    hs[c].pid = (uint64_t)getpid();
+    if (world > 1) CUDA_CHECK(cudaIpcGetMemHandle(&hs[c].ipc, ex->recv[c]));
+  }
+  return 0;
+}
+
+void radix_exchange_scatter(PlanNode& root, const void* all_handles) {
+  PlanNode* agg;
+  View v;
+  std::shared_ptr<FusedPlan> fp = exchange_plan(root, &agg, &v);
+  Ctx* ctx = agg->ctx;
+  auto ex = std::static_pointer_cast<RadixExchange>(fp->exchange);
+  if (!ex || ex->world == 0) throw_internal("exchange: scatter without prepare");
+  RParams& R = ex->R;
+  const ExHandle* hs = (const ExHandle*)all_handles;
+  R.world = ex->world;
+  for (int o = 0; o < ex->world; ++o)
+    for (int c = 0; c < R.n_comp; ++c) {
+      const ExHandle& h = hs[(size_t)o * R.n_comp + c];
+      void* ptr = nullptr;
+      if (o == ex->rank) {
+        ptr = ex->recv[c];
+      } else if (h.pid == (uint64_t)getpid()) {
+        ptr = (void*)(uintptr_t)h.raw_ptr;  // ranks emulated inside one process (tests): the pointer is directly usable
+      } else {
+        const std::string key((const char*)&h.ipc, sizeof(h.ipc));
+        for (auto& op : ex->opened)
+          if (op.first == key) ptr = op.second;
+        if (!ptr) {
+          CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, h.ipc, cudaIpcMemLazyEnablePeerAccess));
+          ex->opened.push_back({key, ptr});
+        }
+      }
+      R.peer_a[o][c] = (unsigned long long*)ptr;
+    }
+  for (int c = 0; c < R.n_comp; ++c) R.tup_a[c] = (unsigned long long*)ex->recv[c];
+  radix_launch_scatter1(ctx, ex->P, R);
+  ctx->sync();  // my stores have left; the caller's barrier then makes every rank's stores complete
+  ctx->trace("exchange: scatter over peer memory");
+}
+
+int radix_exchange_finish(PlanNode& root) {
+  PlanNode* agg;
+  View v;
+  std::shared_ptr<FusedPlan> fp = exchange_plan(root, &agg, &v);
+  auto ex = std::static_pointer_cast<RadixExchange>(fp->exchange);
+  if (!ex || ex->world == 0) throw_internal("exchange: finish without scatter");
+  View out;
+  int fail = 0;
+  if (!radix_tail(*agg, ex->view, *fp, ex->P, ex->key_shift, ex->key_bits, ex->R, ex->st, ex->n_owned, ex->n_tiles2, ex->est_owned, &out,
+                  &fail))
+    return fail ? fail : 1;
+  agg->strategy = "exchange[rank " + std::to_string(ex->rank) + "/" + std::to_string(ex->world) + ", p2p scatter] -> " + agg->strategy;
+  agg->merged_override = std::make_shared<View>(out);
+  return 0;
 }
 
 }  // namespace qgpu

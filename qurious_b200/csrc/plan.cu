@@ -715,6 +715,37 @@ int qgpu_plan_execute_merged(qgpu_plan* p, const void* gathered, int32_t n_state
   });
 }
 
+int qgpu_plan_exchange_keystats(qgpu_plan* p, int64_t* stats, int32_t* n_keys) {
+  if (!p || !stats || !n_keys) return QGPU_ERR_INTERNAL;
+  PlanNode& n = *p->node;
+  return guard(n.ctx, [&] { radix_exchange_keystats(n, stats, n_keys); });
+}
+
+int qgpu_plan_exchange_sketch(qgpu_plan* p, const int64_t* global_stats, void** device_buf, int64_t* bytes, int32_t* eligible) {
+  if (!p || !global_stats || !device_buf || !bytes || !eligible) return QGPU_ERR_INTERNAL;
+  PlanNode& n = *p->node;
+  return guard(n.ctx, [&] { *eligible = radix_exchange_sketch(n, global_stats, device_buf, bytes) == 0 ? 1 : 0; });
+}
+
+int qgpu_plan_exchange_prepare(qgpu_plan* p, const void* gathered_host, int32_t world, int32_t rank, void* handles_out,
+                               int32_t* n_handles, int32_t* eligible) {
+  if (!p || !gathered_host || !handles_out || !n_handles || !eligible) return QGPU_ERR_INTERNAL;
+  PlanNode& n = *p->node;
+  return guard(n.ctx, [&] { *eligible = radix_exchange_prepare(n, gathered_host, world, rank, handles_out, n_handles) == 0 ? 1 : 0; });
+}
+
+int qgpu_plan_exchange_scatter(qgpu_plan* p, const void* all_handles_host) {
+  if (!p || !all_handles_host) return QGPU_ERR_INTERNAL;
+  PlanNode& n = *p->node;
+  return guard(n.ctx, [&] { radix_exchange_scatter(n, all_handles_host); });
+}
+
+int qgpu_plan_exchange_finish(qgpu_plan* p, int32_t* overflow) {
+  if (!p || !overflow) return QGPU_ERR_INTERNAL;
+  PlanNode& n = *p->node;
+  return guard(n.ctx, [&] { *overflow = radix_exchange_finish(n); });
+}
+
 int qgpu_plan_execute_device(qgpu_plan* p, qgpu_table** out, int64_t* out_batches) {
   if (!p || !out) return QGPU_ERR_INTERNAL;
   PlanNode& n = *p->node;

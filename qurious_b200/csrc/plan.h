@@ -58,6 +58,13 @@ void shard_partial_state(PlanNode& root, int64_t row_offset, int32_t max_groups,
 int64_t shard_state_bytes(PlanNode& root, int32_t max_groups);
 View shard_execute_merged(PlanNode& root, const void* gathered, int32_t n_states, int32_t max_groups);
 
+// fused.cu: multi-GPU exchange of a radix-partitioned group-by (see radix_exchange_* there)
+void radix_exchange_keystats(PlanNode& root, int64_t* stats, int32_t* n_keys);
+int radix_exchange_sketch(PlanNode& root, const int64_t* global_stats, void** dev_buf, int64_t* bytes);
+int radix_exchange_prepare(PlanNode& root, const void* gathered_host, int world, int rank, void* handles_out, int32_t* n_handles);
+void radix_exchange_scatter(PlanNode& root, const void* all_handles);
+int radix_exchange_finish(PlanNode& root);
+
 std::shared_ptr<TableImpl> hash_partition_table(TableImpl& t, int key_col, int n_parts, std::vector<int64_t>& offsets);
 
 // fused.cu: returns true and fills `out` when the aggregate over this input can run as one fused

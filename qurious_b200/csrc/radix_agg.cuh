@@ -70,6 +70,10 @@ struct RParams {
   unsigned long long* n_out;
   int64_t out_cap;
   int* overflow;
+  // multi-GPU exchange (world > 1): level-1 bucket b belongs to rank b % world; the level-1 scatter writes its tuples
+  // straight into the owner's tuple arrays over NVLink (peer_a[rank][component]; the local rank's entry is tup_a)
+  int32_t world, pad1;
+  unsigned long long* peer_a[8][R_MAXCOMP];
 };
 
 // guarded variant of load_rows for operands read straight from global memory (no staged tile behind the tail)
@@ -378,8 +382,14 @@ __global__ void __launch_bounds__(R_SNT, 2) k_radix_scatter(const __grid_constan
     for (unsigned i = tid; i < total; i += R_SNT) {
       const unsigned d = bin[i];
       const unsigned long long dest = gbase[d] + (i - toff[d]);
+      if (LEVEL == 1 && r.world > 1) {  // peer (or own) memory of the bucket's owner: P2P stores over NVLink
+        unsigned long long* const* peer = r.peer_a[d % (unsigned)r.world];
 #pragma unroll 1
-      for (int c = 0; c < r.n_comp; ++c) out[c][dest] = sorted[(size_t)c * R_T + i];
+        for (int c = 0; c < r.n_comp; ++c) peer[c][dest] = sorted[(size_t)c * R_T + i];
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < r.n_comp; ++c) out[c][dest] = sorted[(size_t)c * R_T + i];
+      }
     }
     __syncthreads();
   }

@@ -12,6 +12,7 @@ first-occurrence output order identical to a single-GPU run over the whole table
 from __future__ import annotations
 
 import ctypes
+import sys
 from typing import Callable, List, Optional
 
 import pyarrow as pa
@@ -152,9 +153,22 @@ def hash_repartition(ctx: _lib.Context, table: _lib.DeviceTable, key_col: int, w
     exchange the per-destination slices of every column with NCCL all-to-all (ncclSend/ncclRecv over NVLink), return
     the received rows as a new HBM-resident table.  Afterwards equal keys live on exactly one rank, so a purely
     local aggregate is exact and the whole result is the concatenation of the ranks' results."""
+    import os
+    import time
+    trace = bool(os.environ.get("QGPU_TRACE"))
     dev = torch.device("cuda", ctx.device)
     stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
+    t0 = time.perf_counter()
+
+    def mark(what):
+        nonlocal t0
+        if trace:
+            stream.synchronize()
+            t1 = time.perf_counter()
+            print(f"[qgpu trace] repartition: {what:<28s} {1e3 * (t1 - t0):9.3f} ms", file=sys.stderr)
+            t0 = t1
     parted, offs = table.hash_partition(key_col, world)
+    mark("partition kernels")
     cols, widths = [], []
     for c in range(len(table.schema)):
         t, w = column_bytes_tensor(parted, c)
@@ -164,9 +178,151 @@ def hash_repartition(ctx: _lib.Context, table: _lib.DeviceTable, key_col: int, w
         outs, recv_rows = exchange_columns(cols, widths, [offs[i + 1] - offs[i] for i in range(world)],
                                            all_to_all or _dist_all_to_all, device=dev)
     stream.synchronize()
+    mark("all-to-all")
     res = table_from_tensors(ctx, table.schema, outs, sum(recv_rows))
+    mark("received table")
     parted.free()
     return res
+
+
+class ExchangeGroupBy:
+    """High-cardinality group-by over row-range shards (BASELINE.json configs[3]): ONE kernel partitions this rank's rows
+    by key hash and stores every tuple straight into its owner's HBM over NVLink (csrc/radix_agg.cuh k_radix_scatter<1>
+    with peer destinations) -- no send buffers, no NCCL all-to-all; NCCL only carries the 17 KB sketches, the 80-byte
+    buffer handles and the barrier.  Afterwards equal keys live on one rank, which aggregates them locally; the whole
+    result is the concatenation of the ranks' results.  Falls back (collectively) on hash_repartition + a local
+    aggregate when the plan is not eligible or a skewed bucket overflows."""
+
+    HANDLE_BYTES = 80
+
+    def __init__(self, ctx: _lib.Context, plan, world: int, rank: int, collectives=None):
+        self.ctx, self.plan, self.world, self.rank = ctx, plan, int(world), int(rank)
+        _, self.h, _ = plan._native_cached(ctx)
+        self.dev = torch.device("cuda", ctx.device)
+        self.stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=self.dev)
+        self.coll = collectives or _DistCollectives()
+        self.last_path = ""
+        self._gstats = None
+
+    # -- the library stages -------------------------------------------------------------------------------------
+    def keystats(self) -> List[int]:
+        st = (ctypes.c_int64 * 8)()
+        nk = ctypes.c_int32()
+        self.ctx.check(self.ctx.lib.qgpu_plan_exchange_keystats(self.h, st, ctypes.byref(nk)))
+        return list(st)[:2 * nk.value]
+
+    def sketch(self, global_stats: List[int]):
+        """-> (device byte tensor with this rank's sketch, eligible)"""
+        st = (ctypes.c_int64 * 8)(*global_stats)
+        ptr, n, ok = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int32()
+        self.ctx.check(self.ctx.lib.qgpu_plan_exchange_sketch(self.h, st, ctypes.byref(ptr), ctypes.byref(n), ctypes.byref(ok)))
+        if not ok.value:
+            return None, False
+        return torch.as_tensor(_DevBuf(ptr.value, n.value), device=self.dev), True
+
+    def global_keystats(self) -> List[int]:
+        """(min, max) of every key over all ranks; the table is immutable, so this is exchanged once."""
+        if self._gstats is None:
+            mine = self.keystats()
+            t = torch.tensor([(-v if i % 2 == 0 else v) for i, v in enumerate(mine)], dtype=torch.int64, device=self.dev)
+            t = self.coll.all_reduce_max(t)            # max of (-min, max)
+            self._gstats = [(-int(v) if i % 2 == 0 else int(v)) for i, v in enumerate(t.tolist())]
+        return self._gstats
+
+    def prepare(self, gathered_host: torch.Tensor):
+        handles = torch.zeros(6 * self.HANDLE_BYTES, dtype=torch.uint8)
+        nh, ok = ctypes.c_int32(), ctypes.c_int32()
+        self.ctx.check(self.ctx.lib.qgpu_plan_exchange_prepare(self.h, gathered_host.data_ptr(), self.world, self.rank,
+                                                                handles.data_ptr(), ctypes.byref(nh), ctypes.byref(ok)))
+        return handles[:nh.value * self.HANDLE_BYTES], bool(ok.value)
+
+    def scatter(self, all_handles_host: torch.Tensor):
+        self.ctx.check(self.ctx.lib.qgpu_plan_exchange_scatter(self.h, all_handles_host.data_ptr()))
+
+    def finish(self) -> int:
+        ovf = ctypes.c_int32()
+        self.ctx.check(self.ctx.lib.qgpu_plan_exchange_finish(self.h, ctypes.byref(ovf)))
+        return ovf.value
+
+    # -- the collective sequence -----------------------------------------------------------------------------------------
+    def execute_device(self) -> _lib.DeviceTable:
+        gstats = self.global_keystats()
+        with torch.cuda.stream(self.stream):        # ordered after the library's sketch kernel
+            sk, ok = self.sketch(gstats)
+            if ok:
+                gathered = self.coll.all_gather_bytes(sk, self.world).cpu()
+        if ok:
+            handles, ok = self.prepare(gathered)
+        if ok:
+            with torch.cuda.stream(self.stream):
+                all_h = self.coll.all_gather_bytes(handles.to(self.dev), self.world).cpu()
+            self.scatter(all_h)
+            self.coll.barrier()                      # every rank's peer stores have completed
+            failed = self.finish()
+            if self.coll.any_nonzero(failed, self.dev):
+                if not failed:
+                    self.plan.execute_device(self.ctx).free()      # drop this rank's (unused) result
+                ok = False
+        if ok:
+            self.last_path = "exchange"
+            return self.plan.execute_device(self.ctx)
+        return self._fallback()
+
+    def _fallback(self) -> _lib.DeviceTable:
+        from .physical.plan import HashAggregate, MemoryTable, Projection, Scan
+        self.last_path = "hash_repartition"
+        node, chain = self.plan, []
+        while isinstance(node, Projection):
+            chain.append(node)
+            node = node.input
+        if not isinstance(node, HashAggregate) or not isinstance(node.input, Scan):
+            raise _lib.QuriousError(1, "InternalError: exchange fallback needs (Projection)* <- HashAggregate <- Scan")
+        scan = node.input
+        key = node.group_exprs[0]
+        table = scan.datasource.device_table(self.ctx)
+        recv = hash_repartition(self.ctx, table, key.index, self.world, self.coll.all_to_all)
+        p = HashAggregate(node.schema, Scan(scan.schema, MemoryTable.from_device_table(recv), scan.projections, scan.filter),
+                          node.group_exprs, node.aggregate_exprs)
+        for pr in reversed(chain):
+            p = Projection(pr.schema, p, pr.exprs)
+        out = p.execute_device(self.ctx)
+        p.release()
+        recv.free()
+        return out
+
+    def execute(self) -> List[pa.RecordBatch]:
+        t = self.execute_device()
+        out = [t.to_batch()] if t.num_rows > 0 else []
+        t.free()
+        return out
+
+
+class _DistCollectives:
+    """torch.distributed (NCCL) plumbing of ExchangeGroupBy; tests substitute an in-process emulation."""
+
+    def all_gather_bytes(self, t: torch.Tensor, world: int) -> torch.Tensor:
+        import torch.distributed as dist
+        out = torch.empty(world * t.numel(), dtype=torch.uint8, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous())
+        return out
+
+    def barrier(self):
+        import torch.distributed as dist
+        dist.barrier()
+
+    def all_reduce_max(self, t: torch.Tensor) -> torch.Tensor:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t
+
+    def any_nonzero(self, v: int, dev) -> bool:
+        import torch.distributed as dist
+        t = torch.tensor([1 if v else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return bool(t.item())
+
+    def all_to_all(self, out, inp, out_splits, in_splits):
+        _dist_all_to_all(out, inp, out_splits, in_splits)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -127,3 +127,82 @@ def test_q3_gather_merge_equals_single(gpu_ctx, world):
     for p in plans:                               # phase 2: every rank merges the gathered rows identically
         got = rows_of(GatherMergeAggregate(gpu_ctx, p, world, all_gather_ragged=fake_gather).execute())
         check_rows(f"q3 gather-merge x{world}", got, single, ordered=False)
+
+
+# ------------------------------------------------------------------------------------------------
+# exchange (P2P scatter) with the ranks emulated inside one process on one GPU
+# ------------------------------------------------------------------------------------------------
+def groupby_plan_i64(table):
+    """the config-4 shape: SUM/COUNT/MIN/MAX(v), AVG(f) by k -- 64-bit accumulators only (radix / exchange eligible)"""
+    K, V, F = (Column(n, SCHEMA.get_field_index(n)) for n in ("k", "v", "f"))
+    aggs = [SumAggregateExpr(V, pa.int64()), CountAggregateExpr(V), MinAggregateExpr(V, pa.int64()), MaxAggregateExpr(V, pa.int64()),
+            AvgAggregateExpr(F, pa.float64(), pa.float64())]
+    out = pa.schema([("k", pa.int64())] + [(f"a{i}", a.return_type) for i, a in enumerate(aggs)])
+    return HashAggregate(out, Scan(SCHEMA, table, None, None), [K], aggs)
+
+
+class _Emu:
+    """Collectives of `world` emulated ranks that run their stages in lock-step on one GPU."""
+
+    def __init__(self, world):
+        self.world, self.box = world, {}
+
+    def put(self, name, rank, t):
+        self.box.setdefault(name, {})[rank] = t.clone()
+
+    def cat(self, name):
+        return torch.cat([self.box[name][r] for r in range(self.world)])
+
+
+def run_exchange_emulated(gpu_ctx, table, world, make_plan):
+    from qurious_b200.distributed import ExchangeGroupBy
+    full = pa.Table.from_batches(table.data).combine_chunks()
+    n = full.num_rows
+    ex = []
+    for r in range(world):
+        lo, hi = shard_range(n, r, world)
+        st = MemoryTable.try_new(table.schema, full.slice(lo, hi - lo).to_batches())
+        ex.append(ExchangeGroupBy(gpu_ctx, make_plan(st), world, r, collectives=object()))
+    emu = _Emu(world)
+    stats = [e.keystats() for e in ex]
+    gstats = [(min if i % 2 == 0 else max)(s_[i] for s_ in stats) for i in range(len(stats[0]))]
+    for r, e in enumerate(ex):
+        sk, ok = e.sketch(gstats)
+        assert ok
+        emu.put("sketch", r, sk)
+    torch.cuda.synchronize()
+    gathered = emu.cat("sketch").cpu()
+    oks = []
+    for r, e in enumerate(ex):
+        h, ok = e.prepare(gathered)
+        oks.append(ok)
+        emu.put("handles", r, h)
+    assert len(set(oks)) == 1          # the eligibility decision is collective
+    if not oks[0]:
+        return None
+    all_h = emu.cat("handles")
+    for e in ex:
+        e.scatter(all_h)
+    rows, seen = [], set()
+    for e in ex:
+        assert e.finish() == 0
+        got = rows_of(e.plan.execute(gpu_ctx))
+        assert "exchange[rank" in e.plan.last_strategy(), e.plan.last_strategy()
+        keys = {r_[0] for r_ in got}
+        assert not (keys & seen)
+        seen |= keys
+        rows += got
+    return rows
+
+
+@pytest.mark.parametrize("world,n,groups", [(2, 60_000, 7000), (3, 50_000, 50_000), (8, 200_000, 30_000), (4, 9, 4), (1, 20_000, 500)])
+def test_exchange_groupby_equals_single(gpu_ctx, world, n, groups):
+    t = make_table(n, groups, seed=world + 10)
+    single = rows_of(groupby_plan_i64(t).execute(gpu_ctx))
+    check_rows("single vs oracle", single, rows_of(qref.execute(groupby_plan_i64(t))), ordered=False)
+    rows = run_exchange_emulated(gpu_ctx, t, world, groupby_plan_i64)
+    assert rows is not None
+    check_rows(f"exchange x{world}", rows, single, ordered=False)
+    # a second execution re-uses the receive buffers
+    rows2 = run_exchange_emulated(gpu_ctx, t, world, groupby_plan_i64)
+    check_rows(f"exchange x{world} again", rows2, single, ordered=False)
