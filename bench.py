@@ -226,7 +226,8 @@ def gen_raw(query, sf_total, device, rank, world):
     rr = shard_range(n_l, rank, world) if world > 1 else None
     out["lineitem"] = tpch.gen_lineitem(sf_total, device=device, columns=cols["lineitem"], row_range=rr)
     if "orders" in cols:
-        out["orders"] = tpch.gen_orders(sf_total, device=device, columns=cols["orders"])
+        orr = shard_range(tpch.n_orders(sf_total), rank, world) if world > 1 else None
+        out["orders"] = tpch.gen_orders(sf_total, device=device, columns=cols["orders"], row_range=orr)
     if "customer" in cols:
         out["customer"] = tpch.gen_customer(sf_total, device=device, columns=cols["customer"])
     return out
@@ -357,17 +358,20 @@ def run_b200(args):
                 xg.execute_device().free()
                 step.strategy = "%s x%d -> %s" % (xg.last_path, world, plan.last_strategy())
         elif q == "q3":
-            # lineitem row-range shards, build sides replicated (broadcast join); groups straddling a shard boundary
-            # are merged by all-gathering the per-rank result rows and re-aggregating them
-            gm = qd.GatherMergeAggregate(ctx, plan, world)
+            # orders and lineitem row-range sharded, customer replicated: J1 per orders shard, its rows all-gathered
+            # (broadcast build), J2 + aggregate per lineitem shard; groups straddling a shard boundary are merged by
+            # all-gathering the per-rank result rows and re-aggregating them
+            bj = qd.BroadcastJoinAggregate(ctx, tpch.q3_build_plan(tpch.Database(0.0, dev_tables["customer"], dev_tables["orders"], None)),
+                                           lambda b: tpch.q3_probe_plan(b, dev_tables["lineitem"]), world)
 
             def step():
-                gm.execute_device().free()
+                bj.execute_device().free()
+                step.strategy = bj.last_strategy
         else:
             sharded = qd.ShardedAggregate(ctx, plan, lo, world)
 
             def step():
-                sharded.execute()
+                sharded.execute_device().free()
     else:
         def step():
             plan.execute_device(ctx).free()
@@ -422,7 +426,8 @@ def run_b200(args):
             tabs = {k: MemoryTable.try_new(b[0].schema, b) for k, b in host.items()}
             p = build_plan(q, tabs)
             if world > 1 and q == "q3":
-                out = qd.GatherMergeAggregate(ctx, p, world).execute()
+                out = qd.BroadcastJoinAggregate(ctx, tpch.q3_build_plan(tpch.Database(0.0, tabs["customer"], tabs["orders"], None)),
+                                                lambda b: tpch.q3_probe_plan(b, tabs["lineitem"]), world).execute()
             elif world > 1:
                 out = qd.ShardedAggregate(ctx, p, lo, world).execute()
             else:

@@ -269,6 +269,15 @@ int qgpu_plan_exchange_finish(qgpu_plan* p, int32_t* overflow);
 
 int qgpu_plan_state_bytes(qgpu_plan* p, int32_t max_groups, int64_t* bytes);
 int qgpu_plan_partial_state(qgpu_plan* p, int64_t row_offset, int32_t max_groups, void* device_buf, int64_t cap_bytes);
+/* Declares that the consumer of `p` does not depend on its output ROW ORDER (e.g. the rows feed an all-gather or a hash
+ * table).  HashJoinExec's order is deterministic in the reference (hash_join.rs:474-512) and is reproduced by default; an
+ * order-free Inner join with unique integer build keys runs as one probe-scan kernel instead.  The flag is set on the
+ * first join below `p`'s Projection / Filter operators. */
+int qgpu_plan_set_order_free(qgpu_plan* p, int32_t on);
+
+/* like qgpu_plan_execute_merged, the result stays in HBM (cf. qgpu_plan_execute_device) */
+int qgpu_plan_execute_merged_device(qgpu_plan* p, const void* gathered_device_buf, int32_t n_states, int32_t max_groups,
+                                    qgpu_table** out);
 int qgpu_plan_execute_merged(qgpu_plan* p, const void* gathered_device_buf, int32_t n_states, int32_t max_groups,
                              struct ArrowArrayStream* out);
 

@@ -26,7 +26,7 @@ SYMBOLS = [
     "qgpu_table_free", "qgpu_expr_parse", "qgpu_expr_free", "qgpu_plan_scan", "qgpu_plan_filter",
     "qgpu_plan_projection", "qgpu_plan_aggregate", "qgpu_plan_hash_join", "qgpu_plan_schema",
     "qgpu_plan_execute", "qgpu_plan_execute_device", "qgpu_plan_last_stats", "qgpu_plan_strategy",
-    "qgpu_plan_free", "qgpu_plan_state_bytes", "qgpu_plan_partial_state", "qgpu_plan_execute_merged",
+    "qgpu_plan_free", "qgpu_plan_state_bytes", "qgpu_plan_partial_state", "qgpu_plan_execute_merged", "qgpu_plan_execute_merged_device", "qgpu_plan_set_order_free",
     "qgpu_table_hash_partition", "qgpu_table_column_device_buffer",
     "qgpu_plan_exchange_keystats", "qgpu_plan_exchange_sketch", "qgpu_plan_exchange_prepare", "qgpu_plan_exchange_scatter", "qgpu_plan_exchange_finish",
 ]
@@ -125,6 +125,8 @@ def load_library() -> ctypes.CDLL:
     lib.qgpu_plan_state_bytes.argtypes = [vp, i32, P(i64)]
     lib.qgpu_plan_partial_state.argtypes = [vp, i64, i32, vp, i64]
     lib.qgpu_plan_execute_merged.argtypes = [vp, vp, i32, i32, vp]
+    lib.qgpu_plan_execute_merged_device.argtypes = [vp, vp, i32, i32, P(vp)]
+    lib.qgpu_plan_set_order_free.argtypes = [vp, i32]
     _lib = lib
     return lib
 

@@ -2184,7 +2184,7 @@ bool int_like_key(const DCol& c) { return c.phys == PH_I64 || c.phys == PH_I32 |
 // (build row, probe row) pairs with warp-aggregated atomics; the result is a View of index vectors (late
 // materialisation), like the generic join's -- only the row ORDER differs, which is why this path is never used
 // for a join whose output is returned to the caller (hash_join.rs:474-512 pins that order).
-static bool fused_unordered_join(PlanNode& join, View* out) {
+bool fused_unordered_join(PlanNode& join, View* out) {
   Ctx* ctx = join.ctx;
   if (join.kind != PK_HASH_JOIN || join.join_type != QGPU_JOIN_INNER || join.left_on.size() != 1 || join.has_join_filter) return false;
   const ExprNode& lk = *join.left_on[0];

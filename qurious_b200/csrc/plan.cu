@@ -232,6 +232,10 @@ View PlanNode::execute() {
       return run_aggregate(ctx, in, keys, specs, schema, defer);
     }
     case PK_HASH_JOIN: {
+      if (order_free) {
+        View uj;
+        if (fused_unordered_join(*this, &uj)) return uj;
+      }
       View l = children[0]->execute();
       View r = children[1]->execute();
       std::vector<std::shared_ptr<Compiled>> lo, ro;
@@ -712,6 +716,33 @@ int qgpu_plan_execute_merged(qgpu_plan* p, const void* gathered, int32_t n_state
       export_batch(n.ctx, v.schema, cols, v.num_rows, &batches[0]);
     }
     make_stream(n.schema, std::move(batches), out);
+  });
+}
+
+int qgpu_plan_set_order_free(qgpu_plan* p, int32_t on) {
+  if (!p) return QGPU_ERR_INTERNAL;
+  // the flag is inherited by the operators below that preserve order (Projection / Filter) down to the first join
+  PlanNode* n = p->node.get();
+  while (n && (n->kind == PK_PROJECTION || n->kind == PK_FILTER)) n = n->children[0].get();
+  if (n) n->order_free = on != 0;
+  return QGPU_OK;
+}
+
+int qgpu_plan_execute_merged_device(qgpu_plan* p, const void* gathered, int32_t n_states, int32_t max_groups, qgpu_table** out) {
+  if (!p || !gathered || !out) return QGPU_ERR_INTERNAL;
+  PlanNode& n = *p->node;
+  return guard(n.ctx, [&] {
+    View v = shard_execute_merged(n, gathered, n_states, max_groups);
+    auto t = std::make_shared<TableImpl>();
+    t->ctx = n.ctx;
+    t->schema = n.schema;
+    t->num_rows = v.num_rows;
+    t->num_batches = v.num_batches;
+    for (size_t i = 0; i < v.cols.size(); ++i) {
+      if (!v.cols[i].base) t->cols.push_back(nullptr);
+      else t->cols.push_back(materialize(n.ctx, v.cols[i], v.num_rows));
+    }
+    *out = new qgpu_table{t};
   });
 }
 

@@ -41,6 +41,7 @@ struct PlanNode {
   std::string strategy = "not-executed";
   std::string strategy_desc;
   std::shared_ptr<void> fused_cache;
+  bool order_free = false;  // the consumer does not depend on this node's output row order (qgpu_plan_set_order_free)
   // sharded execution (shard.cu): stop before finalisation / resume from merged states
   AggPending* defer = nullptr;
   std::shared_ptr<View> merged_override;
@@ -70,6 +71,9 @@ std::shared_ptr<TableImpl> hash_partition_table(TableImpl& t, int key_col, int n
 // fused.cu: returns true and fills `out` when the aggregate over this input can run as one fused
 // scan+filter+aggregate pipeline kernel.
 bool try_fused_scan_aggregate(PlanNode& agg, View* out);
+// an Inner join with unique integer build keys as ONE probe-scan kernel emitting (build row, probe row) pairs in
+// arbitrary order; only where the order does not matter (build sides of fused join-aggregates, order_free nodes)
+bool fused_unordered_join(PlanNode& join, View* out);
 // fused.cu: Aggregate <- HashJoin(Inner, unique build keys) <- [build plan, probe scan]: probe + aggregate in one kernel
 bool try_fused_join_aggregate(PlanNode& agg, View* out);
 

@@ -67,6 +67,17 @@ class ShardedAggregate:
             self.all_gather(self.gathered, self.state)
         return self.merge(self.gathered, self.world)
 
+    def execute_device(self) -> _lib.DeviceTable:
+        """Like execute(), the merged result stays in HBM."""
+        self.partial()
+        with torch.cuda.stream(self.stream):
+            self.all_gather(self.gathered, self.state)
+        out = ctypes.c_void_p()
+        self.ctx.check(self.ctx.lib.qgpu_plan_execute_merged_device(self.h, self.gathered.data_ptr(), self.world, self.max_groups,
+                                                                    ctypes.byref(out)))
+        self.plan._record_stats(self.ctx, self.h)
+        return _lib.DeviceTable(self.ctx, out, self.plan.schema)
+
 
 # ------------------------------------------------------------------------------------------------
 # hash repartition (SURVEY 8e: high-cardinality group-by / join inputs) over NCCL all-to-all
@@ -406,6 +417,53 @@ class GatherMergeAggregate:
         merged = self._make_merge_plan(gathered).execute_device(self.ctx)
         gathered.free()
         return merged
+
+    def execute(self) -> List[pa.RecordBatch]:
+        t = self.execute_device()
+        out = [t.to_batch()] if t.num_rows > 0 else []
+        t.free()
+        return out
+
+
+def all_gather_table(ctx: _lib.Context, table: _lib.DeviceTable, world: int,
+                     all_gather_ragged: Optional[Callable] = None) -> _lib.DeviceTable:
+    """The rows of every rank's HBM-resident table (fixed-width, NULL-free columns), in rank order, on every rank."""
+    stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", ctx.device))
+    cols, widths = [], []
+    for c in range(len(table.schema)):
+        t, w = column_bytes_tensor(table, c)
+        cols.append(t)
+        widths.append(w)
+    with torch.cuda.stream(stream):
+        outs, n = (all_gather_ragged or _dist_all_gather_ragged)(cols, widths, table.num_rows, world)
+    stream.synchronize()
+    return table_from_tensors(ctx, table.schema, outs, n)
+
+
+class BroadcastJoinAggregate:
+    """Join + aggregate with BOTH inputs row-range sharded (SURVEY 8e "Q3 joins", broadcast variant): every rank runs
+    the build-side sub-plan over its shard, the (small) results are all-gathered over NCCL so that every GPU builds the
+    full join table, then probes it with its shard of the fact table; groups that straddle shard boundaries are merged
+    by GatherMergeAggregate.  probe_plan_of(MemoryTable of the gathered build rows) -> the probe-side plan."""
+
+    def __init__(self, ctx: _lib.Context, build_plan, probe_plan_of: Callable, world: int,
+                 all_gather_ragged: Optional[Callable] = None):
+        self.ctx, self.build_plan, self.probe_plan_of, self.world = ctx, build_plan, probe_plan_of, int(world)
+        self.gather = all_gather_ragged
+        self.last_strategy = ""
+
+    def execute_device(self) -> _lib.DeviceTable:
+        from .physical.plan import MemoryTable
+        self.build_plan.set_order_free(True, self.ctx)      # the rows feed an all-gather and a hash table
+        local = self.build_plan.execute_device(self.ctx)
+        build = all_gather_table(self.ctx, local, self.world, self.gather)
+        local.free()
+        probe = self.probe_plan_of(MemoryTable.from_device_table(build))
+        out = GatherMergeAggregate(self.ctx, probe, self.world, self.gather).execute_device()
+        self.last_strategy = "broadcast-build[%s] -> %s" % (self.build_plan.last_strategy(), probe.last_strategy())
+        probe.release()
+        build.free()
+        return out
 
     def execute(self) -> List[pa.RecordBatch]:
         t = self.execute_device()

@@ -145,6 +145,13 @@ class PhysicalPlan:
         t.reference_num_batches = nb.value
         return t
 
+    def set_order_free(self, on: bool = True, ctx: Optional[_lib.Context] = None):
+        """The consumer does not depend on this plan's output row order (qgpu_plan_set_order_free): lets an Inner join
+        below Projection/Filter operators run as one unordered probe-scan kernel.  Not part of the reference's API."""
+        ctx, h, _ = self._native_cached(ctx)
+        ctx.check(ctx.lib.qgpu_plan_set_order_free(h, 1 if on else 0))
+        return self
+
     def _record_stats(self, ctx, h):
         ms = ctypes.c_double()
         ln = ctypes.c_int64()

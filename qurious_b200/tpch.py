@@ -141,10 +141,13 @@ def _order_dates(i: torch.Tensor) -> torch.Tensor:
     return uniform(20, i, days("1992-01-01"), days("1998-08-02"))
 
 
-def gen_orders(sf: float, device="cpu", columns: Optional[Sequence[str]] = None) -> RawTable:
+def gen_orders(sf: float, device="cpu", columns: Optional[Sequence[str]] = None, row_range=None) -> RawTable:
+    """row_range=(lo, hi): only that contiguous slice of orders (multi-GPU: the build side of Q3 is sharded too)."""
     n = n_orders(sf)
     nc = n_customers(sf)
-    i = torch.arange(n, dtype=torch.int64, device=device)
+    lo, hi = row_range if row_range is not None else (0, n)
+    i = torch.arange(lo, hi, dtype=torch.int64, device=device)
+    n = hi - lo
     want = set(columns) if columns is not None else set(ORDERS_SCHEMA.names)
     cols, codes, vocab = {}, {}, {}
     if "o_orderkey" in want:
@@ -455,6 +458,41 @@ def q3_plan(db: Database) -> Projection:
     l_scan = Scan(ls, db.lineitem, None, _b(_col(ls, "l_shipdate"), O.Gt, _date("1995-03-15")))
     j1 = HashJoinExec.try_new(c_scan, o_scan, JoinType.Inner, [(_col(cs, "c_custkey"), _col(os_, "o_custkey"))], None)
     j2 = HashJoinExec.try_new(j1, l_scan, JoinType.Inner, [(_col(j1.schema, "o_orderkey"), _col(ls, "l_orderkey"))], None)
+    js = j2.schema
+    rev = _b(_col(js, "l_extendedprice"), O.Mul, _b(_one20(), O.Sub, _col(js, "l_discount")))
+    rt = pa.decimal128(38, 4)
+    schema = pa.schema([("l_orderkey", pa.int64()), ("o_orderdate", pa.date32()), ("o_shippriority", pa.int64()), ("revenue", rt)])
+    agg = HashAggregate(schema, j2, [_col(js, "l_orderkey"), _col(js, "o_orderdate"), _col(js, "o_shippriority")],
+                        [SumAggregateExpr(rev, rt)])
+    out = pa.schema([("l_orderkey", pa.int64()), ("revenue", rt), ("o_orderdate", pa.date32()), ("o_shippriority", pa.int64())])
+    return Projection(out, agg, [Column("l_orderkey", 0), Column("revenue", 3), Column("o_orderdate", 1),
+                                 Column("o_shippriority", 2)])
+
+
+# ------------------------------------------------------------------------------------------------
+# Q3 as a broadcast join over row-range shards (SURVEY 8e "Q3 joins"): what a distributed planner emits
+# ------------------------------------------------------------------------------------------------
+Q3_BUILD_SCHEMA = pa.schema([("o_orderkey", pa.int64()), ("o_orderdate", pa.date32()), ("o_shippriority", pa.int64())])
+
+
+def q3_build_plan(db: Database) -> Projection:
+    """J1 = customer(BUILDING) JOIN orders(o_orderdate < 1995-03-15) over THIS rank's shard of orders, projected to the
+    three columns the second join and the aggregate need.  The ranks' results are all-gathered (broadcast build)."""
+    O = Operator
+    cs, os_ = db.customer.schema, db.orders.schema
+    c_scan = Scan(cs, db.customer, None, _b(_col(cs, "c_mktsegment"), O.Eq, Literal(ScalarValue.Utf8("BUILDING"))))
+    o_scan = Scan(os_, db.orders, None, _b(_col(os_, "o_orderdate"), O.Lt, _date("1995-03-15")))
+    j1 = HashJoinExec.try_new(c_scan, o_scan, JoinType.Inner, [(_col(cs, "c_custkey"), _col(os_, "o_custkey"))], None)
+    return Projection(Q3_BUILD_SCHEMA, j1, [_col(j1.schema, n) for n in Q3_BUILD_SCHEMA.names])
+
+
+def q3_probe_plan(build: MemoryTable, lineitem: MemoryTable) -> Projection:
+    """J2 + aggregate of q3_plan with the (gathered) J1 result as a materialised build side; same output schema."""
+    O = Operator
+    ls = lineitem.schema
+    b_scan = Scan(Q3_BUILD_SCHEMA, build, None, None)
+    l_scan = Scan(ls, lineitem, None, _b(_col(ls, "l_shipdate"), O.Gt, _date("1995-03-15")))
+    j2 = HashJoinExec.try_new(b_scan, l_scan, JoinType.Inner, [(_col(Q3_BUILD_SCHEMA, "o_orderkey"), _col(ls, "l_orderkey"))], None)
     js = j2.schema
     rev = _b(_col(js, "l_extendedprice"), O.Mul, _b(_one20(), O.Sub, _col(js, "l_discount")))
     rt = pa.decimal128(38, 4)

@@ -11,7 +11,7 @@ import torch
 
 from oracle import qref
 from qurious_b200 import QuriousError, tpch
-from qurious_b200.distributed import (GatherMergeAggregate, column_bytes_tensor, merge_spec_of, partition_ids_host,
+from qurious_b200.distributed import (BroadcastJoinAggregate, GatherMergeAggregate, column_bytes_tensor, merge_spec_of, partition_ids_host,
                                       shard_range, table_from_tensors)
 from qurious_b200.physical.expr import (AvgAggregateExpr, Column, CountAggregateExpr, MaxAggregateExpr, MinAggregateExpr,
                                         SumAggregateExpr)
@@ -206,3 +206,42 @@ def test_exchange_groupby_equals_single(gpu_ctx, world, n, groups):
     # a second execution re-uses the receive buffers
     rows2 = run_exchange_emulated(gpu_ctx, t, world, groupby_plan_i64)
     check_rows(f"exchange x{world} again", rows2, single, ordered=False)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_q3_broadcast_build_equals_single(gpu_ctx, world):
+    """orders AND lineitem row-range sharded; J1 per shard, its rows all-gathered, J2 + aggregate per lineitem shard."""
+    sf = 0.02
+    db = tpch.generate(sf, batch_rows=None)
+    single = rows_of(tpch.q3_plan(db).execute(gpu_ctx))
+    orders = pa.Table.from_batches(db.orders.data).combine_chunks()
+    items = pa.Table.from_batches(db.lineitem.data).combine_chunks()
+    shards = []
+    for r in range(world):
+        olo, ohi = shard_range(orders.num_rows, r, world)
+        llo, lhi = shard_range(items.num_rows, r, world)
+        shards.append((MemoryTable.try_new(db.orders.schema, orders.slice(olo, ohi - olo).to_batches()),
+                       MemoryTable.try_new(db.lineitem.schema, items.slice(llo, lhi - llo).to_batches())))
+    # phase 1: every rank's J1 rows; phase 2: probe results; the emulated "all-gathers" concatenate them in rank order
+    builds = []
+    for o_sh, _ in shards:
+        d = tpch.q3_build_plan(tpch.Database(sf, db.customer, o_sh, None)).execute_device(gpu_ctx)
+        builds.append(([column_bytes_tensor(d, c)[0].clone() for c in range(3)], d.num_rows))
+        d.free()
+    gathered_build = table_from_tensors(gpu_ctx, tpch.Q3_BUILD_SCHEMA, [torch.cat([b[0][c] for b in builds]) for c in range(3)],
+                                        sum(b[1] for b in builds))
+    probes = []
+    for _, l_sh in shards:
+        p = tpch.q3_probe_plan(MemoryTable.from_device_table(gathered_build), l_sh)
+        d = p.execute_device(gpu_ctx)
+        probes.append(([column_bytes_tensor(d, c)[0].clone() for c in range(len(p.schema))], d.num_rows))
+        d.free()
+
+    def fake_gather(cols, widths, n_rows, w):
+        src = builds if len(cols) == 3 else probes
+        return [torch.cat([b[0][c] for b in src]) for c in range(len(cols))], sum(b[1] for b in src)
+    for o_sh, l_sh in shards:
+        bj = BroadcastJoinAggregate(gpu_ctx, tpch.q3_build_plan(tpch.Database(sf, db.customer, o_sh, None)),
+                                    lambda b, l_sh=l_sh: tpch.q3_probe_plan(b, l_sh), world, all_gather_ragged=fake_gather)
+        check_rows(f"q3 broadcast x{world}", rows_of(bj.execute()), single, ordered=False)
+        assert "broadcast-build" in bj.last_strategy
