@@ -233,6 +233,40 @@ def gen_raw(query, sf_total, device, rank, world):
     return out
 
 
+def metric_name(q):
+    return "group-by rows/sec" if q == "groupby" else f"TPC-H {q.upper()} rows/sec"
+
+
+def cpu_sample(query, rows_q1q6=2_000_000):
+    """-> (callable running the CPU port once, driving-table rows it processes, description): a BOUNDED sample of the
+    workload, generated by the same counter-based generators (so it is a prefix / a smaller scale factor of the same
+    data), referenced columns only, 1024-row batches, one thread (the reference has no threads)."""
+    from oracle import cpu_port
+    from qurious_b200 import tpch
+    if query in ("q1", "q6"):
+        sf = rows_q1q6 / 6_001_215
+        raw = tpch.gen_lineitem(sf, columns=QUERY_COLUMNS[query]["lineitem"])
+        batches = tpch.to_arrow(raw, 1024 * 1024)
+        return (lambda: getattr(cpu_port, query)(batches)), raw.rows, (
+            f"first {raw.rows} rows of the same synthetic lineitem generator (SF{sf:.3f}), referenced columns only, "
+            f"1024-row batches, single thread (the reference has no threads)")
+    if query == "q3":
+        sf = 0.5
+        cols = QUERY_COLUMNS["q3"]
+        t = {"customer": tpch.gen_customer(sf, columns=cols["customer"]), "orders": tpch.gen_orders(sf, columns=cols["orders"]),
+             "lineitem": tpch.gen_lineitem(sf, columns=cols["lineitem"])}
+        b = {k: tpch.to_arrow(v, 1024 * 1024) for k, v in t.items()}
+        return (lambda: cpu_port.q3(b["customer"], b["orders"], b["lineitem"])), t["lineitem"].rows, (
+            f"the same generators at SF{sf} ({t['lineitem'].rows} lineitem / {t['orders'].rows} orders / {t['customer'].rows} customer "
+            f"rows), referenced columns only, 1024-row batches, single thread")
+    rows, groups = 1_000_000, 100_000          # the workload's 10 rows per group
+    raw = gen_groupby(rows, groups, "cpu")
+    batches = tpch.to_arrow(raw, 1024 * 1024)
+    return (lambda: cpu_port.groupby(batches)), rows, (
+        f"{rows} rows / {groups} groups from the same generator (1/1000 of the workload, same rows per group), "
+        f"1024-row batches, single thread")
+
+
 # ------------------------------------------------------------------------------------------------
 # reference arm: the CPU port on host cores
 # ------------------------------------------------------------------------------------------------
@@ -242,27 +276,19 @@ def run_reference(args):
         return
     from oracle import cpu_port
     from qurious_b200 import tpch
-    if args.query not in ("q1", "q6"):
-        print(json.dumps({"impl": "reference", "unavailable": f"no CPU port of {args.query} yet"}))
-        return
-    sample_rows = 2_000_000
-    sf = sample_rows / 6_001_215
-    raw = tpch.gen_lineitem(sf, columns=QUERY_COLUMNS[args.query]["lineitem"])
-    batches = tpch.to_arrow(raw, 1024 * 1024)
-    fn = getattr(cpu_port, args.query)
-    for _ in range(max(args.warmup, 1)):
-        fn(batches)
+    fn, n_rows, sample = cpu_sample(args.query)
+    for _ in range(max(min(args.warmup, 2), 1)):
+        fn()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        fn(batches)
+        fn()
     dt = time.perf_counter() - t0
-    rows_s = raw.rows * args.steps / dt
-    sample = (f"first {raw.rows} rows of the same synthetic lineitem generator (SF{sf:.3f}), referenced columns only, "
-              f"1024-row batches, single thread (the reference has no threads)")
-    line = {"impl": "reference", "metric": f"TPC-H {args.query.upper()} rows/sec", "value": rows_s, "unit": "rows/s",
+    rows_s = n_rows * args.steps / dt
+    line = {"impl": "reference", "metric": metric_name(args.query), "value": rows_s, "unit": "rows/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i128", "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD[args.query]} at SF{args.sf:g} per GPU (bounded sample per step)"},
+            "config": {"workload": (f"{WORKLOAD[args.query]} at SF{args.sf:g} per GPU (bounded sample per step)" if args.query != "groupby"
+                                    else f"{WORKLOAD[args.query]}: {args.rows} rows, {args.groups} groups (bounded sample per step)")},
             "cpu_baseline": {"value": rows_s, "unit": "rows/s", "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": rows_s, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -294,14 +320,18 @@ def run_query_device(ctx, step, steps, warmup, sampler, torch, stream):
     barrier()
     torch.cuda.synchronize()
     sampler.region(True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(min(steps, 64))]   # per-step marks (first 64 steps)
     e0.record(stream)
-    for _ in range(steps):
+    for i in range(steps):
         step()
+        if i < len(marks):
+            marks[i].record(stream)
     e1.record(stream)
     torch.cuda.synchronize()
     sampler.region(False)
     barrier()
     ms = e0.elapsed_time(e1)
+    run_query_device.step_ms = [round(a.elapsed_time(b), 4) for a, b in zip([e0] + marks[:-1], marks)]
     prof = ctx.profile_report()
     ctx.profile(False)
     launches = (ctx.kernel_launches() - l0) / max(steps, 1)
@@ -342,6 +372,8 @@ def run_b200(args):
     raw = gen_raw(q, sf_total, "cuda", rank, world)
     rows_local = raw[driving].rows
     dev_tables = {k: tpch.to_device_table(ctx, v) for k, v in raw.items()}
+    del raw
+    torch.cuda.empty_cache()        # the generator's temporaries go back to the driver: HBM is for the tables
     plan = build_plan(q, dev_tables)
     sharded = None
     if world > 1:
@@ -399,7 +431,6 @@ def run_b200(args):
                 "algorithmic_bytes_per_launch": top_bytes, "bytes_per_row": top_bytes / max(rows_local, 1),
                 "kernel_ms_avg": top_ms, "kernel_share_of_step": top_share, "launches_of_kernel_per_step": top[1] / args.steps,
                 "step_frac_of_roofline": (alg_bytes / (ms / args.steps / 1e3) / 1e9) / peak}
-    del raw
 
     # ---- end-to-end leg: host Arrow buffers -> operators -> host RecordBatches ---------------------
     e2e = None
@@ -422,8 +453,15 @@ def run_b200(args):
         h2d = sum(batches_nbytes(b) for b in host.values())
         from qurious_b200.physical.plan import MemoryTable
 
+        phase = {"upload_ms": 0.0, "execute_ms": 0.0, "n": 0}
+
         def one_e2e():
+            t_a = time.perf_counter()
             tabs = {k: MemoryTable.try_new(b[0].schema, b) for k, b in host.items()}
+            for t in tabs.values():            # H2D staging of every referenced column (pinned cudaMemcpyAsync) + ingest kernels
+                t.device_table(ctx)
+            stream.synchronize()
+            t_b = time.perf_counter()
             p = build_plan(q, tabs)
             if world > 1 and q == "q3":
                 out = qd.BroadcastJoinAggregate(ctx, tpch.q3_build_plan(tpch.Database(0.0, tabs["customer"], tabs["orders"], None)),
@@ -433,12 +471,17 @@ def run_b200(args):
             else:
                 out = p.execute(ctx)
             d2h = batches_nbytes(out)
+            t_c = time.perf_counter()
+            phase["upload_ms"] += 1e3 * (t_b - t_a)
+            phase["execute_ms"] += 1e3 * (t_c - t_b)
+            phase["n"] += 1
             for t in tabs.values():
                 if t._dev is not None:
                     t._dev.free()
             return d2h
         for _ in range(min(args.warmup, 2)):
             d2h = one_e2e()
+        phase.update(upload_ms=0.0, execute_ms=0.0, n=0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         torch.cuda.synchronize()
@@ -459,25 +502,35 @@ def run_b200(args):
         e2e = {"value": rows_total * args.e2e_steps / (float(t_e.item()) / 1e3), "unit": "rows/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
                "ms_per_step": float(t_e.item()) / args.e2e_steps,
+               "upload_ms_per_step": phase["upload_ms"] / max(phase["n"], 1), "execute_ms_per_step": phase["execute_ms"] / max(phase["n"], 1),
+               "host_buffers_pinned": len(regs), "host_buffers_pin_failed": len(PIN_FAILURES),
                "path": "MemoryTable(host RecordBatches, pinned) -> qgpu_table_append (cudaMemcpyAsync) -> "
                        "plan.execute() -> host RecordBatches"}
         unpin(regs)
 
     # ---- CPU baseline (rank 0, N=1): the C++ port on a bounded sample of the same workload -----------
-    if not args.no_cpu and rank == 0 and world == 1 and q in ("q1", "q6") and host_batches is not None:
-        from oracle import cpu_port
-        n = min(args.cpu_sample_rows, host_batches["lineitem"][0].num_rows)
-        sample = [host_batches["lineitem"][0].slice(0, n)]
-        t0 = time.perf_counter()
-        getattr(cpu_port, q)(sample)
-        dt = time.perf_counter() - t0
-        cpu = {"value": n / dt, "unit": "rows/s", "cores": 1, "kind": "port",
-               "sample": f"first {n} rows of this run's lineitem (referenced columns only), 1024-row batches, "
-                         f"{dt:.1f} s on 1 of {os.cpu_count()} host cores (the reference is single-threaded)"}
+    if not args.no_cpu and rank == 0 and world == 1:
+        if q in ("q1", "q6") and host_batches is not None:
+            from oracle import cpu_port
+            n = min(args.cpu_sample_rows, host_batches["lineitem"][0].num_rows)
+            sample = [host_batches["lineitem"][0].slice(0, n)]
+            t0 = time.perf_counter()
+            getattr(cpu_port, q)(sample)
+            dt = time.perf_counter() - t0
+            cpu = {"value": n / dt, "unit": "rows/s", "cores": 1, "kind": "port",
+                   "sample": f"first {n} rows of this run's lineitem (referenced columns only), 1024-row batches, "
+                             f"{dt:.1f} s on 1 of {os.cpu_count()} host cores (the reference is single-threaded)"}
+        else:
+            fn, n, desc = cpu_sample(q)
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            cpu = {"value": n / dt, "unit": "rows/s", "cores": 1, "kind": "port",
+                   "sample": f"{desc}; {dt:.1f} s on 1 of {os.cpu_count()} host cores"}
 
     clocks = sampler.result()
     if rank == 0:
-        line = {"metric": f"TPC-H {q.upper()} rows/sec", "value": value, "unit": "rows/s", "n_gpus": world,
+        line = {"metric": metric_name(q), "value": value, "unit": "rows/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "i64/i128 (exact decimal)", "data": "synthetic",
                 "config": {"workload": (f"{WORKLOAD[q]} at SF{args.sf:g} per GPU ({rows_total} lineitem rows total, "
@@ -487,6 +540,7 @@ def run_b200(args):
                            "strategy": strategy, "rows_per_gpu": rows_local},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(round(launches * args.steps)),
                 "gpu_launches_per_step": launches, "clocks": clocks,
+                "step_ms": getattr(run_query_device, "step_ms", [])[:64],
                 "kernels": [{"name": r[0], "launches": r[1], "total_ms": round(r[2], 4)} for r in prof_sorted[:8]]}
         print(json.dumps(line))
     if world > 1:

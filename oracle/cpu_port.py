@@ -25,6 +25,8 @@ def load() -> ctypes.CDLL:
             subprocess.check_call(["make", "-C", _HERE])
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.qcpu_q1.restype = ctypes.c_int64
+        _lib.qcpu_groupby.restype = ctypes.c_int64
+        _lib.qcpu_q3.restype = ctypes.c_int64
     return _lib
 
 
@@ -90,3 +92,41 @@ def q1(batches: List[pa.RecordBatch], batch_rows: int = 1024, max_groups: int = 
         rows.append((out_rf.raw[i:i + 1].decode(), out_ls.raw[i:i + 1].decode(),
                      *[_i128(sums[i, a]) for a in range(4)], *[_i128(avgs[i, a]) for a in range(3)], int(cnt[i])))
     return rows
+
+
+def groupby(batches: List[pa.RecordBatch], batch_rows: int = 1024, max_groups: int = None) -> List[tuple]:
+    """config 4: -> rows (k, sum_v, count_v, min_v, max_v, avg_f) in first-occurrence order."""
+    lib = load()
+    c = {n: _one_chunk(batches, n) for n in ("k", "v", "f")}
+    n = len(c["k"])
+    mg = n if max_groups is None else max_groups
+    ok, os_, oc, omn, omx = (np.zeros(max(mg, 1), dtype=np.int64) for _ in range(5))
+    oa = np.zeros(max(mg, 1), dtype=np.float64)
+    vp = ctypes.c_void_p
+    g = lib.qcpu_groupby(ctypes.c_int64(n), ctypes.c_int64(batch_rows), vp(_fixed(c["k"], 8)), vp(_fixed(c["v"], 8)),
+                         vp(_fixed(c["f"], 8)), ctypes.c_int64(mg), *[a.ctypes.data_as(vp) for a in (ok, os_, oc, omn, omx, oa)])
+    return [(int(ok[i]), int(os_[i]), int(oc[i]), int(omn[i]), int(omx[i]), float(oa[i])) for i in range(g)]
+
+
+def q3(customer: List[pa.RecordBatch], orders: List[pa.RecordBatch], lineitem: List[pa.RecordBatch], batch_rows: int = 1024,
+       max_groups: int = None) -> List[tuple]:
+    """-> rows (l_orderkey, revenue_raw [unscaled Decimal128(38,4)], o_orderdate [days], o_shippriority), first-occurrence order."""
+    lib = load()
+    cc = {n: _one_chunk(customer, n) for n in ("c_custkey", "c_mktsegment")}
+    oc = {n: _one_chunk(orders, n) for n in ("o_orderkey", "o_custkey", "o_orderdate", "o_shippriority")}
+    lc = {n: _one_chunk(lineitem, n) for n in ("l_orderkey", "l_shipdate", "l_extendedprice", "l_discount")}
+    assert cc["c_mktsegment"].offset == 0 and cc["c_mktsegment"].null_count == 0
+    seg = cc["c_mktsegment"].buffers()
+    n_l = len(lc["l_orderkey"])
+    mg = n_l if max_groups is None else max_groups
+    o_key, o_prio = np.zeros(max(mg, 1), dtype=np.int64), np.zeros(max(mg, 1), dtype=np.int64)
+    o_date = np.zeros(max(mg, 1), dtype=np.int32)
+    o_rev = np.zeros((max(mg, 1), 2), dtype=np.uint64)
+    vp, i64 = ctypes.c_void_p, ctypes.c_int64
+    g = lib.qcpu_q3(i64(len(cc["c_custkey"])), vp(_fixed(cc["c_custkey"], 8)), vp(seg[1].address), vp(seg[2].address),
+                    i64(len(oc["o_orderkey"])), vp(_fixed(oc["o_orderkey"], 8)), vp(_fixed(oc["o_custkey"], 8)),
+                    vp(_fixed(oc["o_orderdate"], 4)), vp(_fixed(oc["o_shippriority"], 8)),
+                    i64(n_l), vp(_fixed(lc["l_orderkey"], 8)), vp(_fixed(lc["l_shipdate"], 4)), vp(_fixed(lc["l_extendedprice"], 16)),
+                    vp(_fixed(lc["l_discount"], 16)), i64(batch_rows), b"BUILDING", b"1995-03-15", i64(mg),
+                    o_key.ctypes.data_as(vp), o_rev.ctypes.data_as(vp), o_date.ctypes.data_as(vp), o_prio.ctypes.data_as(vp))
+    return [(int(o_key[i]), _i128(o_rev[i]), int(o_date[i]), int(o_prio[i])) for i in range(g)]

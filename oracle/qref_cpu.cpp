@@ -21,6 +21,8 @@
 // Only the columns a query references are carried (the reference carries all 17/10/9 columns through
 // filter/take/concat, so this port UNDER-estimates the reference's cost; said so in bench.py's `sample`).
 #include <cstdint>
+#include <algorithm>
+#include <climits>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -300,6 +302,252 @@ int64_t qcpu_q1(int64_t n, int64_t batch_rows, const int32_t* shipdate, const in
     // DecimalAvgAccumulator (avg.rs:89-116): sum * 10^(target_scale - scale) / count, truncating
     for (int a = 0; a < 3; ++a) out_avgs[g * 3 + a] = (sums[4 + a] * 10000) / (i128)count;
     out_count[g] = count;
+    ++g;
+  }
+  return g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Synthetic group-by (BASELINE.json configs[3]): HashAggregate[k; SUM(v) COUNT(v) MIN(v) MAX(v) AVG(f)] over a scan
+// without predicate.  Outputs one row per group in first-occurrence order; returns the number of groups.
+// hash.rs:45-107,138-170 + sum.rs/count.rs/min.rs/max.rs/avg.rs
+// ---------------------------------------------------------------------------------------------
+int64_t qcpu_groupby(int64_t n, int64_t batch_rows, const int64_t* k, const int64_t* v, const double* f, int64_t max_groups,
+                     int64_t* out_k, int64_t* out_sum, int64_t* out_cnt, int64_t* out_min, int64_t* out_max, double* out_avg) {
+  // MemoryTable::scan without filter hands the batches through; concat_batches copies them into one (hash.rs:150)
+  std::vector<int64_t> ck, cv;
+  std::vector<double> cf;
+  for (int64_t b0 = 0; b0 < n; b0 += batch_rows) {
+    const size_t m = (size_t)std::min<int64_t>(batch_rows, n - b0);
+    ck.insert(ck.end(), k + b0, k + b0 + m);
+    cv.insert(cv.end(), v + b0, v + b0 + m);
+    cf.insert(cf.end(), f + b0, f + b0 + m);
+  }
+  const size_t rows = ck.size();
+  if (rows == 0) return 0;
+  std::vector<Sip13> hashers(rows);
+  for (size_t i = 0; i < rows; ++i) hashers[i].write((const uint8_t*)&ck[i], 8);
+  std::vector<uint64_t> hashes(rows);
+  for (size_t i = 0; i < rows; ++i) hashes[i] = hashers[i].finish();
+  std::unordered_map<uint64_t, size_t, SipU64Hash> map;
+  std::unordered_map<uint64_t, std::vector<uint64_t>, SipU64Hash> accs_indices;
+  std::vector<size_t> group_first;
+  for (size_t row = 0; row < rows; ++row) {
+    auto it = map.find(hashes[row]);
+    if (it != map.end()) {
+      accs_indices[it->second].push_back(row);
+    } else {
+      map.emplace(hashes[row], row);
+      accs_indices[row] = std::vector<uint64_t>{row};
+      group_first.push_back(row);
+    }
+  }
+  int64_t g = 0;
+  for (size_t first : group_first) {
+    if (g >= max_groups) break;
+    const std::vector<uint64_t>& idx = accs_indices[first];
+    int64_t sum = 0, mn = INT64_MAX, mx = INT64_MIN, cnt = 0;
+    {
+      std::vector<uint64_t> indices(idx);
+      std::vector<int64_t> t = take(cv, indices);
+      uint64_t acc = 0;
+      for (int64_t x : t) acc += (uint64_t)x;  // add_wrapping
+      sum = (int64_t)acc;
+    }
+    {
+      std::vector<uint64_t> indices(idx);
+      std::vector<int64_t> t = take(cv, indices);
+      cnt = (int64_t)t.size();
+    }
+    {
+      std::vector<uint64_t> indices(idx);
+      std::vector<int64_t> t = take(cv, indices);
+      for (int64_t x : t) mn = std::min(mn, x);
+    }
+    {
+      std::vector<uint64_t> indices(idx);
+      std::vector<int64_t> t = take(cv, indices);
+      for (int64_t x : t) mx = std::max(mx, x);
+    }
+    double fs = 0;
+    int64_t fc = 0;
+    {
+      std::vector<uint64_t> indices(idx);
+      std::vector<double> t = take(cf, indices);
+      for (double x : t) fs += x;
+      fc = (int64_t)t.size();
+    }
+    out_k[g] = ck[first];
+    out_sum[g] = sum;
+    out_cnt[g] = cnt;
+    out_min[g] = mn;
+    out_max[g] = mx;
+    out_avg[g] = fs / (double)fc;
+    ++g;
+  }
+  return g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Q3: customer(BUILDING) JOIN orders(o_orderdate < d) JOIN lineitem(l_shipdate > d)
+//   -> HashAggregate[l_orderkey, o_orderdate, o_shippriority; SUM(l_extendedprice * (1 - l_discount))]
+// hash_join.rs:148-216,354-385 (build = left, chained JoinHashMap, probe per right batch, key equality re-check,
+// take of the carried columns), hash.rs as above.  Outputs groups in first-occurrence order; returns their number.
+// ---------------------------------------------------------------------------------------------
+struct ChainMap {  // JoinHashMap (hash_join.rs:40-107): hash -> last inserted row + 1, next[row] = previous head
+  std::unordered_map<uint64_t, uint64_t, SipU64Hash> map;
+  std::vector<uint64_t> next;
+  void build(const std::vector<uint64_t>& hashes) {
+    next.assign(hashes.size(), 0);
+    for (size_t r = hashes.size(); r-- > 0;) {  // inserted in reverse so that the chains ascend
+      auto it = map.find(hashes[r]);
+      if (it == map.end()) {
+        map.emplace(hashes[r], (uint64_t)r + 1);
+      } else {
+        next[r] = it->second;
+        it->second = (uint64_t)r + 1;
+      }
+    }
+  }
+};
+static std::vector<uint64_t> sip_i64(const int64_t* key, size_t n) {
+  std::vector<Sip13> hs(n);
+  for (size_t i = 0; i < n; ++i) hs[i].write((const uint8_t*)&key[i], 8);
+  std::vector<uint64_t> out(n);
+  for (size_t i = 0; i < n; ++i) out[i] = hs[i].finish();
+  return out;
+}
+
+int64_t qcpu_q3(int64_t n_c, const int64_t* c_custkey, const int32_t* seg_off, const char* seg_data, int64_t n_o,
+                const int64_t* o_orderkey, const int64_t* o_custkey, const int32_t* o_orderdate, const int64_t* o_shippriority,
+                int64_t n_l, const int64_t* l_orderkey, const int32_t* l_shipdate, const i128* l_price, const i128* l_discount,
+                int64_t batch_rows, const char* segment, const char* date, int64_t max_groups, int64_t* out_orderkey,
+                i128* out_revenue, int32_t* out_orderdate, int64_t* out_shippriority) {
+  const std::string seg(segment);
+  // ---- customer scan: c_mktsegment = 'BUILDING' (literal array of N strings per batch, string compare) --------
+  std::vector<int64_t> b1_custkey;
+  for (int64_t b0 = 0; b0 < n_c; b0 += batch_rows) {
+    const size_t m = (size_t)std::min<int64_t>(batch_rows, n_c - b0);
+    std::vector<std::string> lit(m, seg);
+    std::vector<uint8_t> mask(m);
+    for (size_t i = 0; i < m; ++i) {
+      const int32_t a = seg_off[b0 + i], e = seg_off[b0 + i + 1];
+      mask[i] = (size_t)(e - a) == lit[i].size() && memcmp(seg_data + a, lit[i].data(), lit[i].size()) == 0;
+    }
+    auto fk = filter_new(c_custkey + b0, mask);
+    b1_custkey.insert(b1_custkey.end(), fk.begin(), fk.end());  // concat of the build side (hash_join.rs:154)
+  }
+  ChainMap m1;
+  m1.build(sip_i64(b1_custkey.data(), b1_custkey.size()));
+  // ---- J1 probe: orders batches (filter o_orderdate < date), output columns o_orderkey, o_orderdate, o_shippriority
+  std::vector<int64_t> j1_orderkey, j1_prio;
+  std::vector<int32_t> j1_date;
+  for (int64_t b0 = 0; b0 < n_o; b0 += batch_rows) {
+    const size_t m = (size_t)std::min<int64_t>(batch_rows, n_o - b0);
+    auto d = date_literal_array(date, m);
+    auto mask = cmp(o_orderdate + b0, d, m, LT);
+    auto f_ok = filter_new(o_orderkey + b0, mask), f_ck = filter_new(o_custkey + b0, mask), f_pr = filter_new(o_shippriority + b0, mask);
+    auto f_dt = filter_new(o_orderdate + b0, mask);
+    if (f_ok.empty()) continue;
+    auto ph = sip_i64(f_ck.data(), f_ck.size());
+    std::vector<uint64_t> bi, pi;  // candidate (build, probe) pairs by hash, ascending build rows per probe row
+    for (size_t r = 0; r < ph.size(); ++r) {
+      auto it = m1.map.find(ph[r]);
+      if (it == m1.map.end()) continue;
+      for (uint64_t cur = it->second; cur != 0; cur = m1.next[cur - 1]) {
+        bi.push_back(cur - 1);
+        pi.push_back(r);
+      }
+    }
+    // true key equality: take both key columns, eq, filter the index pairs (hash_join.rs:177-216)
+    std::vector<int64_t> bk = take(b1_custkey, bi), pk = take(f_ck, pi);
+    std::vector<uint64_t> pi2;
+    for (size_t i = 0; i < bk.size(); ++i)
+      if (bk[i] == pk[i]) pi2.push_back(pi[i]);
+    // build_batch_from_indices: take of the carried columns
+    auto t_ok = take(f_ok, pi2);
+    auto t_pr = take(f_pr, pi2);
+    auto t_dt = take(f_dt, pi2);
+    j1_orderkey.insert(j1_orderkey.end(), t_ok.begin(), t_ok.end());
+    j1_prio.insert(j1_prio.end(), t_pr.begin(), t_pr.end());
+    j1_date.insert(j1_date.end(), t_dt.begin(), t_dt.end());
+  }
+  ChainMap m2;
+  m2.build(sip_i64(j1_orderkey.data(), j1_orderkey.size()));
+  // ---- J2 probe: lineitem batches (filter l_shipdate > date) -----------------------------------------------------
+  std::vector<int64_t> j2_orderkey, j2_prio;
+  std::vector<int32_t> j2_date;
+  std::vector<i128> j2_price, j2_disc;
+  for (int64_t b0 = 0; b0 < n_l; b0 += batch_rows) {
+    const size_t m = (size_t)std::min<int64_t>(batch_rows, n_l - b0);
+    auto d = date_literal_array(date, m);
+    auto mask = cmp(l_shipdate + b0, d, m, GT);
+    auto f_ok = filter_new(l_orderkey + b0, mask);
+    auto f_price = filter_new(l_price + b0, mask), f_disc = filter_new(l_discount + b0, mask);
+    if (f_ok.empty()) continue;
+    auto ph = sip_i64(f_ok.data(), f_ok.size());
+    std::vector<uint64_t> bi, pi;
+    for (size_t r = 0; r < ph.size(); ++r) {
+      auto it = m2.map.find(ph[r]);
+      if (it == m2.map.end()) continue;
+      for (uint64_t cur = it->second; cur != 0; cur = m2.next[cur - 1]) {
+        bi.push_back(cur - 1);
+        pi.push_back(r);
+      }
+    }
+    std::vector<int64_t> bk = take(j1_orderkey, bi), pk = take(f_ok, pi);
+    std::vector<uint64_t> bi2, pi2;
+    for (size_t i = 0; i < bk.size(); ++i)
+      if (bk[i] == pk[i]) {
+        bi2.push_back(bi[i]);
+        pi2.push_back(pi[i]);
+      }
+    auto t_ok = take(f_ok, pi2);
+    auto t_price = take(f_price, pi2), t_disc = take(f_disc, pi2);
+    auto t_date = take(j1_date, bi2);
+    auto t_prio = take(j1_prio, bi2);
+    j2_orderkey.insert(j2_orderkey.end(), t_ok.begin(), t_ok.end());
+    j2_price.insert(j2_price.end(), t_price.begin(), t_price.end());
+    j2_disc.insert(j2_disc.end(), t_disc.begin(), t_disc.end());
+    j2_date.insert(j2_date.end(), t_date.begin(), t_date.end());
+    j2_prio.insert(j2_prio.end(), t_prio.begin(), t_prio.end());
+  }
+  const size_t rows = j2_orderkey.size();
+  if (rows == 0) return 0;
+  // ---- HashAggregate: revenue = l_extendedprice * (CAST(1 AS Decimal(20,0)) - l_discount) ---------------------------
+  std::vector<int64_t> lit1(rows, 1);
+  std::vector<i128> one20(rows), one_minus(rows), revenue(rows);
+  for (size_t i = 0; i < rows; ++i) one20[i] = (i128)lit1[i];
+  for (size_t i = 0; i < rows; ++i) one_minus[i] = one20[i] * 100 - j2_disc[i];
+  for (size_t i = 0; i < rows; ++i) revenue[i] = (i128)((u128)j2_price[i] * (u128)one_minus[i]);
+  std::vector<Sip13> hashers(rows);
+  for (size_t i = 0; i < rows; ++i) hashers[i].write((const uint8_t*)&j2_orderkey[i], 8);
+  for (size_t i = 0; i < rows; ++i) hashers[i].write((const uint8_t*)&j2_date[i], 4);
+  for (size_t i = 0; i < rows; ++i) hashers[i].write((const uint8_t*)&j2_prio[i], 8);
+  std::vector<uint64_t> hashes(rows);
+  for (size_t i = 0; i < rows; ++i) hashes[i] = hashers[i].finish();
+  std::unordered_map<uint64_t, size_t, SipU64Hash> map;
+  std::unordered_map<uint64_t, std::vector<uint64_t>, SipU64Hash> accs_indices;
+  std::vector<size_t> group_first;
+  for (size_t row = 0; row < rows; ++row) {
+    auto it = map.find(hashes[row]);
+    if (it != map.end()) {
+      accs_indices[it->second].push_back(row);
+    } else {
+      map.emplace(hashes[row], row);
+      accs_indices[row] = std::vector<uint64_t>{row};
+      group_first.push_back(row);
+    }
+  }
+  int64_t g = 0;
+  for (size_t first : group_first) {
+    if (g >= max_groups) break;
+    std::vector<uint64_t> indices(accs_indices[first]);
+    std::vector<i128> taken = take(revenue, indices);
+    out_orderkey[g] = j2_orderkey[first];
+    out_revenue[g] = sum128(taken);
+    out_orderdate[g] = j2_date[first];
+    out_shippriority[g] = j2_prio[first];
     ++g;
   }
   return g;

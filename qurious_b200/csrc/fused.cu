@@ -1766,12 +1766,11 @@ static bool radix_tail(PlanNode& agg, const View& v, FusedPlan& fp, const FParam
   const int64_t n_buckets = (int64_t)R_P1 << b2;
   const int64_t out_cap = std::max<int64_t>(1, std::min<int64_t>(n_tuples, (int64_t)(est * 1.15) + 65536));
   R.out_cap = out_cap;
-  std::vector<DBufP> keep;
-  for (int c = 0; c < R.n_comp; ++c) {
-    DBufP b = ctx->alloc((size_t)n_tuples * 8 + 64);
-    R.tup_b[c] = (unsigned long long*)b->ptr;
-    keep.push_back(b);
-  }
+  // ONE slab for all level-2 tuple arrays: a single large block of a stable size is what the stream-ordered pool re-uses
+  // without fragmenting (many ~8 GB blocks interleaved with the result columns made later executions re-map memory)
+  const size_t comp_bytes = (((size_t)n_tuples * 8 + 64) + 255) & ~(size_t)255;
+  DBufP slab_b = ctx->alloc(comp_bytes * (size_t)R.n_comp);
+  for (int c = 0; c < R.n_comp; ++c) R.tup_b[c] = (unsigned long long*)((char*)slab_b->ptr + comp_bytes * (size_t)c);
   DBufP hist2 = ctx->alloc_zero((size_t)n_buckets * 4), off2 = ctx->alloc((size_t)(n_buckets + 1) * 8), cur2 = ctx->alloc((size_t)n_buckets * 8);
   R.hist2 = (unsigned int*)hist2->ptr;
   R.off2 = (unsigned long long*)off2->ptr;
@@ -1802,7 +1801,7 @@ static bool radix_tail(PlanNode& agg, const View& v, FusedPlan& fp, const FParam
   const int64_t n_groups = (int64_t)fin[0];
   *fail = (int)fin[1];
   if (*fail != 0) return false;
-  keep.clear();
+  slab_b.reset();
   // ---- key columns from the packed codes --------------------------------------------------------------------------
   RKeys rk;
   memset(&rk, 0, sizeof(rk));
@@ -1888,12 +1887,9 @@ static bool run_radix(PlanNode& agg, const View& v, FusedPlan& fp, View* out) {
     return false;
   }
   if (!radix_choose(R, groups, n_tuples, R_P1, &R.b2, &R.cap, &R.row_cap)) return false;
-  std::vector<DBufP> keep;
-  for (int c = 0; c < R.n_comp; ++c) {
-    DBufP a = ctx->alloc((size_t)n_tuples * 8 + 64);
-    R.tup_a[c] = (unsigned long long*)a->ptr;
-    keep.push_back(a);
-  }
+  const size_t comp_bytes = (((size_t)n_tuples * 8 + 64) + 255) & ~(size_t)255;
+  DBufP slab_a = ctx->alloc(comp_bytes * (size_t)R.n_comp);  // one slab (see radix_tail)
+  for (int c = 0; c < R.n_comp; ++c) R.tup_a[c] = (unsigned long long*)((char*)slab_a->ptr + comp_bytes * (size_t)c);
   radix_launch_scatter1(ctx, P, R);
   int fail = 0;
   if (!radix_tail(agg, v, fp, P, fp.key_shift, fp.key_bits, R, st, n_tuples, n_tiles2, est, out, &fail)) {

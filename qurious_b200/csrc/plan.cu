@@ -346,6 +346,7 @@ void qgpu_shutdown(qgpu_ctx* ctx) {
   if (!ctx) return;
   Ctx* c = &ctx->c;
   cudaSetDevice(c->device);
+  c->release_big_blocks();
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->copy_stream);
   for (auto& e : c->prof_events) {

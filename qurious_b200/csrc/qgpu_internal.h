@@ -207,6 +207,10 @@ struct Ctx {
   int trace_on = -1;
 
   DBufP alloc(size_t bytes);
+  // exact-size free list of large device blocks (kernels.cu: DBuf)
+  std::vector<std::pair<size_t, void*>> big_free;
+  size_t big_free_bytes = 0;
+  void release_big_blocks();
   DBufP alloc_zero(size_t bytes);
   void h2d(void* dst, const void* src, size_t bytes);        // pageable or pinned host -> device
   void d2h_sync(void* dst, const void* src, size_t bytes);   // device -> host, waits
