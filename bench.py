@@ -424,10 +424,23 @@ def run_b200(args):
     top_share = top[2] / max(sum(r[2] for r in prof), 1e-9)
     top_bytes = per_table.get(driving, alg_bytes)   # the dominant kernel streams the driving table
     if q == "groupby":
-        top_bytes += 64 * rows_local            # + one random 32 B sector read + write per row on the group table
+        # algorithmic bytes of the radix passes: tuples are 3 x 8 B; groups leave as 6 x 8 B
+        groups_local = args.groups // world
+        per_kernel = {"k_radix_agg": 24 * rows_local + 48 * groups_local, "k_radix_scatter<1>": 48 * rows_local,
+                      "k_radix_scatter<2>": 48 * rows_local, "k_radix_hist1": 8 * rows_local, "k_radix_hist2": 8 * rows_local}
+        # FM_HASH: streamed columns + one random 32 B sector read + write per row on the group table
+        top_bytes = per_kernel.get(top[0], top_bytes + 64 * rows_local)
     achieved = top_bytes / (top_ms / 1e3) / 1e9 if top_ms > 0 else 0.0
+    traffic, traffic_src = None, None      # measured DRAM bytes per launch of that kernel at this size (ncu), when captured
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        hit = tj.get(f"{top[0]}|{q}|{rows_local}")
+        if hit:
+            traffic, traffic_src = hit["bytes"], hit["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": top_bytes, "bytes_per_row": top_bytes / max(rows_local, 1),
                 "kernel_ms_avg": top_ms, "kernel_share_of_step": top_share, "launches_of_kernel_per_step": top[1] / args.steps,
                 "step_frac_of_roofline": (alg_bytes / (ms / args.steps / 1e3) / 1e9) / peak}

@@ -50,6 +50,8 @@ for rep in sorted(f for f in os.listdir(os.path.join(ROOT, "gpurun_out")) if f.s
 
 for f in sorted(f for f in os.listdir(os.path.join(ROOT, "gpurun_out")) if f.startswith(tag + "_launches") and f.endswith(".csv")):
     rows = [r for r in csv.reader(open(os.path.join(ROOT, "gpurun_out", f))) if len(r) > 10 and r[0] != "ID"]
+    n_all = len(rows)
+    rows = [r for r in rows if "qgpu::" in r[4]]      # the data generator's torch kernels are not part of a step
     agg = collections.OrderedDict()
     for r in rows:
         name = r[4].split("(")[0].replace("void ", "")
@@ -57,7 +59,8 @@ for f in sorted(f for f in os.listdir(os.path.join(ROOT, "gpurun_out")) if f.sta
         a[0] += 1
         a[1] += float(r[-1]) / 1e6
     tot = sum(a[1] for a in agg.values())
-    lines = [f"# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:qgpu (launch list of `bench.py ... --steps 3 --warmup 3`)",
+    lines = [f"# ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv: launch list of `bench.py --query Q --steps 2 --warmup 1 --no-e2e --no-cpu`",
+             f"# {n_all} launches captured, {len(rows)} of them the library's (qgpu::*); the rest is the synthetic-data generator (torch)",
              "# per-launch times are cold-cache and serialised: compare SHARES, not absolutes", f"# total {tot:.3f} ms over {len(rows)} launches",
              f"{'kernel':60s} {'launches':>8s} {'total_ms':>10s} {'avg_ms':>9s} {'share':>7s}"]
     for name, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
