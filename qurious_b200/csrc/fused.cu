@@ -2097,7 +2097,7 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
 // ------------------------------------------------------------------------------------------------
 
 // membership bitmap over the build key's value range (from the base column's statistics: the gathered subset lies
-// inside it); skipped when the range is unknown or would need more than 64 MB
+// inside it); skipped when the range is unknown or would need more than 256 MB
 static DBufP join_key_bitmap(Ctx* ctx, const LazyCol& key, int64_t nb, int64_t* kmin, uint64_t* kspan) {
   *kmin = 0;
   *kspan = 0;
@@ -2105,7 +2105,7 @@ static DBufP join_key_bitmap(Ctx* ctx, const LazyCol& key, int64_t nb, int64_t* 
   ensure_stats(ctx, *key.base);
   if (!key.base->has_stats) return nullptr;
   const i128 range = key.base->vmax - key.base->vmin + 1;
-  if (range <= 0 || range > ((i128)1 << 29) || key.base->vmin < -(LIM62 * 2) || key.base->vmax > LIM62 * 2 - 1) return nullptr;
+  if (range <= 0 || range > ((i128)1 << 31) || key.base->vmin < -(LIM62 * 2) || key.base->vmax > LIM62 * 2 - 1) return nullptr;
   *kmin = (int64_t)key.base->vmin;
   *kspan = (uint64_t)(range - 1);
   return ctx->alloc_zero((size_t)((range + 31) / 32) * 4 + 16);
