@@ -423,6 +423,8 @@ def run_b200(args):
     top_ms = top[2] / max(top[1], 1)
     top_share = top[2] / max(sum(r[2] for r in prof), 1e-9)
     top_bytes = per_table.get(driving, alg_bytes)   # the dominant kernel streams the driving table
+    if q == "q3" and "FM_EMIT" in top[0]:
+        top_bytes = per_table.get("orders", top_bytes)     # J1's probe scan streams orders, not lineitem
     if q == "groupby":
         # algorithmic bytes of the radix passes: tuples are 3 x 8 B; groups leave as 6 x 8 B
         groups_local = args.groups // world

@@ -1,0 +1,138 @@
+"""Parity at BASELINE.json's FULL sizes (TPC-H SF10 Q1 / Q6 / Q3 on one B200, 1 B rows / 100 M groups), where the oracle
+cannot run in seconds: the same seeded generator produces the columns in HBM, and plain torch int64 arithmetic over them
+(exact: every sum stays below 2^63 at these sizes) is the independent checker -- whole-result equality for Q6 and Q1,
+size-independent properties (sum of group sums, number of groups, count of counts, min of mins, max of maxes) for Q3
+and the group-by.  The expected values follow the reference's arithmetic: decimal mul = raw product, scale s1+s2
+(binary.rs:51-68 / arrow mul_wrapping), 1 - d = 100 - raw(d) at scale 2, decimal AVG = sum * 10^4 / count truncated
+(avg.rs:89-116), COUNT = rows (count.rs:40-48)."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import bench  # noqa: E402
+from qurious_b200 import tpch  # noqa: E402
+from qurious_b200.distributed import column_bytes_tensor  # noqa: E402
+from tests.cases import rows_of  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+SF = 10.0
+
+
+def raw_dec(v):
+    return int(v.scaleb(-v.as_tuple().exponent))
+
+
+def trunc_div(a: int, b: int) -> int:
+    q = abs(a) // abs(b)
+    return q if (a >= 0) == (b > 0) else -q
+
+
+@pytest.fixture(scope="module")
+def lineitem():
+    cols = sorted(set(bench.QUERY_COLUMNS["q1"]["lineitem"]) | set(bench.QUERY_COLUMNS["q3"]["lineitem"]))
+    t = tpch.gen_lineitem(SF, device="cuda", columns=cols)
+    assert t.rows == 59_986_052
+    yield t
+    del t
+    torch.cuda.empty_cache()
+
+
+def test_q6_sf10_whole_result(gpu_ctx, lineitem):
+    c = lineitem.cols
+    m = ((c["l_shipdate"] >= tpch.days("1994-01-01")) & (c["l_shipdate"] < tpch.days("1995-01-01")) & (c["l_discount"] >= 5) &
+         (c["l_discount"] <= 7) & (c["l_quantity"] < 2400))
+    expect = int((c["l_extendedprice"][m] * c["l_discount"][m]).sum().item())
+    mt = tpch.to_device_table(gpu_ctx, lineitem)
+    plan = tpch.q6_plan(tpch.Database(SF, None, None, mt))
+    got = rows_of(plan.execute(gpu_ctx))
+    assert "fused_scan_agg" in plan.last_strategy()
+    assert len(got) == 1 and raw_dec(got[0][0]) == expect
+    mt._dev.free()
+
+
+def test_q1_sf10_whole_result(gpu_ctx, lineitem):
+    c, codes, vocab = lineitem.cols, lineitem.codes, lineitem.vocab
+    keep = c["l_shipdate"] <= tpch.days("1998-09-02")
+    expect = {}
+    for rf_i, rf in enumerate(vocab["l_returnflag"]):
+        for ls_i, ls in enumerate(vocab["l_linestatus"]):
+            m = keep & (codes["l_returnflag"] == rf_i) & (codes["l_linestatus"] == ls_i)
+            n = int(m.sum().item())
+            if n == 0:
+                continue
+            qty, price, disc, tax = (c[k][m] for k in ("l_quantity", "l_extendedprice", "l_discount", "l_tax"))
+            dp = price * (100 - disc)
+            s_qty, s_price, s_dp = int(qty.sum().item()), int(price.sum().item()), int(dp.sum().item())
+            s_ch, s_disc = int((dp * (100 + tax)).sum().item()), int(disc.sum().item())
+            expect[(rf, ls)] = (s_qty, s_price, s_dp, s_ch, trunc_div(s_qty * 10**4, n), trunc_div(s_price * 10**4, n),
+                                trunc_div(s_disc * 10**4, n), n)
+    mt = tpch.to_device_table(gpu_ctx, lineitem)
+    plan = tpch.q1_plan(tpch.Database(SF, None, None, mt))
+    got = rows_of(plan.execute(gpu_ctx))
+    assert "fused_scan_agg" in plan.last_strategy()
+    assert len(got) == len(expect) == 4
+    for r in got:
+        assert tuple(raw_dec(x) for x in r[2:9]) + (r[9],) == expect[(r[0], r[1])], r
+    mt._dev.free()
+
+
+def test_q3_sf10_properties(gpu_ctx, lineitem):
+    cust = tpch.gen_customer(SF, device="cuda", columns=bench.QUERY_COLUMNS["q3"]["customer"])
+    orders = tpch.gen_orders(SF, device="cuda", columns=bench.QUERY_COLUMNS["q3"]["orders"])
+    d = tpch.days("1995-03-15")
+    building = cust.cols["c_custkey"][cust.codes["c_mktsegment"] == cust.vocab["c_mktsegment"].index("BUILDING")]
+    o = orders.cols
+    o_keep = (o["o_orderdate"] < d) & torch.isin(o["o_custkey"], building)
+    j1_keys = o["o_orderkey"][o_keep]
+    c = lineitem.cols
+    l_keep = (c["l_shipdate"] > d) & torch.isin(c["l_orderkey"], j1_keys)
+    exp_revenue = int((c["l_extendedprice"][l_keep] * (100 - c["l_discount"][l_keep])).sum().item())
+    exp_groups = int(torch.unique(c["l_orderkey"][l_keep]).numel())
+    tabs = {"customer": tpch.to_device_table(gpu_ctx, cust), "orders": tpch.to_device_table(gpu_ctx, orders),
+            "lineitem": tpch.to_device_table(gpu_ctx, lineitem)}
+    plan = tpch.q3_plan(tpch.Database(SF, tabs["customer"], tabs["orders"], tabs["lineitem"]))
+    res = plan.execute_device(gpu_ctx)
+    assert "fused_join_probe_agg" in plan.last_strategy()
+    assert res.num_rows == exp_groups
+    rev = column_bytes_tensor(res, 1)[0].view(torch.int64).view(-1, 2)        # Decimal128(38,4): lo, hi words
+    assert int(rev[:, 1].abs().max().item()) == 0                              # every group's revenue fits the low word
+    assert int(rev[:, 0].sum().item()) == exp_revenue                          # sum of the group sums
+    keys = column_bytes_tensor(res, 0)[0].view(torch.int64)
+    assert int(torch.unique(keys).numel()) == exp_groups                       # one row per group
+    res.free()
+    for t in tabs.values():
+        t._dev.free()
+
+
+def test_groupby_1b_rows_100m_groups_properties(gpu_ctx):
+    rows, groups = 1_000_000_000, 100_000_000
+    raw = bench.gen_groupby(rows, groups, "cuda")
+    k, v, f = raw.cols["k"], raw.cols["v"], raw.cols["f"]
+    exp = {"sum_v": int(v.sum().item()), "min_v": int(v.min().item()), "max_v": int(v.max().item()), "sum_f": float(f.sum().item())}
+    mt = tpch.to_device_table(gpu_ctx, raw)
+    del raw, v, f
+    exp_groups = int(torch.unique(k).numel())
+    del k
+    torch.cuda.empty_cache()
+    plan = bench.groupby_plan(mt)
+    res = plan.execute_device(gpu_ctx)
+    assert "radix-partitioned" in plan.last_strategy(), plan.last_strategy()
+    col = lambda i, dt: column_bytes_tensor(res, i)[0].view(dt)  # noqa: E731
+    assert res.num_rows == exp_groups
+    cnt = col(2, torch.int64)
+    assert int(cnt.sum().item()) == rows and int(cnt.min().item()) >= 1        # count of counts
+    assert int(col(1, torch.int64).sum().item()) == exp["sum_v"]               # sum of sums (exact)
+    assert int(col(3, torch.int64).min().item()) == exp["min_v"]               # min of mins
+    assert int(col(4, torch.int64).max().item()) == exp["max_v"]               # max of maxes
+    got_sum_f = float((col(5, torch.float64) * cnt.to(torch.float64)).sum().item())
+    assert abs(got_sum_f - exp["sum_f"]) <= 1e-9 * abs(exp["sum_f"])           # sum of avg * count (float: order differs)
+    assert int(torch.unique(col(0, torch.int64)).numel()) == exp_groups        # every key exactly once
+    res.free()
+    mt._dev.free()
+    torch.cuda.empty_cache()
