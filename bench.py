@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--extra-queries", default="", help="comma list of further queries reported under 'queries'")
+    ap.add_argument("--order-by", action="store_true", help="q1 / q3 with their ORDER BY (+ LIMIT 10) on the device (Sort, SURVEY 8f #1)")
     return ap.parse_args()
 
 
@@ -202,11 +203,16 @@ def groupby_plan(table):
                           MaxAggregateExpr(V, pa.int64()), AvgAggregateExpr(F, pa.float64(), pa.float64())])
 
 
+ORDER_BY = False
+
+
 def build_plan(query, tables):
     from qurious_b200 import tpch
     if query == "groupby":
         return groupby_plan(tables["t"])
     db = tpch.Database(0.0, tables.get("customer"), tables.get("orders"), tables.get("lineitem"))
+    if ORDER_BY and query in ("q1", "q3"):
+        return tpch.q1_sorted_plan(db) if query == "q1" else tpch.q3_top10_plan(db)
     return getattr(tpch, query + "_plan")(db)
 
 
@@ -563,7 +569,9 @@ def run_b200(args):
 
 
 def main():
+    global ORDER_BY
     args = parse_args()
+    ORDER_BY = args.order_by
     if args.impl == "reference":
         run_reference(args)
     else:

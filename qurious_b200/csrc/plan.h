@@ -4,7 +4,7 @@
 
 namespace qgpu {
 
-enum PlanKind { PK_SCAN = 1, PK_FILTER, PK_PROJECTION, PK_AGGREGATE, PK_HASH_JOIN };
+enum PlanKind { PK_SCAN = 1, PK_FILTER, PK_PROJECTION, PK_AGGREGATE, PK_HASH_JOIN, PK_SORT, PK_LIMIT };
 
 struct AggDesc {
   int op = 0;
@@ -35,6 +35,10 @@ struct PlanNode {
   std::shared_ptr<ExprNode> join_filter_expr;
   Schema join_filter_schema;
   std::vector<int> join_filter_index, join_filter_side;
+  // Sort (exprs = sort expressions) / Limit
+  std::vector<int> sort_desc, sort_nulls_first;
+  int64_t sort_limit = -1;
+  int64_t limit_fetch = -1, limit_skip = 0;
   // stats of the last execute
   double last_ms = 0;
   int64_t last_launches = 0;
@@ -65,6 +69,10 @@ int radix_exchange_sketch(PlanNode& root, const int64_t* global_stats, void** de
 int radix_exchange_prepare(PlanNode& root, const void* gathered_host, int world, int rank, void* handles_out, int32_t* n_handles);
 void radix_exchange_scatter(PlanNode& root, const void* all_handles);
 int radix_exchange_finish(PlanNode& root);
+
+// sort.cu
+View run_sort(PlanNode& node, const View& input);
+View run_limit(PlanNode& node, const View& input);
 
 std::shared_ptr<TableImpl> hash_partition_table(TableImpl& t, int key_col, int n_parts, std::vector<int64_t>& offsets);
 

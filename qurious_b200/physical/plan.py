@@ -258,6 +258,66 @@ class Projection(PhysicalPlan):
         return h
 
 
+class SortOptions:
+    """arrow::compute::SortOptions {descending, nulls_first}."""
+
+    def __init__(self, descending: bool = False, nulls_first: bool = True):
+        self.descending, self.nulls_first = bool(descending), bool(nulls_first)
+
+
+class PhyscialSortExpr:
+    """`PhyscialSortExpr::new(expr, options)` (sort.rs:12-21; the reference's spelling)."""
+
+    def __init__(self, expr: PhysicalExpr, options: SortOptions):
+        self.expr, self.options = expr, options
+
+
+class Sort(PhysicalPlan):
+    """`Sort::new(exprs, input)` / `Sort::new_with_limit(exprs, input, limit)` (sort.rs:29-41)."""
+
+    def __init__(self, exprs: Sequence[PhyscialSortExpr], input: PhysicalPlan, limit: Optional[int] = None):
+        self.exprs = list(exprs)
+        self.input = input
+        self.limit = limit
+        self.schema = input.schema       # sort.rs:44-46
+
+    @staticmethod
+    def new_with_limit(exprs, input, limit) -> "Sort":
+        return Sort(exprs, input, limit)
+
+    def children(self):
+        return self.input.children()     # sort.rs:79-81: the reference skips the input itself
+
+    def _build(self, ctx, keep):
+        ih = self.input._build(ctx, keep)
+        arr, hs = _exprs_array(ctx, [e.expr for e in self.exprs], keep)
+        n = len(self.exprs)
+        desc = (ctypes.c_int32 * max(n, 1))(*[1 if e.options.descending else 0 for e in self.exprs])
+        nf = (ctypes.c_int32 * max(n, 1))(*[1 if e.options.nulls_first else 0 for e in self.exprs])
+        h = ctypes.c_void_p()
+        ctx.check(ctx.lib.qgpu_plan_sort(ctx.handle, ih, arr, desc, nf, n, -1 if self.limit is None else int(self.limit), ctypes.byref(h)))
+        keep.append(("plan", h))
+        return h
+
+
+class Limit(PhysicalPlan):
+    """`Limit::new(input, fetch, skip)` (limit.rs:15-19)."""
+
+    def __init__(self, input: PhysicalPlan, fetch: Optional[int], skip: int):
+        self.input, self.fetch, self.skip = input, fetch, int(skip)
+        self.schema = input.schema       # limit.rs:23-25
+
+    def children(self):
+        return self.input.children()     # limit.rs:60-62
+
+    def _build(self, ctx, keep):
+        ih = self.input._build(ctx, keep)
+        h = ctypes.c_void_p()
+        ctx.check(ctx.lib.qgpu_plan_limit(ctx.handle, ih, -1 if self.fetch is None else int(self.fetch), self.skip, ctypes.byref(h)))
+        keep.append(("plan", h))
+        return h
+
+
 def _agg_descs(ctx, aggs: Sequence[AggregateExpr], keep: list):
     descs = (_lib.qgpu_agg_desc * max(len(aggs), 1))()
     for i, a in enumerate(aggs):

@@ -502,3 +502,22 @@ def q3_probe_plan(build: MemoryTable, lineitem: MemoryTable) -> Projection:
     out = pa.schema([("l_orderkey", pa.int64()), ("revenue", rt), ("o_orderdate", pa.date32()), ("o_shippriority", pa.int64())])
     return Projection(out, agg, [Column("l_orderkey", 0), Column("revenue", 3), Column("o_orderdate", 1),
                                  Column("o_shippriority", 2)])
+
+
+# ------------------------------------------------------------------------------------------------
+# the complete Q1 / Q3 statements: ORDER BY (+ LIMIT) on top of the hot path (SURVEY 8f "next" #1)
+# ------------------------------------------------------------------------------------------------
+def q1_sorted_plan(db: Database):
+    """q1.slt:1-22 with its `ORDER BY l_returnflag, l_linestatus` (planner: ascending, nulls_first = true)."""
+    from .physical.plan import PhyscialSortExpr, Sort, SortOptions
+    p = q1_plan(db)
+    return Sort([PhyscialSortExpr(Column("l_returnflag", 0), SortOptions(False, True)),
+                 PhyscialSortExpr(Column("l_linestatus", 1), SortOptions(False, True))], p)
+
+
+def q3_top10_plan(db: Database):
+    """q3.slt:1-24 with its `ORDER BY revenue DESC, o_orderdate LIMIT 10` (Sort::new_with_limit, planner/mod.rs:69-83)."""
+    from .physical.plan import PhyscialSortExpr, Sort, SortOptions
+    p = q3_plan(db)
+    return Sort.new_with_limit([PhyscialSortExpr(Column("revenue", 1), SortOptions(True, True)),
+                                PhyscialSortExpr(Column("o_orderdate", 2), SortOptions(False, True))], p, 10)

@@ -100,6 +100,30 @@ def _scalar_rows(v) -> List[tuple]:
 
 def golden_cases() -> Iterator[Case]:
     G = GOLDEN
+    # ---------------------------------------------------------------- sort.rs / limit.rs unit tests, order_by.slt, limit.slt
+    from qurious_b200.physical.plan import Limit, PhyscialSortExpr, Sort, SortOptions
+    SL = G["sort_limit"]
+    PT = {"int32": pa.int32(), "float64": pa.float64(), "uint64": pa.uint64()}
+
+    def sort_keys(t, keys):
+        return [PhyscialSortExpr(col(t, k), SortOptions(descending=desc, nulls_first=nf)) for k, desc, nf in keys]
+    for c in SL["sort_unit"]:
+        t = table(c["table"], types={k: PT[v] for k, v in c["types"].items()}, nullable=False)
+        yield (f"sort:{c['name']}", Sort(sort_keys(t, c["keys"]), scan(t), c["limit"]), [tuple(r) for r in c["expected"]], True)
+    lu = SL["limit_unit"]
+    t = table(lu["table"], types={k: PT[v] for k, v in lu["types"].items()}, nullable=False)
+    yield ("limit:test_limit", Limit(scan(t), lu["fetch"], lu["skip"]), [tuple(r) for r in lu["expected"]], True)
+    for n_, c in enumerate(SL["order_by_slt"]):
+        t = table(c["table"])
+        sel = Projection(schema_of(*[(k, I64) for k in c["select"]]), scan(t), [col(t, k) for k in c["select"]])
+        plan = Sort([PhyscialSortExpr(Column(k, c["select"].index(k)), SortOptions(descending=desc, nulls_first=nf)) for k, desc, nf in c["keys"]],
+                    sel)
+        yield (f"order_by.slt:{n_}", plan, [tuple(r) for r in c["expected"]], True)
+    ls = SL["limit_slt"]
+    for n_, c in enumerate(ls["cases"]):
+        t = table(ls["table"], nullable=False)
+        plan = Limit(Projection(schema_of(("v1", I64)), scan(t), [col(t, "v1")]), c["fetch"], c["skip"])
+        yield (f"limit.slt:{n_}", plan, [(x,) for x in c["expected"]], True)
     # ---------------------------------------------------------------- binary.rs unit tests
     for kind, dt, out_t in (("binary_comparison", pa.int32(), pa.bool_()), ("binary_arithmetic", pa.int32(), pa.int32()),
                             ("binary_logical", pa.bool_(), pa.bool_())):
@@ -369,7 +393,10 @@ def check_rows(name: str, got: List[tuple], expected: List[tuple], ordered: bool
     for g, e in zip(got, expected):
         assert len(g) == len(e), f"{name}: arity {g} vs {e}"
         for a, b in zip(g, e):
-            if isinstance(b, float) and a is not None:
+            if isinstance(b, float) and a is not None and (b != b or b in (float("inf"), float("-inf"))):
+                import math
+                assert isinstance(a, float) and ((math.isnan(a) and math.isnan(b)) or a == b), f"{name}: {g} != {e}"
+            elif isinstance(b, float) and a is not None:
                 assert abs(a - b) <= 1e-12 * max(1.0, abs(b)), f"{name}: {g} != {e}"
             else:
                 assert a == b, f"{name}: {g} != {e}\n got={got}\n exp={expected}"
