@@ -182,6 +182,155 @@ __global__ void __launch_bounds__(S_NT) k_rs_scatter(const unsigned char* __rest
   }
 }
 
+
+// exclusive scan of up to a few 100 k int64 counters by ONE block (no host round trip between the radix passes)
+__global__ void __launch_bounds__(1024) k_rs_scan(const long long* __restrict__ in, long long* __restrict__ out, int n) {
+  __shared__ long long part[1024];
+  const int t = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int i0 = min(n, t * per), i1 = min(n, i0 + per);
+  long long s = 0;
+  for (int i = i0; i < i1; ++i) s += in[i];
+  part[t] = s;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    const long long x = t >= d ? part[t - d] : 0;
+    __syncthreads();
+    part[t] += x;
+    __syncthreads();
+  }
+  long long run = part[t] - s;
+  for (int i = i0; i < i1; ++i) {
+    out[i] = run;
+    run += in[i];
+  }
+}
+
+// Small inputs (<= S_TILE rows, e.g. the 4 groups of Q1 or the candidates of a top-N): the whole stable LSD radix sort in
+// ONE block.  ids[m] = the rows to order (ascending row ids: the tie-break), planes indexed by row id; constant planes are
+// detected and skipped on the fly.  out[i] = i-th row id in sorted order, i < keep.
+__global__ void __launch_bounds__(S_NT) k_sort_small(const unsigned char* __restrict__ planes, int64_t n_rows, int key_bytes,
+                                                     const long long* __restrict__ ids, int m, long long* __restrict__ out, int keep) {
+  __shared__ long long sid[S_TILE];
+  __shared__ unsigned short perm[2][S_TILE];
+  __shared__ unsigned short cnt[16][S_NT];
+  __shared__ unsigned int wtot[S_NT / 32];
+  __shared__ unsigned int dbase[16];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int i = t; i < m; i += S_NT) {
+    sid[i] = ids ? ids[i] : (long long)i;
+    perm[0][i] = (unsigned short)i;
+  }
+  __syncthreads();
+  int cur = 0;
+  for (int b = key_bytes - 1; b >= 0; --b) {
+    const unsigned char* plane = planes + (size_t)b * (size_t)n_rows;
+    const unsigned char first = plane[sid[0]];
+    int differs = 0;
+    for (int i = t; i < m; i += S_NT) differs |= plane[sid[i]] != first;
+    if (!__syncthreads_or(differs)) continue;
+    for (int shift = 0; shift < 8; shift += 4) {
+      int dig[S_ITEMS];
+      for (int d = 0; d < 16; ++d) cnt[d][t] = 0;
+      for (int k = 0; k < S_ITEMS; ++k) {
+        const int i = t * S_ITEMS + k;
+        dig[k] = i < m ? ((plane[sid[perm[cur][i]]] >> shift) & 15) : -1;
+        if (dig[k] >= 0) cnt[dig[k]][t]++;
+      }
+      __syncthreads();
+      unsigned int mine[16];
+      for (int d = 0; d < 16; ++d) {
+        const unsigned int c = cnt[d][t];
+        unsigned int incl = c;
+#pragma unroll
+        for (int s2 = 1; s2 < 32; s2 <<= 1) {
+          const unsigned int o = __shfl_up_sync(0xffffffffu, incl, s2);
+          if (lane >= s2) incl += o;
+        }
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();
+        unsigned int wbase = 0, total = 0;
+        for (int w = 0; w < S_NT / 32; ++w) {
+          if (w < warp) wbase += wtot[w];
+          total += wtot[w];
+        }
+        mine[d] = wbase + incl - c;
+        if (t == 0) dbase[d] = total;
+        __syncthreads();
+      }
+      if (t == 0) {
+        unsigned int run = 0;
+        for (int d = 0; d < 16; ++d) {
+          const unsigned int c = dbase[d];
+          dbase[d] = run;
+          run += c;
+        }
+      }
+      __syncthreads();
+      for (int k = 0; k < S_ITEMS; ++k) {
+        if (dig[k] < 0) continue;
+        const int d = dig[k];
+        perm[cur ^ 1][dbase[d] + mine[d]++] = perm[cur][t * S_ITEMS + k];
+      }
+      __syncthreads();
+      cur ^= 1;
+    }
+  }
+  for (int i = t; i < keep && i < m; i += S_NT) out[i] = sid[perm[cur][i]];
+}
+
+// top-N prefilter: 16-bit prefix = the two most significant non-constant key bytes
+__global__ void __launch_bounds__(256) k_topn_hist(const unsigned char* __restrict__ p0, const unsigned char* __restrict__ p1, int64_t n,
+                                                   unsigned int* __restrict__ hist) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride) {
+    // most rows share a few prefixes: one atomic per distinct prefix and warp instead of one per row
+    const unsigned key = ((unsigned)p0[row] << 8) | (p1 ? (unsigned)p1[row] : 0u);
+    const unsigned peers = __match_any_sync(__activemask(), key);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[key], (unsigned)__popc(peers));
+  }
+}
+// smallest prefix t with #rows(prefix <= t) >= limit; res[0] = t, res[1] = that row count
+__global__ void __launch_bounds__(1024) k_topn_threshold(const unsigned int* __restrict__ hist, long long limit, long long* __restrict__ res) {
+  __shared__ long long part[1024];
+  const int t = threadIdx.x;
+  long long s = 0;
+  for (int i = 0; i < 64; ++i) s += hist[t * 64 + i];
+  part[t] = s;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    const long long x = t >= d ? part[t - d] : 0;
+    __syncthreads();
+    part[t] += x;
+    __syncthreads();
+  }
+  long long run = part[t] - s;  // rows with a smaller prefix than this thread's first bin
+  if (run < limit && part[t] >= limit) {
+    for (int i = 0; i < 64; ++i) {
+      run += hist[t * 64 + i];
+      if (run >= limit) {
+        res[0] = t * 64 + i;
+        res[1] = run;
+        break;
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_topn_flags(const unsigned char* __restrict__ p0, const unsigned char* __restrict__ p1, int64_t n,
+                                                    const long long* __restrict__ res, long long* __restrict__ flags) {
+  const unsigned thr = (unsigned)res[0];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride)
+    flags[row] = ((((unsigned)p0[row] << 8) | (p1 ? (unsigned)p1[row] : 0u)) <= thr) ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) k_topn_compact(const long long* __restrict__ flags, const long long* __restrict__ offs, int64_t n,
+                                                      long long* __restrict__ ids) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride)
+    if (flags[row]) ids[offs[row]] = row;
+}
+// the general passes work on a candidate list: perm[i] = ids[i] initially
+
 static int sort_class(const DCol& c, int* src_width) {
   *src_width = phys_width(c.phys);
   switch (c.phys) {
@@ -232,9 +381,13 @@ View run_sort(PlanNode& node, const View& v) {
     sc.offsets = col->offsets ? (const int32_t*)col->offsets->ptr : nullptr;
     sc.validity = (col->validity && col->null_count != 0) ? (const uint32_t*)col->validity->ptr : nullptr;
     if (sc.cls == SC_STR) {
-      DBufP m = ctx->alloc_zero(8);
-      LAUNCH(ctx, k_str_maxlen, grid_for(ctx, n, 256), 256, 0, sc.offsets, sc.validity, n, (int*)m->ptr);
-      sc.width = ctx->read_scalar((const int*)m->ptr) + 4;
+      if (n <= S_TILE && col->str_bytes <= 256) {
+        sc.width = (int)col->str_bytes + 4;  // no value is longer than all bytes together: no round trip for small inputs
+      } else {
+        DBufP m = ctx->alloc_zero(8);
+        LAUNCH(ctx, k_str_maxlen, grid_for(ctx, n, 256), 256, 0, sc.offsets, sc.validity, n, (int*)m->ptr);
+        sc.width = ctx->read_scalar((const int*)m->ptr) + 4;
+      }
     } else {
       sc.width = sc.cls == SC_I128 ? 16 : (sc.cls == SC_BIT ? 1 : sc.src_width);
     }
@@ -242,41 +395,94 @@ View run_sort(PlanNode& node, const View& v) {
     key_bytes += 1 + sc.width;
   }
   a.key_bytes = key_bytes;
-  IdxP perm = iota_idx(ctx, n);
+  IdxP perm;
   int passes = 0;
-  if (key_bytes > 0) {
+  std::string how = "stable 4-bit radix passes";
+  if (key_bytes == 0 || keep == 0) {
+    perm = iota_idx(ctx, keep);
+  } else {
     if ((double)key_bytes * (double)n > 64e9) throw_internal("Sort: the normalised keys would not fit (long string keys on a very large input)");
     DBufP planes = ctx->alloc((size_t)key_bytes * (size_t)n + 16);
-    DBufP diff = ctx->alloc_zero((size_t)key_bytes * 4 + 16);
     LAUNCH(ctx, k_sort_keys, grid_for(ctx, n, 256), 256, 0, a, n, (unsigned char*)planes->ptr);
-    LAUNCH(ctx, k_sort_plane_diff, grid_for(ctx, n, 256), 256, 0, (const unsigned char*)planes->ptr, n, key_bytes, (unsigned int*)diff->ptr);
-    std::vector<unsigned int> hdiff((size_t)key_bytes);
-    ctx->d2h_sync(hdiff.data(), diff->ptr, (size_t)key_bytes * 4);
-    // ---- stable LSD radix sort of the permutation, least significant byte first, two 4-bit digits per byte -------------
-    const int n_blocks = (int)((n + S_TILE - 1) / S_TILE);
-    DBufP hist = ctx->alloc((size_t)16 * n_blocks * 8 + 16), offs = ctx->alloc((size_t)16 * n_blocks * 8 + 16);
-    IdxP other = std::make_shared<IdxVec>();
-    other->length = n;
-    other->buf = ctx->alloc((size_t)n * 8 + 16);
-    for (int b = key_bytes - 1; b >= 0; --b) {
-      if (!hdiff[(size_t)b]) continue;
-      const unsigned char* plane = (const unsigned char*)planes->ptr + (size_t)b * (size_t)n;
-      for (int shift = 0; shift < 8; shift += 4) {
-        LAUNCH(ctx, k_rs_hist, n_blocks, S_NT, 0, plane, (const long long*)perm->buf->ptr, n, shift, (long long*)hist->ptr, n_blocks);
-        exclusive_scan_i64(ctx, (const int64_t*)hist->ptr, (int64_t*)offs->ptr, (int64_t)16 * n_blocks);
-        LAUNCH(ctx, k_rs_scatter, n_blocks, S_NT, 0, plane, (const long long*)perm->buf->ptr, (long long*)other->buf->ptr, n, shift,
-               (const long long*)offs->ptr, n_blocks);
-        std::swap(perm, other);
-        ++passes;
+    const unsigned char* pl = (const unsigned char*)planes->ptr;
+    auto new_idx = [&](int64_t len) {
+      IdxP x = std::make_shared<IdxVec>();
+      x->length = len;
+      x->buf = ctx->alloc((size_t)std::max<int64_t>(len, 1) * 8 + 16);
+      return x;
+    };
+    if (n <= S_TILE) {
+      // ---- small input: keys + ONE single-block sort kernel, no host round trip ---------------------------------------------
+      perm = new_idx(keep);
+      LAUNCH(ctx, k_sort_small, 1, S_NT, 0, pl, n, key_bytes, (const long long*)nullptr, (int)n, (long long*)perm->buf->ptr, (int)keep);
+      how = "single-block stable radix sort";
+    } else {
+      DBufP diff = ctx->alloc_zero((size_t)key_bytes * 4 + 16);
+      LAUNCH(ctx, k_sort_plane_diff, grid_for(ctx, n, 256), 256, 0, pl, n, key_bytes, (unsigned int*)diff->ptr);
+      std::vector<unsigned int> hdiff((size_t)key_bytes);
+      ctx->d2h_sync(hdiff.data(), diff->ptr, (size_t)key_bytes * 4);
+      // ---- top-N prefilter: rows whose 16-bit prefix (the two most significant non-constant bytes) lies above the
+      //      limit-th smallest prefix cannot be among the first `limit` rows ------------------------------------------------
+      IdxP ids;        // candidate rows in ascending row order (null: all rows)
+      int64_t m = n;
+      if (keep < n && keep <= S_TILE) {
+        int p0 = -1, p1 = -1;
+        for (int b = 0; b < key_bytes; ++b)
+          if (hdiff[(size_t)b]) {
+            if (p0 < 0) p0 = b;
+            else if (p1 < 0) p1 = b;
+          }
+        if (p0 >= 0) {
+          DBufP th = ctx->alloc_zero((size_t)65536 * 4 + 64);
+          long long* res = (long long*)((char*)th->ptr + 65536 * 4);
+          const unsigned char* q0 = pl + (size_t)p0 * (size_t)n;
+          const unsigned char* q1 = p1 >= 0 ? pl + (size_t)p1 * (size_t)n : nullptr;
+          LAUNCH(ctx, k_topn_hist, grid_for(ctx, n, 256), 256, 0, q0, q1, n, (unsigned int*)th->ptr);
+          LAUNCH(ctx, k_topn_threshold, 1, 1024, 0, (const unsigned int*)th->ptr, (long long)keep, res);
+          DBufP flags = ctx->alloc((size_t)n * 8 + 16), offs = ctx->alloc((size_t)n * 8 + 16);
+          LAUNCH(ctx, k_topn_flags, grid_for(ctx, n, 256), 256, 0, q0, q1, n, (const long long*)res, (long long*)flags->ptr);
+          m = exclusive_scan_i64(ctx, (const int64_t*)flags->ptr, (int64_t*)offs->ptr, n);
+          ids = new_idx(m);
+          LAUNCH(ctx, k_topn_compact, grid_for(ctx, n, 256), 256, 0, (const long long*)flags->ptr, (const long long*)offs->ptr, n,
+                 (long long*)ids->buf->ptr);
+          how = "top-N prefilter " + std::to_string(n) + " -> " + std::to_string(m) + " rows, " + how;
+        }
+      }
+      if (m <= S_TILE) {
+        perm = new_idx(keep);
+        LAUNCH(ctx, k_sort_small, 1, S_NT, 0, pl, n, key_bytes, ids ? (const long long*)ids->buf->ptr : (const long long*)nullptr, (int)m,
+               (long long*)perm->buf->ptr, (int)keep);
+        how += " + single-block stable radix sort";
+      } else {
+        // ---- stable LSD radix sort of the (candidate) permutation, least significant byte first, two 4-bit digits per byte --
+        perm = ids ? ids : iota_idx(ctx, n);
+        const int n_blocks = (int)((m + S_TILE - 1) / S_TILE);
+        DBufP hist = ctx->alloc((size_t)16 * n_blocks * 8 + 16), offs = ctx->alloc((size_t)16 * n_blocks * 8 + 16);
+        IdxP other = new_idx(m);
+        for (int b = key_bytes - 1; b >= 0; --b) {
+          if (!hdiff[(size_t)b]) continue;
+          const unsigned char* plane = pl + (size_t)b * (size_t)n;
+          for (int shift = 0; shift < 8; shift += 4) {
+            LAUNCH(ctx, k_rs_hist, n_blocks, S_NT, 0, plane, (const long long*)perm->buf->ptr, m, shift, (long long*)hist->ptr, n_blocks);
+            if ((int64_t)16 * n_blocks <= ((int64_t)1 << 20))
+              LAUNCH(ctx, k_rs_scan, 1, 1024, 0, (const long long*)hist->ptr, (long long*)offs->ptr, 16 * n_blocks);
+            else
+              exclusive_scan_i64(ctx, (const int64_t*)hist->ptr, (int64_t*)offs->ptr, (int64_t)16 * n_blocks);
+            LAUNCH(ctx, k_rs_scatter, n_blocks, S_NT, 0, plane, (const long long*)perm->buf->ptr, (long long*)other->buf->ptr, m, shift,
+                   (const long long*)offs->ptr, n_blocks);
+            std::swap(perm, other);
+            ++passes;
+          }
+        }
       }
     }
   }
   perm->length = keep;
   out = apply_selection_view(ctx, v, perm);
   out.num_batches = 1;
-  node.strategy = "sort[" + std::to_string(a.n_cols) + " keys, " + std::to_string(key_bytes) + " key bytes, " + std::to_string(passes) +
-                  " stable 4-bit radix passes" + (node.sort_limit >= 0 ? ", top " + std::to_string(keep) : std::string()) + "] <- " +
-                  node.children[0]->strategy;
+  node.strategy = "sort[" + std::to_string(a.n_cols) + " keys, " + std::to_string(key_bytes) + " key bytes, " +
+                  (passes ? std::to_string(passes) + " " : std::string()) + how +
+                  (node.sort_limit >= 0 ? ", top " + std::to_string(keep) : std::string()) + "] <- " + node.children[0]->strategy;
   return out;
 }
 
