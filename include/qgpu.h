@@ -101,10 +101,12 @@ typedef struct qgpu_type {
  *  QGPU_IR_CAST        type(3B)                     physical/expr/cast.rs:32-38 (safe:false)
  *  QGPU_IR_CASE        u32 n_when; stack: when1 then1 .. whenN thenN else   case.rs:30-47
  *  QGPU_IR_IS_NULL / QGPU_IR_IS_NOT_NULL / QGPU_IR_NEGATIVE   is_null.rs / is_not_null.rs / negative.rs
+ *  QGPU_IR_LIKE        u8 negated; stack: expr pattern     physical/expr/like.rs:28-41 (arrow like / nlike: % _ and \ escape)
+ *  QGPU_IR_EXTRACT     u8 part (0 YEAR, 1 MONTH, 2 DAY)    physical/expr/function.rs + functions/datetime/extract.rs (Date32/Date64 -> Int64)
  */
 typedef enum qgpu_ir_op {
   QGPU_IR_COLUMN = 1, QGPU_IR_LITERAL = 2, QGPU_IR_BINARY = 3, QGPU_IR_CAST = 4, QGPU_IR_CASE = 5,
-  QGPU_IR_IS_NULL = 6, QGPU_IR_IS_NOT_NULL = 7, QGPU_IR_NEGATIVE = 8
+  QGPU_IR_IS_NULL = 6, QGPU_IR_IS_NOT_NULL = 7, QGPU_IR_NEGATIVE = 8, QGPU_IR_LIKE = 9, QGPU_IR_EXTRACT = 10
 } qgpu_ir_op;
 
 /* aggregate operator: AggregateOperator of logical/expr/aggregate.rs:56-62 */

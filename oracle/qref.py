@@ -412,6 +412,26 @@ def _f64_total_key(a: np.ndarray) -> np.ndarray:
     return b ^ ((b >> 63) & 0x7FFFFFFFFFFFFFFF)
 
 
+def _as_bytes(v) -> bytes:
+    return v if isinstance(v, bytes) else (v.encode() if isinstance(v, str) else bytes(v))
+
+
+def _like(s: bytes, p: bytes) -> bool:
+    """arrow-rs `like`: % = any sequence, _ = exactly one character, backslash escapes the next pattern character.
+    Restated through a regular expression over the decoded strings (the product uses an iterative matcher)."""
+    import re
+    pat, i, ps = [], 0, p.decode("utf-8", "surrogateescape")
+    while i < len(ps):
+        c = ps[i]
+        if c == "\\" and i + 1 < len(ps):
+            pat.append(re.escape(ps[i + 1]))
+            i += 2
+            continue
+        pat.append(".*" if c == "%" else ("." if c == "_" else re.escape(c)))
+        i += 1
+    return re.fullmatch("".join(pat), s.decode("utf-8", "surrogateescape"), flags=re.S) is not None
+
+
 def _sort_values(col: Col):
     """per-row Python values that compare like arrow's sort kernels (floats by total order, strings bytewise)."""
     if is_float(col.dtype):
@@ -643,6 +663,39 @@ def evaluate(expr, batch: pa.RecordBatch, _cols: Optional[List[Col]] = None) -> 
                 raise internal_err("CASE WHEN must be boolean")
             acc = zip_cols(cond, evaluate(then, batch, cols), acc)
         return acc
+    if k == "Like":  # like.rs:28-41 -> arrow like / nlike: NULL if either side is NULL
+        v = evaluate(expr.expr, batch, cols)
+        p = evaluate(expr.pattern, batch, cols)
+        if not is_str(v.dtype) or not is_str(p.dtype):
+            raise arrow_err(f"Invalid argument error: Invalid string operation: {v.dtype} LIKE {p.dtype}")
+        out = np.zeros(n, dtype=bool)
+        valid = v.valid & p.valid
+        for i in range(n):
+            if valid[i]:
+                out[i] = _like(_as_bytes(v.vals[i]), _as_bytes(p.vals[i])) != expr.negated
+        return Col(pa.bool_(), out, valid)
+    if k == "Function":  # function.rs:23-32 -> DatetimeExtract::eval (functions/datetime/extract.rs:29-77)
+        if expr.func.name() != "EXTRACT" or len(expr.args) != 2:
+            raise internal_err(f"function {expr.func.name()} is not on the hot path")
+        unit = evaluate(expr.args[0], batch, cols)
+        c = evaluate(expr.args[1], batch, cols)
+        if n == 0:
+            return Col(pa.int64(), np.zeros(0, dtype=np.int64))
+        if not is_str(unit.dtype) or not unit.valid[0]:
+            raise internal_err("First argument of `EXTRACT` must be non-null scalar Utf8")
+        part = _as_bytes(unit.vals[0]).decode().lower()
+        if part not in ("year", "month", "day"):
+            raise internal_err(f"Date part '{part}' not supported")
+        if c.dtype not in (pa.date32(), pa.date64()):
+            raise arrow_err(f"Compute error: EXTRACT does not support {c.dtype}")
+        out = np.zeros(n, dtype=np.int64)
+        import datetime as _dt
+        for i in range(n):
+            if c.valid[i]:
+                days = int(c.vals[i]) if c.dtype == pa.date32() else int(c.vals[i]) // 86400000
+                d = _dt.date(1970, 1, 1) + _dt.timedelta(days=days)
+                out[i] = {"year": d.year, "month": d.month, "day": d.day}[part]
+        return Col(pa.int64(), out, c.valid.copy())
     if k == "IsNull":
         c = evaluate(expr.expr, batch, cols)
         return Col(pa.bool_(), ~c.valid)

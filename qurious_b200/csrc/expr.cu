@@ -142,6 +142,20 @@ std::unique_ptr<ExprNode> parse_ir(const uint8_t* ir, size_t len) {
       case QGPU_IR_IS_NULL:
       case QGPU_IR_IS_NOT_NULL:
       case QGPU_IR_NEGATIVE: n->children.push_back(pop()); break;
+      case QGPU_IR_LIKE: {
+        n->op = r.u8();  // negated
+        auto pat = pop();
+        auto val = pop();
+        n->children.push_back(std::move(val));
+        n->children.push_back(std::move(pat));
+        break;
+      }
+      case QGPU_IR_EXTRACT: {
+        n->op = r.u8();  // 0 year, 1 month, 2 day
+        if (n->op > 2) throw_internal("Date part not supported");
+        n->children.push_back(pop());
+        break;
+      }
       default: throw_internal("malformed expression IR (unknown opcode " + std::to_string(n->kind) + ")");
     }
     st.push_back(std::move(n));
@@ -441,6 +455,28 @@ struct Compiler {
         o.wbits = (uint8_t)int_bits(c.type);
         if (c.is_const) fold(begin, c.type);
         return {c.type, c.is_const, "- " + c.disp};
+      }
+      case QGPU_IR_LIKE: {
+        R v = emit(*n.children[0]);
+        R pt = emit(*n.children[1]);
+        if (v.type.id != QGPU_T_UTF8 || pt.type.id != QGPU_T_UTF8)
+          throw_arrow("Invalid argument error: Invalid string operation: " + v.type.str() + " LIKE " + pt.type.str());
+        Op& o = add_op(OP_LIKE);
+        o.sub = (uint8_t)(n.op ? 1 : 0);
+        DType res = mk_type(QGPU_T_BOOL);
+        if (v.is_const && pt.is_const) fold(begin, res);
+        return {res, v.is_const && pt.is_const, v.disp + (n.op ? " NOT LIKE " : " LIKE ") + pt.disp};
+      }
+      case QGPU_IR_EXTRACT: {
+        R c = emit(*n.children[0]);
+        if (c.type.id != QGPU_T_DATE32 && c.type.id != QGPU_T_DATE64)
+          throw_arrow("Compute error: EXTRACT does not support " + c.type.str());
+        Op& o = add_op(OP_EXTRACT);
+        o.sub = (uint8_t)n.op;
+        o.from_id = (uint8_t)c.type.id;
+        DType res = mk_type(QGPU_T_INT64);
+        if (c.is_const) fold(begin, res);
+        return {res, c.is_const, "EXTRACT"};
       }
       default: throw_internal("unsupported physical expression kind " + std::to_string(n.kind));
     }

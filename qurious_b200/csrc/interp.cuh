@@ -18,7 +18,7 @@ namespace qgpu {
 enum VClass : uint8_t { VC_BOOL = 0, VC_INT = 1, VC_UINT = 2, VC_DEC = 3, VC_FLT = 4, VC_STR = 5, VC_NULLT = 6 };
 
 enum OpCode : uint8_t {
-  OP_COL = 1, OP_CONST, OP_CMP, OP_AND, OP_OR, OP_ARITH, OP_CAST, OP_CASE, OP_ISNULL, OP_ISNOTNULL, OP_NEG
+  OP_COL = 1, OP_CONST, OP_CMP, OP_AND, OP_OR, OP_ARITH, OP_CAST, OP_CASE, OP_ISNULL, OP_ISNOTNULL, OP_NEG, OP_LIKE, OP_EXTRACT
 };
 
 enum EvalErr : int { EE_NONE = 0, EE_DIV_ZERO = 1, EE_CAST = 2, EE_OVERFLOW = 3, EE_DEC_PRECISION = 4, EE_PARSE = 5 };
@@ -147,6 +147,64 @@ QHD int64_t days_from_civil(int64_t y, unsigned m, unsigned d) {
   const unsigned doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
   return era * 146097 + (int64_t)doe - 719468;
 }
+// inverse of days_from_civil (proleptic Gregorian calendar; arrow date_part on Date32/Date64)
+QHD void civil_from_days(int64_t z, int64_t* y, unsigned* m, unsigned* d) {
+  z += 719468;
+  const int64_t era = (z >= 0 ? z : z - 146096) / 146097;
+  const unsigned doe = (unsigned)(z - era * 146097);
+  const unsigned yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+  const int64_t yy = (int64_t)yoe + era * 400;
+  const unsigned doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+  const unsigned mp = (5 * doy + 2) / 153;
+  *d = doy - (153 * mp + 2) / 5 + 1;
+  *m = mp < 10 ? mp + 3 : mp - 9;
+  *y = yy + (*m <= 2);
+}
+// SQL LIKE as arrow-rs `like` implements it: % = any sequence, _ = exactly one (UTF-8) character, \ escapes the next
+// pattern character.  Iterative matcher with one backtracking point (the last %).
+QHD int utf8_len_at(const unsigned char* s, int64_t i, int64_t n) {
+  const unsigned char c = s[i];
+  int l = c < 0x80 ? 1 : ((c >> 5) == 6 ? 2 : ((c >> 4) == 14 ? 3 : ((c >> 3) == 30 ? 4 : 1)));
+  return i + l <= n ? l : (int)(n - i);
+}
+QHD bool like_match(const unsigned char* s, int64_t ls, const unsigned char* p, int64_t lp) {
+  int64_t si = 0, pi = 0, star_p = -1, star_s = 0;
+  while (si < ls) {
+    bool ok = false;
+    if (pi < lp) {
+      const unsigned char c = p[pi];
+      if (c == '%') {
+        star_p = pi++;
+        star_s = si;
+        continue;
+      }
+      if (c == '_') {
+        si += utf8_len_at(s, si, ls);
+        ++pi;
+        continue;
+      }
+      if (c == '\\' && pi + 1 < lp) {
+        if (p[pi + 1] == s[si]) {
+          ++si;
+          pi += 2;
+          ok = true;
+        }
+      } else if (c == s[si]) {
+        ++si;
+        ++pi;
+        ok = true;
+      }
+    }
+    if (ok) continue;
+    if (star_p < 0) return false;
+    pi = star_p + 1;
+    star_s += utf8_len_at(s, star_s, ls);
+    si = star_s;
+  }
+  while (pi < lp && p[pi] == '%') ++pi;
+  return pi == lp;
+}
+
 QHD bool parse_date32(const char* s, int len, int64_t* out) {
   while (len > 0 && (s[0] == ' ')) { ++s; --len; }
   while (len > 0 && (s[len - 1] == ' ')) --len;
@@ -636,6 +694,35 @@ QHD Val eval_row(const Program& P, int64_t row, int* err) {
           if (op.vclass == VC_INT) a.lo = (uint64_t)wrap_signed((int64_t)(0ull - a.lo), op.wbits);
           else if (op.vclass == VC_DEC) set_i128(a, (i128)((u128)0 - (u128)val_i128(a)));
           else if (op.vclass == VC_FLT) set_f64(a, -val_f64(a));
+        }
+        st[sp - 1] = a;
+        break;
+      }
+      case OP_LIKE: {  // like.rs:28-41 -> arrow like / nlike (op.sub = negated); NULL if either side is NULL
+        const Val b = st[--sp];
+        const Val a = st[sp - 1];
+        Val r;
+        r.hi = 0;
+        r.pad = 0;
+        r.valid = a.valid & b.valid;
+        r.lo = 0;
+        if (r.valid) {
+          const bool m = like_match((const unsigned char*)a.lo, (int64_t)a.hi, (const unsigned char*)b.lo, (int64_t)b.hi);
+          r.lo = (uint64_t)(m != (op.sub != 0));
+        }
+        st[sp - 1] = r;
+        break;
+      }
+      case OP_EXTRACT: {  // functions/datetime/extract.rs: date_part(YEAR | MONTH | DAY) cast to Int64
+        Val a = st[sp - 1];
+        if (a.valid) {
+          int64_t days = (int64_t)a.lo;
+          if (op.from_id == QGPU_T_DATE64) days = (days >= 0 ? days : days - 86399999) / 86400000;  // ms -> days (floor)
+          int64_t y;
+          unsigned m, d;
+          civil_from_days(days, &y, &m, &d);
+          a.lo = (uint64_t)(op.sub == 0 ? y : (op.sub == 1 ? (int64_t)m : (int64_t)d));
+          a.hi = 0;
         }
         st[sp - 1] = a;
         break;

@@ -27,8 +27,8 @@ import pyarrow as pa
 from ..datatypes import AggregateOperator, Operator, ScalarValue, encode_type
 
 # IR opcodes (include/qgpu.h: enum qgpu_ir_op)
-IR_COLUMN, IR_LITERAL, IR_BINARY, IR_CAST, IR_CASE, IR_IS_NULL, IR_IS_NOT_NULL, IR_NEGATIVE = (
-    1, 2, 3, 4, 5, 6, 7, 8,
+IR_COLUMN, IR_LITERAL, IR_BINARY, IR_CAST, IR_CASE, IR_IS_NULL, IR_IS_NOT_NULL, IR_NEGATIVE, IR_LIKE, IR_EXTRACT = (
+    1, 2, 3, 4, 5, 6, 7, 8, 9, 10,
 )
 
 
@@ -137,6 +137,60 @@ class Negative(PhysicalExpr):
 
     def __str__(self) -> str:
         return f"- {self.expr}"
+
+
+class Like(PhysicalExpr):
+    """`Like::new(negated, expr, pattern)` (physical/expr/like.rs:20-24): arrow `like` / `nlike`."""
+
+    def __init__(self, negated: bool, expr: PhysicalExpr, pattern: PhysicalExpr):
+        self.negated, self.expr, self.pattern = bool(negated), expr, pattern
+
+    def to_ir(self) -> bytes:
+        return self.expr.to_ir() + self.pattern.to_ir() + struct.pack("<BB", IR_LIKE, 1 if self.negated else 0)
+
+    def __str__(self) -> str:  # like.rs:44-52
+        return f"{self.expr} {'NOT LIKE' if self.negated else 'LIKE'} {self.pattern}"
+
+
+class DatetimeExtract:
+    """`functions::datetime::extract::DatetimeExtract` (functions/datetime/extract.rs:17-27): EXTRACT(part FROM date) -> Int64."""
+
+    PARTS = {"year": 0, "month": 1, "day": 2}
+
+    def name(self) -> str:
+        return "EXTRACT"
+
+    def return_type(self) -> pa.DataType:
+        return pa.int64()
+
+
+class Function(PhysicalExpr):
+    """`Function::new(func, args)` (physical/expr/function.rs:11-20).  The one function on the path is EXTRACT: args =
+    [Literal(Utf8 part), date expression] (planner/sql.rs EXTRACT -> function call); the part is folded into the IR."""
+
+    def __init__(self, func, args: Sequence[PhysicalExpr]):
+        self.func, self.args = func, list(args)
+
+    def to_ir(self) -> bytes:
+        if not isinstance(self.func, DatetimeExtract):
+            raise QuriousErrorLazy(f"InternalError: function {self.func.name()} is not supported on the GPU path")
+        if len(self.args) != 2:
+            raise QuriousErrorLazy("InvalidArgumentError: EXTRACT requires 2 arguments")
+        unit = self.args[0]
+        if not isinstance(unit, Literal) or unit.value.value is None or not pa.types.is_string(unit.value.data_type):
+            raise QuriousErrorLazy("InvalidArgumentError: First argument of `EXTRACT` must be non-null scalar Utf8")
+        part = str(unit.value.value).lower()          # extract.rs:63: case-insensitive
+        if part not in DatetimeExtract.PARTS:
+            raise QuriousErrorLazy(f"InternalError: Date part '{part}' not supported")
+        return self.args[1].to_ir() + struct.pack("<BB", IR_EXTRACT, DatetimeExtract.PARTS[part])
+
+    def __str__(self) -> str:  # function.rs:35-39
+        return self.func.name()
+
+
+def QuriousErrorLazy(msg: str):
+    from .._lib import QuriousError
+    return QuriousError(1, msg)
 
 
 # ---------------------------------------------------------------------------------------------

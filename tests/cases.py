@@ -100,6 +100,15 @@ def _scalar_rows(v) -> List[tuple]:
 
 def golden_cases() -> Iterator[Case]:
     G = GOLDEN
+    # ---------------------------------------------------------------- basic_test.slt: EXTRACT on a date literal
+    from qurious_b200.physical.expr import DatetimeExtract, Function
+    ex = G["extract"]
+    one = table({"x": [0]}, nullable=False)
+    d_lit = CastExpr(Literal(ScalarValue.Utf8(ex["date"])), pa.date32())
+    yield ("basic_test.slt:extract",
+           Projection(schema_of(("year", I64), ("month", I64), ("day", I64)), scan(one),
+                      [Function(DatetimeExtract(), [Literal(ScalarValue.Utf8(p_)), d_lit]) for p_ in ("YEAR", "MONTH", "DAY")]),
+           [(ex["year"], ex["month"], ex["day"])], True)
     # ---------------------------------------------------------------- sort.rs / limit.rs unit tests, order_by.slt, limit.slt
     from qurious_b200.physical.plan import Limit, PhyscialSortExpr, Sort, SortOptions
     SL = G["sort_limit"]
