@@ -92,3 +92,13 @@ def test_radix_off_and_default_small_inputs_use_hash(gpu_ctx, monkeypatch):
     got = rows_of(p.execute(gpu_ctx))
     assert "hbm-hash" in p.last_strategy(), p.last_strategy()
     check_rows("hash", got, rows_of(qref.execute(plan_of(t))), ordered=False)
+
+
+def test_radix_predicate_that_keeps_nothing_or_little(gpu_ctx, monkeypatch):
+    monkeypatch.setenv("QGPU_RADIX", "force")
+    t = table(50_000, 9_000, seed=8)
+    s = t.schema
+    for bound in (10**7, 999_990):            # no row / a handful of rows pass
+        pred = bx(Column("v", s.get_field_index("v")), "Gt", lit(bound))
+        p = plan_of(t, predicate=pred)
+        check_rows(f"radix v > {bound}", rows_of(p.execute(gpu_ctx)), rows_of(qref.execute(plan_of(t, predicate=pred))), ordered=False)

@@ -154,7 +154,7 @@ class _Emu:
         return torch.cat([self.box[name][r] for r in range(self.world)])
 
 
-def run_exchange_emulated(gpu_ctx, table, world, make_plan):
+def run_exchange_emulated(gpu_ctx, table, world, make_plan, key_cols=1):
     from qurious_b200.distributed import ExchangeGroupBy
     full = pa.Table.from_batches(table.data).combine_chunks()
     n = full.num_rows
@@ -188,7 +188,7 @@ def run_exchange_emulated(gpu_ctx, table, world, make_plan):
         assert e.finish() == 0
         got = rows_of(e.plan.execute(gpu_ctx))
         assert "exchange[rank" in e.plan.last_strategy(), e.plan.last_strategy()
-        keys = {r_[0] for r_ in got}
+        keys = {tuple(r_[:key_cols]) for r_ in got}
         assert not (keys & seen)
         seen |= keys
         rows += got
@@ -245,3 +245,22 @@ def test_q3_broadcast_build_equals_single(gpu_ctx, world):
                                     lambda b, l_sh=l_sh: tpch.q3_probe_plan(b, l_sh), world, all_gather_ragged=fake_gather)
         check_rows(f"q3 broadcast x{world}", rows_of(bj.execute()), single, ordered=False)
         assert "broadcast-build" in bj.last_strategy
+
+
+def test_exchange_two_keys_and_predicate(gpu_ctx):
+    """keys (d, k) packed over the GLOBAL value ranges (the shards see different minima), pushed-down predicate"""
+    from tests.cases import bx, lit
+    t = make_table(40_000, 900, seed=21)
+    K, V, F, D = (Column(n, SCHEMA.get_field_index(n)) for n in ("k", "v", "f", "d"))
+
+    def plan(table):
+        aggs = [SumAggregateExpr(V, pa.int64()), CountAggregateExpr(V), AvgAggregateExpr(F, pa.float64(), pa.float64())]
+        out = pa.schema([("d", pa.date32()), ("v", pa.int64())] + [(f"a{i}", a.return_type) for i, a in enumerate(aggs)])
+        return HashAggregate(out, Scan(SCHEMA, table, None, bx(V, "Gt", lit(-900_000))), [D, V], aggs)
+    single = rows_of(plan(t).execute(gpu_ctx))
+    check_rows("single vs oracle", single, rows_of(qref.execute(plan(t))), ordered=False)
+    full = pa.Table.from_batches(t.data).combine_chunks().sort_by("v")     # shards with disjoint key ranges
+    ts = MemoryTable.try_new(SCHEMA, full.to_batches())
+    rows = run_exchange_emulated(gpu_ctx, ts, 4, plan, key_cols=2)
+    assert rows is not None
+    check_rows("exchange 2 keys", rows, single, ordered=False)
