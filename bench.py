@@ -457,6 +457,7 @@ def run_b200(args):
     e2e = None
     cpu = None
     host_batches = None
+    ctx.release_cached_memory()     # the device leg's re-usable blocks: the generator below needs the HBM
     if not args.no_e2e and q != "groupby":
         raw_h = gen_raw(q, sf_total, "cuda", rank, world)
         host = {}

@@ -151,6 +151,9 @@ const char* qgpu_last_error(const qgpu_ctx* ctx);
 int qgpu_set_compat(qgpu_ctx* ctx, const char* name, int value);
 /* number of kernel launches issued by this context since creation (bench.py: gpu_launches) */
 int64_t qgpu_kernel_launches(const qgpu_ctx* ctx);
+/* The context keeps large freed device blocks (>= 256 MB, up to 96 GB) for re-use by the next execution of the same plan;
+ * this returns them to the driver (e.g. before another library allocates on the same GPU). */
+int qgpu_release_cached_memory(qgpu_ctx* ctx);
 /* The context's compute stream (a cudaStream_t) so that callers can record their own CUDA events
  * around calls (bench.py times steps with events on THIS stream). */
 void* qgpu_ctx_stream(const qgpu_ctx* ctx);

@@ -27,7 +27,7 @@ SYMBOLS = [
     "qgpu_plan_projection", "qgpu_plan_sort", "qgpu_plan_limit", "qgpu_plan_aggregate", "qgpu_plan_hash_join", "qgpu_plan_schema",
     "qgpu_plan_execute", "qgpu_plan_execute_device", "qgpu_plan_last_stats", "qgpu_plan_strategy",
     "qgpu_plan_free", "qgpu_plan_state_bytes", "qgpu_plan_partial_state", "qgpu_plan_execute_merged", "qgpu_plan_execute_merged_device", "qgpu_plan_set_order_free",
-    "qgpu_table_hash_partition", "qgpu_table_column_device_buffer",
+    "qgpu_release_cached_memory", "qgpu_table_hash_partition", "qgpu_table_column_device_buffer",
     "qgpu_plan_exchange_keystats", "qgpu_plan_exchange_sketch", "qgpu_plan_exchange_prepare", "qgpu_plan_exchange_scatter", "qgpu_plan_exchange_finish",
 ]
 
@@ -117,6 +117,7 @@ def load_library() -> ctypes.CDLL:
     lib.qgpu_plan_free.restype = None
     lib.qgpu_table_hash_partition.argtypes = [vp, i32, i32, P(vp), P(i64)]
     lib.qgpu_table_column_device_buffer.argtypes = [vp, i32, P(vp), P(i64), P(i32)]
+    lib.qgpu_release_cached_memory.argtypes = [vp]
     lib.qgpu_plan_sort.argtypes = [vp, vp, P(vp), P(i32), P(i32), i32, i64, P(vp)]
     lib.qgpu_plan_limit.argtypes = [vp, vp, i64, i64, P(vp)]
     lib.qgpu_plan_exchange_keystats.argtypes = [vp, P(i64), P(i32)]
@@ -158,6 +159,10 @@ class Context:
 
     def set_compat(self, name: str, value: bool):
         self.check(self.lib.qgpu_set_compat(self.handle, name.encode(), 1 if value else 0))
+
+    def release_cached_memory(self):
+        """Give the context's cached large device blocks back to the driver."""
+        self.check(self.lib.qgpu_release_cached_memory(self.handle))
 
     def kernel_launches(self) -> int:
         return int(self.lib.qgpu_kernel_launches(self.handle))

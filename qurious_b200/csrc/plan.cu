@@ -385,6 +385,14 @@ int qgpu_set_compat(qgpu_ctx* ctx, const char* name, int value) {
 
 int64_t qgpu_kernel_launches(const qgpu_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
 
+int qgpu_release_cached_memory(qgpu_ctx* ctx) {
+  if (!ctx) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] {
+    ctx->c.release_big_blocks();
+    ctx->c.sync();
+  });
+}
+
 void* qgpu_ctx_stream(const qgpu_ctx* ctx) { return ctx ? (void*)ctx->c.stream : nullptr; }
 
 int qgpu_profile_enable(qgpu_ctx* ctx, int on) {
