@@ -2435,6 +2435,9 @@ bool try_fused_join_aggregate(PlanNode& agg, View* out) {
     accs.cnt.push_back(cnt);
   }
   accs.first_row = first;
+  // many groups: keep the build-row order of the groups (deterministic) instead of ranking them by first probe row -- the
+  // reference's group order is unspecified (hash.rs:98) and the ranking is a 64-bit radix sort of n_groups pairs
+  accs.unordered = n_groups > 4096;
   auto rows = std::make_shared<IdxVec>();
   rows->length = n_groups;
   rows->buf = ctx->alloc((size_t)ng_alloc * 8);
