@@ -106,6 +106,15 @@ struct FParams {
   //          one 64 B record per group => one cache line per row instead of one per accumulator
   //   PROBE: structure of arrays over build rows (acc_base 0, kstride = build rows, gstride 1)
   int64_t acc_base, acc_kstride, acc_gstride;
+  // DENSE + specialised body: accumulators in `pack_mask` are bit fields of the row-count word of the thread's private
+  // slot (count in bits [0, pack_cnt_bits), accumulator k in [pack_shift[k], pack_shift[k] + pack_bits[k])): the host
+  // proved from the column statistics that they are non-negative and that a thread's partial sums fit their fields
+  uint32_t pack_mask, pack_cnt_bits;
+  uint8_t pack_shift[F_MAXA], pack_bits[F_MAXA];
+  // DENSE private table: priv[(slot * priv_lines + line) * F_NT + thread]; line of accumulator / count / first row k
+  // (0xff: packed into the count word) and the reverse map
+  int32_t priv_lines;
+  uint8_t priv_line_of[F_MAXA + 2], priv_k_of[F_MAXA + 2];
   FCol cols[F_MAXC];
   FPred pred[F_MAXP];
   FKey keys[F_MAXK];
@@ -513,11 +522,12 @@ __device__ __forceinline__ void fused_main(const FParams& p) {
   long long* priv = (long long*)(smem + p.priv_off);
   const int tid = threadIdx.x;
   const int NA2 = p.n_accs + 2;
+  const int NL = MODE == FM_DENSE ? p.priv_lines : NA2;  // private lines per slot (packed accumulators have none)
   const bool producer = tid >= F_NT;
 
   if (MODE == FM_DENSE && !producer) {
-    const int total = p.dense_groups * NA2 * F_NT;
-    for (int i = tid; i < total; i += F_NT) priv[i] = acc_init(p, (i / F_NT) % NA2);
+    const int total = p.dense_groups * NL * F_NT;
+    for (int i = tid; i < total; i += F_NT) priv[i] = acc_init(p, p.priv_k_of[(i / F_NT) % NL]);
   }
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -533,26 +543,29 @@ __device__ __forceinline__ void fused_main(const FParams& p) {
   const int64_t my_tiles = first_tile < p.n_tiles ? (p.n_tiles - first_tile + gridDim.x - 1) / gridDim.x : 0;
 
   if (producer) {
-    if (tid == F_NT) {
-      const uint64_t l2_policy = l2_evict_first_policy();
+    // Lane c of the producer warp issues column c's bulk copy: the copies of one tile are issued concurrently.  (One
+    // elected thread issuing all of them back to back capped the whole pipeline at ~5.2 TB/s -- Q1 SF10 0.48 ms; one
+    // lane per column reaches the box's read bandwidth, 6.7-6.9 TB/s -- 0.34 ms.)
+    const int lane = tid - F_NT;
+    const uint64_t l2_policy = l2_evict_first_policy();
+    const unsigned char* src = lane < p.n_cols ? p.cols[lane].ptr : nullptr;
+    const uint32_t width = lane < p.n_cols ? p.cols[lane].width : 0u;
+    const uint32_t smem_off = lane < p.n_cols ? p.cols[lane].smem_off : 0u;
 #pragma unroll 1
-      for (int64_t i = 0; i < my_tiles; ++i) {
-        const int s = (int)(i % p.stages);
-        const int64_t use = i / p.stages;
-        if (use > 0) mbar_wait(&empty[s], (uint32_t)((use - 1) & 1));  // every consumer warp released the previous use
-        const int64_t row0 = (first_tile + i * gridDim.x) * F_T;
-        const int64_t rows = min((int64_t)F_T, p.n_rows - row0);
-        unsigned char* dst = tiles + (size_t)s * p.stage_bytes;
-        uint32_t total = 0;
-#pragma unroll 1
-        for (int c = 0; c < p.n_cols; ++c) total += ((uint32_t)(rows * p.cols[c].width) + 15u) & ~15u;
-        mbar_expect_tx(&full[s], total);
-#pragma unroll 1
-        for (int c = 0; c < p.n_cols; ++c) {
-          const uint32_t bytes = ((uint32_t)(rows * p.cols[c].width) + 15u) & ~15u;
-          bulk_g2s(dst + p.cols[c].smem_off, p.cols[c].ptr + (size_t)row0 * p.cols[c].width, bytes, &full[s], l2_policy);
-        }
-      }
+    for (int64_t i = 0; i < my_tiles; ++i) {
+      const int s = (int)(i % p.stages);
+      const int64_t use = i / p.stages;
+      if (use > 0) mbar_wait(&empty[s], (uint32_t)((use - 1) & 1));  // every consumer warp released the previous use
+      const int64_t row0 = (first_tile + i * gridDim.x) * F_T;
+      const int64_t rows = min((int64_t)F_T, p.n_rows - row0);
+      unsigned char* dst = tiles + (size_t)s * p.stage_bytes;
+      const uint32_t bytes = ((uint32_t)(rows * width) + 15u) & ~15u;
+      uint32_t total = bytes;
+#pragma unroll
+      for (int d = 16; d; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+      if (lane == 0) mbar_expect_tx(&full[s], total);
+      __syncwarp();  // the expected byte count is registered before any copy can complete
+      if (lane < p.n_cols) bulk_g2s(dst + smem_off, src + (size_t)row0 * width, bytes, &full[s], l2_policy);
     }
   } else {
 #pragma unroll 1
@@ -563,7 +576,7 @@ __device__ __forceinline__ void fused_main(const FParams& p) {
       const int64_t row0 = (first_tile + i * gridDim.x) * F_T;
       const int rows = (int)min((int64_t)F_T, p.n_rows - row0);
       // HASH: once the table overflowed the host retries with a larger one; the rest of this pass only drains
-      if (!(MODE == FM_HASH && *(volatile int*)p.abort_flag != 0)) Body::tile(p, stage, row0, rows, tid, priv, NA2);
+      if (!(MODE == FM_HASH && *(volatile int*)p.abort_flag != 0)) Body::tile(p, stage, row0, rows, tid, priv, NL);
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s
     }
@@ -577,15 +590,17 @@ __device__ __forceinline__ void fused_main(const FParams& p) {
     for (int line = producer ? n_lines : warp; line < n_lines; line += F_NT / 32) {
       const int k = line % NA2;
       const int g = line / NA2;
-      const long long* src = priv + (size_t)line * F_NT;
+      const int pl = p.priv_line_of[k];  // 0xff: packed into the count word
+      const long long* src = priv + ((size_t)g * NL + (pl == 0xff ? 0 : pl)) * F_NT;
       int kind = FK_SUM;
       if (k < p.n_accs) kind = p.accs[k].kind;
       else if (k == p.n_accs + 1) kind = FK_MIN;
       // skip groups this CTA never saw
       long long cnt = 0;
+      const long long* csrc = priv + ((size_t)g * NL + p.priv_line_of[p.n_accs]) * F_NT;
+      const unsigned long long cmask = p.pack_mask ? ((1ull << p.pack_cnt_bits) - 1ull) : ~0ull;
       {
-        const long long* csrc = priv + ((size_t)g * NA2 + p.n_accs) * F_NT;
-        for (int j = lane; j < F_NT; j += 32) cnt += csrc[j];
+        for (int j = lane; j < F_NT; j += 32) cnt += (long long)((unsigned long long)csrc[j] & cmask);
 #pragma unroll
         for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
       }
@@ -593,8 +608,13 @@ __device__ __forceinline__ void fused_main(const FParams& p) {
       unsigned long long* glo = p.g_lo + line;
       unsigned long long* ghi = p.g_hi + line;
       if (kind == FK_SUM) {
+        // packed accumulators and the row count are fields of the count word (see FParams::pack_mask)
+        const bool packed = k < p.n_accs && ((p.pack_mask >> k) & 1u);
+        const long long* rsrc = packed ? csrc : src;
+        const int sh = packed ? (int)p.pack_shift[k] : 0;
+        const unsigned long long fm = packed ? ((1ull << p.pack_bits[k]) - 1ull) : (k == p.n_accs ? cmask : ~0ull);
         i128 s = 0;
-        for (int j = lane; j < F_NT; j += 32) s += (i128)src[j];
+        for (int j = lane; j < F_NT; j += 32) s += (i128)(long long)(((unsigned long long)rsrc[j] >> sh) & fm);
         unsigned long long lo = (unsigned long long)(u128)s, hi = (unsigned long long)((u128)s >> 64);
 #pragma unroll
         for (int d = 16; d; d >>= 1) {
@@ -700,9 +720,13 @@ __device__ __forceinline__ void load_rows_t(const unsigned char* col, int tid, i
   }
 }
 
-template <uint64_t S0, uint64_t S1, uint64_t S2, uint64_t S3>
+template <uint64_t S0, uint64_t S1, uint64_t S2, uint64_t S3, uint32_t PACK>
 struct SpecBody {
   typedef SigView<S0, S1, S2, S3> G;
+  static constexpr bool packed(int k) { return (PACK >> k) & 1u; }
+  static constexpr int popc(uint32_t x) { return x == 0 ? 0 : (int)(x & 1u) + popc(x >> 1); }
+  static constexpr int line_of(int k) { return k - popc(PACK & ((1u << k) - 1u)); }  // FParams::priv_line_of
+  static constexpr int n_lines = G::n_accs + 2 - popc(PACK);
   // value of accumulator K for the thread's rows (compile-time recursion keeps every index static)
   template <int K, int F>
   static __device__ __forceinline__ void factors(const FParams& p, const unsigned char* stage, int tid, int64_t (&v)[F_R]) {
@@ -766,21 +790,29 @@ struct SpecBody {
   template <int K>
   static __device__ __forceinline__ void rmw_load(const long long* a, long long (&cur)[F_MAXA]) {
     if constexpr (K < G::n_accs) {
-      cur[K] = a[K * F_NT];
+      if constexpr (!packed(K)) cur[K] = a[line_of(K) * F_NT];
       rmw_load<K + 1>(a, cur);
     }
   }
   template <int K>
   static __device__ __forceinline__ void rmw_store(long long* a, const long long (&cur)[F_MAXA], const int64_t (&val)[F_MAXA][F_R], int j) {
     if constexpr (K < G::n_accs) {
-      a[K * F_NT] = comb<G::kind(K)>(cur[K], val[K][j]);
+      if constexpr (!packed(K)) a[line_of(K) * F_NT] = comb<G::kind(K)>(cur[K], val[K][j]);
       rmw_store<K + 1>(a, cur, val, j);
+    }
+  }
+  // increment of the count word: 1 row + the packed accumulators' values in their bit fields
+  template <int K>
+  static __device__ __forceinline__ void pack_inc(const FParams& p, const int64_t (&val)[F_MAXA][F_R], int j, long long& inc) {
+    if constexpr (K < G::n_accs) {
+      if constexpr (packed(K)) inc += (long long)((unsigned long long)val[K][j] << p.pack_shift[K]);
+      pack_inc<K + 1>(p, val, j, inc);
     }
   }
 
   static __device__ __forceinline__ void tile(const FParams& p, const unsigned char* stage, const int64_t row0, const int rows,
                                               const int tid, long long* priv, const int /*NA2*/) {
-    constexpr int NA2c = G::n_accs + 2;
+    constexpr int CL = n_lines - 2, FL = n_lines - 1;  // count word, first row
     uint32_t pass = 0;
 #pragma unroll
     for (int j = 0; j < F_R; ++j)
@@ -796,22 +828,25 @@ struct SpecBody {
 #pragma unroll
     for (int j = 0; j < F_R; ++j) {
       if ((pass >> j) & 1) {
-        long long* a = priv + code[j] * (uint32_t)(NA2c * F_NT) + (uint32_t)tid;
+        long long* a = priv + code[j] * (uint32_t)(n_lines * F_NT) + (uint32_t)tid;
         long long cur[F_MAXA];
         rmw_load<0>(a, cur);
-        const long long cc = a[G::n_accs * F_NT];
-        const long long ff = a[(G::n_accs + 1) * F_NT];
+        const long long cc = a[CL * F_NT];
         rmw_store<0>(a, cur, val, j);
-        a[G::n_accs * F_NT] = cc + 1;
-        a[(G::n_accs + 1) * F_NT] = min(ff, (long long)(row0 + j * F_NT + tid));
+        long long inc = 1;
+        pack_inc<0>(p, val, j, inc);
+        a[CL * F_NT] = cc + inc;
+        // a thread meets its rows in ascending order (static round-robin tiles): the first row of a private slot is
+        // the row that finds its count word still zero
+        if (cc == 0) a[FL * F_NT] = (long long)(row0 + j * F_NT + tid);
       }
     }
   }
 };
 
-template <uint64_t S0, uint64_t S1, uint64_t S2, uint64_t S3>
+template <uint64_t S0, uint64_t S1, uint64_t S2, uint64_t S3, uint32_t PACK>
 __global__ void __launch_bounds__(F_NT + 32, 1) k_fused_scan_agg_spec(const __grid_constant__ FParams p) {
-  fused_main<FM_DENSE, SpecBody<S0, S1, S2, S3>>(p);
+  fused_main<FM_DENSE, SpecBody<S0, S1, S2, S3, PACK>>(p);
 }
 
 // ---- registered shapes --------------------------------------------------------------------------------
@@ -844,19 +879,23 @@ static FSig make_sig(const FParams& P) {
 }
 
 typedef void (*FusedKernel)(const FParams);
-template <uint64_t S0, uint64_t S1, uint64_t S2, uint64_t S3>
-static bool sig_matches(const FSig& g, FusedKernel* out) {
-  if (g.s[0] != S0 || g.s[1] != S1 || g.s[2] != S2 || g.s[3] != S3) return false;
-  *out = k_fused_scan_agg_spec<S0, S1, S2, S3>;
+// PACK: accumulators kept as bit fields of the count word; usable only when every one of them is in `safe_mask`
+template <uint32_t PACK, uint64_t S0, uint64_t S1, uint64_t S2, uint64_t S3>
+static bool sig_matches(const FSig& g, uint32_t safe_mask, FusedKernel* out, uint32_t* pack) {
+  if (g.s[0] != S0 || g.s[1] != S1 || g.s[2] != S2 || g.s[3] != S3 || (PACK & ~safe_mask) != 0) return false;
+  *out = k_fused_scan_agg_spec<S0, S1, S2, S3, PACK>;
+  *pack = PACK;
   return true;
 }
-// returns the specialised DENSE kernel registered for this shape, or nullptr
-static FusedKernel find_specialised(const FParams& P) {
+// returns the specialised DENSE kernel registered for this shape (and the accumulators it packs), or nullptr
+static FusedKernel find_specialised(const FParams& P, uint32_t safe_mask, uint32_t* pack) {
+  *pack = 0;
   if (P.mode != FM_DENSE) return nullptr;
   const FSig g = make_sig(P);
   FusedKernel k = nullptr;
-  if (sig_matches<SIG_Q1>(g, &k)) return k;
-  if (sig_matches<SIG_Q6>(g, &k)) return k;
+  if (sig_matches<0x11, SIG_Q1>(g, safe_mask, &k, pack)) return k;  // SUM(l_quantity), SUM(l_discount) ride in the count word
+  if (sig_matches<0, SIG_Q1>(g, safe_mask, &k, pack)) return k;
+  if (sig_matches<0, SIG_Q6>(g, safe_mask, &k, pack)) return k;
   if (getenv("QGPU_FUSED_DEBUG"))
     fprintf(stderr, "[qgpu] fused shape without a specialised kernel: %016llx %016llx %016llx %016llx\n", (unsigned long long)g.s[0],
             (unsigned long long)g.s[1], (unsigned long long)g.s[2], (unsigned long long)g.s[3]);
@@ -1356,7 +1395,7 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
   specs.clear();
   fp.key_src.clear();
   acc_of.assign(agg.aggs.size(), -1);
-  std::vector<i128> acc_maxabs;
+  std::vector<i128> acc_maxabs, acc_lo;  // bounds of one row's value per accumulator
   bool dense_ok = true;
   i128 dense_groups = 1;
   int total_bits = 0;
@@ -1504,7 +1543,7 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
       }
       FAcc fa;
       memset(&fa, 0, sizeof(fa));
-      i128 maxabs = 0;
+      i128 maxabs = 0, minval = -1;
       const VClass vc = class_of(s.arg->result_type);
       if (vc == VC_FLT) {
         if (!(s.op == QGPU_AGG_SUM || s.op == QGPU_AGG_AVG) || !s.arg->is_column_ref || s.arg->result_type.id != QGPU_T_FLOAT64)
@@ -1531,6 +1570,7 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
           Analyzer::mul_range(lo, hi, flo, fhi, &lo, &hi);
         }
         maxabs = std::max(lo < 0 ? -lo : lo, hi < 0 ? -hi : hi);
+        minval = lo;
       }
       std::string sig((const char*)&fa, sizeof(fa));
       int found = -1;
@@ -1542,6 +1582,7 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
         P.accs[P.n_accs++] = fa;
         acc_sig.push_back(sig);
         acc_maxabs.push_back(maxabs);
+        acc_lo.push_back(minval);
       }
       acc_of[i] = found;
     }
@@ -1668,9 +1709,62 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
   }
   for (int k = 0; k < P.n_keys; ++k) P.keys[k].pad = 0;
   if (P.mode != FM_HASH || P.carry) fp.radix_ok = false;
+  // accumulators that may ride in the count word: non-negative SUMs whose per-thread partial sums (<= rows_per_thread
+  // rows) provably fit a bit field.  Their private lines disappear: fewer shared-memory read-modify-writes per row and
+  // room for one more TMA stage.
+  uint32_t safe_mask = 0;
+  memset(P.pack_shift, 0, sizeof(P.pack_shift));
+  memset(P.pack_bits, 0, sizeof(P.pack_bits));
+  P.pack_mask = 0;
+  P.pack_cnt_bits = 0;
+  auto bits_of = [](i128 x) { int b = 1; while (b < 63 && ((i128)1 << b) <= x) ++b; return b; };
+  const i128 rows_per_thread = (i128)tiles_per_cta * F_R + 1;
+  int need_bits[F_MAXA];
+  if (P.mode == FM_DENSE && !getenv("QGPU_FUSED_NOPACK")) {
+    for (int k = 0; k < P.n_accs; ++k) {
+      need_bits[k] = 64;
+      if (P.accs[k].kind != FK_SUM || acc_lo[k] < 0) continue;
+      const i128 bound = acc_maxabs[k] * rows_per_thread;
+      if (bound >= ((i128)1 << 48)) continue;
+      need_bits[k] = bits_of(bound);
+      safe_mask |= 1u << k;
+    }
+  }
+  uint32_t pack = 0;
+  fp.spec = getenv("QGPU_FUSED_GENERIC") ? nullptr : find_specialised(P, safe_mask, &pack);
+  if (fp.spec && pack) {
+    int shift = bits_of(rows_per_thread);
+    const int cnt_bits = shift;
+    for (int k = 0; k < P.n_accs; ++k)
+      if ((pack >> k) & 1u) {
+        P.pack_shift[k] = (uint8_t)shift;
+        P.pack_bits[k] = (uint8_t)need_bits[k];
+        shift += need_bits[k];
+      }
+    if (shift <= 62) {
+      P.pack_mask = pack;
+      P.pack_cnt_bits = (uint32_t)cnt_bits;
+    } else {  // the fields do not fit one word: the unpacked instantiation of the same shape
+      memset(P.pack_shift, 0, sizeof(P.pack_shift));
+      memset(P.pack_bits, 0, sizeof(P.pack_bits));
+      fp.spec = find_specialised(P, 0, &pack);
+    }
+  }
+  // private-table lines per slot: the unpacked accumulators, then the count word, then the first row
+  P.priv_lines = 0;
+  for (int k = 0; k < NA2; ++k) {
+    if (k < P.n_accs && ((P.pack_mask >> k) & 1u)) {
+      P.priv_line_of[k] = 0xff;
+    } else {
+      P.priv_k_of[P.priv_lines] = (uint8_t)k;
+      P.priv_line_of[k] = (uint8_t)P.priv_lines++;
+    }
+  }
+  if (P.mode == FM_DENSE) priv_bytes = (size_t)dense_groups * P.priv_lines * F_NT * 8;
   int ctas_per_sm = 1;
   int stages = (int)(((size_t)F_SMEM_MAX - 128 - priv_bytes) / stage_bytes);
   stages = std::min(stages, 4);
+  if (const char* se = getenv("QGPU_FUSED_STAGES")) stages = std::min(stages, std::max(2, atoi(se)));  // experiments
   if (P.mode != FM_DENSE) {
     const int s2 = (int)std::min<size_t>(((size_t)F_SMEM_MAX / 2 - 1024 - 128) / stage_bytes, 4);
     if (s2 >= 2) {
@@ -1685,7 +1779,6 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
   fp.smem_bytes = (size_t)P.priv_off + priv_bytes;
   fp.grid = (int)std::min<int64_t>(P.n_tiles, (int64_t)grid_max * ctas_per_sm);
   fp.total_bits = total_bits;
-  fp.spec = getenv("QGPU_FUSED_GENERIC") ? nullptr : find_specialised(P);
   return true;
 }
 
@@ -1920,6 +2013,7 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
   CUDA_CHECK(cudaFuncSetAttribute(k_fused_scan_agg<FM_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   CUDA_CHECK(cudaFuncSetAttribute(k_fused_scan_agg<FM_HASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   DBufP g_lo, g_hi, flags;
+  std::unique_ptr<Slab> slab;  // DENSE only
   int64_t rec = 0;        // HASH: words per group record (0: accumulators start at word 0)
   bool specialised = false;
   int64_t n_slots = 0, k_stride = 0, g_stride = 0;
@@ -1930,7 +2024,11 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
     g_stride = NA2;
     g_lo = ctx->alloc((size_t)n_slots * NA2 * 8);
     g_hi = ctx->alloc((size_t)n_slots * NA2 * 8);
-    flags = ctx->alloc_zero(16);
+    // every zero-initialised buffer of this operator (flags, group count, the export's per-aggregate arrays) comes out
+    // of ONE allocation and ONE memset: a re-executed Q1 step otherwise queues ~25 cudaMallocAsync + cudaMemsetAsync
+    // pairs around the scan kernel
+    slab.reset(new Slab(ctx, (5 + 2 * specs.size()) * Slab::need(std::max<size_t>((size_t)n_slots * 8, 16)), true));
+    flags = slab->take(16);
     LAUNCH(ctx, k_fused_init, grid_for(ctx, n_slots * NA2, 256), 256, 0, (unsigned long long*)g_lo->ptr,
            (unsigned long long*)g_hi->ptr, n_slots, NA2, 1, 0, init);
     P.g_lo = (unsigned long long*)g_lo->ptr;
@@ -1995,7 +2093,7 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
   DBufP occ, offs, n_groups_dev;
   if (small) {
     n_groups = grouped ? n_slots : 1;
-    n_groups_dev = ctx->alloc_zero(8);
+    n_groups_dev = slab->take(8);
   } else {
     occ = ctx->alloc((size_t)n_slots * 8);
     offs = ctx->alloc((size_t)n_slots * 8);
@@ -2007,9 +2105,10 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
   accs.n_groups = grouped ? n_groups : 1;
   if (small && grouped) accs.n_groups_dev = n_groups_dev;
   const int64_t ng_alloc = std::max<int64_t>(accs.n_groups, 1);
-  DBufP cnt = ctx->alloc_zero((size_t)ng_alloc * 8);
-  DBufP first = ctx->alloc_zero((size_t)ng_alloc * 8);
-  DBufP zero = ctx->alloc_zero((size_t)ng_alloc * 8);
+  auto zalloc = [&](size_t bytes) { return slab ? slab->take(bytes) : ctx->alloc_zero(bytes); };
+  DBufP cnt = zalloc((size_t)ng_alloc * 8);
+  DBufP first = zalloc((size_t)ng_alloc * 8);
+  DBufP zero = zalloc((size_t)ng_alloc * 8);
   FExport ex;
   memset(&ex, 0, sizeof(ex));
   ex.n_aggs = (int)specs.size();
@@ -2028,7 +2127,7 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
       else if (vc == VC_DEC) ak = fk == FK_MIN ? AK_MIN_DEC : AK_MAX_DEC;
       else if (vc == VC_UINT) ak = fk == FK_MIN ? AK_MIN_U64 : AK_MAX_U64;
       else ak = fk == FK_MIN ? AK_MIN_I64 : AK_MAX_I64;
-      DBufP lo = ctx->alloc_zero((size_t)ng_alloc * 8), hi = ctx->alloc_zero((size_t)ng_alloc * 8);
+      DBufP lo = zalloc((size_t)ng_alloc * 8), hi = zalloc((size_t)ng_alloc * 8);
       ex.out_lo[i] = (unsigned long long*)lo->ptr;
       ex.out_hi[i] = (unsigned long long*)hi->ptr;
       accs.lo.push_back(lo);
@@ -2404,7 +2503,12 @@ bool try_fused_join_aggregate(PlanNode& agg, View* out) {
   GroupAccs accs;
   accs.n_groups = n_groups;
   const int64_t ng_alloc = std::max<int64_t>(n_groups, 1);
-  DBufP cnt = ctx->alloc_zero((size_t)ng_alloc * 8), first = ctx->alloc_zero((size_t)ng_alloc * 8), zero = ctx->alloc_zero((size_t)ng_alloc * 8);
+  // one allocation + one memset for the export's zero-initialised arrays (see Slab)
+  std::unique_ptr<Slab> slab;
+  if ((size_t)ng_alloc * 8 * (3 + 2 * specs.size()) <= ((size_t)256 << 20))
+    slab.reset(new Slab(ctx, (3 + 2 * specs.size()) * Slab::need((size_t)ng_alloc * 8), true));
+  auto zalloc = [&](size_t bytes) { return slab ? slab->take(bytes) : ctx->alloc_zero(bytes); };
+  DBufP cnt = zalloc((size_t)ng_alloc * 8), first = zalloc((size_t)ng_alloc * 8), zero = zalloc((size_t)ng_alloc * 8);
   FExport ex;
   memset(&ex, 0, sizeof(ex));
   ex.n_aggs = (int)specs.size();
@@ -2422,7 +2526,7 @@ bool try_fused_join_aggregate(PlanNode& agg, View* out) {
       else if (vc == VC_DEC) ak = fk == FK_MIN ? AK_MIN_DEC : AK_MAX_DEC;
       else if (vc == VC_UINT) ak = fk == FK_MIN ? AK_MIN_U64 : AK_MAX_U64;
       else ak = fk == FK_MIN ? AK_MIN_I64 : AK_MAX_I64;
-      DBufP lo = ctx->alloc_zero((size_t)ng_alloc * 8), hi = ctx->alloc_zero((size_t)ng_alloc * 8);
+      DBufP lo = zalloc((size_t)ng_alloc * 8), hi = zalloc((size_t)ng_alloc * 8);
       ex.out_lo[i] = (unsigned long long*)lo->ptr;
       ex.out_hi[i] = (unsigned long long*)hi->ptr;
       accs.lo.push_back(lo);

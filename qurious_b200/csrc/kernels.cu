@@ -42,7 +42,7 @@ DBuf::DBuf(Ctx* c, size_t n) : ctx(c), bytes(n) {
   CUDA_CHECK(e);
 }
 DBuf::~DBuf() {
-  if (!ptr) return;
+  if (!ptr || parent) return;  // a slab's sub-buffer owns nothing
   const size_t alloc = padded_size(bytes);
   if (alloc >= kBigBlock && ctx->big_free.size() < 48 && ctx->big_free_bytes + alloc <= kBigCacheBytes) {
     ctx->big_free.push_back({alloc, ptr});
@@ -58,6 +58,17 @@ void Ctx::release_big_blocks() {
 }
 
 DBufP Ctx::alloc(size_t bytes) { return std::make_shared<DBuf>(this, bytes); }
+
+Slab::Slab(Ctx* ctx, size_t total_bytes, bool zero) {
+  buf = zero ? ctx->alloc_zero(total_bytes) : ctx->alloc(total_bytes);
+}
+DBufP Slab::take(size_t bytes) {
+  const size_t n = need(bytes);
+  if (off + n > buf->bytes + 256) throw_internal("slab overflow (internal error)");
+  DBufP r = std::make_shared<DBuf>(buf, (char*)buf->ptr + off, bytes);
+  off += n;
+  return r;
+}
 DBufP Ctx::alloc_zero(size_t bytes) {
   DBufP b = alloc(bytes);
   CUDA_CHECK(cudaMemsetAsync(b->ptr, 0, ((bytes + 255) / 256) * 256 + 256, stream));
@@ -549,6 +560,49 @@ __global__ void k_str_copy(const char* __restrict__ src, const int32_t* __restri
   }
 }
 
+__global__ void k_str_maxlen(const int32_t* __restrict__ offs, int64_t n, int* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int m = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m = max(m, offs[i + 1] - offs[i]);
+  for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+// Gather of <= 1024 strings (group keys of a small aggregate result) in ONE single-block launch and without a host
+// round trip: lengths -> block scan -> offsets + bytes.  The data buffer is sized by n x (longest value of the source).
+__global__ void __launch_bounds__(1024) k_str_take_small(const char* __restrict__ src, const int32_t* __restrict__ src_offs,
+                                                         const int64_t* __restrict__ idx, int32_t* __restrict__ out_offs,
+                                                         char* __restrict__ dst, int n) {
+  __shared__ int64_t sm[32];
+  const int i = threadIdx.x;
+  int64_t r = -1;
+  int32_t s0 = 0, len = 0;
+  if (i < n) {
+    r = idx[i];
+    if (r >= 0) {
+      s0 = src_offs[r];
+      len = src_offs[r + 1] - s0;
+    }
+  }
+  int64_t total;
+  const int64_t o = block_exclusive_scan((int64_t)len, &total, sm);
+  if (i < n) {
+    out_offs[i] = (int32_t)o;
+    for (int32_t k = 0; k < len; ++k) dst[o + k] = src[s0 + k];
+  }
+  if (i == 0) out_offs[n] = (int32_t)total;
+}
+
+static int32_t max_str_len_of(Ctx* ctx, const DCol& base) {
+  if (base.max_str_len < 0) {
+    DBufP m = ctx->alloc_zero(8);
+    if (base.length > 0)
+      LAUNCH(ctx, k_str_maxlen, grid_for(ctx, base.length, 256), 256, 0, (const int32_t*)base.offsets->ptr, base.length, (int*)m->ptr);
+    base.max_str_len = ctx->read_scalar((const int*)m->ptr);
+  }
+  return base.max_str_len;
+}
+
 DColP take_column(Ctx* ctx, const DCol& base, const int64_t* idx, int64_t n, bool idx_may_have_null) {
   auto col = std::make_shared<DCol>();
   col->type = base.type;
@@ -603,6 +657,18 @@ DColP take_column(Ctx* ctx, const DCol& base, const int64_t* idx, int64_t n, boo
       LAUNCH(ctx, k_take<ulonglong2>, g, 256, 0, (const ulonglong2*)base.data->ptr, idx, (ulonglong2*)col->data->ptr, n);
       break;
     case PH_STR: {
+      if (n <= 1024) {
+        const int64_t cap = (int64_t)max_str_len_of(ctx, base) * n;
+        if (cap <= (1 << 20)) {
+          col->offsets = ctx->alloc((size_t)(n + 1) * 4);
+          col->data = ctx->alloc(std::max<size_t>((size_t)cap, 4));
+          col->str_bytes = cap;
+          col->str_bytes_is_bound = true;
+          LAUNCH(ctx, k_str_take_small, 1, 1024, 0, (const char*)base.data->ptr, (const int32_t*)base.offsets->ptr, idx,
+                 (int32_t*)col->offsets->ptr, (char*)col->data->ptr, (int)n);
+          break;
+        }
+      }
       DBufP lens = ctx->alloc((size_t)n * 8);
       DBufP offs64 = ctx->alloc((size_t)n * 8);
       LAUNCH(ctx, k_str_lens, g, 256, 0, (const int32_t*)base.offsets->ptr, idx, (int64_t*)lens->ptr, n);

@@ -636,13 +636,22 @@ View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<C
   IdxP order;        // output position -> gid
   IdxP first_idx;    // output position -> first input row of the group
   if (accs.unordered && !key_cols) throw_internal("unordered group output needs explicit key columns");
+  // small results (Q1: 4 groups x 8 aggregates): order vectors, output columns and flags out of ONE allocation + memset
+  const int64_t max_words = (n_max + 31) >> 5;
+  const size_t flag_bytes = 8 * (MAX_AGGS + 3 + MAX_KEYS);
+  std::unique_ptr<Slab> slab;
+  if (n_max <= 65536)
+    slab.reset(new Slab(ctx, 2 * Slab::need(std::max<size_t>((size_t)n_max * 8, 8)) + Slab::need(flag_bytes) +
+                                 aggs.size() * (Slab::need(std::max<size_t>((size_t)n_max * 16, 16)) +
+                                                Slab::need(std::max<size_t>((size_t)max_words * 4, 4))), true));
+  auto salloc = [&](size_t bytes) { return slab ? slab->take(bytes) : ctx->alloc(bytes); };
   if (grouped && !accs.unordered) {
     order = std::make_shared<IdxVec>();
     order->length = n_max;
-    order->buf = ctx->alloc(std::max<size_t>((size_t)n_max * 8, 8));
+    order->buf = salloc(std::max<size_t>((size_t)n_max * 8, 8));
     first_idx = std::make_shared<IdxVec>();
     first_idx->length = n_max;
-    first_idx->buf = ctx->alloc(std::max<size_t>((size_t)n_max * 8, 8));
+    first_idx->buf = salloc(std::max<size_t>((size_t)n_max * 8, 8));
     if (n_max > 0 && n_max <= RANK_MAX) {
       LAUNCH(ctx, k_rank_order, 1, 1024, 0, (const long long*)accs.first_row->ptr, (int)n_max, n_dev, (long long*)order->buf->ptr,
              (long long*)first_idx->buf->ptr);
@@ -669,7 +678,6 @@ View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<C
   all.n_aggs = (int)aggs.size();
   all.order = (grouped && order) ? (const long long*)order->buf->ptr : nullptr;
   std::vector<DColP> cols;
-  const int64_t max_words = (n_max + 31) >> 5;
   for (size_t i = 0; i < aggs.size(); ++i) {
     AggSpec& a = aggs[i];
     const Field& of = out_schema.fields[keys.size() + i];
@@ -682,8 +690,8 @@ View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<C
     auto col = std::make_shared<DCol>();
     col->type = produced;
     col->phys = out_phys_of(produced);
-    col->data = ctx->alloc(std::max<size_t>((size_t)n_max * std::max(phys_width(col->phys), 1), 16));
-    col->validity = ctx->alloc(std::max<size_t>((size_t)max_words * 4, 4));
+    col->data = salloc(std::max<size_t>((size_t)n_max * std::max(phys_width(col->phys), 1), 16));
+    col->validity = salloc(std::max<size_t>((size_t)max_words * 4, 4));
     FinSpec& f = all.f[i];
     f.op = a.op;
     f.kind = accs.kind[i];
@@ -703,7 +711,7 @@ View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<C
   int64_t n_groups = n_max;
   if (n_max > 0 && !aggs.empty()) {
     // flags: [0] EvalErr, [1..n_aggs] NULL counts, [MAX_AGGS + 1] group count (copied from the device-side counter)
-    DBufP flags = ctx->alloc_zero(8 * (MAX_AGGS + 3 + MAX_KEYS));
+    DBufP flags = slab ? slab->take(flag_bytes) : ctx->alloc_zero(flag_bytes);
     dim3 grid((unsigned)grid_for(ctx, n_max, 256), (unsigned)aggs.size());
     LAUNCH(ctx, k_agg_finalize, grid, 256, 0, all, n_max, n_dev, (unsigned long long*)flags->ptr);
     if (n_dev)

@@ -46,6 +46,10 @@ void TableImpl::consolidate() {
       if (p->validity) any_valid_buf = true;
       if (p->phys != PH_NULL) all_null_phys = false;
       out->null_count += p->null_count;
+      if (p->str_bytes_is_bound && p->phys == PH_STR && p->offsets) {  // the concatenation below needs exact sizes
+        p->str_bytes = (int64_t)ctx->read_scalar((const int32_t*)p->offsets->ptr + p->length);
+        p->str_bytes_is_bound = false;
+      }
       out->str_bytes += p->str_bytes;
     }
     if (all_null_phys) {

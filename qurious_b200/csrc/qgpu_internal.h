@@ -90,12 +90,24 @@ struct DBuf {
   Ctx* ctx = nullptr;
   void* ptr = nullptr;
   size_t bytes = 0;
+  std::shared_ptr<DBuf> parent;  // sub-buffer of a slab (Slab::take): the memory belongs to `parent`
   DBuf(Ctx* c, size_t n);
+  DBuf(std::shared_ptr<DBuf> slab, void* p, size_t n) : ctx(slab->ctx), ptr(p), bytes(n), parent(std::move(slab)) {}
   ~DBuf();
   DBuf(const DBuf&) = delete;
   DBuf& operator=(const DBuf&) = delete;
 };
 typedef std::shared_ptr<DBuf> DBufP;
+
+// Many small temporaries of one operator from ONE allocation (and one memset): a re-executed Q1 step issued ~100
+// cudaMallocAsync / cudaFreeAsync / cudaMemsetAsync calls for buffers of a few KB each.
+struct Slab {
+  DBufP buf;
+  size_t off = 0;
+  Slab(Ctx* ctx, size_t total_bytes, bool zero);
+  static size_t need(size_t bytes) { return ((bytes + 255) / 256) * 256 + 256; }  // what take(bytes) consumes
+  DBufP take(size_t bytes);
+};
 
 // physical storage class of a device column
 enum Phys : uint8_t {
@@ -128,6 +140,8 @@ struct DCol {
   DBufP offsets;   // utf8: (length+1) int32
   DBufP validity;  // bitmap (uint32 words), null when null_count == 0
   int64_t str_bytes = 0;
+  bool str_bytes_is_bound = false;  // str_bytes >= offsets[length] (small gathers size the data buffer without a round trip)
+  mutable int32_t max_str_len = -1;  // longest value of a Utf8 column, computed on first use (take_column)
   // lazily computed value range of the non-null values (ints / dates / decimals)
   bool has_stats = false;
   i128 vmin = 0, vmax = 0;

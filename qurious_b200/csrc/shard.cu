@@ -420,6 +420,7 @@ View shard_execute_merged(PlanNode& root, const void* gathered, int32_t n_states
       c->data = ctx->alloc_zero((size_t)m_max * 16 + 16);
       c->offsets = ctx->alloc_zero((size_t)(m_max + 1) * 4);
       c->str_bytes = m_max * 16;
+      c->str_bytes_is_bound = true;
     } else {
       c->data = ctx->alloc_zero((size_t)m_max * std::max(phys_width(c->phys), 1) + 16);
     }
