@@ -404,11 +404,27 @@ struct GenericBody {
             sl[j] = hh[j] & p.jt_mask;
             cur[j] = ((pass >> j) & 1) ? __ldg(&p.jt_slots[sl[j]]) : 0ull;
           }
+          // the build keys of the first candidates are verified together as well (F_R loads in flight): a row whose first
+          // slot settles it -- empty, or tag + key match -- never enters the dependent chain below (load factor <= 0.5)
+          int64_t bk0[F_R];
+#pragma unroll
+          for (int j = 0; j < F_R; ++j) {
+            const bool cand = cur[j] != 0 && (uint32_t)(cur[j] >> 32) == (uint32_t)(hh[j] >> 32);
+            const uint64_t row = (cur[j] & 0xffffffffull) - 1;
+            bk0[j] = !cand ? 0 : (p.bkey_width == 8 ? __ldg((const long long*)p.bkey + row) : (int64_t)__ldg((const int*)p.bkey + row));
+            if (!cand && cur[j] != 0) bk0[j] = ~(int64_t)code[j];  // tag mismatch: cannot equal the probe key
+          }
 #pragma unroll
           for (int j = 0; j < F_R; ++j) {
             const uint32_t tag = (uint32_t)(hh[j] >> 32);
             unsigned long long c = cur[j];
-            uint64_t s2 = sl[j];
+            if (c == 0) continue;
+            if (bk0[j] == (int64_t)code[j]) {
+              slot[j] = (c & 0xffffffffull) - 1;
+              continue;
+            }
+            uint64_t s2 = (sl[j] + 1) & p.jt_mask;
+            c = __ldg(&p.jt_slots[s2]);
             while (c != 0) {
               if ((uint32_t)(c >> 32) == tag) {
                 const uint64_t row = (c & 0xffffffffull) - 1;
@@ -648,10 +664,10 @@ __device__ __forceinline__ void fused_main(const FParams& p) {
 }
 
 
-// DENSE keeps one CTA per SM (its private tables fill shared memory); the table-probing modes run two CTAs per
-// SM (16 warps) to hide the latency of their random HBM/L2 accesses
+// DENSE keeps one CTA per SM (its private tables fill shared memory); the table-probing modes run two (HASH) or
+// three (join probes) CTAs per SM to hide the latency of their random HBM/L2 accesses
 template <int MODE>
-__global__ void __launch_bounds__(F_NT + 32, MODE == FM_DENSE ? 1 : 2) k_fused_scan_agg(const __grid_constant__ FParams p) {
+__global__ void __launch_bounds__(F_NT + 32, MODE == FM_DENSE ? 1 : (MODE == FM_HASH ? 2 : 3)) k_fused_scan_agg(const __grid_constant__ FParams p) {
   fused_main<MODE, GenericBody<MODE>>(p);
 }
 
@@ -1770,6 +1786,24 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
     if (s2 >= 2) {
       stages = s2;
       ctas_per_sm = 2;
+    }
+    // join probes: a third resident CTA (27 warps/SM; the kernels are held to 72 registers) hides more of the probes'
+    // L2 latency than deeper staging does -- Q3 SF10: PROBE 0.387 -> 0.355 ms, EMIT 0.196 -> 0.161 ms
+    const int want = getenv("QGPU_FUSED_CTAS") ? atoi(getenv("QGPU_FUSED_CTAS")) : (probe ? 3 : 2);
+    if (want == 3) {
+      const int sw = (int)std::min<size_t>(((size_t)F_SMEM_MAX / 3 - 1024 - 128) / stage_bytes, 4);
+      int fit = 0;
+      if (sw >= 2) {
+        const size_t smem3 = 128 + (size_t)sw * stage_bytes;
+        const void* fn = P.mode == FM_EMIT ? (const void*)k_fused_scan_agg<FM_EMIT>
+                                           : (P.mode == FM_PROBE ? (const void*)k_fused_scan_agg<FM_PROBE> : (const void*)k_fused_scan_agg<FM_HASH>);
+        CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM_MAX));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, fn, F_NT + 32, smem3));
+      }
+      if (fit >= 3) {
+        stages = sw;
+        ctas_per_sm = 3;
+      }
     }
   }
   if (stages < 2) return false;
