@@ -392,6 +392,7 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the ONE JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         _dist = dist
     from qurious_b200 import _lib, tpch

@@ -390,8 +390,15 @@ View shard_execute_merged(PlanNode& root, const void* gathered, int32_t n_states
   GroupAccs accs;
   accs.n_groups = grouped ? m_max : 1;
   accs.kind = kinds;
+  // every zero-initialised buffer of the merge (3 per aggregate, first rows, flags, 3 per key) out of ONE allocation and
+  // ONE memset: ~35 cudaMallocAsync + cudaMemsetAsync pairs per merged step otherwise sit between the all-gather and
+  // the merge kernel
+  Slab slab(ctx, (size_t)(3 * na + 1) * Slab::need((size_t)m_max * 8) + Slab::need(8 * (3 + SH_MAX_KEYS)) +
+                     (size_t)nk * (Slab::need((size_t)((m_max + 31) / 32) * 4 + 4) + Slab::need((size_t)m_max * 16 + 16) +
+                                   Slab::need((size_t)(m_max + 1) * 4)),
+            true);
   for (int i = 0; i < na; ++i) {
-    DBufP lo = ctx->alloc_zero((size_t)m_max * 8), hi = ctx->alloc_zero((size_t)m_max * 8), cnt = ctx->alloc_zero((size_t)m_max * 8);
+    DBufP lo = slab.take((size_t)m_max * 8), hi = slab.take((size_t)m_max * 8), cnt = slab.take((size_t)m_max * 8);
     accs.lo.push_back(lo);
     accs.hi.push_back(hi);
     accs.cnt.push_back(cnt);
@@ -400,11 +407,11 @@ View shard_execute_merged(PlanNode& root, const void* gathered, int32_t n_states
     a.hi[i] = (unsigned long long*)hi->ptr;
     a.cnt[i] = (unsigned long long*)cnt->ptr;
   }
-  accs.first_row = ctx->alloc_zero((size_t)m_max * 8);
+  accs.first_row = slab.take((size_t)m_max * 8);
   a.first_row = (long long*)accs.first_row->ptr;
   // [0] n_groups, [1 .. 1+nk) key NULL counts, [1+nk] error code: the last nk+1 words travel to the host together
   // with finish_aggregate's own flags (one synchronisation for the whole merge)
-  DBufP misc = ctx->alloc_zero(8 * (3 + SH_MAX_KEYS));
+  DBufP misc = slab.take(8 * (3 + SH_MAX_KEYS));
   a.n_groups_out = (long long*)misc->ptr;
   a.key_nulls = (unsigned long long*)((char*)misc->ptr + 8);
   a.err = (int*)((char*)misc->ptr + 8 + 8 * nk);
@@ -415,14 +422,15 @@ View shard_execute_merged(PlanNode& root, const void* gathered, int32_t n_states
     c->type = keys[k]->result_type;
     c->phys = key_phys(c->type);
     c->length = m_max;
-    c->validity = ctx->alloc_zero((size_t)((m_max + 31) / 32) * 4 + 4);
+    c->validity = slab.take((size_t)((m_max + 31) / 32) * 4 + 4);
     if (c->phys == PH_STR) {
-      c->data = ctx->alloc_zero((size_t)m_max * 16 + 16);
-      c->offsets = ctx->alloc_zero((size_t)(m_max + 1) * 4);
+      c->data = slab.take((size_t)m_max * 16 + 16);
+      c->offsets = slab.take((size_t)(m_max + 1) * 4);
       c->str_bytes = m_max * 16;
       c->str_bytes_is_bound = true;
+      c->max_str_len = 16;  // state records carry Utf8 keys of <= 16 bytes: no k_str_maxlen pass + round trip per merge
     } else {
-      c->data = ctx->alloc_zero((size_t)m_max * std::max(phys_width(c->phys), 1) + 16);
+      c->data = slab.take((size_t)m_max * std::max(phys_width(c->phys), 1) + 16);
     }
     c->null_count = 1;  // replaced by the real count inside finish_aggregate
     a.key[k].data = c->data->ptr;
