@@ -1992,6 +1992,7 @@ static bool run_radix(PlanNode& agg, const View& v, FusedPlan& fp, View* out) {
   if (!force && P.n_rows < ((int64_t)1 << 24)) return false;
   RParams R = fp.R;
   R.world = 1;
+  R.nopf = getenv("QGPU_RADIX_NOPF") ? atoi(getenv("QGPU_RADIX_NOPF")) : 0;
   // ---- pass 0: level-1 histogram + HyperLogLog sketch ---------------------------------------------------------
   DBufP st = radix_state_block(ctx, R);
   const int grid1 = (int)std::min<int64_t>(P.n_tiles, (int64_t)ctx->sm_count * 8);
@@ -2200,6 +2201,7 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
   }
   agg.strategy = std::string("fused_scan_agg[") + (P.mode == FM_DENSE ? "dense-private" : "hbm-hash") +
                  (specialised ? "/shape-specialised, " : ", ") +
+                 (P.pack_mask ? std::to_string(__builtin_popcount(P.pack_mask)) + " accs packed into the count word, " : "") +
                  std::to_string(P.n_cols) + " cols, " + std::to_string(P.n_pred) + " range preds, " + std::to_string(P.n_accs) +
                  " accs, " + std::to_string(P.stages) + " TMA stages]";
   ctx->trace("scan-agg: export");

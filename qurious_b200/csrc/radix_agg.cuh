@@ -72,7 +72,7 @@ struct RParams {
   int* overflow;
   // multi-GPU exchange (world > 1): level-1 bucket b belongs to rank b % world; the level-1 scatter writes its tuples
   // straight into the owner's tuple arrays over NVLink (peer_a[rank][component]; the local rank's entry is tup_a)
-  int32_t world, pad1;
+  int32_t world, nopf;  // nopf: experiment bits -- 1/2/4 = no L2 prefetch in scatter<1> / scatter<2> / k_radix_agg, 8 = two-pass probing in k_radix_agg
   unsigned long long* peer_a[8][R_MAXCOMP];
 };
 
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(R_SNT, 2) k_radix_scatter(const __grid_constan
       rows = (int)min((int64_t)R_T, p.n_rows - base);
       // pull this CTA's next tile towards L2 (base pointers are 256 B aligned, tiles are 4096 rows)
       const int64_t nbase = base + (int64_t)gridDim.x * R_T;
-      if (nbase < p.n_rows && tid < p.n_cols) {
+      if (nbase < p.n_rows && tid < p.n_cols && !(r.nopf & 1)) {
         const int64_t nrows = min((int64_t)R_T, p.n_rows - nbase);
         const uint32_t bytes = (uint32_t)((nrows * p.cols[tid].width) & ~15ll);
         if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gcol(p, tid, nbase)), "r"(bytes) : "memory");
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(R_SNT, 2) k_radix_scatter(const __grid_constan
       }
       base = (int64_t)b_off0 + (int64_t)(t - b_tile0) * R_T;
       rows = (int)min((int64_t)R_T, (int64_t)b_off1 - base);
-      if (t + gridDim.x < b_tile1 && tid < r.n_comp) {  // this CTA's next tile, when it lies in the same bucket
+      if (t + gridDim.x < b_tile1 && tid < r.n_comp && !(r.nopf & 2)) {  // this CTA's next tile, when it lies in the same bucket
         const int64_t nbase = base + (int64_t)gridDim.x * R_T;
         const uintptr_t a0 = ((uintptr_t)(r.tup_a[tid] + nbase) + 15) & ~(uintptr_t)15;
         const uintptr_t a1 = (uintptr_t)(r.tup_a[tid] + min((int64_t)b_off1, nbase + R_T)) & ~(uintptr_t)15;
@@ -480,6 +480,7 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
   __shared__ unsigned long long warp_tot[R_AGG_NT / 32];
   __shared__ unsigned long long out_base, bucket_total;
   __shared__ int bucket_overflow;
+  __shared__ unsigned int n_defer;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_buckets = R_P1 << r.b2;
   const int per = (C1 + R_AGG_NT - 1) / R_AGG_NT;
@@ -495,7 +496,7 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
     }
     const int n = (int)n64;
     // the next bucket of this CTA: pull its tuples towards L2 while this one is processed
-    if (b + (int)gridDim.x < n_buckets && tid < r.n_comp) {
+    if (b + (int)gridDim.x < n_buckets && tid < r.n_comp && !(r.nopf & 4)) {
       const int64_t nlo = (int64_t)r.off2[b + gridDim.x];
       const int64_t nn = min((int64_t)r.off2[b + gridDim.x + 1] - nlo, (int64_t)RC);
       const uintptr_t a0 = ((uintptr_t)(r.tup_b[tid] + nlo) + 15) & ~(uintptr_t)15;   // 16 B aligned address and size
@@ -509,6 +510,7 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
     if (tid == 0) bucket_overflow = 0;
     __syncthreads();
     // ---- A: slot + rank of every row (R_U loads in flight per thread: the bucket is read at HBM latency) ------------
+    if (!(r.nopf & 8) || NV < 2) {  // the deferred queue of the two-pass version needs 1.5 staging columns
     for (int i0 = 0; i0 < n; i0 += R_U * R_AGG_NT) {
       unsigned long long c8[R_U];
 #pragma unroll
@@ -547,6 +549,75 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
         }
         pk[i] = (unsigned)slot | (atomicAdd(&cnt[slot], 1u) << 13);
       }
+    }
+    } else {
+    // ---- A (two passes): pass 1 gives every row ONE probe -- convergent, no loop; ~3 of 4 rows settle there (their
+    //      group's key already sits in the home slot, or the slot is free).  The others are queued (code + row, in the
+    //      still unused staging area) and pass 2 walks their probe chains with dense lanes: the warp-wide while loop of
+    //      the one-pass version ran ~3.5 iterations per row for an average chain of 1.3.
+    unsigned long long* dcode = stage;                       // [RC] codes of the deferred rows
+    unsigned int* drow = (unsigned int*)(stage + RC);        // [RC] their row numbers
+    if (tid == 0) n_defer = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += R_U * R_AGG_NT) {
+      unsigned long long c8[R_U];
+#pragma unroll
+      for (int u = 0; u < R_U; ++u) {
+        const int i = i0 + u * R_AGG_NT + tid;
+        c8[u] = i < n ? __ldcs(&r.tup_b[0][lo + i]) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < R_U; ++u) {
+        const int i = i0 + u * R_AGG_NT + tid;
+        const unsigned long long code = c8[u];
+        int slot = cap;
+        bool done = true, live = i < n;
+        if (live && code != F_EMPTY) {
+          slot = (int)(fmix64(code) & (uint64_t)(cap - 1));
+          unsigned long long cur = *(volatile unsigned long long*)&keys[slot];
+          if (cur == F_EMPTY) cur = atomicCAS(&keys[slot], F_EMPTY, code);
+          done = cur == code || cur == F_EMPTY;
+        }
+        if (live && done) pk[i] = (unsigned)slot | (atomicAdd(&cnt[slot], 1u) << 13);
+        const unsigned dm = __ballot_sync(0xffffffffu, live && !done);
+        if (dm) {
+          unsigned at = 0;
+          if (lane == 0) at = atomicAdd(&n_defer, (unsigned)__popc(dm));
+          at = __shfl_sync(0xffffffffu, at, 0) + __popc(dm & ((1u << lane) - 1u));
+          if (live && !done) {
+            dcode[at] = code;
+            drow[at] = (unsigned)i;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const int nd = (int)n_defer;
+    for (int j = tid; j < nd; j += R_AGG_NT) {
+      const unsigned long long code = dcode[j];
+      const uint64_t h = fmix64(code);
+      const int step = (int)((h >> 13) & (uint64_t)(cap - 1)) | 1;
+      int slot = ((int)(h & (uint64_t)(cap - 1)) + step) & (cap - 1);  // the home slot holds another key
+      int probes = 1;
+      while (true) {
+        unsigned long long cur = *(volatile unsigned long long*)&keys[slot];
+        if (cur == code) break;
+        if (cur == F_EMPTY) {
+          cur = atomicCAS(&keys[slot], F_EMPTY, code);
+          if (cur == F_EMPTY || cur == code) break;
+        }
+        slot = (slot + step) & (cap - 1);
+        if (++probes >= cap) {
+          slot = -1;
+          break;
+        }
+      }
+      if (slot < 0) {
+        bucket_overflow = 1;
+        continue;
+      }
+      pk[drow[j]] = (unsigned)slot | (atomicAdd(&cnt[slot], 1u) << 13);
+    }
     }
     __syncthreads();
     if (bucket_overflow) {

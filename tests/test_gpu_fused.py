@@ -212,3 +212,58 @@ def test_join_aggregate_falls_back_on_duplicate_build_keys(gpu_ctx):
                                             MinAggregateExpr(Column("v", 3), pa.int64())])
         s = run_both(plan, gpu_ctx, ordered=True)
         assert ("fused_join_probe_agg" in s) == (not dup), s
+
+
+# ---- packed accumulators (FParams::pack_mask): SUM(l_quantity) and SUM(l_discount) of the Q1 shape ride in the row-count
+# ---- word of the private tables only when the column statistics prove it safe; every variant must equal the oracle
+def _q1_db(mutate):
+    t = tpch.gen_lineitem(0.02, columns=tpch.Q1_COLUMNS)
+    mutate(t.cols)
+    li = MemoryTable.try_new(t.schema, tpch.to_arrow(t, 1024))
+    return tpch.Database(0.02, None, None, li)
+
+
+def test_q1_packs_small_sums_into_the_count_word(gpu_ctx):
+    s = run_both(tpch.q1_plan(_q1_db(lambda c: None)), gpu_ctx)
+    assert "2 accs packed into the count word" in s, s
+
+
+def test_q1_negative_quantity_is_not_packed(gpu_ctx):
+    def neg(c):
+        c["l_quantity"][::97] = -c["l_quantity"][::97]
+    s = run_both(tpch.q1_plan(_q1_db(neg)), gpu_ctx)
+    assert "shape-specialised" in s and "packed" not in s, s
+
+
+def test_q1_wide_discount_is_not_packed(gpu_ctx):
+    def wide(c):
+        c["l_extendedprice"][:] = 1                   # keeps price * (100 - disc) * (100 + tax) inside int64
+        c["l_tax"][:] = 0
+        c["l_discount"][::5] = 10 ** 14 + 7          # a per-thread partial sum no longer fits a 48-bit field
+    s = run_both(tpch.q1_plan(_q1_db(wide)), gpu_ctx)
+    assert "fused_scan_agg[dense-private/shape-specialised" in s and "packed" not in s, s
+
+
+def test_q1_packed_fields_at_their_bounds(gpu_ctx):
+    def big(c):
+        c["l_quantity"][:] = 99_999_999_00          # every row at the column maximum: the bound the host sizes the field by
+        c["l_discount"][:] = 10
+    s = run_both(tpch.q1_plan(_q1_db(big)), gpu_ctx)
+    assert "fused_scan_agg[dense-private" in s, s
+
+
+def test_small_string_keys_one_launch_gather(gpu_ctx):
+    """<= 1024 result groups with Utf8 keys take the single-launch gather (k_str_take_small), more take the
+    lens -> scan -> copy path; both must give the reference's strings (including empty ones)."""
+    rng = np.random.default_rng(11)
+    for n_keys in (3, 1024, 1500):
+        n = 6000
+        words = ["", "a", "BUILDING", "x" * 37] + [f"k{i:05d}" for i in range(n_keys - 4)] if n_keys > 4 else ["", "a", "x" * 37]
+        ks = pa.array([words[i] for i in rng.integers(0, len(words), n)], pa.string())
+        vs = pa.array(rng.integers(-1000, 1000, n), pa.int64())
+        schema = pa.schema([("s", pa.string()), ("v", pa.int64())])
+        t = MemoryTable.try_new(schema, [pa.record_batch([ks, vs], schema=schema)])
+        out = pa.schema([("s", pa.string()), ("sum_v", pa.int64()), ("n", pa.int64())])
+        plan = HashAggregate(out, Scan(schema, t, None, None), [Column("s", 0)],
+                             [SumAggregateExpr(Column("v", 1), pa.int64()), CountAggregateExpr(Column("v", 1))])
+        run_both(plan, gpu_ctx)
