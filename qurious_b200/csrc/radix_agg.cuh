@@ -72,7 +72,7 @@ struct RParams {
   int* overflow;
   // multi-GPU exchange (world > 1): level-1 bucket b belongs to rank b % world; the level-1 scatter writes its tuples
   // straight into the owner's tuple arrays over NVLink (peer_a[rank][component]; the local rank's entry is tup_a)
-  int32_t world, nopf;  // nopf: experiment bits -- 1/2/4 = no L2 prefetch in scatter<1> / scatter<2> / k_radix_agg, 8 = two-pass probing in k_radix_agg
+  int32_t world, nopf;  // nopf: experiment bits -- 1/2/4 = no L2 prefetch in scatter<1> / scatter<2> / k_radix_agg, 8 = one-pass probing in k_radix_agg
   unsigned long long* peer_a[8][R_MAXCOMP];
 };
 
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
     if (tid == 0) bucket_overflow = 0;
     __syncthreads();
     // ---- A: slot + rank of every row (R_U loads in flight per thread: the bucket is read at HBM latency) ------------
-    if (!(r.nopf & 8) || NV < 2) {  // the deferred queue of the two-pass version needs 1.5 staging columns
+    if ((r.nopf & 8) || NV < 2) {  // one-pass version (the deferred queue of the two-pass one needs 1.5 staging columns)
     for (int i0 = 0; i0 < n; i0 += R_U * R_AGG_NT) {
       unsigned long long c8[R_U];
 #pragma unroll
