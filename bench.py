@@ -348,7 +348,9 @@ def run_query_device(ctx, step, steps, warmup, sampler, torch, stream):
     """K timed steps, table resident in HBM; returns (ms_total, per-kernel profile, launches per step)."""
     for _ in range(warmup):
         step()
-    ctx.profile(True)
+    # event pairs only around launches of >= 64 blocks (the scan / probe / radix kernels): bracketing every single-block
+    # helper as well costs the Q1 SF10 step 7 % (0.463 vs 0.431 ms, same box; QGPU_BENCH_PROFILE_ALL=1 restores that)
+    ctx.profile(True, 0 if os.environ.get("QGPU_BENCH_PROFILE_ALL") else 64)
     ctx.profile_report()
     l0 = ctx.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -457,7 +459,7 @@ def run_b200(args):
     prof_sorted = sorted(prof, key=lambda r: -r[2])
     top = prof_sorted[0] if prof_sorted else ("none", 0, 0.0, 0.0)
     top_ms = top[2] / max(top[1], 1)
-    top_share = top[2] / max(sum(r[2] for r in prof), 1e-9)
+    top_share = top[2] / max(ms, 1e-9)                 # of the timed region's device time
     top_bytes = per_table.get(driving, alg_bytes)   # the dominant kernel streams the driving table
     if q == "q3" and "FM_EMIT" in top[0]:
         top_bytes = per_table.get("orders", top_bytes)     # J1's probe scan streams orders, not lineitem

@@ -158,7 +158,8 @@ int qgpu_release_cached_memory(qgpu_ctx* ctx);
  * around calls (bench.py times steps with events on THIS stream). */
 void* qgpu_ctx_stream(const qgpu_ctx* ctx);
 /* Per-kernel device timing: while enabled every kernel launch is bracketed by CUDA events on the
- * compute stream.  qgpu_profile_report synchronises, writes "kernel\tlaunches\ttotal_ms\tmax_ms\n"
+ * compute stream (on == 1), or only the launches of at least `on` thread blocks (on >= 2: the large-grid kernels a
+ * roofline is quoted for, without perturbing a sub-millisecond step).  qgpu_profile_report synchronises, writes "kernel\tlaunches\ttotal_ms\tmax_ms\n"
  * lines for the launches since the last report into buf (NUL terminated, truncated to cap) and
  * returns the number of bytes the full report needs. */
 int qgpu_profile_enable(qgpu_ctx* ctx, int on);

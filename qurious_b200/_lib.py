@@ -171,8 +171,9 @@ class Context:
         """cudaStream_t of the context's compute stream (for caller-side CUDA events)."""
         return int(self.lib.qgpu_ctx_stream(self.handle) or 0)
 
-    def profile(self, on: bool):
-        self.check(self.lib.qgpu_profile_enable(self.handle, 1 if on else 0))
+    def profile(self, on, min_blocks: int = 0):
+        """on: bracket kernel launches with CUDA events; min_blocks >= 2: only launches of at least that many blocks."""
+        self.check(self.lib.qgpu_profile_enable(self.handle, (max(int(min_blocks), 1) if on else 0)))
 
     def profile_report(self):
         """[(kernel, launches, total_ms, max_ms)] since the last report; device time from CUDA events."""

@@ -2074,7 +2074,7 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
     if (spec) {
       specialised = true;
       CUDA_CHECK(cudaFuncSetAttribute(spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-      ::qgpu::KernelScope ks(ctx, "k_fused_scan_agg_spec");
+      ::qgpu::KernelScope ks(ctx, "k_fused_scan_agg_spec", grid);
       spec<<<grid, F_NT + 32, smem_bytes, ctx->stream>>>(P);
       CUDA_CHECK(cudaGetLastError());
     } else {

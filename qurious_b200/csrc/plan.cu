@@ -403,6 +403,7 @@ int qgpu_profile_enable(qgpu_ctx* ctx, int on) {
   if (!ctx) return QGPU_ERR_INTERNAL;
   return guard(&ctx->c, [&] {
     ctx->c.profiling = on != 0;
+    ctx->c.prof_min_blocks = on >= 2 ? on : 0;
     if (!on) ctx->c.prof_report();
   });
 }

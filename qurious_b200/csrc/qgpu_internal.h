@@ -207,6 +207,7 @@ struct Ctx {
 
   // per-kernel CUDA-event profiling (off by default; qgpu_profile_enable)
   bool profiling = false;
+  long long prof_min_blocks = 0;  // qgpu_profile_enable(ctx, n >= 2): only launches of >= n blocks are bracketed
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   std::vector<const char*> prof_names;
   int prof_used = 0;
