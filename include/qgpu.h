@@ -218,6 +218,11 @@ int qgpu_plan_aggregate(qgpu_ctx* ctx, const struct ArrowSchema* schema, qgpu_pl
 int qgpu_plan_hash_join(qgpu_ctx* ctx, qgpu_plan* left, qgpu_plan* right, int32_t join_type,
                         const qgpu_expr* const* left_on, const qgpu_expr* const* right_on, int32_t n_on,
                         const qgpu_join_filter* filter, qgpu_plan** out);
+/* NestedLoopJoinExec::try_new(left, right, join_type, filter) (join/nest_loop_join.rs:52-76): the planner's choice
+ * for joins without equi-conditions (planner/mod.rs:316-320).  Matched pairs come out ordered by (right row, left
+ * row); Left / Right / Full append the unmatched left rows, then the unmatched right rows. */
+int qgpu_plan_nested_loop_join(qgpu_ctx* ctx, qgpu_plan* left, qgpu_plan* right, int32_t join_type,
+                               const qgpu_join_filter* filter, qgpu_plan** out);
 /* PhysicalPlan::schema (physical/plan/mod.rs:26) */
 int qgpu_plan_schema(const qgpu_plan* p, struct ArrowSchema* out);
 /* PhysicalPlan::execute (physical/plan/mod.rs:27): runs the whole subtree on the GPU (intermediate

@@ -12,6 +12,7 @@ What it restates (reference file:line, all relative to /root/reference/qurious/s
   * HashAggregate               physical/plan/aggregate/hash.rs:45-107,138-170
   * accumulators                physical/expr/aggregate/{sum,avg,count,min,max,mod}.rs
   * HashJoinExec + helpers      physical/plan/join/hash_join.rs:40-385, physical/plan/join/mod.rs:26-207
+  * NestedLoopJoinExec          physical/plan/join/nest_loop_join.rs:79-300
   * build_batch_from_indices    utils/batch.rs:18-61
 
 The arithmetic itself lives in the un-vendored third-party crate `arrow = "53.2.0"`
@@ -942,6 +943,8 @@ def execute(plan, compat: bool = False, null_key_compat: bool = False) -> List[p
         return _hash_aggregate(plan, **kw)
     if k == "HashJoinExec":
         return _hash_join(plan, **kw)
+    if k == "NestedLoopJoinExec":
+        return _nested_loop_join(plan, **kw)
     if k == "Sort":  # sort.rs:48-82
         merged = concat_batches(plan.schema, execute(plan.input, **kw))
         n = merged.num_rows
@@ -1185,6 +1188,72 @@ def _hash_join(plan, compat, null_key_compat) -> List[pa.RecordBatch]:
         out.append(build_batch_from_indices(schema, column_indices, build, empty_right, idx, None,
                                             np.zeros(len(idx), dtype=np.int64), np.zeros(len(idx), dtype=bool)))
     return out
+
+
+def _nested_loop_join(plan, compat, null_key_compat) -> List[pa.RecordBatch]:
+    """NestedLoopJoinExec::execute (physical/plan/join/nest_loop_join.rs:79-228).
+
+    build_join_indices (:237-271): for every right row, all left rows, the JoinFilter evaluated on the intermediate
+    batch of that right row (join_filter_indices :273-300; NULL drops the pair like false) -- matched pairs ordered by
+    (right row, left row).  Left / Right / Full return a second batch: unmatched left rows (right side NULL), then
+    unmatched right rows (left side NULL) (:168-226).  LeftSemi / LeftAnti return each kept left row once (:130-166).
+    An empty right side is special-cased (:86-119)."""
+    LEFT, RIGHT, INNER, FULL, SEMI, ANTI = 0, 1, 2, 3, 4, 5
+    jt = int(plan.join_type)
+    kw = dict(compat=compat, null_key_compat=null_key_compat)
+    lb = concat_batches(plan.left.schema, execute(plan.left, **kw))
+    rb = concat_batches(plan.right.schema, execute(plan.right, **kw))
+    nl, nr = lb.num_rows, rb.num_rows
+    schema, column_indices = plan.schema, plan.column_indices
+
+    def batch(li, lv, ri, rv):
+        return build_batch_from_indices(schema, column_indices, lb, rb, np.asarray(li, dtype=np.int64), lv,
+                                        np.asarray(ri, dtype=np.int64), rv)
+
+    def zeros(n):
+        return np.zeros(n, dtype=np.int64)
+
+    def nulls(n):
+        return np.zeros(n, dtype=bool)
+
+    if nr == 0:
+        if jt in (INNER, RIGHT):
+            return []
+        if jt in (LEFT, FULL, ANTI):
+            return [batch(np.arange(nl), None, zeros(nl), nulls(nl))]
+        return [batch(zeros(0), None, zeros(0), nulls(0))]
+    li_parts, ri_parts = [], []
+    for r in range(nr):
+        li = np.arange(nl, dtype=np.int64)
+        ri = np.full(nl, r, dtype=np.int64)
+        if plan.filter is not None and nl > 0:
+            f = plan.filter
+            inter = build_batch_from_indices(f.schema, f.column_indices, lb, rb, li, None, ri, None)
+            m = evaluate(f.expr, inter)
+            keep = m.vals & m.valid
+            li, ri = li[keep], ri[keep]
+        li_parts.append(li)
+        ri_parts.append(ri)
+    li = np.concatenate(li_parts) if li_parts else zeros(0)
+    ri = np.concatenate(ri_parts) if ri_parts else zeros(0)
+    vis_l = np.zeros(nl, dtype=bool)
+    vis_r = np.zeros(nr, dtype=bool)
+    vis_l[li] = True
+    vis_r[ri] = True
+    if jt in (SEMI, ANTI):
+        idx = np.nonzero(vis_l if jt == SEMI else ~vis_l)[0].astype(np.int64)
+        return [batch(idx, None, zeros(len(idx)), nulls(len(idx)))]
+    matched = batch(li, None, ri, None)
+    if jt == INNER:
+        return [matched]
+    l_, lv, r_, rv = [], [], [], []
+    if jt in (LEFT, FULL):
+        ul = np.nonzero(~vis_l)[0]
+        l_.extend(ul.tolist()); lv.extend([True] * len(ul)); r_.extend([0] * len(ul)); rv.extend([False] * len(ul))
+    if jt in (RIGHT, FULL):
+        ur = np.nonzero(~vis_r)[0]
+        l_.extend([0] * len(ur)); lv.extend([False] * len(ur)); r_.extend(ur.tolist()); rv.extend([True] * len(ur))
+    return [matched, batch(l_, np.array(lv, dtype=bool), r_, np.array(rv, dtype=bool))]
 
 
 # ---------------------------------------------------------------------------------------------

@@ -65,6 +65,10 @@ View run_hash_join(Ctx* ctx, const View& build, const View& probe, int join_type
                    std::vector<std::shared_ptr<Compiled>>& left_on, std::vector<std::shared_ptr<Compiled>>& right_on,
                    JoinFilterSpec* filter, const Schema& out_schema);
 
+// NestedLoopJoinExec::execute (nest_loop_join.rs:79-228).  SURVEY 8f #3.
+View run_nested_loop_join(Ctx* ctx, const View& left, const View& right, int join_type, JoinFilterSpec* filter,
+                          const Schema& out_schema);
+
 Schema build_join_schema(const Schema& left, const Schema& right, int join_type);
 
 // validation helpers shared with the fused paths

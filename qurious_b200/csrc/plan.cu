@@ -263,6 +263,19 @@ View PlanNode::execute() {
       strategy = "generic-hash-join(late-materialisation)";
       return run_hash_join(ctx, l, r, join_type, lo, ro, has_join_filter ? &fs : nullptr, schema);
     }
+    case PK_NL_JOIN: {
+      View l = children[0]->execute();
+      View r = children[1]->execute();
+      JoinFilterSpec fs;
+      if (has_join_filter) {
+        fs.schema = join_filter_schema;
+        fs.column_index = join_filter_index;
+        fs.column_side = join_filter_side;
+        fs.expr = compile_expr(*join_filter_expr, join_filter_schema);
+      }
+      strategy = "nested-loop-join(cross pairs + filter, late-materialisation)";
+      return run_nested_loop_join(ctx, l, r, join_type, has_join_filter ? &fs : nullptr, schema);
+    }
   }
   throw_internal("unknown plan node");
 }
@@ -680,6 +693,28 @@ int qgpu_plan_hash_join(qgpu_ctx* ctx, qgpu_plan* left, qgpu_plan* right, int32_
       n->left_on.push_back(left_on[i]->root);
       n->right_on.push_back(right_on[i]->root);
     }
+    if (filter) {
+      n->has_join_filter = true;
+      n->join_filter_expr = filter->expr->root;
+      n->join_filter_schema = import_schema(filter->schema);
+      n->join_filter_index.assign(filter->column_index, filter->column_index + filter->n_columns);
+      n->join_filter_side.assign(filter->column_side, filter->column_side + filter->n_columns);
+      if ((int)n->join_filter_schema.fields.size() != filter->n_columns) throw_internal("join filter schema/column_indices mismatch");
+    }
+    *out = new qgpu_plan{n};
+  });
+}
+
+int qgpu_plan_nested_loop_join(qgpu_ctx* ctx, qgpu_plan* left, qgpu_plan* right, int32_t join_type, const qgpu_join_filter* filter,
+                               qgpu_plan** out) {
+  if (!ctx || !left || !right || !out) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] {
+    if (join_type < 0 || join_type > QGPU_JOIN_LEFT_ANTI) throw_internal("unknown join type");
+    auto n = new_node(ctx, PK_NL_JOIN);
+    n->children.push_back(left->node);
+    n->children.push_back(right->node);
+    n->join_type = join_type;
+    n->schema = build_join_schema(left->node->schema, right->node->schema, join_type);
     if (filter) {
       n->has_join_filter = true;
       n->join_filter_expr = filter->expr->root;

@@ -467,3 +467,51 @@ class HashJoinExec(PhysicalPlan):
                 cs.release(cs)
         keep.append(("plan", h))
         return h
+
+
+def _join_filter_struct(ctx, filter, keep):
+    """-> (ctypes pointer or None, exported ArrowSchema to release or None)"""
+    if filter is None:
+        return None, None
+    fh = ctx.parse_expr(filter.expr)
+    keep.append(("expr", fh))
+    cs = ctx.export_schema(filter.schema)
+    n = len(filter.column_indices)
+    ci = (ctypes.c_int32 * max(n, 1))(*[i for i, _ in filter.column_indices])
+    sd = (ctypes.c_int32 * max(n, 1))(*[int(s) for _, s in filter.column_indices])
+    jf = _lib.qgpu_join_filter(fh.value, _lib.addr(cs), ci, sd, n)
+    keep.append(("raw", (jf, ci, sd)))
+    return ctypes.byref(jf), cs
+
+
+class NestedLoopJoinExec(PhysicalPlan):
+    """`NestedLoopJoinExec::try_new(left, right, join_type, filter)` (nest_loop_join.rs:52-76): the planner's operator
+    for joins without equi-conditions (planner/mod.rs:316-320).  Matched pairs are ordered by (right row, left row);
+    Left / Right / Full add one batch of unmatched left rows followed by unmatched right rows (:168-226)."""
+
+    def __init__(self, left: PhysicalPlan, right: PhysicalPlan, join_type: JoinType, filter: Optional[JoinFilter]):
+        self.left = left
+        self.right = right
+        self.join_type = JoinType(join_type)
+        self.filter = filter
+        self.schema, self.column_indices = build_join_schema(left.schema, right.schema, self.join_type)
+
+    @staticmethod
+    def try_new(left, right, join_type, filter) -> "NestedLoopJoinExec":
+        return NestedLoopJoinExec(left, right, join_type, filter)
+
+    def children(self):
+        return [self.left, self.right]
+
+    def _build(self, ctx, keep):
+        lh = self.left._build(ctx, keep)
+        rh = self.right._build(ctx, keep)
+        fptr, cs = _join_filter_struct(ctx, self.filter, keep)
+        h = ctypes.c_void_p()
+        try:
+            ctx.check(ctx.lib.qgpu_plan_nested_loop_join(ctx.handle, lh, rh, int(self.join_type), fptr, ctypes.byref(h)))
+        finally:
+            if cs is not None:
+                cs.release(cs)
+        keep.append(("plan", h))
+        return h
