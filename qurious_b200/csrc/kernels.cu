@@ -594,6 +594,11 @@ __global__ void __launch_bounds__(1024) k_str_take_small(const char* __restrict_
 }
 
 static int32_t max_str_len_of(Ctx* ctx, const DCol& base) {
+  if (base.max_str_len < 0 && base.dict_state == 1) {  // dictionary-coded column: the dictionary holds every value
+    size_t m = 0;
+    for (const std::string& v : base.dict_values) m = std::max(m, v.size());
+    base.max_str_len = (int32_t)m;
+  }
   if (base.max_str_len < 0) {
     DBufP m = ctx->alloc_zero(8);
     if (base.length > 0)
