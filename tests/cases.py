@@ -165,6 +165,28 @@ def golden_cases() -> Iterator[Case]:
         plan = HashJoinExec.try_new(scan(lt), scan(rt), JoinType[c["join_type"]], on, None)
         yield (f"hash_join:{name}", plan, [tuple(r) for r in c["expected"]], True)
 
+    # ---------------------------------------------------------------- nest_loop_join.rs unit tests
+    from qurious_b200.datatypes import JoinSide
+    from qurious_b200.physical.plan import JoinFilter, NestedLoopJoinExec
+    for name, c in G["nested_loop_join"]["cases"].items():
+        lt = table(c["left"], default=pa.int32()) if any(len(v) for v in c["left"].values()) else \
+            table_with_empty_batch(c["left"], pa.int32())
+        rt = table(c["right"], default=pa.int32()) if any(len(v) for v in c["right"].values()) else \
+            table_with_empty_batch(c["right"], pa.int32())
+        jf = None
+        if c["filter"]:
+            fs = pa.schema([pa.field("k1", pa.int32(), False), pa.field("k2", pa.int32(), False)])
+            jf = JoinFilter(bx(Column("k1", 0), "Eq", Column("k2", 1)), fs, [(1, JoinSide.Left), (0, JoinSide.Right)])
+        plan = NestedLoopJoinExec.try_new(scan(lt), scan(rt), JoinType[c["join_type"]], jf)
+        yield (f"nested_loop_join:{name}", plan, [tuple(r) for r in c["expected"]], True)
+    # ---------------------------------------------------------------- aggregate/hash.rs unit test
+    hu = G["hash_aggregate_unit"]
+    t = table(hu["table"], default=pa.int32(), nullable=False)
+    yield ("hash_aggregate:test_group_by",
+           HashAggregate(schema_of(("c1", pa.int32()), ("b1", pa.int32()), ("MAX(a1)", pa.int32())), scan(t),
+                         [col(t, k) for k in hu["group_by"]], [MaxAggregateExpr(col(t, "a1"), pa.int32())]),
+           [tuple(r) for r in hu["expected"]], False)
+
     S = G["slt"]
     # ---------------------------------------------------------------- aggregation.slt
     a = S["aggregation_t1"]
