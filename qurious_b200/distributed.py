@@ -473,18 +473,29 @@ class BroadcastJoinAggregate:
 
 
 def _dist_all_gather_ragged(cols, widths, n_rows, world):
+    """Ragged all-gather of a set of columns (byte tensors, `widths[c]` bytes per row): every rank receives every rank's
+    rows, in rank order.  TWO collectives whatever the column count: the row counts, then ONE equal-size all-gather of
+    a buffer that packs all columns of this rank, each padded to the largest shard (result rows are few); the ranks'
+    slices are then compacted per column."""
     import torch.distributed as dist
     dev = cols[0].device if cols else None
     mine = torch.tensor([n_rows], dtype=torch.int64, device=dev)
     counts = torch.empty(world, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(counts, mine)
     rows = [int(x) for x in counts.tolist()]
-    outs, mx = [], max(rows) if rows else 0
-    for t, w in zip(cols, widths):
-        # equal-size collective on buffers padded to the largest shard (result rows are few), then compaction
-        mine_p = torch.zeros(mx * w, dtype=torch.uint8, device=t.device)
-        mine_p[:t.numel()] = t
-        allp = torch.empty(world * mx * w, dtype=torch.uint8, device=t.device)
-        dist.all_gather_into_tensor(allp, mine_p)
-        outs.append(torch.cat([allp[r * mx * w:r * mx * w + rows[r] * w] for r in range(world)]))
+    mx = max(rows) if rows else 0
+    offs, block = [], 0                       # byte offset of every column inside one rank's block
+    for w in widths:
+        offs.append(block)
+        block += ((mx * w + 15) // 16) * 16
+    if not cols or block == 0:
+        return [torch.empty(0, dtype=torch.uint8, device=dev) for _ in cols], sum(rows)
+    mine_p = torch.zeros(block, dtype=torch.uint8, device=dev)
+    for t, o in zip(cols, offs):
+        mine_p[o:o + t.numel()] = t
+    allp = torch.empty(world * block, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allp, mine_p)
+    outs = []
+    for w, o in zip(widths, offs):
+        outs.append(torch.cat([allp[r * block + o:r * block + o + rows[r] * w] for r in range(world)]))
     return outs, sum(rows)

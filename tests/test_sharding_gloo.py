@@ -87,6 +87,35 @@ def _repart_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _ragged_worker(rank, world, port, out):
+    from qurious_b200.distributed import _dist_all_gather_ragged
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = [5, 0, 9][rank]                                     # ragged, one rank empty
+    a = (np.arange(n, dtype=np.int64) + 1000 * rank)
+    b = (np.arange(n, dtype=np.int32) * 3 + rank)
+    c = (np.arange(2 * n, dtype=np.int64) - rank)           # a 16-byte column (two words per row)
+    cols = [torch.from_numpy(np.frombuffer(x.tobytes(), dtype=np.uint8).copy()) for x in (a, b, c)]   # byte views, empty included
+    g, total = _dist_all_gather_ragged(cols, [8, 4, 16], n, world)
+    out[rank] = (total, g[0].view(torch.int64).tolist(), g[1].view(torch.int32).tolist(), g[2].view(torch.int64).tolist())
+    dist.destroy_process_group()
+
+
+def test_ragged_all_gather_packs_columns_in_rank_order_gloo():
+    """one collective carries all columns: every rank must see every column's rows in rank order, empty shards included"""
+    world = 3
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_ragged_worker, args=(world, port, out), nprocs=world, join=True)
+    ns = [5, 0, 9]
+    exp_a = sum(([i + 1000 * r for i in range(ns[r])] for r in range(world)), [])
+    exp_b = sum(([i * 3 + r for i in range(ns[r])] for r in range(world)), [])
+    exp_c = sum(([i - r for i in range(2 * ns[r])] for r in range(world)), [])
+    for r in range(world):
+        assert out[r] == (14, exp_a, exp_b, exp_c)
+
+
 def test_hash_repartition_protocol_gloo():
     world = 2
     mgr = mp.Manager()
