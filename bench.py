@@ -45,7 +45,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=20_000_000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--extra-queries", default="", help="comma list of further queries reported under 'queries'")
+    ap.add_argument("--extra-queries", default="q6,q3",
+                    help="N=1: comma list of further TPC-H queries whose device-resident leg is reported under 'queries'")
     ap.add_argument("--order-by", action="store_true", help="q1 / q3 with their ORDER BY (+ LIMIT 10) on the device (Sort, SURVEY 8f #1)")
     return ap.parse_args()
 
@@ -446,6 +447,7 @@ def run_b200(args):
         def step():
             plan.execute_device(ctx).free()
     ms, prof, launches = run_query_device(ctx, step, args.steps, args.warmup, sampler, torch, stream)
+    main_step_ms = list(getattr(run_query_device, "step_ms", []))[:64]     # (the extra-query legs below overwrite the attribute)
     t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     rows_t = torch.tensor([rows_local], dtype=torch.int64, device="cuda")
     if world > 1:
@@ -587,6 +589,39 @@ def run_b200(args):
             cpu = {"value": n / dt, "unit": "rows/s", "cores": 1, "kind": "port",
                    "sample": f"{desc}; {dt:.1f} s on 1 of {os.cpu_count()} host cores"}
 
+    # ---- further TPC-H queries of BASELINE.json's metric, device-resident leg only (N = 1): reported under "queries" ----
+    extra = {}
+    if world == 1 and args.extra_queries:
+        for xq in [x.strip() for x in args.extra_queries.split(",")]:
+            if not xq or xq == q or xq not in QUERY_COLUMNS:
+                continue
+            try:
+                ctx.release_cached_memory()
+                xraw = gen_raw(xq, args.sf, "cuda", 0, 1)
+                xrows = xraw["lineitem"].rows
+                xtabs = {k: tpch.to_device_table(ctx, v) for k, v in xraw.items()}
+                del xraw
+                torch.cuda.empty_cache()
+                xplan = build_plan(xq, xtabs)
+
+                def xstep(xplan=xplan):
+                    xplan.execute_device(ctx).free()
+                xsteps = max(1, min(args.steps, 20))
+                xms, xprof, xlaunches = run_query_device(ctx, xstep, xsteps, args.warmup, sampler, torch, stream)
+                xsorted = sorted(xprof, key=lambda r: -r[2])
+                xtop = xsorted[0] if xsorted else ("none", 0, 0.0, 0.0)
+                xtop_ms = xtop[2] / max(xtop[1], 1)
+                _, xper = algorithmic_bytes(xq, xtabs)
+                xbytes = xper.get("orders" if (xq == "q3" and "FM_EMIT" in xtop[0]) else "lineitem", 0)
+                xach = xbytes / (xtop_ms / 1e3) / 1e9 if xtop_ms > 0 else 0.0
+                extra[xq] = {"metric": metric_name(xq), "value": xrows * xsteps / (xms / 1e3), "unit": "rows/s",
+                             "ms_per_step": xms / xsteps, "steps": xsteps, "rows": xrows, "strategy": xplan.last_strategy(),
+                             "roofline": {"bound": "hbm", "kernel": xtop[0], "kernel_ms_avg": xtop_ms, "achieved": xach, "peak": peak,
+                                          "unit": "GB/s", "frac": xach / peak, "algorithmic_bytes_per_launch": xbytes},
+                             "gpu_launches_per_step": xlaunches}
+                del xplan, xtabs
+            except Exception as e:      # never let an extra query take the headline line down
+                extra[xq] = {"error": repr(e)[:300]}
     clocks = sampler.result()
     if rank == 0:
         line = {"metric": metric_name(q), "value": value, "unit": "rows/s", "n_gpus": world,
@@ -600,8 +635,10 @@ def run_b200(args):
                            "strategy": strategy, "rows_per_gpu": rows_local},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(round(launches * args.steps)),
                 "gpu_launches_per_step": launches, "clocks": clocks,
-                "step_ms": getattr(run_query_device, "step_ms", [])[:64],
+                "step_ms": main_step_ms,
                 "kernels": [{"name": r[0], "launches": r[1], "total_ms": round(r[2], 4)} for r in prof_sorted[:8]]}
+        if extra:
+            line["queries"] = extra
         print(json.dumps(line))
     if world > 1:
         _dist.destroy_process_group()
