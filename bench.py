@@ -303,6 +303,41 @@ def cpu_sample(query, rows_q1q6=2_000_000):
         f"1024-row batches, single thread")
 
 
+def acero_context(query, batches):
+    """SURVEY 8d "second line for context": the same query through Arrow C++ (pyarrow compute + Acero group_by) on ALL host
+    cores.  It is NOT the reference (qurious is single-threaded arrow-rs) and not bit-identical to it: Arrow C++ refuses
+    the reference's Decimal128(38, x) products (precision > 38), so the two wide Q1 products are formed in float64 -- the
+    figure only says what a multi-threaded columnar CPU engine does with these rows."""
+    import datetime
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    t = pa.Table.from_batches(batches)
+    t0 = time.perf_counter()
+    if query == "q6":
+        from decimal import Decimal
+        dec = pa.decimal128(15, 2)
+        m = pc.and_(pc.and_(pc.greater_equal(t["l_shipdate"], datetime.date(1994, 1, 1)), pc.less(t["l_shipdate"], datetime.date(1995, 1, 1))),
+                    pc.and_(pc.and_(pc.greater_equal(t["l_discount"], pa.scalar(Decimal("0.05"), dec)),
+                                    pc.less_equal(t["l_discount"], pa.scalar(Decimal("0.07"), dec))),
+                            pc.less(t["l_quantity"], pa.scalar(Decimal("24.00"), dec))))
+        f = t.filter(m)
+        out = pc.sum(pc.multiply(f["l_extendedprice"], f["l_discount"]))
+        n_out = 1 if out.is_valid else 0
+    else:
+        f = t.filter(pc.less_equal(t["l_shipdate"], datetime.date(1998, 9, 2)))
+        price, disc, tax = (pc.cast(f[c], pa.float64()) for c in ("l_extendedprice", "l_discount", "l_tax"))
+        dp = pc.multiply(price, pc.subtract(1.0, disc))
+        f = f.append_column("disc_price", dp).append_column("charge", pc.multiply(dp, pc.add(1.0, tax)))
+        g = f.group_by(["l_returnflag", "l_linestatus"]).aggregate(
+            [("l_quantity", "sum"), ("l_extendedprice", "sum"), ("disc_price", "sum"), ("charge", "sum"), ("l_quantity", "mean"),
+             ("l_extendedprice", "mean"), ("l_discount", "mean"), ("l_quantity", "count")])
+        n_out = g.num_rows
+    dt = time.perf_counter() - t0
+    return {"value": t.num_rows / dt, "unit": "rows/s", "cores": os.cpu_count(), "seconds": dt, "result_rows": n_out,
+            "what": "Arrow C++ %s (pyarrow compute / Acero) on all host cores over the cpu_baseline sample; float64 for the "
+                    "Decimal128(38,x) products Arrow C++ refuses; context only, not the reference" % pa.__version__}
+
+
 # ------------------------------------------------------------------------------------------------
 # reference arm: the CPU port on host cores
 # ------------------------------------------------------------------------------------------------
@@ -581,6 +616,10 @@ def run_b200(args):
             cpu = {"value": n / dt, "unit": "rows/s", "cores": 1, "kind": "port",
                    "sample": f"first {n} rows of this run's lineitem (referenced columns only), 1024-row batches, "
                              f"{dt:.1f} s on 1 of {os.cpu_count()} host cores (the reference is single-threaded)"}
+            try:
+                cpu["context_arrow_cpp_all_cores"] = acero_context(q, sample)
+            except Exception as e:      # context only: never fatal
+                cpu["context_arrow_cpp_all_cores"] = {"error": repr(e)[:200]}
         else:
             fn, n, desc = cpu_sample(q)
             t0 = time.perf_counter()

@@ -72,3 +72,20 @@ def test_q3_matches_plain_decimal_arithmetic():
     got = sorted(rows_of(qref.execute(tpch.q3_plan(db))))
     assert got == exp
     assert len(exp) > 0
+
+
+def test_q6_matches_arrow_cpp():
+    """SURVEY 8c "independent cross-check available here": Q6 through Arrow C++ (pyarrow compute) -- its decimal
+    comparison / multiply / sum kernels -- must give the oracle's Decimal128(31,4) value exactly."""
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    db = tpch.generate(0.01)
+    t = pa.Table.from_batches(db.lineitem.data)
+    dec = pa.decimal128(15, 2)
+    m = pc.and_(pc.and_(pc.greater_equal(t["l_shipdate"], D(1994, 1, 1)), pc.less(t["l_shipdate"], D(1995, 1, 1))),
+                pc.and_(pc.and_(pc.greater_equal(t["l_discount"], pa.scalar(Decimal("0.05"), dec)),
+                                pc.less_equal(t["l_discount"], pa.scalar(Decimal("0.07"), dec))),
+                        pc.less(t["l_quantity"], pa.scalar(Decimal("24.00"), dec))))
+    f = t.filter(m)
+    exp = pc.sum(pc.multiply(f["l_extendedprice"], f["l_discount"])).as_py()
+    assert rows_of(qref.execute(tpch.q6_plan(db))) == [(exp,)]
