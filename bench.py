@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--groups", type=int, default=100_000_000, help="groupby workload: distinct keys")
     ap.add_argument("--sf", type=float, default=10.0, help="TPC-H scale factor PER GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-sample-rows", type=int, default=20_000_000)
+    ap.add_argument("--cpu-sample-rows", type=int, default=30_000_000)   # ~11 s of single-core CPU work for Q1
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--extra-queries", default="q6,q3",
