@@ -261,7 +261,8 @@ static DColP import_column(Ctx* ctx, const Field& f, const ArrowArray* a, int64_
     col->null_count = n;
     return col;
   }
-  if (a->length < parent_off + n - 0 && a->length < n) throw_arrow("child array shorter than the record batch");
+  // Arrow: child.length >= struct.offset + struct.length
+  if (a->length < parent_off + n) throw_arrow("child array shorter than the record batch");
   // validity
   const uint8_t* vbits = (a->n_buffers > 0) ? (const uint8_t*)a->buffers[0] : nullptr;
   int64_t nulls = a->null_count;

@@ -955,6 +955,9 @@ struct FExport {
   int wide[24];     // 1: the accumulator has a real hi word (DENSE sums / carry mode)
   unsigned long long* out_lo[24];
   unsigned long long* out_hi[24];
+  // ungrouped aggregate over zero qualifying rows: MIN / MAX return the TYPED start value (min.rs / max.rs NATIVE::MAX / MIN,
+  // quirk Q4) -- the kernels' working seed is INT64_MAX / INT64_MIN whatever the type
+  unsigned long long sent_lo[24], sent_hi[24];
 };
 __global__ void k_fused_export(const unsigned long long* __restrict__ lo, const unsigned long long* __restrict__ hi, int64_t n_slots,
                                int64_t k_stride, int64_t g_stride, int n_accs, const int64_t* __restrict__ flags,
@@ -1011,15 +1014,20 @@ __global__ void __launch_bounds__(1024) k_fused_export_small(const unsigned long
   for (int i = 0; i < per; ++i) {
     if (!((mask >> i) & 1)) continue;
     const int64_t g = base + i;
-    out_cnt[o] = lo[(int64_t)n_accs * k_stride + g * g_stride];
+    const unsigned long long rows_g = lo[(int64_t)n_accs * k_stride + g * g_stride];
+    out_cnt[o] = rows_g;
     out_first[o] = (long long)lo[(int64_t)(n_accs + 1) * k_stride + g * g_stride];
     for (int a = 0; a < ex.n_aggs; ++a) {
       const int k = ex.acc_of[a];
       if (k < 0) continue;
-      const unsigned long long l = lo[(int64_t)k * k_stride + g * g_stride];
+      unsigned long long l = lo[(int64_t)k * k_stride + g * g_stride];
       unsigned long long h = 0;
       if (ex.wide[a]) h = hi[(int64_t)k * k_stride + g * g_stride];
       else if (ex.kind_of[a] != FK_SUMF) h = ((long long)l < 0) ? ~0ull : 0ull;
+      if (rows_g == 0 && (ex.kind_of[a] == FK_MIN || ex.kind_of[a] == FK_MAX)) {  // force_all: the ungrouped empty case
+        l = ex.sent_lo[a];
+        h = ex.sent_hi[a];
+      }
       ex.out_lo[a][o] = l;
       ex.out_hi[a][o] = h;
     }
@@ -2157,6 +2165,7 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
       ex.kind_of[i] = fk;
       ex.wide[i] = (fk == FK_SUM && (P.mode == FM_DENSE || P.carry)) ? 1 : 0;
       const VClass vc = class_of(s.arg->result_type);
+      if (fk == FK_MIN || fk == FK_MAX) minmax_sentinel(s.arg->result_type, fk == FK_MIN, &ex.sent_lo[i], &ex.sent_hi[i]);
       if (fk == FK_SUMF) ak = AK_SUM_F64;
       else if (fk == FK_SUM) ak = vc == VC_DEC ? AK_SUM_DEC : AK_SUM_I64;
       else if (vc == VC_DEC) ak = fk == FK_MIN ? AK_MIN_DEC : AK_MAX_DEC;
@@ -2191,8 +2200,7 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
       for (size_t i = 0; i < specs.size(); ++i) {
         const int k = acc_of[i];
         if (k < 0 || P.accs[k].kind == FK_SUM || P.accs[k].kind == FK_SUMF) continue;
-        const long long sent = P.accs[k].kind == FK_MIN ? INT64_MAX : INT64_MIN;
-        unsigned long long h[2] = {(unsigned long long)sent, sent < 0 ? ~0ull : 0ull};
+        unsigned long long h[2] = {ex.sent_lo[i], ex.sent_hi[i]};
         ctx->h2d(accs.lo[i]->ptr, &h[0], 8);
         ctx->h2d(accs.hi[i]->ptr, &h[1], 8);
         ctx->sync();

@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(1024) k_rank_order(const long long* __restrict
   for (int g = threadIdx.x; g < n; g += blockDim.x) {
     const long long mine = fr[g];
     int rank = 0;
-    for (int h = 0; h < n; ++h) rank += fr[h] < mine;
+    for (int h = 0; h < n; ++h) rank += (fr[h] < mine) || (fr[h] == mine && h < g);  // ties (overlapping shard offsets) broken by group id
     order[rank] = g;
     first_idx[rank] = mine;
   }
@@ -497,6 +497,25 @@ void validate_agg_types(const std::vector<AggSpec>& aggs) {
         break;
       default: throw_internal("unknown aggregate operator");
     }
+  }
+}
+
+void minmax_sentinel(const DType& at, bool mn, unsigned long long* lo, unsigned long long* hi) {
+  const VClass vc = class_of(at);
+  *lo = *hi = 0;
+  if (vc == VC_DEC) {
+    *hi = mn ? (unsigned long long)INT64_MAX : (unsigned long long)INT64_MIN;
+    *lo = mn ? ~0ull : 0ull;
+  } else if (vc == VC_FLT) {
+    const double lim = at.id == QGPU_T_FLOAT32 ? 3.4028234663852886e38 : 1.7976931348623157e308;
+    *lo = (unsigned long long)f64_total_key(mn ? lim : -lim);
+  } else if (vc == VC_UINT) {
+    const int bits = arrow_width(at) * 8;
+    *lo = mn ? (bits >= 64 ? ~0ull : ((1ull << bits) - 1ull)) : 0ull;
+  } else {
+    const int bits = arrow_width(at) * 8;
+    const long long mx = bits >= 64 ? INT64_MAX : (((long long)1 << (bits - 1)) - 1);
+    *lo = (unsigned long long)(mn ? mx : (-mx - 1));
   }
 }
 
@@ -563,23 +582,15 @@ View run_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<Comp
         const bool mn = a.op == QGPU_AGG_MIN;
         if (vc == VC_DEC) {
           d.kind = mn ? AK_MIN_DEC : AK_MAX_DEC;
-          init_hi = mn ? (unsigned long long)INT64_MAX : (unsigned long long)INT64_MIN;
-          init_lo = mn ? ~0ull : 0ull;
           need_phase1 = true;
         } else if (vc == VC_FLT) {
           d.kind = mn ? AK_MIN_F64 : AK_MAX_F64;
-          double lim = at.id == QGPU_T_FLOAT32 ? 3.4028234663852886e38 : 1.7976931348623157e308;
-          init_lo = (unsigned long long)f64_total_key(mn ? lim : -lim);
         } else if (vc == VC_UINT) {
           d.kind = mn ? AK_MIN_U64 : AK_MAX_U64;
-          int bits = arrow_width(at) * 8;
-          init_lo = mn ? (bits >= 64 ? ~0ull : ((1ull << bits) - 1ull)) : 0ull;
         } else {
           d.kind = mn ? AK_MIN_I64 : AK_MAX_I64;
-          int bits = arrow_width(at) * 8;
-          long long mx = bits >= 64 ? INT64_MAX : (((long long)1 << (bits - 1)) - 1);
-          init_lo = (unsigned long long)(mn ? mx : (-mx - 1));
         }
+        minmax_sentinel(at, mn, &init_lo, &init_hi);
         break;
       }
     }

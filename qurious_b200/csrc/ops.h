@@ -71,6 +71,11 @@ View run_nested_loop_join(Ctx* ctx, const View& left, const View& right, int joi
 
 Schema build_join_schema(const Schema& left, const Schema& right, int join_type);
 
+// MIN / MAX start value of the accumulator for argument type `at` (min.rs / max.rs: NATIVE::MAX / NATIVE::MIN of the array's
+// native type) as the (lo, hi) words the accumulators and finish_aggregate use; floats travel as their total-order key.
+// An ungrouped MIN/MAX over zero qualifying rows returns exactly this value.
+void minmax_sentinel(const DType& at, bool is_min, unsigned long long* lo, unsigned long long* hi);
+
 // validation helpers shared with the fused paths
 void validate_agg_types(const std::vector<AggSpec>& aggs);
 void check_hash_key_type(const DType& t);

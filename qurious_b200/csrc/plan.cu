@@ -452,6 +452,8 @@ static int table_append(qgpu_table* t, struct ArrowArray* batch, const int32_t* 
   if (!t || !batch) return QGPU_ERR_INTERNAL;
   TableImpl& ti = *t->t;
   int rc = guard(ti.ctx, [&] {
+    // import first: a failing batch (column count, short child, CUDA error) must leave the table untouched
+    TableChunk ch = import_batch(ti.ctx, ti.schema, batch, cols, n, dev);
     if (ti.consolidated && ti.num_batches > 0) {
       // re-open: keep the consolidated columns as the first chunk
       TableChunk first;
@@ -459,7 +461,6 @@ static int table_append(qgpu_table* t, struct ArrowArray* batch, const int32_t* 
       first.rows = ti.num_rows;
       ti.chunks.push_back(first);
     }
-    TableChunk ch = import_batch(ti.ctx, ti.schema, batch, cols, n, dev);
     ti.chunks.push_back(ch);
     ti.num_rows += ch.rows;
     ti.num_batches += 1;

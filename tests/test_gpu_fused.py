@@ -44,6 +44,7 @@ def _table(n, seed=3, nulls=False):
         "p": pa.Array.from_buffers(DEC, n, [None, pa.py_buffer(np.stack([rng.integers(0, 10**7, n), np.zeros(n, np.int64)], 1).tobytes())]),
         "f": pa.array(rng.random(n), pa.float64()),
         "i32": pa.array(rng.integers(-100, 100, n).astype(np.int32), pa.int32()),
+        "u16": pa.array(rng.integers(0, 60000, n).astype(np.uint16), pa.uint16()),
     }
     schema = pa.schema([(k, v.type) for k, v in cols.items()])
     full = pa.record_batch(list(cols.values()), schema=schema)
@@ -104,6 +105,16 @@ def test_empty_range_and_unknown_string(gpu_ctx):
         gschema = pa.schema([("k", pa.int64()), ("c", pa.int64())])
         gplan = HashAggregate(gschema, Scan(t.schema, t, None, pred), [C(t, "k")], [CountAggregateExpr(lit(1))])
         run_both(gplan, gpu_ctx)
+        # typed MIN / MAX start values when no row qualifies (min.rs / max.rs NATIVE::MAX / MIN; quirk Q4): Decimal128 keeps
+        # i128::MAX / MIN, Int32 / UInt16 their own type's limits -- not the kernels' 64-bit working seed
+        tschema = pa.schema([("mn_p", DEC), ("mx_p", DEC), ("mn_i", pa.int32()), ("mx_i", pa.int32()), ("mn_u", pa.uint16()),
+                             ("mx_u", pa.uint16())])
+        tplan = NoGroupingAggregate(tschema, Scan(t.schema, t, None, pred),
+                                    [MinAggregateExpr(C(t, "p"), DEC), MaxAggregateExpr(C(t, "p"), DEC),
+                                     MinAggregateExpr(C(t, "i32"), pa.int32()), MaxAggregateExpr(C(t, "i32"), pa.int32()),
+                                     MinAggregateExpr(C(t, "u16"), pa.uint16()), MaxAggregateExpr(C(t, "u16"), pa.uint16())])
+        s = run_both(tplan, gpu_ctx, ordered=True)
+        assert "fused_scan_agg" in s, s
 
 
 def test_hash_mode_full_range_keys_and_carry(gpu_ctx):
