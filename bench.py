@@ -269,6 +269,53 @@ def gen_raw(query, sf_total, device, rank, world):
     return out
 
 
+def local_invariants(query, raw, torch, gather_keys=None):
+    """Independent check values of THIS rank's shard, computed with plain torch int64 arithmetic over the generated
+    columns (none of the library's code): they are summed over the ranks and compared with the merged result
+    (`parity_check` in the JSON line).  -> {name: int}"""
+    from qurious_b200 import tpch
+    if query == "groupby":
+        t = raw["t"].cols
+        return {"rows": int(t["k"].numel()), "sum_v": int(t["v"].sum().item())}
+    c = raw["lineitem"].cols
+    if query == "q1":
+        m = c["l_shipdate"] <= tpch.days("1998-09-02")
+        return {"rows": int(m.sum().item()), "sum_qty": int(c["l_quantity"][m].sum().item()),
+                "sum_base_price": int(c["l_extendedprice"][m].sum().item())}
+    if query == "q6":
+        m = ((c["l_shipdate"] >= tpch.days("1994-01-01")) & (c["l_shipdate"] < tpch.days("1995-01-01")) & (c["l_discount"] >= 5) &
+             (c["l_discount"] <= 7) & (c["l_quantity"] < 2400))
+        return {"revenue": int((c["l_extendedprice"][m] * c["l_discount"][m]).sum().item())}
+    # q3: the qualifying orders of every rank's orders shard are needed by every rank (gather_keys: ragged all-gather)
+    cust, o = raw["customer"], raw["orders"].cols
+    d = tpch.days("1995-03-15")
+    building = cust.cols["c_custkey"][cust.codes["c_mktsegment"] == cust.vocab["c_mktsegment"].index("BUILDING")]
+    keys = o["o_orderkey"][(o["o_orderdate"] < d) & torch.isin(o["o_custkey"], building)]
+    if gather_keys is not None:
+        keys = gather_keys(keys)
+    m = (c["l_shipdate"] > d) & torch.isin(c["l_orderkey"], keys)
+    return {"revenue": int((c["l_extendedprice"][m] * (100 - c["l_discount"][m])).sum().item())}
+
+
+def result_invariants(query, batches):
+    """The same quantities read back from the query's (merged) result batches."""
+    def raw_dec(v):
+        return int(v.scaleb(-v.as_tuple().exponent))
+    import pyarrow as pa
+    if not batches:
+        return {}
+    t = pa.Table.from_batches(batches)
+    if query == "groupby":
+        return {"rows": sum(t["count_v"].to_pylist()), "sum_v": sum(t["sum_v"].to_pylist())}
+    if query == "q1":
+        return {"rows": sum(t["count_order"].to_pylist()), "sum_qty": sum(raw_dec(v) for v in t["sum_qty"].to_pylist()),
+                "sum_base_price": sum(raw_dec(v) for v in t["sum_base_price"].to_pylist())}
+    if query == "q6":
+        v = t.column(0).to_pylist()[0]
+        return {"revenue": raw_dec(v) if v is not None else 0}
+    return {"revenue": sum(raw_dec(v) for v in t["revenue"].to_pylist())}
+
+
 def metric_name(q):
     return "group-by rows/sec" if q == "groupby" else f"TPC-H {q.upper()} rows/sec"
 
@@ -368,6 +415,19 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+def kernel_bytes(kernel, q, per_table, driving, rows_local, groups_local):
+    """Algorithmic bytes ONE launch of `kernel` moves, or None when the kernel does not stream a table (no
+    roofline fraction is quoted for it): the fused scan kernels read every referenced column of the table they scan once
+    (FM_EMIT = J1's probe scan over orders, everything else the driving table); the radix passes move 3 x 8 B tuples."""
+    if kernel.startswith("k_fused_scan_agg"):
+        return per_table.get("orders" if "FM_EMIT" in kernel else driving)
+    if q == "groupby":
+        # tuples are 3 x 8 B; groups leave as 6 x 8 B (DESIGN.md 3.1c)
+        return {"k_radix_agg": 24 * rows_local + 48 * groups_local, "k_radix_scatter<1>": 48 * rows_local,
+                "k_radix_scatter<2>": 48 * rows_local, "k_radix_hist1": 8 * rows_local, "k_radix_hist2": 8 * rows_local}.get(kernel)
+    return None
+
+
 def algorithmic_bytes(query, dev_tables):
     """Bytes of every referenced column in the layout the kernels read (after ingest narrowing), once."""
     total = 0
@@ -380,10 +440,37 @@ def algorithmic_bytes(query, dev_tables):
     return total, per_table
 
 
+class Pipelined:
+    """Depth-2 pipeline of asynchronous executions (qgpu_plan_execute_device_async / _sharded_device async): step i is
+    queued, then the result of step i-1 is waited for (its row count is read: DeviceTable.wait) and released -- the host
+    consumes every result while the GPU already runs the next step.  Plans whose last operator is not the fused dense
+    aggregate resolve inside the call, i.e. run synchronously as before."""
+
+    def __init__(self, launch):
+        self.launch, self.inflight, self.rows = launch, [], None
+
+    def __call__(self):
+        self.inflight.append(self.launch())
+        if len(self.inflight) > 1:
+            self._retire()
+
+    def _retire(self):
+        t = self.inflight.pop(0)
+        t.wait()
+        self.rows = t.num_rows
+        t.free()
+
+    def drain(self):
+        while self.inflight:
+            self._retire()
+
+
 def run_query_device(ctx, step, steps, warmup, sampler, torch, stream):
     """K timed steps, table resident in HBM; returns (ms_total, per-kernel profile, launches per step)."""
+    drain = getattr(step, "drain", lambda: None)
     for _ in range(warmup):
         step()
+    drain()
     # event pairs only around launches of >= 64 blocks (the scan / probe / radix kernels): bracketing every single-block
     # helper as well costs the Q1 SF10 step 7 % (0.463 vs 0.431 ms, same box; QGPU_BENCH_PROFILE_ALL=1 restores that)
     ctx.profile(True, 0 if os.environ.get("QGPU_BENCH_PROFILE_ALL") else 64)
@@ -400,6 +487,7 @@ def run_query_device(ctx, step, steps, warmup, sampler, torch, stream):
         if i < len(marks):
             marks[i].record(stream)
     e1.record(stream)
+    drain()                      # the last results are consumed inside the timed region as well
     torch.cuda.synchronize()
     sampler.region(False)
     barrier()
@@ -417,6 +505,47 @@ _dist = None
 def barrier():
     if _dist is not None:
         _dist.barrier()
+
+
+def _gather_ragged_i64(t, world, torch):
+    """all ranks' int64 vectors concatenated (NCCL all-gather of the sizes, then of the padded vectors)"""
+    n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+    ns = torch.empty(world, dtype=torch.int64, device=t.device)
+    _dist.all_gather_into_tensor(ns, n)
+    sizes = [int(x) for x in ns.tolist()]
+    pad = torch.zeros(max(sizes + [1]), dtype=torch.int64, device=t.device)
+    pad[:t.numel()] = t
+    out = torch.empty(world * pad.numel(), dtype=torch.int64, device=t.device)
+    _dist.all_gather_into_tensor(out, pad)
+    return torch.cat([out[r * pad.numel(): r * pad.numel() + sizes[r]] for r in range(world)])
+
+
+def parity_check(q, expect_local, result_of, world, torch):
+    """One more execution of the step's plan; its (merged) result is compared with invariants computed independently
+    by torch over every rank's generated columns (summed over the ranks with all_reduce): sum of the group counts =
+    qualifying rows, sum of the group sums = the plain column sums."""
+    try:
+        names = sorted(expect_local)
+        exp = torch.tensor([expect_local[k] for k in names], dtype=torch.int64, device="cuda")
+        if world > 1:
+            _dist.all_reduce(exp)
+        res = result_of()
+        if isinstance(res, list):
+            got = result_invariants(q, res)
+            got_t = torch.tensor([got.get(k, 0) for k in names], dtype=torch.int64, device="cuda")
+        else:                               # group-by: the result stays in HBM (10^8 groups); this rank's share of the groups
+            from qurious_b200.distributed import column_bytes_tensor
+            cnt = column_bytes_tensor(res, 2)[0].view(torch.int64)
+            sv = column_bytes_tensor(res, 1)[0].view(torch.int64)
+            got_t = torch.stack([cnt.sum(), sv.sum()])           # names: rows, sum_v
+            res.free()
+            if world > 1:
+                _dist.all_reduce(got_t)
+        ok = bool(torch.equal(exp, got_t))
+        return {"ok": ok, "checked": names, "expected": [int(x) for x in exp.tolist()], "got": [int(x) for x in got_t.tolist()],
+                "how": "torch int64 sums over the generated columns of every shard (all_reduce) vs the query's merged result"}
+    except Exception as e:                  # a failing check must be visible, not fatal for the measurement
+        return {"ok": False, "error": repr(e)[:300]}
 
 
 def run_b200(args):
@@ -445,11 +574,13 @@ def run_b200(args):
     # ---- device-resident leg -----------------------------------------------------------------
     raw = gen_raw(q, sf_total, "cuda", rank, world)
     rows_local = raw[driving].rows
+    expect = local_invariants(q, raw, torch, (lambda k: _gather_ragged_i64(k, world, torch)) if world > 1 else None)
     dev_tables = {k: tpch.to_device_table(ctx, v) for k, v in raw.items()}
     del raw
     torch.cuda.empty_cache()        # the generator's temporaries go back to the driver: HBM is for the tables
     plan = build_plan(q, dev_tables)
     sharded = None
+    result_of = None                # -> (host batches | device table) of one more execution, for the parity check
     if world > 1:
         # row-range shards: shard-local partial aggregate -> NCCL all-gather of the state blocks -> exact merge
         from qurious_b200 import distributed as qd
@@ -463,6 +594,7 @@ def run_b200(args):
             def step():
                 xg.execute_device().free()
                 step.strategy = "%s x%d -> %s" % (xg.last_path, world, plan.last_strategy())
+            result_of = xg.execute_device
         elif q == "q3":
             # orders and lineitem row-range sharded, customer replicated: J1 per orders shard, its rows all-gathered
             # (broadcast build), J2 + aggregate per lineitem shard; groups straddling a shard boundary are merged by
@@ -473,15 +605,20 @@ def run_b200(args):
             def step():
                 bj.execute_device().free()
                 step.strategy = bj.last_strategy
+            result_of = bj.execute
         else:
+            # Q1 / Q6: scan kernel + ONE epilogue kernel per step; the epilogue stores the state block into every peer's
+            # buffer over NVLink, waits on the peers' flags, merges and finalises (no collective call, no host round trip)
             sharded = qd.ShardedAggregate(ctx, plan, lo, world)
-
-            def step():
-                sharded.execute_device().free()
+            sharded.execute_device().free()            # records the strategy
+            step = Pipelined(lambda: sharded.execute_device(wait=False))
+            result_of = sharded.execute
     else:
-        def step():
-            plan.execute_device(ctx).free()
+        plan.execute_device(ctx).free()                # records the strategy
+        step = Pipelined(lambda: plan.execute_device_async(ctx))
+        result_of = (lambda: plan.execute_device(ctx)) if q == "groupby" else (lambda: plan.execute(ctx))
     ms, prof, launches = run_query_device(ctx, step, args.steps, args.warmup, sampler, torch, stream)
+    parity = parity_check(q, expect, result_of, world, torch)
     main_step_ms = list(getattr(run_query_device, "step_ms", []))[:64]     # (the extra-query legs below overwrite the attribute)
     t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     rows_t = torch.tensor([rows_local], dtype=torch.int64, device="cuda")
@@ -497,17 +634,8 @@ def run_b200(args):
     top = prof_sorted[0] if prof_sorted else ("none", 0, 0.0, 0.0)
     top_ms = top[2] / max(top[1], 1)
     top_share = top[2] / max(ms, 1e-9)                 # of the timed region's device time
-    top_bytes = per_table.get(driving, alg_bytes)   # the dominant kernel streams the driving table
-    if q == "q3" and "FM_EMIT" in top[0]:
-        top_bytes = per_table.get("orders", top_bytes)     # J1's probe scan streams orders, not lineitem
-    if q == "groupby":
-        # algorithmic bytes of the radix passes: tuples are 3 x 8 B; groups leave as 6 x 8 B
-        groups_local = args.groups // world
-        per_kernel = {"k_radix_agg": 24 * rows_local + 48 * groups_local, "k_radix_scatter<1>": 48 * rows_local,
-                      "k_radix_scatter<2>": 48 * rows_local, "k_radix_hist1": 8 * rows_local, "k_radix_hist2": 8 * rows_local}
-        # FM_HASH: streamed columns + one random 32 B sector read + write per row on the group table
-        top_bytes = per_kernel.get(top[0], top_bytes + 64 * rows_local)
-    achieved = top_bytes / (top_ms / 1e3) / 1e9 if top_ms > 0 else 0.0
+    top_bytes = kernel_bytes(top[0], q, per_table, driving, rows_local, args.groups // world)
+    achieved = top_bytes / (top_ms / 1e3) / 1e9 if (top_ms > 0 and top_bytes) else None
     traffic, traffic_src = None, None      # measured DRAM bytes per launch of that kernel at this size (ncu), when captured
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
@@ -517,13 +645,13 @@ def run_b200(args):
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": top_bytes, "bytes_per_row": top_bytes / max(rows_local, 1),
+                "frac": (achieved / peak) if achieved is not None else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": top_bytes, "bytes_per_row": (top_bytes / max(rows_local, 1)) if top_bytes else None,
                 "kernel_ms_avg": top_ms, "kernel_share_of_step": top_share, "launches_of_kernel_per_step": top[1] / args.steps,
                 "step_frac_of_roofline": (alg_bytes / (ms / args.steps / 1e3) / 1e9) / peak}
     ctx.release_cached_memory()
     rp = read_peak_live(torch)
-    if rp:
+    if rp and achieved is not None:
         roofline["read_only_reference"] = {"gbs": rp, "frac": achieved / rp,
                                            "how": "torch int64 sum over 1.68 GB, measured in this run (reads only; the peak above is a copy)"}
 
@@ -643,20 +771,20 @@ def run_b200(args):
                 torch.cuda.empty_cache()
                 xplan = build_plan(xq, xtabs)
 
-                def xstep(xplan=xplan):
-                    xplan.execute_device(ctx).free()
+                xplan.execute_device(ctx).free()       # records the strategy
+                xstep = Pipelined(lambda xplan=xplan: xplan.execute_device_async(ctx))
                 xsteps = max(1, min(args.steps, 20))
                 xms, xprof, xlaunches = run_query_device(ctx, xstep, xsteps, args.warmup, sampler, torch, stream)
                 xsorted = sorted(xprof, key=lambda r: -r[2])
                 xtop = xsorted[0] if xsorted else ("none", 0, 0.0, 0.0)
                 xtop_ms = xtop[2] / max(xtop[1], 1)
                 _, xper = algorithmic_bytes(xq, xtabs)
-                xbytes = xper.get("orders" if (xq == "q3" and "FM_EMIT" in xtop[0]) else "lineitem", 0)
-                xach = xbytes / (xtop_ms / 1e3) / 1e9 if xtop_ms > 0 else 0.0
+                xbytes = kernel_bytes(xtop[0], xq, xper, "lineitem", xrows, 0)
+                xach = xbytes / (xtop_ms / 1e3) / 1e9 if (xtop_ms > 0 and xbytes) else None
                 extra[xq] = {"metric": metric_name(xq), "value": xrows * xsteps / (xms / 1e3), "unit": "rows/s",
                              "ms_per_step": xms / xsteps, "steps": xsteps, "rows": xrows, "strategy": xplan.last_strategy(),
                              "roofline": {"bound": "hbm", "kernel": xtop[0], "kernel_ms_avg": xtop_ms, "achieved": xach, "peak": peak,
-                                          "unit": "GB/s", "frac": xach / peak, "algorithmic_bytes_per_launch": xbytes},
+                                          "unit": "GB/s", "frac": (xach / peak) if xach is not None else None, "algorithmic_bytes_per_launch": xbytes},
                              "gpu_launches_per_step": xlaunches}
                 del xplan, xtabs
             except Exception as e:      # never let an extra query take the headline line down
@@ -674,7 +802,7 @@ def run_b200(args):
                            "strategy": strategy, "rows_per_gpu": rows_local},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(round(launches * args.steps)),
                 "gpu_launches_per_step": launches, "clocks": clocks,
-                "step_ms": main_step_ms,
+                "step_ms": main_step_ms, "parity_check": parity,
                 "kernels": [{"name": r[0], "launches": r[1], "total_ms": round(r[2], 4)} for r in prof_sorted[:8]]}
         if extra:
             line["queries"] = extra

@@ -301,6 +301,43 @@ int qgpu_plan_execute_merged_device(qgpu_plan* p, const void* gathered_device_bu
 int qgpu_plan_execute_merged(qgpu_plan* p, const void* gathered_device_buf, int32_t n_states, int32_t max_groups,
                              struct ArrowArrayStream* out);
 
+/* ---- asynchronous execution ---------------------------------------------------------------------------------------
+ * Like qgpu_plan_execute_device, but returns as soon as the kernels are queued on the context stream: the result table's
+ * row count / NULL counts may still be on their way from the device (plans that end in the fused dense aggregate: scan
+ * kernel + single-CTA epilogue, no host round trip).  qgpu_table_wait (or the first accessor that needs the numbers:
+ * qgpu_table_num_rows, _export, a Scan over the table ...) waits for them; errors of the producing kernels (decimal AVG
+ * overflow, sharded-merge overflow, peer time-out) surface there.  Other plans resolve before returning. */
+int qgpu_plan_execute_device_async(qgpu_plan* p, qgpu_table** out);
+int qgpu_table_wait(qgpu_table* t);
+
+/* ---- communicator: multi-GPU plumbing below the ABI (no reference counterpart) ---------------------------------
+ * One process per GPU.  Rank 0 calls qgpu_comm_unique_id and hands the 128 bytes to every rank (any side channel); every
+ * rank then calls qgpu_comm_init, which creates an NCCL communicator owned by the library (libnccl.so.2 is dlopen'ed here:
+ * single-GPU hosts never need it), allocates this rank's SYMMETRIC peer buffer and maps every peer's buffer over
+ * NVLink (CUDA IPC).  Failures are QGPU_ERR_NCCL.  qgpu_comm_init_local wires several contexts of ONE process together
+ * without NCCL (tests: ranks emulated on one GPU; peer kernels, no NCCL collectives). */
+int qgpu_comm_unique_id(void* out, int64_t cap /* >= 128 */);
+int qgpu_comm_init(qgpu_ctx* ctx, const void* unique_id, int32_t rank, int32_t world);
+int qgpu_comm_init_local(qgpu_ctx** ctxs, int32_t n);
+int qgpu_comm_destroy(qgpu_ctx* ctx);
+int qgpu_comm_world(const qgpu_ctx* ctx, int32_t* rank, int32_t* world);
+/* plain NCCL collectives on the context stream over DEVICE buffers (hosts without their own NCCL binding) */
+int qgpu_comm_all_gather(qgpu_ctx* ctx, const void* send_device, void* recv_device, int64_t bytes_per_rank);
+int qgpu_comm_all_to_all(qgpu_ctx* ctx, const void* send_device, const int64_t* send_offsets, const int64_t* send_bytes,
+                         void* recv_device, const int64_t* recv_offsets, const int64_t* recv_bytes);
+int qgpu_comm_barrier(qgpu_ctx* ctx);
+
+/* Whole sharded aggregate step in one call (replaces partial_state + all-gather + execute_merged): every rank runs
+ * `p` over its row-range shard; the shard-local aggregate is followed by ONE kernel that stores this rank's state block
+ * into every peer's symmetric buffer over NVLink, waits on the peers' epoch flags, merges all blocks exactly and
+ * finalises -- no collective call, no host round trip.  Every rank returns the same (whole) result.  row_offset = global
+ * index of the shard's first row; more than max_groups (<= 4096) groups on a shard -> QGPU_ERR_INTERNAL (use the
+ * exchange / hash repartition for high-cardinality keys); a peer that never arrives -> QGPU_ERR_NCCL after
+ * QGPU_PEER_TIMEOUT_MS (default 20 s).  Every rank must issue the same sequence of sharded executions. */
+int qgpu_plan_execute_sharded(qgpu_plan* p, int64_t row_offset, int32_t max_groups, struct ArrowArrayStream* out);
+/* the result stays in HBM; async != 0: see qgpu_plan_execute_device_async */
+int qgpu_plan_execute_sharded_device(qgpu_plan* p, int64_t row_offset, int32_t max_groups, int32_t async, qgpu_table** out);
+
 #ifdef __cplusplus
 }
 #endif

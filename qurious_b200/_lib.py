@@ -29,6 +29,9 @@ SYMBOLS = [
     "qgpu_plan_free", "qgpu_plan_state_bytes", "qgpu_plan_partial_state", "qgpu_plan_execute_merged", "qgpu_plan_execute_merged_device", "qgpu_plan_set_order_free",
     "qgpu_release_cached_memory", "qgpu_table_hash_partition", "qgpu_table_column_device_buffer",
     "qgpu_plan_exchange_keystats", "qgpu_plan_exchange_sketch", "qgpu_plan_exchange_prepare", "qgpu_plan_exchange_scatter", "qgpu_plan_exchange_finish",
+    "qgpu_plan_execute_device_async", "qgpu_table_wait",
+    "qgpu_comm_unique_id", "qgpu_comm_init", "qgpu_comm_init_local", "qgpu_comm_destroy", "qgpu_comm_world", "qgpu_comm_all_gather",
+    "qgpu_comm_all_to_all", "qgpu_comm_barrier", "qgpu_plan_execute_sharded", "qgpu_plan_execute_sharded_device",
 ]
 
 STATUS_KIND = {1: "InternalError", 2: "ArrowError", 3: "CudaError", 4: "NcclError", 5: "OutOfMemory"}
@@ -131,6 +134,18 @@ def load_library() -> ctypes.CDLL:
     lib.qgpu_plan_execute_merged.argtypes = [vp, vp, i32, i32, vp]
     lib.qgpu_plan_execute_merged_device.argtypes = [vp, vp, i32, i32, P(vp)]
     lib.qgpu_plan_set_order_free.argtypes = [vp, i32]
+    lib.qgpu_plan_execute_device_async.argtypes = [vp, P(vp)]
+    lib.qgpu_table_wait.argtypes = [vp]
+    lib.qgpu_comm_unique_id.argtypes = [vp, i64]
+    lib.qgpu_comm_init.argtypes = [vp, vp, i32, i32]
+    lib.qgpu_comm_init_local.argtypes = [P(vp), i32]
+    lib.qgpu_comm_destroy.argtypes = [vp]
+    lib.qgpu_comm_world.argtypes = [vp, P(i32), P(i32)]
+    lib.qgpu_comm_all_gather.argtypes = [vp, vp, vp, i64]
+    lib.qgpu_comm_all_to_all.argtypes = [vp, vp, P(i64), P(i64), vp, P(i64), P(i64)]
+    lib.qgpu_comm_barrier.argtypes = [vp]
+    lib.qgpu_plan_execute_sharded.argtypes = [vp, i64, i32, vp]
+    lib.qgpu_plan_execute_sharded_device.argtypes = [vp, i64, i32, i32, P(vp)]
     _lib = lib
     return lib
 
@@ -194,6 +209,38 @@ class Context:
             self.lib.qgpu_shutdown(self.handle)
             self.handle = None
 
+    # ---- communicator (multi-GPU, include/qgpu.h "communicator") ------------------------------------
+    def comm_unique_id(self) -> bytes:
+        """128-byte NCCL unique id (rank 0 creates it, every rank passes it to comm_init)."""
+        buf = ctypes.create_string_buffer(128)
+        rc = self.lib.qgpu_comm_unique_id(buf, 128)
+        if rc != 0:
+            raise QuriousError(rc, self.lib.qgpu_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        self.check(self.lib.qgpu_comm_init(self.handle, buf, rank, world))
+
+    def comm_destroy(self):
+        self.check(self.lib.qgpu_comm_destroy(self.handle))
+
+    def comm_world(self):
+        r, w = ctypes.c_int32(), ctypes.c_int32()
+        self.lib.qgpu_comm_world(self.handle, ctypes.byref(r), ctypes.byref(w))
+        return r.value, w.value
+
+    def comm_barrier(self):
+        self.check(self.lib.qgpu_comm_barrier(self.handle))
+
+    def comm_all_gather(self, send_ptr: int, recv_ptr: int, bytes_per_rank: int):
+        self.check(self.lib.qgpu_comm_all_gather(self.handle, send_ptr, recv_ptr, bytes_per_rank))
+
+    def comm_all_to_all(self, send_ptr, send_off, send_bytes, recv_ptr, recv_off, recv_bytes):
+        n = len(send_off)
+        A = ctypes.c_int64 * n
+        self.check(self.lib.qgpu_comm_all_to_all(self.handle, send_ptr, A(*send_off), A(*send_bytes), recv_ptr, A(*recv_off), A(*recv_bytes)))
+
     # ---- marshalling helpers ------------------------------------------------------------------
     def export_schema(self, schema: pa.Schema):
         c = _ffi.new("struct ArrowSchema*")
@@ -208,6 +255,13 @@ class Context:
 
 
 _default_ctx: Optional[Context] = None
+
+
+def comm_init_local(ctxs: Sequence["Context"]):
+    """Wire several contexts of THIS process into one group without NCCL (ranks emulated on one GPU, tests)."""
+    arr = (ctypes.c_void_p * len(ctxs))(*[c.handle for c in ctxs])
+    rc = ctxs[0].lib.qgpu_comm_init_local(arr, len(ctxs))
+    ctxs[0].check(rc)
 
 
 def default_context() -> Context:
@@ -252,7 +306,15 @@ class DeviceTable:
 
     @property
     def num_rows(self) -> int:
-        return int(self.ctx.lib.qgpu_table_num_rows(self.handle))
+        n = int(self.ctx.lib.qgpu_table_num_rows(self.handle))
+        if n < 0:
+            raise QuriousError(1, self.ctx.lib.qgpu_last_error(self.ctx.handle).decode())
+        return n
+
+    def wait(self) -> "DeviceTable":
+        """Result of an asynchronous execute: wait for its metadata; errors of the producing kernels are raised here."""
+        self.ctx.check(self.ctx.lib.qgpu_table_wait(self.handle))
+        return self
 
     @property
     def num_batches(self) -> int:

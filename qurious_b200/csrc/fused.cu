@@ -30,6 +30,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "comm.h"
+#include "epilogue.h"
 #include "launch.h"
 #include "plan.h"
 
@@ -1379,6 +1381,7 @@ struct FusedPlan {
   bool radix_ok = false;
   bool radix_failed = false;  // overflowed or declined (few groups) once on this table: stay on FM_HASH
   std::shared_ptr<void> exchange;  // RadixExchange: state of a multi-GPU exchange in flight + its receive buffers
+  std::shared_ptr<void> dense;     // DenseRun: persistent accumulator table + epilogue description (DENSE mode)
   RParams R;                  // comps / comp_of / kind_of filled by the analysis
   int key_bits[F_MAXK] = {0, 0, 0, 0}, key_shift[F_MAXK] = {0, 0, 0, 0}, key_width[F_MAXK] = {0, 0, 0, 0};
   int64_t key_min[F_MAXK] = {0, 0, 0, 0}, key_max[F_MAXK] = {0, 0, 0, 0};  // value range of every key column (this table)
@@ -2035,6 +2038,137 @@ static bool run_radix(PlanNode& agg, const View& v, FusedPlan& fp, View* out) {
   return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// DENSE mode, launch-lean: scan kernel + ONE epilogue kernel (epilogue.cu), no host round trip.  The global accumulator
+// table lives as long as the cached analysis: it is initialised once and re-initialised by every epilogue; the result
+// columns of one execution come out of a single stream-ordered allocation and their metadata (group count, NULL
+// counts, error code) is still in flight when this returns (View::pending).  With `sharded` the same two kernels are
+// the whole multi-GPU step: the epilogue exchanges the state blocks over peer memory and merges them.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct DenseRun {
+  bool eligible = false;
+  bool inited = false;
+  DBufP g_lo, g_hi;
+  std::vector<DBufP> keep;  // dictionary strings on the device
+  std::vector<DType> key_types;
+  std::vector<int> kinds;   // AccKind per aggregate
+  EpiParams E;
+};
+}  // namespace
+
+static int acc_kind_of(int fk, const DType& arg_type) {
+  const VClass vc = class_of(arg_type);
+  if (fk == FK_SUMF) return AK_SUM_F64;
+  if (fk == FK_SUM) return vc == VC_DEC ? AK_SUM_DEC : AK_SUM_I64;
+  if (vc == VC_DEC) return fk == FK_MIN ? AK_MIN_DEC : AK_MAX_DEC;
+  if (vc == VC_UINT) return fk == FK_MIN ? AK_MIN_U64 : AK_MAX_U64;
+  return fk == FK_MIN ? AK_MIN_I64 : AK_MAX_I64;
+}
+
+static DenseRun* prepare_dense(PlanNode& agg, FusedPlan& fp) {
+  if (fp.dense) {
+    DenseRun* d = (DenseRun*)fp.dense.get();
+    return d->eligible ? d : nullptr;
+  }
+  auto d = std::make_shared<DenseRun>();
+  fp.dense = d;
+  Ctx* ctx = agg.ctx;
+  const FParams& P = fp.P;
+  const int nk = (int)fp.keys.size(), na = (int)fp.specs.size();
+  if (P.mode != FM_DENSE || getenv("QGPU_NO_EPILOGUE")) return nullptr;
+  if (nk > EPI_MAXK || na > EPI_MAXAGG || P.n_accs > EPI_MAXACC || P.dense_groups > EPI_MAXG || P.dense_groups < 1) return nullptr;
+  EpiParams& E = d->E;
+  memset(&E, 0, sizeof(E));
+  E.src = EPI_SRC_DENSE;
+  E.n_slots = P.dense_groups;
+  E.n_accs = P.n_accs;
+  for (int k = 0; k < P.n_accs + 2; ++k) {
+    if (k < P.n_accs) E.init[k] = P.accs[k].kind == FK_MIN ? INT64_MAX : (P.accs[k].kind == FK_MAX ? INT64_MIN : 0);
+    else E.init[k] = k == P.n_accs ? 0 : INT64_MAX;
+  }
+  for (int k = 0; k < P.n_accs; ++k) {
+    E.acc_kind[k] = P.accs[k].kind;
+    E.acc_wide[k] = P.accs[k].kind == FK_SUM ? 1 : 0;
+  }
+  for (int k = 0; k < nk; ++k) {
+    d->key_types.push_back(fp.keys[k]->result_type);
+    EpiKey& K = E.key[k];
+    K.is_dict = fp.key_width[k] == 0 ? 1 : 0;
+    K.base = P.keys[k].base;
+    K.mult = (unsigned int)P.keys[k].mult;
+    K.range = (unsigned int)((i128)fp.key_max[k] - (i128)fp.key_min[k] + 1);
+    if (K.is_dict) {
+      const DCol& src = *fp.key_src[k];
+      std::vector<int32_t> offs(1, 0);
+      std::string bytes;
+      for (const std::string& sv : src.dict_values) {
+        if (sv.size() > 16) return nullptr;  // state records carry Utf8 keys of <= 16 bytes: the multi-kernel path runs
+        bytes += sv;
+        offs.push_back((int32_t)bytes.size());
+      }
+      DBufP o = ctx->alloc(offs.size() * 4), b = ctx->alloc(std::max<size_t>(bytes.size(), 16));
+      ctx->h2d(o->ptr, offs.data(), offs.size() * 4);
+      if (!bytes.empty()) ctx->h2d(b->ptr, bytes.data(), bytes.size());
+      ctx->sync();
+      K.dict_offs = (const int32_t*)o->ptr;
+      K.dict_data = (const char*)b->ptr;
+      d->keep.push_back(o);
+      d->keep.push_back(b);
+    }
+  }
+  for (int i = 0; i < na; ++i) {
+    const int k = fp.acc_of[i];
+    E.agg_acc[i] = k;
+    d->kinds.push_back(k < 0 ? (int)AK_COUNT : acc_kind_of(P.accs[k].kind, fp.specs[i].arg->result_type));
+  }
+  d->eligible = true;
+  return d.get();
+}
+
+static View run_dense(PlanNode& agg, FusedPlan& fp, DenseRun& D, bool sharded, int64_t row_offset, int max_groups) {
+  Ctx* ctx = agg.ctx;
+  FParams P = fp.P;
+  EpiParams E = D.E;
+  epilogue_describe(ctx, D.key_types, fp.specs, D.kinds, agg.schema, E);  // type checks (RecordBatch::try_new) before any launch
+  const int NA2 = P.n_accs + 2;
+  if (!D.g_lo) {
+    D.g_lo = ctx->alloc((size_t)P.dense_groups * NA2 * 8);
+    D.g_hi = ctx->alloc((size_t)P.dense_groups * NA2 * 8);
+  }
+  if (!D.inited) {
+    FInit init;
+    for (int k = 0; k < NA2; ++k) init.v[k] = E.init[k];
+    LAUNCH(ctx, k_fused_init, grid_for(ctx, (int64_t)P.dense_groups * NA2, 256), 256, 0, (unsigned long long*)D.g_lo->ptr,
+           (unsigned long long*)D.g_hi->ptr, (int64_t)P.dense_groups, NA2, 1, 0, init);
+  }
+  D.inited = false;  // until the epilogue that re-initialises the table has been queued
+  P.g_lo = (unsigned long long*)D.g_lo->ptr;
+  P.g_hi = (unsigned long long*)D.g_hi->ptr;
+  P.n_groups = nullptr;   // DENSE never touches them
+  P.abort_flag = nullptr;
+  E.g_lo = P.g_lo;
+  E.g_hi = P.g_hi;
+  const bool specialised = fp.spec != nullptr;
+  if (fp.spec) {
+    CUDA_CHECK(cudaFuncSetAttribute(fp.spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.smem_bytes));
+    ::qgpu::KernelScope ks(ctx, "k_fused_scan_agg_spec", fp.grid);
+    fp.spec<<<fp.grid, F_NT + 32, fp.smem_bytes, ctx->stream>>>(P);
+    CUDA_CHECK(cudaGetLastError());
+  } else {
+    CUDA_CHECK(cudaFuncSetAttribute(k_fused_scan_agg<FM_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.smem_bytes));
+    LAUNCH(ctx, k_fused_scan_agg<FM_DENSE>, fp.grid, F_NT + 32, fp.smem_bytes, P);
+  }
+  View out = epilogue_execute(ctx, E, D.key_types, fp.specs, agg.schema, sharded, row_offset, sharded ? max_groups : P.dense_groups, nullptr);
+  D.inited = true;
+  agg.strategy = std::string("fused_scan_agg[dense-private") + (specialised ? "/shape-specialised, " : ", ") +
+                 (P.pack_mask ? std::to_string(__builtin_popcount(P.pack_mask)) + " accs packed into the count word, " : "") +
+                 std::to_string(P.n_cols) + " cols, " + std::to_string(P.n_pred) + " range preds, " + std::to_string(P.n_accs) +
+                 " accs, " + std::to_string(P.stages) + " TMA stages] + single-CTA epilogue" +
+                 (sharded ? "[peer exchange + merge over " + std::to_string(ctx->comm ? ctx->comm->world : 1) + " ranks]" : "");
+  return out;
+}
+
 static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
   Ctx* ctx = agg.ctx;
   ctx->trace(nullptr);
@@ -2061,6 +2195,9 @@ static View run_fused(PlanNode& agg, const View& v, FusedPlan& fp) {
   bool specialised = false;
   int64_t n_slots = 0, k_stride = 0, g_stride = 0;
   int64_t cap = 0;
+  if (P.mode == FM_DENSE && !agg.defer) {
+    if (DenseRun* D = prepare_dense(agg, fp)) return run_dense(agg, fp, *D, false, 0, 0);
+  }
   if (P.mode == FM_DENSE) {
     n_slots = P.dense_groups;
     k_stride = 1;
@@ -2368,7 +2505,7 @@ bool fused_unordered_join(PlanNode& join, View* out) {
   if (!fp->usable) return false;
   // build side (recursively order-free when it is itself such a join)
   View bv;
-  if (!fused_unordered_join(*join.children[0], &bv)) bv = join.children[0]->execute();
+  if (!fused_unordered_join(*join.children[0], &bv)) bv = join.child_view(0);
   const int64_t nb = bv.num_rows;
   if (nb >= 0xfffffff0LL) return false;
   DColP bkey = nb > 0 ? materialize(ctx, bv.cols[lk.col_index], nb) : nullptr;
@@ -2483,7 +2620,7 @@ bool try_fused_join_aggregate(PlanNode& agg, View* out) {
   // ---- build side: ordinary operators, then the join table ------------------------------------------------
   ctx->trace(nullptr);
   View bv;
-  if (!fused_unordered_join(*join->children[0], &bv)) bv = join->children[0]->execute();
+  if (!fused_unordered_join(*join->children[0], &bv)) bv = join->child_view(0);
   const int64_t nb = bv.num_rows;
   if (nb >= 0xfffffff0LL) return false;
   DColP bkey = nb > 0 ? materialize(ctx, bv.cols[lk.col_index], nb) : nullptr;
@@ -2650,6 +2787,18 @@ static std::shared_ptr<FusedPlan> fused_plan_for(PlanNode& agg, View* vout) {
   }
   *vout = v;
   return fp;
+}
+
+// Sharded (multi-GPU) variant: scan + epilogue with the peer exchange and the merge inside the epilogue.  false: this
+// rank's plan is not DENSE-eligible (the caller packs the generic accumulators into the same state block instead).
+bool try_fused_scan_aggregate_sharded(PlanNode& agg, int64_t row_offset, int max_groups, View* out) {
+  View v;
+  std::shared_ptr<FusedPlan> fp = fused_plan_for(agg, &v);
+  if (!fp || !fp->usable || fp->P.mode != FM_DENSE) return false;
+  DenseRun* D = prepare_dense(agg, *fp);
+  if (!D) return false;
+  *out = run_dense(agg, *fp, *D, true, row_offset, max_groups);
+  return true;
 }
 
 bool try_fused_scan_aggregate(PlanNode& agg, View* out) {

@@ -137,6 +137,58 @@ void Ctx::d2h_sync(void* dst, const void* src, size_t bytes) {
   }
 }
 
+// ---- asynchronous result metadata (qgpu_internal.h: Pending) ------------------------------------------
+PendingP make_pending(Ctx* ctx, const void* dev_meta, int words, std::function<void(const unsigned long long*, Pending&)> apply) {
+  if (words > META_WORDS) throw_internal("metadata block too large");
+  MetaSlot* slot = nullptr;
+  for (MetaSlot* s : ctx->meta_slots)
+    if (!s->busy && cudaEventQuery(s->ev) == cudaSuccess) {  // an abandoned slot is reusable once its copy has landed
+      slot = s;
+      break;
+    }
+  cudaGetLastError();
+  if (!slot) {
+    slot = new MetaSlot();
+    CUDA_CHECK(cudaHostAlloc((void**)&slot->host, META_WORDS * 8, cudaHostAllocDefault));
+    CUDA_CHECK(cudaEventCreateWithFlags(&slot->ev, cudaEventDisableTiming));
+    ctx->meta_slots.push_back(slot);
+  }
+  slot->busy = true;
+  auto p = std::make_shared<Pending>();
+  p->ctx = ctx;
+  p->slot = slot;
+  p->apply = std::move(apply);
+  CUDA_CHECK(cudaMemcpyAsync(slot->host, dev_meta, (size_t)words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaEventRecord(slot->ev, ctx->stream));
+  return p;
+}
+void Pending::resolve() {
+  if (!done) {
+    done = true;
+    cudaError_t e = cudaEventSynchronize(slot->ev);
+    unsigned long long meta[META_WORDS];
+    memcpy(meta, slot->host, sizeof(meta));
+    slot->busy = false;
+    slot = nullptr;
+    if (e != cudaSuccess) {
+      err_code = QGPU_ERR_CUDA;
+      err_msg = std::string("CUDA error: ") + cudaGetErrorString(e);
+    } else {
+      try {
+        if (apply) apply(meta, *this);
+      } catch (QError& q) {
+        err_code = q.code;
+        err_msg = q.what();
+      }
+    }
+    apply = nullptr;
+  }
+  if (err_code) throw QError(err_code, err_msg);
+}
+Pending::~Pending() {
+  if (slot) slot->busy = false;  // the slot's event tells the next user when the abandoned copy has landed
+}
+
 // ---- per-kernel profiling (bench.py roofline leg) ---------------------------------------------------
 int Ctx::prof_begin(const char* name) {
   if (prof_used == (int)prof_events.size()) {

@@ -17,6 +17,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 
+#include "finalize.cuh"
 #include "launch.h"
 #include "ops.h"
 
@@ -289,35 +290,6 @@ __global__ void k_fill_u64(unsigned long long* p, int64_t n, unsigned long long 
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
 }
 
-struct FinSpec {
-  int op;          // qgpu_agg_op
-  int kind;        // AccKind
-  int out_phys;    // Phys of the output column
-  int sum_scale;   // AVG decimal
-  int target_scale;
-  int target_prec;
-  int compat_avg;  // validate the pre-division value (reference quirk Q5)
-  int no_input;    // ungrouped aggregate over zero input batches
-  const unsigned long long* lo;
-  const unsigned long long* hi;
-  const unsigned long long* cnt;
-  void* out;
-  uint32_t* out_valid;
-};
-
-__device__ __forceinline__ double key_to_f64(long long k) {
-  union { long long i; double d; } c;
-  c.i = k ^ (long long)(((unsigned long long)(k >> 63)) >> 1);
-  return c.d;
-}
-
-// high word of an accumulator: stored, or (hi == nullptr) the sign extension of lo (0 for f64 / unsigned kinds)
-__device__ __forceinline__ unsigned long long fin_hi(const FinSpec& f, int64_t g, unsigned long long lo) {
-  if (f.hi) return f.hi[g];
-  if (f.kind == AK_SUM_F64 || f.kind == AK_MIN_F64 || f.kind == AK_MAX_F64 || f.kind == AK_MIN_U64 || f.kind == AK_MAX_U64) return 0;
-  return ((long long)lo < 0) ? ~0ull : 0ull;
-}
-
 struct FinAll {
   int n_aggs;
   int pad;
@@ -342,84 +314,14 @@ __global__ void __launch_bounds__(256) k_agg_finalize(const __grid_constant__ Fi
     const int64_t pos = (w << 5) + lane;
     bool valid = false;
     unsigned long long lo = 0, hi = 0;
-    if (pos < n_groups) {
-      const int64_t g = all.order ? all.order[pos] : pos;
-      const unsigned long long cnt = f.cnt[g];
-      switch (f.op) {
-        case QGPU_AGG_COUNT:
-          lo = cnt;
-          valid = true;
-          break;
-        case QGPU_AGG_SUM:
-          valid = cnt > 0;
-          lo = f.lo[g];
-          hi = fin_hi(f, g, lo);
-          break;
-        case QGPU_AGG_MIN:
-        case QGPU_AGG_MAX:
-          // an all-NULL input leaves the type's MAX/MIN sentinel, not NULL
-          valid = !f.no_input;
-          lo = f.lo[g];
-          hi = fin_hi(f, g, lo);
-          if (f.kind == AK_MIN_F64 || f.kind == AK_MAX_F64) {
-            union { unsigned long long u; double d; } c;
-            c.d = key_to_f64((long long)lo);
-            lo = c.u;
-          }
-          break;
-        case QGPU_AGG_AVG:
-          if (cnt > 0) {
-            if (f.kind == AK_SUM_F64) {
-              union { unsigned long long u; double d; } c;
-              c.u = f.lo[g];
-              c.d = c.d / (double)cnt;
-              lo = c.u;
-              valid = true;
-            } else {
-              // avg.rs:89-116: value = sum * 10^(target_scale - sum_scale) (checked); result = value / count
-              i128 sum = (i128)(((u128)fin_hi(f, g, f.lo[g]) << 64) | (u128)f.lo[g]);
-              i128 mul = pow10_i128(f.target_scale - f.sum_scale);
-              i128 value = sum * mul;
-              bool ovf = sum != 0 && value / mul != sum;
-              if (!ovf && f.compat_avg && !dec_fits_precision(value, f.target_prec)) ovf = true;
-              if (ovf) {
-                // the reference yields a NULL of type Decimal128(38,10) which then fails the schema check
-                if (f.compat_avg) raise_err(err, EE_DEC_PRECISION);
-                else if (sum != 0 && value / mul != sum) raise_err(err, EE_OVERFLOW);
-              } else {
-                i128 q = value / (i128)cnt;
-                lo = (unsigned long long)(u128)q;
-                hi = (unsigned long long)((u128)q >> 64);
-                valid = true;
-              }
-            }
-          }
-          break;
-      }
-    }
+    if (pos < n_groups) valid = fin_value(f, all.order ? all.order[pos] : pos, err, &lo, &hi);
     const uint32_t vw = __ballot_sync(0xffffffffu, valid);
     if (lane == 0) {
       f.out_valid[w] = vw;
       int live = (int)min((int64_t)32, n_groups - (w << 5));
       if (live - __popc(vw)) atomicAdd(null_count, (unsigned long long)(live - __popc(vw)));
     }
-    if (pos < n_groups) {
-      if (!valid) lo = hi = 0;
-      switch (f.out_phys) {
-        case PH_I8: case PH_U8: ((uint8_t*)f.out)[pos] = (uint8_t)lo; break;
-        case PH_I16: case PH_U16: ((uint16_t*)f.out)[pos] = (uint16_t)lo; break;
-        case PH_I32: case PH_U32: ((uint32_t*)f.out)[pos] = (uint32_t)lo; break;
-        case PH_I64: case PH_U64: case PH_F64: ((unsigned long long*)f.out)[pos] = lo; break;
-        case PH_F32: {
-          union { unsigned long long u; double d; } c;
-          c.u = lo;
-          ((float*)f.out)[pos] = (float)c.d;
-          break;
-        }
-        case PH_I128: ((ulonglong2*)f.out)[pos] = make_ulonglong2(lo, hi); break;
-        default: break;
-      }
-    }
+    if (pos < n_groups) fin_store(f, pos, lo, hi);
   }
 }
 
@@ -442,7 +344,7 @@ __global__ void __launch_bounds__(1024) k_rank_order(const long long* __restrict
   }
 }
 
-static Phys out_phys_of(const DType& t) {
+Phys out_phys_of(const DType& t) {
   switch (t.id) {
     case QGPU_T_INT8: return PH_I8;
     case QGPU_T_INT16: return PH_I16;
@@ -455,6 +357,8 @@ static Phys out_phys_of(const DType& t) {
     case QGPU_T_FLOAT32: return PH_F32;
     case QGPU_T_FLOAT64: return PH_F64;
     case QGPU_T_DECIMAL128: return PH_I128;
+    case QGPU_T_UTF8: return PH_STR;
+    case QGPU_T_BOOL: return PH_BIT;
     default: return PH_NULL;
   }
 }

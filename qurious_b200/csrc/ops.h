@@ -76,6 +76,9 @@ Schema build_join_schema(const Schema& left, const Schema& right, int join_type)
 // An ungrouped MIN/MAX over zero qualifying rows returns exactly this value.
 void minmax_sentinel(const DType& at, bool is_min, unsigned long long* lo, unsigned long long* hi);
 
+// physical layout of an output column of logical type `t` (canonical Arrow layout)
+Phys out_phys_of(const DType& t);
+
 // validation helpers shared with the fused paths
 void validate_agg_types(const std::vector<AggSpec>& aggs);
 void check_hash_key_type(const DType& t);

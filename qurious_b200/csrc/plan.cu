@@ -1,6 +1,7 @@
 // Plan execution + table consolidation + the extern "C" surface declared in include/qgpu.h.
 #include <cstring>
 
+#include "comm.h"
 #include "launch.h"
 #include "plan.h"
 
@@ -20,6 +21,7 @@ __global__ void k_widen_chunk(const int64_t* __restrict__ src, ulonglong2* __res
 }
 
 void TableImpl::consolidate() {
+  resolve();  // result table of an asynchronous execute: its row count is needed from here on
   if (consolidated) return;
   const size_t nf = schema.fields.size();
   cols.assign(nf, nullptr);
@@ -173,6 +175,14 @@ View scan_view(PlanNode& n) {
   return v;
 }
 
+// a child's result with its metadata resolved (row count / NULL counts known on the host): what every operator but a
+// pure column Projection needs
+View PlanNode::child_view(int i) {
+  View v = children[i]->execute();
+  v.resolve();
+  return v;
+}
+
 View PlanNode::execute() {
   switch (kind) {
     case PK_SCAN: {
@@ -187,7 +197,7 @@ View PlanNode::execute() {
       return v;
     }
     case PK_FILTER: {
-      View in = children[0]->execute();
+      View in = child_view(0);
       auto c = compile_expr(*predicate, in.schema);
       IdxP sel = eval_filter(ctx, *c, in);
       strategy = "filter(selection-vector)";
@@ -195,7 +205,18 @@ View PlanNode::execute() {
     }
     case PK_PROJECTION: {
       View in = children[0]->execute();
+      if (in.pending) {
+        // result metadata still in flight (dense fused aggregate): a Projection of plain columns only re-orders column
+        // handles and passes the pending metadata on; anything computed needs the row count now
+        bool pure = exprs.size() == schema.fields.size();
+        for (size_t i = 0; pure && i < exprs.size(); ++i) {
+          auto c = compile_expr(*exprs[i], in.schema);
+          pure = c->is_column_ref && c->result_type == schema.fields[i].type;
+        }
+        if (!pure) in.resolve();
+      }
       View out;
+      out.pending = in.pending;
       out.schema = schema;
       out.num_rows = in.num_rows;
       out.num_batches = in.num_batches;
@@ -220,7 +241,7 @@ View PlanNode::execute() {
       View fused;
       if (try_fused_scan_aggregate(*this, &fused)) return fused;
       if (try_fused_join_aggregate(*this, &fused)) return fused;
-      View in = children[0]->execute();
+      View in = child_view(0);
       std::vector<std::shared_ptr<Compiled>> keys;
       for (auto& e : group_exprs) keys.push_back(compile_expr(*e, in.schema));
       std::vector<AggSpec> specs;
@@ -236,11 +257,11 @@ View PlanNode::execute() {
       return run_aggregate(ctx, in, keys, specs, schema, defer);
     }
     case PK_SORT: {
-      View in = children[0]->execute();
+      View in = child_view(0);
       return run_sort(*this, in);
     }
     case PK_LIMIT: {
-      View in = children[0]->execute();
+      View in = child_view(0);
       return run_limit(*this, in);
     }
     case PK_HASH_JOIN: {
@@ -248,8 +269,8 @@ View PlanNode::execute() {
         View uj;
         if (fused_unordered_join(*this, &uj)) return uj;
       }
-      View l = children[0]->execute();
-      View r = children[1]->execute();
+      View l = child_view(0);
+      View r = child_view(1);
       std::vector<std::shared_ptr<Compiled>> lo, ro;
       for (auto& e : left_on) lo.push_back(compile_expr(*e, l.schema));
       for (auto& e : right_on) ro.push_back(compile_expr(*e, r.schema));
@@ -264,8 +285,8 @@ View PlanNode::execute() {
       return run_hash_join(ctx, l, r, join_type, lo, ro, has_join_filter ? &fs : nullptr, schema);
     }
     case PK_NL_JOIN: {
-      View l = children[0]->execute();
-      View r = children[1]->execute();
+      View l = child_view(0);
+      View r = child_view(1);
       JoinFilterSpec fs;
       if (has_join_filter) {
         fs.schema = join_filter_schema;
@@ -383,6 +404,12 @@ void qgpu_shutdown(qgpu_ctx* ctx) {
     if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
   }
   if (c->pinned_scratch) cudaFreeHost(c->pinned_scratch);
+  for (MetaSlot* m : c->meta_slots) {
+    cudaFreeHost(m->host);
+    cudaEventDestroy(m->ev);
+    delete m;
+  }
+  c->comm.reset();
   cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->copy_stream);
   delete ctx;
@@ -475,7 +502,18 @@ int qgpu_table_append(qgpu_table* t, struct ArrowArray* batch, const int32_t* up
 }
 int qgpu_table_append_device(qgpu_table* t, struct ArrowArray* batch) { return table_append(t, batch, nullptr, 0, true); }
 
-int64_t qgpu_table_num_rows(const qgpu_table* t) { return t ? t->t->num_rows : -1; }
+int64_t qgpu_table_num_rows(const qgpu_table* t) {
+  if (!t) return -1;
+  if (t->t->pending) {  // result of an asynchronous execute: wait for its metadata (errors of the producing kernels surface here)
+    if (guard(t->t->ctx, [&] { t->t->resolve(); }) != QGPU_OK) return -1;
+  }
+  return t->t->num_rows;
+}
+
+int qgpu_table_wait(qgpu_table* t) {
+  if (!t) return QGPU_ERR_INTERNAL;
+  return guard(t->t->ctx, [&] { t->t->resolve(); });
+}
 int64_t qgpu_table_num_batches(const qgpu_table* t) { return t ? t->t->num_batches : -1; }
 
 int64_t qgpu_table_column_bytes(const qgpu_table* t, int32_t col) {
@@ -765,6 +803,7 @@ int qgpu_plan_execute(qgpu_plan* p, struct ArrowArrayStream* out) {
   return guard(n.ctx, [&] {
     Timer tm(n.ctx);
     View v = n.execute();
+    v.resolve();
     tm.stop(n);
     std::vector<ArrowArray> batches;
     if (v.num_batches > 0) {
@@ -796,6 +835,7 @@ int qgpu_plan_execute_merged(qgpu_plan* p, const void* gathered, int32_t n_state
   PlanNode& n = *p->node;
   return guard(n.ctx, [&] {
     View v = shard_execute_merged(n, gathered, n_states, max_groups);
+    v.resolve();
     std::vector<ArrowArray> batches;
     if (v.num_batches > 0) {
       std::vector<DColP> cols = materialize_view(n.ctx, v);
@@ -820,6 +860,7 @@ int qgpu_plan_execute_merged_device(qgpu_plan* p, const void* gathered, int32_t 
   PlanNode& n = *p->node;
   return guard(n.ctx, [&] {
     View v = shard_execute_merged(n, gathered, n_states, max_groups);
+    v.resolve();
     auto t = std::make_shared<TableImpl>();
     t->ctx = n.ctx;
     t->schema = n.schema;
@@ -864,6 +905,22 @@ int qgpu_plan_exchange_finish(qgpu_plan* p, int32_t* overflow) {
   return guard(n.ctx, [&] { *overflow = radix_exchange_finish(n); });
 }
 
+// the result View of a plan as an HBM-resident table; `async`: the metadata may still be pending
+static std::shared_ptr<TableImpl> view_to_table(PlanNode& n, View& v, bool async) {
+  if (!async) v.resolve();
+  auto t = std::make_shared<TableImpl>();
+  t->ctx = n.ctx;
+  t->schema = n.schema;
+  t->num_rows = v.num_rows;
+  t->num_batches = v.num_batches;
+  for (size_t i = 0; i < v.cols.size(); ++i) {
+    if (!v.cols[i].base) t->cols.push_back(nullptr);
+    else t->cols.push_back(materialize(n.ctx, v.cols[i], v.num_rows));  // pending results carry no index vectors: handles only
+  }
+  t->pending = v.pending;
+  return t;
+}
+
 int qgpu_plan_execute_device(qgpu_plan* p, qgpu_table** out, int64_t* out_batches) {
   if (!p || !out) return QGPU_ERR_INTERNAL;
   PlanNode& n = *p->node;
@@ -872,18 +929,106 @@ int qgpu_plan_execute_device(qgpu_plan* p, qgpu_table** out, int64_t* out_batche
     Timer tm(n.ctx);
     View v = n.execute();
     n.ctx->trace("execute_device: plan");
-    auto t = std::make_shared<TableImpl>();
-    t->ctx = n.ctx;
-    t->schema = n.schema;
-    t->num_rows = v.num_rows;
-    t->num_batches = v.num_batches;
-    for (size_t i = 0; i < v.cols.size(); ++i) {
-      if (!v.cols[i].base) t->cols.push_back(nullptr);
-      else t->cols.push_back(materialize(n.ctx, v.cols[i], v.num_rows));
-    }
+    auto t = view_to_table(n, v, false);
     n.ctx->trace("execute_device: materialize result");
     tm.stop(n);
     if (out_batches) *out_batches = v.num_batches;
+    *out = new qgpu_table{t};
+  });
+}
+
+int qgpu_plan_execute_device_async(qgpu_plan* p, qgpu_table** out) {
+  if (!p || !out) return QGPU_ERR_INTERNAL;
+  PlanNode& n = *p->node;
+  return guard(n.ctx, [&] {
+    const int64_t l0 = n.ctx->launches;
+    View v = n.execute();
+    auto t = view_to_table(n, v, true);
+    n.last_launches = n.ctx->launches - l0;
+    *out = new qgpu_table{t};
+  });
+}
+
+// ---- multi-GPU: communicator + sharded execution below the ABI ---------------------------------------------------------------
+int qgpu_comm_unique_id(void* out, int64_t cap) {
+  if (!out || cap < 128) return QGPU_ERR_INTERNAL;
+  try {
+    comm_unique_id(out);
+    return QGPU_OK;
+  } catch (QError& e) {
+    g_last_error = e.what();
+    return e.code;
+  }
+}
+
+int qgpu_comm_init(qgpu_ctx* ctx, const void* unique_id, int32_t rank, int32_t world) {
+  if (!ctx || !unique_id) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] { comm_init(&ctx->c, unique_id, rank, world); });
+}
+
+int qgpu_comm_init_local(qgpu_ctx** ctxs, int32_t n) {
+  if (!ctxs || n < 1) return QGPU_ERR_INTERNAL;
+  return guard(&ctxs[0]->c, [&] {
+    std::vector<Ctx*> cs;
+    for (int i = 0; i < n; ++i) cs.push_back(&ctxs[i]->c);
+    comm_init_local(cs.data(), n);
+  });
+}
+
+int qgpu_comm_destroy(qgpu_ctx* ctx) {
+  if (!ctx) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] { comm_destroy(&ctx->c); });
+}
+
+int qgpu_comm_world(const qgpu_ctx* ctx, int32_t* rank, int32_t* world) {
+  if (!ctx) return QGPU_ERR_INTERNAL;
+  if (rank) *rank = ctx->c.comm ? ctx->c.comm->rank : 0;
+  if (world) *world = ctx->c.comm ? ctx->c.comm->world : 1;
+  return QGPU_OK;
+}
+
+int qgpu_comm_all_gather(qgpu_ctx* ctx, const void* send_device, void* recv_device, int64_t bytes_per_rank) {
+  if (!ctx || !send_device || !recv_device || bytes_per_rank < 0) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] { comm_all_gather(&ctx->c, send_device, recv_device, (size_t)bytes_per_rank); });
+}
+
+int qgpu_comm_all_to_all(qgpu_ctx* ctx, const void* send_device, const int64_t* send_offsets, const int64_t* send_bytes, void* recv_device,
+                         const int64_t* recv_offsets, const int64_t* recv_bytes) {
+  if (!ctx || !send_offsets || !send_bytes || !recv_offsets || !recv_bytes) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] { comm_all_to_all(&ctx->c, send_device, send_offsets, send_bytes, recv_device, recv_offsets, recv_bytes); });
+}
+
+int qgpu_comm_barrier(qgpu_ctx* ctx) {
+  if (!ctx) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] { comm_barrier(&ctx->c); });
+}
+
+int qgpu_plan_execute_sharded(qgpu_plan* p, int64_t row_offset, int32_t max_groups, struct ArrowArrayStream* out) {
+  if (!p || !out) return QGPU_ERR_INTERNAL;
+  PlanNode& n = *p->node;
+  return guard(n.ctx, [&] {
+    Timer tm(n.ctx);
+    View v = shard_execute_fused(n, row_offset, max_groups);
+    v.resolve();
+    tm.stop(n);
+    std::vector<ArrowArray> batches;
+    if (v.num_batches > 0) {
+      std::vector<DColP> cols = materialize_view(n.ctx, v);
+      batches.resize(1);
+      export_batch(n.ctx, v.schema, cols, v.num_rows, &batches[0]);
+    }
+    make_stream(n.schema, std::move(batches), out);
+  });
+}
+
+int qgpu_plan_execute_sharded_device(qgpu_plan* p, int64_t row_offset, int32_t max_groups, int32_t async, qgpu_table** out) {
+  if (!p || !out) return QGPU_ERR_INTERNAL;
+  PlanNode& n = *p->node;
+  return guard(n.ctx, [&] {
+    const int64_t l0 = n.ctx->launches;
+    View v = shard_execute_fused(n, row_offset, max_groups);
+    auto t = view_to_table(n, v, async != 0);
+    n.last_launches = n.ctx->launches - l0;
     *out = new qgpu_table{t};
   });
 }

@@ -52,6 +52,7 @@ struct PlanNode {
   std::shared_ptr<AggPending> shard_pending;  // kept between qgpu_plan_partial_state and qgpu_plan_execute_merged  // fused.cu: analysis of this Aggregate <- (Filter)* <- Scan subtree
 
   View execute();
+  View child_view(int i);  // children[i]->execute() with the result metadata resolved
 };
 
 // the (unfiltered) view of a Scan node's table: consolidates appended batches, applies the projection
@@ -62,6 +63,7 @@ PlanNode* find_aggregate_node(PlanNode& root);
 void shard_partial_state(PlanNode& root, int64_t row_offset, int32_t max_groups, void* out_buf, int64_t cap_bytes);
 int64_t shard_state_bytes(PlanNode& root, int32_t max_groups);
 View shard_execute_merged(PlanNode& root, const void* gathered, int32_t n_states, int32_t max_groups);
+View shard_execute_fused(PlanNode& root, int64_t row_offset, int32_t max_groups);
 
 // fused.cu: multi-GPU exchange of a radix-partitioned group-by (see radix_exchange_* there)
 void radix_exchange_keystats(PlanNode& root, int64_t* stats, int32_t* n_keys);
@@ -79,6 +81,7 @@ std::shared_ptr<TableImpl> hash_partition_table(TableImpl& t, int key_col, int n
 // fused.cu: returns true and fills `out` when the aggregate over this input can run as one fused
 // scan+filter+aggregate pipeline kernel.
 bool try_fused_scan_aggregate(PlanNode& agg, View* out);
+bool try_fused_scan_aggregate_sharded(PlanNode& agg, int64_t row_offset, int max_groups, View* out);
 // an Inner join with unique integer build keys as ONE probe-scan kernel emitting (build row, probe row) pairs in
 // arbitrary order; only where the order does not matter (build sides of fused join-aggregates, order_free nodes)
 bool fused_unordered_join(PlanNode& join, View* out);

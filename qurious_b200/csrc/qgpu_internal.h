@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -86,6 +87,8 @@ struct Schema {
 // device memory
 // ----------------------------------------------------------------------------------------------
 struct Ctx;
+struct Comm;         // comm.h: NCCL communicator + symmetric peer buffers (multi-GPU)
+struct MetaSlot;     // pending.h
 struct DBuf {
   Ctx* ctx = nullptr;
   void* ptr = nullptr;
@@ -174,11 +177,45 @@ struct LazyCol {
   IdxP idx;    // null = identity
 };
 
+// Result metadata that is still on its way from the device (row count, NULL counts, error code of the producing
+// kernels): the single-CTA epilogue of the dense fused path writes a small block that is copied to a pinned slot
+// behind the kernels; whoever needs the numbers calls resolve() -- one event wait, no stream synchronisation.  Until
+// then View::num_rows / DCol::length are UPPER BOUNDS (buffers are sized for them).
+struct MetaSlot {
+  unsigned long long* host = nullptr;  // pinned, META_WORDS words
+  cudaEvent_t ev = nullptr;
+  bool busy = false;
+};
+constexpr int META_WORDS = 64;
+struct Pending {
+  Ctx* ctx = nullptr;
+  MetaSlot* slot = nullptr;
+  bool done = false;
+  int err_code = 0;
+  std::string err_msg;
+  int64_t num_rows = 0;
+  // patches the result columns from the metadata words and sets num_rows; may throw QError
+  std::function<void(const unsigned long long*, Pending&)> apply;
+  void resolve();
+  ~Pending();
+};
+typedef std::shared_ptr<Pending> PendingP;
+// queues the copy of `words` metadata words at `dev_meta` into a pinned slot on ctx->stream (+ an event)
+PendingP make_pending(Ctx* ctx, const void* dev_meta, int words, std::function<void(const unsigned long long*, Pending&)> apply);
+
 struct View {
   Schema schema;
   std::vector<LazyCol> cols;
   int64_t num_rows = 0;
   int64_t num_batches = 1;  // how many RecordBatches the reference would have returned
+  PendingP pending;         // non-null: num_rows and the columns' lengths / NULL counts are bounds until resolve()
+  void resolve() {
+    if (!pending) return;
+    PendingP p = pending;
+    pending.reset();
+    p->resolve();
+    num_rows = p->num_rows;
+  }
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -215,6 +252,11 @@ struct Ctx {
   int prof_begin(const char* name);
   void prof_end(int slot);
   std::string prof_report();  // "name\tlaunches\ttotal_ms\tmax_ms\n" per kernel; resets the log
+
+  bool epi_attr_set = false;   // epilogue.cu: dynamic shared memory opt-in done on this device
+  std::shared_ptr<Comm> comm;  // set by qgpu_comm_init / qgpu_comm_init_local
+  // pinned result-metadata slots of asynchronous executions (pending.h)
+  std::vector<MetaSlot*> meta_slots;
 
   // QGPU_TRACE=1: synchronising wall-clock marks printed to stderr (debug aid, never on in benchmarks)
   void trace(const char* what);
@@ -256,6 +298,14 @@ struct TableImpl {
   bool consolidated = true;
   int64_t num_rows = 0;
   int64_t num_batches = 0;
+  PendingP pending;  // result table of an asynchronous execute: see View::pending
+  void resolve() {
+    if (!pending) return;
+    PendingP p = pending;
+    pending.reset();
+    p->resolve();
+    num_rows = p->num_rows;
+  }
   void consolidate();
 };
 }  // namespace qgpu

@@ -17,6 +17,8 @@
 #include <algorithm>
 #include <cstring>
 
+#include "comm.h"
+#include "epilogue.h"
 #include "launch.h"
 #include "plan.h"
 
@@ -452,6 +454,39 @@ View shard_execute_merged(PlanNode& root, const void* gathered, int32_t n_states
   for (auto& c : key_cols) c->length = merged.num_rows;
   agg->merged_override = std::make_shared<View>(merged);
   agg->strategy = "sharded-merge(" + std::to_string(n_states) + " states) <- " + agg->strategy;
+  return root.execute();
+}
+
+// Whole sharded step below the C ABI: shard-local aggregate -> state block -> peer exchange + exact merge + finalisation
+// in ONE kernel (epilogue.cu) -> the operators above the aggregate.  DENSE-eligible plans (Q1 / Q6) run as scan kernel +
+// epilogue; everything else packs its generic accumulators (k_pack_records) into the same block format first, so ranks
+// whose shards chose different local strategies still merge.  The result's metadata is pending (View::pending).
+View shard_execute_fused(PlanNode& root, int64_t row_offset, int32_t max_groups) {
+  PlanNode* agg = find_aggregate_node(root);
+  Ctx* ctx = agg->ctx;
+  if (!ctx->comm) throw QError(QGPU_ERR_NCCL, "NcclError: no communicator: call qgpu_comm_init first");
+  if (max_groups < 1 || max_groups > EPI_MAXG) throw_internal("max_groups must be in [1, 4096]");
+  agg->merged_override.reset();
+  View merged;
+  if (!try_fused_scan_aggregate_sharded(*agg, row_offset, max_groups, &merged)) {
+    const int nk = (int)agg->group_exprs.size(), na = (int)agg->aggs.size();
+    if (nk > EPI_MAXK || na > EPI_MAXAGG) throw_internal("too many keys / aggregates for sharded execution");
+    const int64_t need = shard_state_bytes(root, max_groups);
+    DBufP rec = ctx->alloc((size_t)need);
+    shard_partial_state(root, row_offset, max_groups, rec->ptr, need);
+    std::shared_ptr<AggPending> pend = agg->shard_pending;
+    if (!pend || !pend->set)
+      throw_internal("sharded execution: the local shard must have at least one batch (CREATE TABLE without INSERT cannot take part)");
+    std::vector<DType> key_types;
+    for (auto& k : pend->keys) key_types.push_back(k->result_type);
+    EpiParams E;
+    memset(&E, 0, sizeof(E));
+    E.src = EPI_SRC_PACKED;
+    epilogue_describe(ctx, key_types, pend->specs, pend->accs.kind, agg->schema, E);
+    merged = epilogue_execute(ctx, E, key_types, pend->specs, agg->schema, true, row_offset, max_groups, rec);
+    agg->strategy = "sharded[state block -> peer exchange + merge over " + std::to_string(ctx->comm->world) + " ranks] <- " + agg->strategy;
+  }
+  agg->merged_override = std::make_shared<View>(merged);
   return root.execute();
 }
 

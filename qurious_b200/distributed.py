@@ -2,9 +2,10 @@
 torch.distributed for the plumbing.  The reference is single-process, so nothing here mirrors a reference file;
 the merge itself is exact and happens on the GPU inside libqgpu (csrc/shard.cu):
 
-    every rank:  partial state of (Projection* <- Aggregate <- Scan(shard))      qgpu_plan_partial_state
-    NCCL:        all-gather of the fixed-size state blocks                       dist.all_gather_into_tensor
-    every rank:  merge the gathered states + finalise (AVG division, order...)   qgpu_plan_execute_merged
+    every rank:  shard-local aggregate of (Projection* <- Aggregate <- Scan(shard)), then ONE kernel: state block ->
+                 peer stores into every rank's symmetric buffer (NVLink) -> epoch-flag barrier -> exact merge ->
+                 finalise (AVG division, order...)                                qgpu_plan_execute_sharded
+    (hosts with their own collectives: qgpu_plan_partial_state / all-gather / qgpu_plan_execute_merged)
 
 No compute happens in Python.  `row_offset` is the global index of the shard's first row: it keeps the
 first-occurrence output order identical to a single-GPU run over the whole table.
@@ -26,13 +27,35 @@ def shard_range(total_rows: int, rank: int, world: int):
     return (total_rows * rank) // world, (total_rows * (rank + 1)) // world
 
 
+def init_comm(ctx: _lib.Context) -> None:
+    """Create the library-owned communicator of `ctx` (qgpu_comm_init): rank 0's NCCL unique id travels over the
+    already-initialised torch.distributed process group (any side channel would do: a file, MPI, the host's own RPC)."""
+    import torch.distributed as dist
+    if ctx.comm_world()[1] > 1:
+        return
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [ctx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx.comm_init(box[0], rank, world)
+
+
 class ShardedAggregate:
-    """plan: (Projection|Filter)* <- HashAggregate/NoGroupingAggregate <- ... over THIS rank's shard."""
+    """plan: (Projection|Filter)* <- HashAggregate/NoGroupingAggregate <- ... over THIS rank's shard.
+
+    Default (all_gather=None): the whole step runs below the C ABI (qgpu_plan_execute_sharded*): shard-local aggregate,
+    then ONE kernel that stores the state block into every peer's buffer over NVLink, waits on the peers' flags, merges
+    and finalises.  With an explicit `all_gather` callable the three-call protocol (partial_state / caller's all-gather /
+    execute_merged) is used instead -- hosts with their own collective layer, and the single-GPU emulation in the tests."""
 
     def __init__(self, ctx: _lib.Context, plan, row_offset: int, world: int, max_groups: int = 64,
                  all_gather: Optional[Callable[[torch.Tensor, torch.Tensor], None]] = None):
         self.ctx, self.plan, self.row_offset, self.world, self.max_groups = ctx, plan, int(row_offset), int(world), int(max_groups)
         _, self.h, _ = plan._native_cached(ctx)
+        self.fused = all_gather is None
+        if self.fused:
+            if ctx.comm_world()[1] != self.world:
+                init_comm(ctx)
+            return
         n = ctypes.c_int64()
         ctx.check(ctx.lib.qgpu_plan_state_bytes(self.h, self.max_groups, ctypes.byref(n)))
         self.state_bytes = n.value
@@ -40,11 +63,6 @@ class ShardedAggregate:
         self.state = torch.zeros(self.state_bytes, dtype=torch.uint8, device=dev)
         self.gathered = torch.zeros(self.state_bytes * self.world, dtype=torch.uint8, device=dev)
         self.stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
-        if all_gather is None:
-            import torch.distributed as dist
-
-            def all_gather(out, inp):
-                dist.all_gather_into_tensor(out, inp)
         self.all_gather = all_gather
         torch.cuda.synchronize(dev)  # the zero-fills above ran on torch's stream
 
@@ -62,17 +80,29 @@ class ShardedAggregate:
         return _lib.read_stream(self.ctx, out)
 
     def execute(self) -> List[pa.RecordBatch]:
+        if self.fused:
+            out = _lib.new_stream()
+            self.ctx.check(self.ctx.lib.qgpu_plan_execute_sharded(self.h, self.row_offset, self.max_groups, _lib.addr(out)))
+            self.plan._record_stats(self.ctx, self.h)
+            return _lib.read_stream(self.ctx, out)
         self.partial()
         with torch.cuda.stream(self.stream):       # the collective is ordered after the library's stream work
             self.all_gather(self.gathered, self.state)
         return self.merge(self.gathered, self.world)
 
-    def execute_device(self) -> _lib.DeviceTable:
-        """Like execute(), the merged result stays in HBM."""
+    def execute_device(self, wait: bool = True) -> _lib.DeviceTable:
+        """Like execute(), the merged result stays in HBM.  wait=False (fused protocol only): returns once the kernels are
+        queued; DeviceTable.wait() / .num_rows wait for the metadata."""
+        out = ctypes.c_void_p()
+        if self.fused:
+            self.ctx.check(self.ctx.lib.qgpu_plan_execute_sharded_device(self.h, self.row_offset, self.max_groups,
+                                                                         0 if wait else 1, ctypes.byref(out)))
+            if wait:
+                self.plan._record_stats(self.ctx, self.h)
+            return _lib.DeviceTable(self.ctx, out, self.plan.schema)
         self.partial()
         with torch.cuda.stream(self.stream):
             self.all_gather(self.gathered, self.state)
-        out = ctypes.c_void_p()
         self.ctx.check(self.ctx.lib.qgpu_plan_execute_merged_device(self.h, self.gathered.data_ptr(), self.world, self.max_groups,
                                                                     ctypes.byref(out)))
         self.plan._record_stats(self.ctx, self.h)

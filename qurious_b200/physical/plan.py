@@ -145,6 +145,14 @@ class PhysicalPlan:
         t.reference_num_batches = nb.value
         return t
 
+    def execute_device_async(self, ctx: Optional[_lib.Context] = None) -> "_lib.DeviceTable":
+        """qgpu_plan_execute_device_async: returns once the kernels are queued; `DeviceTable.wait()` / `.num_rows` wait
+        for the result metadata (and raise the producing kernels' errors)."""
+        ctx, h, keep = self._native_cached(ctx)
+        out = ctypes.c_void_p()
+        ctx.check(ctx.lib.qgpu_plan_execute_device_async(h, ctypes.byref(out)))
+        return _lib.DeviceTable(ctx, out, self.schema)
+
     def set_order_free(self, on: bool = True, ctx: Optional[_lib.Context] = None):
         """The consumer does not depend on this plan's output row order (qgpu_plan_set_order_free): lets an Inner join
         below Projection/Filter operators run as one unordered probe-scan kernel.  Not part of the reference's API."""
