@@ -43,7 +43,7 @@ constexpr int F_R = F_T / F_NT;
 constexpr int F_MAXC = 10, F_MAXP = 8, F_MAXK = 4, F_MAXA = 8, F_MAXF = 3;
 constexpr int F_SMEM_MAX = 232448 - 1024;  // 227 KB opt-in limit minus static slack
 enum { FK_SUM = 0, FK_MIN = 1, FK_MAX = 2, FK_SUMF = 3 };
-enum { FM_DENSE = 0, FM_HASH = 1, FM_PROBE = 2, FM_EMIT = 3 };
+enum { FM_DENSE = 0, FM_HASH = 1, FM_PROBE = 2, FM_EMIT = 3, FM_BUILD = 4 };
 #define F_EMPTY 0xffffffffffffffffULL
 
 struct FCol {
@@ -103,6 +103,9 @@ struct FParams {
   uint64_t jt_kspan;
   const void* bkey;
   int32_t bkey_width, pad_probe;
+  // FM_BUILD: the same table / bitmap, writable
+  unsigned long long* jt_wslots;
+  uint32_t* jt_wbitmap;
   // accumulator word of (accumulator k, slot g) = g_lo[acc_base + k * acc_kstride + g * acc_gstride]
   //   HASH : array of records {key, acc[0..n_accs), count, first row, pad} (acc_base 1, kstride 1, gstride = record words):
   //          one 64 B record per group => one cache line per row instead of one per accumulator
@@ -346,6 +349,40 @@ struct GenericBody {
 #pragma unroll
         for (int j = 0; j < F_R; ++j) fr[j] = row0 + j * F_NT + tid;
         dense_update<FK_MIN>(a, (uint32_t)(p.n_accs + 1) * F_NT, fr, 0u, rep);  // the representative is the smallest row
+      } else if (MODE == FM_BUILD) {
+        // ---- join BUILD over the filtered scan (hash_join.rs:148-175 build_hash_table): every qualifying row claims a
+        // slot of the HBM-resident linear-probing table (slot = hash tag | row + 1, atomicCAS) and sets its bit of the
+        // membership bitmap; an equal key already present raises the duplicate flag (the fused probes need unique keys).
+        // No selection vector, no gathered key column: the table holds BASE-table rows and the key column is the base's.
+#pragma unroll
+        for (int j = 0; j < F_R; ++j) {
+          if (!((pass >> j) & 1)) continue;
+          const int64_t key = (int64_t)code[j];
+          const uint64_t h = fmix64((uint64_t)key);
+          const uint32_t tag = (uint32_t)(h >> 32);
+          const unsigned long long mine = ((unsigned long long)tag << 32) | (unsigned long long)(row0 + j * F_NT + tid + 1);
+          if (p.jt_wbitmap) {
+            const uint64_t kk = (uint64_t)key - (uint64_t)p.jt_kmin;
+            atomicOr(&p.jt_wbitmap[kk >> 5], 1u << (kk & 31));
+          }
+          uint64_t sl = h & p.jt_mask;
+          while (true) {
+            unsigned long long cur = *(volatile unsigned long long*)&p.jt_wslots[sl];
+            if (cur == 0) {
+              cur = atomicCAS(&p.jt_wslots[sl], 0ull, mine);
+              if (cur == 0) break;
+            }
+            if ((uint32_t)(cur >> 32) == tag) {
+              const uint64_t other = (cur & 0xffffffffull) - 1;
+              const int64_t ok = p.bkey_width == 8 ? ((const long long*)p.bkey)[other] : (int64_t)((const int*)p.bkey)[other];
+              if (ok == key) {
+                *p.abort_flag = 1;
+                break;
+              }
+            }
+            sl = (sl + 1) & p.jt_mask;
+          }
+        }
       } else {
         // ---- HBM-resident open-addressing table on the packed key -------------------------------------------
         uint64_t slot[F_R];
@@ -669,7 +706,7 @@ __device__ __forceinline__ void fused_main(const FParams& p) {
 // DENSE keeps one CTA per SM (its private tables fill shared memory); the table-probing modes run two (HASH) or
 // three (join probes) CTAs per SM to hide the latency of their random HBM/L2 accesses
 template <int MODE>
-__global__ void __launch_bounds__(F_NT + 32, MODE == FM_DENSE ? 1 : (MODE == FM_HASH ? 2 : 3)) k_fused_scan_agg(const __grid_constant__ FParams p) {
+__global__ void __launch_bounds__(F_NT + 32, MODE == FM_DENSE ? 1 : (MODE == FM_HASH ? 2 : 3)) k_fused_scan_agg(const __grid_constant__ FParams p) {  // FM_BUILD: like the probes
   fused_main<MODE, GenericBody<MODE>>(p);
 }
 
@@ -1092,6 +1129,7 @@ __global__ void k_dict_codes(const uint16_t* __restrict__ row_slot, const uint8_
 // than 255 distinct values, NULLs, or rows beyond the u32 representative-row range.
 static bool ensure_dict(Ctx* ctx, DCol& col) {
   if (col.dict_state != 0) return col.dict_state > 0;
+  SpecSuspend cached_work(ctx);
   col.dict_state = -1;
   if (col.phys != PH_STR || col.null_count != 0 || col.length == 0 || col.length >= 0xfffffff0LL) return false;
   const int64_t n = col.length;
@@ -1406,6 +1444,7 @@ struct ProbeOpts {
 static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& predicates, const View& v, FusedPlan& fp,
                           const ProbeOpts* probe = nullptr) {
   Ctx* ctx = agg.ctx;
+  SpecSuspend cached_work(ctx);  // the analysis is cached on the plan node
   auto agg_expr = [&](size_t i) -> const ExprNode& { return probe ? *probe->agg_exprs[i] : *agg.aggs[i].expr; };
   const bool emit = probe && probe->emit;
   if (!emit) {
@@ -2074,6 +2113,7 @@ static DenseRun* prepare_dense(PlanNode& agg, FusedPlan& fp) {
   auto d = std::make_shared<DenseRun>();
   fp.dense = d;
   Ctx* ctx = agg.ctx;
+  SpecSuspend cached_work(ctx);
   const FParams& P = fp.P;
   const int nk = (int)fp.keys.size(), na = (int)fp.specs.size();
   if (P.mode != FM_DENSE || getenv("QGPU_NO_EPILOGUE")) return nullptr;
@@ -2382,7 +2422,10 @@ static DBufP join_key_bitmap(Ctx* ctx, const LazyCol& key, int64_t nb, int64_t* 
   *kmin = 0;
   *kspan = 0;
   if (nb <= 0 || !key.base || getenv("QGPU_NO_JOIN_BITMAP")) return nullptr;
-  ensure_stats(ctx, *key.base);
+  {
+    SpecSuspend cached_work(ctx);
+    ensure_stats(ctx, *key.base);
+  }
   if (!key.base->has_stats) return nullptr;
   const i128 range = key.base->vmax - key.base->vmin + 1;
   if (range <= 0 || range > ((i128)1 << 31) || key.base->vmin < -(LIM62 * 2) || key.base->vmax > LIM62 * 2 - 1) return nullptr;
@@ -2454,6 +2497,125 @@ std::unique_ptr<ExprNode> clone_shift(const ExprNode& n, int shift, bool* ok) {
 bool int_like_key(const DCol& c) { return c.phys == PH_I64 || c.phys == PH_I32 || c.phys == PH_D64; }
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// The build side of a fused probe: HBM-resident linear-probing table over the build key (+ membership bitmap).
+//   (i)  build side = (Filter)* <- Scan with range / dictionary predicates: ONE scan kernel (FM_BUILD) evaluates the
+//        predicate and inserts the qualifying rows -- no selection vector, no gathered key column; the table holds
+//        base-table rows;
+//   (ii) anything else: the build side's operators run, its key column is gathered, k_join_build_unique inserts it.
+// false: the fused probes cannot use this build side (non-integer key, duplicate keys, >= 2^32 rows).
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct JoinTable {
+  View bv;          // build-side columns, addressed by the row ids stored in the table
+  int64_t nb = 0;   // build rows (bound of the row ids)
+  DColP bkey;       // key column indexed by build row (null when nb == 0)
+  DBufP slots, bitmap, dup;
+  int64_t cap = 0, kmin = 0;
+  uint64_t kspan = 0;
+  std::string how;
+  void bind(FParams& P) const {
+    P.jt_slots = (const unsigned long long*)slots->ptr;
+    P.jt_mask = (uint64_t)(cap - 1);
+    P.jt_bitmap = bitmap ? (const uint32_t*)bitmap->ptr : nullptr;
+    P.jt_kmin = kmin;
+    P.jt_kspan = kspan;
+    P.bkey = nb > 0 ? bkey->data->ptr : slots->ptr;
+    P.bkey_width = nb > 0 ? phys_width(bkey->phys) : 8;
+  }
+};
+}  // namespace
+
+static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& predicates, const View& v, FusedPlan& fp,
+                          const ProbeOpts* probe);
+bool fused_unordered_join(PlanNode& join, View* out);
+
+static bool fused_filtered_build(PlanNode& child, int key_col, JoinTable& jt) {
+  Ctx* ctx = child.ctx;
+  if (getenv("QGPU_NO_FUSED_BUILD")) return false;
+  std::vector<const ExprNode*> predicates;
+  PlanNode* n = &child;
+  while (n->kind == PK_FILTER) {
+    predicates.push_back(n->predicate.get());
+    n = n->children[0].get();
+  }
+  if (n->kind != PK_SCAN) return false;
+  if (n->predicate) predicates.push_back(n->predicate.get());
+  if (predicates.empty()) return false;  // nothing to fuse: (ii) builds straight from the resident key column
+  View pv = scan_view(*n);
+  if (pv.num_batches == 0 || pv.num_rows == 0 || pv.num_rows >= 0xfffffff0LL) return false;
+  if (key_col < 0 || key_col >= (int)pv.cols.size() || !pv.cols[key_col].base) return false;
+  const DCol& kc = *pv.cols[key_col].base;
+  if (!(kc.phys == PH_I64 || kc.phys == PH_I32 || kc.phys == PH_D64) || kc.null_count != 0) return false;
+  std::shared_ptr<FusedPlan> fp = std::static_pointer_cast<FusedPlan>(child.fused_cache);
+  bool fresh = false;
+  if (fp) {
+    fresh = fp->n_rows == pv.num_rows && fp->n_batches == pv.num_batches && fp->col_ids.size() == pv.cols.size();
+    for (size_t i = 0; fresh && i < pv.cols.size(); ++i) fresh = fp->col_ids[i] == pv.cols[i].base.get() && !pv.cols[i].idx;
+  }
+  if (!fresh) {
+    fp = std::make_shared<FusedPlan>();
+    ProbeOpts po;
+    po.emit = true;  // no aggregates: the kernel-side "key" is the build key
+    po.probe_key_col = key_col;
+    PlanNode shell;
+    shell.ctx = ctx;
+    try {
+      fp->usable = analyze_fused(shell, predicates, pv, *fp, &po);
+    } catch (QError&) {
+      fp->usable = false;  // the generic operators raise the error in their own order
+    }
+    fp->n_rows = pv.num_rows;
+    fp->n_batches = pv.num_batches;
+    for (auto& c : pv.cols) fp->col_ids.push_back(c.base.get());
+    child.fused_cache = fp;
+  }
+  if (!fp->usable) return false;
+  jt.bv = pv;
+  jt.nb = pv.num_rows;
+  jt.bkey = pv.cols[key_col].base;
+  jt.cap = 1024;
+  while (jt.cap < 2 * jt.nb) jt.cap <<= 1;
+  jt.slots = ctx->alloc_zero((size_t)jt.cap * 8);
+  jt.dup = ctx->alloc_zero(8);
+  jt.bitmap = join_key_bitmap(ctx, pv.cols[key_col], jt.nb, &jt.kmin, &jt.kspan);
+  FParams P = fp->P;
+  jt.bind(P);
+  P.jt_wslots = (unsigned long long*)jt.slots->ptr;
+  P.jt_wbitmap = jt.bitmap ? (uint32_t*)jt.bitmap->ptr : nullptr;
+  P.abort_flag = (int*)jt.dup->ptr;
+  P.n_groups = (unsigned long long*)((char*)jt.dup->ptr);
+  CUDA_CHECK(cudaFuncSetAttribute(k_fused_scan_agg<FM_BUILD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem_bytes));
+  LAUNCH(ctx, k_fused_scan_agg<FM_BUILD>, fp->grid, F_NT + 32, fp->smem_bytes, P);
+  jt.how = "fused_filtered_build[" + std::to_string(P.n_cols) + " cols, " + std::to_string(P.n_pred) + " range preds]";
+  child.strategy = jt.how;
+  return true;
+}
+
+static bool build_join_table(PlanNode& join, int lk_col, JoinTable& jt) {
+  Ctx* ctx = join.ctx;
+  PlanNode& child = *join.children[0];
+  if (!fused_filtered_build(child, lk_col, jt)) {
+    if (!fused_unordered_join(child, &jt.bv)) jt.bv = join.child_view(0);
+    jt.nb = jt.bv.num_rows;
+    if (jt.nb >= 0xfffffff0LL) return false;
+    jt.bkey = jt.nb > 0 ? materialize(ctx, jt.bv.cols[lk_col], jt.nb) : nullptr;
+    if (jt.nb > 0 && !int_like_key(*jt.bkey)) return false;
+    jt.cap = 1024;
+    while (jt.cap < 2 * jt.nb) jt.cap <<= 1;
+    jt.slots = ctx->alloc_zero((size_t)jt.cap * 8);
+    jt.dup = ctx->alloc_zero(8);
+    jt.bitmap = join_key_bitmap(ctx, jt.bv.cols[lk_col], jt.nb, &jt.kmin, &jt.kspan);
+    if (jt.nb > 0)
+      LAUNCH(ctx, k_join_build_unique, grid_for(ctx, jt.nb, 256), 256, 0, jt.bkey->data->ptr, phys_width(jt.bkey->phys),
+             jt.bkey->validity ? (const uint32_t*)jt.bkey->validity->ptr : nullptr, jt.nb, (unsigned long long*)jt.slots->ptr,
+             (uint64_t)(jt.cap - 1), (int*)jt.dup->ptr, jt.bitmap ? (uint32_t*)jt.bitmap->ptr : nullptr, jt.kmin);
+    jt.how = child.strategy;
+  }
+  if (jt.nb > 0 && ctx->read_count((const int*)jt.dup->ptr, "join_build.dup")) return false;  // duplicate build keys: the generic join runs
+  return true;
+}
+
 // Order-free Inner join used INSIDE a fused pipeline whose consumer does not depend on row order (the build
 // side of try_fused_join_aggregate): HashJoin(Inner, one integer key, no JoinFilter, unique build keys) with a
 // (Filter)* <- Scan probe side.  The probe scan streams through the TMA pipeline (FM_EMIT) and appends
@@ -2503,26 +2665,11 @@ bool fused_unordered_join(PlanNode& join, View* out) {
     join.fused_cache = fp;
   }
   if (!fp->usable) return false;
-  // build side (recursively order-free when it is itself such a join)
-  View bv;
-  if (!fused_unordered_join(*join.children[0], &bv)) bv = join.child_view(0);
-  const int64_t nb = bv.num_rows;
-  if (nb >= 0xfffffff0LL) return false;
-  DColP bkey = nb > 0 ? materialize(ctx, bv.cols[lk.col_index], nb) : nullptr;
-  if (nb > 0 && !int_like_key(*bkey)) return false;
-  int64_t cap = 1024;
-  while (cap < 2 * nb) cap <<= 1;
-  DBufP slots = ctx->alloc_zero((size_t)cap * 8);
-  DBufP dup = ctx->alloc_zero(8);
-  int64_t jt_kmin = 0;
-  uint64_t jt_kspan = 0;
-  DBufP bitmap = join_key_bitmap(ctx, bv.cols[lk.col_index], nb, &jt_kmin, &jt_kspan);
-  if (nb > 0) {
-    LAUNCH(ctx, k_join_build_unique, grid_for(ctx, nb, 256), 256, 0, bkey->data->ptr, phys_width(bkey->phys),
-           bkey->validity ? (const uint32_t*)bkey->validity->ptr : nullptr, nb, (unsigned long long*)slots->ptr, (uint64_t)(cap - 1),
-           (int*)dup->ptr, bitmap ? (uint32_t*)bitmap->ptr : nullptr, jt_kmin);
-    if (ctx->read_scalar((const int*)dup->ptr)) return false;
-  }
+  // build side (a filtered scan builds the table in one kernel; recursively order-free when it is itself such a join)
+  JoinTable jt;
+  if (!build_join_table(join, lk.col_index, jt)) return false;
+  View& bv = jt.bv;
+  const int64_t nb = jt.nb;
   ctx->trace("  emit-join: build side + table");
   FParams P = fp->P;
   auto b_idx = std::make_shared<IdxVec>();
@@ -2534,16 +2681,10 @@ bool fused_unordered_join(PlanNode& join, View* out) {
   P.g_hi = (unsigned long long*)p_idx->buf->ptr;
   P.n_groups = (unsigned long long*)flags->ptr;
   P.abort_flag = (int*)((char*)flags->ptr + 8);
-  P.jt_slots = (const unsigned long long*)slots->ptr;
-  P.jt_mask = (uint64_t)(cap - 1);
-  P.jt_bitmap = bitmap ? (const uint32_t*)bitmap->ptr : nullptr;
-  P.jt_kmin = jt_kmin;
-  P.jt_kspan = jt_kspan;
-  P.bkey = nb > 0 ? bkey->data->ptr : slots->ptr;
-  P.bkey_width = nb > 0 ? phys_width(bkey->phys) : 8;
+  jt.bind(P);
   CUDA_CHECK(cudaFuncSetAttribute(k_fused_scan_agg<FM_EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem_bytes));
   LAUNCH(ctx, k_fused_scan_agg<FM_EMIT>, fp->grid, F_NT + 32, fp->smem_bytes, P);
-  const int64_t n_out = (int64_t)ctx->read_scalar((const unsigned long long*)flags->ptr);
+  const int64_t n_out = (int64_t)ctx->read_count((const unsigned long long*)flags->ptr, "join_emit.pairs");
   ctx->trace("  emit-join: probe kernel");
   b_idx->length = p_idx->length = n_out;
   View v;
@@ -2560,7 +2701,7 @@ bool fused_unordered_join(PlanNode& join, View* out) {
   return true;
 }
 
-bool try_fused_join_aggregate(PlanNode& agg, View* out) {
+static bool join_aggregate_body(PlanNode& agg, View* out) {
   Ctx* ctx = agg.ctx;
   if (agg.defer || agg.group_exprs.empty() || agg.aggs.empty() || (int)agg.aggs.size() > 24) return false;
   PlanNode* join = agg.children[0].get();
@@ -2619,27 +2760,12 @@ bool try_fused_join_aggregate(PlanNode& agg, View* out) {
 
   // ---- build side: ordinary operators, then the join table ------------------------------------------------
   ctx->trace(nullptr);
-  View bv;
-  if (!fused_unordered_join(*join->children[0], &bv)) bv = join->child_view(0);
-  const int64_t nb = bv.num_rows;
-  if (nb >= 0xfffffff0LL) return false;
-  DColP bkey = nb > 0 ? materialize(ctx, bv.cols[lk.col_index], nb) : nullptr;
-  if (nb > 0 && !int_like_key(*bkey)) return false;
   // the probe key must compare like the build key: same logical type (the generic join raises otherwise)
   if (join->children[0]->schema.fields[lk.col_index].type != pv.schema.fields[rk.col_index].type) return false;
-  int64_t cap = 1024;
-  while (cap < 2 * nb) cap <<= 1;
-  DBufP slots = ctx->alloc_zero((size_t)cap * 8);
-  DBufP dup = ctx->alloc_zero(8);
-  int64_t jt_kmin = 0;
-  uint64_t jt_kspan = 0;
-  DBufP bitmap = join_key_bitmap(ctx, bv.cols[lk.col_index], nb, &jt_kmin, &jt_kspan);
-  if (nb > 0) {
-    LAUNCH(ctx, k_join_build_unique, grid_for(ctx, nb, 256), 256, 0, bkey->data->ptr, phys_width(bkey->phys),
-           bkey->validity ? (const uint32_t*)bkey->validity->ptr : nullptr, nb, (unsigned long long*)slots->ptr, (uint64_t)(cap - 1),
-           (int*)dup->ptr, bitmap ? (uint32_t*)bitmap->ptr : nullptr, jt_kmin);
-    if (ctx->read_scalar((const int*)dup->ptr)) return false;  // duplicate build keys: generic join
-  }
+  JoinTable jt;
+  if (!build_join_table(*join, lk.col_index, jt)) return false;
+  View& bv = jt.bv;
+  const int64_t nb = jt.nb;
 
   ctx->trace("join-agg: build side + join table");
   // ---- probe + aggregate ---------------------------------------------------------------------------------------
@@ -2660,13 +2786,7 @@ bool try_fused_join_aggregate(PlanNode& agg, View* out) {
   P.g_hi = g_hi ? (unsigned long long*)g_hi->ptr : nullptr;
   P.n_groups = (unsigned long long*)flags->ptr;
   P.abort_flag = (int*)((char*)flags->ptr + 8);
-  P.jt_slots = (const unsigned long long*)slots->ptr;
-  P.jt_mask = (uint64_t)(cap - 1);
-  P.jt_bitmap = bitmap ? (const uint32_t*)bitmap->ptr : nullptr;
-  P.jt_kmin = jt_kmin;
-  P.jt_kspan = jt_kspan;
-  P.bkey = nb > 0 ? bkey->data->ptr : slots->ptr;
-  P.bkey_width = nb > 0 ? phys_width(bkey->phys) : 8;
+  jt.bind(P);
   P.acc_base = 0;
   P.acc_kstride = n_slots;
   P.acc_gstride = 1;
@@ -2749,14 +2869,71 @@ bool try_fused_join_aggregate(PlanNode& agg, View* out) {
   }
   agg.strategy = "fused_join_probe_agg[unique-build " + std::to_string(nb) + " rows, " + std::to_string(P.n_cols) + " probe cols, " +
                  std::to_string(P.n_pred) + " range preds, " + std::to_string(P.n_accs) + " accs, " + std::to_string(P.stages) +
-                 " TMA stages] <- build[" + join->children[0]->strategy + "]";
-  join->strategy = "fused-into-aggregate <- [" + join->children[0]->strategy + ", probe scan]";
+                 " TMA stages] <- build[" + jt.how + "]";
+  join->strategy = "fused-into-aggregate <- [" + jt.how + ", probe scan]";
   ctx->trace("join-agg: key columns");
   View dummy;
   dummy.schema = js;
-  *out = finish_aggregate(ctx, dummy, keys, specs, agg.schema, accs, &key_cols, nullptr);
+  // asynchronous execution of a replayed pipeline: every count is already on the host (speculated), so the finalise
+  // flags may stay in flight too -- the whole step then never waits for the device
+  const bool defer_flags = ctx->async_ok && ctx->spec && ctx->spec->replay;
+  *out = finish_aggregate(ctx, dummy, keys, specs, agg.schema, accs, &key_cols, nullptr, defer_flags);
   ctx->trace("join-agg: finish_aggregate");
   return true;
+}
+
+// identity of every table scanned below `n` (resident column buffers, row / batch counts): learned counts are only
+// replayed over exactly the tables they were learned on
+static uint64_t subtree_signature(PlanNode& n) {
+  uint64_t h = 0x9e3779b97f4a7c15ULL * (uint64_t)n.kind;
+  auto mix = [&](uint64_t x) { h = (h ^ x) * 0xff51afd7ed558ccdULL; h ^= h >> 29; };
+  if (n.kind == PK_SCAN && n.table) {
+    n.table->consolidate();
+    mix((uint64_t)(uintptr_t)n.table.get());
+    mix((uint64_t)n.table->num_rows);
+    mix((uint64_t)n.table->num_batches);
+    for (auto& c : n.table->cols) mix((uint64_t)(uintptr_t)(c && c->data ? c->data->ptr : nullptr));
+  }
+  for (auto& c : n.children) mix(subtree_signature(*c));
+  return h;
+}
+
+// Speculative re-execution: the first execution of the join pipeline learns its device-side counts (selection sizes,
+// join output size, duplicate flags, group count) with one host round trip each; later executions over the same
+// tables take them from the cache, never wait, and verify all of them after the pipeline's single final
+// synchronisation.  A wrong guess (cannot happen over immutable tables; detected anyway) re-runs in learning mode.
+bool try_fused_join_aggregate(PlanNode& agg, View* out) {
+  Ctx* ctx = agg.ctx;
+  if (ctx->spec) return join_aggregate_body(agg, out);  // already inside an enclosing scope
+  if (!agg.spec) agg.spec = std::make_shared<Speculation>();
+  Speculation& sp = *agg.spec;
+  const uint64_t sig = subtree_signature(agg);
+  if (sig != agg.spec_sig) sp.have = false;
+  agg.spec_sig = sig;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    SpecScope scope(ctx, &sp);
+    const bool replay = sp.replay;
+    bool ok = false;
+    try {
+      View v;
+      ok = join_aggregate_body(agg, &v);
+      if (!replay) {
+        sp.have = ok && !sp.learned.empty();
+        if (ok) *out = v;
+        return ok;
+      }
+      if (ok && v.pending ? scope.defer_verify(v.pending) : scope.verify()) {
+        if (ok) *out = v;
+        return ok;
+      }
+    } catch (SpeculationMiss&) {
+      if (!replay) throw_internal("speculation miss outside a replay (internal error)");
+    } catch (QError&) {
+      if (!replay) throw;  // a replay's error may be an artefact of a wrong guess: learn again, which raises the real one
+    }
+    sp.have = false;
+  }
+  return false;
 }
 
 // analysis (cached on the node) of Aggregate <- (Filter <-)* Scan; null when the subtree has another shape

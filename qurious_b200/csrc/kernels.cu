@@ -76,6 +76,17 @@ DBufP Ctx::alloc_zero(size_t bytes) {
 }
 void Ctx::sync() { CUDA_CHECK(cudaStreamSynchronize(stream)); }
 
+void debug_sync_launch(Ctx* ctx, const char* name) {
+  static int on = -1;
+  if (on < 0) on = getenv("QGPU_SYNC_LAUNCH") ? 1 : 0;
+  if (!on) return;
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "[qgpu] kernel %s failed: %s\n", name, cudaGetErrorString(e));
+    throw QError(QGPU_ERR_CUDA, std::string("CUDA error in ") + name + ": " + cudaGetErrorString(e));
+  }
+}
+
 void Ctx::trace(const char* what) {
   if (trace_on < 0) trace_on = getenv("QGPU_TRACE") ? 1 : 0;
   if (!trace_on) return;
@@ -137,6 +148,50 @@ void Ctx::d2h_sync(void* dst, const void* src, size_t bytes) {
   }
 }
 
+// ---- speculation on device-side counts (qgpu_internal.h: Speculation) ---------------------------------
+SpecScope::SpecScope(Ctx* c, Speculation* s) : ctx(c), sp(s), saved(c->spec) {
+  sp->replay = sp->have && !getenv("QGPU_NO_SPECULATION");
+  sp->cursor = 0;
+  if (sp->replay) {
+    sp->check = ctx->alloc_zero(8 * (size_t)Speculation::kMax);
+  } else {
+    sp->learned.clear();
+    sp->sites.clear();
+    sp->have = false;
+  }
+  ctx->spec = sp;
+}
+bool SpecScope::verify() {
+  if (!sp->replay) return true;
+  bool ok = sp->cursor == sp->learned.size();
+  if (ok && sp->cursor > 0) {
+    std::vector<unsigned long long> got(sp->cursor);
+    ctx->d2h_sync(got.data(), sp->check->ptr, 8 * sp->cursor);
+    ok = memcmp(got.data(), sp->learned.data(), 8 * sp->cursor) == 0;
+  }
+  sp->check.reset();
+  return ok;
+}
+
+bool SpecScope::defer_verify(const PendingP& p) {
+  if (!sp->replay || !p) return verify();
+  if (sp->cursor != sp->learned.size()) {
+    sp->check.reset();
+    return false;
+  }
+  if (sp->cursor > 0) {
+    std::vector<unsigned long long> expect(sp->learned.begin(), sp->learned.begin() + (long)sp->cursor);
+    DBufP keep = sp->check;
+    p->also = make_pending(ctx, sp->check->ptr, (int)sp->cursor, [expect, keep](const unsigned long long* m, Pending&) {
+      if (memcmp(m, expect.data(), expect.size() * 8) != 0)
+        throw_internal("a speculated device-side count of an asynchronous execution did not match (were the plan's tables modified "
+                       "while it ran?); re-run with qgpu_plan_execute_device");
+    });
+  }
+  sp->check.reset();
+  return true;
+}
+
 // ---- asynchronous result metadata (qgpu_internal.h: Pending) ------------------------------------------
 PendingP make_pending(Ctx* ctx, const void* dev_meta, int words, std::function<void(const unsigned long long*, Pending&)> apply) {
   if (words > META_WORDS) throw_internal("metadata block too large");
@@ -163,6 +218,11 @@ PendingP make_pending(Ctx* ctx, const void* dev_meta, int words, std::function<v
   return p;
 }
 void Pending::resolve() {
+  if (also) {
+    PendingP a = also;
+    also.reset();
+    a->resolve();
+  }
   if (!done) {
     done = true;
     cudaError_t e = cudaEventSynchronize(slot->ev);
@@ -312,7 +372,7 @@ int64_t exclusive_scan_i64(Ctx* ctx, const int64_t* in, int64_t* out, int64_t n)
   if (n > (int64_t)SCAN_TILE * 2147483647LL) throw_internal("scan too large");
   DBufP total = ctx->alloc(8);
   scan_rec(ctx, in, out, n, (int64_t*)total->ptr);
-  return ctx->read_scalar((const int64_t*)total->ptr);
+  return ctx->read_count((const int64_t*)total->ptr, "exclusive_scan_i64");
 }
 
 // ================================================================================================
@@ -429,7 +489,7 @@ static Phys result_phys(const DType& t) {
 }
 
 static void check_eval_err(Ctx* ctx, const int* err_dev) {
-  int e = ctx->read_scalar(err_dev);
+  int e = ctx->read_count(err_dev, "check_eval_err");
   if (e) throw_eval_error(e);
 }
 
@@ -679,7 +739,7 @@ DColP take_column(Ctx* ctx, const DCol& base, const int64_t* idx, int64_t n, boo
     if (n > 0)
       LAUNCH(ctx, k_take_bits, g, 256, 0, base.validity ? (const uint32_t*)base.validity->ptr : nullptr, idx,
              (uint32_t*)col->validity->ptr, n, false, (unsigned long long*)zc->ptr);
-    col->null_count = (int64_t)ctx->read_scalar((const unsigned long long*)zc->ptr);
+    col->null_count = (int64_t)ctx->read_count((const unsigned long long*)zc->ptr, "take_column.nulls");
     if (col->null_count == 0) col->validity.reset();
   }
   if (n == 0) {

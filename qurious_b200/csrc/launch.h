@@ -24,11 +24,15 @@ struct KernelScope {
   }
 };
 
+// QGPU_SYNC_LAUNCH=1 (debug aid): synchronise after every launch and name the kernel that faulted
+void debug_sync_launch(Ctx* ctx, const char* name);
+
 #define LAUNCH(ctx, kernel, grid, block, smem, ...)                    \
   do {                                                                 \
     ::qgpu::KernelScope _ks((ctx), #kernel, ::qgpu::grid_blocks(grid)); \
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);   \
     CUDA_CHECK(cudaGetLastError());                                    \
+    ::qgpu::debug_sync_launch((ctx), #kernel);                         \
   } while (0)
 
 static inline int grid_for(Ctx* ctx, int64_t n, int per_block) {

@@ -539,7 +539,8 @@ View run_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<Comp
 }
 
 View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<Compiled>>& keys, std::vector<AggSpec>& aggs,
-                      const Schema& out_schema, GroupAccs& accs, std::vector<DColP>* key_cols, const unsigned long long* key_nulls) {
+                      const Schema& out_schema, GroupAccs& accs, std::vector<DColP>* key_cols, const unsigned long long* key_nulls,
+                      bool allow_pending) {
   const bool grouped = !keys.empty();
   // with a device-side count, `n_max` only sizes the buffers; the real count arrives with the flags below
   const int64_t n_max = accs.n_groups;
@@ -634,8 +635,28 @@ View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<C
     if (key_nulls)
       CUDA_CHECK(cudaMemcpyAsync((char*)flags->ptr + 8 * (MAX_AGGS + 2), key_nulls, 8 * (keys.size() + 1), cudaMemcpyDeviceToDevice,
                                  ctx->stream));  // + one caller-defined word (shard.cu: merge error code)
+    if (allow_pending && !n_dev && !key_nulls) {
+      std::vector<int> ops;
+      for (auto& a : aggs) ops.push_back(a.op);
+      const bool compat_empty = ctx->compat_empty_decimal_sum;
+      const int64_t ng = n_max;
+      out.pending = make_pending(ctx, flags->ptr, MAX_AGGS + 3 + MAX_KEYS, [cols, ops, compat_empty, ng, flags](const unsigned long long* m, Pending& P) {
+        if ((int)m[0]) throw_eval_error((int)m[0]);
+        for (size_t i = 0; i < cols.size(); ++i) {
+          DCol& c = *cols[i];
+          c.null_count = (int64_t)m[1 + i];
+          if (c.null_count == 0) c.validity.reset();
+          if (c.null_count > 0 && ops[i] == QGPU_AGG_SUM && c.type.is_decimal() && compat_empty)
+            throw_arrow("column types must match schema types, expected " + c.type.str() + " but found Decimal128(38, 10)");
+          if (c.null_count > 0 && (ops[i] == QGPU_AGG_MIN || ops[i] == QGPU_AGG_MAX) && compat_empty)
+            throw_arrow("column types must match schema types, expected " + c.type.str() + " but found Null");
+        }
+        P.num_rows = ng;
+      });
+    }
     unsigned long long h[MAX_AGGS + 3 + MAX_KEYS];
-    ctx->d2h_sync(h, flags->ptr, 8 * (MAX_AGGS + 3 + MAX_KEYS));
+    memset(h, 0, sizeof(h));
+    if (!out.pending) ctx->d2h_sync(h, flags->ptr, 8 * (MAX_AGGS + 3 + MAX_KEYS));
     if (key_nulls) accs.side_word = h[MAX_AGGS + 2 + keys.size()];
     if ((int)h[0]) throw_eval_error((int)h[0]);
     for (size_t i = 0; i < aggs.size(); ++i) cols[i]->null_count = (int64_t)h[1 + i];
@@ -676,6 +697,10 @@ View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<C
     AggSpec& a = aggs[i];
     DColP& col = cols[i];
     col->length = n_groups;
+    if (out.pending) {  // NULL counts still in flight: the validity buffers stay until resolve()
+      out.cols.push_back({col, nullptr});
+      continue;
+    }
     if (col->null_count == 0) col->validity.reset();
     if (col->null_count > 0 && a.op == QGPU_AGG_SUM && col->type.is_decimal() && ctx->compat_empty_decimal_sum)
       throw_arrow("column types must match schema types, expected " + col->type.str() + " but found Decimal128(38, 10)");

@@ -38,7 +38,9 @@ struct GroupAccs {
 // key_nulls: device u64[n_keys] NULL counts of those columns, fetched together with the other flags.
 View finish_aggregate(Ctx* ctx, const View& input, std::vector<std::shared_ptr<Compiled>>& keys, std::vector<AggSpec>& aggs,
                       const Schema& out_schema, GroupAccs& accs, std::vector<DColP>* key_cols = nullptr,
-                      const unsigned long long* key_nulls = nullptr);
+                      const unsigned long long* key_nulls = nullptr, bool allow_pending = false);
+// allow_pending: when the group count is already exact on the host, the error code and the aggregates' NULL counts
+// may stay in flight (View::pending) instead of costing a host round trip here
 
 // An aggregate stopped right before finalisation: per-group accumulator state + what finish_aggregate needs.
 struct AggPending {

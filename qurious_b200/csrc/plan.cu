@@ -368,9 +368,26 @@ int qgpu_init(const int* devices, int n, qgpu_ctx** out) {
     CUDA_CHECK(cudaSetDevice(dev));
     CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    CUDA_CHECK(cudaDeviceGetDefaultMemPool(&c->pool, dev));
+    // One stream-ordered pool PER CONTEXT: contexts of one process (ranks emulated on one GPU, several qurious sessions)
+    // must not share a pool -- the driver may make an allocation on one context's stream wait for a free that is still
+    // queued on another's, and a peer-exchange kernel waiting for that other context would never see it arrive.
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    CUDA_CHECK(cudaMemPoolCreate(&c->pool, &props));
     uint64_t thr = UINT64_MAX;
     CUDA_CHECK(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    // pinned slots for asynchronous result metadata: allocated up front (a page-locked allocation while a peer-exchange
+    // kernel of another context spins may synchronise with it)
+    for (int i = 0; i < 8; ++i) {
+      MetaSlot* m = new MetaSlot();
+      CUDA_CHECK(cudaHostAlloc((void**)&m->host, META_WORDS * 8, cudaHostAllocDefault));
+      CUDA_CHECK(cudaEventCreateWithFlags(&m->ev, cudaEventDisableTiming));
+      c->meta_slots.push_back(m);
+    }
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
     c->sm_count = prop.multiProcessorCount;
@@ -412,6 +429,7 @@ void qgpu_shutdown(qgpu_ctx* ctx) {
   c->comm.reset();
   cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->copy_stream);
+  if (c->pool) cudaMemPoolDestroy(c->pool);
   delete ctx;
 }
 
@@ -434,6 +452,7 @@ int qgpu_release_cached_memory(qgpu_ctx* ctx) {
   return guard(&ctx->c, [&] {
     ctx->c.release_big_blocks();
     ctx->c.sync();
+    CUDA_CHECK(cudaMemPoolTrimTo(ctx->c.pool, 0));  // back to the driver: other allocators of the process can use it
   });
 }
 
@@ -942,6 +961,11 @@ int qgpu_plan_execute_device_async(qgpu_plan* p, qgpu_table** out) {
   PlanNode& n = *p->node;
   return guard(n.ctx, [&] {
     const int64_t l0 = n.ctx->launches;
+    struct AsyncOk {
+      Ctx* c;
+      explicit AsyncOk(Ctx* x) : c(x) { c->async_ok = true; }
+      ~AsyncOk() { c->async_ok = false; }
+    } scope(n.ctx);
     View v = n.execute();
     auto t = view_to_table(n, v, true);
     n.last_launches = n.ctx->launches - l0;

@@ -45,6 +45,8 @@ struct PlanNode {
   std::string strategy = "not-executed";
   std::string strategy_desc;
   std::shared_ptr<void> fused_cache;
+  std::shared_ptr<Speculation> spec;  // learned device-side counts of this subtree's fused pipeline (fused.cu)
+  uint64_t spec_sig = 0;              // identity of the scanned tables the counts were learned on
   bool order_free = false;  // the consumer does not depend on this node's output row order (qgpu_plan_set_order_free)
   // sharded execution (shard.cu): stop before finalisation / resume from merged states
   AggPending* defer = nullptr;

@@ -10,6 +10,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include <functional>
 #include <memory>
@@ -186,7 +187,7 @@ struct MetaSlot {
   cudaEvent_t ev = nullptr;
   bool busy = false;
 };
-constexpr int META_WORDS = 64;
+constexpr int META_WORDS = 128;
 struct Pending {
   Ctx* ctx = nullptr;
   MetaSlot* slot = nullptr;
@@ -196,6 +197,7 @@ struct Pending {
   int64_t num_rows = 0;
   // patches the result columns from the metadata words and sets num_rows; may throw QError
   std::function<void(const unsigned long long*, Pending&)> apply;
+  std::shared_ptr<Pending> also;  // resolved first (deferred verification of speculated counts)
   void resolve();
   ~Pending();
 };
@@ -253,6 +255,7 @@ struct Ctx {
   void prof_end(int slot);
   std::string prof_report();  // "name\tlaunches\ttotal_ms\tmax_ms\n" per kernel; resets the log
 
+  bool async_ok = false;       // inside qgpu_plan_execute_device_async: operators may leave result metadata pending
   bool epi_attr_set = false;   // epilogue.cu: dynamic shared memory opt-in done on this device
   std::shared_ptr<Comm> comm;  // set by qgpu_comm_init / qgpu_comm_init_local
   // pinned result-metadata slots of asynchronous executions (pending.h)
@@ -278,6 +281,68 @@ struct Ctx {
     d2h_sync(&v, dptr, sizeof(T));
     return v;
   }
+  // A device-side COUNT (selection size, join output size, group count, duplicate / error flag) the host needs to size
+  // the next buffers and launches.  Outside a speculation scope this is read_scalar (one host round trip).  Inside one
+  // (Speculation, below) the first execution of a cached plan learns the values; re-executions over the same immutable
+  // tables take the learned value immediately, queue a copy of the actual device word for later verification and keep
+  // the stream busy -- the whole pipeline then synchronises once, at its end.
+  template <typename T>
+  T read_count(const T* dptr, const char* site);  // site: names the call site; a replay that reaches another one re-learns
+  struct Speculation* spec = nullptr;
+};
+
+struct Speculation {
+  static const int kMax = 96;
+  bool have = false;    // `learned` holds the counts of a complete earlier execution
+  bool replay = false;  // this execution takes learned counts and verifies them at the end
+  std::vector<unsigned long long> learned;  // raw bits (zero-extended), in call order
+  std::vector<const char*> sites;           // call site of every learned count
+  size_t cursor = 0;
+  DBufP check;          // replay: the actual device words, one per read
+};
+struct SpeculationMiss {};  // a replay reached a count it did not learn (other call site / more reads): re-run in learning mode
+// Work whose result is CACHED across executions (plan analysis, dictionary encoding, column statistics) runs outside the
+// speculation: its counts are read once, not once per execution
+struct SpecSuspend {
+  Ctx* ctx;
+  Speculation* saved;
+  explicit SpecSuspend(Ctx* c) : ctx(c), saved(c->spec) { c->spec = nullptr; }
+  ~SpecSuspend() { ctx->spec = saved; }
+};
+
+template <typename T>
+T Ctx::read_count(const T* dptr, const char* site) {
+  static_assert(sizeof(T) <= 8, "counts are at most 64 bits");
+  Speculation* sp = spec;
+  if (!sp) return read_scalar(dptr);
+  if (!sp->replay) {
+    const T v = read_scalar(dptr);
+    unsigned long long bits = 0;
+    memcpy(&bits, &v, sizeof(T));
+    sp->learned.push_back(bits);
+    sp->sites.push_back(site);
+    return v;
+  }
+  if (sp->cursor >= sp->learned.size() || sp->cursor >= (size_t)Speculation::kMax || sp->sites[sp->cursor] != site) throw SpeculationMiss();
+  CUDA_CHECK(cudaMemcpyAsync((char*)sp->check->ptr + 8 * sp->cursor, dptr, sizeof(T), cudaMemcpyDeviceToDevice, stream));
+  T v;
+  memcpy(&v, &sp->learned[sp->cursor], sizeof(T));
+  sp->cursor++;
+  return v;
+}
+
+// RAII: runs the enclosed host code under `sp` (learning or replaying); verify() after the pipeline's final
+// synchronisation tells whether every speculated count was right
+struct SpecScope {
+  Ctx* ctx;
+  Speculation* sp;
+  Speculation* saved;
+  SpecScope(Ctx* c, Speculation* s);
+  ~SpecScope() { ctx->spec = saved; }
+  bool verify();
+  // replay only: the comparison of the actual counts with the speculated ones rides with `p` (resolved before it); a
+  // mismatch is an InternalError there.  false: the replay already diverged on the host (read fewer / more counts)
+  bool defer_verify(const PendingP& p);
 };
 
 // ----------------------------------------------------------------------------------------------
