@@ -486,8 +486,8 @@ def run_query_device(ctx, step, steps, warmup, sampler, torch, stream):
         step()
         if i < len(marks):
             marks[i].record(stream)
+    drain()                      # the last results are awaited inside the timed region: their epilogues run on the library's side stream
     e1.record(stream)
-    drain()                      # the last results are consumed inside the timed region as well
     torch.cuda.synchronize()
     sampler.region(False)
     barrier()

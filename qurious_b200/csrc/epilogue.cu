@@ -31,45 +31,64 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
+// shared-memory layout for `cap` records / groups (dynamic: the small cases -- Q1: 4 groups x 8 ranks -- leave room for a
+// scan CTA of the NEXT execution on the same SM, so the epilogue overlaps it; see run_dense in fused.cu)
 struct EpiSmem {
-  int pre[EPI_NT];
-  long long first[EPI_MAXG];        // merged group -> first row
-  unsigned int pos[EPI_MAXG];       // gathered record -> word offset inside this rank's symmetric buffer
-  unsigned short slot[EPI_MAXG];    // local group -> dense slot
-  unsigned short leader[EPI_MAXG];  // gathered record -> first record with the same key
-  unsigned short gid[EPI_MAXG];     // leader record -> merged group
-  unsigned short order[EPI_MAXG];   // output position -> merged group
-  unsigned long long nulls[EPI_MAXAGG];
-  unsigned long long key_nulls[EPI_MAXK];
-  int base[COMM_MAX_WORLD + 1];
-  int n_local, n_rec, n_groups, eval_err, x_err;
+  long long* first;        // merged group -> first row                                   [cap]
+  unsigned int* pos;       // gathered record -> word offset in this rank's buffer        [cap]
+  int* pre;                // compaction prefix                                           [EPI_NT]
+  unsigned short* slot;    // local group -> dense slot                                   [cap]
+  unsigned short* leader;  // gathered record -> first record with the same key           [cap]
+  unsigned short* gid;     // leader record -> merged group                               [cap]
+  unsigned short* order;   // output position -> merged group                             [cap]
+  unsigned long long* nulls;      // [EPI_MAXAGG]
+  unsigned long long* key_nulls;  // [EPI_MAXK]
+  int* base;               // [COMM_MAX_WORLD + 1]
+  int* scalars;            // n_local, n_rec, n_groups, eval_err, x_err
+  __device__ EpiSmem(unsigned char* raw, int cap) {
+    first = (long long*)raw;
+    nulls = (unsigned long long*)(first + cap);
+    key_nulls = nulls + EPI_MAXAGG;
+    pos = (unsigned int*)(key_nulls + EPI_MAXK);
+    pre = (int*)(pos + cap);
+    base = pre + EPI_NT;
+    scalars = base + COMM_MAX_WORLD + 1;
+    slot = (unsigned short*)(scalars + 7);
+    leader = slot + cap;
+    gid = leader + cap;
+    order = gid + cap;
+  }
 };
-
 }  // namespace
 
 __global__ void __launch_bounds__(EPI_NT) k_dense_epilogue(const __grid_constant__ EpiParams p) {
   extern __shared__ __align__(16) unsigned char epi_smem_raw[];
-  EpiSmem& s = *reinterpret_cast<EpiSmem*>(epi_smem_raw);
+  EpiSmem s(epi_smem_raw, p.smem_cap);
+  int& s_n_local = s.scalars[0];
+  int& s_n_rec = s.scalars[1];
+  int& s_n_groups = s.scalars[2];
+  int& s_eval_err = s.scalars[3];
+  int& s_x_err = s.scalars[4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NA2 = p.n_accs + 2;
   const int nk = p.n_keys, rw = p.rw;
   const int off_first = 3 * nk, off_agg = 3 * nk + 1;  // record: keys | first row | n_aggs x {lo, hi, count}
 
   if (tid == 0) {
-    s.eval_err = 0;
-    s.x_err = 0;
+    s_eval_err = 0;
+    s_x_err = 0;
   }
   if (tid < EPI_MAXAGG) s.nulls[tid] = 0;
   if (tid < EPI_MAXK) s.key_nulls[tid] = 0;
 
   // ---- A: occupied slots ---------------------------------------------------------------------------------------
   if (p.src == EPI_SRC_PACKED) {
-    if (tid == 0) s.n_local = (int)p.rec[1] + (p.rec[4] ? p.max_groups + 1 : 0);  // k_pack_records filled the block
+    if (tid == 0) s_n_local = (int)p.rec[1] + (p.rec[4] ? p.max_groups + 1 : 0);  // k_pack_records filled the block
     __syncthreads();
   } else if (!p.grouped) {
     if (tid == 0) {
       s.slot[0] = 0;  // the single group is exported even when no row qualified (NULL sums, MIN/MAX start values)
-      s.n_local = 1;
+      s_n_local = 1;
     }
     __syncthreads();
   } else {
@@ -94,10 +113,10 @@ __global__ void __launch_bounds__(EPI_NT) k_dense_epilogue(const __grid_constant
     int o = s.pre[tid] - c;
     for (int i = 0; i < per; ++i)
       if ((mask >> i) & 1) s.slot[o++] = (unsigned short)(b0 + i);
-    if (tid == EPI_NT - 1) s.n_local = s.pre[EPI_NT - 1];
+    if (tid == EPI_NT - 1) s_n_local = s.pre[EPI_NT - 1];
     __syncthreads();
   }
-  const int n_local = s.n_local;
+  const int n_local = s_n_local;
   const int n_send = min(n_local, p.max_groups);
 
   // ---- B: state block --------------------------------------------------------------------------------------------
@@ -183,7 +202,7 @@ __global__ void __launch_bounds__(EPI_NT) k_dense_epilogue(const __grid_constant
       while (ld_acquire_sys(f) != p.epoch) {
         __nanosleep(64);
         if (((++spins) & 1023u) == 0 && global_ns() - t0 > p.timeout_ns) {
-          atomicMax(&s.x_err, (int)EPI_ERR_TIMEOUT);
+          atomicMax(&s_x_err, (int)EPI_ERR_TIMEOUT);
           break;
         }
       }
@@ -192,7 +211,7 @@ __global__ void __launch_bounds__(EPI_NT) k_dense_epilogue(const __grid_constant
     // ---- M: merge ------------------------------------------------------------------------------------------------
     const volatile unsigned long long* in = p.peer[p.rank] + flag_words + (size_t)parity * p.world * slot_words;
     if (tid == 0) {
-      int t = 0, bad = s.x_err;
+      int t = 0, bad = s_x_err;
       for (int r = 0; r < p.world && !bad; ++r) {
         const volatile unsigned long long* h = in + (size_t)r * slot_words;
         s.base[r] = t;
@@ -200,14 +219,14 @@ __global__ void __launch_bounds__(EPI_NT) k_dense_epilogue(const __grid_constant
         else if (h[4]) bad = EPI_ERR_OVERFLOW;
         else t += (int)h[1];
       }
-      if (!bad && t > EPI_MAXG) bad = EPI_ERR_TOO_MANY;
+      if (!bad && t > p.smem_cap) bad = EPI_ERR_TOO_MANY;
       s.base[p.world] = bad ? 0 : t;
-      s.n_rec = bad ? 0 : t;
-      s.x_err = bad;
+      s_n_rec = bad ? 0 : t;
+      s_x_err = bad;
     }
     __syncthreads();
-    const int M = s.n_rec;
-    x_err = s.x_err;
+    const int M = s_n_rec;
+    x_err = s_x_err;
     for (int r = 0; r < p.world && M > 0; ++r) {
       const int n = s.base[r + 1] - s.base[r];
       for (int g = tid; g < n; g += EPI_NT) s.pos[s.base[r] + g] = (unsigned int)((size_t)r * slot_words + EPI_HDR + (size_t)g * rw);
@@ -233,14 +252,14 @@ __global__ void __launch_bounds__(EPI_NT) k_dense_epilogue(const __grid_constant
       for (int i = 0; i < M; ++i)
         if (s.leader[i] == i) s.gid[i] = (unsigned short)ng++;
       if (ng > p.g_max) {
-        s.x_err = EPI_ERR_TOO_MANY;
+        s_x_err = EPI_ERR_TOO_MANY;
         ng = 0;
       }
-      s.n_groups = ng;
+      s_n_groups = ng;
     }
     __syncthreads();
-    G = s.n_groups;
-    x_err = s.x_err;
+    G = s_n_groups;
+    x_err = s_x_err;
     // one thread per merged group folds that group's records in (rank, slot) order: deterministic
     for (int i = tid; i < M && G > 0; i += EPI_NT) {
       if (s.leader[i] != i) continue;
@@ -320,7 +339,7 @@ __global__ void __launch_bounds__(EPI_NT) k_dense_epilogue(const __grid_constant
     unsigned long long lo = 0, hi = 0;
     if (pos < G) {
       const int t = s.order[pos];
-      valid = fin_value(f, t, &s.eval_err, &lo, &hi);
+      valid = fin_value(f, t, &s_eval_err, &lo, &hi);
     }
     const uint32_t vw = __ballot_sync(0xffffffffu, valid);
     if (lane == 0) {
@@ -380,7 +399,7 @@ __global__ void __launch_bounds__(EPI_NT) k_dense_epilogue(const __grid_constant
   __syncthreads();
   if (tid == 0) {
     p.meta[0] = (unsigned long long)G;
-    p.meta[1] = (unsigned long long)s.eval_err;
+    p.meta[1] = (unsigned long long)s_eval_err;
     p.meta[2] = (unsigned long long)x_err;
   }
   if (tid < p.n_aggs) p.meta[3 + tid] = s.nulls[tid];
@@ -394,14 +413,23 @@ __global__ void __launch_bounds__(EPI_NT) k_dense_epilogue(const __grid_constant
   }
 }
 
-size_t epilogue_smem_bytes() { return sizeof(EpiSmem); }
+size_t epilogue_smem_bytes(int cap) {
+  return (size_t)cap * (8 + 4 + 4 * 2) + (EPI_MAXAGG + EPI_MAXK) * 8 + (EPI_NT + COMM_MAX_WORLD + 1 + 7) * 4 + 64;
+}
 
 void launch_dense_epilogue(Ctx* ctx, const EpiParams& p) {
-  if (!ctx->epi_attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_dense_epilogue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EpiSmem)));
-    ctx->epi_attr_set = true;
+  const size_t smem = epilogue_smem_bytes(p.smem_cap);
+  if (smem > ctx->epi_smem_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_dense_epilogue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 << 10)));
+    ctx->epi_smem_set = std::max<size_t>(smem, 48 << 10);
   }
-  LAUNCH(ctx, k_dense_epilogue, 1, EPI_NT, sizeof(EpiSmem), p);
+  // on the epilogue stream, behind everything queued on the compute stream so far
+  CUDA_CHECK(cudaEventRecord(ctx->epi_ready, ctx->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(ctx->epi_stream, ctx->epi_ready, 0));
+  ctx->launches++;
+  k_dense_epilogue<<<1, EPI_NT, smem, ctx->epi_stream>>>(p);
+  CUDA_CHECK(cudaGetLastError());
+  debug_sync_launch(ctx, "k_dense_epilogue");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -459,6 +487,8 @@ View epilogue_execute(Ctx* ctx, EpiParams E, const std::vector<DType>& key_types
   E.max_groups = max_groups;
   E.g_max = E.grouped ? (int)std::min<int64_t>((int64_t)EPI_MAXG, (int64_t)E.world * max_groups) : 1;
   E.row_offset = row_offset;
+  // the shared-memory arrays hold up to world x max_groups gathered records (ungrouped: one record per rank)
+  E.smem_cap = std::max(std::max(E.g_max, max_groups), (int)std::min<int64_t>((int64_t)EPI_MAXG, (int64_t)E.world * max_groups));
   const size_t rec_words = (size_t)EPI_HDR + (size_t)max_groups * E.rw;
   if (comm && rec_words * 8 > COMM_SLOT_BYTES)
     throw_internal("sharded aggregate: the state block of " + std::to_string(max_groups) + " groups exceeds the " +
@@ -476,6 +506,8 @@ View epilogue_execute(Ctx* ctx, EpiParams E, const std::vector<DType>& key_types
   for (int a = 0; a < na; ++a)
     total += Slab::need((size_t)g * std::max(phys_width((Phys)E.agg[a].out_phys), 1) + 16) + Slab::need(words * 4 + 4);
   Slab slab(ctx, total, false);
+  slab.buf->free_stream = ctx->epi_stream;  // last written by the epilogue: freed in that stream's order
+  if (packed_rec) packed_rec->free_stream = ctx->epi_stream;
   DBufP meta = slab.take(EPI_META_WORDS * 8);
   E.meta = (unsigned long long*)meta->ptr;
   DBufP rec = packed_rec ? packed_rec : slab.take(rec_words * 8);
@@ -560,7 +592,7 @@ View epilogue_execute(Ctx* ctx, EpiParams E, const std::vector<DType>& key_types
         throw_arrow("column types must match schema types, expected " + c.type.str() + " but found Null");
     }
     P.num_rows = G;
-  });
+  }, ctx->epi_stream);
   return out;
 }
 

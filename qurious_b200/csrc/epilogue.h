@@ -16,7 +16,7 @@
 
 namespace qgpu {
 
-constexpr int EPI_NT = 1024;
+constexpr int EPI_NT = 256;     // small enough (registers) to share an SM with a CTA of the next scan
 constexpr int EPI_MAXG = 4096;   // groups (and gathered records) one epilogue CTA handles
 constexpr int EPI_MAXK = 8, EPI_MAXACC = 8, EPI_MAXAGG = 24;
 constexpr int EPI_HDR = 8;       // state block header words: magic, n records, n_keys, n_accs, overflow, record words
@@ -52,6 +52,7 @@ struct EpiParams {
   unsigned long long* g_hi;
   int n_slots, n_accs, n_keys, n_aggs;
   int src;                             // EPI_SRC_DENSE: records come from the table above; EPI_SRC_PACKED: `rec` is already filled
+  int smem_cap;                        // capacity the shared-memory arrays are laid out for (>= max_groups, g_max, gathered records)
   int grouped, max_groups, g_max, rw;  // max_groups: records one rank may send; g_max: output capacity; rw: record words
   long long row_offset;                // global index of this shard's first row (first-occurrence order across shards)
   long long init[EPI_MAXACC + 2];      // the table is re-initialised for the next execution
@@ -71,7 +72,7 @@ struct EpiParams {
   unsigned long long* peer[8];
 };
 
-size_t epilogue_smem_bytes();
+size_t epilogue_smem_bytes(int cap);
 void launch_dense_epilogue(Ctx* ctx, const EpiParams& p);
 
 // FinSpec static fields / accumulator kinds / typed MIN-MAX start values of every aggregate (+ the RecordBatch::try_new

@@ -2087,8 +2087,16 @@ static bool run_radix(PlanNode& agg, const View& v, FusedPlan& fp, View* out) {
 namespace {
 struct DenseRun {
   bool eligible = false;
-  bool inited = false;
-  DBufP g_lo, g_hi;
+  // TWO accumulator tables used alternately: the epilogue of execution i (epilogue stream) still reads and re-initialises
+  // table i & 1 while the scan kernel of execution i + 1 (compute stream) already fills the other one
+  bool inited[2] = {false, false};
+  DBufP g_lo[2], g_hi[2];
+  cudaEvent_t epi_done[2] = {nullptr, nullptr};  // recorded on the epilogue stream behind the epilogue that used table b
+  uint64_t runs = 0;
+  ~DenseRun() {
+    for (cudaEvent_t e : epi_done)
+      if (e) cudaEventDestroy(e);
+  }
   std::vector<DBufP> keep;  // dictionary strings on the device
   std::vector<DType> key_types;
   std::vector<int> kinds;   // AccKind per aggregate
@@ -2172,19 +2180,24 @@ static View run_dense(PlanNode& agg, FusedPlan& fp, DenseRun& D, bool sharded, i
   EpiParams E = D.E;
   epilogue_describe(ctx, D.key_types, fp.specs, D.kinds, agg.schema, E);  // type checks (RecordBatch::try_new) before any launch
   const int NA2 = P.n_accs + 2;
-  if (!D.g_lo) {
-    D.g_lo = ctx->alloc((size_t)P.dense_groups * NA2 * 8);
-    D.g_hi = ctx->alloc((size_t)P.dense_groups * NA2 * 8);
+  const int b = (int)(D.runs++ & 1);
+  if (!D.g_lo[b]) {
+    D.g_lo[b] = ctx->alloc((size_t)P.dense_groups * NA2 * 8);
+    D.g_hi[b] = ctx->alloc((size_t)P.dense_groups * NA2 * 8);
+    D.g_lo[b]->free_stream = D.g_hi[b]->free_stream = ctx->epi_stream;  // the last epilogue re-initialises them
+    CUDA_CHECK(cudaEventCreateWithFlags(&D.epi_done[b], cudaEventDisableTiming));
+  } else {
+    CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, D.epi_done[b], 0));  // the epilogue two executions ago has reset this table
   }
-  if (!D.inited) {
+  if (!D.inited[b]) {
     FInit init;
     for (int k = 0; k < NA2; ++k) init.v[k] = E.init[k];
-    LAUNCH(ctx, k_fused_init, grid_for(ctx, (int64_t)P.dense_groups * NA2, 256), 256, 0, (unsigned long long*)D.g_lo->ptr,
-           (unsigned long long*)D.g_hi->ptr, (int64_t)P.dense_groups, NA2, 1, 0, init);
+    LAUNCH(ctx, k_fused_init, grid_for(ctx, (int64_t)P.dense_groups * NA2, 256), 256, 0, (unsigned long long*)D.g_lo[b]->ptr,
+           (unsigned long long*)D.g_hi[b]->ptr, (int64_t)P.dense_groups, NA2, 1, 0, init);
   }
-  D.inited = false;  // until the epilogue that re-initialises the table has been queued
-  P.g_lo = (unsigned long long*)D.g_lo->ptr;
-  P.g_hi = (unsigned long long*)D.g_hi->ptr;
+  D.inited[b] = false;  // until the epilogue that re-initialises the table has been queued
+  P.g_lo = (unsigned long long*)D.g_lo[b]->ptr;
+  P.g_hi = (unsigned long long*)D.g_hi[b]->ptr;
   P.n_groups = nullptr;   // DENSE never touches them
   P.abort_flag = nullptr;
   E.g_lo = P.g_lo;
@@ -2200,7 +2213,8 @@ static View run_dense(PlanNode& agg, FusedPlan& fp, DenseRun& D, bool sharded, i
     LAUNCH(ctx, k_fused_scan_agg<FM_DENSE>, fp.grid, F_NT + 32, fp.smem_bytes, P);
   }
   View out = epilogue_execute(ctx, E, D.key_types, fp.specs, agg.schema, sharded, row_offset, sharded ? max_groups : P.dense_groups, nullptr);
-  D.inited = true;
+  CUDA_CHECK(cudaEventRecord(D.epi_done[b], ctx->epi_stream));
+  D.inited[b] = true;
   agg.strategy = std::string("fused_scan_agg[dense-private") + (specialised ? "/shape-specialised, " : ", ") +
                  (P.pack_mask ? std::to_string(__builtin_popcount(P.pack_mask)) + " accs packed into the count word, " : "") +
                  std::to_string(P.n_cols) + " cols, " + std::to_string(P.n_pred) + " range preds, " + std::to_string(P.n_accs) +

@@ -44,12 +44,12 @@ DBuf::DBuf(Ctx* c, size_t n) : ctx(c), bytes(n) {
 DBuf::~DBuf() {
   if (!ptr || parent) return;  // a slab's sub-buffer owns nothing
   const size_t alloc = padded_size(bytes);
-  if (alloc >= kBigBlock && ctx->big_free.size() < 48 && ctx->big_free_bytes + alloc <= kBigCacheBytes) {
+  if (alloc >= kBigBlock && !free_stream && ctx->big_free.size() < 48 && ctx->big_free_bytes + alloc <= kBigCacheBytes) {
     ctx->big_free.push_back({alloc, ptr});
     ctx->big_free_bytes += alloc;
     return;
   }
-  cudaFreeAsync(ptr, ctx->stream);
+  cudaFreeAsync(ptr, free_stream ? free_stream : ctx->stream);
 }
 void Ctx::release_big_blocks() {
   for (auto& b : big_free) cudaFreeAsync(b.second, stream);
@@ -74,7 +74,10 @@ DBufP Ctx::alloc_zero(size_t bytes) {
   CUDA_CHECK(cudaMemsetAsync(b->ptr, 0, ((bytes + 255) / 256) * 256 + 256, stream));
   return b;
 }
-void Ctx::sync() { CUDA_CHECK(cudaStreamSynchronize(stream)); }
+void Ctx::sync() {
+  CUDA_CHECK(cudaStreamSynchronize(stream));
+  if (epi_stream) CUDA_CHECK(cudaStreamSynchronize(epi_stream));
+}
 
 void debug_sync_launch(Ctx* ctx, const char* name) {
   static int on = -1;
@@ -193,7 +196,9 @@ bool SpecScope::defer_verify(const PendingP& p) {
 }
 
 // ---- asynchronous result metadata (qgpu_internal.h: Pending) ------------------------------------------
-PendingP make_pending(Ctx* ctx, const void* dev_meta, int words, std::function<void(const unsigned long long*, Pending&)> apply) {
+PendingP make_pending(Ctx* ctx, const void* dev_meta, int words, std::function<void(const unsigned long long*, Pending&)> apply,
+                      cudaStream_t stream) {
+  if (!stream) stream = ctx->stream;
   if (words > META_WORDS) throw_internal("metadata block too large");
   MetaSlot* slot = nullptr;
   for (MetaSlot* s : ctx->meta_slots)
@@ -213,8 +218,8 @@ PendingP make_pending(Ctx* ctx, const void* dev_meta, int words, std::function<v
   p->ctx = ctx;
   p->slot = slot;
   p->apply = std::move(apply);
-  CUDA_CHECK(cudaMemcpyAsync(slot->host, dev_meta, (size_t)words * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaEventRecord(slot->ev, ctx->stream));
+  CUDA_CHECK(cudaMemcpyAsync(slot->host, dev_meta, (size_t)words * 8, cudaMemcpyDeviceToHost, stream));
+  CUDA_CHECK(cudaEventRecord(slot->ev, stream));
   return p;
 }
 void Pending::resolve() {

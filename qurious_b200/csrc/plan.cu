@@ -368,6 +368,8 @@ int qgpu_init(const int* devices, int n, qgpu_ctx** out) {
     CUDA_CHECK(cudaSetDevice(dev));
     CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->epi_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&c->epi_ready, cudaEventDisableTiming));
     // One stream-ordered pool PER CONTEXT: contexts of one process (ranks emulated on one GPU, several qurious sessions)
     // must not share a pool -- the driver may make an allocation on one context's stream wait for a free that is still
     // queued on another's, and a peer-exchange kernel waiting for that other context would never see it arrive.
@@ -412,6 +414,7 @@ void qgpu_shutdown(qgpu_ctx* ctx) {
   c->release_big_blocks();
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->copy_stream);
+  if (c->epi_stream) cudaStreamSynchronize(c->epi_stream);
   for (auto& e : c->prof_events) {
     cudaEventDestroy(e.first);
     cudaEventDestroy(e.second);
@@ -429,6 +432,8 @@ void qgpu_shutdown(qgpu_ctx* ctx) {
   c->comm.reset();
   cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->copy_stream);
+  if (c->epi_stream) cudaStreamDestroy(c->epi_stream);
+  if (c->epi_ready) cudaEventDestroy(c->epi_ready);
   if (c->pool) cudaMemPoolDestroy(c->pool);
   delete ctx;
 }

@@ -95,6 +95,7 @@ struct DBuf {
   void* ptr = nullptr;
   size_t bytes = 0;
   std::shared_ptr<DBuf> parent;  // sub-buffer of a slab (Slab::take): the memory belongs to `parent`
+  cudaStream_t free_stream = nullptr;  // freed in this stream's order instead of ctx->stream (buffers last used on the epilogue stream)
   DBuf(Ctx* c, size_t n);
   DBuf(std::shared_ptr<DBuf> slab, void* p, size_t n) : ctx(slab->ctx), ptr(p), bytes(n), parent(std::move(slab)) {}
   ~DBuf();
@@ -203,7 +204,8 @@ struct Pending {
 };
 typedef std::shared_ptr<Pending> PendingP;
 // queues the copy of `words` metadata words at `dev_meta` into a pinned slot on ctx->stream (+ an event)
-PendingP make_pending(Ctx* ctx, const void* dev_meta, int words, std::function<void(const unsigned long long*, Pending&)> apply);
+PendingP make_pending(Ctx* ctx, const void* dev_meta, int words, std::function<void(const unsigned long long*, Pending&)> apply,
+                      cudaStream_t stream = nullptr /* default: the compute stream */);
 
 struct View {
   Schema schema;
@@ -227,6 +229,10 @@ struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;       // compute stream
   cudaStream_t copy_stream = nullptr;  // H2D staging side stream
+  // The single-CTA epilogues (epilogue.cu: finalisation / multi-GPU exchange + merge of the dense fused aggregate) run
+  // here, behind an event of the compute stream: the next execution's scan kernel overlaps them.
+  cudaStream_t epi_stream = nullptr;
+  cudaEvent_t epi_ready = nullptr;
   cudaMemPool_t pool = nullptr;
   std::recursive_mutex mu;
   std::string last_error;
@@ -256,7 +262,7 @@ struct Ctx {
   std::string prof_report();  // "name\tlaunches\ttotal_ms\tmax_ms\n" per kernel; resets the log
 
   bool async_ok = false;       // inside qgpu_plan_execute_device_async: operators may leave result metadata pending
-  bool epi_attr_set = false;   // epilogue.cu: dynamic shared memory opt-in done on this device
+  size_t epi_smem_set = 0;     // epilogue.cu: dynamic shared memory opt-in done on this device up to this size
   std::shared_ptr<Comm> comm;  // set by qgpu_comm_init / qgpu_comm_init_local
   // pinned result-metadata slots of asynchronous executions (pending.h)
   std::vector<MetaSlot*> meta_slots;
