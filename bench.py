@@ -45,8 +45,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=30_000_000)   # ~11 s of single-core CPU work for Q1
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--extra-queries", default="q6,q3",
-                    help="N=1: comma list of further TPC-H queries whose device-resident leg is reported under 'queries'")
+    ap.add_argument("--extra-queries", default="q6,q3,groupby",
+                    help="comma list of further workloads whose device-resident leg (at the same N) is reported under 'queries'")
     ap.add_argument("--order-by", action="store_true", help="q1 / q3 with their ORDER BY (+ LIMIT 10) on the device (Sort, SURVEY 8f #1)")
     return ap.parse_args()
 
@@ -548,6 +548,70 @@ def parity_check(q, expect_local, result_of, world, torch):
         return {"ok": False, "error": repr(e)[:300]}
 
 
+def setup_leg(q, args, ctx, rank, world, torch):
+    """Tables of `q` resident in HBM (this rank's shard at N > 1), its plan, the step callable of the device-resident leg
+    and the independent check values.  -> dict"""
+    from qurious_b200 import tpch
+    sf_total = args.sf * world if q != "groupby" else (args.rows, args.groups)
+    driving = "t" if q == "groupby" else "lineitem"
+    raw = gen_raw(q, sf_total, "cuda", rank, world)
+    rows_local = raw[driving].rows
+    expect = local_invariants(q, raw, torch, (lambda k: _gather_ragged_i64(k, world, torch)) if world > 1 else None)
+    dev_tables = {k: tpch.to_device_table(ctx, v) for k, v in raw.items()}
+    del raw
+    torch.cuda.empty_cache()        # the generator's temporaries go back to the driver: HBM is for the tables
+    plan = build_plan(q, dev_tables)
+    leg = {"q": q, "plan": plan, "tables": dev_tables, "rows_local": rows_local, "expect": expect, "driving": driving,
+           "sf_total": sf_total, "lo": 0, "strategy": lambda: plan.last_strategy()}
+    if world > 1:
+        from qurious_b200 import distributed as qd
+        lo = 0 if q == "groupby" else shard_range(tpch.n_lineitems(sf_total), rank, world)[0]
+        leg["lo"] = lo
+        if q == "groupby":
+            # config 4: one kernel partitions the rows by key hash and stores every tuple into its owner's HBM over
+            # NVLink (peer-to-peer), then a purely local aggregate (groups are rank-disjoint); result = concatenation
+            xg = qd.ExchangeGroupBy(ctx, plan, world, rank)
+
+            def step():
+                xg.execute_device().free()
+            leg["strategy"] = lambda: "%s x%d -> %s" % (xg.last_path, world, plan.last_strategy())
+            leg["result_of"] = xg.execute_device
+        elif q == "q3":
+            # orders and lineitem row-range sharded, customer replicated: J1 per orders shard, its rows all-gathered
+            # (broadcast build), J2 + aggregate per lineitem shard; groups straddling a shard boundary are merged by
+            # all-gathering the per-rank result rows and re-aggregating them
+            bj = qd.BroadcastJoinAggregate(ctx, tpch.q3_build_plan(tpch.Database(0.0, dev_tables["customer"], dev_tables["orders"], None)),
+                                           lambda b: tpch.q3_probe_plan(b, dev_tables["lineitem"]), world)
+
+            def step():
+                bj.execute_device().free()
+            leg["strategy"] = lambda: bj.last_strategy
+            leg["result_of"] = bj.execute
+        else:
+            # Q1 / Q6: scan kernel + ONE epilogue kernel per step; the epilogue stores the state block into every peer's
+            # buffer over NVLink, waits on the peers' flags, merges and finalises (no collective call, no host round trip)
+            sharded = qd.ShardedAggregate(ctx, plan, lo, world)
+            sharded.execute_device().free()            # records the strategy
+            step = Pipelined(lambda: sharded.execute_device(wait=False))
+            leg["result_of"] = sharded.execute
+    else:
+        plan.execute_device(ctx).free()                # records the strategy
+        step = Pipelined(lambda: plan.execute_device_async(ctx))
+        leg["result_of"] = (lambda: plan.execute_device(ctx)) if q == "groupby" else (lambda: plan.execute(ctx))
+    leg["step"] = step
+    return leg
+
+
+def free_leg(leg, ctx, torch):
+    leg["plan"].release()
+    for t in leg["tables"].values():
+        if t._dev is not None:
+            t._dev.free()
+    leg.clear()
+    ctx.release_cached_memory()
+    torch.cuda.empty_cache()
+
+
 def run_b200(args):
     global _dist
     import torch
@@ -567,56 +631,15 @@ def run_b200(args):
     stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", local_rank))
     sampler = ClockSampler(local_rank)
     peak, peak_src = measured_peak_gbs()
-    sf_total = args.sf * world if args.query != "groupby" else (args.rows, args.groups)
-    driving = "t" if args.query == "groupby" else "lineitem"
     q = args.query
+    if world > 1:
+        from qurious_b200 import distributed as qd
+        qd.init_comm(ctx)           # the library-owned communicator (NCCL + symmetric peer buffers)
 
     # ---- device-resident leg -----------------------------------------------------------------
-    raw = gen_raw(q, sf_total, "cuda", rank, world)
-    rows_local = raw[driving].rows
-    expect = local_invariants(q, raw, torch, (lambda k: _gather_ragged_i64(k, world, torch)) if world > 1 else None)
-    dev_tables = {k: tpch.to_device_table(ctx, v) for k, v in raw.items()}
-    del raw
-    torch.cuda.empty_cache()        # the generator's temporaries go back to the driver: HBM is for the tables
-    plan = build_plan(q, dev_tables)
-    sharded = None
-    result_of = None                # -> (host batches | device table) of one more execution, for the parity check
-    if world > 1:
-        # row-range shards: shard-local partial aggregate -> NCCL all-gather of the state blocks -> exact merge
-        from qurious_b200 import distributed as qd
-        lo = 0 if q == "groupby" else shard_range(tpch.n_lineitems(sf_total), rank, world)[0]
-        if q == "groupby":
-            # config 4: one kernel partitions the rows by key hash and stores every tuple into its owner's HBM over
-            # NVLink (peer-to-peer), then a purely local aggregate (groups are rank-disjoint); result = concatenation
-
-            xg = qd.ExchangeGroupBy(ctx, plan, world, rank)
-
-            def step():
-                xg.execute_device().free()
-                step.strategy = "%s x%d -> %s" % (xg.last_path, world, plan.last_strategy())
-            result_of = xg.execute_device
-        elif q == "q3":
-            # orders and lineitem row-range sharded, customer replicated: J1 per orders shard, its rows all-gathered
-            # (broadcast build), J2 + aggregate per lineitem shard; groups straddling a shard boundary are merged by
-            # all-gathering the per-rank result rows and re-aggregating them
-            bj = qd.BroadcastJoinAggregate(ctx, tpch.q3_build_plan(tpch.Database(0.0, dev_tables["customer"], dev_tables["orders"], None)),
-                                           lambda b: tpch.q3_probe_plan(b, dev_tables["lineitem"]), world)
-
-            def step():
-                bj.execute_device().free()
-                step.strategy = bj.last_strategy
-            result_of = bj.execute
-        else:
-            # Q1 / Q6: scan kernel + ONE epilogue kernel per step; the epilogue stores the state block into every peer's
-            # buffer over NVLink, waits on the peers' flags, merges and finalises (no collective call, no host round trip)
-            sharded = qd.ShardedAggregate(ctx, plan, lo, world)
-            sharded.execute_device().free()            # records the strategy
-            step = Pipelined(lambda: sharded.execute_device(wait=False))
-            result_of = sharded.execute
-    else:
-        plan.execute_device(ctx).free()                # records the strategy
-        step = Pipelined(lambda: plan.execute_device_async(ctx))
-        result_of = (lambda: plan.execute_device(ctx)) if q == "groupby" else (lambda: plan.execute(ctx))
+    leg = setup_leg(q, args, ctx, rank, world, torch)
+    sf_total, driving, rows_local, dev_tables, plan, lo = (leg[k] for k in ("sf_total", "driving", "rows_local", "tables", "plan", "lo"))
+    step, expect, result_of = leg["step"], leg["expect"], leg["result_of"]
     ms, prof, launches = run_query_device(ctx, step, args.steps, args.warmup, sampler, torch, stream)
     parity = parity_check(q, expect, result_of, world, torch)
     main_step_ms = list(getattr(run_query_device, "step_ms", []))[:64]     # (the extra-query legs below overwrite the attribute)
@@ -627,7 +650,7 @@ def run_b200(args):
         _dist.all_reduce(rows_t, op=_dist.ReduceOp.SUM)
     ms_max, rows_total = float(t_ms.item()), int(rows_t.item())
     value = rows_total * args.steps / (ms_max / 1e3)
-    strategy = getattr(step, "strategy", None) or plan.last_strategy()
+    strategy = leg["strategy"]()
     alg_bytes, per_table = algorithmic_bytes(q, dev_tables)
     # dominant kernel by total device time
     prof_sorted = sorted(prof, key=lambda r: -r[2])
@@ -756,38 +779,42 @@ def run_b200(args):
             cpu = {"value": n / dt, "unit": "rows/s", "cores": 1, "kind": "port",
                    "sample": f"{desc}; {dt:.1f} s on 1 of {os.cpu_count()} host cores"}
 
-    # ---- further TPC-H queries of BASELINE.json's metric, device-resident leg only (N = 1): reported under "queries" ----
+    # ---- the other workloads of BASELINE.json (Q6, Q3, the 1 B-row group-by), device-resident leg, at the same N: "queries" ----
     extra = {}
-    if world == 1 and args.extra_queries:
+    if args.extra_queries:
+        free_leg(leg, ctx, torch)       # the main workload's tables: HBM for the next ones
         for xq in [x.strip() for x in args.extra_queries.split(",")]:
-            if not xq or xq == q or xq not in QUERY_COLUMNS:
+            if not xq or xq == q or xq not in WORKLOAD:
                 continue
             try:
-                ctx.release_cached_memory()
-                xraw = gen_raw(xq, args.sf, "cuda", 0, 1)
-                xrows = xraw["lineitem"].rows
-                xtabs = {k: tpch.to_device_table(ctx, v) for k, v in xraw.items()}
-                del xraw
-                torch.cuda.empty_cache()
-                xplan = build_plan(xq, xtabs)
-
-                xplan.execute_device(ctx).free()       # records the strategy
-                xstep = Pipelined(lambda xplan=xplan: xplan.execute_device_async(ctx))
-                xsteps = max(1, min(args.steps, 20))
-                xms, xprof, xlaunches = run_query_device(ctx, xstep, xsteps, args.warmup, sampler, torch, stream)
+                xleg = setup_leg(xq, args, ctx, rank, world, torch)
+                xsteps = max(1, min(args.steps, 5 if xq == "groupby" else 20))
+                xwarm = min(args.warmup, 3) if xq == "groupby" else args.warmup
+                xms, xprof, xlaunches = run_query_device(ctx, xleg["step"], xsteps, xwarm, sampler, torch, stream)
+                xstep_ms = list(getattr(run_query_device, "step_ms", []))[:20]
+                xparity = parity_check(xq, xleg["expect"], xleg["result_of"], world, torch)
+                xt = torch.tensor([xms], dtype=torch.float64, device="cuda")
+                xr = torch.tensor([xleg["rows_local"]], dtype=torch.int64, device="cuda")
+                if world > 1:
+                    _dist.all_reduce(xt, op=_dist.ReduceOp.MAX)
+                    _dist.all_reduce(xr, op=_dist.ReduceOp.SUM)
+                xms_max, xrows = float(xt.item()), int(xr.item())
                 xsorted = sorted(xprof, key=lambda r: -r[2])
                 xtop = xsorted[0] if xsorted else ("none", 0, 0.0, 0.0)
                 xtop_ms = xtop[2] / max(xtop[1], 1)
-                _, xper = algorithmic_bytes(xq, xtabs)
-                xbytes = kernel_bytes(xtop[0], xq, xper, "lineitem", xrows, 0)
+                _, xper = algorithmic_bytes(xq, xleg["tables"])
+                xbytes = kernel_bytes(xtop[0], xq, xper, xleg["driving"], xleg["rows_local"], args.groups // world)
                 xach = xbytes / (xtop_ms / 1e3) / 1e9 if (xtop_ms > 0 and xbytes) else None
-                extra[xq] = {"metric": metric_name(xq), "value": xrows * xsteps / (xms / 1e3), "unit": "rows/s",
-                             "ms_per_step": xms / xsteps, "steps": xsteps, "rows": xrows, "strategy": xplan.last_strategy(),
+                extra[xq] = {"metric": metric_name(xq), "value": xrows * xsteps / (xms_max / 1e3), "unit": "rows/s",
+                             "ms_per_step": xms_max / xsteps, "steps": xsteps, "rows": xrows,
+                             "scaling": "strong" if xq == "groupby" else "weak", "strategy": xleg["strategy"](),
                              "roofline": {"bound": "hbm", "kernel": xtop[0], "kernel_ms_avg": xtop_ms, "achieved": xach, "peak": peak,
-                                          "unit": "GB/s", "frac": (xach / peak) if xach is not None else None, "algorithmic_bytes_per_launch": xbytes},
-                             "gpu_launches_per_step": xlaunches}
-                del xplan, xtabs
-            except Exception as e:      # never let an extra query take the headline line down
+                                          "unit": "GB/s", "frac": (xach / peak) if xach is not None else None,
+                                          "algorithmic_bytes_per_launch": xbytes, "kernel_share_of_step": xtop[2] / max(xms, 1e-9)},
+                             "gpu_launches_per_step": xlaunches, "step_ms": xstep_ms, "parity_check": xparity,
+                             "kernels": [{"name": r[0], "launches": r[1], "total_ms": round(r[2], 4)} for r in xsorted[:6]]}
+                free_leg(xleg, ctx, torch)
+            except Exception as e:      # never let an extra workload take the headline line down
                 extra[xq] = {"error": repr(e)[:300]}
     clocks = sampler.result()
     if rank == 0:
