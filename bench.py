@@ -388,14 +388,26 @@ def acero_context(query, batches):
 # ------------------------------------------------------------------------------------------------
 # reference arm: the CPU port on host cores
 # ------------------------------------------------------------------------------------------------
+def workload_string(q, args, world, rows_total):
+    """config.workload: the SAME string on both arms (the reference arm times a bounded sample of this workload per step)."""
+    if q == "groupby":
+        return f"{WORKLOAD[q]}: {rows_total} rows, {args.groups} groups, {world} GPU(s)"
+    return (f"{WORKLOAD[q]} at SF{args.sf:g} per GPU ({rows_total} lineitem rows total, "
+            f"row-range sharded over {world} GPU(s))")
+
+
 def run_reference(args):
+    """The CPU arm: oracle/qref_cpu.cpp (kind "port": the reference is Rust, no cargo / rustc here) on the host cores, one
+    thread like the reference, each step the SAME bounded sample `cpu_baseline` of the B200 arm uses (--cpu-sample-rows,
+    30 M lineitem rows for Q1 / Q6: ~12 s per step)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import cpu_port
     from qurious_b200 import tpch
-    fn, n_rows, sample = cpu_sample(args.query)
-    for _ in range(max(min(args.warmup, 2), 1)):
+    world = max(1, args.gpus)
+    rows_total = args.rows if args.query == "groupby" else tpch.n_lineitems(args.sf * world)
+    fn, n_rows, sample = cpu_sample(args.query, min(args.cpu_sample_rows, rows_total))
+    for _ in range(1 if args.warmup > 0 else 0):      # one warm-up pass (each is ~12 s of single-core work)
         fn()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -404,10 +416,11 @@ def run_reference(args):
     rows_s = n_rows * args.steps / dt
     line = {"impl": "reference", "metric": metric_name(args.query), "value": rows_s, "unit": "rows/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i128", "data": "synthetic",
-            "config": {"workload": (f"{WORKLOAD[args.query]} at SF{args.sf:g} per GPU (bounded sample per step)" if args.query != "groupby"
-                                    else f"{WORKLOAD[args.query]}: {args.rows} rows, {args.groups} groups (bounded sample per step)")},
-            "cpu_baseline": {"value": rows_s, "unit": "rows/s", "cores": 1, "kind": "port", "sample": sample},
+            "higher_is_better": True, "scaling": "strong" if args.query == "groupby" else "weak", "vs_baseline": None,
+            "dtype": "i64/i128 (exact decimal)", "data": "synthetic",
+            "config": {"workload": workload_string(args.query, args, world, rows_total)},
+            "cpu_baseline": {"value": rows_s, "unit": "rows/s", "cores": 1, "kind": "port", "sample": sample,
+                             "sample_rows_per_step": n_rows, "warmup_passes_run": 1 if args.warmup > 0 else 0},
             "e2e": {"value": rows_s, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -693,67 +706,108 @@ def run_b200(args):
             host[k] = tpch.to_arrow(v, None)
         del raw_h
         torch.cuda.empty_cache()
-        regs = []
-        for k in host:
-            regs += pin_batches(host[k])
         host_batches = host
         h2d = sum(batches_nbytes(b) for b in host.values())
         from qurious_b200.physical.plan import MemoryTable
 
-        phase = {"upload_ms": 0.0, "execute_ms": 0.0, "n": 0}
+        def measure_e2e(tables, steps, label, path):
+            """`steps` timed end-to-end steps over the host tables `tables` ({name: [RecordBatch]})."""
+            phase = {"upload_ms": 0.0, "execute_ms": 0.0, "n": 0}
 
-        def one_e2e():
-            t_a = time.perf_counter()
-            tabs = {k: MemoryTable.try_new(b[0].schema, b) for k, b in host.items()}
-            for t in tabs.values():            # H2D staging of every referenced column (pinned cudaMemcpyAsync) + ingest kernels
-                t.device_table(ctx)
-            stream.synchronize()
-            t_b = time.perf_counter()
-            p = build_plan(q, tabs)
-            if world > 1 and q == "q3":
-                out = qd.BroadcastJoinAggregate(ctx, tpch.q3_build_plan(tpch.Database(0.0, tabs["customer"], tabs["orders"], None)),
-                                                lambda b: tpch.q3_probe_plan(b, tabs["lineitem"]), world).execute()
-            elif world > 1:
-                out = qd.ShardedAggregate(ctx, p, lo, world).execute()
-            else:
-                out = p.execute(ctx)
-            d2h = batches_nbytes(out)
-            t_c = time.perf_counter()
-            phase["upload_ms"] += 1e3 * (t_b - t_a)
-            phase["execute_ms"] += 1e3 * (t_c - t_b)
-            phase["n"] += 1
-            for t in tabs.values():
-                if t._dev is not None:
-                    t._dev.free()
-            return d2h
-        for _ in range(min(args.warmup, 2)):
-            d2h = one_e2e()
-        phase.update(upload_ms=0.0, execute_ms=0.0, n=0)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        torch.cuda.synchronize()
-        sampler.region(True)
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for _ in range(args.e2e_steps):
-            d2h = one_e2e()
-        e1.record(stream)
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-        sampler.region(False)
-        barrier()
-        ems = max(e0.elapsed_time(e1), wall * 1e3)   # host-side staging is part of the step
-        t_e = torch.tensor([ems], dtype=torch.float64, device="cuda")
-        if world > 1:
-            _dist.all_reduce(t_e, op=_dist.ReduceOp.MAX)
-        e2e = {"value": rows_total * args.e2e_steps / (float(t_e.item()) / 1e3), "unit": "rows/s",
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
-               "ms_per_step": float(t_e.item()) / args.e2e_steps,
-               "upload_ms_per_step": phase["upload_ms"] / max(phase["n"], 1), "execute_ms_per_step": phase["execute_ms"] / max(phase["n"], 1),
-               "host_buffers_pinned": len(regs), "host_buffers_pin_failed": len(PIN_FAILURES),
-               "path": "MemoryTable(host RecordBatches, pinned) -> qgpu_table_append (cudaMemcpyAsync) -> "
-                       "plan.execute() -> host RecordBatches"}
+            def one_e2e():
+                t_a = time.perf_counter()
+                tabs = {k: MemoryTable.try_new(b[0].schema, b) for k, b in tables.items()}
+                for t in tabs.values():            # append (retain) every batch, then ONE staged upload of the table (ingest.cu)
+                    t.device_table(ctx).flush()
+                stream.synchronize()
+                t_b = time.perf_counter()
+                p = build_plan(q, tabs)
+                if world > 1 and q == "q3":
+                    out = qd.BroadcastJoinAggregate(ctx, tpch.q3_build_plan(tpch.Database(0.0, tabs["customer"], tabs["orders"], None)),
+                                                    lambda b: tpch.q3_probe_plan(b, tabs["lineitem"]), world).execute()
+                elif world > 1:
+                    out = qd.ShardedAggregate(ctx, p, lo, world).execute()
+                else:
+                    out = p.execute(ctx)
+                d2h = batches_nbytes(out)
+                t_c = time.perf_counter()
+                phase["upload_ms"] += 1e3 * (t_b - t_a)
+                phase["execute_ms"] += 1e3 * (t_c - t_b)
+                phase["n"] += 1
+                p.release()
+                for t in tabs.values():
+                    if t._dev is not None:
+                        t._dev.free()
+                return d2h
+            for _ in range(min(args.warmup, 2)):
+                d2h = one_e2e()
+            phase.update(upload_ms=0.0, execute_ms=0.0, n=0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            torch.cuda.synchronize()
+            sampler.region(True)
+            t0 = time.perf_counter()
+            e0.record(stream)
+            for _ in range(steps):
+                d2h = one_e2e()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            sampler.region(False)
+            barrier()
+            ems = max(e0.elapsed_time(e1), wall * 1e3)   # host-side staging is part of the step
+            t_e = torch.tensor([ems], dtype=torch.float64, device="cuda")
+            if world > 1:
+                _dist.all_reduce(t_e, op=_dist.ReduceOp.MAX)
+            return {"label": label, "value": rows_total * steps / (float(t_e.item()) / 1e3), "unit": "rows/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
+                    "ms_per_step": float(t_e.item()) / steps,
+                    "upload_ms_per_step": phase["upload_ms"] / max(phase["n"], 1),
+                    "execute_ms_per_step": phase["execute_ms"] / max(phase["n"], 1),
+                    "batches_per_step": sum(len(b) for b in tables.values()), "path": path}
+
+        staged = ("qgpu_table_append (batches retained) -> one staged upload per table: host worker threads gather the batches "
+                  "through a pinned ring, Decimal128(15,2) narrowed to int64 on the way (46 instead of 78 B/row cross PCIe for Q1) "
+                  "-> plan.execute() -> host RecordBatches")
+        paths = {}
+        # (i) the call a user of the reference makes: pageable Arrow buffers, one RecordBatch per table
+        paths["pageable_single_batch"] = measure_e2e(host, args.e2e_steps, "pageable_single_batch",
+                                                     "MemoryTable(host RecordBatches, pageable, 1 batch per table) -> " + staged)
+        # (iii) the reference's own granularity: 1024-row batches (datasource/file/csv.rs:34-72), pageable
+        if world == 1 and not os.environ.get("QGPU_BENCH_SKIP_1024"):
+            small = {k: [b[0].slice(o, 1024) for o in range(0, b[0].num_rows, 1024)] for k, b in host.items()}
+            r = measure_e2e(small, max(1, min(args.e2e_steps, 2)), "pageable_1024_row_batches",
+                            "MemoryTable(host RecordBatches, pageable, 1024-row batches) -> qgpu_table_append_stream -> " + staged)
+            # what pyarrow alone needs to hand these batches over the Arrow C stream interface (export + release, no upload):
+            # the floor of this path in this Python harness, outside the library
+            from pyarrow.cffi import ffi as _ffi
+            import pyarrow as pa
+            t0 = time.perf_counter()
+            for k, bl in small.items():
+                cs = _ffi.new("struct ArrowArrayStream*")
+                pa.RecordBatchReader.from_batches(bl[0].schema, bl)._export_to_c(int(_ffi.cast("uintptr_t", cs)))
+                arr = _ffi.new("struct ArrowArray*")
+                while True:
+                    cs.get_next(cs, arr)
+                    if arr.release == _ffi.NULL:
+                        break
+                    arr.release(arr)
+                cs.release(cs)
+            r["arrow_c_stream_export_floor_ms"] = 1e3 * (time.perf_counter() - t0)
+            paths["pageable_1024_row_batches"] = r
+            del small
+        # (ii) page-locked sources (cudaHostRegister outside the timed region): untransformed columns are DMA'd directly
+        regs = []
+        for k in host:
+            regs += pin_batches(host[k])
+        r = measure_e2e(host, args.e2e_steps, "pinned_single_batch",
+                        "MemoryTable(host RecordBatches, page-locked, 1 batch per table) -> " + staged)
+        r["host_buffers_pinned"], r["host_buffers_pin_failed"] = len(regs), len(PIN_FAILURES)
+        paths["pinned_single_batch"] = r
         unpin(regs)
+        # headline: the plain user-facing call (pageable buffers, no pinning by the caller)
+        e2e = dict(paths["pageable_single_batch"])
+        e2e["paths"] = {k: v for k, v in paths.items() if k != "pageable_single_batch"}
 
     # ---- CPU baseline (rank 0, N=1): the C++ port on a bounded sample of the same workload -----------
     if not args.no_cpu and rank == 0 and world == 1:
@@ -822,9 +876,7 @@ def run_b200(args):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "strong" if q == "groupby" else "weak",   # the group-by's row count is fixed, TPC-H is SF per GPU
                 "vs_baseline": None, "dtype": "i64/i128 (exact decimal)", "data": "synthetic",
-                "config": {"workload": (f"{WORKLOAD[q]} at SF{args.sf:g} per GPU ({rows_total} lineitem rows total, "
-                                        f"row-range sharded over {world} GPU(s))") if q != "groupby" else
-                           f"{WORKLOAD[q]}: {rows_total} rows, {args.groups} groups, {world} GPU(s)",
+                "config": {"workload": workload_string(q, args, world, rows_total),
                            "l2": "inputs larger than L2 (resident columns >> 126 MB), no flush needed",
                            "strategy": strategy, "rows_per_gpu": rows_local},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(round(launches * args.steps)),

@@ -149,6 +149,10 @@ const char* qgpu_last_error(const qgpu_ctx* ctx);
 /* Compatibility switches for reference quirks: name in {"avg_precision",
  * "empty_decimal_sum"}; value 1 reproduces the reference's failure, 0 (default) the intended value. */
 int qgpu_set_compat(qgpu_ctx* ctx, const char* name, int value);
+/* Tuning knobs: "ingest_threads" (host worker threads of the staged ingest, 0 = min(hardware threads, 16); at most 16),
+ * "ingest_host_narrow" (1: Decimal128(p <= 18) narrowed to int64 by the host workers while staging -- 8 instead of 16
+ * bytes per value cross PCIe; 0: uploaded as 16-byte values and narrowed by one kernel; -1: default = 1). */
+int qgpu_set_option(qgpu_ctx* ctx, const char* name, int64_t value);
 /* number of kernel launches issued by this context since creation (bench.py: gpu_launches) */
 int64_t qgpu_kernel_launches(const qgpu_ctx* ctx);
 /* The context keeps large freed device blocks (>= 256 MB, up to 96 GB) for re-use by the next execution of the same plan;
@@ -167,11 +171,20 @@ int64_t qgpu_profile_report(qgpu_ctx* ctx, char* buf, int64_t cap);
 
 /* ---- tables: replaces MemoryTable (datasource/memory.rs:20-45) ---------------------------- */
 int qgpu_table_create(qgpu_ctx* ctx, const struct ArrowSchema* schema, qgpu_table** out);
-/* MemoryTable::insert (memory.rs:104-111): appends one RecordBatch (struct array).  Host buffers are
- * staged through pinned memory and copied with cudaMemcpyAsync on a side stream.  Takes ownership:
- * calls batch->release.  Only the columns later referenced need to be uploaded: pass
- * upload_columns = NULL for all, else n indices. */
+/* MemoryTable::insert (memory.rs:104-111): appends one RecordBatch (struct array).  The batch is validated and
+ * RETAINED (ownership moves to the table; batch->release is called after the upload, or by qgpu_table_free): all
+ * retained batches are uploaded at once when the table is first used or on qgpu_table_flush -- host worker threads
+ * gather the many small batches the reference produces (1024 rows: datasource/file/csv.rs:34-72) through a pinned ring
+ * into the final contiguous device columns, narrowing Decimal128(p <= 18) to int64 on the way (ingest.cu).  Only the
+ * columns later referenced need to be uploaded: pass upload_columns = NULL for all, else n indices. */
 int qgpu_table_append(qgpu_table* t, struct ArrowArray* batch, const int32_t* upload_columns, int32_t n);
+/* The same for every batch of an Arrow C stream (arrow-rs: FFI_ArrowArrayStream over a RecordBatchReader; one FFI call
+ * instead of one per 1024-row batch).  Takes ownership of the stream (released before returning); *out_batches (may be
+ * NULL) = batches appended.  On an error the batches appended so far stay. */
+int qgpu_table_append_stream(qgpu_table* t, struct ArrowArrayStream* stream, const int32_t* upload_columns, int32_t n,
+                             int64_t* out_batches);
+/* Upload the retained batches now (otherwise: first use). */
+int qgpu_table_flush(qgpu_table* t);
 /* Same, but every buffer pointer inside `batch` is a DEVICE pointer on this context's GPU
  * (Arrow C Device Data Interface, device_type ARROW_DEVICE_CUDA); buffers are copied D2D. */
 int qgpu_table_append_device(qgpu_table* t, struct ArrowArray* batch);

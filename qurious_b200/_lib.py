@@ -21,6 +21,7 @@ LIB_PATH = os.path.join(_HERE, "libqgpu.so")
 SYMBOLS = [
     "qgpu_init", "qgpu_shutdown", "qgpu_last_error", "qgpu_set_compat", "qgpu_kernel_launches",
     "qgpu_ctx_stream", "qgpu_profile_enable", "qgpu_profile_report",
+    "qgpu_set_option", "qgpu_table_append_stream", "qgpu_table_flush",
     "qgpu_table_create", "qgpu_table_append", "qgpu_table_append_device", "qgpu_table_num_rows",
     "qgpu_table_num_batches", "qgpu_table_column_bytes", "qgpu_table_schema", "qgpu_table_export",
     "qgpu_table_free", "qgpu_expr_parse", "qgpu_expr_free", "qgpu_plan_scan", "qgpu_plan_filter",
@@ -92,6 +93,9 @@ def load_library() -> ctypes.CDLL:
     lib.qgpu_table_create.argtypes = [vp, vp, P(vp)]
     lib.qgpu_table_append.argtypes = [vp, vp, P(i32), i32]
     lib.qgpu_table_append_device.argtypes = [vp, vp]
+    lib.qgpu_table_append_stream.argtypes = [vp, vp, P(i32), i32, P(i64)]
+    lib.qgpu_table_flush.argtypes = [vp]
+    lib.qgpu_set_option.argtypes = [vp, ctypes.c_char_p, i64]
     lib.qgpu_table_num_rows.argtypes = [vp]
     lib.qgpu_table_num_rows.restype = i64
     lib.qgpu_table_num_batches.argtypes = [vp]
@@ -175,6 +179,10 @@ class Context:
 
     def set_compat(self, name: str, value: bool):
         self.check(self.lib.qgpu_set_compat(self.handle, name.encode(), 1 if value else 0))
+
+    def set_option(self, name: str, value: int):
+        """qgpu_set_option: "ingest_threads", "ingest_host_narrow"."""
+        self.check(self.lib.qgpu_set_option(self.handle, name.encode(), int(value)))
 
     def release_cached_memory(self):
         """Give the context's cached large device blocks back to the driver."""
@@ -299,6 +307,25 @@ class DeviceTable:
             arr = (ctypes.c_int32 * len(upload_columns))(*upload_columns)
             rc = self.ctx.lib.qgpu_table_append(self.handle, _addr(ca), arr, len(upload_columns))
         self.ctx.check(rc)
+
+    def append_batches(self, batches: Sequence[pa.RecordBatch], upload_columns: Optional[Sequence[int]] = None) -> int:
+        """Every batch through ONE FFI call (an Arrow C stream over the batches): the reference's tables arrive as tens of
+        thousands of 1024-row batches (datasource/file/csv.rs:34-72).  -> batches appended"""
+        reader = pa.RecordBatchReader.from_batches(self.schema, batches)
+        cstream = _ffi.new("struct ArrowArrayStream*")
+        reader._export_to_c(_addr(cstream))
+        got = ctypes.c_int64()
+        if upload_columns is None:
+            rc = self.ctx.lib.qgpu_table_append_stream(self.handle, _addr(cstream), None, 0, ctypes.byref(got))
+        else:
+            arr = (ctypes.c_int32 * len(upload_columns))(*upload_columns)
+            rc = self.ctx.lib.qgpu_table_append_stream(self.handle, _addr(cstream), arr, len(upload_columns), ctypes.byref(got))
+        self.ctx.check(rc)
+        return got.value
+
+    def flush(self):
+        """Upload the retained host batches now (otherwise they are uploaded when the table is first used)."""
+        self.ctx.check(self.ctx.lib.qgpu_table_flush(self.handle))
 
     def append_device_struct(self, array_addr: int):
         """`array_addr`: address of a struct ArrowArray whose buffers are device pointers."""

@@ -1,5 +1,6 @@
 // Plan execution + table consolidation + the extern "C" surface declared in include/qgpu.h.
 #include <cstring>
+#include <thread>
 
 #include "comm.h"
 #include "launch.h"
@@ -20,8 +21,46 @@ __global__ void k_widen_chunk(const int64_t* __restrict__ src, ulonglong2* __res
   }
 }
 
+// The producer's release callbacks (Arrow C Data Interface: independent arrays may be released from any thread); tens of
+// thousands of 1024-row batches are released by a few threads (~1 us each otherwise: 55 ms for TPC-H SF10's lineitem)
+static void release_host_batches(std::vector<ArrowArray>& v) {
+  auto run = [&](size_t a, size_t b) {
+    for (size_t i = a; i < b; ++i)
+      if (v[i].release) v[i].release(&v[i]);
+  };
+  if (v.size() < 4096) {
+    run(0, v.size());
+    return;
+  }
+  const size_t nt = 8, per = (v.size() + nt - 1) / nt;
+  std::vector<std::thread> pool;
+  for (size_t t = 1; t < nt; ++t) pool.emplace_back(run, std::min(v.size(), t * per), std::min(v.size(), (t + 1) * per));
+  run(0, std::min(v.size(), per));
+  for (auto& th : pool) th.join();
+}
+
+TableImpl::~TableImpl() { release_host_batches(pending_host); }
+
+// uploads every retained host batch as ONE chunk (ingest.cu)
+void TableImpl::flush_pending() {
+  if (pending_host.empty()) return;
+  TableChunk ch = import_host_batches(ctx, schema, pending_host, pending_want);
+  if (consolidated && num_batches > (int64_t)pending_host.size()) {
+    // re-open: keep the consolidated columns as the first chunk
+    TableChunk first;
+    first.cols = cols;
+    first.rows = num_rows - ch.rows;
+    chunks.push_back(first);
+  }
+  chunks.push_back(ch);
+  consolidated = false;
+  release_host_batches(pending_host);
+  pending_host.clear();
+}
+
 void TableImpl::consolidate() {
   resolve();  // result table of an asynchronous execute: its row count is needed from here on
+  flush_pending();
   if (consolidated) return;
   const size_t nf = schema.fields.size();
   cols.assign(nf, nullptr);
@@ -423,6 +462,7 @@ void qgpu_shutdown(qgpu_ctx* ctx) {
     if (c->stage[i]) cudaFreeHost(c->stage[i]);
     if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
   }
+  for (cudaEvent_t e : c->ingest_ev) cudaEventDestroy(e);
   if (c->pinned_scratch) cudaFreeHost(c->pinned_scratch);
   for (MetaSlot* m : c->meta_slots) {
     cudaFreeHost(m->host);
@@ -499,10 +539,38 @@ int qgpu_table_create(qgpu_ctx* ctx, const struct ArrowSchema* schema, qgpu_tabl
   });
 }
 
+static std::vector<char> want_columns(const Schema& schema, const int32_t* cols, int32_t n) {
+  std::vector<char> want(schema.fields.size(), cols ? 0 : 1);
+  if (cols)
+    for (int32_t i = 0; i < n; ++i) {
+      if (cols[i] < 0 || cols[i] >= (int32_t)schema.fields.size()) throw_internal("upload column index out of range");
+      want[cols[i]] = 1;
+    }
+  return want;
+}
+
+// A HOST batch is validated and retained; the upload of all retained batches happens at once, when the table is first
+// used (ingest.cu).  Takes ownership of *batch (moved into the table; released after the upload).
+static void retain_host_batch(TableImpl& ti, struct ArrowArray* batch, const std::vector<char>& want) {
+  validate_host_batch(ti.schema, batch, want);
+  if (!ti.pending_host.empty() && ti.pending_want != want) ti.flush_pending();
+  ti.pending_want = want;
+  ti.pending_host.push_back(*batch);
+  batch->release = nullptr;  // moved
+  ti.num_rows += ti.pending_host.back().length;
+  ti.num_batches += 1;
+}
+
 static int table_append(qgpu_table* t, struct ArrowArray* batch, const int32_t* cols, int32_t n, bool dev) {
   if (!t || !batch) return QGPU_ERR_INTERNAL;
   TableImpl& ti = *t->t;
   int rc = guard(ti.ctx, [&] {
+    ti.resolve();
+    if (!dev) {
+      retain_host_batch(ti, batch, want_columns(ti.schema, cols, n));
+      return;
+    }
+    ti.flush_pending();  // row order: earlier host batches first
     // import first: a failing batch (column count, short child, CUDA error) must leave the table untouched
     TableChunk ch = import_batch(ti.ctx, ti.schema, batch, cols, n, dev);
     if (ti.consolidated && ti.num_batches > 0) {
@@ -525,6 +593,58 @@ int qgpu_table_append(qgpu_table* t, struct ArrowArray* batch, const int32_t* up
   return table_append(t, batch, upload_columns, n, false);
 }
 int qgpu_table_append_device(qgpu_table* t, struct ArrowArray* batch) { return table_append(t, batch, nullptr, 0, true); }
+
+int qgpu_table_append_stream(qgpu_table* t, struct ArrowArrayStream* stream, const int32_t* upload_columns, int32_t n, int64_t* out_batches) {
+  if (!t || !stream || !stream->get_next) return QGPU_ERR_INTERNAL;
+  TableImpl& ti = *t->t;
+  int64_t got = 0;
+  int rc = guard(ti.ctx, [&] {
+    ti.resolve();
+    const std::vector<char> want = want_columns(ti.schema, upload_columns, n);
+    for (;;) {
+      ArrowArray b;
+      memset(&b, 0, sizeof(b));
+      const int e = stream->get_next(stream, &b);
+      if (e != 0) {
+        const char* m = stream->get_last_error ? stream->get_last_error(stream) : nullptr;
+        throw_arrow(std::string("ArrowArrayStream::get_next failed: ") + (m ? m : "(no message)"));
+      }
+      if (!b.release) break;  // end of stream
+      try {
+        retain_host_batch(ti, &b, want);
+      } catch (...) {
+        if (b.release) b.release(&b);
+        throw;
+      }
+      ++got;
+    }
+  });
+  if (out_batches) *out_batches = got;
+  ti.ctx->trace("append_stream: pulled");
+  if (stream->release) stream->release(stream);  // takes ownership, also on failure
+  return rc;
+}
+
+int qgpu_table_flush(qgpu_table* t) {
+  if (!t) return QGPU_ERR_INTERNAL;
+  TableImpl& ti = *t->t;
+  return guard(ti.ctx, [&] { ti.consolidate(); });
+}
+
+int qgpu_set_option(qgpu_ctx* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] {
+    std::string s(name);
+    if (s == "ingest_threads") {
+      if (value < 0 || value > 16) throw_internal("ingest_threads must be 0 (automatic) .. 16");
+      ctx->c.ingest_threads = (int)value;
+    } else if (s == "ingest_host_narrow") {
+      ctx->c.ingest_host_narrow = value < 0 ? -1 : (value != 0);
+    } else {
+      throw_internal("unknown option '" + s + "'");
+    }
+  });
+}
 
 int64_t qgpu_table_num_rows(const qgpu_table* t) {
   if (!t) return -1;

@@ -246,6 +246,11 @@ struct Ctx {
   void* stage[kStageSlots] = {nullptr, nullptr};
   cudaEvent_t stage_ev[kStageSlots] = {nullptr, nullptr};
   int stage_next = 0;
+  // staged multi-batch ingest (ingest.cu): the ring above cut into 2 slots per host worker thread
+  size_t ingest_slot_bytes = (size_t)2 << 20;
+  int ingest_threads = 0;       // 0: min(hardware threads, 16) (QGPU_INGEST_THREADS); qgpu_set_option "ingest_threads"
+  int ingest_host_narrow = -1;  // -1: on (QGPU_INGEST_HOST_NARROW); qgpu_set_option "ingest_host_narrow"
+  std::vector<cudaEvent_t> ingest_ev;
   // small pinned scratch for D2H of scalars / flags
   void* pinned_scratch = nullptr;
   size_t pinned_scratch_bytes = 1 << 16;
@@ -365,6 +370,12 @@ struct TableImpl {
   Ctx* ctx = nullptr;
   Schema schema;
   std::vector<TableChunk> chunks;  // appended batches, consolidated lazily
+  // host batches appended but not uploaded yet (owned: released by flush_pending / the destructor); they follow `chunks`
+  // in row order and share one upload-column set
+  std::vector<ArrowArray> pending_host;
+  std::vector<char> pending_want;
+  void flush_pending();
+  ~TableImpl();
   std::vector<DColP> cols;         // consolidated columns (one per schema field; null = not uploaded)
   bool consolidated = true;
   int64_t num_rows = 0;
@@ -395,6 +406,10 @@ Schema import_schema(const ArrowSchema* s);
 void export_schema(const Schema& s, ArrowSchema* out);
 TableChunk import_batch(Ctx* ctx, const Schema& schema, ArrowArray* batch, const int32_t* upload_columns,
                         int32_t n_upload, bool device_resident);
+// ---- ingest.cu ---------------------------------------------------------------------------------
+void validate_host_batch(const Schema& schema, const ArrowArray* batch, const std::vector<char>& want);
+TableChunk import_host_batches(Ctx* ctx, const Schema& schema, const std::vector<ArrowArray>& batches, const std::vector<char>& want,
+                               int host_narrow = -1);
 // materialised columns -> host ArrowArray (struct); blocks until the copy is done
 void export_batch(Ctx* ctx, const Schema& schema, const std::vector<DColP>& cols, int64_t num_rows,
                   ArrowArray* out);

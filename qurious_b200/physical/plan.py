@@ -57,10 +57,14 @@ class MemoryTable:
     def device_table(self, ctx: _lib.Context) -> "_lib.DeviceTable":
         if self._dev is None:
             dev = _lib.DeviceTable.create(ctx, self.schema)
-            for b in self.data:
-                if b.schema.types != self.schema.types:
+            for b in self.data:      # (Schema.equals first: identical schemas compare by pointer, 0.1 us instead of 10 us per batch)
+                if not b.schema.equals(self.schema) and b.schema.types != self.schema.types:
                     raise _lib.QuriousError(2, "ArrowError: batch schema does not match the table schema")
-                dev.append(b, self.upload_columns)
+            if len(self.data) > 1:
+                dev.append_batches(self.data, self.upload_columns)     # one FFI call for all batches
+            else:
+                for b in self.data:
+                    dev.append(b, self.upload_columns)
             self._dev = dev
         return self._dev
 
