@@ -21,22 +21,11 @@ __global__ void k_widen_chunk(const int64_t* __restrict__ src, ulonglong2* __res
   }
 }
 
-// The producer's release callbacks (Arrow C Data Interface: independent arrays may be released from any thread); tens of
-// thousands of 1024-row batches are released by a few threads (~1 us each otherwise: 55 ms for TPC-H SF10's lineitem)
+// The producer's release callbacks, on the calling thread (~1 us per 1024-row batch; pyarrow's callbacks contend for
+// its allocator / the GIL when called from several threads: 8 threads took 115 ms instead of 55 ms for SF10's lineitem)
 static void release_host_batches(std::vector<ArrowArray>& v) {
-  auto run = [&](size_t a, size_t b) {
-    for (size_t i = a; i < b; ++i)
-      if (v[i].release) v[i].release(&v[i]);
-  };
-  if (v.size() < 4096) {
-    run(0, v.size());
-    return;
-  }
-  const size_t nt = 8, per = (v.size() + nt - 1) / nt;
-  std::vector<std::thread> pool;
-  for (size_t t = 1; t < nt; ++t) pool.emplace_back(run, std::min(v.size(), t * per), std::min(v.size(), (t + 1) * per));
-  run(0, std::min(v.size(), per));
-  for (auto& th : pool) th.join();
+  for (auto& b : v)
+    if (b.release) b.release(&b);
 }
 
 TableImpl::~TableImpl() { release_host_batches(pending_host); }
