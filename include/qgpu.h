@@ -236,6 +236,10 @@ int qgpu_plan_hash_join(qgpu_ctx* ctx, qgpu_plan* left, qgpu_plan* right, int32_
  * row); Left / Right / Full append the unmatched left rows, then the unmatched right rows. */
 int qgpu_plan_nested_loop_join(qgpu_ctx* ctx, qgpu_plan* left, qgpu_plan* right, int32_t join_type,
                                const qgpu_join_filter* filter, qgpu_plan** out);
+/* CrossJoin::new(left, right) (join/cross_join.rs:62-116): the cartesian product (what `FROM a, b` stays when no
+ * equi-condition links a and b: optimizer/rule/eliminate_cross_join.rs).  Rows come out left-row major; the reference's
+ * order additionally depends on its inputs' batch boundaries (one batch per (left batch, right batch, left row)). */
+int qgpu_plan_cross_join(qgpu_ctx* ctx, qgpu_plan* left, qgpu_plan* right, qgpu_plan** out);
 /* PhysicalPlan::schema (physical/plan/mod.rs:26) */
 int qgpu_plan_schema(const qgpu_plan* p, struct ArrowSchema* out);
 /* PhysicalPlan::execute (physical/plan/mod.rs:27): runs the whole subtree on the GPU (intermediate

@@ -13,6 +13,7 @@ What it restates (reference file:line, all relative to /root/reference/qurious/s
   * accumulators                physical/expr/aggregate/{sum,avg,count,min,max,mod}.rs
   * HashJoinExec + helpers      physical/plan/join/hash_join.rs:40-385, physical/plan/join/mod.rs:26-207
   * NestedLoopJoinExec          physical/plan/join/nest_loop_join.rs:79-300
+  * CrossJoin                   physical/plan/join/cross_join.rs:118-168 (Q2 / Q8 / Q9 keep one)
   * build_batch_from_indices    utils/batch.rs:18-61
 
 The arithmetic itself lives in the un-vendored third-party crate `arrow = "53.2.0"`
@@ -945,6 +946,18 @@ def execute(plan, compat: bool = False, null_key_compat: bool = False) -> List[p
         return _hash_join(plan, **kw)
     if k == "NestedLoopJoinExec":
         return _nested_loop_join(plan, **kw)
+    if k == "CrossJoin":  # cross_join.rs:118-168: one batch per (left batch, right batch, left row)
+        left_batches = execute(plan.left, **kw)
+        right_batches = execute(plan.right, **kw)
+        out = []
+        for lb in left_batches:
+            lcols = batch_cols(lb)
+            for rb in right_batches:
+                rcols = batch_cols(rb)
+                for row in range(lb.num_rows):          # repeat_array(array, row, rb.num_rows) ++ rb's columns
+                    rep = np.full(rb.num_rows, row, dtype=np.int64)
+                    out.append(make_batch(plan.schema, [c.take(rep) for c in lcols] + rcols, rb.num_rows))
+        return out
     if k == "Sort":  # sort.rs:48-82
         merged = concat_batches(plan.schema, execute(plan.input, **kw))
         n = merged.num_rows
@@ -1102,6 +1115,8 @@ def build_batch_from_indices(schema, column_indices, build_batch, probe_batch,
             cols.append(bcols[idx].take(build_idx, build_valid))
         else:
             cols.append(pcols[idx].take(probe_idx, probe_valid))
+    if len(schema) == 0:     # batch.rs:27-35: a zero-column schema keeps the row count (RecordBatchOptions::with_row_count)
+        return pa.RecordBatch.from_struct_array(pa.array([{}] * len(build_idx), type=pa.struct([])))
     arrays = [to_arrow(c) for c in cols]
     return pa.record_batch(arrays, schema=schema)
 

@@ -1084,34 +1084,78 @@ __device__ __forceinline__ uint64_t str_hash(const char* s, int len) {
   return fmix64(x);
 }
 // slots[s] = (tag32 << 32) | (rep_row + 1); row_slot[row] = s
+__device__ __forceinline__ uint32_t dict_global_slot(const int32_t* __restrict__ offs, const char* __restrict__ data, int64_t row,
+                                                     int32_t o0, int32_t len, unsigned long long* __restrict__ slots,
+                                                     unsigned int* __restrict__ n_dict, int* __restrict__ abort_flag) {
+  const uint64_t h = str_hash(data + o0, len);
+  const uint32_t tag = (uint32_t)(h >> 32);
+  uint32_t s = (uint32_t)h & (DICT_CAP - 1);
+  const unsigned long long mine = ((unsigned long long)tag << 32) | (unsigned long long)(row + 1);
+  while (true) {
+    unsigned long long cur = *(volatile unsigned long long*)&slots[s];
+    if (cur == 0) {
+      cur = atomicCAS(&slots[s], 0ull, mine);
+      if (cur == 0) {
+        if (atomicAdd(n_dict, 1u) >= 255u) *abort_flag = 1;
+        return s;
+      }
+    }
+    if ((uint32_t)(cur >> 32) == tag) {
+      const int64_t rep = (int64_t)(cur & 0xffffffffull) - 1;
+      const int32_t r0 = offs[rep], rl = offs[rep + 1] - r0;
+      bool eq = rl == len;
+      for (int i = 0; eq && i < len; ++i) eq = data[r0 + i] == data[o0 + i];
+      if (eq) return s;
+    }
+    s = (s + 1) & (DICT_CAP - 1);
+  }
+}
+// Values of <= 8 bytes (flags, status codes, most segment / mode names' prefixes do not count: the WHOLE value must fit) are
+// their own key: a per-CTA shared-memory table maps (length, packed bytes) -> global slot, so that after a CTA's first
+// meeting with a value its rows cost one coalesced offsets / data read, one shared-memory probe and a 2-byte store -- no
+// dependent chain through the global table and the representative row (0.65 ms -> see DESIGN 3.3 for 60 M rows).
+#define DICT_LCAP 512
+#define DICT_L_EMPTY 0xffffffffu
+#define DICT_L_BUSY 0xfffffffeu
 __global__ void __launch_bounds__(256) k_dict_insert(const int32_t* __restrict__ offs, const char* __restrict__ data, int64_t n,
                                                      unsigned long long* __restrict__ slots, uint16_t* __restrict__ row_slot,
                                                      unsigned int* __restrict__ n_dict, int* __restrict__ abort_flag) {
+  __shared__ unsigned long long l_key[DICT_LCAP];
+  __shared__ unsigned int l_val[DICT_LCAP];  // (len << 16) | global slot
+  for (int i = threadIdx.x; i < DICT_LCAP; i += blockDim.x) l_val[i] = DICT_L_EMPTY;
+  __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride) {
     if (*(volatile int*)abort_flag) return;
     const int32_t o0 = offs[row], len = offs[row + 1] - o0;
-    const uint64_t h = str_hash(data + o0, len);
-    const uint32_t tag = (uint32_t)(h >> 32);
-    uint32_t s = (uint32_t)h & (DICT_CAP - 1);
-    const unsigned long long mine = ((unsigned long long)tag << 32) | (unsigned long long)(row + 1);
-    while (true) {
-      unsigned long long cur = *(volatile unsigned long long*)&slots[s];
-      if (cur == 0) {
-        cur = atomicCAS(&slots[s], 0ull, mine);
-        if (cur == 0) {
-          if (atomicAdd(n_dict, 1u) >= 255u) *abort_flag = 1;
-          break;
+    uint32_t s;
+    if (len <= 8) {
+      unsigned long long key = 0;
+      for (int i = 0; i < len; ++i) key |= (unsigned long long)(unsigned char)data[o0 + i] << (8 * i);
+      uint32_t li = (uint32_t)(fmix64(key + (unsigned long long)len) >> 40) & (DICT_LCAP - 1);
+      bool done = false;
+      for (int probe = 0; probe < 8 && !done; ++probe, li = (li + 1) & (DICT_LCAP - 1)) {
+        unsigned int v = *(volatile unsigned int*)&l_val[li];
+        if (v == DICT_L_EMPTY) {
+          v = atomicCAS(&l_val[li], DICT_L_EMPTY, DICT_L_BUSY);
+          if (v == DICT_L_EMPTY) {  // claimed: resolve through the global table once, then publish
+            s = dict_global_slot(offs, data, row, o0, len, slots, n_dict, abort_flag);
+            l_key[li] = key;
+            __threadfence_block();
+            *(volatile unsigned int*)&l_val[li] = ((unsigned int)len << 16) | s;
+            done = true;
+            break;
+          }
+        }
+        if (v == DICT_L_BUSY) break;  // being published by another thread: take the global path, no spinning
+        if ((v >> 16) == (unsigned int)len && *(volatile unsigned long long*)&l_key[li] == key) {
+          s = v & 0xffffu;
+          done = true;
         }
       }
-      if ((uint32_t)(cur >> 32) == tag) {
-        const int64_t rep = (int64_t)(cur & 0xffffffffull) - 1;
-        const int32_t r0 = offs[rep], rl = offs[rep + 1] - r0;
-        bool eq = rl == len;
-        for (int i = 0; eq && i < len; ++i) eq = data[r0 + i] == data[o0 + i];
-        if (eq) break;
-      }
-      s = (s + 1) & (DICT_CAP - 1);
+      if (!done) s = dict_global_slot(offs, data, row, o0, len, slots, n_dict, abort_flag);
+    } else {
+      s = dict_global_slot(offs, data, row, o0, len, slots, n_dict, abort_flag);
     }
     row_slot[row] = (uint16_t)s;
   }

@@ -1158,6 +1158,34 @@ __global__ void k_cross_pairs(long long* __restrict__ l, long long* __restrict__
   }
 }
 
+__global__ void k_cross_pairs_left_major(long long* __restrict__ l, long long* __restrict__ r, int64_t n_right, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+    const int64_t ll = k / n_right;
+    l[k] = ll;
+    r[k] = k - ll * n_right;
+  }
+}
+
+View run_cross_join(Ctx* ctx, const View& left, const View& right, const Schema& out_schema) {
+  const int64_t nl = left.num_rows, nr = right.num_rows;
+  if (nl > 0 && nr > ((int64_t)1 << 40) / nl) throw_internal("CrossJoin: more than 2^40 output rows");
+  const int64_t total = nl * nr;
+  IdxP li = make_idx(ctx, total, false), ri = make_idx(ctx, total, false);
+  if (total > 0)
+    LAUNCH(ctx, k_cross_pairs_left_major, grid_for(ctx, total, 256), 256, 0, (long long*)li->buf->ptr, (long long*)ri->buf->ptr, nr, total);
+  View out;
+  out.schema = out_schema;
+  out.num_rows = total;
+  // one batch per (left batch, right batch, left row) in the reference; nothing downstream depends on the count
+  out.num_batches = (left.num_batches > 0 && right.num_batches > 0) ? std::max<int64_t>(1, nl * right.num_batches) : 0;
+  std::vector<std::pair<IdxP, IdxP>> cl, cr;
+  for (const LazyCol& c : left.cols) out.cols.push_back(apply_selection(ctx, c, li, &cl));
+  for (const LazyCol& c : right.cols) out.cols.push_back(apply_selection(ctx, c, ri, &cr));
+  if (out.cols.size() != out_schema.fields.size()) throw_internal("join output schema mismatch");
+  return out;
+}
+
 // rows of [0, n) whose bit in `visited` is (invert ? clear : set), ascending
 static IdxP rows_by_bit(Ctx* ctx, const DBufP& visited, int64_t n, int invert) {
   if (n <= 0) return make_idx(ctx, 0, false);

@@ -71,6 +71,11 @@ View run_hash_join(Ctx* ctx, const View& build, const View& probe, int join_type
 View run_nested_loop_join(Ctx* ctx, const View& left, const View& right, int join_type, JoinFilterSpec* filter,
                           const Schema& out_schema);
 
+// CrossJoin::execute (join/cross_join.rs:118-168): the cartesian product, left row major.  The reference emits one batch
+// per (left batch, right batch, left row); with one batch per side that is exactly this order, otherwise the same rows
+// in an order that depends on the inputs' batch boundaries.
+View run_cross_join(Ctx* ctx, const View& left, const View& right, const Schema& out_schema);
+
 Schema build_join_schema(const Schema& left, const Schema& right, int join_type);
 
 // MIN / MAX start value of the accumulator for argument type `at` (min.rs / max.rs: NATIVE::MAX / NATIVE::MIN of the array's

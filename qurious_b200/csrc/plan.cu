@@ -325,6 +325,12 @@ View PlanNode::execute() {
       strategy = "nested-loop-join(cross pairs + filter, late-materialisation)";
       return run_nested_loop_join(ctx, l, r, join_type, has_join_filter ? &fs : nullptr, schema);
     }
+    case PK_CROSS_JOIN: {
+      View l = child_view(0);
+      View r = child_view(1);
+      strategy = "cross-join(index vectors, late-materialisation)";
+      return run_cross_join(ctx, l, r, schema);
+    }
   }
   throw_internal("unknown plan node");
 }
@@ -895,6 +901,18 @@ int qgpu_plan_nested_loop_join(qgpu_ctx* ctx, qgpu_plan* left, qgpu_plan* right,
       n->join_filter_side.assign(filter->column_side, filter->column_side + filter->n_columns);
       if ((int)n->join_filter_schema.fields.size() != filter->n_columns) throw_internal("join filter schema/column_indices mismatch");
     }
+    *out = new qgpu_plan{n};
+  });
+}
+
+int qgpu_plan_cross_join(qgpu_ctx* ctx, qgpu_plan* left, qgpu_plan* right, qgpu_plan** out) {
+  if (!ctx || !left || !right || !out) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] {
+    auto n = new_node(ctx, PK_CROSS_JOIN);
+    n->children.push_back(left->node);
+    n->children.push_back(right->node);
+    n->join_type = QGPU_JOIN_INNER;
+    n->schema = build_join_schema(left->node->schema, right->node->schema, QGPU_JOIN_INNER);  // fields and qualifiers concatenated
     *out = new qgpu_plan{n};
   });
 }

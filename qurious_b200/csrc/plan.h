@@ -4,7 +4,7 @@
 
 namespace qgpu {
 
-enum PlanKind { PK_SCAN = 1, PK_FILTER, PK_PROJECTION, PK_AGGREGATE, PK_HASH_JOIN, PK_SORT, PK_LIMIT, PK_NL_JOIN };
+enum PlanKind { PK_SCAN = 1, PK_FILTER, PK_PROJECTION, PK_AGGREGATE, PK_HASH_JOIN, PK_SORT, PK_LIMIT, PK_NL_JOIN, PK_CROSS_JOIN };
 
 struct AggDesc {
   int op = 0;

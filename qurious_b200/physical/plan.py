@@ -527,3 +527,30 @@ class NestedLoopJoinExec(PhysicalPlan):
                 cs.release(cs)
         keep.append(("plan", h))
         return h
+
+
+class CrossJoin(PhysicalPlan):
+    """`CrossJoin::new(left, right)` (join/cross_join.rs:62-116): the cartesian product; what `FROM a, b` stays when no
+    equi-condition links the two sides (optimizer/rule/eliminate_cross_join.rs).  Schema = left fields ++ right fields with
+    the merged field qualifiers.  The library returns the rows left-row major; the reference emits one batch per (left batch,
+    right batch, left row), i.e. the same rows in an order that depends on its inputs' batch boundaries (cross_join.rs:118-168)."""
+
+    def __init__(self, left: PhysicalPlan, right: PhysicalPlan):
+        self.left = left
+        self.right = right
+        self.schema, self.column_indices = build_join_schema(left.schema, right.schema, JoinType.Inner)
+
+    @staticmethod
+    def new(left, right) -> "CrossJoin":
+        return CrossJoin(left, right)
+
+    def children(self):
+        return [self.left, self.right]
+
+    def _build(self, ctx, keep):
+        lh = self.left._build(ctx, keep)
+        rh = self.right._build(ctx, keep)
+        h = ctypes.c_void_p()
+        ctx.check(ctx.lib.qgpu_plan_cross_join(ctx.handle, lh, rh, ctypes.byref(h)))
+        keep.append(("plan", h))
+        return h

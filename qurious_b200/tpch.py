@@ -108,6 +108,20 @@ def n_customers(sf: float) -> int:
     return max(int(round(150_000 * sf)), 8)
 
 
+def n_suppliers(sf: float) -> int:
+    return max(int(10_000 * sf), 100)
+
+
+def n_parts(sf: float) -> int:
+    return max(int(200_000 * sf), 1000)
+
+
+def supplier_of(partkey: torch.Tensor, j: torch.Tensor, sf: float) -> torch.Tensor:
+    """The j-th (0..3) supplier of a part: partsupp holds exactly these four (partkey, suppkey) pairs per part."""
+    s = n_suppliers(sf)
+    return ((partkey - 1) + j * (s // 4)) % s + 1
+
+
 def n_lineitems(sf: float) -> int:
     return LINEITEM_ROWS.get(float(sf), max(int(round(6_001_215 * sf)), n_orders(sf)))
 
@@ -221,7 +235,7 @@ def gen_lineitem(sf: float, device="cpu", columns: Optional[Sequence[str]] = Non
     ship = odate + uniform(2, key, 1, 121)
     receipt = ship + uniform(4, key, 1, 30)
     qty = uniform(5, key, 1, 50)
-    pk = uniform(6, key, 1, max(int(200_000 * sf), 1000))
+    pk = uniform(6, key, 1, n_parts(sf))
     retail = 90000 + (pk // 10) % 20001 + 100 * (pk % 1000)
     cutoff = days("1995-06-17")
     if "l_orderkey" in want:
@@ -229,7 +243,7 @@ def gen_lineitem(sf: float, device="cpu", columns: Optional[Sequence[str]] = Non
     if "l_partkey" in want:
         cols["l_partkey"] = pk
     if "l_suppkey" in want:
-        cols["l_suppkey"] = uniform(7, key, 1, max(int(10_000 * sf), 100))
+        cols["l_suppkey"] = supplier_of(pk, rnd(7, key) % 4, sf)       # one of the part's four partsupp rows (Q9 joins them)
     if "l_linenumber" in want:
         cols["l_linenumber"] = line + 1
     if "l_quantity" in want:

@@ -179,6 +179,11 @@ def golden_cases() -> Iterator[Case]:
             jf = JoinFilter(bx(Column("k1", 0), "Eq", Column("k2", 1)), fs, [(1, JoinSide.Left), (0, JoinSide.Right)])
         plan = NestedLoopJoinExec.try_new(scan(lt), scan(rt), JoinType[c["join_type"]], jf)
         yield (f"nested_loop_join:{name}", plan, [tuple(r) for r in c["expected"]], True)
+    # ---------------------------------------------------------------- cross_join.rs unit test
+    from qurious_b200.physical.plan import CrossJoin
+    cj = G["cross_join"]
+    yield ("cross_join:test_cross_join", CrossJoin.new(scan(table(cj["left"], default=pa.int32())), scan(table(cj["right"], default=pa.int32()))),
+           [tuple(r) for r in cj["expected"]], True)
     # ---------------------------------------------------------------- aggregate/hash.rs unit test
     hu = G["hash_aggregate_unit"]
     t = table(hu["table"], default=pa.int32(), nullable=False)
