@@ -431,6 +431,56 @@ __global__ void __launch_bounds__(256) k_eval_store(const Program* __restrict__ 
   if (lane == 0 && nulls) atomicAdd(null_count, nulls);
 }
 
+// String-valued expressions (CASE over Utf8 branches -- case.rs:30-47 zips string arrays --, Utf8 literals): a row's value is
+// a (pointer, length) pair into a source column or the literal blob.  Pass 1 stores the lengths (+ validity), a scan turns
+// them into Arrow offsets, pass 2 evaluates again and copies the bytes.
+__global__ void __launch_bounds__(256) k_eval_strlen(const Program* __restrict__ Pp, int64_t* __restrict__ lens,
+                                                     uint32_t* __restrict__ validity, int64_t n, int* __restrict__ err,
+                                                     unsigned long long* __restrict__ null_count) {
+  __shared__ Program P;
+  for (int i = threadIdx.x; i < (int)(sizeof(Program) / 4); i += blockDim.x) ((uint32_t*)&P)[i] = ((const uint32_t*)Pp)[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_words = (n + 31) >> 5;
+  unsigned long long nulls = 0;
+  for (int64_t w = warp_id; w < n_words; w += warps) {
+    const int64_t row = (w << 5) + lane;
+    Val v;
+    v.lo = v.hi = 0;
+    v.valid = 0;
+    if (row < n) {
+      v = eval_row(P, row, err);
+      lens[row] = v.valid ? (int64_t)v.hi : 0;
+    }
+    const uint32_t vw = __ballot_sync(0xffffffffu, v.valid != 0);
+    if (lane == 0) {
+      validity[w] = vw;
+      nulls += (int)min((int64_t)32, n - (w << 5)) - __popc(vw);
+    }
+  }
+  if (lane == 0 && nulls) atomicAdd(null_count, nulls);
+}
+__global__ void __launch_bounds__(256) k_eval_strcopy(const Program* __restrict__ Pp, const int64_t* __restrict__ offs64,
+                                                      int32_t* __restrict__ offsets, char* __restrict__ data, int64_t n,
+                                                      int64_t total, int* __restrict__ err) {
+  __shared__ Program P;
+  for (int i = threadIdx.x; i < (int)(sizeof(Program) / 4); i += blockDim.x) ((uint32_t*)&P)[i] = ((const uint32_t*)Pp)[i];
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride) {
+    const Val v = eval_row(P, row, err);
+    const int64_t o = offs64[row];
+    offsets[row] = (int32_t)o;
+    if (v.valid) {
+      const char* src = (const char*)v.lo;
+      for (int64_t i = 0; i < (int64_t)v.hi; ++i) data[o + i] = src[i];
+    }
+    if (row == n - 1) offsets[n] = (int32_t)total;
+  }
+}
+
 // predicate -> keep bitmap words + per-word popcounts (int64 so the scan can be reused)
 __global__ void __launch_bounds__(256) k_eval_mask(const Program* __restrict__ Pp, uint32_t* __restrict__ keep,
                                                    int64_t* __restrict__ counts, int64_t n, int* __restrict__ err) {
@@ -510,9 +560,33 @@ DColP eval_to_column(Ctx* ctx, Compiled& c, const View& v) {
     return col;
   }
   if (col->phys == PH_STR) {
-    // string-valued computed expressions (CASE over strings, string literals)
-    // are listed under SURVEY 8f "next" #3; bare string columns never reach here (aliased).
-    throw_internal("string-valued computed expressions are not supported on the GPU path yet");
+    // string-valued computed expressions (CASE over Utf8 branches, Utf8 literals); bare string columns never reach here
+    // (they are aliased).  Two evaluation passes around a scan of the lengths.
+    const int64_t words = (n + 31) >> 5;
+    col->offsets = ctx->alloc_zero((size_t)(n + 1) * 4);
+    if (n == 0) {
+      col->data = ctx->alloc(4);
+      return col;
+    }
+    col->validity = ctx->alloc(std::max<size_t>((size_t)words * 4, 4));
+    Program P = bind_program(ctx, c, v);
+    DBufP dp = upload_program(ctx, P);
+    DBufP flags = ctx->alloc_zero(16);
+    DBufP lens = ctx->alloc((size_t)n * 8), offs64 = ctx->alloc((size_t)n * 8);
+    LAUNCH(ctx, k_eval_strlen, grid_for(ctx, n, 256), 256, 0, (const Program*)dp->ptr, (int64_t*)lens->ptr,
+           (uint32_t*)col->validity->ptr, n, (int*)flags->ptr, (unsigned long long*)((char*)flags->ptr + 8));
+    const int64_t total = exclusive_scan_i64(ctx, (const int64_t*)lens->ptr, (int64_t*)offs64->ptr, n);
+    struct { int err; int pad; unsigned long long nulls; } h;
+    ctx->d2h_sync(&h, flags->ptr, 16);
+    if (h.err) throw_eval_error(h.err);
+    if (total > 2147483647LL) throw_arrow("Utf8 column exceeds 2 GiB of string data; LargeUtf8 is not supported");
+    col->str_bytes = total;
+    col->data = ctx->alloc(std::max<size_t>((size_t)total, 4));
+    LAUNCH(ctx, k_eval_strcopy, grid_for(ctx, n, 256), 256, 0, (const Program*)dp->ptr, (const int64_t*)offs64->ptr,
+           (int32_t*)col->offsets->ptr, (char*)col->data->ptr, n, total, (int*)flags->ptr);
+    col->null_count = (int64_t)h.nulls;
+    if (col->null_count == 0) col->validity.reset();
+    return col;
   }
   const int64_t n_words = (n + 31) >> 5;
   size_t data_bytes = col->phys == PH_BIT ? (size_t)n_words * 4 : (size_t)n * phys_width(col->phys);
