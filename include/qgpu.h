@@ -82,7 +82,10 @@ typedef enum qgpu_type_id {
   QGPU_T_NULL = 0, QGPU_T_BOOL = 1, QGPU_T_INT8 = 2, QGPU_T_INT16 = 3, QGPU_T_INT32 = 4,
   QGPU_T_INT64 = 5, QGPU_T_UINT8 = 6, QGPU_T_UINT16 = 7, QGPU_T_UINT32 = 8, QGPU_T_UINT64 = 9,
   QGPU_T_FLOAT32 = 10, QGPU_T_FLOAT64 = 11, QGPU_T_UTF8 = 12, QGPU_T_DATE32 = 13,
-  QGPU_T_DATE64 = 14, QGPU_T_DECIMAL128 = 15
+  QGPU_T_DATE64 = 14, QGPU_T_DECIMAL128 = 15,
+  /* Time32(Second | Millisecond) / Time64(Microsecond | Nanosecond): the unit travels in qgpu_type.scale
+   * (0 = s, 1 = ms, 2 = us, 3 = ns); hashable key types of the reference (utils/array.rs:198-201) */
+  QGPU_T_TIME32 = 16, QGPU_T_TIME64 = 17
 } qgpu_type_id;
 
 typedef struct qgpu_type {

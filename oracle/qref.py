@@ -111,7 +111,10 @@ _NP = {
     pa.uint8(): np.uint8, pa.uint16(): np.uint16, pa.uint32(): np.uint32, pa.uint64(): np.uint64,
     pa.float32(): np.float32, pa.float64(): np.float64, pa.date32(): np.int32, pa.date64(): np.int64,
     pa.bool_(): np.bool_,
+    pa.time32("s"): np.int32, pa.time32("ms"): np.int32, pa.time64("us"): np.int64, pa.time64("ns"): np.int64,
 }
+_AS_INT = {pa.date32(): pa.int32(), pa.date64(): pa.int64(), pa.time32("s"): pa.int32(), pa.time32("ms"): pa.int32(),
+           pa.time64("us"): pa.int64(), pa.time64("ns"): pa.int64()}
 
 
 def is_dec(dt) -> bool:
@@ -158,7 +161,7 @@ def from_arrow(arr) -> Col:
         if dt == pa.bool_():
             vals = np.array(arr.fill_null(False)) if arr.null_count else np.array(arr)
             return Col(dt, vals.astype(bool), valid)
-        raw = arr.cast(pa.int32()) if dt == pa.date32() else (arr.cast(pa.int64()) if dt == pa.date64() else arr)
+        raw = arr.cast(_AS_INT[dt]) if dt in _AS_INT else arr
         vals = raw.fill_null(0).to_numpy(zero_copy_only=False) if arr.null_count else raw.to_numpy(zero_copy_only=False)
         return Col(dt, np.ascontiguousarray(vals).astype(_NP[dt]), valid)
     if is_dec(dt):
@@ -186,10 +189,8 @@ def to_arrow(col: Col) -> pa.Array:
     if pa.types.is_null(dt):
         return pa.nulls(len(col))
     if dt in _NP:
-        if dt == pa.date32():
-            return pa.array(col.vals.astype(np.int32), type=pa.int32(), mask=mask).cast(dt)
-        if dt == pa.date64():
-            return pa.array(col.vals.astype(np.int64), type=pa.int64(), mask=mask).cast(dt)
+        if dt in _AS_INT:
+            return pa.array(col.vals.astype(_NP[dt]), type=_AS_INT[dt], mask=mask).cast(dt)
         return pa.array(col.vals, type=dt, mask=mask)
     if is_dec(dt):
         n = len(col)
@@ -835,10 +836,8 @@ class MinMaxAcc:
         self.rt, self.is_min, self.result = rt, is_min, None
         if rt in _INT_RANGE:
             lo, hi = _INT_RANGE[rt]
-        elif rt == pa.date32():
-            lo, hi = _INT_RANGE[pa.int32()]
-        elif rt == pa.date64():
-            lo, hi = _INT_RANGE[pa.int64()]
+        elif rt in _AS_INT:      # dates and times (mod.rs:100-107)
+            lo, hi = _INT_RANGE[_AS_INT[rt]]
         elif is_dec(rt):
             lo, hi = I128_MIN, I128_MAX
         elif rt == pa.float64():
@@ -867,8 +866,8 @@ class MinMaxAcc:
     def evaluate(self):
         if self.result is None:
             return (pa.null(), None)  # mod.rs:83 ScalarValue::Null
-        if self.rt in (pa.date32(), pa.date64()):
-            # scalar.rs:228: ScalarValue::try_from_array has no Date variants -> unimplemented!()
+        if self.rt in _AS_INT:
+            # scalar.rs:228: ScalarValue::try_from_array has no Date / Time variants -> unimplemented!()
             raise QError("Unimplemented", f"data type {self.rt} not supported")
         return (self.rt, self.result)
 
@@ -1024,6 +1023,7 @@ def _hashable(c: Col, row: int):
 
 _HASHABLE_KEYS = (
     pa.int64(), pa.uint8(), pa.int32(), pa.string(), pa.date32(), pa.date64(),
+    pa.time32("s"), pa.time32("ms"), pa.time64("us"), pa.time64("ns"),          # utils/array.rs:198-201
 )
 
 

@@ -100,6 +100,10 @@ static DType parse_format(const char* f) {
   if (s == "u") return mk_type(QGPU_T_UTF8);
   if (s == "tdD") return mk_type(QGPU_T_DATE32);
   if (s == "tdm") return mk_type(QGPU_T_DATE64);
+  if (s == "tts") return mk_type(QGPU_T_TIME32, 0, 0);
+  if (s == "ttm") return mk_type(QGPU_T_TIME32, 0, 1);
+  if (s == "ttu") return mk_type(QGPU_T_TIME64, 0, 2);
+  if (s == "ttn") return mk_type(QGPU_T_TIME64, 0, 3);
   if (s.rfind("d:", 0) == 0) {
     int p = 0, sc = 0, bits = 128;
     int k = sscanf(s.c_str(), "d:%d,%d,%d", &p, &sc, &bits);
@@ -125,6 +129,8 @@ static std::string format_of(const DType& t) {
     case QGPU_T_UTF8: return "u";
     case QGPU_T_DATE32: return "tdD";
     case QGPU_T_DATE64: return "tdm";
+    case QGPU_T_TIME32: return t.scale == 1 ? "ttm" : "tts";
+    case QGPU_T_TIME64: return t.scale == 3 ? "ttn" : "ttu";
     case QGPU_T_DECIMAL128: return "d:" + std::to_string(t.precision) + "," + std::to_string(t.scale);
   }
   return "n";
@@ -197,8 +203,8 @@ static Phys canonical_phys(const DType& t) {
     case QGPU_T_BOOL: return PH_BIT;
     case QGPU_T_INT8: return PH_I8;
     case QGPU_T_INT16: return PH_I16;
-    case QGPU_T_INT32: case QGPU_T_DATE32: return PH_I32;
-    case QGPU_T_INT64: case QGPU_T_DATE64: return PH_I64;
+    case QGPU_T_INT32: case QGPU_T_DATE32: case QGPU_T_TIME32: return PH_I32;
+    case QGPU_T_INT64: case QGPU_T_DATE64: case QGPU_T_TIME64: return PH_I64;
     case QGPU_T_UINT8: return PH_U8;
     case QGPU_T_UINT16: return PH_U16;
     case QGPU_T_UINT32: return PH_U32;

@@ -17,6 +17,8 @@ std::string DType::str() const {
                                 "UInt32", "UInt64", "Float32", "Float64", "Utf8", "Date32", "Date64"};
   if (id == QGPU_T_DECIMAL128) return "Decimal128(" + std::to_string(precision) + ", " + std::to_string(scale) + ")";
   if (id <= QGPU_T_DATE64) return names[id];
+  if (id == QGPU_T_TIME32) return scale == 1 ? "Time32(Millisecond)" : "Time32(Second)";
+  if (id == QGPU_T_TIME64) return scale == 3 ? "Time64(Nanosecond)" : "Time64(Microsecond)";
   return "Unknown(" + std::to_string(id) + ")";
 }
 
@@ -24,8 +26,8 @@ int arrow_width(const DType& t) {
   switch (t.id) {
     case QGPU_T_INT8: case QGPU_T_UINT8: return 1;
     case QGPU_T_INT16: case QGPU_T_UINT16: return 2;
-    case QGPU_T_INT32: case QGPU_T_UINT32: case QGPU_T_FLOAT32: case QGPU_T_DATE32: return 4;
-    case QGPU_T_INT64: case QGPU_T_UINT64: case QGPU_T_FLOAT64: case QGPU_T_DATE64: return 8;
+    case QGPU_T_INT32: case QGPU_T_UINT32: case QGPU_T_FLOAT32: case QGPU_T_DATE32: case QGPU_T_TIME32: return 4;
+    case QGPU_T_INT64: case QGPU_T_UINT64: case QGPU_T_FLOAT64: case QGPU_T_DATE64: case QGPU_T_TIME64: return 8;
     case QGPU_T_DECIMAL128: return 16;
     default: return 0;
   }
@@ -33,7 +35,7 @@ int arrow_width(const DType& t) {
 
 VClass class_of(const DType& t) {
   if (t.id == QGPU_T_BOOL) return VC_BOOL;
-  if (t.is_signed_int() || t.is_date()) return VC_INT;
+  if (t.is_signed_int() || t.is_date() || t.is_time()) return VC_INT;
   if (t.is_unsigned_int()) return VC_UINT;
   if (t.is_decimal()) return VC_DEC;
   if (t.is_float()) return VC_FLT;
@@ -45,7 +47,7 @@ static int int_bits(const DType& t) {
   switch (t.id) {
     case QGPU_T_INT8: case QGPU_T_UINT8: return 8;
     case QGPU_T_INT16: case QGPU_T_UINT16: return 16;
-    case QGPU_T_INT32: case QGPU_T_UINT32: case QGPU_T_DATE32: return 32;
+    case QGPU_T_INT32: case QGPU_T_UINT32: case QGPU_T_DATE32: case QGPU_T_TIME32: return 32;
     default: return 64;
   }
 }
@@ -241,7 +243,7 @@ struct Compiler {
       case VC_BOOL: ok = to_int || to.id == QGPU_T_BOOL; break;
       case VC_INT:
       case VC_UINT:
-        ok = to_int || to.is_float() || to.is_decimal() || (to.is_date() && from.is_int()) || (from.is_date() && to == from);
+        ok = to_int || to.is_float() || to.is_decimal() || (to.is_date() && from.is_int()) || ((from.is_date() || from.is_time()) && to == from);
         break;
       case VC_FLT: ok = to_int || to.is_float() || to.is_decimal(); break;
       case VC_DEC: ok = to_int || to.is_float() || to.is_decimal(); break;

@@ -168,7 +168,7 @@ void check_hash_key_type(const DType& t) {
   // create_hashes (utils/array.rs:190-210): Int64, UInt8, Int32, Utf8, Date32/64, (Time*), Decimal128/256 only
   switch (t.id) {
     case QGPU_T_INT64: case QGPU_T_UINT8: case QGPU_T_INT32: case QGPU_T_UTF8: case QGPU_T_DATE32: case QGPU_T_DATE64:
-    case QGPU_T_DECIMAL128:
+    case QGPU_T_DECIMAL128: case QGPU_T_TIME32: case QGPU_T_TIME64:
       return;
     default: throw_internal("Unsupported data type in hasher: " + t.str());
   }
@@ -348,8 +348,8 @@ Phys out_phys_of(const DType& t) {
   switch (t.id) {
     case QGPU_T_INT8: return PH_I8;
     case QGPU_T_INT16: return PH_I16;
-    case QGPU_T_INT32: case QGPU_T_DATE32: return PH_I32;
-    case QGPU_T_INT64: case QGPU_T_DATE64: return PH_I64;
+    case QGPU_T_INT32: case QGPU_T_DATE32: case QGPU_T_TIME32: return PH_I32;
+    case QGPU_T_INT64: case QGPU_T_DATE64: case QGPU_T_TIME64: return PH_I64;
     case QGPU_T_UINT8: return PH_U8;
     case QGPU_T_UINT16: return PH_U16;
     case QGPU_T_UINT32: return PH_U32;
@@ -393,10 +393,10 @@ void validate_agg_types(const std::vector<AggSpec>& aggs) {
         break;
       case QGPU_AGG_MIN:
       case QGPU_AGG_MAX:
-        if (!(rt.is_int() || rt.is_float() || rt.is_decimal() || rt.is_date()))
+        if (!(rt.is_int() || rt.is_float() || rt.is_decimal() || rt.is_date() || rt.is_time()))
           throw_internal("PrimitiveAccumulator not supported for datatype: " + rt.str());
         if (!same_native(at, rt)) throw_internal("MIN/MAX input type " + at.str() + " does not match accumulator type " + rt.str());
-        if (rt.is_date())  // scalar.rs:228 ScalarValue::try_from_array has no Date variants -> unimplemented!()
+        if (rt.is_date() || rt.is_time())  // scalar.rs:228 ScalarValue::try_from_array has no Date / Time variants -> unimplemented!()
           throw_internal("data type " + rt.str() + " not supported");
         break;
       default: throw_internal("unknown aggregate operator");

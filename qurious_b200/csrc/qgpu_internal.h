@@ -61,6 +61,7 @@ struct DType {
   bool is_int() const { return is_signed_int() || is_unsigned_int(); }
   bool is_float() const { return id == QGPU_T_FLOAT32 || id == QGPU_T_FLOAT64; }
   bool is_date() const { return id == QGPU_T_DATE32 || id == QGPU_T_DATE64; }
+  bool is_time() const { return id == QGPU_T_TIME32 || id == QGPU_T_TIME64; }  // unit in `scale`: 0 s, 1 ms, 2 us, 3 ns
   std::string str() const;
 };
 inline DType mk_type(int id, int p = 0, int s = 0) {

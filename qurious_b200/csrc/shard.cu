@@ -288,8 +288,8 @@ static Phys key_phys(const DType& t) {
   switch (t.id) {
     case QGPU_T_INT8: return PH_I8;
     case QGPU_T_INT16: return PH_I16;
-    case QGPU_T_INT32: case QGPU_T_DATE32: return PH_I32;
-    case QGPU_T_INT64: case QGPU_T_DATE64: return PH_I64;
+    case QGPU_T_INT32: case QGPU_T_DATE32: case QGPU_T_TIME32: return PH_I32;
+    case QGPU_T_INT64: case QGPU_T_DATE64: case QGPU_T_TIME64: return PH_I64;
     case QGPU_T_UINT8: return PH_U8;
     case QGPU_T_UINT16: return PH_U16;
     case QGPU_T_UINT32: return PH_U32;

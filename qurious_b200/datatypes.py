@@ -75,6 +75,7 @@ class AggregateOperator(enum.IntEnum):
 T_NULL, T_BOOL, T_INT8, T_INT16, T_INT32, T_INT64 = 0, 1, 2, 3, 4, 5
 T_UINT8, T_UINT16, T_UINT32, T_UINT64 = 6, 7, 8, 9
 T_FLOAT32, T_FLOAT64, T_UTF8, T_DATE32, T_DATE64, T_DECIMAL128 = 10, 11, 12, 13, 14, 15
+T_TIME32, T_TIME64 = 16, 17      # unit in the `scale` slot: 0 s, 1 ms, 2 us, 3 ns
 
 _SIMPLE = {
     pa.null(): T_NULL, pa.bool_(): T_BOOL, pa.int8(): T_INT8, pa.int16(): T_INT16,
@@ -90,6 +91,10 @@ def type_triple(dt: pa.DataType) -> tuple[int, int, int]:
         return (T_DECIMAL128, dt.precision, dt.scale)
     if dt in _SIMPLE:
         return (_SIMPLE[dt], 0, 0)
+    if pa.types.is_time32(dt):
+        return (T_TIME32, 0, {"s": 0, "ms": 1}[dt.unit])
+    if pa.types.is_time64(dt):
+        return (T_TIME64, 0, {"us": 2, "ns": 3}[dt.unit])
     raise TypeError(f"InternalError: data type {dt} is not supported by the GPU operators")
 
 
