@@ -546,6 +546,8 @@ def parity_check(q, expect_local, result_of, world, torch):
         if isinstance(res, list):
             got = result_invariants(q, res)
             got_t = torch.tensor([got.get(k, 0) for k in names], dtype=torch.int64, device="cuda")
+            if world > 1 and q == "q3":     # the distributed Q3 result stays sharded: every group on exactly one rank
+                _dist.all_reduce(got_t)
         else:                               # group-by: the result stays in HBM (10^8 groups); this rank's share of the groups
             from qurious_b200.distributed import column_bytes_tensor
             cnt = column_bytes_tensor(res, 2)[0].view(torch.int64)
@@ -590,14 +592,25 @@ def setup_leg(q, args, ctx, rank, world, torch):
             leg["strategy"] = lambda: "%s x%d -> %s" % (xg.last_path, world, plan.last_strategy())
             leg["result_of"] = xg.execute_device
         elif q == "q3":
-            # orders and lineitem row-range sharded, customer replicated: J1 per orders shard, its rows all-gathered
-            # (broadcast build), J2 + aggregate per lineitem shard; groups straddling a shard boundary are merged by
-            # all-gathering the per-rank result rows and re-aggregating them
+            # orders and lineitem row-range sharded, customer replicated; ONE native plan per rank (csrc/exchange.cu):
+            # FinalAggregate <- Aggregate <- Join(Broadcast(J1 over the orders shard), lineitem shard): the J1 rows of all
+            # ranks reach every GPU in one grouped NCCL exchange, groups straddling a shard boundary are merged by a hash
+            # exchange of the partial groups; the result stays sharded
             bj = qd.BroadcastJoinAggregate(ctx, tpch.q3_build_plan(tpch.Database(0.0, dev_tables["customer"], dev_tables["orders"], None)),
                                            lambda b: tpch.q3_probe_plan(b, dev_tables["lineitem"]), world)
 
+            host_t = {"exec": 0.0, "free": 0.0, "n": 0}
+
             def step():
-                bj.execute_device().free()
+                t0 = time.perf_counter()
+                t = bj.execute_device()
+                t1 = time.perf_counter()
+                t.free()
+                host_t["exec"] += t1 - t0
+                host_t["free"] += time.perf_counter() - t1
+                host_t["n"] += 1
+                if os.environ.get("QGPU_BENCH_HOSTTIME") and host_t["n"] % 10 == 0:
+                    print("[bench] q3 host ms per step: execute_device %.3f, free %.3f" % (1e3 * host_t["exec"] / host_t["n"], 1e3 * host_t["free"] / host_t["n"]), file=sys.stderr)
             leg["strategy"] = lambda: bj.last_strategy
             leg["result_of"] = bj.execute
         else:

@@ -243,6 +243,18 @@ int qgpu_plan_nested_loop_join(qgpu_ctx* ctx, qgpu_plan* left, qgpu_plan* right,
  * equi-condition links a and b: optimizer/rule/eliminate_cross_join.rs).  Rows come out left-row major; the reference's
  * order additionally depends on its inputs' batch boundaries (one batch per (left batch, right batch, left row)). */
 int qgpu_plan_cross_join(qgpu_ctx* ctx, qgpu_plan* left, qgpu_plan* right, qgpu_plan** out);
+/* ---- exchange operators of a distributed plan (one process per GPU, qgpu_comm_init first) -----------------
+ * The reference is single-process: these two nodes are what a distributed planner inserts around its operators.
+ * Broadcast: every rank executes `child` over its shard; the rows of ALL ranks (rank order) are this node's output on
+ * every rank -- the build side of a broadcast join.  Fixed-width columns (NULLs allowed).  order_free != 0: the consumer
+ * does not depend on the child's row order (it feeds a hash table), so joins below may emit rows in any order.
+ * FinalAggregate: `child` yields PARTIAL groups per rank; rows are hash-partitioned on the first key column, exchanged
+ * all-to-all and re-aggregated (merge_ops[i] for value_columns[i]: 0 SUM -- partial sums and counts --, 1 MIN, 2 MAX);
+ * every child column must be a key or a value; NULL-free fixed-width columns.  The result stays sharded: each final group
+ * is returned by exactly one rank.  Without a communicator (or world 1) both nodes are the identity. */
+int qgpu_plan_broadcast(qgpu_ctx* ctx, qgpu_plan* child, int32_t order_free, qgpu_plan** out);
+int qgpu_plan_final_aggregate(qgpu_ctx* ctx, qgpu_plan* child, const int32_t* key_columns, int32_t n_keys,
+                              const int32_t* value_columns, const int32_t* merge_ops, int32_t n_values, qgpu_plan** out);
 /* PhysicalPlan::schema (physical/plan/mod.rs:26) */
 int qgpu_plan_schema(const qgpu_plan* p, struct ArrowSchema* out);
 /* PhysicalPlan::execute (physical/plan/mod.rs:27): runs the whole subtree on the GPU (intermediate

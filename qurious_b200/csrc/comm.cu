@@ -3,7 +3,10 @@
 #include <nccl.h>
 #include <unistd.h>
 
+#include <chrono>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
 
 #include "comm.h"
 
@@ -122,8 +125,34 @@ void comm_init(Ctx* ctx, const void* id128, int rank, int world) {
   comm_barrier(ctx);  // every rank has zeroed its flags before anybody's first epoch can arrive
 }
 
+// In-process groups: the ranks are threads of one process.  A grouped exchange is a host rendezvous -- every rank posts its
+// send list, waits for the others, copies what is addressed to it on its own stream, and nobody leaves before all copies
+// are done (the send buffers stay alive).
+struct LocalGroup {
+  std::mutex mu;
+  std::condition_variable cv;
+  int world = 1, arrived = 0;
+  unsigned long long gen = 0;
+  std::vector<std::vector<Xfer>> sends;
+  void barrier() {
+    std::unique_lock<std::mutex> lk(mu);
+    const unsigned long long g = gen;
+    if (++arrived == world) {
+      arrived = 0;
+      ++gen;
+      cv.notify_all();
+    } else if (!cv.wait_for(lk, std::chrono::seconds(120), [&] { return gen != g; })) {
+      --arrived;
+      throw QError(QGPU_ERR_NCCL, "NcclError: a rank of the in-process group never arrived at the exchange");
+    }
+  }
+};
+
 void comm_init_local(Ctx** ctxs, int n) {
   if (n < 1 || n > COMM_MAX_WORLD) throw_internal("qgpu_comm_init_local: 1 to 8 contexts");
+  auto group = std::make_shared<LocalGroup>();
+  group->world = n;
+  group->sends.resize((size_t)n);
   std::vector<std::shared_ptr<Comm>> cs;
   for (int r = 0; r < n; ++r) {
     if (ctxs[r]->comm) throw_internal("qgpu_comm_init_local: context already has a communicator");
@@ -132,6 +161,7 @@ void comm_init_local(Ctx** ctxs, int n) {
     c->world = n;
     c->rank = r;
     c->local = true;
+    c->group = group;
     CUDA_CHECK(cudaSetDevice(ctxs[r]->device));
     alloc_symmetric(*c);
     CUDA_CHECK(cudaStreamSynchronize(ctxs[r]->stream));
@@ -182,7 +212,68 @@ void comm_all_to_all(Ctx* ctx, const void* send, const int64_t* send_off, const 
   nccl_check(api.GroupEnd(), "ncclGroupEnd");
 }
 
+void comm_exchange(Ctx* ctx, const std::vector<Xfer>& sends, const std::vector<Xfer>& recvs) {
+  if (!ctx->comm) throw_nccl("no communicator: call qgpu_comm_init first");
+  Comm& c = *ctx->comm;
+  if (!c.local) {
+    NcclApi& api = nccl_api();
+    nccl_check(api.GroupStart(), "ncclGroupStart");
+    for (const Xfer& x : sends)
+      if (x.bytes) nccl_check(api.Send(x.ptr, x.bytes, ncclUint8, x.peer, (ncclComm_t)c.nccl, ctx->stream), "ncclSend");
+    for (const Xfer& x : recvs)
+      if (x.bytes) nccl_check(api.Recv(x.ptr, x.bytes, ncclUint8, x.peer, (ncclComm_t)c.nccl, ctx->stream), "ncclRecv");
+    nccl_check(api.GroupEnd(), "ncclGroupEnd");
+    return;
+  }
+  LocalGroup& g = *c.group;
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // my send buffers are complete
+  {
+    std::lock_guard<std::mutex> lk(g.mu);
+    g.sends[(size_t)c.rank] = sends;
+  }
+  g.barrier();
+  std::vector<size_t> next((size_t)c.world, 0);  // per peer: how many of its sends addressed to me were consumed
+  std::string err;
+  for (const Xfer& x : recvs) {
+    const std::vector<Xfer>& ps = g.sends[(size_t)x.peer];
+    size_t& k = next[(size_t)x.peer];
+    while (k < ps.size() && ps[k].peer != c.rank) ++k;
+    if (k >= ps.size() || ps[k].bytes != x.bytes) {
+      err = "grouped exchange: a receive has no matching send of the same size";
+      break;
+    }
+    if (x.bytes && cudaMemcpyAsync(x.ptr, ps[k].ptr, x.bytes, cudaMemcpyDefault, ctx->stream) != cudaSuccess) {
+      err = "grouped exchange: device copy failed";
+      break;
+    }
+    ++k;
+  }
+  cudaStreamSynchronize(ctx->stream);
+  g.barrier();  // every rank has copied: the send buffers may go
+  if (!err.empty()) throw_nccl(err);
+}
+
+void comm_all_gather_any(Ctx* ctx, const void* send, void* recv, size_t bytes_per_rank) {
+  if (!ctx->comm) throw_nccl("no communicator: call qgpu_comm_init first");
+  Comm& c = *ctx->comm;
+  if (!c.local) {
+    comm_all_gather(ctx, send, recv, bytes_per_rank);
+    return;
+  }
+  std::vector<Xfer> sends, recvs;
+  for (int r = 0; r < c.world; ++r) {
+    sends.push_back({r, (void*)send, bytes_per_rank});
+    recvs.push_back({r, (char*)recv + (size_t)r * bytes_per_rank, bytes_per_rank});
+  }
+  comm_exchange(ctx, sends, recvs);
+}
+
 void comm_barrier(Ctx* ctx) {
+  if (ctx->comm && ctx->comm->local) {
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->comm->group->barrier();
+    return;
+  }
   Comm& c = need_nccl(ctx);
   DBufP b = ctx->alloc_zero(8 * (size_t)(c.world + 1));
   nccl_check(nccl_api().AllGather(b->ptr, (char*)b->ptr + 8, 8, ncclUint8, (ncclComm_t)c.nccl, ctx->stream), "ncclAllGather(barrier)");

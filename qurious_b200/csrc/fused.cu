@@ -2945,6 +2945,10 @@ static bool join_aggregate_body(PlanNode& agg, View* out) {
 static uint64_t subtree_signature(PlanNode& n) {
   uint64_t h = 0x9e3779b97f4a7c15ULL * (uint64_t)n.kind;
   auto mix = [&](uint64_t x) { h = (h ^ x) * 0xff51afd7ed558ccdULL; h ^= h >> 29; };
+  if (n.kind == PK_BROADCAST) {  // what EVERY rank contributed (the node runs now, once per call: exchange.cu)
+    mix(broadcast_signature(n));
+    return h;
+  }
   if (n.kind == PK_SCAN && n.table) {
     n.table->consolidate();
     mix((uint64_t)(uintptr_t)n.table.get());
@@ -2954,6 +2958,35 @@ static uint64_t subtree_signature(PlanNode& n) {
   }
   for (auto& c : n.children) mix(subtree_signature(*c));
   return h;
+}
+
+uint64_t local_subtree_signature(PlanNode& n) { return subtree_signature(n); }
+
+View run_speculated(PlanNode& owner, uint64_t signature, const std::function<View()>& body) {
+  Ctx* ctx = owner.ctx;
+  if (ctx->spec) return body();  // already inside an enclosing scope
+  if (!owner.spec) owner.spec = std::make_shared<Speculation>();
+  Speculation& sp = *owner.spec;
+  if (signature != owner.spec_sig) sp.have = false;
+  owner.spec_sig = signature;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    SpecScope scope(ctx, &sp);
+    const bool replay = sp.replay;
+    try {
+      View v = body();
+      if (!replay) {
+        sp.have = !sp.learned.empty();
+        return v;
+      }
+      if (v.pending ? scope.defer_verify(v.pending) : scope.verify()) return v;
+    } catch (SpeculationMiss&) {
+      if (!replay) throw_internal("speculation miss outside a replay (internal error)");
+    } catch (QError&) {
+      if (!replay) throw;
+    }
+    sp.have = false;
+  }
+  throw_internal("speculated execution did not settle");
 }
 
 // Speculative re-execution: the first execution of the join pipeline learns its device-side counts (selection sizes,

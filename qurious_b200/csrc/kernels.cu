@@ -991,6 +991,36 @@ __global__ void __launch_bounds__(256) k_minmax(const T* __restrict__ src, const
   }
 }
 
+__global__ void k_init_minmax(long long* __restrict__ mn_mx) {
+  if (threadIdx.x == 0) {
+    mn_mx[0] = INT64_MAX;
+    mn_mx[1] = INT64_MIN;
+  }
+}
+// min / max of the non-NULL values into dev_mn_mx[0..1] (INT64_MAX / INT64_MIN when there are none), no host round trip;
+// false: the column's physical type has no integer statistics
+bool stats_to_device(Ctx* ctx, const DCol& col, long long* dev_mn_mx) {
+  LAUNCH(ctx, k_init_minmax, 1, 32, 0, dev_mn_mx);
+  if (col.length == 0 || col.null_count == col.length || !col.data) return col.phys != PH_STR;
+  const uint32_t* val = col.validity ? (const uint32_t*)col.validity->ptr : nullptr;
+  const int g = grid_for(ctx, col.length, 256 * 4);
+  long long* mn = dev_mn_mx;
+  long long* mx = dev_mn_mx + 1;
+  switch (col.phys) {
+    case PH_I8: LAUNCH(ctx, k_minmax<int8_t>, g, 256, 0, (const int8_t*)col.data->ptr, val, col.length, mn, mx); break;
+    case PH_I16: LAUNCH(ctx, k_minmax<int16_t>, g, 256, 0, (const int16_t*)col.data->ptr, val, col.length, mn, mx); break;
+    case PH_I32: LAUNCH(ctx, k_minmax<int32_t>, g, 256, 0, (const int32_t*)col.data->ptr, val, col.length, mn, mx); break;
+    case PH_I64: case PH_D64:
+      LAUNCH(ctx, k_minmax<int64_t>, g, 256, 0, (const int64_t*)col.data->ptr, val, col.length, mn, mx);
+      break;
+    case PH_U8: LAUNCH(ctx, k_minmax<uint8_t>, g, 256, 0, (const uint8_t*)col.data->ptr, val, col.length, mn, mx); break;
+    case PH_U16: LAUNCH(ctx, k_minmax<uint16_t>, g, 256, 0, (const uint16_t*)col.data->ptr, val, col.length, mn, mx); break;
+    case PH_U32: LAUNCH(ctx, k_minmax<uint32_t>, g, 256, 0, (const uint32_t*)col.data->ptr, val, col.length, mn, mx); break;
+    default: return false;
+  }
+  return true;
+}
+
 void ensure_stats(Ctx* ctx, DCol& col) {
   if (col.has_stats || col.length == 0 || col.null_count == col.length) return;
   struct { long long mn; long long mx; } h = {INT64_MAX, INT64_MIN};

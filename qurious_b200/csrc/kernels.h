@@ -30,6 +30,7 @@ View apply_selection_view(Ctx* ctx, const View& v, const IdxP& sel);
 // Try to narrow a 16 B Decimal128 column to int64; returns nullptr if some value does not fit.
 DColP try_narrow_decimal(Ctx* ctx, const DCol& wide);
 void ensure_stats(Ctx* ctx, DCol& col);  // min/max over non-null values (ints, dates, decimals)
+bool stats_to_device(Ctx* ctx, const DCol& col, long long* dev_mn_mx);  // the same into device words, no host round trip
 void copy_bits(Ctx* ctx, uint32_t* dst, int64_t dst_bit, const uint32_t* src, int64_t src_bit, int64_t n);
 void fill_bits(Ctx* ctx, uint32_t* dst, int64_t dst_bit, int64_t n, bool value);
 void rebase_offsets(Ctx* ctx, int32_t* dst, const int32_t* src, int64_t n_plus_1, int64_t add);

@@ -1187,7 +1187,7 @@ View run_cross_join(Ctx* ctx, const View& left, const View& right, const Schema&
 }
 
 // rows of [0, n) whose bit in `visited` is (invert ? clear : set), ascending
-static IdxP rows_by_bit(Ctx* ctx, const DBufP& visited, int64_t n, int invert) {
+IdxP rows_by_bit(Ctx* ctx, const DBufP& visited, int64_t n, int invert) {
   if (n <= 0) return make_idx(ctx, 0, false);
   const int64_t words = (n + 31) >> 5;
   DBufP keep = ctx->alloc((size_t)words * 4);

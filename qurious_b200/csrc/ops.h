@@ -77,6 +77,8 @@ View run_nested_loop_join(Ctx* ctx, const View& left, const View& right, int joi
 View run_cross_join(Ctx* ctx, const View& left, const View& right, const Schema& out_schema);
 
 Schema build_join_schema(const Schema& left, const Schema& right, int join_type);
+// rows of [0, n) whose bit in the bitmap is (invert ? clear : set), ascending
+IdxP rows_by_bit(Ctx* ctx, const DBufP& bits, int64_t n, int invert);
 
 // MIN / MAX start value of the accumulator for argument type `at` (min.rs / max.rs: NATIVE::MAX / NATIVE::MIN of the array's
 // native type) as the (lo, hi) words the accumulators and finish_aggregate use; floats travel as their total-order key.

@@ -325,6 +325,8 @@ View PlanNode::execute() {
       strategy = "nested-loop-join(cross pairs + filter, late-materialisation)";
       return run_nested_loop_join(ctx, l, r, join_type, has_join_filter ? &fs : nullptr, schema);
     }
+    case PK_BROADCAST: return run_broadcast(*this);
+    case PK_FINAL_AGG: return run_final_aggregate(*this);
     case PK_CROSS_JOIN: {
       View l = child_view(0);
       View r = child_view(1);
@@ -358,6 +360,7 @@ static int guard(Ctx* ctx, F&& f) {
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) throw QError(QGPU_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
+    ++ctx->exec_epoch;
     f();
     return QGPU_OK;
   } catch (QError& e) {
@@ -913,6 +916,34 @@ int qgpu_plan_cross_join(qgpu_ctx* ctx, qgpu_plan* left, qgpu_plan* right, qgpu_
     n->children.push_back(right->node);
     n->join_type = QGPU_JOIN_INNER;
     n->schema = build_join_schema(left->node->schema, right->node->schema, QGPU_JOIN_INNER);  // fields and qualifiers concatenated
+    *out = new qgpu_plan{n};
+  });
+}
+
+int qgpu_plan_broadcast(qgpu_ctx* ctx, qgpu_plan* child, int32_t order_free, qgpu_plan** out) {
+  if (!ctx || !child || !out) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] {
+    auto n = new_node(ctx, PK_BROADCAST);
+    n->children.push_back(child->node);
+    n->schema = child->node->schema;
+    n->order_free = order_free != 0;
+    *out = new qgpu_plan{n};
+  });
+}
+
+int qgpu_plan_final_aggregate(qgpu_ctx* ctx, qgpu_plan* child, const int32_t* key_columns, int32_t n_keys, const int32_t* value_columns,
+                              const int32_t* merge_ops, int32_t n_values, qgpu_plan** out) {
+  if (!ctx || !child || !out || !key_columns || n_keys <= 0 || n_values < 0 || (n_values > 0 && (!value_columns || !merge_ops)))
+    return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] {
+    auto n = new_node(ctx, PK_FINAL_AGG);
+    n->children.push_back(child->node);
+    n->schema = child->node->schema;
+    n->exchange_keys.assign(key_columns, key_columns + n_keys);
+    n->exchange_cols.assign(value_columns, value_columns + n_values);
+    n->exchange_ops.assign(merge_ops, merge_ops + n_values);
+    for (int op : n->exchange_ops)
+      if (op < 0 || op > 2) throw_internal("FinalAggregate: merge operator must be 0 (SUM), 1 (MIN) or 2 (MAX)");
     *out = new qgpu_plan{n};
   });
 }

@@ -4,7 +4,7 @@
 
 namespace qgpu {
 
-enum PlanKind { PK_SCAN = 1, PK_FILTER, PK_PROJECTION, PK_AGGREGATE, PK_HASH_JOIN, PK_SORT, PK_LIMIT, PK_NL_JOIN, PK_CROSS_JOIN };
+enum PlanKind { PK_SCAN = 1, PK_FILTER, PK_PROJECTION, PK_AGGREGATE, PK_HASH_JOIN, PK_SORT, PK_LIMIT, PK_NL_JOIN, PK_CROSS_JOIN, PK_BROADCAST, PK_FINAL_AGG };
 
 struct AggDesc {
   int op = 0;
@@ -47,6 +47,9 @@ struct PlanNode {
   std::shared_ptr<void> fused_cache;
   std::shared_ptr<Speculation> spec;  // learned device-side counts of this subtree's fused pipeline (fused.cu)
   uint64_t spec_sig = 0;              // identity of the scanned tables the counts were learned on
+  // exchange operators (exchange.cu): Broadcast memo; FinalAggregate key / value columns and merge operators (0 SUM, 1 MIN, 2 MAX)
+  std::shared_ptr<void> exchange_cache;
+  std::vector<int> exchange_keys, exchange_cols, exchange_ops;
   bool order_free = false;  // the consumer does not depend on this node's output row order (qgpu_plan_set_order_free)
   // sharded execution (shard.cu): stop before finalisation / resume from merged states
   AggPending* defer = nullptr;
@@ -73,6 +76,14 @@ int radix_exchange_sketch(PlanNode& root, const int64_t* global_stats, void** de
 int radix_exchange_prepare(PlanNode& root, const void* gathered_host, int world, int rank, void* handles_out, int32_t* n_handles);
 void radix_exchange_scatter(PlanNode& root, const void* all_handles);
 int radix_exchange_finish(PlanNode& root);
+
+// exchange.cu: the two exchange operators of a distributed plan
+View run_broadcast(PlanNode& node);
+uint64_t broadcast_signature(PlanNode& node);  // executes the node (memoised per C-ABI call): identity of what every rank contributed
+View run_final_aggregate(PlanNode& node);
+// fused.cu: runs `body` under the speculation of `owner` (learned device-side counts replayed without host round trips and
+// verified at the end; a wrong guess re-runs in learning mode).  `body` must not issue collectives.
+View run_speculated(PlanNode& owner, uint64_t signature, const std::function<View()>& body);
 
 // sort.cu
 View run_sort(PlanNode& node, const View& input);

@@ -267,6 +267,7 @@ struct Ctx {
   void prof_end(int slot);
   std::string prof_report();  // "name\tlaunches\ttotal_ms\tmax_ms\n" per kernel; resets the log
 
+  unsigned long long exec_epoch = 0;  // one per C-ABI call (guard): exchange nodes memoise their output within a call
   bool async_ok = false;       // inside qgpu_plan_execute_device_async: operators may leave result metadata pending
   size_t epi_smem_set = 0;     // epilogue.cu: dynamic shared memory opt-in done on this device up to this size
   std::shared_ptr<Comm> comm;  // set by qgpu_comm_init / qgpu_comm_init_local

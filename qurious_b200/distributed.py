@@ -471,18 +471,40 @@ def all_gather_table(ctx: _lib.Context, table: _lib.DeviceTable, world: int,
 
 
 class BroadcastJoinAggregate:
-    """Join + aggregate with BOTH inputs row-range sharded (SURVEY 8e "Q3 joins", broadcast variant): every rank runs
-    the build-side sub-plan over its shard, the (small) results are all-gathered over NCCL so that every GPU builds the
-    full join table, then probes it with its shard of the fact table; groups that straddle shard boundaries are merged
-    by GatherMergeAggregate.  probe_plan_of(MemoryTable of the gathered build rows) -> the probe-side plan."""
+    """Join + aggregate with BOTH inputs row-range sharded (SURVEY 8e "Q3 joins", broadcast variant).
+
+    Default: ONE native plan per rank, executed below the C ABI (csrc/exchange.cu):
+        FinalAggregate <- probe_plan_of( Broadcast(build_plan) )
+    Broadcast: every rank runs the build-side sub-plan over its shard (under its own speculation scope: no host round
+    trips after the first execution) and the rows of all ranks reach every GPU in one grouped NCCL exchange, integer
+    statistics included; the probe plan (fused probe + aggregate kernel) then runs over this rank's shard of the fact
+    table; FinalAggregate hash-partitions the partial groups (groups may straddle shard boundaries), exchanges them
+    all-to-all and re-aggregates.  The result STAYS SHARDED: execute() returns this rank's final groups, every group on
+    exactly one rank.  probe_plan_of(build: PhysicalPlan | MemoryTable) -> (Projection <-) HashAggregate plan.
+
+    With an explicit `all_gather_ragged` callable the older host-driven protocol runs instead (all-gather of the build
+    rows, probe, all-gather of the result rows + re-aggregation: every rank gets the whole result) -- hosts with their own
+    collective layer and the single-GPU emulation in the tests."""
 
     def __init__(self, ctx: _lib.Context, build_plan, probe_plan_of: Callable, world: int,
                  all_gather_ragged: Optional[Callable] = None):
         self.ctx, self.build_plan, self.probe_plan_of, self.world = ctx, build_plan, probe_plan_of, int(world)
         self.gather = all_gather_ragged
         self.last_strategy = ""
+        self.plan = None
+        if all_gather_ragged is None:
+            from .physical.plan import Broadcast, FinalAggregate
+            if self.world > 1 and ctx.comm_world()[1] != self.world:
+                init_comm(ctx)
+            probe = probe_plan_of(Broadcast(build_plan, order_free=True))
+            keys, aggs = merge_spec_of(probe)
+            self.plan = FinalAggregate(probe, keys, aggs)
 
     def execute_device(self) -> _lib.DeviceTable:
+        if self.plan is not None:
+            out = self.plan.execute_device(self.ctx)
+            self.last_strategy = self.plan.last_strategy()
+            return out
         from .physical.plan import MemoryTable
         self.build_plan.set_order_free(True, self.ctx)      # the rows feed an all-gather and a hash table
         local = self.build_plan.execute_device(self.ctx)
@@ -500,6 +522,10 @@ class BroadcastJoinAggregate:
         out = [t.to_batch()] if t.num_rows > 0 else []
         t.free()
         return out
+
+    def release(self):
+        if self.plan is not None:
+            self.plan.release()
 
 
 def _dist_all_gather_ragged(cols, widths, n_rows, world):

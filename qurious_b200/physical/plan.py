@@ -554,3 +554,48 @@ class CrossJoin(PhysicalPlan):
         ctx.check(ctx.lib.qgpu_plan_cross_join(ctx.handle, lh, rh, ctypes.byref(h)))
         keep.append(("plan", h))
         return h
+
+
+class Broadcast(PhysicalPlan):
+    """Exchange operator of a distributed plan (no reference counterpart: qurious is single-process): every rank executes
+    `input` over its shard and receives the rows of ALL ranks, in rank order -- the build side of a broadcast join (SURVEY 8e
+    "Q3 joins").  order_free: the consumer does not depend on the input's row order (it feeds a hash table)."""
+
+    def __init__(self, input: PhysicalPlan, order_free: bool = False):
+        self.input, self.order_free, self.schema = input, bool(order_free), input.schema
+
+    def children(self):
+        return [self.input]
+
+    def _build(self, ctx, keep):
+        ch = self.input._build(ctx, keep)
+        h = ctypes.c_void_p()
+        ctx.check(ctx.lib.qgpu_plan_broadcast(ctx.handle, ch, 1 if self.order_free else 0, ctypes.byref(h)))
+        keep.append(("plan", h))
+        return h
+
+
+class FinalAggregate(PhysicalPlan):
+    """Exchange operator of a distributed plan: `input` yields PARTIAL groups per rank (groups may straddle shards); the rows
+    are hash-partitioned on the first key column, exchanged all-to-all and re-aggregated with one merge operator per value
+    column ("sum" for partial sums and counts, "min", "max").  The result stays sharded: every final group is returned by
+    exactly one rank.  keys / values: column indices of `input`'s schema."""
+
+    OPS = {"sum": 0, "min": 1, "max": 2}
+
+    def __init__(self, input: PhysicalPlan, keys: Sequence[int], values: Sequence[Tuple[int, str]]):
+        self.input, self.keys, self.values, self.schema = input, list(keys), list(values), input.schema
+
+    def children(self):
+        return [self.input]
+
+    def _build(self, ctx, keep):
+        ch = self.input._build(ctx, keep)
+        k = (ctypes.c_int32 * len(self.keys))(*self.keys)
+        n = len(self.values)
+        v = (ctypes.c_int32 * max(n, 1))(*[c for c, _ in self.values])
+        o = (ctypes.c_int32 * max(n, 1))(*[self.OPS[m] for _, m in self.values])
+        h = ctypes.c_void_p()
+        ctx.check(ctx.lib.qgpu_plan_final_aggregate(ctx.handle, ch, k, len(self.keys), v, o, n, ctypes.byref(h)))
+        keep.append(("plan", h))
+        return h

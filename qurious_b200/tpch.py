@@ -500,11 +500,13 @@ def q3_build_plan(db: Database) -> Projection:
     return Projection(Q3_BUILD_SCHEMA, j1, [_col(j1.schema, n) for n in Q3_BUILD_SCHEMA.names])
 
 
-def q3_probe_plan(build: MemoryTable, lineitem: MemoryTable) -> Projection:
-    """J2 + aggregate of q3_plan with the (gathered) J1 result as a materialised build side; same output schema."""
+def q3_probe_plan(build, lineitem: MemoryTable) -> Projection:
+    """J2 + aggregate of q3_plan over THIS rank's lineitem shard; same output schema.  build: the J1 rows of all ranks -- a
+    plan producing them (Broadcast(q3_build_plan(...)): the whole step is then one native plan) or a MemoryTable holding
+    them (the host-driven protocol)."""
     O = Operator
     ls = lineitem.schema
-    b_scan = Scan(Q3_BUILD_SCHEMA, build, None, None)
+    b_scan = Scan(Q3_BUILD_SCHEMA, build, None, None) if isinstance(build, MemoryTable) else build
     l_scan = Scan(ls, lineitem, None, _b(_col(ls, "l_shipdate"), O.Gt, _date("1995-03-15")))
     j2 = HashJoinExec.try_new(b_scan, l_scan, JoinType.Inner, [(_col(Q3_BUILD_SCHEMA, "o_orderkey"), _col(ls, "l_orderkey"))], None)
     js = j2.schema
