@@ -432,7 +432,7 @@ def kernel_bytes(kernel, q, per_table, driving, rows_local, groups_local):
     """Algorithmic bytes ONE launch of `kernel` moves, or None when the kernel does not stream a table (no
     roofline fraction is quoted for it): the fused scan kernels read every referenced column of the table they scan once
     (FM_EMIT = J1's probe scan over orders, everything else the driving table); the radix passes move 3 x 8 B tuples."""
-    if kernel.startswith("k_fused_scan_agg"):
+    if kernel.startswith("k_fused_scan_agg"):       # (_spec: ahead-of-time shape, _jit: run-time shape, <FM_*>: generic body)
         return per_table.get("orders" if "FM_EMIT" in kernel else driving)
     if q == "groupby":
         # tuples are 3 x 8 B; groups leave as 6 x 8 B (DESIGN.md 3.1c)
@@ -704,6 +704,36 @@ def run_b200(args):
         roofline["read_only_reference"] = {"gbs": rp, "frac": achieved / rp,
                                            "how": "torch int64 sum over 1.68 GB, measured in this run (reads only; the peak above is a copy)"}
 
+    # ---- the same plan through the other two tile bodies -------------------------------------------------------------------
+    # The headline runs the AHEAD-OF-TIME specialised shape (fused.cu: SIG_Q1 / SIG_Q6).  Every other DENSE plan gets the
+    # same SpecBody instantiated for its shape at RUN TIME (NVRTC, fused_jit.cu): roofline_jit forces that path for this very
+    # workload (QGPU_FUSED_NOAOT=1).  roofline_generic is the interpreted body that remains the fallback (QGPU_FUSED_GENERIC=1:
+    # no NVRTC on the host, a failed compilation) and that the HASH / join-probe modes still run.
+    roofline_generic = roofline_jit = None
+    if world == 1 and q in ("q1", "q6") and not os.environ.get("QGPU_BENCH_SKIP_GENERIC"):
+        def variant(env_name, how):
+            try:
+                os.environ[env_name] = "1"
+                gplan = build_plan(q, dev_tables)           # a fresh plan object: the analysis (and the kernel choice) is per plan
+                gplan.execute_device(ctx).free()
+                gstep = Pipelined(lambda: gplan.execute_device_async(ctx))
+                gsteps = max(3, min(args.steps, 20))
+                gms, gprof, _ = run_query_device(ctx, gstep, gsteps, min(args.warmup, 3), sampler, torch, stream)
+                gtop = sorted(gprof, key=lambda r: -r[2])[0]
+                gtop_ms = gtop[2] / max(gtop[1], 1)
+                gbytes = kernel_bytes(gtop[0], q, per_table, driving, rows_local, 0)
+                gach = gbytes / (gtop_ms / 1e3) / 1e9 if gbytes and gtop_ms > 0 else None
+                out = {"kernel": gtop[0], "kernel_ms_avg": gtop_ms, "achieved": gach, "peak": peak, "unit": "GB/s",
+                       "frac": (gach / peak) if gach else None, "ms_per_step": gms / gsteps, "strategy": gplan.last_strategy(), "how": how}
+                gplan.release()
+                return out
+            except Exception as e:      # context figure: never fatal
+                return {"error": repr(e)[:300]}
+            finally:
+                os.environ.pop(env_name, None)
+        roofline_jit = variant("QGPU_FUSED_NOAOT", "the same plan and tables with QGPU_FUSED_NOAOT=1: SpecBody instantiated for this shape by NVRTC at run time")
+        roofline_generic = variant("QGPU_FUSED_GENERIC", "the same plan and tables with QGPU_FUSED_GENERIC=1: the interpreted tile body")
+
     # ---- end-to-end leg: host Arrow buffers -> operators -> host RecordBatches ---------------------
     e2e = None
     cpu = None
@@ -892,7 +922,7 @@ def run_b200(args):
                 "config": {"workload": workload_string(q, args, world, rows_total),
                            "l2": "inputs larger than L2 (resident columns >> 126 MB), no flush needed",
                            "strategy": strategy, "rows_per_gpu": rows_local},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(round(launches * args.steps)),
+                "roofline": roofline, "roofline_jit": roofline_jit, "roofline_generic": roofline_generic, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(round(launches * args.steps)),
                 "gpu_launches_per_step": launches, "clocks": clocks,
                 "step_ms": main_step_ms, "parity_check": parity,
                 "kernels": [{"name": r[0], "launches": r[1], "total_ms": round(r[2], 4)} for r in prof_sorted[:8]]}

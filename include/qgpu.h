@@ -152,6 +152,12 @@ const char* qgpu_last_error(const qgpu_ctx* ctx);
 /* Compatibility switches for reference quirks: name in {"avg_precision",
  * "empty_decimal_sum"}; value 1 reproduces the reference's failure, 0 (default) the intended value. */
 int qgpu_set_compat(qgpu_ctx* ctx, const char* name, int value);
+/* Run-time specialisation of the fused scan-aggregate kernel (csrc/fused_jit.cu): DENSE plans whose shape has no
+ * ahead-of-time kernel get the same hand-written source instantiated for their shape signature through NVRTC (once per
+ * process and shape; QGPU_JIT=0 disables it, the generic tile body then runs).  qgpu_jit_compile compiles a signature
+ * without a GPU (build checks, tests): returns the CUBIN size in bytes, 0 when the compilation failed or NVRTC is not
+ * installed, -1 on an internal error; the compiler log goes to log_buf (NUL terminated, truncated to cap). */
+int64_t qgpu_jit_compile(const uint64_t* signature4, uint32_t pack, char* log_buf, int64_t cap);
 /* Tuning knobs: "ingest_threads" (host worker threads of the staged ingest, 0 = min(hardware threads, 16); at most 16),
  * "ingest_host_narrow" (1: Decimal128(p <= 18) narrowed to int64 by the host workers while staging -- 8 instead of 16
  * bytes per value cross PCIe; 0: uploaded as 16-byte values and narrowed by one kernel; -1: default = 1). */

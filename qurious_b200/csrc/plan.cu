@@ -3,6 +3,7 @@
 #include <thread>
 
 #include "comm.h"
+#include "fused_jit.h"
 #include "launch.h"
 #include "plan.h"
 
@@ -486,6 +487,23 @@ int qgpu_set_compat(qgpu_ctx* ctx, const char* name, int value) {
     else if (s == "empty_decimal_sum") ctx->c.compat_empty_decimal_sum = value != 0;
     else throw_internal("unknown compat switch '" + s + "'");
   });
+}
+
+int64_t qgpu_jit_compile(const uint64_t* signature4, uint32_t pack, char* log_buf, int64_t cap) {
+  if (!signature4) return -1;
+  try {
+    std::string log;
+    const std::string cubin = jit_compile_cubin(signature4, pack, &log);
+    if (log_buf && cap > 0) {
+      const size_t n = std::min<size_t>((size_t)cap - 1, log.size());
+      memcpy(log_buf, log.data(), n);
+      log_buf[n] = 0;
+    }
+    return (int64_t)cubin.size();
+  } catch (std::exception& e) {
+    g_last_error = e.what();
+    return -1;
+  }
 }
 
 int64_t qgpu_kernel_launches(const qgpu_ctx* ctx) { return ctx ? ctx->c.launches : 0; }

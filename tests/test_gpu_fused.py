@@ -278,3 +278,30 @@ def test_small_string_keys_one_launch_gather(gpu_ctx):
         plan = HashAggregate(out, Scan(schema, t, None, None), [Column("s", 0)],
                              [SumAggregateExpr(Column("v", 1), pa.int64()), CountAggregateExpr(Column("v", 1))])
         run_both(plan, gpu_ctx)
+
+
+def test_unregistered_dense_shape_is_specialised_at_run_time(gpu_ctx, monkeypatch):
+    """A DENSE plan whose shape has no ahead-of-time kernel (MIN / MAX / decimal and Float64 sums over a string key) runs
+    SpecBody instantiated for its signature by NVRTC (csrc/fused_jit.cu); QGPU_JIT=0 runs the interpreted body instead.
+    Both equal the oracle."""
+    t = _table(30000, seed=11)
+    pred = bx(C(t, "d"), "Lt", CastExpr(lit("1994-11-01"), pa.date32()))
+    aggs = [SumAggregateExpr(C(t, "p"), DEC), MinAggregateExpr(C(t, "v"), pa.int64()), MaxAggregateExpr(C(t, "p"), DEC),
+            CountAggregateExpr(C(t, "v")), AvgAggregateExpr(C(t, "f"), pa.float64(), pa.float64())]
+    schema = pa.schema([("s", pa.string())] + [(f"a{i}", a.return_type) for i, a in enumerate(aggs)])
+
+    def make():
+        return HashAggregate(schema, Scan(t.schema, t, None, pred), [C(t, "s")], aggs)
+    ref = sorted(rows_of(qref.execute(make())))
+
+    def check(plan):
+        got = sorted(rows_of(plan.execute(gpu_ctx)))
+        assert len(got) == len(ref)
+        for a, b in zip(got, ref):
+            assert a[:5] == b[:5] and abs(a[5] - b[5]) <= 1e-12 * abs(b[5])
+        return plan.last_strategy()
+    s = check(make())
+    assert "dense-private/shape-specialised at run time" in s, s
+    monkeypatch.setenv("QGPU_JIT", "0")
+    s = check(make())
+    assert "dense-private, " in s and "specialised" not in s, s
