@@ -839,6 +839,45 @@ def run_b200(args):
             r["arrow_c_stream_export_floor_ms"] = 1e3 * (time.perf_counter() - t0)
             paths["pageable_1024_row_batches"] = r
             del small
+        # (iv) file -> HBM: a '|'-delimited text file of the first rows of this run's lineitem (written outside the timed region by
+        # Arrow C++'s CSV writer), read and PARSED ON THE GPU (qgpu_table_append_csv_file, csrc/csv.cu) -- the reference's
+        # `COPY lineitem FROM 'lineitem.tbl' (DELIMITER '|')` route without any host-side Arrow batches
+        if world == 1 and q in ("q1", "q6") and not os.environ.get("QGPU_BENCH_SKIP_CSV"):
+            try:
+                import tempfile
+                import pyarrow.csv as pacsv
+                from qurious_b200 import _lib as qlib
+                n_s = min(6_001_215, host["lineitem"][0].num_rows)
+                sample = host["lineitem"][0].slice(0, n_s)
+                tmpdir = tempfile.mkdtemp(prefix="qgpu_bench_")
+                path = os.path.join(tmpdir, "lineitem.tbl")
+                pacsv.write_csv(sample, path, pacsv.WriteOptions(include_header=False, delimiter="|", quoting_style="none"))
+                fbytes = os.path.getsize(path)
+
+                def one_file():
+                    dev = qlib.DeviceTable.create(ctx, sample.schema)
+                    dev.append_csv(path, has_header=False, delimiter="|")
+                    mt = MemoryTable.from_device_table(dev)
+                    p = build_plan(q, {"lineitem": mt})
+                    out = p.execute(ctx)
+                    p.release()
+                    dev.free()
+                    return out
+                one_file()
+                t0 = time.perf_counter()
+                reps = 3
+                for _ in range(reps):
+                    one_file()
+                dt = (time.perf_counter() - t0) / reps
+                paths["tbl_file_sample"] = {"label": "tbl_file_sample", "value": n_s / dt, "unit": "rows/s", "rows": n_s, "file_bytes": fbytes,
+                                            "ms_per_step": dt * 1e3, "text_gb_per_s": fbytes / dt / 1e9, "steps": reps,
+                                            "path": "lineitem.tbl (first %d rows, '|'-delimited text, page cache) -> qgpu_table_append_csv_file: pread into "
+                                                    "the pinned ring -> H2D -> split + parse kernels -> resident columns -> plan.execute() -> host "
+                                                    "RecordBatches" % n_s}
+                os.remove(path)
+                os.rmdir(tmpdir)
+            except Exception as e:      # context figure: never fatal
+                paths["tbl_file_sample"] = {"error": repr(e)[:300]}
         # (ii) page-locked sources (cudaHostRegister outside the timed region): untransformed columns are DMA'd directly
         regs = []
         for k in host:

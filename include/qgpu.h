@@ -194,6 +194,20 @@ int qgpu_table_append_stream(qgpu_table* t, struct ArrowArrayStream* stream, con
                              int64_t* out_batches);
 /* Upload the retained batches now (otherwise: first use). */
 int qgpu_table_flush(qgpu_table* t);
+/* File -> HBM ingest: replaces read_csv / `COPY t FROM 'x.tbl' (DELIMITER '|')` (datasource/file/csv.rs:16-72,
+ * planner/sql.rs:324-375) for a table whose schema is declared (CREATE TABLE): the raw bytes go to the device and are
+ * split and parsed there into the table's column types (csrc/csv.cu) -- no host-side Arrow batches at all.
+ * CsvReadOptions (csv.rs:16-32): has_header, delimiter (0 = ','), quote / escape (must be 0: not supported on the
+ * device -> QGPU_ERR_INTERNAL).  An empty field is NULL; a trailing delimiter yields one more (empty) field.
+ * _csv: `text` is a HOST buffer of `len` bytes; _csv_file: the library reads the file itself (pread into pinned
+ * memory).  *out_rows (may be NULL) = rows appended.  Parse errors: QGPU_ERR_ARROW with line and column. */
+typedef struct qgpu_csv_options {
+  uint8_t has_header, delimiter, quote, escape;
+} qgpu_csv_options;
+int qgpu_table_append_csv(qgpu_table* t, const void* text, int64_t len, const qgpu_csv_options* options,
+                          const int32_t* upload_columns, int32_t n, int64_t* out_rows);
+int qgpu_table_append_csv_file(qgpu_table* t, const char* path, const qgpu_csv_options* options,
+                               const int32_t* upload_columns, int32_t n, int64_t* out_rows);
 /* Same, but every buffer pointer inside `batch` is a DEVICE pointer on this context's GPU
  * (Arrow C Device Data Interface, device_type ARROW_DEVICE_CUDA); buffers are copied D2D. */
 int qgpu_table_append_device(qgpu_table* t, struct ArrowArray* batch);

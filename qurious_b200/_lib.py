@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_HERE, "libqgpu.so")
 SYMBOLS = [
     "qgpu_init", "qgpu_shutdown", "qgpu_last_error", "qgpu_set_compat", "qgpu_kernel_launches",
     "qgpu_ctx_stream", "qgpu_profile_enable", "qgpu_profile_report",
-    "qgpu_set_option", "qgpu_table_append_stream", "qgpu_table_flush", "qgpu_jit_compile",
+    "qgpu_set_option", "qgpu_table_append_stream", "qgpu_table_flush", "qgpu_jit_compile", "qgpu_table_append_csv", "qgpu_table_append_csv_file",
     "qgpu_table_create", "qgpu_table_append", "qgpu_table_append_device", "qgpu_table_num_rows",
     "qgpu_table_num_batches", "qgpu_table_column_bytes", "qgpu_table_schema", "qgpu_table_export",
     "qgpu_table_free", "qgpu_expr_parse", "qgpu_expr_free", "qgpu_plan_scan", "qgpu_plan_filter",
@@ -49,6 +49,10 @@ class QuriousError(RuntimeError):
 
 class qgpu_type(ctypes.Structure):
     _fields_ = [("id", ctypes.c_uint8), ("precision", ctypes.c_uint8), ("scale", ctypes.c_int8)]
+
+
+class qgpu_csv_options(ctypes.Structure):
+    _fields_ = [("has_header", ctypes.c_uint8), ("delimiter", ctypes.c_uint8), ("quote", ctypes.c_uint8), ("escape", ctypes.c_uint8)]
 
 
 class qgpu_agg_desc(ctypes.Structure):
@@ -95,6 +99,8 @@ def load_library() -> ctypes.CDLL:
     lib.qgpu_table_append_device.argtypes = [vp, vp]
     lib.qgpu_table_append_stream.argtypes = [vp, vp, P(i32), i32, P(i64)]
     lib.qgpu_table_flush.argtypes = [vp]
+    lib.qgpu_table_append_csv.argtypes = [vp, ctypes.c_char_p, i64, P(qgpu_csv_options), P(i32), i32, P(i64)]
+    lib.qgpu_table_append_csv_file.argtypes = [vp, ctypes.c_char_p, P(qgpu_csv_options), P(i32), i32, P(i64)]
     lib.qgpu_set_option.argtypes = [vp, ctypes.c_char_p, i64]
     lib.qgpu_jit_compile.argtypes = [P(ctypes.c_uint64), ctypes.c_uint32, ctypes.c_char_p, i64]
     lib.qgpu_jit_compile.restype = i64
@@ -325,6 +331,21 @@ class DeviceTable:
         else:
             arr = (ctypes.c_int32 * len(upload_columns))(*upload_columns)
             rc = self.ctx.lib.qgpu_table_append_stream(self.handle, _addr(cstream), arr, len(upload_columns), ctypes.byref(got))
+        self.ctx.check(rc)
+        return got.value
+
+    def append_csv(self, source, has_header: bool = True, delimiter: str = ",", quote: Optional[str] = None,
+                   escape: Optional[str] = None, upload_columns: Optional[Sequence[int]] = None) -> int:
+        """`read_csv(path, CsvReadOptions{has_header, delimiter, quote, escape})` (datasource/file/csv.rs:16-72) into this
+        table's declared schema, parsed on the GPU.  source: a path (str) or the file's bytes.  -> rows appended"""
+        opt = qgpu_csv_options(1 if has_header else 0, ord(delimiter), ord(quote) if quote else 0, ord(escape) if escape else 0)
+        got = ctypes.c_int64()
+        arr, n = (None, 0) if upload_columns is None else ((ctypes.c_int32 * len(upload_columns))(*upload_columns), len(upload_columns))
+        if isinstance(source, (bytes, bytearray, memoryview)):
+            b = bytes(source)
+            rc = self.ctx.lib.qgpu_table_append_csv(self.handle, b, len(b), ctypes.byref(opt), arr, n, ctypes.byref(got))
+        else:
+            rc = self.ctx.lib.qgpu_table_append_csv_file(self.handle, str(source).encode(), ctypes.byref(opt), arr, n, ctypes.byref(got))
         self.ctx.check(rc)
         return got.value
 

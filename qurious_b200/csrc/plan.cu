@@ -641,6 +641,49 @@ int qgpu_table_append_stream(qgpu_table* t, struct ArrowArrayStream* stream, con
   return rc;
 }
 
+static int table_append_csv(qgpu_table* t, const void* host_text, int64_t len, const char* path, const qgpu_csv_options* options,
+                            const int32_t* cols, int32_t n, int64_t* out_rows) {
+  if (!t || (!host_text && !path) || len < 0) return QGPU_ERR_INTERNAL;
+  TableImpl& ti = *t->t;
+  return guard(ti.ctx, [&] {
+    ti.resolve();
+    qgpu_csv_options opt;
+    memset(&opt, 0, sizeof(opt));
+    if (options) opt = *options;
+    const std::vector<char> want = want_columns(ti.schema, cols, n);
+    ti.flush_pending();  // row order: earlier host batches first
+    DBufP text;
+    int64_t bytes = len;
+    if (path) {
+      text = read_file_to_device(ti.ctx, path, &bytes);
+    } else {
+      text = ti.ctx->alloc(std::max<size_t>((size_t)len, 16));
+      if (len > 0) ti.ctx->h2d(text->ptr, host_text, (size_t)len);
+    }
+    TableChunk ch = parse_csv_device(ti.ctx, ti.schema, want, (const unsigned char*)text->ptr, bytes, opt);
+    if (ti.consolidated && ti.num_batches > 0) {  // re-open: keep the consolidated columns as the first chunk
+      TableChunk first;
+      first.cols = ti.cols;
+      first.rows = ti.num_rows;
+      ti.chunks.push_back(first);
+    }
+    ti.chunks.push_back(ch);
+    ti.num_rows += ch.rows;
+    ti.num_batches += std::max<int64_t>(1, (ch.rows + 1023) / 1024);  // the reference's reader yields 1024-row batches (csv.rs:63-66)
+    ti.consolidated = false;
+    if (out_rows) *out_rows = ch.rows;
+  });
+}
+
+int qgpu_table_append_csv(qgpu_table* t, const void* text, int64_t len, const qgpu_csv_options* options, const int32_t* upload_columns,
+                          int32_t n, int64_t* out_rows) {
+  return table_append_csv(t, text, len, nullptr, options, upload_columns, n, out_rows);
+}
+int qgpu_table_append_csv_file(qgpu_table* t, const char* path, const qgpu_csv_options* options, const int32_t* upload_columns, int32_t n,
+                               int64_t* out_rows) {
+  return table_append_csv(t, nullptr, 0, path, options, upload_columns, n, out_rows);
+}
+
 int qgpu_table_flush(qgpu_table* t) {
   if (!t) return QGPU_ERR_INTERNAL;
   TableImpl& ti = *t->t;

@@ -408,6 +408,10 @@ Schema import_schema(const ArrowSchema* s);
 void export_schema(const Schema& s, ArrowSchema* out);
 TableChunk import_batch(Ctx* ctx, const Schema& schema, ArrowArray* batch, const int32_t* upload_columns,
                         int32_t n_upload, bool device_resident);
+// ---- csv.cu ------------------------------------------------------------------------------------
+TableChunk parse_csv_device(Ctx* ctx, const Schema& schema, const std::vector<char>& want, const unsigned char* text, int64_t len,
+                            const qgpu_csv_options& opt);
+DBufP read_file_to_device(Ctx* ctx, const char* path, int64_t* len_out);
 // ---- ingest.cu ---------------------------------------------------------------------------------
 void validate_host_batch(const Schema& schema, const ArrowArray* batch, const std::vector<char>& want);
 TableChunk import_host_batches(Ctx* ctx, const Schema& schema, const std::vector<ArrowArray>& batches, const std::vector<char>& want,
