@@ -157,6 +157,10 @@ int qgpu_set_compat(qgpu_ctx* ctx, const char* name, int value);
  * process and shape; QGPU_JIT=0 disables it, the generic tile body then runs).  qgpu_jit_compile compiles a signature
  * without a GPU (build checks, tests): returns the CUBIN size in bytes, 0 when the compilation failed or NVRTC is not
  * installed, -1 on an internal error; the compiler log goes to log_buf (NUL terminated, truncated to cap). */
+/* Monotonic counters of a context: "alloc_bytes" (bytes of every device allocation: all temporaries an execution
+ * creates -- index vectors, gathered columns, accumulator tables), "gather_bytes" (payload bytes written by column
+ * gathers: what late materialisation finally copies), "kernel_launches".  -1: unknown name. */
+int64_t qgpu_counter(const qgpu_ctx* ctx, const char* name);
 int64_t qgpu_jit_compile(const uint64_t* signature4, uint32_t pack, char* log_buf, int64_t cap);
 /* Tuning knobs: "ingest_threads" (host worker threads of the staged ingest, 0 = min(hardware threads, 16); at most 16),
  * "ingest_host_narrow" (1: Decimal128(p <= 18) narrowed to int64 by the host workers while staging -- 8 instead of 16

@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_HERE, "libqgpu.so")
 SYMBOLS = [
     "qgpu_init", "qgpu_shutdown", "qgpu_last_error", "qgpu_set_compat", "qgpu_kernel_launches",
     "qgpu_ctx_stream", "qgpu_profile_enable", "qgpu_profile_report",
-    "qgpu_set_option", "qgpu_table_append_stream", "qgpu_table_flush", "qgpu_jit_compile", "qgpu_table_append_csv", "qgpu_table_append_csv_file",
+    "qgpu_set_option", "qgpu_table_append_stream", "qgpu_table_flush", "qgpu_jit_compile", "qgpu_counter", "qgpu_table_append_csv", "qgpu_table_append_csv_file",
     "qgpu_table_create", "qgpu_table_append", "qgpu_table_append_device", "qgpu_table_num_rows",
     "qgpu_table_num_batches", "qgpu_table_column_bytes", "qgpu_table_schema", "qgpu_table_export",
     "qgpu_table_free", "qgpu_expr_parse", "qgpu_expr_free", "qgpu_plan_scan", "qgpu_plan_filter",
@@ -104,6 +104,8 @@ def load_library() -> ctypes.CDLL:
     lib.qgpu_set_option.argtypes = [vp, ctypes.c_char_p, i64]
     lib.qgpu_jit_compile.argtypes = [P(ctypes.c_uint64), ctypes.c_uint32, ctypes.c_char_p, i64]
     lib.qgpu_jit_compile.restype = i64
+    lib.qgpu_counter.argtypes = [vp, ctypes.c_char_p]
+    lib.qgpu_counter.restype = i64
     lib.qgpu_table_num_rows.argtypes = [vp]
     lib.qgpu_table_num_rows.restype = i64
     lib.qgpu_table_num_batches.argtypes = [vp]
@@ -198,6 +200,10 @@ class Context:
     def release_cached_memory(self):
         """Give the context's cached large device blocks back to the driver."""
         self.check(self.lib.qgpu_release_cached_memory(self.handle))
+
+    def counter(self, name: str) -> int:
+        """qgpu_counter: "alloc_bytes", "gather_bytes", "kernel_launches"."""
+        return int(self.lib.qgpu_counter(self.handle, name.encode()))
 
     def kernel_launches(self) -> int:
         return int(self.lib.qgpu_kernel_launches(self.handle))

@@ -24,6 +24,7 @@ static inline size_t padded_size(size_t n) { return ((n + 255) / 256) * 256 + 25
 
 DBuf::DBuf(Ctx* c, size_t n) : ctx(c), bytes(n) {
   const size_t alloc = padded_size(n);
+  c->alloc_bytes_total += (int64_t)n;
   if (alloc >= kBigBlock) {
     for (size_t i = 0; i < c->big_free.size(); ++i)
       if (c->big_free[i].first == alloc) {
@@ -811,6 +812,8 @@ DColP take_column(Ctx* ctx, const DCol& base, const int64_t* idx, int64_t n, boo
   }
   const int g = grid_for(ctx, n, 256);
   const int64_t n_words = (n + 31) >> 5;
+  ctx->gather_bytes_total += base.phys == PH_STR ? (n + 1) * 4 + (base.length > 0 ? (int64_t)((double)base.str_bytes / (double)base.length * (double)n) : 0)
+                                                 : (base.phys == PH_BIT ? n_words * 4 : n * phys_width(base.phys));
   // validity: a NULL index or a NULL source slot => NULL (skipped when neither can occur)
   if (base.null_count != 0 || idx_may_have_null) {
     col->validity = ctx->alloc(std::max<size_t>((size_t)n_words * 4, 4));

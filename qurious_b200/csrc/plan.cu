@@ -506,6 +506,15 @@ int64_t qgpu_jit_compile(const uint64_t* signature4, uint32_t pack, char* log_bu
   }
 }
 
+int64_t qgpu_counter(const qgpu_ctx* ctx, const char* name) {
+  if (!ctx || !name) return -1;
+  const std::string s(name);
+  if (s == "alloc_bytes") return ctx->c.alloc_bytes_total;
+  if (s == "gather_bytes") return ctx->c.gather_bytes_total;
+  if (s == "kernel_launches") return ctx->c.launches;
+  return -1;
+}
+
 int64_t qgpu_kernel_launches(const qgpu_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
 
 int qgpu_release_cached_memory(qgpu_ctx* ctx) {

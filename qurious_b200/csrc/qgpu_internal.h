@@ -238,6 +238,9 @@ struct Ctx {
   std::recursive_mutex mu;
   std::string last_error;
   int64_t launches = 0;
+  // qgpu_counter: bytes of every device allocation (all temporaries: index vectors, gathered columns, tables) and the
+  // payload bytes written by column gathers (take_column) since the context was created
+  int64_t alloc_bytes_total = 0, gather_bytes_total = 0;
   int sm_count = 148;
   bool compat_avg_precision = false;
   bool compat_empty_decimal_sum = false;
