@@ -21,7 +21,10 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <cstring>
+#include <mutex>
+#include <thread>
 
 #include "kernels.h"
 #include "launch.h"
@@ -492,7 +495,9 @@ TableChunk parse_csv_device(Ctx* ctx, const Schema& schema, const std::vector<ch
   return ch;
 }
 
-// the file's bytes -> one device buffer: pread into the pinned ring slots, one cudaMemcpyAsync per slot
+// the file's bytes -> one device buffer: worker threads pread 2 MiB ranges straight into their pinned ring slots (two per
+// worker: the DMA of one overlaps the read of the other), one cudaMemcpyAsync per slot -- the same ring and threads as the
+// staged Arrow ingest (ingest.cu).  A single pread thread tops out at ~5.4 GB/s from the page cache.
 DBufP read_file_to_device(Ctx* ctx, const char* path, int64_t* len_out) {
   const int fd = open(path, O_RDONLY);
   if (fd < 0) throw_internal(std::string("file path: ") + path + ", err: " + strerror(errno));
@@ -504,32 +509,69 @@ DBufP read_file_to_device(Ctx* ctx, const char* path, int64_t* len_out) {
   const int64_t len = (int64_t)st.st_size;
   *len_out = len;
   DBufP buf = ctx->alloc(std::max<size_t>((size_t)len, 16));
+  const size_t slot_bytes = ctx->ingest_slot_bytes;
+  const size_t ring_bytes = ctx->stage_bytes * Ctx::kStageSlots;
+  const int64_t n_tasks = (len + (int64_t)slot_bytes - 1) / (int64_t)slot_bytes;
+  int threads = ctx->ingest_threads > 0 ? ctx->ingest_threads : (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+  threads = (int)std::min<size_t>((size_t)threads, ring_bytes / (2 * slot_bytes));
+  threads = (int)std::max<int64_t>(1, std::min<int64_t>(threads, n_tasks));
+  while ((int)ctx->ingest_ev.size() < threads * 2) {
+    cudaEvent_t e;
+    CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->ingest_ev.push_back(e);
+  }
   for (int i = 0; i < Ctx::kStageSlots; ++i) CUDA_CHECK(cudaEventSynchronize(ctx->stage_ev[i]));
   cudaEvent_t ready;
   CUDA_CHECK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventRecord(ready, ctx->stream));
   CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ready, 0));
   CUDA_CHECK(cudaEventDestroy(ready));
-  int64_t off = 0;
-  int s = 0;
+  const size_t per_half = ctx->stage_bytes / slot_bytes;
+  auto slot_ptr = [&](int s) {
+    return (size_t)s < per_half ? (char*)ctx->stage[0] + (size_t)s * slot_bytes : (char*)ctx->stage[1] + ((size_t)s - per_half) * slot_bytes;
+  };
+  std::atomic<int64_t> next(0);
+  std::mutex err_mu;
   std::string err;
-  while (off < len) {
-    const size_t n = (size_t)std::min<int64_t>((int64_t)ctx->stage_bytes, len - off);
-    cudaEventSynchronize(ctx->stage_ev[s]);
-    size_t got = 0;
-    while (got < n) {
-      const ssize_t r = pread(fd, (char*)ctx->stage[s] + got, n - got, off + (int64_t)got);
-      if (r <= 0) {
-        err = std::string("read error on ") + path;
+  auto worker = [&](int w) {
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return;
+    int cur = 0;
+    bool used[2] = {false, false};
+    for (;;) {
+      const int64_t t = next.fetch_add(1);
+      if (t >= n_tasks) break;
+      const int64_t off = t * (int64_t)slot_bytes;
+      const size_t n = (size_t)std::min<int64_t>((int64_t)slot_bytes, len - off);
+      const int s = w * 2 + cur;
+      if (used[cur]) cudaEventSynchronize(ctx->ingest_ev[s]);
+      char* slot = slot_ptr(s);
+      size_t got = 0;
+      while (got < n) {
+        const ssize_t r = pread(fd, slot + got, n - got, off + (int64_t)got);
+        if (r <= 0) break;
+        got += (size_t)r;
+      }
+      bool bad = got < n;
+      if (!bad) {
+        bad = cudaMemcpyAsync((char*)buf->ptr + off, slot, n, cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess ||
+              cudaEventRecord(ctx->ingest_ev[s], ctx->copy_stream) != cudaSuccess;
+        used[cur] = true;
+      }
+      if (bad) {
+        std::lock_guard<std::mutex> lk(err_mu);
+        if (err.empty()) err = std::string("read error on ") + path;
         break;
       }
-      got += (size_t)r;
+      cur ^= 1;
     }
-    if (!err.empty()) break;
-    CUDA_CHECK(cudaMemcpyAsync((char*)buf->ptr + off, ctx->stage[s], n, cudaMemcpyHostToDevice, ctx->copy_stream));
-    CUDA_CHECK(cudaEventRecord(ctx->stage_ev[s], ctx->copy_stream));
-    off += (int64_t)n;
-    s = (s + 1) % Ctx::kStageSlots;
+  };
+  if (threads == 1) {
+    worker(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int w = 1; w < threads; ++w) pool.emplace_back(worker, w);
+    worker(0);
+    for (auto& th : pool) th.join();
   }
   close(fd);
   CUDA_CHECK(cudaStreamSynchronize(ctx->copy_stream));

@@ -275,39 +275,63 @@ __global__ void __launch_bounds__(256) k_dict_insert(const int32_t* __restrict__
   for (int i = threadIdx.x; i < DICT_LCAP; i += blockDim.x) l_val[i] = DICT_L_EMPTY;
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride) {
+  // four rows per iteration: their offsets and (short) values are loaded before the first table probe, so that the
+  // dependent chain offsets -> bytes -> probe of one row overlaps the others'; the abort flag (too many distinct values)
+  // is polled once per iteration, not per row
+  constexpr int U = 4;
+  for (int64_t row0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row0 < n; row0 += stride * U) {
     if (*(volatile int*)abort_flag) return;
-    const int32_t o0 = offs[row], len = offs[row + 1] - o0;
-    uint32_t s;
-    if (len <= 8) {
-      unsigned long long key = 0;
-      for (int i = 0; i < len; ++i) key |= (unsigned long long)(unsigned char)data[o0 + i] << (8 * i);
-      uint32_t li = (uint32_t)(fmix64(key + (unsigned long long)len) >> 40) & (DICT_LCAP - 1);
-      bool done = false;
-      for (int probe = 0; probe < 8 && !done; ++probe, li = (li + 1) & (DICT_LCAP - 1)) {
-        unsigned int v = *(volatile unsigned int*)&l_val[li];
-        if (v == DICT_L_EMPTY) {
-          v = atomicCAS(&l_val[li], DICT_L_EMPTY, DICT_L_BUSY);
-          if (v == DICT_L_EMPTY) {  // claimed: resolve through the global table once, then publish
-            s = dict_global_slot(offs, data, row, o0, len, slots, n_dict, abort_flag);
-            l_key[li] = key;
-            __threadfence_block();
-            *(volatile unsigned int*)&l_val[li] = ((unsigned int)len << 16) | s;
+    int32_t o0[U], len[U];
+    unsigned long long key[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + (int64_t)u * stride;
+      o0[u] = 0;
+      len[u] = -1;
+      if (row < n) {
+        o0[u] = offs[row];
+        len[u] = offs[row + 1] - o0[u];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      key[u] = 0;
+      if (len[u] >= 0 && len[u] <= 8)
+        for (int i = 0; i < len[u]; ++i) key[u] |= (unsigned long long)(unsigned char)data[o0[u] + i] << (8 * i);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (len[u] < 0) continue;
+      const int64_t row = row0 + (int64_t)u * stride;
+      uint32_t s;
+      if (len[u] <= 8) {
+        uint32_t li = (uint32_t)(fmix64(key[u] + (unsigned long long)len[u]) >> 40) & (DICT_LCAP - 1);
+        bool done = false;
+        for (int probe = 0; probe < 8 && !done; ++probe, li = (li + 1) & (DICT_LCAP - 1)) {
+          unsigned int v = *(volatile unsigned int*)&l_val[li];
+          if (v == DICT_L_EMPTY) {
+            v = atomicCAS(&l_val[li], DICT_L_EMPTY, DICT_L_BUSY);
+            if (v == DICT_L_EMPTY) {  // claimed: resolve through the global table once, then publish
+              s = dict_global_slot(offs, data, row, o0[u], len[u], slots, n_dict, abort_flag);
+              l_key[li] = key[u];
+              __threadfence_block();
+              *(volatile unsigned int*)&l_val[li] = ((unsigned int)len[u] << 16) | s;
+              done = true;
+              break;
+            }
+          }
+          if (v == DICT_L_BUSY) break;  // being published by another thread: take the global path, no spinning
+          if ((v >> 16) == (unsigned int)len[u] && *(volatile unsigned long long*)&l_key[li] == key[u]) {
+            s = v & 0xffffu;
             done = true;
-            break;
           }
         }
-        if (v == DICT_L_BUSY) break;  // being published by another thread: take the global path, no spinning
-        if ((v >> 16) == (unsigned int)len && *(volatile unsigned long long*)&l_key[li] == key) {
-          s = v & 0xffffu;
-          done = true;
-        }
+        if (!done) s = dict_global_slot(offs, data, row, o0[u], len[u], slots, n_dict, abort_flag);
+      } else {
+        s = dict_global_slot(offs, data, row, o0[u], len[u], slots, n_dict, abort_flag);
       }
-      if (!done) s = dict_global_slot(offs, data, row, o0, len, slots, n_dict, abort_flag);
-    } else {
-      s = dict_global_slot(offs, data, row, o0, len, slots, n_dict, abort_flag);
+      row_slot[row] = (uint16_t)s;
     }
-    row_slot[row] = (uint16_t)s;
   }
 }
 __global__ void k_dict_codes(const uint16_t* __restrict__ row_slot, const uint8_t* __restrict__ slot_code, int64_t n,
