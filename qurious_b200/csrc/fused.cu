@@ -241,7 +241,10 @@ __device__ __forceinline__ uint32_t dict_global_slot(const int32_t* __restrict__
   const uint32_t tag = (uint32_t)(h >> 32);
   uint32_t s = (uint32_t)h & (DICT_CAP - 1);
   const unsigned long long mine = ((unsigned long long)tag << 32) | (unsigned long long)(row + 1);
-  while (true) {
+  // the walk is bounded: once more than 255 values exist the column is not dictionary material (abort), and rows already
+  // in flight must not keep filling -- or circling -- the 1024-slot table
+  for (int probes = 0; probes < DICT_CAP; ++probes) {
+    if (*(volatile int*)abort_flag) return 0;
     unsigned long long cur = *(volatile unsigned long long*)&slots[s];
     if (cur == 0) {
       cur = atomicCAS(&slots[s], 0ull, mine);
@@ -259,6 +262,8 @@ __device__ __forceinline__ uint32_t dict_global_slot(const int32_t* __restrict__
     }
     s = (s + 1) & (DICT_CAP - 1);
   }
+  *abort_flag = 1;  // table full
+  return 0;
 }
 // Values of <= 8 bytes (flags, status codes, most segment / mode names' prefixes do not count: the WHOLE value must fit) are
 // their own key: a per-CTA shared-memory table maps (length, packed bytes) -> global slot, so that after a CTA's first
