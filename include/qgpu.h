@@ -164,7 +164,8 @@ int64_t qgpu_counter(const qgpu_ctx* ctx, const char* name);
 int64_t qgpu_jit_compile(const uint64_t* signature4, uint32_t pack, char* log_buf, int64_t cap);
 /* Tuning knobs: "ingest_threads" (host worker threads of the staged ingest, 0 = min(hardware threads, 16); at most 16),
  * "ingest_host_narrow" (1: Decimal128(p <= 18) narrowed to int64 by the host workers while staging -- 8 instead of 16
- * bytes per value cross PCIe; 0: uploaded as 16-byte values and narrowed by one kernel; -1: default = 1). */
+ * bytes per value cross PCIe; 0: uploaded as 16-byte values and narrowed by one kernel; -1: automatic = on, except for
+ * large page-locked sources when this rank has fewer than 8 worker threads: those are DMA'd directly). */
 int qgpu_set_option(qgpu_ctx* ctx, const char* name, int64_t value);
 /* number of kernel launches issued by this context since creation (bench.py: gpu_launches) */
 int64_t qgpu_kernel_launches(const qgpu_ctx* ctx);

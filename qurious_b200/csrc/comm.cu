@@ -181,6 +181,8 @@ void comm_init_local(Ctx** ctxs, int n) {
   }
 }
 
+int comm_world_size(Ctx* ctx) { return ctx->comm ? ctx->comm->world : 0; }
+
 void comm_destroy(Ctx* ctx) {
   if (!ctx->comm) return;
   cudaStreamSynchronize(ctx->stream);

@@ -512,7 +512,7 @@ DBufP read_file_to_device(Ctx* ctx, const char* path, int64_t* len_out) {
   const size_t slot_bytes = ctx->ingest_slot_bytes;
   const size_t ring_bytes = ctx->stage_bytes * Ctx::kStageSlots;
   const int64_t n_tasks = (len + (int64_t)slot_bytes - 1) / (int64_t)slot_bytes;
-  int threads = ctx->ingest_threads > 0 ? ctx->ingest_threads : (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+  int threads = ingest_worker_threads(ctx);
   threads = (int)std::min<size_t>((size_t)threads, ring_bytes / (2 * slot_bytes));
   threads = (int)std::max<int64_t>(1, std::min<int64_t>(threads, n_tasks));
   while ((int)ctx->ingest_ev.size() < threads * 2) {

@@ -277,6 +277,20 @@ Phys phys_of(const DType& t) {
 
 }  // namespace
 
+// Host worker threads of one upload: qgpu_set_option / QGPU_INGEST_THREADS, else min(16, host threads / ranks on this
+// node) -- eight processes uploading at once must share the cores (16 workers each on a 2 x 64-thread host took 446 ms
+// per rank where 204 ms were measured without any host work); the node-local rank count is LOCAL_WORLD_SIZE (torchrun,
+// mpirun) or the communicator's world size
+int ingest_worker_threads(Ctx* ctx) {
+  int threads = ctx->ingest_threads > 0 ? ctx->ingest_threads : env_int("QGPU_INGEST_THREADS", 0);
+  if (threads > 0) return std::min(threads, 16);
+  int ranks = env_int("LOCAL_WORLD_SIZE", 0);
+  if (ranks <= 0 && ctx->comm) ranks = comm_world_size(ctx);
+  if (ranks <= 0) ranks = 1;
+  const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+  return std::max(2, std::min(16, hw / ranks));
+}
+
 // Cheap structural checks at append time: a failing batch must be reported by qgpu_table_append itself and leave the
 // table untouched (the expensive part, the upload, is deferred).
 void validate_host_batch(const Schema& schema, const ArrowArray* batch, const std::vector<char>& want) {
@@ -308,8 +322,7 @@ static void run_tasks(Ctx* ctx, std::vector<Task>& tasks, size_t total_bytes) {
   if (tasks.empty()) return;
   // the ring: the context's 2 x 32 MiB pinned staging area cut into 2 slots per worker
   const size_t ring_bytes = ctx->stage_bytes * Ctx::kStageSlots;
-  int threads = ctx->ingest_threads > 0 ? ctx->ingest_threads : env_int("QGPU_INGEST_THREADS", 0);
-  if (threads <= 0) threads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+  int threads = ingest_worker_threads(ctx);
   if (total_bytes < ((size_t)4 << 20)) threads = 1;  // small tables: the calling thread alone
   threads = (int)std::min<size_t>((size_t)threads, tasks.size());
   const size_t slot_bytes = ctx->ingest_slot_bytes;  // tasks were cut for this size; 16 workers x 2 slots x 2 MiB = the ring
@@ -390,7 +403,12 @@ TableChunk import_host_batches(Ctx* ctx, const Schema& schema, const std::vector
   for (auto& b : batches) rows += b.length;
   ch.rows = rows;
   if (host_narrow < 0) host_narrow = ctx->ingest_host_narrow;
-  if (host_narrow < 0) host_narrow = env_int("QGPU_INGEST_HOST_NARROW", 1);
+  if (host_narrow < 0) host_narrow = env_int("QGPU_INGEST_HOST_NARROW", -1);
+  // -1 = automatic, decided per column below: a source the workers must touch anyway (pageable, or many small batches) is
+  // narrowed on the way; a large page-locked source is narrowed by the host only when this rank has enough worker threads
+  // to keep PCIe busy (>= 8) -- otherwise it is DMA'd as 16-byte values and narrowed by one kernel.  Measured, Q1 SF10
+  // lineitem per GPU: 16 workers 62 ms vs 89 ms direct; 4 workers per rank (8 ranks on a 32-thread host) 357 ms vs 218 ms.
+  const bool many_workers = ingest_worker_threads(ctx) >= 8;
   const size_t slot_bytes = ctx->ingest_slot_bytes;
   const int64_t n_words = (rows + 31) >> 5;
   const size_t kDirectMin = (size_t)256 << 10;  // page-locked source buffers at least this large are DMA'd directly
@@ -413,7 +431,7 @@ TableChunk import_host_batches(Ctx* ctx, const Schema& schema, const std::vector
     cp->col = col;
     cp->rows = rows;
     cp->w = arrow_width(ty);
-    cp->narrow = host_narrow && col->phys == PH_I128 && ty.precision <= 18 && rows > 0;
+    cp->narrow = host_narrow != 0 && col->phys == PH_I128 && ty.precision <= 18 && rows > 0;
     plans.push_back(std::move(cp));
   }
   // one Part per (column, non-empty batch): with tens of thousands of batches this walk over separately allocated
@@ -480,6 +498,14 @@ TableChunk import_host_batches(Ctx* ctx, const Schema& schema, const std::vector
     for (auto& cpp : plans) plan_column(*cpp);
   }
 
+  if (host_narrow < 0 && !many_workers)
+    for (auto& cpp : plans) {
+      ColPlan& cp = *cpp;
+      if (!cp.narrow || cp.parts.empty()) continue;
+      bool all_big = true;
+      for (auto& p : cp.parts) all_big = all_big && (size_t)p.n * cp.w >= kDirectMin;
+      if (all_big && cp.parts[0].values && is_pinned(cp.parts[0].values)) cp.narrow = false;  // direct DMA + k_narrow
+    }
   // destination buffers (stream-ordered allocations on the compute stream; the copy stream waits for them below)
   for (auto& cpp : plans) {
     ColPlan& cp = *cpp;

@@ -416,6 +416,8 @@ TableChunk parse_csv_device(Ctx* ctx, const Schema& schema, const std::vector<ch
                             const qgpu_csv_options& opt);
 DBufP read_file_to_device(Ctx* ctx, const char* path, int64_t* len_out);
 // ---- ingest.cu ---------------------------------------------------------------------------------
+int ingest_worker_threads(Ctx* ctx);
+int comm_world_size(Ctx* ctx);  // comm.cu: 0 without a communicator
 void validate_host_batch(const Schema& schema, const ArrowArray* batch, const std::vector<char>& want);
 TableChunk import_host_batches(Ctx* ctx, const Schema& schema, const std::vector<ArrowArray>& batches, const std::vector<char>& want,
                                int host_narrow = -1);
