@@ -106,10 +106,13 @@ typedef struct qgpu_type {
  *  QGPU_IR_IS_NULL / QGPU_IR_IS_NOT_NULL / QGPU_IR_NEGATIVE   is_null.rs / is_not_null.rs / negative.rs
  *  QGPU_IR_LIKE        u8 negated; stack: expr pattern     physical/expr/like.rs:28-41 (arrow like / nlike: % _ and \ escape)
  *  QGPU_IR_EXTRACT     u8 part (0 YEAR, 1 MONTH, 2 DAY)    physical/expr/function.rs + functions/datetime/extract.rs (Date32/Date64 -> Int64)
+ *  QGPU_IR_SUBQUERY    u64 qgpu_plan* (a plan of the same context)   physical/expr/subquery.rs:15-20: the sub-plan runs once per
+ *                      evaluation and its FIRST column stands in as an array operand; like the reference's arrow kernels the
+ *                      evaluation fails (ArrowError) unless it has exactly as many rows as the input
  */
 typedef enum qgpu_ir_op {
   QGPU_IR_COLUMN = 1, QGPU_IR_LITERAL = 2, QGPU_IR_BINARY = 3, QGPU_IR_CAST = 4, QGPU_IR_CASE = 5,
-  QGPU_IR_IS_NULL = 6, QGPU_IR_IS_NOT_NULL = 7, QGPU_IR_NEGATIVE = 8, QGPU_IR_LIKE = 9, QGPU_IR_EXTRACT = 10
+  QGPU_IR_IS_NULL = 6, QGPU_IR_IS_NOT_NULL = 7, QGPU_IR_NEGATIVE = 8, QGPU_IR_LIKE = 9, QGPU_IR_EXTRACT = 10, QGPU_IR_SUBQUERY = 11
 } qgpu_ir_op;
 
 /* aggregate operator: AggregateOperator of logical/expr/aggregate.rs:56-62 */
@@ -165,7 +168,9 @@ int64_t qgpu_jit_compile(const uint64_t* signature4, uint32_t pack, char* log_bu
 /* Tuning knobs: "ingest_threads" (host worker threads of the staged ingest, 0 = min(hardware threads, 16); at most 16),
  * "ingest_host_narrow" (1: Decimal128(p <= 18) narrowed to int64 by the host workers while staging -- 8 instead of 16
  * bytes per value cross PCIe; 0: uploaded as 16-byte values and narrowed by one kernel; -1: automatic = on, except for
- * large page-locked sources when this rank has fewer than 8 worker threads: those are DMA'd directly). */
+ * large page-locked sources when this rank has fewer than 8 worker threads: those are DMA'd directly);
+ * "pool_reserve_mb": the context's device memory pool keeps at least this much reserved (default 4096; grown now, kept by
+ * qgpu_release_cached_memory), so that no execution waits for the driver to map memory in the middle of a step. */
 int qgpu_set_option(qgpu_ctx* ctx, const char* name, int64_t value);
 /* number of kernel launches issued by this context since creation (bench.py: gpu_launches) */
 int64_t qgpu_kernel_launches(const qgpu_ctx* ctx);

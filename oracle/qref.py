@@ -5,7 +5,7 @@ TEST INFRASTRUCTURE ONLY.  Nothing in `qurious_b200/` imports this module.  Only
 only as the checker / the reported CPU baseline -- never as the thing shipped.
 
 What it restates (reference file:line, all relative to /root/reference/qurious/src):
-  * expression evaluation      physical/expr/{column,literal,binary,cast,case,is_null,is_not_null,negative}.rs
+  * expression evaluation      physical/expr/{column,literal,binary,cast,case,is_null,is_not_null,negative,like,function,subquery}.rs
   * Filter / MemoryTable::scan  physical/plan/filter.rs:28-44, datasource/memory.rs:69-98
   * Projection                  physical/plan/projection.rs:27-46
   * NoGroupingAggregate         physical/plan/aggregate/no_grouping.rs:30-62
@@ -699,6 +699,14 @@ def evaluate(expr, batch: pa.RecordBatch, _cols: Optional[List[Col]] = None) -> 
                 d = _dt.date(1970, 1, 1) + _dt.timedelta(days=days)
                 out[i] = {"year": d.year, "month": d.month, "day": d.day}[part]
         return Col(pa.int64(), out, c.valid.copy())
+    if k == "SubQuery":  # subquery.rs:15-20: batches[0].column(0), whatever the input batch is
+        batches = execute(expr.plan)
+        if not batches:
+            raise internal_err("SubQuery returned no batch")       # index out of bounds panic in the reference
+        c = from_arrow(batches[0].column(0))
+        if len(c) != n:   # arrow's binary kernels reject operands of different lengths
+            raise arrow_err(f"Invalid argument error: Cannot perform a binary operation on arrays of different length ({len(c)} vs {n})")
+        return c
     if k == "IsNull":
         c = evaluate(expr.expr, batch, cols)
         return Col(pa.bool_(), ~c.valid)

@@ -273,13 +273,23 @@ class Context:
         return c
 
     def parse_expr(self, expr) -> ctypes.c_void_p:
-        ir = expr.to_ir()
+        global _parse_ctx
+        prev, _parse_ctx = _parse_ctx, self           # SubQuery.to_ir builds its sub-plan in this context
+        try:
+            ir = expr.to_ir()
+        finally:
+            _parse_ctx = prev
         h = ctypes.c_void_p()
         self.check(self.lib.qgpu_expr_parse(self.handle, ir, len(ir), ctypes.byref(h)))
         return h
 
 
 _default_ctx: Optional[Context] = None
+_parse_ctx: Optional[Context] = None
+
+
+def current_parse_context() -> Optional[Context]:
+    return _parse_ctx
 
 
 def comm_init_local(ctxs: Sequence["Context"]):

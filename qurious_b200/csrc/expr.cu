@@ -9,6 +9,7 @@
 #include <cstring>
 
 #include "expr.h"
+#include "plan.h"
 
 namespace qgpu {
 
@@ -158,6 +159,12 @@ std::unique_ptr<ExprNode> parse_ir(const uint8_t* ir, size_t len) {
         n->children.push_back(pop());
         break;
       }
+      case QGPU_IR_SUBQUERY: {
+        const qgpu_plan* sp = (const qgpu_plan*)(uintptr_t)r.rd<uint64_t>();
+        if (!sp || !sp->node) throw_internal("SubQuery: null plan");
+        n->subplan = sp->node;
+        break;
+      }
       default: throw_internal("malformed expression IR (unknown opcode " + std::to_string(n->kind) + ")");
     }
     st.push_back(std::move(n));
@@ -300,6 +307,13 @@ struct Compiler {
         o.arg = slot_of(n.col_index);
         const Field& f = schema.fields[n.col_index];
         return {f.type, false, f.name + "(" + std::to_string(n.col_index) + ")"};
+      }
+      case QGPU_IR_SUBQUERY: {  // subquery.rs:15-20: batches[0].column(0)
+        if (!n.subplan || n.subplan->schema.fields.empty()) throw_internal("SubQuery plan has no columns");
+        out.subqueries.push_back(n.subplan);
+        Op& o = add_op(OP_COL);
+        o.arg = slot_of(-(1000 + (int)out.subqueries.size() - 1));
+        return {n.subplan->schema.fields[0].type, false, "SubQuery"};
       }
       case QGPU_IR_LITERAL: {
         Val v;
@@ -515,10 +529,24 @@ Program bind_program(Ctx* ctx, Compiled& c, const View& v) {
   }
   for (int i = 0; i < P.n_consts; ++i)
     if (c.const_is_str[i]) P.consts[i].lo = (uint64_t)((const char*)c.dev_blob->ptr + c.prog.consts[i].lo);
+  c.bound_subquery_cols.clear();
   for (size_t s = 0; s < c.col_slots.size(); ++s) {
     int ci = c.col_slots[s];
-    if (ci < 0 || ci >= (int)v.cols.size()) throw_internal("expression column index out of range");
-    const LazyCol& lc = v.cols[ci];
+    LazyCol sub;
+    if (ci <= -1000) {  // SubQuery operand: execute the sub-plan now
+      PlanNode& sp = *c.subqueries[(size_t)(-ci - 1000)];
+      View sv = sp.execute();
+      sv.resolve();
+      if (sv.num_batches == 0 || sv.cols.empty()) throw_internal("SubQuery returned no batch");  // batches[0] panics in the reference
+      if (sv.num_rows != v.num_rows)
+        throw_arrow("Invalid argument error: Cannot perform a binary operation on arrays of different length (SubQuery returned " +
+                    std::to_string(sv.num_rows) + " rows for " + std::to_string(v.num_rows) + " input rows)");
+      sub = sv.cols[0];
+      c.bound_subquery_cols.push_back(sub);
+    } else if (ci < 0 || ci >= (int)v.cols.size()) {
+      throw_internal("expression column index out of range");
+    }
+    const LazyCol& lc = ci <= -1000 ? sub : v.cols[ci];
     ColRef& r = P.cols[s];
     memset(&r, 0, sizeof(ColRef));
     if (!lc.base) {
@@ -526,7 +554,7 @@ Program bind_program(Ctx* ctx, Compiled& c, const View& v) {
         r.phys = PH_NULL;
         continue;
       }
-      throw_internal("column '" + v.schema.fields[ci].name + "' is referenced but was not uploaded to the GPU table");
+      throw_internal("column '" + (ci >= 0 ? v.schema.fields[ci].name : std::string("SubQuery")) + "' is referenced but was not uploaded to the GPU table");
     }
     const DCol& d = *lc.base;
     r.phys = d.phys;

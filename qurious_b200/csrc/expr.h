@@ -9,7 +9,10 @@
 
 namespace qgpu {
 
+struct PlanNode;
+
 struct ExprNode {
+  std::shared_ptr<PlanNode> subplan;  // QGPU_IR_SUBQUERY
   int kind = 0;  // qgpu_ir_op
   int col_index = -1;
   DType lit_type;
@@ -37,6 +40,10 @@ struct Compiled {
   std::vector<uint8_t> const_is_str;
   DBufP dev_blob;               // blob uploaded to the device (lazily)
   int deferred_err = 0;         // EvalErr raised while folding constants; raised if rows > 0
+  // SubQuery operands (subquery.rs): column slot -(1000 + k) is the first column of subqueries[k]'s result, executed by
+  // bind_program; bound_subquery_cols keeps the columns alive while the kernels read them
+  std::vector<std::shared_ptr<PlanNode>> subqueries;
+  std::vector<LazyCol> bound_subquery_cols;
   std::string display;
 };
 

@@ -60,6 +60,17 @@ void Ctx::release_big_blocks() {
 
 DBufP Ctx::alloc(size_t bytes) { return std::make_shared<DBuf>(this, bytes); }
 
+void Ctx::reserve_pool() {
+  if (!pool || pool_floor_bytes == 0) return;
+  void* p = nullptr;
+  if (cudaMallocAsync(&p, pool_floor_bytes, pool, stream) != cudaSuccess) {  // a small GPU: no reservation, not an error
+    cudaGetLastError();
+    return;
+  }
+  cudaFreeAsync(p, stream);
+  cudaStreamSynchronize(stream);
+}
+
 Slab::Slab(Ctx* ctx, size_t total_bytes, bool zero) {
   buf = zero ? ctx->alloc_zero(total_bytes) : ctx->alloc(total_bytes);
 }

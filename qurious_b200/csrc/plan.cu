@@ -436,6 +436,8 @@ int qgpu_init(const int* devices, int n, qgpu_ctx** out) {
       CUDA_CHECK(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
     }
     CUDA_CHECK(cudaHostAlloc(&c->pinned_scratch, c->pinned_scratch_bytes, cudaHostAllocDefault));
+    if (const char* e = getenv("QGPU_POOL_RESERVE_MB")) c->pool_floor_bytes = (size_t)std::max(0, atoi(e)) << 20;
+    c->reserve_pool();
   } catch (QError& err) {
     g_last_error = err.what();
     delete h;
@@ -522,7 +524,8 @@ int qgpu_release_cached_memory(qgpu_ctx* ctx) {
   return guard(&ctx->c, [&] {
     ctx->c.release_big_blocks();
     ctx->c.sync();
-    CUDA_CHECK(cudaMemPoolTrimTo(ctx->c.pool, 0));  // back to the driver: other allocators of the process can use it
+    // back to the driver (other allocators of the process can use it) -- down to the floor the context keeps reserved
+    CUDA_CHECK(cudaMemPoolTrimTo(ctx->c.pool, ctx->c.pool_floor_bytes));
   });
 }
 
@@ -706,6 +709,12 @@ int qgpu_set_option(qgpu_ctx* ctx, const char* name, int64_t value) {
     if (s == "ingest_threads") {
       if (value < 0 || value > 16) throw_internal("ingest_threads must be 0 (automatic) .. 16");
       ctx->c.ingest_threads = (int)value;
+    } else if (s == "pool_reserve_mb") {
+      // grow the stream-ordered pool now (it keeps what it once reserved): later executions then never wait for the driver
+      // to map more physical memory in the middle of a step
+      if (value < 0 || value > (1 << 20)) throw_internal("pool_reserve_mb out of range");
+      ctx->c.pool_floor_bytes = (size_t)value << 20;
+      ctx->c.reserve_pool();
     } else if (s == "ingest_host_narrow") {
       ctx->c.ingest_host_narrow = value < 0 ? -1 : (value != 0);
     } else {

@@ -235,6 +235,12 @@ struct Ctx {
   cudaStream_t epi_stream = nullptr;
   cudaEvent_t epi_ready = nullptr;
   cudaMemPool_t pool = nullptr;
+  // The stream-ordered pool keeps at least this much reserved (grown at init, kept by qgpu_release_cached_memory): a plan
+  // that allocates and frees hundreds of MB per execution otherwise keeps sending the pool back to the driver for physical
+  // memory in the middle of a step (distributed Q3 at N = 2: median step 1.83 -> 1.40 ms, 5-38 ms outliers gone).
+  // qgpu_set_option "pool_reserve_mb" / QGPU_POOL_RESERVE_MB.
+  size_t pool_floor_bytes = (size_t)4 << 30;
+  void reserve_pool();
   std::recursive_mutex mu;
   std::string last_error;
   int64_t launches = 0;

@@ -27,8 +27,8 @@ import pyarrow as pa
 from ..datatypes import AggregateOperator, Operator, ScalarValue, encode_type
 
 # IR opcodes (include/qgpu.h: enum qgpu_ir_op)
-IR_COLUMN, IR_LITERAL, IR_BINARY, IR_CAST, IR_CASE, IR_IS_NULL, IR_IS_NOT_NULL, IR_NEGATIVE, IR_LIKE, IR_EXTRACT = (
-    1, 2, 3, 4, 5, 6, 7, 8, 9, 10,
+IR_COLUMN, IR_LITERAL, IR_BINARY, IR_CAST, IR_CASE, IR_IS_NULL, IR_IS_NOT_NULL, IR_NEGATIVE, IR_LIKE, IR_EXTRACT, IR_SUBQUERY = (
+    1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11,
 )
 
 
@@ -186,6 +186,27 @@ class Function(PhysicalExpr):
 
     def __str__(self) -> str:  # function.rs:35-39
         return self.func.name()
+
+
+class SubQuery(PhysicalExpr):
+    """`SubQuery { plan }` (physical/expr/subquery.rs:11-20): `evaluate` executes the sub-plan and returns the FIRST column of
+    its first batch, whatever the input batch is -- usable where that array has as many rows as the input (a scalar subquery
+    over a one-row relation; arrow's kernels reject operands of different lengths).  The planner leaves these in SELECT
+    lists; scalar subqueries in predicates are rewritten into joins (scalar_subquery_to_join.rs)."""
+
+    def __init__(self, plan):
+        self.plan = plan
+
+    def to_ir(self) -> bytes:
+        from .. import _lib
+        ctx = _lib.current_parse_context()
+        if ctx is None:
+            raise QuriousErrorLazy("InternalError: SubQuery expressions are serialised by Context.parse_expr")
+        _, h, _ = self.plan._native_cached(ctx)       # the sub-plan's native handles live as long as the plan object
+        return struct.pack("<BQ", IR_SUBQUERY, h.value)
+
+    def __str__(self) -> str:  # subquery.rs:29-33
+        return "SubQuery"
 
 
 def QuriousErrorLazy(msg: str):
