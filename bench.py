@@ -596,8 +596,10 @@ def setup_leg(q, args, ctx, rank, world, torch):
             # FinalAggregate <- Aggregate <- Join(Broadcast(J1 over the orders shard), lineitem shard): the J1 rows of all
             # ranks reach every GPU in one grouped NCCL exchange, groups straddling a shard boundary are merged by a hash
             # exchange of the partial groups; the result stays sharded
+            # Broadcast with key-range pruning: a J1 row only travels to the ranks whose lineitem shard can hold its order key
             bj = qd.BroadcastJoinAggregate(ctx, tpch.q3_build_plan(tpch.Database(0.0, dev_tables["customer"], dev_tables["orders"], None)),
-                                           lambda b: tpch.q3_probe_plan(b, dev_tables["lineitem"]), world)
+                                           lambda b: tpch.q3_probe_plan(b, dev_tables["lineitem"]), world,
+                                           prune=(0, dev_tables["lineitem"], dev_tables["lineitem"].schema.get_field_index("l_orderkey")))
 
             host_t = {"exec": 0.0, "free": 0.0, "n": 0}
 
@@ -767,7 +769,8 @@ def run_b200(args):
                 p = build_plan(q, tabs)
                 if world > 1 and q == "q3":
                     out = qd.BroadcastJoinAggregate(ctx, tpch.q3_build_plan(tpch.Database(0.0, tabs["customer"], tabs["orders"], None)),
-                                                    lambda b: tpch.q3_probe_plan(b, tabs["lineitem"]), world).execute()
+                                                    lambda b: tpch.q3_probe_plan(b, tabs["lineitem"]), world,
+                                                    prune=(0, tabs["lineitem"], tabs["lineitem"].schema.get_field_index("l_orderkey"))).execute()
                 elif world > 1:
                     out = qd.ShardedAggregate(ctx, p, lo, world).execute()
                 else:

@@ -283,6 +283,12 @@ int qgpu_plan_cross_join(qgpu_ctx* ctx, qgpu_plan* left, qgpu_plan* right, qgpu_
  * every child column must be a key or a value; NULL-free fixed-width columns.  The result stays sharded: each final group
  * is returned by exactly one rank.  Without a communicator (or world 1) both nodes are the identity. */
 int qgpu_plan_broadcast(qgpu_ctx* ctx, qgpu_plan* child, int32_t order_free, qgpu_plan** out);
+/* Broadcast for the build side of an INNER equi-join whose probe side is `probe_table` on this rank, joined on
+ * child column `key_column` = probe column `probe_key_column`: a build row travels only to the ranks whose probe-side key
+ * range (column statistics) contains its key -- dynamic partition pruning; with range-sharded inputs every rank receives
+ * ~1/world of the rows.  Implies order_free.  Falls back to the full broadcast when a range is unknown or a column has NULLs. */
+int qgpu_plan_broadcast_pruned(qgpu_ctx* ctx, qgpu_plan* child, int32_t key_column, qgpu_table* probe_table,
+                               int32_t probe_key_column, qgpu_plan** out);
 int qgpu_plan_final_aggregate(qgpu_ctx* ctx, qgpu_plan* child, const int32_t* key_columns, int32_t n_keys,
                               const int32_t* value_columns, const int32_t* merge_ops, int32_t n_values, qgpu_plan** out);
 /* PhysicalPlan::schema (physical/plan/mod.rs:26) */

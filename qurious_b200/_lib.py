@@ -25,7 +25,7 @@ SYMBOLS = [
     "qgpu_table_create", "qgpu_table_append", "qgpu_table_append_device", "qgpu_table_num_rows",
     "qgpu_table_num_batches", "qgpu_table_column_bytes", "qgpu_table_schema", "qgpu_table_export",
     "qgpu_table_free", "qgpu_expr_parse", "qgpu_expr_free", "qgpu_plan_scan", "qgpu_plan_filter",
-    "qgpu_plan_projection", "qgpu_plan_sort", "qgpu_plan_limit", "qgpu_plan_aggregate", "qgpu_plan_hash_join", "qgpu_plan_nested_loop_join", "qgpu_plan_cross_join", "qgpu_plan_broadcast", "qgpu_plan_final_aggregate", "qgpu_plan_schema",
+    "qgpu_plan_projection", "qgpu_plan_sort", "qgpu_plan_limit", "qgpu_plan_aggregate", "qgpu_plan_hash_join", "qgpu_plan_nested_loop_join", "qgpu_plan_cross_join", "qgpu_plan_broadcast", "qgpu_plan_broadcast_pruned", "qgpu_plan_final_aggregate", "qgpu_plan_schema",
     "qgpu_plan_execute", "qgpu_plan_execute_device", "qgpu_plan_last_stats", "qgpu_plan_strategy",
     "qgpu_plan_free", "qgpu_plan_state_bytes", "qgpu_plan_partial_state", "qgpu_plan_execute_merged", "qgpu_plan_execute_merged_device", "qgpu_plan_set_order_free",
     "qgpu_release_cached_memory", "qgpu_table_hash_partition", "qgpu_table_column_device_buffer",
@@ -127,6 +127,7 @@ def load_library() -> ctypes.CDLL:
     lib.qgpu_plan_nested_loop_join.argtypes = [vp, vp, vp, i32, P(qgpu_join_filter), P(vp)]
     lib.qgpu_plan_cross_join.argtypes = [vp, vp, vp, P(vp)]
     lib.qgpu_plan_broadcast.argtypes = [vp, vp, i32, P(vp)]
+    lib.qgpu_plan_broadcast_pruned.argtypes = [vp, vp, i32, vp, i32, P(vp)]
     lib.qgpu_plan_final_aggregate.argtypes = [vp, vp, P(i32), i32, P(i32), P(i32), i32, P(vp)]
     lib.qgpu_plan_schema.argtypes = [vp, vp]
     lib.qgpu_plan_execute.argtypes = [vp, vp]

@@ -66,6 +66,151 @@ void store_words(Ctx* ctx, long long* dst, const long long* vals, size_t n) {
 
 uint64_t local_subtree_signature(PlanNode& n);  // fused.cu
 
+struct PruneParams {
+  int n_dest, n_cols, key_width, pad;
+  long long lo[COMM_MAX_WORLD], hi[COMM_MAX_WORLD];
+  const unsigned char* src[16];
+  unsigned char* dst[16];
+  int width[16];
+};
+// pass 1: per row the set of destination ranks (key inside their probe range) + per-destination row counts
+__global__ void k_prune_count(const void* __restrict__ keys, int64_t n, PruneParams P, unsigned char* __restrict__ mask,
+                              unsigned long long* __restrict__ counts) {
+  __shared__ unsigned int sc[COMM_MAX_WORLD];
+  if (threadIdx.x < COMM_MAX_WORLD) sc[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long k = P.key_width == 8 ? ((const long long*)keys)[i] : (long long)((const int*)keys)[i];
+    unsigned m = 0;
+    for (int r = 0; r < P.n_dest; ++r)
+      if (k >= P.lo[r] && k <= P.hi[r]) {
+        m |= 1u << r;
+        atomicAdd(&sc[r], 1u);
+      }
+    mask[i] = (unsigned char)m;
+  }
+  __syncthreads();
+  if (threadIdx.x < P.n_dest && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)sc[threadIdx.x]);
+}
+// pass 2: every selected row of every column into its destination's slice of the send buffers (order inside a slice is
+// arbitrary: the consumer is order-free)
+__global__ void k_prune_scatter(int64_t n, PruneParams P, const unsigned char* __restrict__ mask, unsigned long long* __restrict__ cursor) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t n_words = (n + 31) >> 5;
+  for (int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_words; w += warps) {
+    const int64_t i = (w << 5) + lane;
+    const unsigned m = i < n ? mask[i] : 0u;
+    for (int r = 0; r < P.n_dest; ++r) {  // warp-aggregated reservation: one atomic per (warp, destination)
+      const unsigned b = __ballot_sync(0xffffffffu, (m >> r) & 1u);
+      if (!b) continue;
+      unsigned long long base = 0;
+      if (lane == __ffs(b) - 1) base = atomicAdd(&cursor[r], (unsigned long long)__popc(b));
+      base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
+      if ((m >> r) & 1u) {
+        const unsigned long long pos = base + __popc(b & ((1u << lane) - 1u));
+        for (int c = 0; c < P.n_cols; ++c) {
+          const int wd = P.width[c];
+          if (wd == 8) ((unsigned long long*)P.dst[c])[pos] = ((const unsigned long long*)P.src[c])[i];
+          else if (wd == 4) ((unsigned int*)P.dst[c])[pos] = ((const unsigned int*)P.src[c])[i];
+          else if (wd == 16) ((ulonglong2*)P.dst[c])[pos] = ((const ulonglong2*)P.src[c])[i];
+          else if (wd == 2) ((unsigned short*)P.dst[c])[pos] = ((const unsigned short*)P.src[c])[i];
+          else P.dst[c][pos] = P.src[c][i];
+        }
+      }
+    }
+  }
+}
+
+// Key-range pruned broadcast (dynamic partition pruning by zone maps): a build row travels only to the ranks whose
+// probe-side key range contains its key -- with range-sharded inputs (orders and lineitem are both sorted by order key) every
+// rank receives ~1 / world of the rows instead of all of them, and builds a correspondingly smaller join table.
+static View broadcast_pruned(PlanNode& node, const View& in, const std::vector<DColP>& mine, const std::vector<long long>& am,
+                             size_t meta_words, size_t HDR, int world, int rank) {
+  Ctx* ctx = node.ctx;
+  const int nc = (int)mine.size();
+  const int64_t n = in.num_rows;
+  PruneParams P;
+  memset(&P, 0, sizeof(P));
+  P.n_dest = world;
+  P.n_cols = nc;
+  P.key_width = phys_width(mine[node.prune_key_col]->phys);
+  for (int r = 0; r < world; ++r) {
+    P.lo[r] = am[(size_t)r * meta_words + 3];
+    P.hi[r] = am[(size_t)r * meta_words + 4];
+  }
+  DBufP mask = ctx->alloc(std::max<size_t>((size_t)n, 16));
+  DBufP counts = ctx->alloc_zero(8 * (size_t)world), matrix = ctx->alloc(8 * (size_t)world * world);
+  if (n > 0) LAUNCH(ctx, k_prune_count, grid_for(ctx, n, 256), 256, 0, mine[node.prune_key_col]->data->ptr, n, P, (unsigned char*)mask->ptr, (unsigned long long*)counts->ptr);
+  comm_all_gather_any(ctx, counts->ptr, matrix->ptr, 8 * (size_t)world);
+  std::vector<long long> mx((size_t)world * world);
+  ctx->d2h_sync(mx.data(), matrix->ptr, mx.size() * 8);  // second (and last) host round trip: who sends how much to whom
+  std::vector<int64_t> send0((size_t)world + 1, 0), recv0((size_t)world + 1, 0);
+  for (int r = 0; r < world; ++r) {
+    send0[r + 1] = send0[r] + mx[(size_t)rank * world + r];
+    recv0[r + 1] = recv0[r] + mx[(size_t)r * world + rank];
+  }
+  const int64_t n_send = send0[world], n_recv = recv0[world];
+  std::vector<DBufP> sendbuf((size_t)nc);
+  std::vector<DColP> out((size_t)nc);
+  std::vector<Xfer> sends, recvs;
+  for (int c = 0; c < nc; ++c) {
+    const int w = phys_width(mine[c]->phys);
+    sendbuf[c] = ctx->alloc(std::max<size_t>((size_t)n_send * w, 16));
+    P.src[c] = (const unsigned char*)mine[c]->data->ptr;
+    P.dst[c] = (unsigned char*)sendbuf[c]->ptr;
+    P.width[c] = w;
+    auto d = std::make_shared<DCol>();
+    d->type = mine[c]->type;
+    d->phys = mine[c]->phys;
+    d->length = n_recv;
+    d->data = ctx->alloc(std::max<size_t>((size_t)n_recv * w, 16));
+    // conservative statistics: the bounds over everything the ranks hold contain what arrived here
+    bool stats = true;
+    long long mn = INT64_MAX, mxv = INT64_MIN;
+    for (int r = 0; r < world; ++r) {
+      const long long* m = &am[(size_t)r * meta_words + HDR + 5 * c];
+      if (am[(size_t)r * meta_words] == 0) continue;
+      if (!m[1]) stats = false;
+      mn = std::min(mn, m[2]);
+      mxv = std::max(mxv, m[3]);
+    }
+    if (c == node.prune_key_col) {  // the key column is additionally bounded by this rank's probe range
+      mn = std::max(mn, (long long)P.lo[rank]);
+      mxv = std::min(mxv, (long long)P.hi[rank]);
+    }
+    if (stats && mn <= mxv) {
+      d->has_stats = true;
+      d->vmin = mn;
+      d->vmax = mxv;
+    }
+    for (int r = 0; r < world; ++r) {
+      sends.push_back({r, (char*)sendbuf[c]->ptr + (size_t)send0[r] * w, (size_t)(send0[r + 1] - send0[r]) * w});
+      recvs.push_back({r, (char*)d->data->ptr + (size_t)recv0[r] * w, (size_t)(recv0[r + 1] - recv0[r]) * w});
+    }
+    out[c] = d;
+  }
+  if (n > 0 && n_send > 0) {
+    DBufP cursor = ctx->alloc(8 * (size_t)world);
+    std::vector<long long> c0(send0.begin(), send0.end() - 1);
+    store_words(ctx, (long long*)cursor->ptr, c0.data(), (size_t)world);
+    LAUNCH(ctx, k_prune_scatter, grid_for(ctx, n, 256), 256, 0, n, P, (const unsigned char*)mask->ptr, (unsigned long long*)cursor->ptr);
+  }
+  comm_exchange(ctx, sends, recvs);
+  ctx->trace("broadcast: pruned exchange");
+  View v;
+  v.schema = in.schema;
+  v.num_rows = n_recv;
+  v.num_batches = 1;
+  for (int c = 0; c < nc; ++c) v.cols.push_back({out[c], nullptr});
+  int64_t total = 0;
+  for (int r = 0; r < world; ++r) total += am[(size_t)r * meta_words];
+  node.strategy = "broadcast[key-range pruned: " + std::to_string(n_recv) + " of " + std::to_string(total) + " rows of " + std::to_string(world) +
+                  " ranks needed here, " + std::to_string(n_send) + " sent]";
+  return v;
+}
+
 // executes (once per C-ABI call) and returns the memo of a Broadcast node
 static BroadcastMemo& broadcast_run(PlanNode& node) {
   Ctx* ctx = node.ctx;
@@ -99,25 +244,47 @@ static BroadcastMemo& broadcast_run(PlanNode& node) {
     if (mine[c]->phys == PH_STR || mine[c]->phys == PH_BIT)
       throw_internal("Broadcast exchanges fixed-width columns only (column '" + in.schema.fields[c].name + "' is " + in.schema.fields[c].type.str() + ")");
   }
-  // ---- meta block: [n_rows, child signature, per column: NULLs, has_stats, min, max, -] --------------------------
-  const size_t meta_words = 2 + 5 * (size_t)nc;
+  // ---- meta block: [n_rows, child signature, probe key range (has, lo, hi); per column: NULLs, has_stats, min, max, phys] --------------------------
+  constexpr size_t HDR = 5;  // n_rows, child signature, probe range: has / lo / hi
+  const size_t meta_words = HDR + 5 * (size_t)nc;
   DBufP meta = ctx->alloc_zero(meta_words * 8), all_meta = ctx->alloc(meta_words * 8 * (size_t)world);
   std::vector<long long> h(meta_words, 0);
   h[0] = n_local;
   h[1] = (long long)child_sig;
+  // pruned broadcast: the value range of this rank's PROBE-side key column (table statistics, cached on the column)
+  if (node.prune_table) {
+    TableImpl& pt = *node.prune_table;
+    pt.consolidate();
+    if (node.prune_probe_col >= 0 && node.prune_probe_col < (int)pt.cols.size() && pt.cols[node.prune_probe_col]) {
+      DCol& pc = *pt.cols[node.prune_probe_col];
+      {
+        SpecSuspend cached_work(ctx);
+        ensure_stats(ctx, pc);
+      }
+      if (pc.has_stats && pc.null_count == 0) {
+        h[2] = 1;
+        h[3] = (long long)pc.vmin;
+        h[4] = (long long)pc.vmax;
+      } else if (pt.num_rows == 0) {
+        h[2] = 1;  // an empty probe side needs no build rows at all
+        h[3] = 1;
+        h[4] = 0;
+      }
+    }
+  }
   for (int c = 0; c < nc; ++c) {
-    h[2 + 5 * c] = mine[c]->null_count;
-    h[2 + 5 * c + 4] = (long long)mine[c]->phys;
+    h[HDR + 5 * c] = mine[c]->null_count;
+    h[HDR + 5 * c + 4] = (long long)mine[c]->phys;
   }
   std::vector<char> want_stats((size_t)nc, 0);
   for (int c = 0; c < nc; ++c) {
     const Phys ph = mine[c]->phys;
     want_stats[c] = ph == PH_I8 || ph == PH_I16 || ph == PH_I32 || ph == PH_I64 || ph == PH_D64 || ph == PH_U8 || ph == PH_U16 || ph == PH_U32;
-    h[2 + 5 * c + 1] = want_stats[c] ? 1 : 0;
+    h[HDR + 5 * c + 1] = want_stats[c] ? 1 : 0;
   }
   store_words(ctx, (long long*)meta->ptr, h.data(), meta_words);
   for (int c = 0; c < nc; ++c)
-    if (want_stats[c]) stats_to_device(ctx, *mine[c], (long long*)meta->ptr + 2 + 5 * c + 2);
+    if (want_stats[c]) stats_to_device(ctx, *mine[c], (long long*)meta->ptr + HDR + 5 * c + 2);
   comm_all_gather_any(ctx, meta->ptr, all_meta->ptr, meta_words * 8);
   std::vector<long long> am(meta_words * (size_t)world);
   ctx->d2h_sync(am.data(), all_meta->ptr, am.size() * 8);  // the one host round trip of the exchange
@@ -130,6 +297,27 @@ static BroadcastMemo& broadcast_run(PlanNode& node) {
     sig = (sig ^ (uint64_t)am[(size_t)r * meta_words + 1]) * 0xff51afd7ed558ccdULL;
     sig = (sig ^ (uint64_t)rows[r]) * 0xff51afd7ed558ccdULL;
     sig ^= sig >> 29;
+  }
+  // ---- pruned variant: every rank receives only the rows whose key lies in ITS probe-side key range ---------------------
+  if (node.prune_table && node.order_free) {
+    bool ok = node.prune_key_col >= 0 && node.prune_key_col < nc && nc <= 16;
+    for (int r = 0; r < world && ok; ++r) ok = am[(size_t)r * meta_words + 2] != 0;
+    for (int c = 0; c < nc && ok; ++c)
+      for (int r = 0; r < world && ok; ++r) {
+        const long long* m = &am[(size_t)r * meta_words + HDR + 5 * c];
+        ok = m[0] == 0 && (Phys)m[4] == mine[c]->phys && mine[c]->phys != PH_NULL;
+      }
+    const int kw = ok ? phys_width(mine[node.prune_key_col]->phys) : 0;
+    ok = ok && (kw == 4 || kw == 8) && mine[node.prune_key_col]->phys != PH_F32 && mine[node.prune_key_col]->phys != PH_F64 &&
+         mine[node.prune_key_col]->phys != PH_U64;
+    if (ok) {
+      View v = broadcast_pruned(node, in, mine, am, meta_words, HDR, world, rank);
+      for (int r = 0; r < world; ++r) sig = (sig ^ (uint64_t)am[(size_t)r * meta_words + 3] ^ ((uint64_t)am[(size_t)r * meta_words + 4] << 1)) * 0xff51afd7ed558ccdULL;
+      memo->view = v;
+      memo->signature = sig ^ (uint64_t)v.num_rows;
+      memo->epoch = ctx->exec_epoch;
+      return *memo;
+    }
   }
   const int64_t total = row0[world];
   // ---- gathered columns + the grouped exchange -----------------------------------------------------------------------
@@ -152,7 +340,7 @@ static BroadcastMemo& broadcast_run(PlanNode& node) {
     bool stats = true;
     long long mn = INT64_MAX, mx = INT64_MIN;
     for (int r = 0; r < world; ++r) {
-      const long long* m = &am[(size_t)r * meta_words + 2 + 5 * c];
+      const long long* m = &am[(size_t)r * meta_words + HDR + 5 * c];
       nulls += m[0];
       if (rows[r] > 0 && (Phys)m[4] != PH_NULL) {
         if (phys == PH_NULL) phys = (Phys)m[4];

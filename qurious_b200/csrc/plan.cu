@@ -1010,6 +1010,23 @@ int qgpu_plan_broadcast(qgpu_ctx* ctx, qgpu_plan* child, int32_t order_free, qgp
   });
 }
 
+int qgpu_plan_broadcast_pruned(qgpu_ctx* ctx, qgpu_plan* child, int32_t key_column, qgpu_table* probe_table, int32_t probe_key_column,
+                               qgpu_plan** out) {
+  if (!ctx || !child || !probe_table || !out) return QGPU_ERR_INTERNAL;
+  return guard(&ctx->c, [&] {
+    if (key_column < 0 || key_column >= (int32_t)child->node->schema.fields.size()) throw_internal("Broadcast: key column out of range");
+    if (probe_key_column < 0 || probe_key_column >= (int32_t)probe_table->t->schema.fields.size()) throw_internal("Broadcast: probe key column out of range");
+    auto n = new_node(ctx, PK_BROADCAST);
+    n->children.push_back(child->node);
+    n->schema = child->node->schema;
+    n->order_free = true;
+    n->prune_table = probe_table->t;
+    n->prune_key_col = key_column;
+    n->prune_probe_col = probe_key_column;
+    *out = new qgpu_plan{n};
+  });
+}
+
 int qgpu_plan_final_aggregate(qgpu_ctx* ctx, qgpu_plan* child, const int32_t* key_columns, int32_t n_keys, const int32_t* value_columns,
                               const int32_t* merge_ops, int32_t n_values, qgpu_plan** out) {
   if (!ctx || !child || !out || !key_columns || n_keys <= 0 || n_values < 0 || (n_values > 0 && (!value_columns || !merge_ops)))

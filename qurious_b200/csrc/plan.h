@@ -50,6 +50,9 @@ struct PlanNode {
   // exchange operators (exchange.cu): Broadcast memo; FinalAggregate key / value columns and merge operators (0 SUM, 1 MIN, 2 MAX)
   std::shared_ptr<void> exchange_cache;
   std::vector<int> exchange_keys, exchange_cols, exchange_ops;
+  // pruned Broadcast: rows travel only to the ranks whose probe-side key range (statistics of prune_table's column) holds their key
+  std::shared_ptr<TableImpl> prune_table;
+  int prune_key_col = -1, prune_probe_col = -1;
   bool order_free = false;  // the consumer does not depend on this node's output row order (qgpu_plan_set_order_free)
   // sharded execution (shard.cu): stop before finalisation / resume from merged states
   AggPending* defer = nullptr;

@@ -487,7 +487,9 @@ class BroadcastJoinAggregate:
     collective layer and the single-GPU emulation in the tests."""
 
     def __init__(self, ctx: _lib.Context, build_plan, probe_plan_of: Callable, world: int,
-                 all_gather_ragged: Optional[Callable] = None):
+                 all_gather_ragged: Optional[Callable] = None, prune=None):
+        """prune = (key column of build_plan's output, this rank's probe-side MemoryTable, its key column): Broadcast's
+        key-range pruning (every rank receives only the build rows its probe shard can match)."""
         self.ctx, self.build_plan, self.probe_plan_of, self.world = ctx, build_plan, probe_plan_of, int(world)
         self.gather = all_gather_ragged
         self.last_strategy = ""
@@ -496,7 +498,7 @@ class BroadcastJoinAggregate:
             from .physical.plan import Broadcast, FinalAggregate
             if self.world > 1 and ctx.comm_world()[1] != self.world:
                 init_comm(ctx)
-            probe = probe_plan_of(Broadcast(build_plan, order_free=True))
+            probe = probe_plan_of(Broadcast(build_plan, order_free=True, prune=prune))
             keys, aggs = merge_spec_of(probe)
             self.plan = FinalAggregate(probe, keys, aggs)
 

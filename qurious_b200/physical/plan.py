@@ -561,8 +561,11 @@ class Broadcast(PhysicalPlan):
     `input` over its shard and receives the rows of ALL ranks, in rank order -- the build side of a broadcast join (SURVEY 8e
     "Q3 joins").  order_free: the consumer does not depend on the input's row order (it feeds a hash table)."""
 
-    def __init__(self, input: PhysicalPlan, order_free: bool = False):
-        self.input, self.order_free, self.schema = input, bool(order_free), input.schema
+    def __init__(self, input: PhysicalPlan, order_free: bool = False, prune: Optional[Tuple[int, "MemoryTable", int]] = None):
+        """prune = (key column of `input`, this rank's probe-side MemoryTable, its key column): the rows feed the build side of
+        an Inner equi-join against that table, so a row only has to reach the ranks whose probe-side key RANGE contains its key
+        (dynamic partition pruning; implies order_free)."""
+        self.input, self.order_free, self.schema, self.prune = input, bool(order_free) or prune is not None, input.schema, prune
 
     def children(self):
         return [self.input]
@@ -570,6 +573,12 @@ class Broadcast(PhysicalPlan):
     def _build(self, ctx, keep):
         ch = self.input._build(ctx, keep)
         h = ctypes.c_void_p()
+        if self.prune is not None:
+            key_col, table, probe_col = self.prune
+            dev = table.device_table(ctx)
+            ctx.check(ctx.lib.qgpu_plan_broadcast_pruned(ctx.handle, ch, int(key_col), dev.handle, int(probe_col), ctypes.byref(h)))
+            keep.append(("plan", h))
+            return h
         ctx.check(ctx.lib.qgpu_plan_broadcast(ctx.handle, ch, 1 if self.order_free else 0, ctypes.byref(h)))
         keep.append(("plan", h))
         return h

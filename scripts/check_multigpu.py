@@ -73,20 +73,22 @@ for q in ("q1", "q6"):
 # ---- Q3: broadcast build + gather-merge ---------------------------------------------------------------------------------------
 raw = bench.gen_raw("q3", SF, "cuda", rank, world)
 tabs = {k: tpch.to_device_table(ctx, v) for k, v in raw.items()}
-bj = qd.BroadcastJoinAggregate(ctx, tpch.q3_build_plan(tpch.Database(0.0, tabs["customer"], tabs["orders"], None)),
-                               lambda b: tpch.q3_probe_plan(b, tabs["lineitem"]), world)
-for rnd in range(3):                      # a learning run, then replays of the learned counts
-    mine = rows_of(bj.execute())
-    parts = [None] * world
-    dist.all_gather_object(parts, mine)    # the result stays sharded: every group on exactly one rank
-    got = sorted(r for part in parts for r in part)
-    if rnd == 0:
-        ref = sorted(rows_of(single("q3", SF))) if rank == 0 else None
-        box = [ref]
-        dist.broadcast_object_list(box, src=0)
-    keys = [r[0] for r in got]
-    report(f"q3 broadcast join + final aggregate (native plan, run {rnd})", got == box[0] and len(keys) == len(set(keys)),
-           f"{len(got)} groups, {len(mine)} here")
+for variant in ("full broadcast", "key-range pruned broadcast"):
+  prune = None if variant.startswith("full") else (0, tabs["lineitem"], tabs["lineitem"].schema.get_field_index("l_orderkey"))
+  bj = qd.BroadcastJoinAggregate(ctx, tpch.q3_build_plan(tpch.Database(0.0, tabs["customer"], tabs["orders"], None)),
+                                 lambda b: tpch.q3_probe_plan(b, tabs["lineitem"]), world, prune=prune)
+  for rnd in range(3):                      # a learning run, then replays of the learned counts
+      mine = rows_of(bj.execute())
+      parts = [None] * world
+      dist.all_gather_object(parts, mine)    # the result stays sharded: every group on exactly one rank
+      got = sorted(r for part in parts for r in part)
+      if rnd == 0:
+          ref = sorted(rows_of(single("q3", SF))) if rank == 0 else None
+          box = [ref]
+          dist.broadcast_object_list(box, src=0)
+      keys = [r[0] for r in got]
+      report(f"q3 {variant} + final aggregate (native plan, run {rnd})", got == box[0] and len(keys) == len(set(keys)),
+             f"{len(got)} groups, {len(mine)} here; " + bj.last_strategy[-150:])
 
 # ---- group-by exchange (configs[3] shape at 1/250 scale) ----------------------------------------------------------------------
 os.environ["QGPU_RADIX"] = "force"

@@ -50,8 +50,8 @@ def shard(mt: MemoryTable, r: int, world: int) -> MemoryTable:
                                [pa.RecordBatch.from_pylist([], schema=mt.schema)])
 
 
-@pytest.mark.parametrize("world", [2, 3, 8])
-def test_q3_broadcast_join_final_aggregate(gpu_ctx, world):
+@pytest.mark.parametrize("world,pruned", [(2, False), (3, True), (8, False), (8, True)])
+def test_q3_broadcast_join_final_aggregate(gpu_ctx, world, pruned):
     sf = 0.02
     db = tpch.generate(sf, batch_rows=None)
     single = rows_of(tpch.q3_plan(db).execute(gpu_ctx))
@@ -59,8 +59,9 @@ def test_q3_broadcast_join_final_aggregate(gpu_ctx, world):
     def work(r, ctx):
         o_sh, l_sh = shard(db.orders, r, world), shard(db.lineitem, r, world)
         cust = MemoryTable.try_new(db.customer.schema, db.customer.data)
+        prune = (0, l_sh, l_sh.schema.get_field_index("l_orderkey")) if pruned else None
         bj = BroadcastJoinAggregate(ctx, tpch.q3_build_plan(tpch.Database(sf, cust, o_sh, None)),
-                                    lambda b: tpch.q3_probe_plan(b, l_sh), world)
+                                    lambda b: tpch.q3_probe_plan(b, l_sh), world, prune=prune)
         rounds = [rows_of(bj.execute()) for _ in range(3)]          # learning run, then replays of the learned counts
         strat = bj.last_strategy
         bj.release()
@@ -71,7 +72,8 @@ def test_q3_broadcast_join_final_aggregate(gpu_ctx, world):
         keys = [r[0] for r in rows]
         assert len(keys) == len(set(keys)), "a group was returned by two ranks"
         check_rows(f"q3 x{world} round {i}", rows, single, ordered=False)
-    assert "final-aggregate[" in res[0][1] and "broadcast[all-gather" in res[0][1] and "fused_join_probe_agg" in res[0][1], res[0][1]
+    assert "final-aggregate[" in res[0][1] and "fused_join_probe_agg" in res[0][1], res[0][1]
+    assert ("broadcast[key-range pruned" if pruned else "broadcast[all-gather") in res[0][1], res[0][1]
 
 
 def test_broadcast_gathers_rows_in_rank_order_with_nulls(gpu_ctx):
