@@ -1174,11 +1174,46 @@ static bool radix_choose(const RParams& R, double groups, int64_t n_tuples, int 
 
 static size_t radix_scatter_smem(const RParams& R) { return (size_t)R.n_comp * R_T * 8 + 512 * 8 + 512 * 4 * 2 + (size_t)R_T * 2; }
 
+// input stages of the TMA-pipelined scatter (k_radix_scatter_tma): LEVEL 1 stages the raw columns of a 4096-row tile,
+// LEVEL 2 the tuple components (+ 2 tuples: an 8 B aligned source is copied from the 16 B boundary below it).  false when
+// two stages do not fit the shared memory (wide tuples: the register-staged kernel runs) or QGPU_RADIX_SCATTER=regs.
+static size_t radix_tma_smem(const RStage& st) { return 128 + 2 * (size_t)st.stage_bytes + 2 * (size_t)R_T * 2 + 512 * 8 + 512 * 4 * 2; }
+static bool radix_tma_stage(int level, const FParams& P, const RParams& R, RStage* st) {
+  const char* e = getenv("QGPU_RADIX_SCATTER");
+  if (e && strcmp(e, "regs") == 0) return false;
+  memset(st, 0, sizeof(*st));
+  uint32_t off = 0;
+  if (level == 1) {
+    st->n_in = (uint32_t)P.n_cols;
+    for (int c = 0; c < P.n_cols; ++c) {
+      st->off[c] = off;
+      st->bytes_per_row[c] = P.cols[c].width;
+      off += (uint32_t)(((size_t)R_T * P.cols[c].width + 127) & ~(size_t)127);
+    }
+  } else {
+    st->n_in = (uint32_t)R.n_comp;
+    for (int c = 0; c < R.n_comp; ++c) {
+      st->off[c] = off;
+      st->bytes_per_row[c] = 8;
+      off += (uint32_t)(((size_t)(R_T + 2) * 8 + 127) & ~(size_t)127);
+    }
+  }
+  st->stage_bytes = off;
+  return radix_tma_smem(*st) + 256 <= (size_t)F_SMEM_MAX;
+}
+
 static void radix_launch_scatter1(Ctx* ctx, const FParams& P, const RParams& R) {
+  const int64_t tiles1 = (P.n_rows + R_T - 1) / R_T;
+  RStage st;
+  if (radix_tma_stage(1, P, R, &st)) {
+    const size_t smem = radix_tma_smem(st);
+    CUDA_CHECK(cudaFuncSetAttribute(k_radix_scatter_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAUNCH(ctx, k_radix_scatter_tma<1>, (int)std::max<int64_t>(1, std::min<int64_t>(tiles1, (int64_t)ctx->sm_count)), R2_NT, smem, P, R, st);
+    return;
+  }
   const size_t sc_smem = radix_scatter_smem(R);
   CUDA_CHECK(cudaFuncSetAttribute(k_radix_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
   const int sc_per_sm = (2 * (sc_smem + 1024 + 64) <= (size_t)233472) ? 2 : 1;
-  const int64_t tiles1 = (P.n_rows + R_T - 1) / R_T;
   LAUNCH(ctx, k_radix_scatter<1>, (int)std::max<int64_t>(1, std::min<int64_t>(tiles1, (int64_t)ctx->sm_count * sc_per_sm)), R_SNT, sc_smem, P, R);
 }
 
@@ -1201,34 +1236,10 @@ static bool radix_tail(PlanNode& agg, const View& v, FusedPlan& fp, const FParam
   R.hist2 = (unsigned int*)hist2->ptr;
   R.off2 = (unsigned long long*)off2->ptr;
   R.cur2 = (unsigned long long*)cur2->ptr;
-  DBufP out_code = ctx->alloc((size_t)out_cap * 8 + 64), out_cnt = ctx->alloc((size_t)out_cap * 8 + 64);
-  std::vector<DBufP> out_acc;
-  R.out_code = (unsigned long long*)out_code->ptr;
-  R.out_cnt = (unsigned long long*)out_cnt->ptr;
-  for (int k = 0; k < P.n_accs; ++k) {
-    out_acc.push_back(ctx->alloc((size_t)out_cap * 8 + 64));
-    R.out_acc[k] = (unsigned long long*)out_acc.back()->ptr;
-  }
-  const size_t sc_smem = radix_scatter_smem(R);
-  CUDA_CHECK(cudaFuncSetAttribute(k_radix_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
-  const int sc_per_sm = (2 * (sc_smem + 1024 + 64) <= (size_t)233472) ? 2 : 1;
-  RParams R2 = R;
-  R2.world = 1;  // level 2 and the final pass are local
-  LAUNCH(ctx, k_radix_hist2, (int)std::min<int64_t>(std::max<int64_t>(n_tiles2, 1), (int64_t)ctx->sm_count * 8), R_NT, 0, R2);
-  LAUNCH(ctx, k_radix_scan2, 1, 1024, 0, R2.hist2, (int)n_buckets, R2.off2, R2.cur2);
-  LAUNCH(ctx, k_radix_scatter<2>, (int)std::min<int64_t>(std::max<int64_t>(n_tiles2, 1), (int64_t)ctx->sm_count * sc_per_sm), R_SNT, sc_smem,
-         P, R2);
-  const size_t ag_smem = (size_t)(cap + 1) * 18 + (size_t)row_cap * row_bytes + 64;
-  CUDA_CHECK(cudaFuncSetAttribute(k_radix_agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ag_smem));
-  LAUNCH(ctx, k_radix_agg, (int)std::min<int64_t>(n_buckets, (int64_t)ctx->sm_count), R_AGG_NT, ag_smem, R2);
-  unsigned long long fin[2];
-  ctx->d2h_sync(fin, (char*)st->ptr + RO_NOUT, 16);
-  ctx->trace("radix: level 2 + aggregate");
-  const int64_t n_groups = (int64_t)fin[0];
-  *fail = (int)fin[1];
-  if (*fail != 0) return false;
-  slab_b.reset();
-  // ---- key columns from the packed codes --------------------------------------------------------------------------
+  // ---- result layout.  Key columns are decoded from the packed code by the final pass itself.  When every aggregate is
+  //      a copy (SUM / MIN / MAX of an int64-like value, COUNT), a sign extension (Decimal128) or a Float64 mean of one
+  //      accumulator, the final pass also writes the RESULT columns (no NULLs can arise: every group has rows and the
+  //      arguments are NULL-free in this mode) and finish_aggregate's extra pass over 5 x 100 M values disappears.
   RKeys rk;
   memset(&rk, 0, sizeof(rk));
   rk.n_keys = P.n_keys;
@@ -1237,9 +1248,8 @@ static bool radix_tail(PlanNode& agg, const View& v, FusedPlan& fp, const FParam
     auto d = std::make_shared<DCol>();
     d->type = fp.key_src[k]->type;
     d->phys = fp.key_src[k]->phys;
-    d->length = n_groups;
     d->null_count = 0;
-    d->data = ctx->alloc(std::max<size_t>((size_t)n_groups * fp.key_width[k], 16));
+    d->data = ctx->alloc(std::max<size_t>((size_t)out_cap * fp.key_width[k], 16));
     rk.shift[k] = key_shift[k];
     rk.bits[k] = key_bits[k];
     rk.width[k] = fp.key_width[k];
@@ -1247,36 +1257,137 @@ static bool radix_tail(PlanNode& agg, const View& v, FusedPlan& fp, const FParam
     rk.out[k] = d->data->ptr;
     key_cols.push_back(d);
   }
-  if (n_groups > 0) LAUNCH(ctx, k_radix_keys, grid_for(ctx, n_groups, 256), 256, 0, (const unsigned long long*)out_code->ptr, n_groups, rk);
-  for (auto& kc : key_cols)
-    if (kc->phys == PH_D64) kc = materialize_arrow(ctx, {kc, nullptr}, n_groups);
-  // ---- GroupAccs ----------------------------------------------------------------------------------------------------
-  GroupAccs accs;
-  accs.n_groups = n_groups;
-  accs.unordered = true;
+  std::vector<int> acc_kind(fp.specs.size(), AK_COUNT);
   for (size_t i = 0; i < fp.specs.size(); ++i) {
     const int k = fp.acc_of[i];
-    int ak = AK_COUNT;
-    if (k >= 0) {
-      const int fk = P.accs[k].kind;
-      const VClass vc = class_of(fp.specs[i].arg->result_type);
-      if (fk == FK_SUMF) ak = AK_SUM_F64;
-      else if (fk == FK_SUM) ak = vc == VC_DEC ? AK_SUM_DEC : AK_SUM_I64;
-      else if (vc == VC_DEC) ak = fk == FK_MIN ? AK_MIN_DEC : AK_MAX_DEC;
-      else if (vc == VC_UINT) ak = fk == FK_MIN ? AK_MIN_U64 : AK_MAX_U64;
-      else ak = fk == FK_MIN ? AK_MIN_I64 : AK_MAX_I64;
-      accs.lo.push_back(out_acc[k]);
-    } else {
-      accs.lo.push_back(out_cnt);
+    if (k < 0) continue;
+    const int fk = P.accs[k].kind;
+    const VClass vc = class_of(fp.specs[i].arg->result_type);
+    if (fk == FK_SUMF) acc_kind[i] = AK_SUM_F64;
+    else if (fk == FK_SUM) acc_kind[i] = vc == VC_DEC ? AK_SUM_DEC : AK_SUM_I64;
+    else if (vc == VC_DEC) acc_kind[i] = fk == FK_MIN ? AK_MIN_DEC : AK_MAX_DEC;
+    else if (vc == VC_UINT) acc_kind[i] = fk == FK_MIN ? AK_MIN_U64 : AK_MAX_U64;
+    else acc_kind[i] = fk == FK_MIN ? AK_MIN_I64 : AK_MAX_I64;
+  }
+  bool direct = !getenv("QGPU_RADIX_NODIRECT");
+  std::vector<int> fin_mode(fp.specs.size(), 0);
+  {
+    int per_acc[F_MAXA] = {0}, n_cnt = 0;
+    for (size_t i = 0; i < fp.specs.size() && direct; ++i) {
+      const AggSpec& a = fp.specs[i];
+      DType produced = a.op == QGPU_AGG_COUNT ? mk_type(QGPU_T_INT64) : a.return_type;
+      if (produced != agg.schema.fields[fp.keys.size() + i].type) direct = false;  // finish_aggregate raises the schema error
+      const Phys op = out_phys_of(produced);
+      const int ak = acc_kind[i];
+      int mode = 0;
+      if (a.op == QGPU_AGG_COUNT) mode = op == PH_I64 ? 1 : 0;
+      else if (a.op == QGPU_AGG_AVG) mode = (ak == AK_SUM_F64 && op == PH_F64) ? 3 : 0;
+      else if (op == PH_I128) mode = (ak == AK_SUM_DEC || ak == AK_MIN_DEC || ak == AK_MAX_DEC) ? 2 : 0;
+      else if (op == PH_I64 || op == PH_U64)
+        mode = (ak == AK_SUM_I64 || ak == AK_MIN_I64 || ak == AK_MAX_I64 || ak == AK_MIN_U64 || ak == AK_MAX_U64) ? 1 : 0;
+      else if (op == PH_F64) mode = (ak == AK_SUM_F64 && a.op == QGPU_AGG_SUM) ? 1 : 0;
+      if (!mode) direct = false;
+      else if (fp.acc_of[i] < 0 ? ++n_cnt > 4 : ++per_acc[fp.acc_of[i]] > 2) direct = false;
+      fin_mode[i] = mode;
     }
-    accs.hi.push_back(nullptr);  // no carry in this mode: the high word is the sign extension
-    accs.kind.push_back(ak);
-    accs.cnt.push_back(out_cnt);
+  }
+  R.direct = direct ? 1 : 0;
+  R.n_cnt_dst = 0;
+  memset(R.fin_mode, 0, sizeof(R.fin_mode));
+  std::vector<DColP> agg_cols;
+  DBufP out_cnt;
+  std::vector<DBufP> out_acc;
+  if (direct) {
+    int per_acc[F_MAXA] = {0};
+    for (size_t i = 0; i < fp.specs.size(); ++i) {
+      const AggSpec& a = fp.specs[i];
+      auto col = std::make_shared<DCol>();
+      col->type = a.op == QGPU_AGG_COUNT ? mk_type(QGPU_T_INT64) : a.return_type;
+      col->phys = out_phys_of(col->type);
+      col->null_count = 0;
+      col->data = ctx->alloc((size_t)out_cap * phys_width(col->phys) + 64);
+      const int k = fp.acc_of[i];
+      if (k < 0) {
+        R.cnt_dst[R.n_cnt_dst++] = (unsigned long long*)col->data->ptr;
+      } else {
+        R.fin_mode[k][per_acc[k]] = fin_mode[i];
+        R.fin_dst[k][per_acc[k]++] = col->data->ptr;
+      }
+      agg_cols.push_back(col);
+    }
+  } else {
+    out_cnt = ctx->alloc((size_t)out_cap * 8 + 64);
+    R.out_cnt = (unsigned long long*)out_cnt->ptr;
+    for (int k = 0; k < P.n_accs; ++k) {
+      out_acc.push_back(ctx->alloc((size_t)out_cap * 8 + 64));
+      R.out_acc[k] = (unsigned long long*)out_acc.back()->ptr;
+    }
+  }
+  const size_t sc_smem = radix_scatter_smem(R);
+  CUDA_CHECK(cudaFuncSetAttribute(k_radix_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
+  const int sc_per_sm = (2 * (sc_smem + 1024 + 64) <= (size_t)233472) ? 2 : 1;
+  RParams R2 = R;
+  R2.world = 1;  // level 2 and the final pass are local
+  LAUNCH(ctx, k_radix_hist2, (int)std::min<int64_t>(std::max<int64_t>(n_tiles2, 1), (int64_t)ctx->sm_count * 8), R_NT, 0, R2);
+  LAUNCH(ctx, k_radix_scan2, 1, 1024, 0, R2.hist2, (int)n_buckets, R2.off2, R2.cur2);
+  RStage st2;
+  if (radix_tma_stage(2, P, R2, &st2)) {
+    const size_t smem = radix_tma_smem(st2);
+    CUDA_CHECK(cudaFuncSetAttribute(k_radix_scatter_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAUNCH(ctx, k_radix_scatter_tma<2>, (int)std::min<int64_t>(std::max<int64_t>(n_tiles2, 1), (int64_t)ctx->sm_count), R2_NT, smem, P, R2, st2);
+  } else {
+    LAUNCH(ctx, k_radix_scatter<2>, (int)std::min<int64_t>(std::max<int64_t>(n_tiles2, 1), (int64_t)ctx->sm_count * sc_per_sm), R_SNT, sc_smem,
+           P, R2);
+  }
+  const int ag_grid = (int)std::min<int64_t>(n_buckets, (int64_t)ctx->sm_count);
+  const size_t ag_smem = (size_t)(cap + 1) * 18 + (size_t)row_cap * row_bytes + 64;
+  CUDA_CHECK(cudaFuncSetAttribute(k_radix_agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ag_smem));
+  LAUNCH(ctx, k_radix_agg, ag_grid, R_AGG_NT, ag_smem, R2, rk);
+  unsigned long long fin[2];
+  ctx->d2h_sync(fin, (char*)st->ptr + RO_NOUT, 16);
+  ctx->trace("radix: level 2 + aggregate");
+  const int64_t n_groups = (int64_t)fin[0];
+  *fail = (int)fin[1];
+  if (*fail != 0) return false;
+  slab_b.reset();
+  for (auto& kc : key_cols) {
+    kc->length = n_groups;
+    if (kc->phys == PH_D64) kc = materialize_arrow(ctx, {kc, nullptr}, n_groups);
+  }
+  GroupAccs accs;
+  if (!direct) {
+    accs.n_groups = n_groups;
+    accs.unordered = true;
+    for (size_t i = 0; i < fp.specs.size(); ++i) {
+      const int k = fp.acc_of[i];
+      accs.lo.push_back(k >= 0 ? out_acc[k] : out_cnt);
+      accs.hi.push_back(nullptr);  // no carry in this mode: the high word is the sign extension
+      accs.kind.push_back(acc_kind[i]);
+      accs.cnt.push_back(out_cnt);
+    }
   }
   agg.strategy = "fused_scan_agg[radix-partitioned: 256 x " + std::to_string(1 << b2) + " buckets, smem table " + std::to_string(cap) +
                  " slots / " + std::to_string(row_cap) + " rows, " + std::to_string(R.n_comp) + " x 8 B tuples, " +
                  std::to_string(P.n_cols) + " cols, " + std::to_string(P.n_pred) + " range preds, " + std::to_string(P.n_accs) +
-                 " accs, est " + std::to_string((int64_t)est) + " groups]";
+                 " accs, est " + std::to_string((int64_t)est) + " groups" + (direct ? ", result columns written by the final pass]" : "]");
+  if (direct) {
+    View o;
+    o.schema = agg.schema;
+    o.num_rows = n_groups;
+    o.num_batches = 1;
+    for (size_t i = 0; i < fp.keys.size(); ++i) {
+      if (fp.keys[i]->result_type != agg.schema.fields[i].type)
+        throw_arrow("column types must match schema types, expected " + agg.schema.fields[i].type.str() + " but found " +
+                    fp.keys[i]->result_type.str() + " at column index " + std::to_string(i));
+      o.cols.push_back({key_cols[i], nullptr});
+    }
+    for (auto& c : agg_cols) {
+      c->length = n_groups;
+      o.cols.push_back({c, nullptr});
+    }
+    *out = o;
+    return true;
+  }
   *out = finish_aggregate(ctx, v, fp.keys, fp.specs, agg.schema, accs, &key_cols, nullptr);
   ctx->trace("radix: finish_aggregate");
   return true;

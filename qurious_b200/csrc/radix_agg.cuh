@@ -17,7 +17,8 @@
 //   k_radix_agg      one CTA per final bucket: rows counting-sorted by group in shared memory (key table claimed
 //                    with 64-bit CAS, ranks from native 32-bit shared atomics), one thread reduces each group
 //                    sequentially in registers and writes it straight to the group arrays
-//   k_radix_keys     packed code -> key columns
+//                    (key columns decoded from the packed code; when every aggregate is a copy / sign extension / f64 mean
+//                    of an accumulator the result columns themselves -- no finalise pass)
 //
 // Semantics are those of FM_HASH (hash.rs:45-107,138-170 with grouping by key equality);
 // output order is the bucket order (the reference's order is unspecified, quirk Q2).  Anything that does not fit
@@ -35,6 +36,7 @@ constexpr int R_MAXB2 = 9;
 constexpr int R_MAXCOMP = 6;              // tuple components (code + operand values) that fit the sort tile
 constexpr int R_HLL_BITS = 12;
 constexpr int R_HLL_M = 1 << R_HLL_BITS;
+constexpr int R_HLL_SAMPLE = 8;          // the sketch sees the keys whose hash bits 52..54 are zero
 constexpr int R_AGG_NT = 1024;            // threads per CTA of the final pass
 constexpr int R_U = 8;                    // final pass: global loads in flight per thread
 static_assert(R_AGG_NT == 1024, "the final pass scans 32 warp totals with one warp");
@@ -64,7 +66,6 @@ struct RParams {
   unsigned int* hist2;        // [256 << b2]
   unsigned long long* off2;   // [(256 << b2) + 1]
   unsigned long long* cur2;   // [256 << b2]
-  unsigned long long* out_code;
   unsigned long long* out_acc[F_MAXA];
   unsigned long long* out_cnt;
   unsigned long long* n_out;
@@ -72,28 +73,41 @@ struct RParams {
   int* overflow;
   // multi-GPU exchange (world > 1): level-1 bucket b belongs to rank b % world; the level-1 scatter writes its tuples
   // straight into the owner's tuple arrays over NVLink (peer_a[rank][component]; the local rank's entry is tup_a)
+  // final pass writing the result columns itself (radix_tail: every aggregate is a plain copy / sign extension / f64 mean
+  // of an accumulator): accumulator k -> up to two result columns, COUNT columns, key columns decoded from the code
+  int32_t direct, n_cnt_dst;
+  int32_t fin_mode[F_MAXA][2];   // 0 = none, 1 = 8-byte copy, 2 = 16-byte sign extension (Decimal128), 3 = f64 sum / count
+  void* fin_dst[F_MAXA][2];
+  unsigned long long* cnt_dst[4];
   int32_t world, nopf;  // nopf: experiment bits (QGPU_RADIX_NOPF) -- 1 = L2 prefetch in scatter<1> ON, 2 / 4 = no L2 prefetch in scatter<2> / k_radix_agg, 8 = one-pass probing in k_radix_agg
   unsigned long long* peer_a[8][R_MAXCOMP];
 };
 
-// guarded variant of load_rows for operands read straight from global memory (no staged tile behind the tail)
-__device__ __forceinline__ void load_rows_g(const unsigned char* col, uint32_t wk, int tid, int rows, int64_t (&x)[F_R]) {
+// guarded variant of load_rows for operands read straight from global memory (no staged tile behind the tail); the width
+// is dispatched once per call, not once per row
+template <typename T>
+__device__ __forceinline__ void load_rows_t(const unsigned char* col, int tid, int rows, int64_t (&x)[F_R]) {
+  const T* c = (const T*)col;
+  if (rows == F_T) {
 #pragma unroll
-  for (int j = 0; j < F_R; ++j) {
-    const int r = j * F_NT + tid;
-    int64_t v = 0;
-    if (r < rows) {
-      switch (wk) {
-        case 8: v = ((const int64_t*)col)[r]; break;
-        case 4: v = (int64_t)((const int32_t*)col)[r]; break;
-        case 4 | 256: v = (int64_t)((const uint32_t*)col)[r]; break;
-        case 2: v = (int64_t)((const int16_t*)col)[r]; break;
-        case 2 | 256: v = (int64_t)((const uint16_t*)col)[r]; break;
-        case 1: v = (int64_t)((const int8_t*)col)[r]; break;
-        default: v = (int64_t)((const uint8_t*)col)[r]; break;
-      }
+    for (int j = 0; j < F_R; ++j) x[j] = (int64_t)c[j * F_NT + tid];
+  } else {
+#pragma unroll
+    for (int j = 0; j < F_R; ++j) {
+      const int r = j * F_NT + tid;
+      x[j] = r < rows ? (int64_t)c[r] : 0;
     }
-    x[j] = v;
+  }
+}
+__device__ __forceinline__ void load_rows_g(const unsigned char* col, uint32_t wk, int tid, int rows, int64_t (&x)[F_R]) {
+  switch (wk) {
+    case 8: load_rows_t<int64_t>(col, tid, rows, x); break;
+    case 4: load_rows_t<int32_t>(col, tid, rows, x); break;
+    case 4 | 256: load_rows_t<uint32_t>(col, tid, rows, x); break;
+    case 2: load_rows_t<int16_t>(col, tid, rows, x); break;
+    case 2 | 256: load_rows_t<uint16_t>(col, tid, rows, x); break;
+    case 1: load_rows_t<int8_t>(col, tid, rows, x); break;
+    default: load_rows_t<uint8_t>(col, tid, rows, x); break;
   }
 }
 __device__ __forceinline__ const unsigned char* gcol(const FParams& p, int col, int64_t row0) {
@@ -146,7 +160,10 @@ __global__ void __launch_bounds__(R_NT) k_radix_hist1(const __grid_constant__ FP
       if (!((pass >> j) & 1)) continue;
       const uint64_t h = fmix64(code[j]);
       atomicAdd(&sh[h >> (64 - R_B1)], 1u);
-      // HyperLogLog: register = low 12 bits, rank = leading zeros of bits 12..51 (40 bits) + 1
+      // HyperLogLog over the keys whose hash bits 52..54 are zero (a 1/8 sample of the KEY space: a key is in or out
+      // with all of its rows, so the estimate is distinct / 8): register = low 12 bits, rank = leading zeros of bits
+      // 12..51 (40 bits) + 1
+      if ((h >> 52) & (R_HLL_SAMPLE - 1)) continue;
       const uint64_t w = (h >> R_HLL_BITS) & ((1ull << 40) - 1);
       const unsigned rho = w ? (unsigned)(__clzll((long long)w) - 24 + 1) : 41u;
       atomicMax(&sl[h & (R_HLL_M - 1)], rho);
@@ -397,6 +414,309 @@ __global__ void __launch_bounds__(R_SNT, 2) k_radix_scatter(const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The scatter as a TMA pipeline (the default whenever two input stages of a 4096-tuple tile fit the shared memory; the
+// register-staged kernel above remains for wider tuples).  ncu on the kernel above: issue slots 41 % busy, DRAM 50-60 %,
+// and the two add up -- with every tile's loads issued by the threads that then wait for them, and two CTAs per SM, the
+// memory system idles while a CTA ranks and sorts, and the SM idles while it loads.  Here ONE CTA of 1024 threads per SM
+// keeps two input stages: a few lanes issue the 1-D bulk copies (cp.async.bulk -> mbarrier, SASS UBLKCP) of tile i + 1
+// before anybody touches tile i, so the input of a whole tile (~96 KB) is in flight during all of tile i's phases.
+// The tile is not sorted through shared memory either: the counting sort places only a 16-bit SOURCE INDEX per output
+// position; the write-out gathers the tuple from the input stage (LEVEL 1: evaluates the operand values from the staged
+// raw columns there) and stores it to its run -- one shared-memory pass over the tuple data instead of three.
+//   phase 1  code (LEVEL 1: predicates + packed key) from the stage, digit, unordered rank (native shared atomicAdd)
+//   scan     exclusive scan of the bin counts; one global reservation per non-empty bin, its round trip overlapping phase 2
+//   phase 2  source index + bin of every output position
+//   phase 3  coalesced write-out (consecutive threads = consecutive tuples of one bin)
+// dynamic shared memory: full[2] mbarriers (128 B) | stage 0 | stage 1 | src[R_T] u16 | bin[R_T] u16 | delta[512] u64 |
+//                        hist[512] u32 | toff[512] u32
+constexpr int R2_NT = 1024;
+constexpr int R2_PT = R_T / R2_NT;  // tuples per thread and tile
+struct RStage {
+  uint32_t n_in, stage_bytes;
+  uint32_t off[F_MAXC];    // LEVEL 1: staged column c of FParams::cols; LEVEL 2: tuple component c
+  uint32_t bytes_per_row[F_MAXC];
+};
+static_assert(F_MAXC >= R_MAXCOMP, "RStage holds columns or components");
+
+// element idx[u] of a staged column, u = 0..R2_PT-1 (width dispatched once)
+template <typename T>
+__device__ __forceinline__ void lds_rows_t(const unsigned char* col, const int (&idx)[R2_PT], int64_t (&x)[R2_PT]) {
+  const T* c = (const T*)col;
+#pragma unroll
+  for (int u = 0; u < R2_PT; ++u) x[u] = (int64_t)c[idx[u]];
+}
+__device__ __forceinline__ void lds_rows(const unsigned char* col, uint32_t wk, const int (&idx)[R2_PT], int64_t (&x)[R2_PT]) {
+  switch (wk) {
+    case 8: lds_rows_t<int64_t>(col, idx, x); break;
+    case 4: lds_rows_t<int32_t>(col, idx, x); break;
+    case 4 | 256: lds_rows_t<uint32_t>(col, idx, x); break;
+    case 2: lds_rows_t<int16_t>(col, idx, x); break;
+    case 2 | 256: lds_rows_t<uint16_t>(col, idx, x); break;
+    case 1: lds_rows_t<int8_t>(col, idx, x); break;
+    default: lds_rows_t<uint8_t>(col, idx, x); break;
+  }
+}
+// packed key of the staged rows idx[] (LEVEL 1)
+__device__ __forceinline__ void r2_codes(const FParams& p, const RStage& st, const unsigned char* stage, const int (&idx)[R2_PT],
+                                         uint64_t (&code)[R2_PT]) {
+#pragma unroll
+  for (int u = 0; u < R2_PT; ++u) code[u] = 0;
+#pragma unroll 1
+  for (int k = 0; k < p.n_keys; ++k) {
+    int64_t x[R2_PT];
+    lds_rows(stage + st.off[p.keys[k].col], p.keys[k].wk, idx, x);
+    const uint64_t base = (uint64_t)p.keys[k].base, mult = p.keys[k].mult;
+#pragma unroll
+    for (int u = 0; u < R2_PT; ++u) code[u] += ((uint64_t)x[u] - base) * mult;
+  }
+}
+
+struct R2Tile {
+  int64_t base;  // first row (LEVEL 1) / first level-1 tuple (LEVEL 2)
+  int rows, b1;
+};
+
+template <int LEVEL>
+__global__ void __launch_bounds__(R2_NT, 1) k_radix_scatter_tma(const __grid_constant__ FParams p, const __grid_constant__ RParams r,
+                                                                const __grid_constant__ RStage st) {
+  extern __shared__ __align__(128) unsigned char rsm[];
+  uint64_t* full = (uint64_t*)rsm;
+  unsigned char* stage0 = rsm + 128;
+  unsigned short* srcidx = (unsigned short*)(stage0 + 2 * (size_t)st.stage_bytes);
+  unsigned short* bin = srcidx + R_T;
+  unsigned long long* delta = (unsigned long long*)(bin + R_T);
+  unsigned int* hist = (unsigned int*)(delta + 512);
+  unsigned int* toff = hist + 512;
+  __shared__ unsigned int warp_tot[16];
+  __shared__ unsigned int tile_total;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NB = LEVEL == 1 ? R_P1 : (1 << r.b2);
+  const int shift = LEVEL == 1 ? (64 - R_B1) : (64 - R_B1 - r.b2);
+  const unsigned int n_tiles = LEVEL == 1 ? (unsigned int)((p.n_rows + R_T - 1) / R_T) : r.tpre[R_P1];
+  unsigned long long* const cursor = LEVEL == 1 ? r.cur1 : r.cur2;
+  unsigned long long* const* out = LEVEL == 1 ? r.tup_a : r.tup_b;
+
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  for (int i = tid; i < 512; i += R2_NT) hist[i] = 0;
+  __syncthreads();
+  const uint64_t l2_policy = l2_evict_first_policy();
+
+  // LEVEL 2 walks the bucket-aligned tile list (tiles [tpre[b], tpre[b + 1]) hold the tuples [off1[b], off1[b + 1]))
+  int wb = 0;
+  unsigned int w_tile0 = 0, w_tile1 = 0;
+  unsigned long long w_off0 = 0, w_off1 = 0;
+  if (LEVEL == 2) {
+    w_tile1 = r.tpre[1];
+    w_off1 = r.off1[1];
+  }
+  auto describe = [&](unsigned int t) {
+    R2Tile d;
+    if (LEVEL == 1) {
+      d.base = (int64_t)t * R_T;
+      d.rows = (int)min((int64_t)R_T, p.n_rows - d.base);
+      d.b1 = 0;
+    } else {
+      while (t >= w_tile1) {  // next non-empty level-1 bucket
+        ++wb;
+        w_tile0 = w_tile1;
+        w_tile1 = r.tpre[wb + 1];
+        w_off0 = w_off1;
+        w_off1 = r.off1[wb + 1];
+      }
+      d.base = (int64_t)w_off0 + (int64_t)(t - w_tile0) * R_T;
+      d.rows = (int)min((int64_t)R_T, (int64_t)w_off1 - d.base);
+      d.b1 = wb;
+    }
+    return d;
+  };
+  // lanes 0..n_in-1 of warp 0 each copy one column / component of the tile into stage s.  LEVEL 2 sources are only
+  // 8 B aligned: the copy starts one tuple early when the tile starts at an odd tuple (the stage is read at + (base & 1))
+  auto issue = [&](const R2Tile& d, int s) {
+    if (warp != 0) return;
+    const int a = LEVEL == 2 ? (int)(d.base & 1) : 0;
+    uint32_t bytes = 0;
+    if (lane < (int)st.n_in) bytes = ((uint32_t)(d.rows + a) * st.bytes_per_row[lane] + 15u) & ~15u;
+    uint32_t total = bytes;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (lane == 0) mbar_expect_tx(&full[s], total);
+    __syncwarp();  // the expected byte count is registered before any copy can complete
+    if (lane < (int)st.n_in) {
+      const unsigned char* src = LEVEL == 1 ? p.cols[lane].ptr + (size_t)d.base * st.bytes_per_row[lane]
+                                            : (const unsigned char*)(r.tup_a[lane] + (d.base - a));
+      bulk_g2s(stage0 + (size_t)s * st.stage_bytes + st.off[lane], src, bytes, &full[s], l2_policy);
+    }
+  };
+
+  unsigned int t = blockIdx.x;
+  R2Tile cur, nxt;
+  cur.base = 0; cur.rows = 0; cur.b1 = 0;
+  nxt = cur;
+  if (t < n_tiles) {
+    nxt = describe(t);
+    issue(nxt, 0);
+  }
+  for (unsigned int it = 0; t < n_tiles; ++it, t += gridDim.x) {
+    const int s = (int)(it & 1);
+    cur = nxt;
+    if (t + gridDim.x < n_tiles) {  // stage s ^ 1 was released by the barrier that ended the previous tile
+      nxt = describe(t + gridDim.x);
+      issue(nxt, s ^ 1);
+    }
+    mbar_wait(&full[s], (it >> 1) & 1u);
+    const unsigned char* stage = stage0 + (size_t)s * st.stage_bytes;
+    const int rows = cur.rows;
+    const int a = LEVEL == 2 ? (int)(cur.base & 1) : 0;
+    // ---- phase 1 ------------------------------------------------------------------------------------------------------
+    int idx[R2_PT];
+    uint32_t pass = 0;
+#pragma unroll
+    for (int u = 0; u < R2_PT; ++u) {
+      idx[u] = u * R2_NT + tid + a;
+      if (u * R2_NT + tid < rows) pass |= 1u << u;
+    }
+    uint64_t code[R2_PT];
+    if (LEVEL == 1) {
+#pragma unroll 1
+      for (int k = 0; k < p.n_pred; ++k) {
+        int64_t x[R2_PT];
+        lds_rows(stage + st.off[p.pred[k].col], p.pred[k].wk, idx, x);
+        const uint64_t plo = (uint64_t)p.pred[k].lo, span = p.pred[k].span;
+#pragma unroll
+        for (int u = 0; u < R2_PT; ++u)
+          if (((uint64_t)x[u] - plo) > span) pass &= ~(1u << u);
+      }
+      r2_codes(p, st, stage, idx, code);
+    } else {
+      const unsigned long long* c0 = (const unsigned long long*)(stage + st.off[0]);
+#pragma unroll
+      for (int u = 0; u < R2_PT; ++u) code[u] = c0[idx[u]];
+    }
+    uint32_t pr[R2_PT];
+#pragma unroll
+    for (int u = 0; u < R2_PT; ++u) {
+      pr[u] = 0xffffffffu;
+      if ((pass >> u) & 1) {
+        const unsigned d = (unsigned)(fmix64(code[u]) >> shift) & (unsigned)(NB - 1);
+        pr[u] = (d << 16) | atomicAdd(&hist[d], 1u);
+      }
+    }
+    __syncthreads();
+    // ---- scan (threads 0..511: one bin each) + global reservations ---------------------------------------------------------
+    unsigned h0 = 0, incl = 0;
+    if (tid < 512) {
+      h0 = tid < NB ? hist[tid] : 0u;
+      hist[tid] = 0;  // for the next tile
+      incl = h0;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      if (lane == 31) warp_tot[warp] = incl;
+    }
+    __syncthreads();
+    unsigned long long reserved = 0;
+    unsigned my_toff = 0;
+    if (tid < 512) {
+      unsigned wbase = 0;
+#pragma unroll
+      for (int w = 0; w < 16; ++w)
+        if (w < warp) wbase += warp_tot[w];
+      my_toff = wbase + incl - h0;
+      toff[tid] = my_toff;
+      if (tid == 511) tile_total = wbase + incl;
+      if (h0) reserved = atomicAdd(&cursor[(LEVEL == 1 ? 0 : (cur.b1 << r.b2)) + tid], (unsigned long long)h0);
+    }
+    __syncthreads();
+    // ---- phase 2: source index + bin of every output position ------------------------------------------------------------
+#pragma unroll
+    for (int u = 0; u < R2_PT; ++u) {
+      if (pr[u] != 0xffffffffu) {
+        const unsigned d = pr[u] >> 16;
+        const unsigned pos = toff[d] + (pr[u] & 0xffffu);
+        srcidx[pos] = (unsigned short)(u * R2_NT + tid);
+        bin[pos] = (unsigned short)d;
+      }
+    }
+    if (tid < 512) delta[tid] = reserved - my_toff;  // destination of output position i of bin d: delta[d] + i
+    __syncthreads();
+    // ---- phase 3: write-out ----------------------------------------------------------------------------------------------
+    const unsigned total = tile_total;
+    unsigned long long dest[R2_PT];
+    int jdx[R2_PT];
+    unsigned dd[R2_PT];
+    uint32_t live = 0;
+#pragma unroll
+    for (int u = 0; u < R2_PT; ++u) {
+      const unsigned i = (unsigned)(u * R2_NT + tid);
+      jdx[u] = a;
+      dest[u] = 0;
+      dd[u] = 0;
+      if (i < total) {
+        live |= 1u << u;
+        dd[u] = bin[i];
+        jdx[u] = (int)srcidx[i] + a;
+        dest[u] = delta[dd[u]] + i;
+      }
+    }
+    if (LEVEL == 2) {
+#pragma unroll 1
+      for (int c = 0; c < r.n_comp; ++c) {
+        const unsigned long long* in = (const unsigned long long*)(stage + st.off[c]);
+        unsigned long long* o = out[c];
+#pragma unroll
+        for (int u = 0; u < R2_PT; ++u)
+          if ((live >> u) & 1) o[dest[u]] = in[jdx[u]];
+      }
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < r.n_comp; ++c) {
+        int64_t v[R2_PT];
+        if (c == 0) {
+          uint64_t cd[R2_PT];
+          r2_codes(p, st, stage, jdx, cd);
+#pragma unroll
+          for (int u = 0; u < R2_PT; ++u) v[u] = (int64_t)cd[u];
+        } else {
+          const RComp& C = r.comp[c - 1];
+          if (C.is_f64) {
+            lds_rows(stage + st.off[C.f[0].col], C.f[0].wk, jdx, v);
+          } else {
+#pragma unroll
+            for (int u = 0; u < R2_PT; ++u) v[u] = C.coef;
+#pragma unroll 1
+            for (int f = 0; f < C.n_factors; ++f) {
+              int64_t x[R2_PT];
+              lds_rows(stage + st.off[C.f[f].col], C.f[f].wk, jdx, x);
+              const int64_t fa = C.f[f].a, fb = C.f[f].b;
+#pragma unroll
+              for (int u = 0; u < R2_PT; ++u) v[u] *= (fa + fb * x[u]);
+            }
+          }
+        }
+        if (r.world > 1) {  // peer (or own) memory of the bucket's owner: P2P stores over NVLink
+#pragma unroll
+          for (int u = 0; u < R2_PT; ++u)
+            if ((live >> u) & 1) r.peer_a[dd[u] % (unsigned)r.world][c][dest[u]] = (unsigned long long)v[u];
+        } else {
+          unsigned long long* o = out[c];
+#pragma unroll
+          for (int u = 0; u < R2_PT; ++u)
+            if ((live >> u) & 1) o[dest[u]] = (unsigned long long)v[u];
+        }
+      }
+    }
+    __syncthreads();  // stage s, src[] and bin[] are free again
+  }
+}
+
 // level-2 histogram: every CTA owns a contiguous range of tiles so that the shared histogram is flushed only when
 // the level-1 bucket changes
 __global__ void __launch_bounds__(R_NT) k_radix_hist2(const __grid_constant__ RParams r) {
@@ -461,6 +781,41 @@ __global__ void __launch_bounds__(1024) k_radix_scan2(const unsigned int* __rest
   if (t == 1023) off[n] = part[1023];
 }
 
+struct RKeys {
+  int n_keys;
+  int shift[F_MAXK], bits[F_MAXK], width[F_MAXK];
+  long long base[F_MAXK];
+  void* out[F_MAXK];
+};
+// packed code -> key k (base_k + bits [shift_k, shift_k + bits_k) of the code), stored at row g of its column
+__device__ __forceinline__ void r_store_keys(const RKeys& rk, unsigned long long c, unsigned long long g) {
+  for (int k = 0; k < rk.n_keys; ++k) {
+    const unsigned long long field = rk.bits[k] >= 64 ? c : ((c >> rk.shift[k]) & ((1ull << rk.bits[k]) - 1ull));
+    const long long v = (long long)((unsigned long long)rk.base[k] + field);
+    switch (rk.width[k]) {
+      case 8: ((long long*)rk.out[k])[g] = v; break;
+      case 4: ((int*)rk.out[k])[g] = (int)v; break;
+      case 2: ((short*)rk.out[k])[g] = (short)v; break;
+      default: ((signed char*)rk.out[k])[g] = (signed char)v; break;
+    }
+  }
+}
+// accumulator k of output row o: into the accumulator array (finish_aggregate finalises it) or straight into the result
+// column(s) it feeds (SumAccumulator / Min / Max evaluate: the value; AvgAccumulator Float64: sum / n, avg.rs:62-75)
+__device__ __forceinline__ void r_emit(const RParams& r, int k, unsigned long long o, unsigned long long v, unsigned c) {
+  if (!r.direct) {
+    r.out_acc[k][o] = v;
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int mode = r.fin_mode[k][j];
+    if (mode == 1) ((unsigned long long*)r.fin_dst[k][j])[o] = v;
+    else if (mode == 2) ((ulonglong2*)r.fin_dst[k][j])[o] = make_ulonglong2(v, (long long)v < 0 ? ~0ull : 0ull);
+    else if (mode == 3) ((double*)r.fin_dst[k][j])[o] = __longlong_as_double((long long)v) / (double)c;
+  }
+}
+
 // Final pass: one CTA per final bucket.  No accumulator atomics: the bucket's rows are counting-sorted by GROUP in
 // shared memory and every group is then reduced sequentially in registers by one thread.
 //   A  stream the packed codes: claim / find the group's slot in an open-addressing key table (64-bit CAS only for
@@ -470,7 +825,7 @@ __global__ void __launch_bounds__(1024) k_radix_scan2(const unsigned int* __rest
 //   R  thread-per-slot: reduce the slot's contiguous staged rows, write the group straight to the output arrays
 // dynamic shared memory: keys[C1] u64 | stage[n_comp - 1][row_cap] u64 | cnt[C1] u32 | start[C1] u32 | pk[row_cap] u32 |
 //                        occ[C1] u16
-__global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant__ RParams r) {
+__global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant__ RParams r, const __grid_constant__ RKeys rk) {
   extern __shared__ __align__(16) unsigned char rsm[];
   const int cap = r.cap, C1 = cap + 1, RC = r.row_cap, NV = r.n_comp - 1;
   unsigned long long* keys = (unsigned long long*)rsm;
@@ -701,8 +1056,10 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
       const unsigned c = cnt[sl];
       const unsigned first = start[sl];
       const unsigned long long o = ob + g;
-      r.out_code[o] = sl == cap ? F_EMPTY : keys[sl];
-      r.out_cnt[o] = c;
+      r_store_keys(rk, sl == cap ? F_EMPTY : keys[sl], o);
+      if (!r.direct) r.out_cnt[o] = c;
+      else
+        for (int j = 0; j < r.n_cnt_dst; ++j) r.cnt_dst[j][o] = c;
 #pragma unroll 1
       for (int cc = 0; cc < NV; ++cc) {
         const unsigned long long* src = stage + (size_t)cc * RC + first;
@@ -712,12 +1069,12 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
           double fs = __longlong_as_double(v0);
 #pragma unroll 4
           for (unsigned i = 1; i < c; ++i) fs += __longlong_as_double((long long)src[i]);
-          r.out_acc[r.acc_at[cc][3]][o] = (unsigned long long)__double_as_longlong(fs);
+          r_emit(r, r.acc_at[cc][3], o, (unsigned long long)__double_as_longlong(fs), c);
         } else if (m == 1) {
           long long sm = v0;
 #pragma unroll 4
           for (unsigned i = 1; i < c; ++i) sm += (long long)src[i];
-          r.out_acc[r.acc_at[cc][0]][o] = (unsigned long long)sm;
+          r_emit(r, r.acc_at[cc][0], o, (unsigned long long)sm, c);
         } else {
           long long sm = v0, mn = v0, mx = v0;
 #pragma unroll 4
@@ -727,13 +1084,13 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
             mn = min(mn, v);
             mx = max(mx, v);
           }
-          if (m & 1) r.out_acc[r.acc_at[cc][0]][o] = (unsigned long long)sm;
-          if (m & 2) r.out_acc[r.acc_at[cc][1]][o] = (unsigned long long)mn;
-          if (m & 4) r.out_acc[r.acc_at[cc][2]][o] = (unsigned long long)mx;
+          if (m & 1) r_emit(r, r.acc_at[cc][0], o, (unsigned long long)sm, c);
+          if (m & 2) r_emit(r, r.acc_at[cc][1], o, (unsigned long long)mn, c);
+          if (m & 4) r_emit(r, r.acc_at[cc][2], o, (unsigned long long)mx, c);
           if (m & 8) {  // (an f64 operand never carries integer kinds; kept for completeness)
             double fs = __longlong_as_double(v0);
             for (unsigned i = 1; i < c; ++i) fs += __longlong_as_double((long long)src[i]);
-            r.out_acc[r.acc_at[cc][3]][o] = (unsigned long long)__double_as_longlong(fs);
+            r_emit(r, r.acc_at[cc][3], o, (unsigned long long)__double_as_longlong(fs), c);
           }
         }
       }
@@ -742,29 +1099,12 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
   }
 }
 
-struct RKeys {
-  int n_keys;
-  int shift[F_MAXK], bits[F_MAXK], width[F_MAXK];
-  long long base[F_MAXK];
-  void* out[F_MAXK];
-};
-// packed code -> key columns (key k = base_k + bits [shift_k, shift_k + bits_k) of the code)
-__global__ void __launch_bounds__(256) k_radix_keys(const unsigned long long* __restrict__ code, int64_t n, const RKeys rk) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) {
-    const unsigned long long c = code[g];
-    for (int k = 0; k < rk.n_keys; ++k) {
-      const unsigned long long field = rk.bits[k] >= 64 ? c : ((c >> rk.shift[k]) & ((1ull << rk.bits[k]) - 1ull));
-      const long long v = (long long)((unsigned long long)rk.base[k] + field);
-      switch (rk.width[k]) {
-        case 8: ((long long*)rk.out[k])[g] = v; break;
-        case 4: ((int*)rk.out[k])[g] = (int)v; break;
-        case 2: ((short*)rk.out[k])[g] = (short)v; break;
-        default: ((signed char*)rk.out[k])[g] = (signed char)v; break;
-      }
-    }
-  }
-}
+// (A second form of the final pass -- shared memory holding only the group table, every row accumulating straight into
+// its slot -- was built and measured in round 2 and removed: 64-bit shared-memory atomics are CAS loops in SASS
+// (ATOMS.CAST.SPIN.64), one per accumulator and row made it 44 ms per 1 B rows against 17 ms for the sorting form; with a
+// per-slot micro-lock in the row count's top bit (one native ATOMS.OR, plain updates, releasing store) 1024 threads
+// working on ~1500 groups collide on half of their rows and it still took 38 ms.  Native 32-bit atomics, which the
+// sorting form uses for its ranks, cost about as much as a random LDS: scripts/ubench/rank_ubench.cu.)
 
 // HyperLogLog estimate from the 4096 registers (host side)
 static double hll_estimate(const unsigned int* reg) {
@@ -778,5 +1118,5 @@ static double hll_estimate(const unsigned int* reg) {
   const double alpha = 0.7213 / (1.0 + 1.079 / m);
   double e = alpha * m * m / sum;
   if (e <= 2.5 * m && zeros > 0) e = m * log(m / (double)zeros);
-  return e;
+  return e * R_HLL_SAMPLE;
 }
