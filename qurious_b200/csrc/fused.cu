@@ -1124,8 +1124,8 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
 // ------------------------------------------------------------------------------------------------
 namespace {
 // small device state block: hll[4096] u32 | hist1[256] u32 | tpre[257] u32 (+pad) | off1[257] u64 | cur1[256] u64 | n_out u64 | overflow
-constexpr size_t RO_HLL = 0, RO_HIST1 = RO_HLL + R_HLL_M * 4, RO_TPRE = RO_HIST1 + R_P1 * 4, RO_OFF1 = RO_TPRE + 260 * 4,
-                 RO_CUR1 = RO_OFF1 + 257 * 8, RO_NOUT = RO_CUR1 + 256 * 8, RO_OVF = RO_NOUT + 8, RO_BYTES = RO_OVF + 8;
+constexpr size_t RO_HLL = 0, RO_HIST1 = RO_HLL + R_HLL_M * 4, RO_TPRE = RO_HIST1 + R_P1 * 4, RO_OFF1 = RO_TPRE + (R_P1 + 4) * 4,
+                 RO_CUR1 = RO_OFF1 + (R_P1 + 1) * 8, RO_NOUT = RO_CUR1 + R_P1 * 8, RO_OVF = RO_NOUT + 8, RO_BYTES = RO_OVF + 8;
 constexpr size_t R_SKETCH_BYTES = RO_TPRE;  // hll + hist1: what the ranks exchange
 }  // namespace
 
@@ -1161,6 +1161,10 @@ static bool radix_choose(const RParams& R, double groups, int64_t n_tuples, int 
     if ((double)row_cap >= r_b * 1.15 + 6.0 * sqrt(r_b) + 64.0) break;
   }
   if (b2 > R_MAXB2) return false;
+  if (const char* fb = getenv("QGPU_RADIX_B2")) {  // experiments: a larger level-2 fan-out than the sizes ask for
+    const int want = std::min(R_MAXB2, atoi(fb));
+    if (want > b2) b2 = want;
+  }
   if (const char* tc = getenv("QGPU_RADIX_TEST_CAP")) {  // tests: provoke the overflow -> FM_HASH fallback
     cap = std::max(64, std::min(4096, atoi(tc)));
     b2 = 1;
@@ -1190,6 +1194,14 @@ static bool radix_tma_stage(int level, const FParams& P, const RParams& R, RStag
       st->bytes_per_row[c] = P.cols[c].width;
       off += (uint32_t)(((size_t)R_T * P.cols[c].width + 127) & ~(size_t)127);
     }
+  } else if (R.pair12) {  // codes | (value 1, value 2) pairs
+    st->n_in = 2;
+    st->off[0] = 0;
+    st->bytes_per_row[0] = 8;
+    off = (uint32_t)(((size_t)(R_T + 2) * 8 + 127) & ~(size_t)127);
+    st->off[1] = off;
+    st->bytes_per_row[1] = 16;
+    off += (uint32_t)(((size_t)R_T * 16 + 127) & ~(size_t)127);
   } else {
     st->n_in = (uint32_t)R.n_comp;
     for (int c = 0; c < R.n_comp; ++c) {
@@ -1200,6 +1212,16 @@ static bool radix_tma_stage(int level, const FParams& P, const RParams& R, RStag
   }
   st->stage_bytes = off;
   return radix_tma_smem(*st) + 256 <= (size_t)F_SMEM_MAX;
+}
+
+// two operand values and the TMA scatter on both levels: the values travel as 16-byte pairs (RParams::pair12)
+static bool radix_pair12(const FParams& P, const RParams& R) {
+  const char* e = getenv("QGPU_RADIX_PAIR");
+  if ((e && e[0] == '0') || R.n_comp != 3) return false;
+  RParams t = R;
+  t.pair12 = 1;
+  RStage st;
+  return radix_tma_stage(1, P, t, &st) && radix_tma_stage(2, P, t, &st);
 }
 
 static void radix_launch_scatter1(Ctx* ctx, const FParams& P, const RParams& R) {
@@ -1341,8 +1363,21 @@ static bool radix_tail(PlanNode& agg, const View& v, FusedPlan& fp, const FParam
   }
   const int ag_grid = (int)std::min<int64_t>(n_buckets, (int64_t)ctx->sm_count);
   const size_t ag_smem = (size_t)(cap + 1) * 18 + (size_t)row_cap * row_bytes + 64;
-  CUDA_CHECK(cudaFuncSetAttribute(k_radix_agg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ag_smem));
-  LAUNCH(ctx, k_radix_agg, ag_grid, R_AGG_NT, ag_smem, R2, rk);
+#define QGPU_RADIX_AGG(NV)                                                                                             \
+  case NV:                                                                                                             \
+    CUDA_CHECK(cudaFuncSetAttribute(k_radix_agg<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ag_smem));      \
+    LAUNCH(ctx, k_radix_agg<NV>, ag_grid, R_AGG_NT, ag_smem, R2, rk);                                                  \
+    break;
+  switch (R.n_comp - 1) {  // operand values per tuple: unrolled in the kernel
+    QGPU_RADIX_AGG(0)
+    QGPU_RADIX_AGG(1)
+    QGPU_RADIX_AGG(2)
+    QGPU_RADIX_AGG(3)
+    QGPU_RADIX_AGG(4)
+    QGPU_RADIX_AGG(5)
+    default: throw_internal("radix aggregate: too many operand values");
+  }
+#undef QGPU_RADIX_AGG
   unsigned long long fin[2];
   ctx->d2h_sync(fin, (char*)st->ptr + RO_NOUT, 16);
   ctx->trace("radix: level 2 + aggregate");
@@ -1366,7 +1401,7 @@ static bool radix_tail(PlanNode& agg, const View& v, FusedPlan& fp, const FParam
       accs.cnt.push_back(out_cnt);
     }
   }
-  agg.strategy = "fused_scan_agg[radix-partitioned: 256 x " + std::to_string(1 << b2) + " buckets, smem table " + std::to_string(cap) +
+  agg.strategy = "fused_scan_agg[radix-partitioned: " + std::to_string(R_P1) + " x " + std::to_string(1 << b2) + " buckets, smem table " + std::to_string(cap) +
                  " slots / " + std::to_string(row_cap) + " rows, " + std::to_string(R.n_comp) + " x 8 B tuples, " +
                  std::to_string(P.n_cols) + " cols, " + std::to_string(P.n_pred) + " range preds, " + std::to_string(P.n_accs) +
                  " accs, est " + std::to_string((int64_t)est) + " groups" + (direct ? ", result columns written by the final pass]" : "]");
@@ -1425,6 +1460,7 @@ static bool run_radix(PlanNode& agg, const View& v, FusedPlan& fp, View* out) {
     return false;
   }
   if (!radix_choose(R, groups, n_tuples, R_P1, &R.b2, &R.cap, &R.row_cap)) return false;
+  R.pair12 = radix_pair12(P, R) ? 1 : 0;  // array 1 then spans the slab's second and third part
   const size_t comp_bytes = (((size_t)n_tuples * 8 + 64) + 255) & ~(size_t)255;
   DBufP slab_a = ctx->alloc(comp_bytes * (size_t)R.n_comp);  // one slab (see radix_tail)
   for (int c = 0; c < R.n_comp; ++c) R.tup_a[c] = (unsigned long long*)((char*)slab_a->ptr + comp_bytes * (size_t)c);
@@ -2429,6 +2465,7 @@ struct RadixExchange {
   unsigned int n_tiles2 = 0;
   void* recv[R_MAXCOMP] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t recv_cap = 0;  // bytes per component
+  int recv_pair = 0;    // buffer 1 sized for 16-byte pairs (RParams::pair12)
   std::vector<std::pair<std::string, void*>> opened;
   ~RadixExchange() {
     for (auto& o : opened) cudaIpcCloseMemHandle(o.second);
@@ -2559,15 +2596,17 @@ int radix_exchange_prepare(PlanNode& root, const void* gathered_host, int world,
   ctx->h2d(sp + RO_CUR1, cur1.data(), R_P1 * 8);
   ctx->sync();
   // ---- receive buffers: plain cudaMalloc (exportable through CUDA IPC), kept across executions ----------------------------
+  R.pair12 = radix_pair12(ex->P, R) ? 1 : 0;  // the same on every rank (plan shape + environment); buffer 1 then holds 16 B pairs
   const size_t need = (size_t)owned[rank] * 8 + 256;
-  if (need > ex->recv_cap) {
+  if (need > ex->recv_cap || ex->recv_pair != R.pair12) {
+    ex->recv_pair = R.pair12;
     ctx->sync();
     for (int c = 0; c < R_MAXCOMP; ++c) {
       if (ex->recv[c]) CUDA_CHECK(cudaFree(ex->recv[c]));
       ex->recv[c] = nullptr;
     }
     ex->recv_cap = need + need / 8 + ((size_t)1 << 20);
-    for (int c = 0; c < R.n_comp; ++c) CUDA_CHECK(cudaMalloc(&ex->recv[c], ex->recv_cap));
+    for (int c = 0; c < R.n_comp; ++c) CUDA_CHECK(cudaMalloc(&ex->recv[c], ex->recv_cap * ((R.pair12 && c == 1) ? 2 : 1)));
   }
   ExHandle* hs = (ExHandle*)handles_out;
   for (int c = 0; c < R.n_comp; ++c) {

@@ -30,7 +30,7 @@ constexpr int R_SNT = 512;                // threads per CTA of the scatter kern
 constexpr int R_SPT = R_SUB * F_NT / R_SNT;  // sub-tiles per thread
 static_assert(R_SNT == 512 && R_SPT == 2, "scatter: one histogram bin per thread, two sub-tiles per thread");
 constexpr int R_T = F_T * R_SUB;          // tuples per tile
-constexpr int R_B1 = 8;                   // level-1 digit: top 8 hash bits
+constexpr int R_B1 = 8;                   // level-1 digit: top 8 hash bits (9 + 8 instead of 8 + 9 was measured: level 1 +4.5 ms, level 2 -3.1 ms per 1 B rows)
 constexpr int R_P1 = 1 << R_B1;
 constexpr int R_MAXB2 = 9;
 constexpr int R_MAXCOMP = 6;              // tuple components (code + operand values) that fit the sort tile
@@ -76,6 +76,11 @@ struct RParams {
   // final pass writing the result columns itself (radix_tail: every aggregate is a plain copy / sign extension / f64 mean
   // of an accumulator): accumulator k -> up to two result columns, COUNT columns, key columns decoded from the code
   int32_t direct, n_cnt_dst;
+  // tuples of exactly two operand values (TMA scatter on both levels): the two values of a tuple travel side by side as ONE
+  // 16-byte element of array 1 (array 2 is unused) -- a run of n tuples is one n * 16 B piece instead of two n * 8 B pieces:
+  // fewer, fuller lines per store instruction (the scatter is bound by its L1 -> L2 write requests), one 16-byte load per
+  // row in the final pass
+  int32_t pair12, pad_pair;
   int32_t fin_mode[F_MAXA][2];   // 0 = none, 1 = 8-byte copy, 2 = 16-byte sign extension (Decimal128), 3 = f64 sum / count
   void* fin_dst[F_MAXA][2];
   unsigned long long* cnt_dst[4];
@@ -535,11 +540,12 @@ __global__ void __launch_bounds__(R2_NT, 1) k_radix_scatter_tma(const __grid_con
     }
     return d;
   };
-  // lanes 0..n_in-1 of warp 0 each copy one column / component of the tile into stage s.  LEVEL 2 sources are only
-  // 8 B aligned: the copy starts one tuple early when the tile starts at an odd tuple (the stage is read at + (base & 1))
+  // lanes 0..n_in-1 of warp 0 each copy one column / tuple array of the tile into stage s.  LEVEL 2 sources of 8-byte
+  // elements are only 8 B aligned: the copy starts one tuple early when the tile starts at an odd tuple (the stage is read
+  // at + (base & 1)); the 16-byte pair array needs no such shift
   auto issue = [&](const R2Tile& d, int s) {
     if (warp != 0) return;
-    const int a = LEVEL == 2 ? (int)(d.base & 1) : 0;
+    const int a = (LEVEL == 2 && lane < (int)st.n_in && st.bytes_per_row[lane] == 8) ? (int)(d.base & 1) : 0;
     uint32_t bytes = 0;
     if (lane < (int)st.n_in) bytes = ((uint32_t)(d.rows + a) * st.bytes_per_row[lane] + 15u) & ~15u;
     uint32_t total = bytes;
@@ -549,7 +555,7 @@ __global__ void __launch_bounds__(R2_NT, 1) k_radix_scatter_tma(const __grid_con
     __syncwarp();  // the expected byte count is registered before any copy can complete
     if (lane < (int)st.n_in) {
       const unsigned char* src = LEVEL == 1 ? p.cols[lane].ptr + (size_t)d.base * st.bytes_per_row[lane]
-                                            : (const unsigned char*)(r.tup_a[lane] + (d.base - a));
+                                            : (const unsigned char*)r.tup_a[lane] + (size_t)(d.base - a) * st.bytes_per_row[lane];
       bulk_g2s(stage0 + (size_t)s * st.stage_bytes + st.off[lane], src, bytes, &full[s], l2_policy);
     }
   };
@@ -666,7 +672,18 @@ __global__ void __launch_bounds__(R2_NT, 1) k_radix_scatter_tma(const __grid_con
         dest[u] = delta[dd[u]] + i;
       }
     }
-    if (LEVEL == 2) {
+    if (LEVEL == 2 && r.pair12) {
+      const unsigned long long* in0 = (const unsigned long long*)(stage + st.off[0]);
+      const ulonglong2* in1 = (const ulonglong2*)(stage + st.off[1]);
+      unsigned long long* o0 = out[0];
+      ulonglong2* o1 = (ulonglong2*)out[1];
+#pragma unroll
+      for (int u = 0; u < R2_PT; ++u)
+        if ((live >> u) & 1) o0[dest[u]] = in0[jdx[u]];
+#pragma unroll
+      for (int u = 0; u < R2_PT; ++u)
+        if ((live >> u) & 1) o1[dest[u]] = in1[jdx[u] - a];
+    } else if (LEVEL == 2) {
 #pragma unroll 1
       for (int c = 0; c < r.n_comp; ++c) {
         const unsigned long long* in = (const unsigned long long*)(stage + st.off[c]);
@@ -676,6 +693,9 @@ __global__ void __launch_bounds__(R2_NT, 1) k_radix_scatter_tma(const __grid_con
           if ((live >> u) & 1) o[dest[u]] = in[jdx[u]];
       }
     } else {
+      int64_t held[R2_PT];  // pair12: operand value 1, stored together with value 2
+#pragma unroll
+      for (int u = 0; u < R2_PT; ++u) held[u] = 0;
 #pragma unroll 1
       for (int c = 0; c < r.n_comp; ++c) {
         int64_t v[R2_PT];
@@ -700,6 +720,25 @@ __global__ void __launch_bounds__(R2_NT, 1) k_radix_scatter_tma(const __grid_con
               for (int u = 0; u < R2_PT; ++u) v[u] *= (fa + fb * x[u]);
             }
           }
+        }
+        if (r.pair12 && c == 1) {
+#pragma unroll
+          for (int u = 0; u < R2_PT; ++u) held[u] = v[u];
+          continue;
+        }
+        if (r.pair12 && c == 2) {
+          if (r.world > 1) {
+#pragma unroll
+            for (int u = 0; u < R2_PT; ++u)
+              if ((live >> u) & 1)
+                ((ulonglong2*)r.peer_a[dd[u] % (unsigned)r.world][1])[dest[u]] = make_ulonglong2((unsigned long long)held[u], (unsigned long long)v[u]);
+          } else {
+            ulonglong2* o1 = (ulonglong2*)out[1];
+#pragma unroll
+            for (int u = 0; u < R2_PT; ++u)
+              if ((live >> u) & 1) o1[dest[u]] = make_ulonglong2((unsigned long long)held[u], (unsigned long long)v[u]);
+          }
+          continue;
         }
         if (r.world > 1) {  // peer (or own) memory of the bucket's owner: P2P stores over NVLink
 #pragma unroll
@@ -821,16 +860,18 @@ __device__ __forceinline__ void r_emit(const RParams& r, int k, unsigned long lo
 //   A  stream the packed codes: claim / find the group's slot in an open-addressing key table (64-bit CAS only for
 //      the first row of a group), rank = native 32-bit shared atomicAdd on the slot's row count; remember (slot, rank)
 //   S  block scan of the slot row counts -> first staged row of every slot; occupied slots -> output positions
-//   B  stream the operand values (coalesced) into the staging area at start[slot] + rank
-//   R  thread-per-slot: reduce the slot's contiguous staged rows, write the group straight to the output arrays
-// dynamic shared memory: keys[C1] u64 | stage[n_comp - 1][row_cap] u64 | cnt[C1] u32 | start[C1] u32 | pk[row_cap] u32 |
+//   B  stream the operand values (coalesced, all operands of a row together) into the staging area at start[slot] + rank
+//   R  thread-per-slot: reduce the slot's contiguous staged rows (every operand in the same walk), write the group straight
+//      to the output arrays
+// dynamic shared memory: stage[row_cap][n_comp - 1] u64 | keys[C1] u64 | cnt[C1] u32 | start[C1] u32 | pk[row_cap] u32 |
 //                        occ[C1] u16
+template <int NV>
 __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant__ RParams r, const __grid_constant__ RKeys rk) {
   extern __shared__ __align__(16) unsigned char rsm[];
-  const int cap = r.cap, C1 = cap + 1, RC = r.row_cap, NV = r.n_comp - 1;
-  unsigned long long* keys = (unsigned long long*)rsm;
-  unsigned long long* stage = keys + C1;
-  unsigned int* cnt = (unsigned int*)(stage + (size_t)NV * RC);
+  const int cap = r.cap, C1 = cap + 1, RC = r.row_cap;
+  unsigned long long* stage = (unsigned long long*)rsm;  // 16 B aligned: staged row = NV consecutive words
+  unsigned long long* keys = stage + (size_t)NV * RC;
+  unsigned int* cnt = (unsigned int*)(keys + C1);
   unsigned int* start = cnt + C1;
   unsigned int* pk = start + C1;
   unsigned short* occ = (unsigned short*)(pk + RC);
@@ -853,9 +894,10 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
     }
     const int n = (int)n64;
     // the next bucket of this CTA: pull its tuples towards L2 while this one is processed
-    if (b + (int)gridDim.x < n_buckets && tid < r.n_comp && !(r.nopf & 4)) {
-      const int64_t nlo = (int64_t)r.off2[b + gridDim.x];
-      const int64_t nn = min((int64_t)r.off2[b + gridDim.x + 1] - nlo, (int64_t)RC);
+    if (b + (int)gridDim.x < n_buckets && tid < (r.pair12 ? 2 : r.n_comp) && !(r.nopf & 4)) {
+      const int64_t words = (r.pair12 && tid == 1) ? 2 : 1;  // 8-byte words per element of tuple array `tid`
+      const int64_t nlo = (int64_t)r.off2[b + gridDim.x] * words;
+      const int64_t nn = min((int64_t)r.off2[b + gridDim.x + 1] * words - nlo, (int64_t)RC * words);
       const uintptr_t a0 = ((uintptr_t)(r.tup_b[tid] + nlo) + 15) & ~(uintptr_t)15;   // 16 B aligned address and size
       const uintptr_t a1 = (uintptr_t)(r.tup_b[tid] + nlo + nn) & ~(uintptr_t)15;
       if (a1 > a0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((uint32_t)(a1 - a0)) : "memory");
@@ -1026,73 +1068,95 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
       continue;
     }
     __syncthreads();
-    // ---- B: operand values into the staging area, grouped by slot --------------------------------------------------------
-#pragma unroll 1
-    for (int c = 0; c < NV; ++c) {
-      const unsigned long long* src = r.tup_b[c + 1] + lo;
-      unsigned long long* dst = stage + (size_t)c * RC;
-      for (int i0 = 0; i0 < n; i0 += R_U * R_AGG_NT) {
-        unsigned long long v8[R_U];
+    // ---- B: operand values into the staging area, grouped by slot; a staged row holds its NV operands side by side ---------
+    if (NV > 0) {
+      constexpr int UB = NV >= 3 ? 2 : 4;
+      for (int i0 = 0; i0 < n; i0 += UB * R_AGG_NT) {
+        unsigned long long v8[NV > 0 ? NV : 1][UB];
+        if (NV == 2 && r.pair12) {
 #pragma unroll
-        for (int u = 0; u < R_U; ++u) {
-          const int i = i0 + u * R_AGG_NT + tid;
-          v8[u] = i < n ? __ldcs(&src[i]) : 0ull;
+          for (int u = 0; u < UB; ++u) {
+            const int i = i0 + u * R_AGG_NT + tid;
+            const ulonglong2 q = i < n ? __ldcs((const ulonglong2*)r.tup_b[1] + lo + i) : make_ulonglong2(0ull, 0ull);
+            v8[0][u] = q.x;
+            v8[NV > 1 ? 1 : 0][u] = q.y;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < NV; ++c)
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+              const int i = i0 + u * R_AGG_NT + tid;
+              v8[c][u] = i < n ? __ldcs(&r.tup_b[c + 1][lo + i]) : 0ull;
+            }
         }
 #pragma unroll
-        for (int u = 0; u < R_U; ++u) {
+        for (int u = 0; u < UB; ++u) {
           const int i = i0 + u * R_AGG_NT + tid;
           if (i >= n) continue;
           const unsigned p = pk[i];
-          dst[start[p & 8191u] + (p >> 13)] = v8[u];
+          unsigned long long* dst = stage + (size_t)(start[p & 8191u] + (p >> 13)) * NV;
+          if (NV == 2) {
+            *(ulonglong2*)dst = make_ulonglong2(v8[0][u], v8[NV > 1 ? 1 : 0][u]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < NV; ++c) dst[c] = v8[c][u];
+          }
         }
       }
     }
     __syncthreads();
-    // ---- R: one thread per GROUP (dense over the lanes) reduces its contiguous staged rows in registers, operand by
-    //         operand (SUM / MIN / MAX of the same operand share one pass), and writes the group; consecutive threads
-    //         write consecutive output rows
+    // ---- R: one thread per GROUP (dense over the lanes) reduces its contiguous staged rows in registers -- all operands in
+    //         one walk, SUM / MIN / MAX of the same operand sharing it -- and writes the group; consecutive threads write
+    //         consecutive output rows
+    int msk[NV > 0 ? NV : 1];
+#pragma unroll
+    for (int cc = 0; cc < NV; ++cc) msk[cc] = r.cmask[cc];
     for (unsigned g = tid; g < n_occ; g += R_AGG_NT) {
       const int sl = occ[g];
       const unsigned c = cnt[sl];
-      const unsigned first = start[sl];
+      const unsigned long long* src = stage + (size_t)start[sl] * NV;
       const unsigned long long o = ob + g;
       r_store_keys(rk, sl == cap ? F_EMPTY : keys[sl], o);
       if (!r.direct) r.out_cnt[o] = c;
       else
         for (int j = 0; j < r.n_cnt_dst; ++j) r.cnt_dst[j][o] = c;
-#pragma unroll 1
+      long long sm[NV > 0 ? NV : 1], mn[NV > 0 ? NV : 1], mx[NV > 0 ? NV : 1];
+      double fs[NV > 0 ? NV : 1];
+#pragma unroll
       for (int cc = 0; cc < NV; ++cc) {
-        const unsigned long long* src = stage + (size_t)cc * RC + first;
-        const int m = r.cmask[cc];
-        const long long v0 = (long long)src[0];
-        if (m == 8) {
-          double fs = __longlong_as_double(v0);
-#pragma unroll 4
-          for (unsigned i = 1; i < c; ++i) fs += __longlong_as_double((long long)src[i]);
-          r_emit(r, r.acc_at[cc][3], o, (unsigned long long)__double_as_longlong(fs), c);
-        } else if (m == 1) {
-          long long sm = v0;
-#pragma unroll 4
-          for (unsigned i = 1; i < c; ++i) sm += (long long)src[i];
-          r_emit(r, r.acc_at[cc][0], o, (unsigned long long)sm, c);
+        const long long v0 = (long long)src[cc];
+        sm[cc] = mn[cc] = mx[cc] = v0;
+        fs[cc] = __longlong_as_double(v0);
+      }
+      for (unsigned i = 1; i < c; ++i) {
+        long long v[NV > 0 ? NV : 1];
+        if (NV == 2) {
+          const ulonglong2 q = *(const ulonglong2*)(src + (size_t)i * NV);
+          v[0] = (long long)q.x;
+          v[NV > 1 ? 1 : 0] = (long long)q.y;
         } else {
-          long long sm = v0, mn = v0, mx = v0;
-#pragma unroll 4
-          for (unsigned i = 1; i < c; ++i) {
-            const long long v = (long long)src[i];
-            sm += v;
-            mn = min(mn, v);
-            mx = max(mx, v);
-          }
-          if (m & 1) r_emit(r, r.acc_at[cc][0], o, (unsigned long long)sm, c);
-          if (m & 2) r_emit(r, r.acc_at[cc][1], o, (unsigned long long)mn, c);
-          if (m & 4) r_emit(r, r.acc_at[cc][2], o, (unsigned long long)mx, c);
-          if (m & 8) {  // (an f64 operand never carries integer kinds; kept for completeness)
-            double fs = __longlong_as_double(v0);
-            for (unsigned i = 1; i < c; ++i) fs += __longlong_as_double((long long)src[i]);
-            r_emit(r, r.acc_at[cc][3], o, (unsigned long long)__double_as_longlong(fs), c);
+#pragma unroll
+          for (int cc = 0; cc < NV; ++cc) v[cc] = (long long)src[(size_t)i * NV + cc];
+        }
+#pragma unroll
+        for (int cc = 0; cc < NV; ++cc) {
+          if (msk[cc] & 8) {
+            fs[cc] += __longlong_as_double(v[cc]);
+          } else {
+            sm[cc] += v[cc];
+            mn[cc] = min(mn[cc], v[cc]);
+            mx[cc] = max(mx[cc], v[cc]);
           }
         }
+      }
+#pragma unroll
+      for (int cc = 0; cc < NV; ++cc) {
+        const int m = msk[cc];
+        if (m & 1) r_emit(r, r.acc_at[cc][0], o, (unsigned long long)sm[cc], c);
+        if (m & 2) r_emit(r, r.acc_at[cc][1], o, (unsigned long long)mn[cc], c);
+        if (m & 4) r_emit(r, r.acc_at[cc][2], o, (unsigned long long)mx[cc], c);
+        if (m & 8) r_emit(r, r.acc_at[cc][3], o, (unsigned long long)__double_as_longlong(fs[cc]), c);
       }
     }
     __syncthreads();
