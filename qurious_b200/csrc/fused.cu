@@ -964,7 +964,10 @@ static bool analyze_fused(PlanNode& agg, const std::vector<const ExprNode*>& pre
     a.unit = (a.kind != FK_SUMF && !a.chain && a.coef == 1 && a.n_factors > 0 && a.f[0].plain) ? 1 : 0;
   }
   for (int c = 0; c + 1 < fp.R.n_comp; ++c)
-    for (int f = 0; f < fp.R.comp[c].n_factors; ++f) resolve(fp.R.comp[c].f[f].col, &fp.R.comp[c].f[f].off, &fp.R.comp[c].f[f].wk);
+    for (int f = 0; f < fp.R.comp[c].n_factors; ++f) {
+      resolve(fp.R.comp[c].f[f].col, &fp.R.comp[c].f[f].off, &fp.R.comp[c].f[f].wk);
+      fp.R.comp[c].f[f].plain = (fp.R.comp[c].f[f].a == 0 && fp.R.comp[c].f[f].b == 1) ? 1 : 0;
+    }
   P.stage_bytes = stage_bytes;
   const int NA2 = P.n_accs + 2;
   const int grid_max = ctx->sm_count;
@@ -1190,6 +1193,7 @@ static bool radix_tma_stage(int level, const FParams& P, const RParams& R, RStag
   if (level == 1) {
     st->n_in = (uint32_t)P.n_cols;
     for (int c = 0; c < P.n_cols; ++c) {
+      st->col_of[c] = (uint32_t)c;
       st->off[c] = off;
       st->bytes_per_row[c] = P.cols[c].width;
       off += (uint32_t)(((size_t)R_T * P.cols[c].width + 127) & ~(size_t)127);
@@ -1211,7 +1215,40 @@ static bool radix_tma_stage(int level, const FParams& P, const RParams& R, RStag
     }
   }
   st->stage_bytes = off;
+  st->n_stages = 2;
   return radix_tma_smem(*st) + 256 <= (size_t)F_SMEM_MAX;
+}
+
+// level-1 histogram + sketch: the TMA-pipelined kernel whenever two stages of the key / predicate columns fit
+static void radix_launch_hist1(Ctx* ctx, const FParams& P, const RParams& R) {
+  RStage st;
+  memset(&st, 0, sizeof(st));
+  bool used[F_MAXC] = {false};
+  for (int k = 0; k < P.n_pred; ++k) used[P.pred[k].col] = true;
+  for (int k = 0; k < P.n_keys; ++k) used[P.keys[k].col] = true;
+  uint32_t off = 0;
+  for (int c = 0; c < P.n_cols; ++c) {
+    if (!used[c]) continue;
+    st.col_of[st.n_in++] = (uint32_t)c;
+    st.off[c] = off;
+    st.bytes_per_row[c] = P.cols[c].width;
+    off += (uint32_t)(((size_t)R_T * P.cols[c].width + 127) & ~(size_t)127);
+  }
+  st.stage_bytes = off;
+  const size_t fixed = 128 + (size_t)R_P1 * 4 + (size_t)R_HLL_M * 4;
+  const size_t budget = ((size_t)F_SMEM_MAX - 2048) / 2;  // two CTAs per SM
+  const char* e = getenv("QGPU_RADIX_SCATTER");
+  if (st.n_in > 0 && off > 0 && fixed + 2 * (size_t)off <= budget && !(e && strcmp(e, "regs") == 0)) {
+    st.n_stages = (uint32_t)std::min<size_t>(4, (budget - fixed) / off);
+    const size_t smem = fixed + (size_t)st.n_stages * off;
+    const int64_t tiles = (P.n_rows + R_T - 1) / R_T;
+    CUDA_CHECK(cudaFuncSetAttribute(k_radix_hist1_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAUNCH(ctx, k_radix_hist1_tma, (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 2)), RH_NT + 32, smem, P, st, R.hist1,
+           R.hll);
+    return;
+  }
+  const int grid1 = (int)std::max<int64_t>(1, std::min<int64_t>(P.n_tiles, (int64_t)ctx->sm_count * 8));
+  LAUNCH(ctx, k_radix_hist1, grid1, R_NT, 0, P, R.hist1, R.hll);
 }
 
 // two operand values and the TMA scatter on both levels: the values travel as 16-byte pairs (RParams::pair12)
@@ -1440,8 +1477,7 @@ static bool run_radix(PlanNode& agg, const View& v, FusedPlan& fp, View* out) {
   R.nopf = getenv("QGPU_RADIX_NOPF") ? atoi(getenv("QGPU_RADIX_NOPF")) : 0;
   // ---- pass 0: level-1 histogram + HyperLogLog sketch ---------------------------------------------------------
   DBufP st = radix_state_block(ctx, R);
-  const int grid1 = (int)std::min<int64_t>(P.n_tiles, (int64_t)ctx->sm_count * 8);
-  LAUNCH(ctx, k_radix_hist1, grid1, R_NT, 0, P, R.hist1, R.hll);
+  radix_launch_hist1(ctx, P, R);
   LAUNCH(ctx, k_radix_scan1, 1, R_P1, 0, R.hist1, R.off1, R.cur1, R.tpre);
   std::vector<unsigned char> hst(RO_CUR1);
   ctx->d2h_sync(hst.data(), st->ptr, RO_CUR1);
@@ -2529,8 +2565,7 @@ int radix_exchange_sketch(PlanNode& root, const int64_t* global_stats, void** de
   ex->view = v;
   ex->st = radix_state_block(ctx, ex->R);
   const FParams& P = ex->P;
-  LAUNCH(ctx, k_radix_hist1, (int)std::max<int64_t>(1, std::min<int64_t>(P.n_tiles, (int64_t)ctx->sm_count * 8)), R_NT, 0, P, ex->R.hist1,
-         ex->R.hll);
+  radix_launch_hist1(ctx, P, ex->R);
   *dev_buf = ex->st->ptr;
   return 0;
 }

@@ -141,8 +141,13 @@ __device__ __forceinline__ uint32_t r_pass_code(const FParams& p, int64_t row0, 
     int64_t x[F_R];
     load_rows_g(gcol(p, p.keys[k].col, row0), p.keys[k].wk, tid, rows, x);
     const uint64_t base = (uint64_t)p.keys[k].base, mult = p.keys[k].mult;
+    if (mult == 1) {
 #pragma unroll
-    for (int j = 0; j < F_R; ++j) code[j] += ((uint64_t)x[j] - base) * mult;
+      for (int j = 0; j < F_R; ++j) code[j] += (uint64_t)x[j] - base;
+    } else {
+#pragma unroll
+      for (int j = 0; j < F_R; ++j) code[j] += ((uint64_t)x[j] - base) * mult;
+    }
   }
   return pass;
 }
@@ -439,8 +444,10 @@ constexpr int R2_NT = 1024;
 constexpr int R2_PT = R_T / R2_NT;  // tuples per thread and tile
 struct RStage {
   uint32_t n_in, stage_bytes;
-  uint32_t off[F_MAXC];    // LEVEL 1: staged column c of FParams::cols; LEVEL 2: tuple component c
+  uint32_t off[F_MAXC];    // LEVEL 1: staged column c of FParams::cols; LEVEL 2: tuple array c
   uint32_t bytes_per_row[F_MAXC];
+  uint32_t col_of[F_MAXC];  // LEVEL 1: copy lane -> column (off / bytes_per_row are indexed by the column)
+  uint32_t n_stages, pad;
 };
 static_assert(F_MAXC >= R_MAXCOMP, "RStage holds columns or components");
 
@@ -472,8 +479,13 @@ __device__ __forceinline__ void r2_codes(const FParams& p, const RStage& st, con
     int64_t x[R2_PT];
     lds_rows(stage + st.off[p.keys[k].col], p.keys[k].wk, idx, x);
     const uint64_t base = (uint64_t)p.keys[k].base, mult = p.keys[k].mult;
+    if (mult == 1) {  // the first key sits at bit 0: no 64-bit multiply
 #pragma unroll
-    for (int u = 0; u < R2_PT; ++u) code[u] += ((uint64_t)x[u] - base) * mult;
+      for (int u = 0; u < R2_PT; ++u) code[u] += (uint64_t)x[u] - base;
+    } else {
+#pragma unroll
+      for (int u = 0; u < R2_PT; ++u) code[u] += ((uint64_t)x[u] - base) * mult;
+    }
   }
 }
 
@@ -545,18 +557,19 @@ __global__ void __launch_bounds__(R2_NT, 1) k_radix_scatter_tma(const __grid_con
   // at + (base & 1)); the 16-byte pair array needs no such shift
   auto issue = [&](const R2Tile& d, int s) {
     if (warp != 0) return;
-    const int a = (LEVEL == 2 && lane < (int)st.n_in && st.bytes_per_row[lane] == 8) ? (int)(d.base & 1) : 0;
+    const int arr = lane < (int)st.n_in ? (LEVEL == 1 ? (int)st.col_of[lane] : lane) : 0;  // column / tuple array of this lane
+    const int a = (LEVEL == 2 && lane < (int)st.n_in && st.bytes_per_row[arr] == 8) ? (int)(d.base & 1) : 0;
     uint32_t bytes = 0;
-    if (lane < (int)st.n_in) bytes = ((uint32_t)(d.rows + a) * st.bytes_per_row[lane] + 15u) & ~15u;
+    if (lane < (int)st.n_in) bytes = ((uint32_t)(d.rows + a) * st.bytes_per_row[arr] + 15u) & ~15u;
     uint32_t total = bytes;
 #pragma unroll
     for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
     if (lane == 0) mbar_expect_tx(&full[s], total);
     __syncwarp();  // the expected byte count is registered before any copy can complete
     if (lane < (int)st.n_in) {
-      const unsigned char* src = LEVEL == 1 ? p.cols[lane].ptr + (size_t)d.base * st.bytes_per_row[lane]
-                                            : (const unsigned char*)r.tup_a[lane] + (size_t)(d.base - a) * st.bytes_per_row[lane];
-      bulk_g2s(stage0 + (size_t)s * st.stage_bytes + st.off[lane], src, bytes, &full[s], l2_policy);
+      const unsigned char* src = LEVEL == 1 ? p.cols[arr].ptr + (size_t)d.base * st.bytes_per_row[arr]
+                                            : (const unsigned char*)r.tup_a[arr] + (size_t)(d.base - a) * st.bytes_per_row[arr];
+      bulk_g2s(stage0 + (size_t)s * st.stage_bytes + st.off[arr], src, bytes, &full[s], l2_policy);
     }
   };
 
@@ -708,6 +721,8 @@ __global__ void __launch_bounds__(R2_NT, 1) k_radix_scatter_tma(const __grid_con
           const RComp& C = r.comp[c - 1];
           if (C.is_f64) {
             lds_rows(stage + st.off[C.f[0].col], C.f[0].wk, jdx, v);
+          } else if (C.n_factors == 1 && C.f[0].plain && C.coef == 1) {  // the bare column
+            lds_rows(stage + st.off[C.f[0].col], C.f[0].wk, jdx, v);
           } else {
 #pragma unroll
             for (int u = 0; u < R2_PT; ++u) v[u] = C.coef;
@@ -754,6 +769,108 @@ __global__ void __launch_bounds__(R2_NT, 1) k_radix_scatter_tma(const __grid_con
     }
     __syncthreads();  // stage s, src[] and bin[] are free again
   }
+}
+
+// Level-1 histogram + sketch as a warp-specialised TMA pipeline (the skeleton of fused_main): the register-staged
+// k_radix_hist1 issues a tile's loads and then waits for them (3.1 TB/s).  Here two CTAs per SM keep two to four 4096-row
+// stages of the key / predicate columns in flight each: warp 16 is the producer (lane l issues the bulk copy of staged
+// column l), warps 0..15 consume (two passes of 2048 rows per tile); full[s]: producer -> consumers (complete_tx bytes), empty[s]: one arrive per consumer warp.
+// No CTA-wide barrier per tile (a first version with one ran at 3.0 ms per 1 B rows, slower than the kernel it replaces).
+// dynamic shared memory: full[4] + empty[4] mbarriers (128 B) | n_stages stages | hist[R_P1] u32 | hll[R_HLL_M] u32
+constexpr int RH_NT = 512;  // consumer threads
+__global__ void __launch_bounds__(RH_NT + 32, 2) k_radix_hist1_tma(const __grid_constant__ FParams p, const __grid_constant__ RStage st,
+                                                                   unsigned int* __restrict__ hist1, unsigned int* __restrict__ hll) {
+  extern __shared__ __align__(128) unsigned char rsm[];
+  uint64_t* full = (uint64_t*)rsm;
+  uint64_t* empty = full + 4;
+  unsigned char* stage0 = rsm + 128;
+  unsigned int* sh = (unsigned int*)(stage0 + (size_t)st.n_stages * st.stage_bytes);
+  unsigned int* sl = sh + R_P1;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const bool producer = tid >= RH_NT;
+  const int NS = (int)st.n_stages;
+  const unsigned int n_tiles = (unsigned int)((p.n_rows + R_T - 1) / R_T);
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], RH_NT / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  for (int i = tid; i < R_P1; i += RH_NT + 32) sh[i] = 0;
+  for (int i = tid; i < R_HLL_M; i += RH_NT + 32) sl[i] = 0;
+  __syncthreads();
+  const unsigned int my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (producer) {
+    const uint64_t l2_policy = l2_evict_first_policy();
+    const int col = lane < (int)st.n_in ? (int)st.col_of[lane] : 0;
+#pragma unroll 1
+    for (unsigned int it = 0; it < my_tiles; ++it) {
+      const int s = (int)(it % (unsigned)NS);
+      const unsigned int use = it / (unsigned)NS;
+      if (use > 0) mbar_wait(&empty[s], (use - 1) & 1u);  // every consumer warp released the previous use
+      const int64_t base = (int64_t)(blockIdx.x + it * gridDim.x) * R_T;
+      const int rows = (int)min((int64_t)R_T, p.n_rows - base);
+      uint32_t bytes = 0;
+      if (lane < (int)st.n_in) bytes = ((uint32_t)rows * st.bytes_per_row[col] + 15u) & ~15u;
+      uint32_t total = bytes;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+      if (lane == 0) mbar_expect_tx(&full[s], total);
+      __syncwarp();  // the expected byte count is registered before any copy can complete
+      if (lane < (int)st.n_in)
+        bulk_g2s(stage0 + (size_t)s * st.stage_bytes + st.off[col], p.cols[col].ptr + (size_t)base * st.bytes_per_row[col], bytes, &full[s], l2_policy);
+    }
+  } else {
+#pragma unroll 1
+    for (unsigned int it = 0; it < my_tiles; ++it) {
+      const int s = (int)(it % (unsigned)NS);
+      mbar_wait(&full[s], (it / (unsigned)NS) & 1u);
+      const unsigned char* stage = stage0 + (size_t)s * st.stage_bytes;
+      const int rows = (int)min((int64_t)R_T, p.n_rows - (int64_t)(blockIdx.x + it * gridDim.x) * R_T);
+#pragma unroll 1
+      for (int half = 0; half < R_T / (R2_PT * RH_NT); ++half) {
+      int idx[R2_PT];
+      uint32_t pass = 0;
+#pragma unroll
+      for (int u = 0; u < R2_PT; ++u) {
+        idx[u] = (half * R2_PT + u) * RH_NT + tid;
+        if (idx[u] < rows) pass |= 1u << u;
+      }
+#pragma unroll 1
+      for (int k = 0; k < p.n_pred; ++k) {
+        int64_t x[R2_PT];
+        lds_rows(stage + st.off[p.pred[k].col], p.pred[k].wk, idx, x);
+        const uint64_t plo = (uint64_t)p.pred[k].lo, span = p.pred[k].span;
+#pragma unroll
+        for (int u = 0; u < R2_PT; ++u)
+          if (((uint64_t)x[u] - plo) > span) pass &= ~(1u << u);
+      }
+      uint64_t code[R2_PT];
+      r2_codes(p, st, stage, idx, code);
+      if (half == R_T / (R2_PT * RH_NT) - 1) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);  // this warp has read its rows of stage s
+      }
+#pragma unroll
+      for (int u = 0; u < R2_PT; ++u) {
+        if (!((pass >> u) & 1)) continue;
+        const uint64_t h = fmix64(code[u]);
+        atomicAdd(&sh[h >> (64 - R_B1)], 1u);
+        if ((h >> 52) & (R_HLL_SAMPLE - 1)) continue;  // the sketch's key-space sample (see k_radix_hist1)
+        const uint64_t w = (h >> R_HLL_BITS) & ((1ull << 40) - 1);
+        const unsigned rho = w ? (unsigned)(__clzll((long long)w) - 24 + 1) : 41u;
+        atomicMax(&sl[h & (R_HLL_M - 1)], rho);
+      }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < R_P1; i += RH_NT + 32)
+    if (sh[i]) atomicAdd(&hist1[i], sh[i]);
+  for (int i = tid; i < R_HLL_M; i += RH_NT + 32)
+    if (sl[i]) atomicMax(&hll[i], sl[i]);
 }
 
 // level-2 histogram: every CTA owns a contiguous range of tiles so that the shared histogram is flushed only when
