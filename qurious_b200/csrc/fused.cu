@@ -1441,7 +1441,9 @@ static bool radix_tail(PlanNode& agg, const View& v, FusedPlan& fp, const FParam
   agg.strategy = "fused_scan_agg[radix-partitioned: " + std::to_string(R_P1) + " x " + std::to_string(1 << b2) + " buckets, smem table " + std::to_string(cap) +
                  " slots / " + std::to_string(row_cap) + " rows, " + std::to_string(R.n_comp) + " x 8 B tuples, " +
                  std::to_string(P.n_cols) + " cols, " + std::to_string(P.n_pred) + " range preds, " + std::to_string(P.n_accs) +
-                 " accs, est " + std::to_string((int64_t)est) + " groups" + (direct ? ", result columns written by the final pass]" : "]");
+                 " accs, est " + std::to_string((int64_t)est) + " groups, scatter " + (radix_tma_stage(1, P, R, &st2) ? "tma" : "regs") + "/" +
+                 (radix_tma_stage(2, P, R2, &st2) ? "tma" : "regs") + (R.pair12 ? ", 16 B value pairs" : "") +
+                 (direct ? ", result columns written by the final pass]" : "]");
   if (direct) {
     View o;
     o.schema = agg.schema;
