@@ -42,6 +42,18 @@ constexpr int R_U = 8;                    // final pass: global loads in flight 
 static_assert(R_AGG_NT == 1024, "the final pass scans 32 warp totals with one warp");
 static_assert(R_NT == F_NT, "load_rows_g uses the F_NT row mapping");
 
+// The tuples carry fmix64(code), not the code: every later pass (level-2 histogram and scatter, final pass: digit, table
+// slot, probe step, key equality) works on the hash itself, and fmix64 is a bijection -- the final pass inverts it once per
+// GROUP when it decodes the key columns.
+__device__ __forceinline__ uint64_t r_unmix64(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0x9cb4b2f8129337dbULL;  // inverse of 0xc4ceb9fe1a85ec53 modulo 2^64
+  x ^= x >> 33;
+  x *= 0x4f74430c22a54005ULL;  // inverse of 0xff51afd7ed558ccd
+  x ^= x >> 33;
+  return x;
+}
+
 struct RComp {           // operand value = coef * prod(a_i + b_i * x_i) (int64, proven not to overflow) or raw f64 bits
   int32_t is_f64, n_factors;
   int64_t coef;
@@ -319,7 +331,8 @@ __global__ void __launch_bounds__(R_SNT, 2) k_radix_scatter(const __grid_constan
       for (int j = 0; j < F_R; ++j) {
         pr[s][j] = 0xffffffffu;
         if ((passm[s] >> j) & 1) {
-          const unsigned d = (unsigned)(fmix64(code[s][j]) >> shift) & (unsigned)(NB - 1);
+          if (LEVEL == 1) code[s][j] = fmix64(code[s][j]);  // from here on the tuple carries the hash
+          const unsigned d = (unsigned)(code[s][j] >> shift) & (unsigned)(NB - 1);
           pr[s][j] = (d << 16) | atomicAdd(&hist[d], 1u);
         }
       }
@@ -622,7 +635,8 @@ __global__ void __launch_bounds__(R2_NT, 1) k_radix_scatter_tma(const __grid_con
     for (int u = 0; u < R2_PT; ++u) {
       pr[u] = 0xffffffffu;
       if ((pass >> u) & 1) {
-        const unsigned d = (unsigned)(fmix64(code[u]) >> shift) & (unsigned)(NB - 1);
+        const uint64_t h = LEVEL == 1 ? fmix64(code[u]) : code[u];  // level-1 tuples already carry the hash
+        const unsigned d = (unsigned)(h >> shift) & (unsigned)(NB - 1);
         pr[u] = (d << 16) | atomicAdd(&hist[d], 1u);
       }
     }
@@ -716,7 +730,7 @@ __global__ void __launch_bounds__(R2_NT, 1) k_radix_scatter_tma(const __grid_con
           uint64_t cd[R2_PT];
           r2_codes(p, st, stage, jdx, cd);
 #pragma unroll
-          for (int u = 0; u < R2_PT; ++u) v[u] = (int64_t)cd[u];
+          for (int u = 0; u < R2_PT; ++u) v[u] = (int64_t)fmix64(cd[u]);
         } else {
           const RComp& C = r.comp[c - 1];
           if (C.is_f64) {
@@ -901,7 +915,7 @@ __global__ void __launch_bounds__(R_NT) k_radix_hist2(const __grid_constant__ RP
       cur_b1 = b1;
     }
     for (int i = tid; i < rows; i += R_NT) {
-      const uint64_t h = fmix64(r.tup_a[0][base + i]);
+      const uint64_t h = r.tup_a[0][base + i];
       atomicAdd(&sh[(unsigned)(h >> (64 - R_B1 - r.b2)) & (unsigned)(NB - 1)], 1u);
     }
   }
@@ -1041,7 +1055,7 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
         const unsigned long long code = c8[u];
         int slot = cap;  // the key whose code equals the EMPTY marker owns the extra slot
         if (code != F_EMPTY) {
-          const uint64_t h = fmix64(code);
+          const uint64_t h = code;  // the tuple's first word IS the hash (r_unmix64)
           slot = (int)(h & (uint64_t)(cap - 1));
           const int step = (int)((h >> 13) & (uint64_t)(cap - 1)) | 1;  // double hashing: odd step, no clustering tails
           int probes = 0;
@@ -1089,7 +1103,7 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
         int slot = cap;
         bool done = true, live = i < n;
         if (live && code != F_EMPTY) {
-          slot = (int)(fmix64(code) & (uint64_t)(cap - 1));
+          slot = (int)(code & (uint64_t)(cap - 1));
           unsigned long long cur = *(volatile unsigned long long*)&keys[slot];
           if (cur == F_EMPTY) cur = atomicCAS(&keys[slot], F_EMPTY, code);
           done = cur == code || cur == F_EMPTY;
@@ -1111,7 +1125,7 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
     const int nd = (int)n_defer;
     for (int j = tid; j < nd; j += R_AGG_NT) {
       const unsigned long long code = dcode[j];
-      const uint64_t h = fmix64(code);
+      const uint64_t h = code;
       const int step = (int)((h >> 13) & (uint64_t)(cap - 1)) | 1;
       int slot = ((int)(h & (uint64_t)(cap - 1)) + step) & (cap - 1);  // the home slot holds another key
       int probes = 1;
@@ -1234,7 +1248,7 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
       const unsigned c = cnt[sl];
       const unsigned long long* src = stage + (size_t)start[sl] * NV;
       const unsigned long long o = ob + g;
-      r_store_keys(rk, sl == cap ? F_EMPTY : keys[sl], o);
+      r_store_keys(rk, r_unmix64(sl == cap ? F_EMPTY : keys[sl]), o);
       if (!r.direct) r.out_cnt[o] = c;
       else
         for (int j = 0; j < r.n_cnt_dst; ++j) r.cnt_dst[j][o] = c;
