@@ -436,8 +436,12 @@ def kernel_bytes(kernel, q, per_table, driving, rows_local, groups_local):
         return per_table.get("orders" if "FM_EMIT" in kernel else driving)
     if q == "groupby":
         # tuples are 3 x 8 B; groups leave as 6 x 8 B
-        return {"k_radix_agg": 24 * rows_local + 48 * groups_local, "k_radix_scatter<1>": 48 * rows_local,
-                "k_radix_scatter<2>": 48 * rows_local, "k_radix_hist1": 8 * rows_local, "k_radix_hist2": 8 * rows_local}.get(kernel)
+        # (kernel names carry template arguments and the _tma suffix of the pipelined variants: match on the stem)
+        for stem, b in (("k_radix_agg", 24 * rows_local + 48 * groups_local), ("k_radix_scatter", 48 * rows_local),
+                        ("k_radix_hist1", 8 * rows_local), ("k_radix_hist2", 8 * rows_local)):
+            if kernel.startswith(stem):
+                return b
+        return None
     return None
 
 

@@ -1388,7 +1388,7 @@ static bool radix_tail(PlanNode& agg, const View& v, FusedPlan& fp, const FParam
   RParams R2 = R;
   R2.world = 1;  // level 2 and the final pass are local
   LAUNCH(ctx, k_radix_hist2, (int)std::min<int64_t>(std::max<int64_t>(n_tiles2, 1), (int64_t)ctx->sm_count * 8), R_NT, 0, R2);
-  LAUNCH(ctx, k_radix_scan2, 1, 1024, 0, R2.hist2, (int)n_buckets, R2.off2, R2.cur2);
+  LAUNCH(ctx, k_radix_scan2, R_P1, 1 << R_MAXB2, 0, R2.hist2, b2, R2.off1, R2.off2, R2.cur2);
   RStage st2;
   if (radix_tma_stage(2, P, R2, &st2)) {
     const size_t smem = radix_tma_smem(st2);

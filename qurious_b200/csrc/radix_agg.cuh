@@ -510,7 +510,7 @@ struct R2Tile {
 template <int LEVEL>
 __global__ void __launch_bounds__(R2_NT, 1) k_radix_scatter_tma(const __grid_constant__ FParams p, const __grid_constant__ RParams r,
                                                                 const __grid_constant__ RStage st) {
-  extern __shared__ __align__(128) unsigned char rsm[];
+  extern __shared__ __align__(16) unsigned char rsm[];  // (bulk copies and mbarriers need 16 B / 8 B)
   uint64_t* full = (uint64_t*)rsm;
   unsigned char* stage0 = rsm + 128;
   unsigned short* srcidx = (unsigned short*)(stage0 + 2 * (size_t)st.stage_bytes);
@@ -794,7 +794,7 @@ __global__ void __launch_bounds__(R2_NT, 1) k_radix_scatter_tma(const __grid_con
 constexpr int RH_NT = 512;  // consumer threads
 __global__ void __launch_bounds__(RH_NT + 32, 2) k_radix_hist1_tma(const __grid_constant__ FParams p, const __grid_constant__ RStage st,
                                                                    unsigned int* __restrict__ hist1, unsigned int* __restrict__ hll) {
-  extern __shared__ __align__(128) unsigned char rsm[];
+  extern __shared__ __align__(16) unsigned char rsm[];  // (bulk copies and mbarriers need 16 B / 8 B)
   uint64_t* full = (uint64_t*)rsm;
   uint64_t* empty = full + 4;
   unsigned char* stage0 = rsm + 128;
@@ -925,30 +925,33 @@ __global__ void __launch_bounds__(R_NT) k_radix_hist2(const __grid_constant__ RP
       if (sh[i]) atomicAdd(&r.hist2[(cur_b1 << r.b2) + i], sh[i]);
 }
 
-// exclusive scan of n counters by ONE CTA of 1024 threads (n <= 131072): off[0..n], cur[i] = off[i]
-__global__ void __launch_bounds__(1024) k_radix_scan2(const unsigned int* __restrict__ hist, int n, unsigned long long* __restrict__ off,
-                                                      unsigned long long* __restrict__ cur) {
-  __shared__ unsigned long long part[1024];
-  const int t = threadIdx.x;
-  const int per = (n + 1023) / 1024;
-  const int i0 = t * per, i1 = min(n, i0 + per);
-  unsigned long long s = 0;
-  for (int i = i0; i < i1; ++i) s += hist[i];
-  part[t] = s;
+// offsets of the final buckets: the 1 << b2 counters of level-1 bucket b sum to that bucket's size, so bucket b's final
+// buckets start at off1[b] and every level-1 bucket is scanned independently -- one CTA of 512 threads each (a single CTA
+// scanning all 131072 counters took 0.34 ms per step)
+__global__ void __launch_bounds__(1 << R_MAXB2) k_radix_scan2(const unsigned int* __restrict__ hist, int b2, const unsigned long long* __restrict__ off1,
+                                                              unsigned long long* __restrict__ off, unsigned long long* __restrict__ cur) {
+  __shared__ unsigned int warp_tot[(1 << R_MAXB2) / 32];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, b = blockIdx.x;
+  const int NB = 1 << b2;
+  const unsigned int h = t < NB ? hist[((size_t)b << b2) + t] : 0u;
+  unsigned int incl = h;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned int o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
   __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {
-    const unsigned long long x = t >= d ? part[t - d] : 0;
-    __syncthreads();
-    part[t] += x;
-    __syncthreads();
+  unsigned int wbase = 0;
+#pragma unroll
+  for (int w = 0; w < (1 << R_MAXB2) / 32; ++w)
+    if (w < warp) wbase += warp_tot[w];
+  if (t < NB) {
+    const unsigned long long o = off1[b] + (unsigned long long)(wbase + incl - h);
+    off[((size_t)b << b2) + t] = o;
+    cur[((size_t)b << b2) + t] = o;
   }
-  unsigned long long run = part[t] - s;
-  for (int i = i0; i < i1; ++i) {
-    off[i] = run;
-    cur[i] = run;
-    run += hist[i];
-  }
-  if (t == 1023) off[n] = part[1023];
+  if (b == (int)gridDim.x - 1 && t == 0) off[(size_t)gridDim.x << b2] = off1[gridDim.x];
 }
 
 struct RKeys {
