@@ -7,7 +7,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 txt = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "qurious_b200", "libqgpu.so")], capture_output=True, text=True).stdout
 out = ["# cuobjdump -sass qurious_b200/libqgpu.so (sm_100a), excerpt: the 1-D TMA bulk copies (UBLKCP.S.G = cp.async.bulk.shared::cluster.global",
-       "# .mbarrier::complete_tx::bytes) and the mbarrier operations (SYNCS.*) of the fused scan kernels: one line per distinct mnemonic.",
+       "# .mbarrier::complete_tx::bytes) and the mbarrier operations (SYNCS.*) of the fused scan kernels and of the radix group-by kernels (k_radix_scatter_tma, k_radix_hist1_tma): one line per distinct mnemonic.",
        "# No UTMALDG (tensor-map TMA) and no UTC*MMA anywhere in the library: the path moves 1-D column tiles and contracts nothing (DESIGN 3).",
        ""]
 n_tensor = len(re.findall(r"UTMALDG|UTCMMA|UTCHMMA|UTCQMMA", txt))
