@@ -5,20 +5,22 @@
 // the table outgrows L2; here the rows are instead streamed twice through a partitioning pass until every bucket
 // holds few enough groups for a SHARED-MEMORY table, so that all random accesses stay on chip:
 //
-//   k_radix_hist1    scan (predicate, packed key) -> 256-bin histogram of the hash's top byte + HyperLogLog sketch
+//   k_radix_hist1[_tma]  scan (predicate, packed key) -> 256-bin histogram of the hash's top byte + HyperLogLog sketch
 //                    (the group-count estimate picks level-2 fan-out, table capacity and output sizes)
 //   k_radix_scan1    bucket offsets / cursors / bucket-aligned tile list
-//   k_radix_scatter<1>  scan again, materialise tuples (code, operand values) and scatter them into the 256
-//                    level-1 buckets: tile of 4096 tuples -> shared-memory counting sort (unordered ranks from
-//                    shared atomics) -> one global reservation per (tile, bucket) -> coalesced run write-out
+//   k_radix_scatter[_tma]<1>  scan again, materialise tuples (hash of the packed key, operand values) and scatter them
+//                    into the 256 level-1 buckets: tile of 4096 tuples -> shared-memory counting sort (unordered ranks
+//                    from shared atomics) -> one global reservation per (tile, bucket) -> coalesced run write-out
 //   k_radix_hist2    per level-1 bucket: histogram of the next b2 hash bits
 //   k_radix_scan2    offsets of the 256 << b2 final buckets
-//   k_radix_scatter<2>  same scatter, tuples -> final buckets
-//   k_radix_agg      one CTA per final bucket: rows counting-sorted by group in shared memory (key table claimed
+//   k_radix_scatter[_tma]<2>  same scatter, tuples -> final buckets
+//   k_radix_agg<NV>  one CTA per final bucket: rows counting-sorted by group in shared memory (key table claimed
 //                    with 64-bit CAS, ranks from native 32-bit shared atomics), one thread reduces each group
 //                    sequentially in registers and writes it straight to the group arrays
-//                    (key columns decoded from the packed code; when every aggregate is a copy / sign extension / f64 mean
-//                    of an accumulator the result columns themselves -- no finalise pass)
+//                    (key columns decoded from the inverted hash word; when every aggregate is a copy / sign extension /
+//                    f64 mean of an accumulator the result columns themselves -- no finalise pass)
+// The _tma kernels are TMA pipelines (input tiles staged in shared memory by 1-D bulk copies one tile ahead); they run
+// whenever their stages fit the shared memory (tuples of <= 2 operand values at level 2), the register-staged ones otherwise.
 //
 // Semantics are those of FM_HASH (hash.rs:45-107,138-170 with grouping by key equality);
 // output order is the bucket order (the reference's order is unspecified, quirk Q2).  Anything that does not fit
