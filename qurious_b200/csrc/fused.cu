@@ -1400,10 +1400,17 @@ static bool radix_tail(PlanNode& agg, const View& v, FusedPlan& fp, const FParam
   }
   const int ag_grid = (int)std::min<int64_t>(n_buckets, (int64_t)ctx->sm_count);
   const size_t ag_smem = (size_t)(cap + 1) * 18 + (size_t)row_cap * row_bytes + 64;
+  const char* agf = getenv("QGPU_RADIX_AGG");  // "sort": the sorting form of the final pass
+  const bool list_form = !(agf && strcmp(agf, "sort") == 0);
 #define QGPU_RADIX_AGG(NV)                                                                                             \
   case NV:                                                                                                             \
-    CUDA_CHECK(cudaFuncSetAttribute(k_radix_agg<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ag_smem));      \
-    LAUNCH(ctx, k_radix_agg<NV>, ag_grid, R_AGG_NT, ag_smem, R2, rk);                                                  \
+    if (list_form) {                                                                                                   \
+      CUDA_CHECK(cudaFuncSetAttribute(k_radix_agg_list<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ag_smem)); \
+      LAUNCH(ctx, k_radix_agg_list<NV>, ag_grid, R_AGG_NT, ag_smem, R2, rk);                                           \
+    } else {                                                                                                           \
+      CUDA_CHECK(cudaFuncSetAttribute(k_radix_agg<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ag_smem));    \
+      LAUNCH(ctx, k_radix_agg<NV>, ag_grid, R_AGG_NT, ag_smem, R2, rk);                                                \
+    }                                                                                                                  \
     break;
   switch (R.n_comp - 1) {  // operand values per tuple: unrolled in the kernel
     QGPU_RADIX_AGG(0)

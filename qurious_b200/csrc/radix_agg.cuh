@@ -1299,6 +1299,287 @@ __global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg(const __grid_constant
   }
 }
 
+// Final pass, list form (the default; QGPU_RADIX_AGG=sort selects the form above).  The sorting form reads a bucket three
+// times with exposed latency (codes, then the operand values twice over: into the staging area at start[slot] + rank, then
+// out of it) around a scan of the slot counts.  Here the operand values of the WHOLE bucket are brought into shared memory
+// by 1-D bulk copies (cp.async.bulk -> mbarrier) issued before the first row is looked at -- they stay in arrival order --
+// and phase A threads every row onto a per-slot linked list instead of ranking it: prev = atomicExch(&head[slot], row)
+// (native 32-bit shared atomic), next[row] = prev.  No start[] scan, no second pass over the values; phase R walks a
+// group's list (a dependent 4-byte LDS per row) and reads the values where the copy put them.
+//   0  init keys / heads; warp 0 issues the bulk copies of the bucket's value arrays
+//   A  (two passes like the sorting form) slot of every row, row pushed onto the slot's list; the deferred queue lives in
+//      whatever the copies leave free of the staging area -- rows that find it full walk their chain on the spot
+//   S  occupied slots -> dense list + output positions; wait for the copies
+//   R  thread-per-group: walk the list, reduce, write the group
+// dynamic shared memory: stage (value arrays of this bucket, packed) | keys[C1] u64 | head[C1] u32 | next[row_cap] u32 |
+//                        occ[C1] u16   -- within the sorting form's size
+constexpr unsigned R_NIL = 0xffffffffu;
+template <int NV>
+__global__ void __launch_bounds__(R_AGG_NT, 1) k_radix_agg_list(const __grid_constant__ RParams r, const __grid_constant__ RKeys rk) {
+  extern __shared__ __align__(16) unsigned char rsm[];
+  const int cap = r.cap, C1 = cap + 1, RC = r.row_cap;
+  const size_t stage_bytes = (size_t)NV * RC * 8;
+  unsigned char* stage = rsm;
+  unsigned long long* keys = (unsigned long long*)(rsm + stage_bytes);
+  unsigned int* head = (unsigned int*)(keys + C1);
+  unsigned int* next = head + C1;
+  unsigned short* occ = (unsigned short*)(next + RC);
+  __shared__ __align__(8) uint64_t full;
+  __shared__ unsigned int warp_tot[R_AGG_NT / 32];
+  __shared__ unsigned long long out_base;
+  __shared__ unsigned int n_occ_sh;
+  __shared__ int bucket_overflow;
+  __shared__ unsigned int n_defer;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_buckets = R_P1 << r.b2;
+  const int per = (C1 + R_AGG_NT - 1) / R_AGG_NT;
+  const int s0 = min(C1, tid * per), s1 = min(C1, s0 + per);
+  const bool pairs = NV == 2 && r.pair12;
+  const int n_arr = NV == 0 ? 0 : (pairs ? 1 : NV);  // value arrays to copy
+  if (tid == 0) {
+    mbar_init(&full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const uint64_t l2_policy = l2_evict_first_policy();
+  uint32_t phase = 0;
+
+  for (int b = blockIdx.x; b < n_buckets; b += gridDim.x) {
+    const int64_t lo = (int64_t)r.off2[b];
+    const int64_t n64 = (int64_t)r.off2[b + 1] - lo;
+    if (n64 == 0) continue;  // uniform for the CTA
+    if (n64 + 2 > RC) {      // skewed bucket: more rows than the staging area holds (+ the alignment shift of its copies)
+      if (tid == 0) *r.overflow = 3;
+      continue;
+    }
+    const int n = (int)n64;
+    // value arrays of 8-byte elements are only 8 B aligned: copied from the 16 B boundary below (read at + sh)
+    const int sh = pairs ? 0 : (int)(lo & 1);
+    const uint32_t arr_bytes = pairs ? (uint32_t)n * 16u : (((uint32_t)(n + sh) * 8u + 15u) & ~15u);
+    const size_t used = (size_t)n_arr * arr_bytes;
+    // ---- 0: table init; the bucket's values start moving (the barrier that ended the previous bucket ordered its reads of
+    //         the staging area before these writes)
+    if (warp == 0 && n_arr > 0) {
+      if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&full, (uint32_t)used);
+      }
+      __syncwarp();
+      if (lane < n_arr) {
+        const unsigned char* src = pairs ? (const unsigned char*)r.tup_b[1] + (size_t)lo * 16
+                                         : (const unsigned char*)(r.tup_b[lane + 1] + (lo - sh));
+        bulk_g2s(stage + (size_t)lane * arr_bytes, src, arr_bytes, &full, l2_policy);
+      }
+    }
+    // the next bucket of this CTA: pull its codes towards L2 while this one is processed
+    if (b + (int)gridDim.x < n_buckets && tid == 32 && !(r.nopf & 4)) {
+      const int64_t nlo = (int64_t)r.off2[b + gridDim.x];
+      const int64_t nn = min((int64_t)r.off2[b + gridDim.x + 1] - nlo, (int64_t)RC);
+      const uintptr_t a0 = ((uintptr_t)(r.tup_b[0] + nlo) + 15) & ~(uintptr_t)15;
+      const uintptr_t a1 = (uintptr_t)(r.tup_b[0] + nlo + nn) & ~(uintptr_t)15;
+      if (a1 > a0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((uint32_t)(a1 - a0)) : "memory");
+    }
+    for (int i = tid; i < C1; i += R_AGG_NT) {
+      keys[i] = F_EMPTY;
+      head[i] = R_NIL;
+    }
+    if (tid == 0) {
+      bucket_overflow = 0;
+      n_defer = 0;
+    }
+    // deferred queue (hash word + row) in what the copies leave free of the staging area
+    unsigned long long* dcode = (unsigned long long*)(stage + ((used + 15) & ~(size_t)15));
+    const int dq_cap = (int)((stage_bytes - ((used + 15) & ~(size_t)15)) / 12);
+    unsigned int* drow = (unsigned int*)(dcode + dq_cap);
+    __syncthreads();
+    // ---- A, pass 1: one convergent probe per row; settled rows go onto their slot's list -------------------------------------
+    for (int i0 = 0; i0 < n; i0 += R_U * R_AGG_NT) {
+      unsigned long long c8[R_U];
+#pragma unroll
+      for (int u = 0; u < R_U; ++u) {
+        const int i = i0 + u * R_AGG_NT + tid;
+        c8[u] = i < n ? __ldcs(&r.tup_b[0][lo + i]) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < R_U; ++u) {
+        const int i = i0 + u * R_AGG_NT + tid;
+        const unsigned long long code = c8[u];
+        int slot = cap;  // the key whose hash word equals the EMPTY marker owns the extra slot
+        bool done = true, live = i < n;
+        if (live && code != F_EMPTY) {
+          slot = (int)(code & (uint64_t)(cap - 1));
+          unsigned long long cur = *(volatile unsigned long long*)&keys[slot];
+          if (cur == F_EMPTY) cur = atomicCAS(&keys[slot], F_EMPTY, code);
+          done = cur == code || cur == F_EMPTY;
+        }
+        if (live && done) next[i] = atomicExch(&head[slot], (unsigned)i);
+        const unsigned dm = __ballot_sync(0xffffffffu, live && !done);
+        if (dm) {
+          unsigned at = 0;
+          if (lane == 0) at = atomicAdd(&n_defer, (unsigned)__popc(dm));
+          at = __shfl_sync(0xffffffffu, at, 0) + __popc(dm & ((1u << lane) - 1u));
+          if (live && !done) {
+            if ((int)at < dq_cap) {
+              dcode[at] = code;
+              drow[at] = (unsigned)i;
+            } else {  // no room in the queue (a bucket that nearly fills the staging area): walk the chain here
+              const int step = (int)((code >> 13) & (uint64_t)(cap - 1)) | 1;
+              int probes = 1;
+              slot = (slot + step) & (cap - 1);
+              while (true) {
+                unsigned long long cur = *(volatile unsigned long long*)&keys[slot];
+                if (cur == code) break;
+                if (cur == F_EMPTY) {
+                  cur = atomicCAS(&keys[slot], F_EMPTY, code);
+                  if (cur == F_EMPTY || cur == code) break;
+                }
+                slot = (slot + step) & (cap - 1);
+                if (++probes >= cap) {
+                  slot = -1;
+                  break;
+                }
+              }
+              if (slot < 0) bucket_overflow = 1;
+              else next[i] = atomicExch(&head[slot], (unsigned)i);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- A, pass 2: the queued rows walk their probe chains with dense lanes ---------------------------------------------------
+    const int nd = min((int)n_defer, dq_cap);
+    for (int j = tid; j < nd; j += R_AGG_NT) {
+      const unsigned long long code = dcode[j];
+      const int step = (int)((code >> 13) & (uint64_t)(cap - 1)) | 1;
+      int slot = ((int)(code & (uint64_t)(cap - 1)) + step) & (cap - 1);  // the home slot holds another key
+      int probes = 1;
+      while (true) {
+        unsigned long long cur = *(volatile unsigned long long*)&keys[slot];
+        if (cur == code) break;
+        if (cur == F_EMPTY) {
+          cur = atomicCAS(&keys[slot], F_EMPTY, code);
+          if (cur == F_EMPTY || cur == code) break;
+        }
+        slot = (slot + step) & (cap - 1);
+        if (++probes >= cap) {
+          slot = -1;
+          break;
+        }
+      }
+      if (slot < 0) {
+        bucket_overflow = 1;
+        continue;
+      }
+      const unsigned i = drow[j];
+      next[i] = atomicExch(&head[slot], i);
+    }
+    __syncthreads();
+    if (n_arr > 0) {
+      mbar_wait(&full, phase);  // the values have landed (long ago: phase A is most of a bucket's time)
+      phase ^= 1u;
+    }
+    if (bucket_overflow) {
+      if (tid == 0) *r.overflow = 1;
+      __syncthreads();
+      continue;
+    }
+    // ---- S: occupied slots -> dense list + output positions ---------------------------------------------------------------------
+    unsigned mine = 0;
+    for (int sl = s0; sl < s1; ++sl) mine += head[sl] != R_NIL ? 1u : 0u;
+    unsigned incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned wt = warp_tot[lane];
+      unsigned wi = wt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, wi, d);
+        if (lane >= d) wi += o;
+      }
+      warp_tot[lane] = wi - wt;
+      if (lane == 31) {
+        n_occ_sh = wi;
+        out_base = atomicAdd(r.n_out, (unsigned long long)wi);
+      }
+    }
+    __syncthreads();
+    {
+      unsigned g = warp_tot[warp] + incl - mine;
+      for (int sl = s0; sl < s1; ++sl)
+        if (head[sl] != R_NIL) occ[g++] = (unsigned short)sl;
+    }
+    const unsigned n_occ = n_occ_sh;
+    const unsigned long long ob = out_base;
+    if (ob + n_occ > (unsigned long long)r.out_cap) {  // uniform
+      if (tid == 0) *r.overflow = 2;
+      __syncthreads();
+      continue;
+    }
+    __syncthreads();
+    // ---- R: one thread per GROUP walks its list and reduces the rows where the copies put them ------------------------------------
+    int msk[NV > 0 ? NV : 1];
+#pragma unroll
+    for (int cc = 0; cc < NV; ++cc) msk[cc] = r.cmask[cc];
+    for (unsigned g = tid; g < n_occ; g += R_AGG_NT) {
+      const int sl = occ[g];
+      const unsigned long long o = ob + g;
+      long long sm[NV > 0 ? NV : 1], mn[NV > 0 ? NV : 1], mx[NV > 0 ? NV : 1];
+      double fs[NV > 0 ? NV : 1];
+#pragma unroll
+      for (int cc = 0; cc < NV; ++cc) {
+        sm[cc] = 0;
+        mn[cc] = INT64_MAX;
+        mx[cc] = INT64_MIN;
+        fs[cc] = 0.0;
+      }
+      unsigned c = 0;
+      for (unsigned i = head[sl]; i != R_NIL; i = next[i]) {
+        long long v[NV > 0 ? NV : 1];
+        if (pairs) {
+          const ulonglong2 q = ((const ulonglong2*)stage)[i];
+          v[0] = (long long)q.x;
+          v[NV > 1 ? 1 : 0] = (long long)q.y;
+        } else {
+#pragma unroll
+          for (int cc = 0; cc < NV; ++cc) v[cc] = (long long)((const unsigned long long*)(stage + (size_t)cc * arr_bytes))[i + sh];
+        }
+#pragma unroll
+        for (int cc = 0; cc < NV; ++cc) {
+          if (msk[cc] & 8) {
+            fs[cc] += __longlong_as_double(v[cc]);
+          } else {
+            sm[cc] += v[cc];
+            mn[cc] = min(mn[cc], v[cc]);
+            mx[cc] = max(mx[cc], v[cc]);
+          }
+        }
+        ++c;
+      }
+      r_store_keys(rk, r_unmix64(sl == cap ? F_EMPTY : keys[sl]), o);
+      if (!r.direct) r.out_cnt[o] = c;
+      else
+        for (int j = 0; j < r.n_cnt_dst; ++j) r.cnt_dst[j][o] = c;
+#pragma unroll
+      for (int cc = 0; cc < NV; ++cc) {
+        const int m = msk[cc];
+        if (m & 1) r_emit(r, r.acc_at[cc][0], o, (unsigned long long)sm[cc], c);
+        if (m & 2) r_emit(r, r.acc_at[cc][1], o, (unsigned long long)mn[cc], c);
+        if (m & 4) r_emit(r, r.acc_at[cc][2], o, (unsigned long long)mx[cc], c);
+        if (m & 8) r_emit(r, r.acc_at[cc][3], o, (unsigned long long)__double_as_longlong(fs[cc]), c);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // (A second form of the final pass -- shared memory holding only the group table, every row accumulating straight into
 // its slot -- was built and measured in round 2 and removed: 64-bit shared-memory atomics are CAS loops in SASS
 // (ATOMS.CAST.SPIN.64), one per accumulator and row made it 44 ms per 1 B rows against 17 ms for the sorting form; with a
