@@ -14,9 +14,10 @@
 //   k_radix_hist2    per level-1 bucket: histogram of the next b2 hash bits
 //   k_radix_scan2    offsets of the 256 << b2 final buckets
 //   k_radix_scatter[_tma]<2>  same scatter, tuples -> final buckets
-//   k_radix_agg<NV>  one CTA per final bucket: rows counting-sorted by group in shared memory (key table claimed
-//                    with 64-bit CAS, ranks from native 32-bit shared atomics), one thread reduces each group
-//                    sequentially in registers and writes it straight to the group arrays
+//   k_radix_agg_list<NV>  one CTA per final bucket: the bucket's operand values bulk-copied into shared memory, key table
+//                    claimed with 64-bit CAS, every row pushed onto its slot's linked list (native 32-bit shared
+//                    atomicExch), one thread walks each group's list, reduces it in registers and writes the group
+//                    (k_radix_agg<NV>, QGPU_RADIX_AGG=sort: the earlier form that ranks, scans and re-stages the rows)
 //                    (key columns decoded from the inverted hash word; when every aggregate is a copy / sign extension /
 //                    f64 mean of an accumulator the result columns themselves -- no finalise pass)
 // The _tma kernels are TMA pipelines (input tiles staged in shared memory by 1-D bulk copies one tile ahead); they run
