@@ -176,3 +176,15 @@ def test_radix_register_staged_scatter_still_matches(gpu_ctx, monkeypatch):
     got = rows_of(p.execute(gpu_ctx))
     assert "scatter regs/regs" in p.last_strategy(), p.last_strategy()
     check_rows("radix regs", got, rows_of(qref.execute(narrow_plan(t, "vf"))), ordered=False)
+
+
+@pytest.mark.parametrize("shape", ["vf", "v", "count"])
+def test_radix_sorting_form_of_the_final_pass_still_matches(gpu_ctx, monkeypatch, shape):
+    """QGPU_RADIX_AGG=sort: the final pass that ranks, scans and re-stages the rows (the list form is the default)."""
+    monkeypatch.setenv("QGPU_RADIX", "force")
+    monkeypatch.setenv("QGPU_RADIX_AGG", "sort")
+    t = narrow_table(120_000, 14_000, seed=29)
+    p = narrow_plan(t, shape)
+    got = rows_of(p.execute(gpu_ctx))
+    assert "radix-partitioned" in p.last_strategy(), p.last_strategy()
+    check_rows(f"radix sort form {shape}", got, rows_of(qref.execute(narrow_plan(t, shape))), ordered=False)
